@@ -1,0 +1,199 @@
+/*
+ * tgb200.h -- C ABI of the B200-native path_tracer hot path (libtgb200.so).
+ *
+ * This is the drop-in boundary that sits UNDER Tungsten's C++ `Integrator` interface
+ * (reference: src/core/integrators/Integrator.hpp:16-63).  The reference has no C ABI; an in-tree
+ * adapter class (`B200PathTraceIntegrator`) forwards
+ *     prepareForRender(TraceableScene&, seed)  -> tgb200_create()
+ *     startRender()/renderTile()               -> tgb200_render_tiles()
+ *     abortRender()                            -> tgb200_abort()
+ *     teardownAfterRender()                    -> tgb200_destroy()
+ * and converts non-zero return codes into std::runtime_error (reference: src/core/Debug.hpp:26-33).
+ *
+ * Conventions: plain pointers and sizes only; the caller owns every host buffer passed in (they may
+ * be freed as soon as the call returns); the context owns all device memory; no call throws;
+ * one host thread drives a context at a time (tgb200_abort may be called from any thread).
+ * All geometry is WORLD SPACE, i.e. what the reference holds after `prepareForRender()`
+ * (TriangleMesh::_tfVerts, Quad::_base/_edge0/_edge1, Cube::_pos/_rot/_scale), fp32.
+ */
+#ifndef TGB200_H_
+#define TGB200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TGB200_ABI_VERSION 1
+
+/* ---- return codes -------------------------------------------------------------------------- */
+enum {
+    TGB_OK               =  0,
+    TGB_ERR_INVALID      = -1,   /* bad argument / malformed scene description                   */
+    TGB_ERR_UNSUPPORTED  = -2,   /* scene uses a feature outside the hot path    */
+    TGB_ERR_NO_DEVICE    = -3,   /* no CUDA device / wrong architecture: there is NO CPU fallback */
+    TGB_ERR_CUDA         = -4,   /* CUDA runtime error, text in tgb200_last_error()               */
+    TGB_ERR_ABORTED      = -5,   /* tgb200_abort() was called during the render                   */
+    TGB_ERR_OOM          = -6
+};
+
+/* ---- textures (reference: src/core/textures/{ConstantTexture,CheckerTexture,BitmapTexture}) - */
+enum { TGB_TEX_CONSTANT = 0, TGB_TEX_CHECKER = 1, TGB_TEX_BITMAP = 2 };
+
+typedef struct tgb_texture {
+    uint32_t type;
+    float    value[3];      /* CONSTANT: value;  CHECKER: "on" colour                              */
+    float    value2[3];     /* CHECKER: "off" colour                                               */
+    uint32_t res_u, res_v;  /* CHECKER: res_u/res_v;  BITMAP: width/height                         */
+    uint32_t flags;         /* BITMAP: bit0 linear filter, bit1 clamp (else repeat)                */
+    const float *texels;    /* BITMAP: res_u*res_v RGB fp32, row-major, top row first (host ptr)   */
+} tgb_texture;
+
+/* ---- BSDFs (reference: src/core/bsdfs/; the lobes north_star names + Null) ------------- */
+enum {
+    TGB_BSDF_NULL = 0, TGB_BSDF_LAMBERT = 1, TGB_BSDF_ROUGH_CONDUCTOR = 2,
+    TGB_BSDF_ROUGH_DIELECTRIC = 3, TGB_BSDF_PLASTIC = 4, TGB_BSDF_ROUGH_PLASTIC = 5,
+    TGB_BSDF_SMOOTH_COAT = 6, TGB_BSDF_CONDUCTOR = 7, TGB_BSDF_DIELECTRIC = 8, TGB_BSDF_MIRROR = 9
+};
+enum { TGB_DIST_BECKMANN = 0, TGB_DIST_PHONG = 1, TGB_DIST_GGX = 2 };
+
+typedef struct tgb_bsdf {
+    uint32_t type;
+    int32_t  albedo_tex;        /* index into textures[]                                           */
+    uint32_t distribution;      /* TGB_DIST_* (rough lobes)                                        */
+    int32_t  roughness_tex;     /* index into textures[] (rough lobes), -1 if unused               */
+    float    ior;               /* dielectric / plastic / coat                                     */
+    float    eta[3], k[3];      /* conductor complex IOR (RGB)                                     */
+    float    thickness;         /* plastic / coat                                                  */
+    float    sigma_a[3];        /* plastic / coat absorption                                       */
+    int32_t  substrate;         /* SMOOTH_COAT: index of the substrate bsdf, else -1               */
+    uint32_t enable_refraction; /* (rough) dielectric "enable_refraction"                          */
+} tgb_bsdf;
+
+/* ---- geometry ------------------------------------------------------------------------------- */
+/* 32 B / 16 B: identical to the reference's Vertex / TriangleI and to the .wo3 on-disk layout
+ * (src/core/primitives/Vertex.hpp:12-13, Triangle.hpp:14-20, io/MeshIO.cpp:19-25).               */
+typedef struct tgb_vertex   { float pos[3]; float normal[3]; float uv[2]; } tgb_vertex;
+typedef struct tgb_triangle { uint32_t v0, v1, v2; int32_t material; } tgb_triangle;
+
+enum { TGB_PRIM_MESH = 0, TGB_PRIM_QUAD = 1, TGB_PRIM_CUBE = 2, TGB_PRIM_INFINITE_SPHERE = 3 };
+
+/* One entry per scene primitive, in the reference's Scene::primitives() order.                    */
+typedef struct tgb_primitive {
+    uint32_t type;
+    int32_t  emission_tex;      /* -1 = not emissive (Primitive::_emission)                        */
+    /* MESH: world-space vertices/triangles; triangle.material indexes bsdfs[bsdf_first + m]        */
+    const tgb_vertex   *verts;  uint32_t n_verts;
+    const tgb_triangle *tris;   uint32_t n_tris;
+    uint32_t smooth;            /* TriangleMesh::_smoothed                                          */
+    uint32_t bsdf_first, bsdf_count;   /* range in bsdf_slots[] (QUAD/CUBE: exactly one)            */
+    /* QUAD: Quad::_base/_edge0/_edge1 as prepared (Quad.cpp:298-305)                               */
+    float base[3], edge0[3], edge1[3];
+    /* CUBE: Cube::_pos, _rot (row-major 3x3), _scale as prepared (Cube.cpp:351-355)                */
+    float pos[3], rot[9], scale[3];
+    /* INFINITE_SPHERE: rotation (row-major 3x3, InfiniteSphere::_rotTransform), sample flag        */
+    uint32_t do_sample;
+} tgb_primitive;
+
+/* ---- camera (reference: cameras/PinholeCamera.cpp:28-35,70-86; Camera.cpp:44-68) ------------ */
+enum { TGB_FILTER_DIRAC = 0, TGB_FILTER_BOX = 1, TGB_FILTER_TENT = 2, TGB_FILTER_GAUSSIAN = 3,
+       TGB_FILTER_MITCHELL = 4, TGB_FILTER_CATMULL_ROM = 5, TGB_FILTER_LANCZOS = 6 };
+
+typedef struct tgb_camera {
+    float    pos[3];            /* Camera::_pos                                                     */
+    float    xform[9];          /* upper 3x3 of Camera::_transform AFTER setRight(-right), row-major */
+    float    fov_deg;           /* PinholeCamera::_fovDeg                                           */
+    uint32_t res_x, res_y;
+    uint32_t filter;            /* TGB_FILTER_*                                                     */
+} tgb_camera;
+
+/* ---- integrator + renderer settings (PathTracerSettings.hpp:25-32, TraceSettings.hpp:23-29,
+ *      RendererSettings.hpp:49-76) ----------------------------------------------------------- */
+typedef struct tgb_settings {
+    int32_t  min_bounces, max_bounces;
+    uint32_t enable_light_sampling;
+    uint32_t enable_two_sided_shading;
+    uint32_t enable_consistency_checks;
+    uint32_t use_sobol;         /* renderer.stratified_sampler; only 1 is supported                  */
+    uint32_t supplemental_mode; /* 0 = per-path reseed (parity contract)        */
+    int32_t  device;            /* CUDA ordinal, -1 = current                                        */
+    uint32_t max_paths_in_flight; /* 0 = library default                                             */
+} tgb_settings;
+
+typedef struct tgb_scene_desc {
+    uint32_t abi_version;       /* TGB200_ABI_VERSION                                                */
+    tgb_camera    camera;
+    tgb_settings  settings;
+    const tgb_primitive *primitives;  uint32_t n_primitives;
+    const tgb_bsdf      *bsdfs;       uint32_t n_bsdfs;
+    const uint32_t      *bsdf_slots;  uint32_t n_bsdf_slots;   /* per-primitive bsdf index lists    */
+    const tgb_texture   *textures;    uint32_t n_textures;
+} tgb_scene_desc;
+
+/* ImageTile minus the sampler object (reference: integrators/ImageTile.hpp:12-31); sampler_seed is
+ * the value the tile's SobolPathSampler was constructed with (PathTraceIntegrator.cpp:27-42).      */
+typedef struct tgb_tile { uint32_t x, y, w, h; uint32_t sampler_seed; } tgb_tile;
+
+/* Parity hook: one closest-hit query == one TraceableScene::intersect (TraceableScene.hpp:170-192) */
+typedef struct tgb_ray { float o[3]; float d[3]; float tmin, tmax; } tgb_ray;
+typedef struct tgb_hit {
+    int32_t  primitive;         /* index into primitives[], -1 = miss                               */
+    int32_t  prim_id;           /* triangle index within the mesh (0 for quad/cube)                 */
+    float    t, u, v;
+    uint32_t backside;
+} tgb_hit;
+
+/* Counters with the definitions of SURVEY.md section 8(d): a "ray" is one closest-hit query
+ * (primary + continuation + NEE shadow + MIS), a "hit" is a query that found a surface.            */
+typedef struct tgb_stats {
+    uint64_t samples;           /* camera paths started                                             */
+    uint64_t rays;
+    uint64_t hits;
+    uint64_t kernel_launches;   /* launches of this library's own kernels                           */
+    double   trace_ms;          /* CUDA-event time inside trace kernels (closest + shadow)          */
+    uint64_t trace_launches;
+    double   total_ms;          /* CUDA-event time of the whole device section                      */
+} tgb_stats;
+
+typedef struct tgb_ctx tgb_ctx;
+
+/* Flatten + upload the scene, build the BVH, allocate the wavefront queues.
+ * Replaces: TraceableScene ctor body that prepares primitives/lights + PathTraceIntegrator::
+ * prepareForRender (renderer/TraceableScene.hpp:57-137; PathTraceIntegrator.cpp:184-201).           */
+int tgb200_create(const tgb_scene_desc *scene, tgb_ctx **out);
+
+/* Render samples [spp_begin, spp_begin+spp_count) of every pixel of the given tiles and fold them
+ * into rgb_mean (w*h*3 floats, row-major, top row first) with the reference's running mean
+ * (OutputBuffer::addSample, cameras/OutputBuffer.hpp:104-132); count (w*h, may be NULL) receives
+ * the per-pixel accepted-sample count.  n_tiles == 0 renders the whole image with the reference's
+ * own tile dicing and tile seeds derived from `seed` (PathTraceIntegrator.cpp:27-42,187).
+ * rgb_mean/count are HOST pointers: input state on entry (may hold earlier samples), updated on exit.
+ * Replaces: PathTraceIntegrator::renderTile over all tiles (PathTraceIntegrator.cpp:136-156).       */
+int tgb200_render_tiles(tgb_ctx *ctx, const tgb_tile *tiles, uint32_t n_tiles, uint32_t seed,
+                        uint32_t spp_begin, uint32_t spp_count, float *rgb_mean, uint32_t *count);
+
+/* Same, but the framebuffer stays resident on the device between calls (no host<->device copy);
+ * fetch it with tgb200_read_framebuffer.  Used by the multi-GPU path and the device-resident bench. */
+int tgb200_render_resident(tgb_ctx *ctx, const tgb_tile *tiles, uint32_t n_tiles, uint32_t seed,
+                           uint32_t spp_begin, uint32_t spp_count);
+int tgb200_clear_framebuffer(tgb_ctx *ctx);
+int tgb200_read_framebuffer(tgb_ctx *ctx, float *rgb_mean, uint32_t *count);
+/* Device address of the resident fp32 RGB framebuffer (w*h*3) for zero-copy hand-off to NCCL.       */
+int tgb200_framebuffer_device_ptr(tgb_ctx *ctx, void **rgb_mean_dev, uint64_t *n_bytes);
+
+/* Batch of closest-hit queries through the same traversal kernel the renderer uses.                 */
+int tgb200_trace_closest(tgb_ctx *ctx, const tgb_ray *rays, tgb_hit *hits, uint32_t n);
+
+int  tgb200_get_stats(tgb_ctx *ctx, tgb_stats *out);
+int  tgb200_reset_stats(tgb_ctx *ctx);
+int  tgb200_abort(tgb_ctx *ctx);
+void tgb200_destroy(tgb_ctx *ctx);
+/* Last error text of the context; with ctx == NULL the text of the last failed tgb200_create.       */
+const char *tgb200_last_error(const tgb_ctx *ctx);
+uint32_t tgb200_abi_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TGB200_H_ */
