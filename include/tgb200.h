@@ -186,6 +186,12 @@ int tgb200_framebuffer_device_ptr(tgb_ctx *ctx, void **rgb_mean_dev, uint64_t *n
 int tgb200_trace_closest(tgb_ctx *ctx, const tgb_ray *rays, tgb_hit *hits, uint32_t n);
 
 int  tgb200_get_stats(tgb_ctx *ctx, tgb_stats *out);
+/* Time every traversal-kernel launch with CUDA events on the render stream (fills trace_ms).        */
+int  tgb200_set_profiling(tgb_ctx *ctx, int enable);
+/* Size of what was built: triangles, BVH nodes, BVH depth, bytes of nodes+triangle records, and the
+ * wavefront capacity (paths in flight).  Any pointer may be NULL.                                   */
+int  tgb200_scene_info(tgb_ctx *ctx, uint32_t *n_tris, uint32_t *n_nodes, uint32_t *bvh_depth,
+                       uint64_t *geom_bytes, uint32_t *capacity);
 int  tgb200_reset_stats(tgb_ctx *ctx);
 int  tgb200_abort(tgb_ctx *ctx);
 void tgb200_destroy(tgb_ctx *ctx);

@@ -1,0 +1,173 @@
+// Binned-SAH BVH2 builder (host, multi-threaded).  See bvh_build.h for what it replaces.
+#include "bvh_build.h"
+
+#include <algorithm>
+#include <atomic>
+#include <cmath>
+#include <cstring>
+#include <limits>
+#include <thread>
+
+namespace tgb {
+namespace {
+
+struct Box {
+    float lo[3], hi[3];
+    void reset() { for (int a = 0; a < 3; ++a) { lo[a] = std::numeric_limits<float>::infinity(); hi[a] = -lo[a]; } }
+    void grow(const Box &b) { for (int a = 0; a < 3; ++a) { lo[a] = std::min(lo[a], b.lo[a]); hi[a] = std::max(hi[a], b.hi[a]); } }
+    void grow(const float *p) { for (int a = 0; a < 3; ++a) { lo[a] = std::min(lo[a], p[a]); hi[a] = std::max(hi[a], p[a]); } }
+    float half_area() const {
+        float dx = hi[0] - lo[0], dy = hi[1] - lo[1], dz = hi[2] - lo[2];
+        if (!(dx >= 0.0f)) return 0.0f;
+        return dx*dy + dy*dz + dz*dx;
+    }
+};
+
+struct Tmp { Box box; int32_t left, right; uint32_t first, count; };
+
+constexpr int kBins = 16;
+constexpr uint32_t kMaxLeaf = 4;
+constexpr float kTraversalCost = 1.0f, kIntersectCost = 1.0f;
+
+struct Builder {
+    const Box *tb; const float *cent; uint32_t *idx; std::vector<Tmp> nodes; std::atomic<uint32_t> n_nodes{0};
+    std::atomic<int> free_threads{0};
+
+    uint32_t alloc() { return n_nodes.fetch_add(1); }
+
+    void build(uint32_t node, uint32_t first, uint32_t count, int depth) {
+        Tmp &nd = nodes[node];
+        Box box, cb; box.reset(); cb.reset();
+        for (uint32_t i = 0; i < count; ++i) { uint32_t t = idx[first + i]; box.grow(tb[t]); cb.grow(cent + 3*t); }
+        nd.box = box; nd.first = first; nd.count = count; nd.left = nd.right = -1;
+        if (count <= 1) return;
+
+        int best_axis = -1, best_split = -1; float best_cost = std::numeric_limits<float>::infinity();
+        for (int a = 0; a < 3; ++a) {
+            float ext = cb.hi[a] - cb.lo[a];
+            if (!(ext > 0.0f)) continue;
+            Box bb[kBins]; uint32_t bc[kBins];
+            for (int b = 0; b < kBins; ++b) { bb[b].reset(); bc[b] = 0; }
+            float scale = kBins/ext;
+            for (uint32_t i = 0; i < count; ++i) {
+                uint32_t t = idx[first + i];
+                int b = std::min(kBins - 1, std::max(0, int((cent[3*t + a] - cb.lo[a])*scale)));
+                bb[b].grow(tb[t]); bc[b]++;
+            }
+            float right_area[kBins]; Box acc; acc.reset();
+            for (int b = kBins - 1; b > 0; --b) { acc.grow(bb[b]); right_area[b] = acc.half_area(); }
+            acc.reset(); uint32_t nl = 0;
+            for (int b = 0; b < kBins - 1; ++b) {
+                acc.grow(bb[b]); nl += bc[b];
+                if (nl == 0 || nl == count) continue;
+                float cost = acc.half_area()*nl + right_area[b + 1]*(count - nl);
+                if (cost < best_cost) { best_cost = cost; best_axis = a; best_split = b; }
+            }
+        }
+        float leaf_cost = kIntersectCost*count;
+        float split_cost = best_axis >= 0 ? kTraversalCost + kIntersectCost*best_cost/std::max(box.half_area(), 1e-30f)
+                                          : std::numeric_limits<float>::infinity();
+        if (count <= kMaxLeaf && !(split_cost < leaf_cost)) return;
+
+        uint32_t mid;
+        if (best_axis >= 0) {
+            float ext = cb.hi[best_axis] - cb.lo[best_axis], scale = kBins/ext, lo = cb.lo[best_axis];
+            const float *c = cent; int ax = best_axis, sp = best_split;
+            uint32_t *m = std::partition(idx + first, idx + first + count, [=](uint32_t t) {
+                int b = std::min(kBins - 1, std::max(0, int((c[3*t + ax] - lo)*scale)));
+                return b <= sp;
+            });
+            mid = uint32_t(m - (idx + first));
+        } else {
+            mid = count/2;   // all centroids coincide: split by index
+        }
+        if (mid == 0 || mid == count) mid = count/2;
+        uint32_t l = alloc(), r = alloc();
+        nodes[node].left = int32_t(l); nodes[node].right = int32_t(r);
+        bool spawned = false; std::thread th;
+        if (count > 32768) {
+            int avail = free_threads.load();
+            while (avail > 0 && !free_threads.compare_exchange_weak(avail, avail - 1)) {}
+            if (avail > 0) { spawned = true; th = std::thread([=] { build(l, first, mid, depth + 1); free_threads.fetch_add(1); }); }
+        }
+        if (!spawned) build(l, first, mid, depth + 1);
+        build(r, first + mid, count - mid, depth + 1);
+        if (spawned) th.join();
+    }
+};
+
+inline float pad_down(float v) { return std::nextafter(std::nextafter(v, -std::numeric_limits<float>::infinity()), -std::numeric_limits<float>::infinity()); }
+inline float pad_up(float v) { return std::nextafter(std::nextafter(v, std::numeric_limits<float>::infinity()), std::numeric_limits<float>::infinity()); }
+
+}  // namespace
+
+void build_bvh2(const BuildTri *tris, uint32_t n, Bvh2 &out, int threads) {
+    out.nodes.clear(); out.order.clear(); out.root_link = 0; out.max_depth = 0; out.sah_cost = 0.0;
+    for (int a = 0; a < 3; ++a) { out.lo[a] = std::numeric_limits<float>::infinity(); out.hi[a] = -out.lo[a]; }
+    if (n == 0) return;
+    std::vector<Box> tb(n); std::vector<float> cent(3*size_t(n));
+    for (uint32_t i = 0; i < n; ++i) {
+        Box b; b.reset(); b.grow(tris[i].v0); b.grow(tris[i].v1); b.grow(tris[i].v2);
+        for (int a = 0; a < 3; ++a) { cent[3*size_t(i) + a] = 0.5f*b.lo[a] + 0.5f*b.hi[a]; b.lo[a] = pad_down(b.lo[a]); b.hi[a] = pad_up(b.hi[a]); }
+        tb[i] = b;
+    }
+    out.order.resize(n);
+    for (uint32_t i = 0; i < n; ++i) out.order[i] = i;
+    Builder bl; bl.tb = tb.data(); bl.cent = cent.data(); bl.idx = out.order.data();
+    bl.nodes.resize(2*size_t(n) + 1);
+    if (threads <= 0) threads = int(std::thread::hardware_concurrency());
+    bl.free_threads = std::max(0, threads - 1);
+    uint32_t root = bl.alloc();
+    bl.build(root, 0, n, 0);
+
+    for (int a = 0; a < 3; ++a) { out.lo[a] = bl.nodes[root].box.lo[a]; out.hi[a] = bl.nodes[root].box.hi[a]; }
+
+    // flatten: every inner Tmp node becomes one Node2 carrying its two children's boxes
+    auto leaf_link = [](const Tmp &t) { return ~int32_t((t.first << 3) | (t.count - 1)); };
+    // leaves may hold more than 8 only if all centroids coincide and SAH refused: force-split guard
+    struct Item { uint32_t tmp; int32_t out_index; uint32_t depth; };
+    const Tmp &rt = bl.nodes[root];
+    if (rt.left < 0) {
+        out.root_link = leaf_link(rt);
+        out.max_depth = 1;
+        // a single-leaf scene still gets one node so the kernel has something to read
+        Node2 nd; std::memset(&nd, 0, sizeof(nd));
+        for (int k = 0; k < 12; ++k) nd.f[k] = 0.0f;
+        nd.f[0] = rt.box.lo[0]; nd.f[1] = rt.box.hi[0]; nd.f[2] = rt.box.lo[1]; nd.f[3] = rt.box.hi[1];
+        nd.f[8] = rt.box.lo[2]; nd.f[9] = rt.box.hi[2];
+        nd.f[4] = 1.0f; nd.f[5] = -1.0f; nd.f[6] = 1.0f; nd.f[7] = -1.0f; nd.f[10] = 1.0f; nd.f[11] = -1.0f;  // empty c1
+        nd.link[0] = leaf_link(rt); nd.link[1] = leaf_link(rt);
+        out.nodes.push_back(nd);
+        out.root_link = 0;
+        return;
+    }
+    std::vector<Item> stack; stack.push_back({root, 0, 1});
+    out.nodes.resize(1);
+    double root_area = std::max(double(rt.box.half_area()), 1e-30);
+    while (!stack.empty()) {
+        Item it = stack.back(); stack.pop_back();
+        const Tmp &t = bl.nodes[it.tmp];
+        const Tmp &c0 = bl.nodes[t.left], &c1 = bl.nodes[t.right];
+        Node2 nd; std::memset(&nd, 0, sizeof(nd));
+        nd.f[0] = c0.box.lo[0]; nd.f[1] = c0.box.hi[0]; nd.f[2] = c0.box.lo[1]; nd.f[3] = c0.box.hi[1];
+        nd.f[4] = c1.box.lo[0]; nd.f[5] = c1.box.hi[0]; nd.f[6] = c1.box.lo[1]; nd.f[7] = c1.box.hi[1];
+        nd.f[8] = c0.box.lo[2]; nd.f[9] = c0.box.hi[2]; nd.f[10] = c1.box.lo[2]; nd.f[11] = c1.box.hi[2];
+        out.sah_cost += kTraversalCost*t.box.half_area()/root_area;
+        out.max_depth = std::max(out.max_depth, it.depth + 1);
+        const Tmp *cs[2] = {&c0, &c1}; const int32_t ci[2] = {t.left, t.right};
+        for (int k = 0; k < 2; ++k) {
+            if (cs[k]->left < 0) {
+                nd.link[k] = leaf_link(*cs[k]);
+                out.sah_cost += kIntersectCost*cs[k]->count*cs[k]->box.half_area()/root_area;
+            } else {
+                nd.link[k] = int32_t(out.nodes.size());
+                out.nodes.emplace_back();
+                stack.push_back({uint32_t(ci[k]), nd.link[k], it.depth + 1});
+            }
+        }
+        out.nodes[size_t(it.out_index)] = nd;
+    }
+    out.root_link = 0;
+}
+
+}  // namespace tgb

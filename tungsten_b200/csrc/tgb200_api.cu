@@ -1,0 +1,714 @@
+// C ABI of libtgb200.so (include/tgb200.h): scene preparation, device upload, wavefront render loop.
+// Host logic mirrors the reference's TraceableScene constructor + PathTraceIntegrator (prepare, tile
+// dicing, sample stepping); all rendering arithmetic runs in the CUDA kernels of tgb_kernels.cuh.
+// There is NO CPU fallback: without a CUDA device every entry point fails with TGB_ERR_NO_DEVICE.
+#include <atomic>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "bvh_build.h"
+#include "tgb_kernels.cuh"
+
+extern "C" const unsigned char tgb_sobol_blob[];      // sobol_blob.cpp (.incbin of data/sobol_1024x32.u32)
+
+using namespace tgb;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+struct DeviceBuf {
+    void *p = nullptr; size_t bytes = 0;
+};
+
+}  // namespace
+
+struct tgb_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    std::string error;
+    std::atomic<int> abort_flag{0};
+    std::vector<void *> allocs;
+    DScene sc{};
+    uint32_t res_x = 0, res_y = 0;
+    // wavefront storage
+    uint32_t capacity = 0;
+    PathState st{};
+    uint32_t *queue_a = nullptr, *queue_b = nullptr, *squeue = nullptr;
+    uint32_t *counts = nullptr;          // [0]=count A, [1]=count B, [2]=shadow count
+    uint32_t *h_counts = nullptr;        // pinned
+    Counters *ctr = nullptr; Counters *h_ctr = nullptr;
+    float *fb = nullptr; uint32_t *fb_count = nullptr;
+    float *h_fb = nullptr; uint32_t *h_fb_count = nullptr;   // pinned staging
+    // cached pixel list
+    std::vector<tgb_tile> tiles_cached; uint32_t *pix_id = nullptr, *pix_seed = nullptr; uint32_t n_pix = 0, pix_capacity = 0;
+    tgb_stats stats{};
+    bool profiling = false;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, evt0 = nullptr, evt1 = nullptr;
+    uint32_t bvh_depth = 0; uint32_t n_tris = 0; double bvh_sah = 0.0; size_t geom_bytes = 0;
+};
+
+namespace {
+
+int fail(tgb_ctx *c, int code, const char *fmt, ...) {
+    char buf[1024];
+    va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof(buf), fmt, ap); va_end(ap);
+    if (c) c->error = buf; else g_create_error = buf;
+    return code;
+}
+
+#define CU(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) \
+    return fail(c, e_ == cudaErrorMemoryAllocation ? TGB_ERR_OOM : TGB_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); } while (0)
+
+template <typename T>
+int dev_alloc(tgb_ctx *c, T **out, size_t n) {
+    void *p = nullptr;
+    CU(cudaMalloc(&p, std::max<size_t>(n, 1)*sizeof(T)));
+    c->allocs.push_back(p);
+    *out = static_cast<T *>(p);
+    return TGB_OK;
+}
+template <typename T>
+int dev_upload(tgb_ctx *c, const T **out, const std::vector<T> &v) {
+    T *p = nullptr;
+    int rc = dev_alloc(c, &p, v.size());
+    if (rc) return rc;
+    if (!v.empty()) CU(cudaMemcpy(p, v.data(), v.size()*sizeof(T), cudaMemcpyHostToDevice));
+    *out = p;
+    return TGB_OK;
+}
+
+V3 f3(const float *p) { return v3(p[0], p[1], p[2]); }
+void transpose3(const float *m, float *t) {
+    t[0] = m[0]; t[1] = m[3]; t[2] = m[6]; t[3] = m[1]; t[4] = m[4]; t[5] = m[7]; t[6] = m[2]; t[7] = m[5]; t[8] = m[8];
+}
+
+// ---- host-side "prepareForRender" pieces (fp32, reference operation order; compiled with -fmad=false) ----
+float filter_width(uint32_t f) {
+    switch (f) { case TGB_FILTER_DIRAC: return 0.0f; case TGB_FILTER_BOX: return 0.5f; case TGB_FILTER_TENT: return 1.0f; default: return 2.0f; }
+}
+float filter_eval(uint32_t f, float x) {                        // cameras/ReconstructionFilter.hpp:171-193
+    switch (f) {
+    case TGB_FILTER_BOX: return (x >= -0.5f && x <= 0.5f) ? 1.0f : 0.0f;
+    case TGB_FILTER_TENT: return 1.0f - std::fabs(x);
+    case TGB_FILTER_GAUSSIAN: { const float Alpha = 2.0f; return std::max(std::exp(-Alpha*x*x) - std::exp(-Alpha*4.0f), 0.0f); }
+    case TGB_FILTER_MITCHELL: { x = std::fabs(x); const float B = 1.0f/3.0f, C = 1.0f/3.0f;
+        if (x < 1.0f) return 1.0f/6.0f*((12.0f - 9.0f*B - 6.0f*C)*x*x*x + (-18.0f + 12.0f*B + 6.0f*C)*x*x + (6.0f - 2.0f*B));
+        else if (x < 2.0f) return 1.0f/6.0f*((-B - 6.0f*C)*x*x*x + (6.0f*B + 30.0f*C)*x*x + (-12.0f*B - 48.0f*C)*x + (8.0f*B + 24.0f*C));
+        return 0.0f; }
+    case TGB_FILTER_CATMULL_ROM: { x = std::fabs(x);
+        if (x < 1.0f) return 1.0f/6.0f*((12.0f - 3.0f)*x*x*x + (-18.0f + 3.0f)*x*x + 6.0f);
+        else if (x < 2.0f) return 1.0f/6.0f*(-3.0f*x*x*x + 15.0f*x*x - 24.0f*x + 12.0f);
+        return 0.0f; }
+    case TGB_FILTER_LANCZOS: { x = std::fabs(x);
+        if (x == 0.0f) return 1.0f;
+        else if (x < 2.0f) return std::sin(PI_F*x)*std::sin(PI_F*x/2.0f)/(PI_F*PI_F*x*x/2.0f);
+        return 0.0f; }
+    default: return 0.0f;
+    }
+}
+void filter_precompute(DCamera &cam) {                          // cameras/ReconstructionFilter.cpp:34-58
+    const int R = 31;
+    float width = filter_width(cam.filter);
+    cam.filter_bin = width/R;
+    std::memset(cam.filter_cdf, 0, sizeof(cam.filter_cdf));
+    if (cam.filter == TGB_FILTER_BOX || cam.filter == TGB_FILTER_DIRAC) return;
+    float f[32], sum = 0.0f;
+    for (int i = 0; i < R; ++i) { f[i] = filter_eval(cam.filter, (i*width)/R); sum += f[i]; }
+    cam.filter_cdf[0] = 0.0f;
+    for (int i = 1; i < R; ++i) cam.filter_cdf[i] = cam.filter_cdf[i - 1] + f[i - 1]/sum;
+    cam.filter_cdf[R] = 1.0f;
+}
+float h_dielectric_reflectance(float eta, float cosThetaI) {    // bsdfs/Fresnel.hpp:75-92
+    if (cosThetaI < 0.0f) { eta = 1.0f/eta; cosThetaI = -cosThetaI; }
+    float sinThetaTSq = eta*eta*(1.0f - cosThetaI*cosThetaI);
+    if (sinThetaTSq > 1.0f) return 1.0f;
+    float cosThetaT = std::sqrt(std::max(1.0f - sinThetaTSq, 0.0f));
+    float Rs = (eta*cosThetaI - cosThetaT)/(eta*cosThetaI + cosThetaT);
+    float Rp = (eta*cosThetaT - cosThetaI)/(eta*cosThetaT + cosThetaI);
+    return (Rs*Rs + Rp*Rp)*0.5f;
+}
+float diffuse_fresnel(float ior, int sampleCount) {             // bsdfs/Fresnel.hpp:141-153
+    double acc = 0.0;
+    float fb = h_dielectric_reflectance(ior, 0.0f);
+    for (int i = 1; i <= sampleCount; ++i) {
+        float cosThetaSq = float(i)/sampleCount;
+        float fa = h_dielectric_reflectance(ior, std::min(std::sqrt(cosThetaSq), 1.0f));
+        acc += double(fa + fb)*(0.5/sampleCount);
+        fb = fa;
+    }
+    return float(acc);
+}
+uint32_t bsdf_lobes(const tgb_bsdf &b) {
+    switch (b.type) {
+    case TGB_BSDF_NULL: return 0;
+    case TGB_BSDF_LAMBERT: return LOBE_DIFFUSE_R;
+    case TGB_BSDF_ROUGH_CONDUCTOR: return LOBE_GLOSSY_R;
+    case TGB_BSDF_ROUGH_DIELECTRIC: return b.enable_refraction ? (LOBE_GLOSSY_R | LOBE_GLOSSY_T) : LOBE_GLOSSY_R;
+    case TGB_BSDF_PLASTIC: return LOBE_SPEC_R | LOBE_DIFFUSE_R;
+    case TGB_BSDF_ROUGH_PLASTIC: return LOBE_GLOSSY_R | LOBE_DIFFUSE_R;
+    default: return 0xFFFFFFFFu;
+    }
+}
+
+struct HostTex { DTex d; V3 maxv; std::vector<float> marg_pdf, marg_cdf, pdf, cdf; bool has_dist = false; };
+
+// BitmapTexture::makeSamplable(MAP_SPHERICAL) + Distribution2D (textures/BitmapTexture.cpp:400-431,
+// sampling/Distribution2D.hpp:18-46)
+void build_spherical_distribution(const tgb_texture &t, HostTex &ht) {
+    int w = int(t.res_u), h = int(t.res_v);
+    std::vector<float> weights(size_t(w)*h), tmp(size_t(w)*h);
+    for (int y = 0; y < h; ++y) {
+        float rowWeight = std::sin((y*PI_F)/h);
+        for (int x = 0; x < w; ++x) {
+            const float *p = t.texels + 3*(size_t(y)*w + x);
+            weights[size_t(y)*w + x] = std::max(p[0], std::max(p[1], p[2]))*rowWeight;
+        }
+    }
+    for (int y = 0; y < h; ++y) for (int x = 0; x < w; ++x) {
+        float m = weights[size_t(y)*w + x];
+        if (x < w - 1) m = std::max(m, weights[size_t(y)*w + x + 1]);
+        if (x > 0) m = std::max(m, weights[size_t(y)*w + x - 1]);
+        tmp[size_t(y)*w + x] = m;
+    }
+    for (int y = 0; y < h; ++y) for (int x = 0; x < w; ++x) {
+        float m = tmp[size_t(y)*w + x];
+        if (y < h - 1) m = std::max(m, tmp[size_t(y + 1)*w + x]);
+        if (y > 0) m = std::max(m, tmp[size_t(y - 1)*w + x]);
+        weights[size_t(y)*w + x] = m;
+    }
+    ht.pdf = weights; ht.cdf.assign(size_t(w + 1)*h, 0.0f); ht.marg_pdf.assign(h, 0.0f); ht.marg_cdf.assign(h + 1, 0.0f);
+    for (int y = 0; y < h; ++y) {
+        float *pdf = ht.pdf.data() + size_t(y)*w, *cdf = ht.cdf.data() + size_t(y)*(w + 1);
+        cdf[0] = 0.0f;
+        for (int x = 0; x < w; ++x) cdf[x + 1] = cdf[x] + pdf[x];
+        ht.marg_pdf[y] = cdf[w];
+        ht.marg_cdf[y + 1] = ht.marg_cdf[y] + ht.marg_pdf[y];
+    }
+    for (int y = 0; y < h; ++y) {
+        float *pdf = ht.pdf.data() + size_t(y)*w, *cdf = ht.cdf.data() + size_t(y)*(w + 1);
+        if (ht.marg_pdf[y] > 0.0f) { float scale = 1.0f/ht.marg_pdf[y]; for (int x = 0; x < w; ++x) { pdf[x] *= scale; cdf[x] *= scale; } }
+        cdf[w] = 1.0f;
+    }
+    if (ht.marg_cdf[h] > 0.0f) { float scale = 1.0f/ht.marg_cdf[h]; for (int y = 0; y < h; ++y) { ht.marg_pdf[y] *= scale; ht.marg_cdf[y] *= scale; } }
+    ht.marg_cdf[h] = 1.0f;
+    ht.has_dist = true;
+}
+
+int upload_scene(tgb_ctx *c, const tgb_scene_desc *d) {
+    const tgb_camera &cam = d->camera;
+    DScene &sc = c->sc;
+    sc.set = d->settings;
+    // camera precompute (cameras/PinholeCamera.cpp:28-35, Camera.cpp:37-42)
+    sc.cam.pos = f3(cam.pos); std::memcpy(sc.cam.m, cam.xform, sizeof(sc.cam.m));
+    float fovRad = cam.fov_deg*(PI_F/180.0f);
+    sc.cam.plane_dist = 1.0f/std::tan(fovRad*0.5f);
+    sc.cam.ratio = cam.res_y/float(cam.res_x);
+    sc.cam.pixel_size_x = 1.0f/cam.res_x;
+    sc.cam.res_x = cam.res_x; sc.cam.res_y = cam.res_y; sc.cam.filter = cam.filter;
+    filter_precompute(sc.cam);
+    c->res_x = cam.res_x; c->res_y = cam.res_y;
+
+    // ---- textures
+    std::vector<HostTex> tex(d->n_textures + 1);
+    for (uint32_t i = 0; i < d->n_textures; ++i) {
+        const tgb_texture &t = d->textures[i]; DTex &o = tex[i].d;
+        std::memset(&o, 0, sizeof(o));
+        o.type = t.type; o.value = f3(t.value); o.value2 = f3(t.value2); o.res_u = int(t.res_u); o.res_v = int(t.res_v); o.flags = t.flags;
+        if (t.type == TGB_TEX_BITMAP) {
+            if (!t.texels || !t.res_u || !t.res_v) return fail(c, TGB_ERR_INVALID, "bitmap texture %u has no texels", i);
+            size_t n = size_t(t.res_u)*t.res_v;
+            V3 acc = v3s(0.0f), mx = v3s(0.0f);
+            for (size_t k = 0; k < n; ++k) { V3 cc = f3(t.texels + 3*k); acc = acc + cc/float(n); mx = v3(std::max(mx.x, cc.x), std::max(mx.y, cc.y), std::max(mx.z, cc.z)); }
+            o.avg = acc; tex[i].maxv = mx;
+            std::vector<float> tx(t.texels, t.texels + 3*n);
+            int rc = dev_upload(c, &o.texels, tx); if (rc) return rc;
+        } else if (t.type == TGB_TEX_CHECKER) {
+            o.avg = (o.value + o.value2)*0.5f;
+            tex[i].maxv = v3(std::max(o.value.x, o.value2.x), std::max(o.value.y, o.value2.y), std::max(o.value.z, o.value2.z));
+        } else if (t.type == TGB_TEX_CONSTANT) { o.avg = o.value; tex[i].maxv = o.value; }
+        else return fail(c, TGB_ERR_UNSUPPORTED, "texture type %u is outside the hot path", t.type);
+    }
+    { DTex &o = tex[d->n_textures].d; std::memset(&o, 0, sizeof(o)); o.type = TGB_TEX_CONSTANT; o.value = v3s(1.0f); o.avg = o.value; tex[d->n_textures].maxv = o.value; }
+
+    // ---- bsdfs
+    std::vector<DBsdf> bsdfs(d->n_bsdfs);
+    for (uint32_t i = 0; i < d->n_bsdfs; ++i) {
+        const tgb_bsdf &b = d->bsdfs[i]; DBsdf &o = bsdfs[i];
+        std::memset(&o, 0, sizeof(o));
+        o.type = b.type; o.lobes = bsdf_lobes(b);
+        if (o.lobes == 0xFFFFFFFFu) return fail(c, TGB_ERR_UNSUPPORTED, "bsdf type %u is outside the hot path", b.type);
+        if (b.albedo_tex < 0 || uint32_t(b.albedo_tex) >= d->n_textures) return fail(c, TGB_ERR_INVALID, "bsdf %u: bad albedo texture", i);
+        bool rough = b.type == TGB_BSDF_ROUGH_CONDUCTOR || b.type == TGB_BSDF_ROUGH_DIELECTRIC || b.type == TGB_BSDF_ROUGH_PLASTIC;
+        if (rough && (b.roughness_tex < 0 || uint32_t(b.roughness_tex) >= d->n_textures)) return fail(c, TGB_ERR_INVALID, "bsdf %u: bad roughness texture", i);
+        o.dist = b.distribution; o.albedo_tex = b.albedo_tex; o.rough_tex = b.roughness_tex;
+        o.ior = b.ior; o.inv_ior = 1.0f/b.ior; o.eta = f3(b.eta); o.k = f3(b.k); o.enable_t = b.enable_refraction;
+        if (b.type == TGB_BSDF_PLASTIC || b.type == TGB_BSDF_ROUGH_PLASTIC) {             // bsdfs/PlasticBsdf.cpp:179-185
+            o.scaled_sigma_a = f3(b.sigma_a)*b.thickness;
+            o.avg_transmittance = std::exp(-2.0f*avg(o.scaled_sigma_a));
+            o.diffuse_fresnel = diffuse_fresnel(b.ior, 1000000);
+            o.substrate_weight = avg(tex[b.albedo_tex].d.avg);                             // RoughPlasticBsdf.cpp:215-222
+        }
+    }
+
+    // ---- primitives, lights, triangles
+    std::vector<DPrim> prims(d->n_primitives);
+    std::vector<int> lights, inf_lights, analytic;
+    std::vector<BuildTri> btris; std::vector<uint32_t> tri_prim; std::vector<float4> tri_shade;
+    int lightCount = 0;
+    for (uint32_t i = 0; i < d->n_primitives; ++i) {
+        const tgb_primitive &p = d->primitives[i]; DPrim &o = prims[i];
+        std::memset(&o, 0, sizeof(o));
+        o.type = p.type; o.emission_tex = p.emission_tex; o.bsdf_first = p.bsdf_first; o.bsdf_count = p.bsdf_count;
+        if (p.emission_tex >= int(d->n_textures)) return fail(c, TGB_ERR_INVALID, "primitive %u: bad emission texture", i);
+        bool emissive = p.emission_tex >= 0 && max_comp(tex[p.emission_tex].maxv) > 0.0f;  // primitives/Primitive.hpp:111-115
+        bool samplable = true, infinite = false;
+        if (p.type != TGB_PRIM_INFINITE_SPHERE) {
+            if (p.bsdf_count == 0 || p.bsdf_first + p.bsdf_count > d->n_bsdf_slots) return fail(c, TGB_ERR_INVALID, "primitive %u: bad bsdf range", i);
+            for (uint32_t k = 0; k < p.bsdf_count; ++k) if (d->bsdf_slots[p.bsdf_first + k] >= d->n_bsdfs) return fail(c, TGB_ERR_INVALID, "primitive %u: bad bsdf index", i);
+        }
+        switch (p.type) {
+        case TGB_PRIM_MESH: {
+            if (p.n_tris && (!p.verts || !p.tris)) return fail(c, TGB_ERR_INVALID, "mesh %u has null buffers", i);
+            o.tri_first = uint32_t(btris.size()); o.n_tris = p.n_tris;
+            if (p.smooth) o.flags |= PF_SMOOTH;
+            std::vector<float> areas(p.n_tris), lverts;
+            float total = 0.0f;
+            for (uint32_t k = 0; k < p.n_tris; ++k) {
+                const tgb_triangle &t = p.tris[k];
+                if (t.v0 >= p.n_verts || t.v1 >= p.n_verts || t.v2 >= p.n_verts) return fail(c, TGB_ERR_INVALID, "mesh %u: vertex index out of range", i);
+                const tgb_vertex &a = p.verts[t.v0], &b = p.verts[t.v1], &cc = p.verts[t.v2];
+                BuildTri bt; std::memcpy(bt.v0, a.pos, 12); std::memcpy(bt.v1, b.pos, 12); std::memcpy(bt.v2, cc.pos, 12);
+                btris.push_back(bt); tri_prim.push_back(i);
+                int mat = std::min(std::max(t.material, 0), int(p.bsdf_count) - 1);      // TriangleMesh.cpp:539
+                float4 s0 = make_float4(a.normal[0], a.normal[1], a.normal[2], b.normal[0]);
+                float4 s1 = make_float4(b.normal[1], b.normal[2], cc.normal[0], cc.normal[1]);
+                float4 s2 = make_float4(cc.normal[2], a.uv[0], a.uv[1], b.uv[0]);
+                float4 s3 = make_float4(b.uv[1], cc.uv[0], cc.uv[1], 0.0f);
+                std::memcpy(&s3.w, &mat, 4);
+                tri_shade.push_back(s0); tri_shade.push_back(s1); tri_shade.push_back(s2); tri_shade.push_back(s3);
+                V3 p0 = f3(a.pos), p1 = f3(b.pos), p2 = f3(cc.pos);
+                areas[k] = length(cross(p1 - p0, p2 - p0))*0.5f;                           // MathUtil::triangleArea
+                total += areas[k];                                                         // TriangleMesh.cpp:556-562
+                if (emissive) { const float *pp[3] = {a.pos, b.pos, cc.pos}; for (int q = 0; q < 3; ++q) for (int r = 0; r < 3; ++r) lverts.push_back(pp[q][r]); }
+            }
+            o.total_area = total;
+            if (p.n_tris == 0 || p.n_verts == 0) emissive = false;                         // isDirac(): not traced, not a light
+            if (emissive) {
+                // Distribution1D over triangle areas (TriangleMesh.cpp:389-403; sampling/Distribution1D.hpp:16-35)
+                std::vector<float> pdf = areas, cdf(p.n_tris + 1);
+                cdf[0] = 0.0f;
+                for (uint32_t k = 0; k < p.n_tris; ++k) cdf[k + 1] = cdf[k] + pdf[k];
+                float tw = cdf[p.n_tris];
+                for (float &x : pdf) x /= tw;
+                for (float &x : cdf) x /= tw;
+                cdf[p.n_tris] = 1.0f;
+                int rc = dev_upload(c, &o.tri_pdf, pdf); if (rc) return rc;
+                rc = dev_upload(c, &o.tri_cdf, cdf); if (rc) return rc;
+                rc = dev_upload(c, &o.light_verts, lverts); if (rc) return rc;
+            }
+            break; }
+        case TGB_PRIM_QUAD: {                                                             // primitives/Quad.cpp:298-316
+            o.base = f3(p.base); o.edge0 = f3(p.edge0); o.edge1 = f3(p.edge1);
+            V3 n = cross(o.edge1, o.edge0);
+            o.area = length(n);
+            o.normal = n/o.area;
+            o.inv_uv_sq0 = 1.0f/length_sq(o.edge0); o.inv_uv_sq1 = 1.0f/length_sq(o.edge1);
+            analytic.push_back(int(i));
+            break; }
+        case TGB_PRIM_CUBE: {                                                             // primitives/Cube.cpp:351-367
+            o.pos = f3(p.pos); o.scale = f3(p.scale);
+            std::memcpy(o.rot, p.rot, sizeof(o.rot)); transpose3(o.rot, o.inv_rot);
+            if (emissive) return fail(c, TGB_ERR_UNSUPPORTED, "emissive cubes are outside the hot path");
+            analytic.push_back(int(i));
+            break; }
+        case TGB_PRIM_INFINITE_SPHERE: {                                                  // primitives/InfiniteSphere.cpp prepareForRender
+            std::memcpy(o.rot, p.rot, sizeof(o.rot)); transpose3(o.rot, o.inv_rot);
+            samplable = p.do_sample != 0; infinite = true;
+            if (emissive && tex[p.emission_tex].d.type == TGB_TEX_CHECKER) return fail(c, TGB_ERR_UNSUPPORTED, "checker environment maps are outside the hot path");
+            break; }
+        default: return fail(c, TGB_ERR_UNSUPPORTED, "primitive type %u is outside the hot path", p.type);
+        }
+        if (emissive) {                                                                   // renderer/TraceableScene.hpp:89-96
+            o.flags |= PF_EMISSIVE; lightCount++;
+            if (samplable) lights.push_back(int(i));
+            if (infinite) inf_lights.push_back(int(i));
+        }
+        if (samplable) o.flags |= PF_SAMPLABLE;
+        if (infinite) o.flags |= PF_INFINITE;
+    }
+    if (lightCount == 0) {                                                                // renderer/TraceableScene.hpp:97-102
+        DPrim o; std::memset(&o, 0, sizeof(o));
+        o.type = TGB_PRIM_INFINITE_SPHERE; o.emission_tex = int(d->n_textures);
+        o.flags = PF_EMISSIVE | PF_SAMPLABLE | PF_INFINITE;
+        const float id[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+        std::memcpy(o.rot, id, sizeof(id)); std::memcpy(o.inv_rot, id, sizeof(id));
+        lights.push_back(int(prims.size())); inf_lights.push_back(int(prims.size()));
+        prims.push_back(o);
+    }
+    if (lights.size() > 16) return fail(c, TGB_ERR_UNSUPPORTED, "more than 16 samplable lights");
+    if (analytic.size() > 4096) return fail(c, TGB_ERR_UNSUPPORTED, "more than 4096 analytic primitives");
+    for (int li : lights) {
+        DPrim &l = prims[li];
+        if (l.type == TGB_PRIM_INFINITE_SPHERE && tex[l.emission_tex].d.type == TGB_TEX_BITMAP && !tex[l.emission_tex].has_dist)
+            build_spherical_distribution(d->textures[l.emission_tex], tex[l.emission_tex]);
+    }
+    std::vector<DTex> dtex(tex.size());
+    for (size_t i = 0; i < tex.size(); ++i) {
+        if (tex[i].has_dist) {
+            int rc = dev_upload(c, &tex[i].d.marg_pdf, tex[i].marg_pdf); if (rc) return rc;
+            rc = dev_upload(c, &tex[i].d.marg_cdf, tex[i].marg_cdf); if (rc) return rc;
+            rc = dev_upload(c, &tex[i].d.pdf, tex[i].pdf); if (rc) return rc;
+            rc = dev_upload(c, &tex[i].d.cdf, tex[i].cdf); if (rc) return rc;
+        }
+        dtex[i] = tex[i].d;
+    }
+
+    // ---- BVH over every mesh triangle
+    Bvh2 bvh;
+    build_bvh2(btris.data(), uint32_t(btris.size()), bvh, 0);
+    if (bvh.max_depth + 2 > uint32_t(kStackSize)) return fail(c, TGB_ERR_UNSUPPORTED, "BVH depth %u exceeds the traversal stack", bvh.max_depth);
+    c->bvh_depth = bvh.max_depth; c->n_tris = uint32_t(btris.size()); c->bvh_sah = bvh.sah_cost;
+    std::vector<float4> tri_isect(3*btris.size());
+    for (size_t k = 0; k < bvh.order.size(); ++k) {
+        const BuildTri &t = btris[bvh.order[k]];
+        // Embree TriangleM: v0, e1 = v0-v1, e2 = v2-v0, Ng = cross(e1, e2) (kernels/geometry/triangle.h:54)
+        V3 v0 = f3(t.v0), v1 = f3(t.v1), v2 = f3(t.v2);
+        V3 e1 = v0 - v1, e2 = v2 - v0, ng = cross(e1, e2);
+        tri_isect[3*k] = make_float4(v0.x, v0.y, v0.z, e1.x);
+        tri_isect[3*k + 1] = make_float4(e1.y, e1.z, e2.x, e2.y);
+        tri_isect[3*k + 2] = make_float4(e2.z, ng.x, ng.y, ng.z);
+    }
+    std::vector<float4> nodes(4*bvh.nodes.size());
+    std::memcpy(nodes.data(), bvh.nodes.data(), bvh.nodes.size()*sizeof(Node2));
+    c->geom_bytes = nodes.size()*16 + tri_isect.size()*16 + tri_shade.size()*16;
+
+    int rc;
+    if ((rc = dev_upload(c, &sc.prims, prims))) return rc;
+    if ((rc = dev_upload(c, &sc.bsdfs, bsdfs))) return rc;
+    std::vector<uint32_t> slots(d->bsdf_slots, d->bsdf_slots + d->n_bsdf_slots);
+    if ((rc = dev_upload(c, &sc.slots, slots))) return rc;
+    if ((rc = dev_upload(c, &sc.tex, dtex))) return rc;
+    if ((rc = dev_upload(c, &sc.lights, lights))) return rc;
+    if ((rc = dev_upload(c, &sc.inf_lights, inf_lights))) return rc;
+    if ((rc = dev_upload(c, &sc.analytic, analytic))) return rc;
+    if ((rc = dev_upload(c, &sc.tri_isect, tri_isect))) return rc;
+    if ((rc = dev_upload(c, &sc.tri_global, bvh.order))) return rc;
+    if ((rc = dev_upload(c, &sc.tri_prim, tri_prim))) return rc;
+    if ((rc = dev_upload(c, &sc.tri_shade, tri_shade))) return rc;
+    if ((rc = dev_upload(c, &sc.nodes, nodes))) return rc;
+    std::vector<uint32_t> sobol(1024*32);
+    std::memcpy(sobol.data(), tgb_sobol_blob, sobol.size()*4);
+    if ((rc = dev_upload(c, &sc.sobol, sobol))) return rc;
+    sc.n_prims = uint32_t(prims.size()); sc.n_lights = int(lights.size()); sc.n_inf_lights = int(inf_lights.size());
+    sc.n_analytic = int(analytic.size()); sc.n_nodes = uint32_t(bvh.nodes.size()); sc.n_tris = uint32_t(btris.size());
+    return TGB_OK;
+}
+
+int alloc_wavefront(tgb_ctx *c, uint32_t capacity) {
+    c->capacity = capacity;
+    float **fp = reinterpret_cast<float **>(&c->st);
+    // PathState is a struct of pointers; allocate one slab per array in declaration order
+    int rc;
+#define ALLOCF(name) if ((rc = dev_alloc(c, &c->st.name, capacity))) return rc;
+    ALLOCF(ox) ALLOCF(oy) ALLOCF(oz) ALLOCF(dx) ALLOCF(dy) ALLOCF(dz) ALLOCF(tmin)
+    ALLOCF(tx) ALLOCF(ty) ALLOCF(tz) ALLOCF(ex) ALLOCF(ey) ALLOCF(ez)
+    ALLOCF(pcg) ALLOCF(info) ALLOCF(ht) ALLOCF(hu) ALLOCF(hv) ALLOCF(hid)
+    ALLOCF(px) ALLOCF(py) ALLOCF(pz)
+    ALLOCF(lx) ALLOCF(ly) ALLOCF(lz) ALLOCF(bx) ALLOCF(by) ALLOCF(bz) ALLOCF(wl) ALLOCF(sx) ALLOCF(sy) ALLOCF(sz) ALLOCF(ux) ALLOCF(uy) ALLOCF(uz)
+    ALLOCF(ndx) ALLOCF(ndy) ALLOCF(ndz) ALLOCF(ndist) ALLOCF(nfx) ALLOCF(nfy) ALLOCF(nfz) ALLOCF(npl) ALLOCF(npb)
+    ALLOCF(mdx) ALLOCF(mdy) ALLOCF(mdz) ALLOCF(mwx) ALLOCF(mwy) ALLOCF(mwz) ALLOCF(mpb) ALLOCF(qlight)
+#undef ALLOCF
+    (void)fp;
+    if ((rc = dev_alloc(c, &c->queue_a, capacity))) return rc;
+    if ((rc = dev_alloc(c, &c->queue_b, capacity))) return rc;
+    if ((rc = dev_alloc(c, &c->squeue, size_t(capacity)*2))) return rc;
+    if ((rc = dev_alloc(c, &c->counts, 4))) return rc;
+    if ((rc = dev_alloc(c, &c->ctr, 1))) return rc;
+    CU(cudaMemset(c->ctr, 0, sizeof(Counters)));
+    CU(cudaMallocHost(reinterpret_cast<void **>(&c->h_counts), 4*sizeof(uint32_t)));
+    CU(cudaMallocHost(reinterpret_cast<void **>(&c->h_ctr), sizeof(Counters)));
+    size_t npx = size_t(c->res_x)*c->res_y;
+    if ((rc = dev_alloc(c, &c->fb, npx*3))) return rc;
+    if ((rc = dev_alloc(c, &c->fb_count, npx))) return rc;
+    CU(cudaMemset(c->fb, 0, npx*3*sizeof(float)));
+    CU(cudaMemset(c->fb_count, 0, npx*sizeof(uint32_t)));
+    CU(cudaMallocHost(reinterpret_cast<void **>(&c->h_fb), npx*3*sizeof(float)));
+    CU(cudaMallocHost(reinterpret_cast<void **>(&c->h_fb_count), npx*sizeof(uint32_t)));
+    return TGB_OK;
+}
+
+// PathTraceIntegrator::diceTiles + the sampler seeding of prepareForRender (PathTraceIntegrator.cpp:27-42,187)
+void dice_tiles(uint32_t w, uint32_t h, uint32_t seed, std::vector<tgb_tile> &out) {
+    const uint32_t TileSize = 16;
+    uint64_t st = uint64_t(hash32(seed));
+    out.clear();
+    for (uint32_t y = 0; y < h; y += TileSize)
+        for (uint32_t x = 0; x < w; x += TileSize) {
+            tgb_tile t; t.x = x; t.y = y; t.w = std::min(TileSize, w - x); t.h = std::min(TileSize, h - y);
+            t.sampler_seed = hash32(pcg_next(st));
+            out.push_back(t);
+        }
+}
+
+int set_tiles(tgb_ctx *c, const tgb_tile *tiles, uint32_t n_tiles, uint32_t seed) {
+    std::vector<tgb_tile> own;
+    if (n_tiles == 0) { dice_tiles(c->res_x, c->res_y, seed, own); tiles = own.data(); n_tiles = uint32_t(own.size()); }
+    if (c->tiles_cached.size() == n_tiles && n_tiles && std::memcmp(c->tiles_cached.data(), tiles, n_tiles*sizeof(tgb_tile)) == 0) return TGB_OK;
+    std::vector<uint32_t> pid, pseed;
+    for (uint32_t t = 0; t < n_tiles; ++t) {
+        const tgb_tile &tl = tiles[t];
+        if (tl.x + tl.w > c->res_x || tl.y + tl.h > c->res_y) return fail(c, TGB_ERR_INVALID, "tile %u lies outside the image", t);
+        for (uint32_t y = 0; y < tl.h; ++y) for (uint32_t x = 0; x < tl.w; ++x) { pid.push_back((tl.x + x) + (tl.y + y)*c->res_x); pseed.push_back(tl.sampler_seed); }
+    }
+    if (pid.size() > c->pix_capacity) {
+        int rc;
+        if ((rc = dev_alloc(c, &c->pix_id, pid.size()))) return rc;
+        if ((rc = dev_alloc(c, &c->pix_seed, pid.size()))) return rc;
+        c->pix_capacity = uint32_t(pid.size());
+    }
+    c->n_pix = uint32_t(pid.size());
+    if (c->n_pix) {
+        CU(cudaMemcpyAsync(c->pix_id, pid.data(), pid.size()*4, cudaMemcpyHostToDevice, c->stream));
+        CU(cudaMemcpyAsync(c->pix_seed, pseed.data(), pseed.size()*4, cudaMemcpyHostToDevice, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+    }
+    c->tiles_cached.assign(tiles, tiles + n_tiles);
+    return TGB_OK;
+}
+
+inline unsigned blocks(uint32_t n, unsigned bs) { return n ? (n + bs - 1)/bs : 1; }
+
+// The wavefront loop: the GPU analogue of renderTile over (pixels of the tiles) x (sample range).
+int render_device(tgb_ctx *c, uint32_t spp_begin, uint32_t spp_count) {
+    if (c->n_pix == 0 || spp_count == 0) return TGB_OK;
+    const DScene &sc = c->sc;
+    CU(cudaEventRecord(c->ev0, c->stream));
+    uint64_t launches = 0;
+    float trace_ms = 0.0f; uint64_t trace_launches = 0;
+    for (uint32_t pix0 = 0; pix0 < c->n_pix; pix0 += c->capacity) {
+        uint32_t npx = std::min(c->capacity, c->n_pix - pix0);
+        uint32_t chunk = std::max(1u, c->capacity/npx);
+        for (uint32_t s0 = 0; s0 < spp_count; s0 += chunk) {
+            uint32_t ns = std::min(chunk, spp_count - s0);
+            BatchInfo bi; bi.pix_id = c->pix_id + pix0; bi.pix_seed = c->pix_seed + pix0; bi.n_pix = npx;
+            bi.spp_begin = spp_begin + s0; bi.n_paths = npx*ns;
+            uint32_t *qa = c->queue_a, *qb = c->queue_b; uint32_t *ca = c->counts, *cb = c->counts + 1, *cs = c->counts + 2;
+            k_raygen<<<blocks(bi.n_paths, 256), 256, 0, c->stream>>>(sc, c->st, bi, qa, ca); launches++;
+            uint32_t n_active = bi.n_paths;
+            for (int bounce = 0; n_active > 0; ++bounce) {
+                if (c->abort_flag.load()) { cudaStreamSynchronize(c->stream); return fail(c, TGB_ERR_ABORTED, "render aborted"); }
+                CU(cudaMemsetAsync(cb, 0, sizeof(uint32_t), c->stream));         // next queue count
+                CU(cudaMemsetAsync(cs, 0, sizeof(uint32_t), c->stream));         // shadow query count
+                if (c->profiling) CU(cudaEventRecord(c->evt0, c->stream));
+                k_trace<<<blocks(n_active, 128), 128, 0, c->stream>>>(sc, c->st, qa, ca, c->ctr); launches++;
+                if (c->profiling) CU(cudaEventRecord(c->evt1, c->stream));
+                k_shade<<<blocks(n_active, 128), 128, 0, c->stream>>>(sc, c->st, bi, qa, ca, c->squeue, cs); launches++;
+                k_shadow<<<blocks(2*n_active, 128), 128, 0, c->stream>>>(sc, c->st, c->squeue, cs, c->ctr); launches++;
+                k_accum<<<blocks(n_active, 256), 256, 0, c->stream>>>(sc, c->st, qa, ca, qb, cb); launches++;
+                CU(cudaMemcpyAsync(c->h_counts, c->counts, 3*sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+                CU(cudaStreamSynchronize(c->stream));
+                if (c->profiling) { float ms = 0.0f; cudaEventElapsedTime(&ms, c->evt0, c->evt1); trace_ms += ms; trace_launches++; }
+                n_active = c->h_counts[cb - c->counts];
+                std::swap(qa, qb); std::swap(ca, cb);
+                if (bounce > 4096) return fail(c, TGB_ERR_CUDA, "wavefront loop did not terminate");
+            }
+            k_resolve<<<blocks(npx, 256), 256, 0, c->stream>>>(c->st, bi, ns, c->fb, c->fb_count); launches++;
+        }
+    }
+    CU(cudaEventRecord(c->ev1, c->stream));
+    CU(cudaMemcpyAsync(c->h_ctr, c->ctr, sizeof(Counters), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    CU(cudaGetLastError());
+    float ms = 0.0f; cudaEventElapsedTime(&ms, c->ev0, c->ev1);
+    c->stats.samples += uint64_t(c->n_pix)*spp_count;
+    c->stats.rays = c->h_ctr->rays; c->stats.hits = c->h_ctr->hits;
+    c->stats.kernel_launches += launches;
+    c->stats.total_ms += ms; c->stats.trace_ms += trace_ms; c->stats.trace_launches += trace_launches;
+    return TGB_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+uint32_t tgb200_abi_version(void) { return TGB200_ABI_VERSION; }
+
+const char *tgb200_last_error(const tgb_ctx *ctx) { return ctx ? ctx->error.c_str() : g_create_error.c_str(); }
+
+void tgb200_destroy(tgb_ctx *c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    for (void *p : c->allocs) cudaFree(p);
+    if (c->h_counts) cudaFreeHost(c->h_counts);
+    if (c->h_ctr) cudaFreeHost(c->h_ctr);
+    if (c->h_fb) cudaFreeHost(c->h_fb);
+    if (c->h_fb_count) cudaFreeHost(c->h_fb_count);
+    for (cudaEvent_t e : {c->ev0, c->ev1, c->evt0, c->evt1}) if (e) cudaEventDestroy(e);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+int tgb200_create(const tgb_scene_desc *d, tgb_ctx **out) {
+    tgb_ctx *c = nullptr;
+    if (!d || !out) return fail(nullptr, TGB_ERR_INVALID, "null argument");
+    *out = nullptr;
+    if (d->abi_version != TGB200_ABI_VERSION) return fail(nullptr, TGB_ERR_INVALID, "ABI version mismatch (got %u, library is %u)", d->abi_version, TGB200_ABI_VERSION);
+    if (!d->settings.use_sobol) return fail(nullptr, TGB_ERR_UNSUPPORTED, "only the Sobol sampler (renderer.stratified_sampler = true) is on the hot path");
+    if (d->settings.supplemental_mode != 0) return fail(nullptr, TGB_ERR_UNSUPPORTED, "supplemental_mode %u: the per-tile serial PCG stream cannot be reproduced by a wavefront renderer (DESIGN.md section 3)", d->settings.supplemental_mode);
+    if (d->camera.res_x == 0 || d->camera.res_y == 0) return fail(nullptr, TGB_ERR_INVALID, "empty image");
+    if (d->settings.max_bounces > 255 || d->settings.max_bounces < 0) return fail(nullptr, TGB_ERR_UNSUPPORTED, "max_bounces must be in [0, 255]");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { cudaGetLastError(); return fail(nullptr, TGB_ERR_NO_DEVICE, "no CUDA device available (this library has no CPU fallback)"); }
+    int dev = d->settings.device;
+    if (dev < 0) { if (cudaGetDevice(&dev) != cudaSuccess) dev = 0; }
+    if (dev >= ndev) return fail(nullptr, TGB_ERR_NO_DEVICE, "CUDA device %d not present (%d devices)", dev, ndev);
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, dev) != cudaSuccess) return fail(nullptr, TGB_ERR_NO_DEVICE, "cannot query device %d", dev);
+    if (prop.major != 10) return fail(nullptr, TGB_ERR_NO_DEVICE, "device %d is sm_%d%d; this library is built for sm_100a only", dev, prop.major, prop.minor);
+    c = new tgb_ctx();
+    c->device = dev;
+    int rc = TGB_OK;
+    do {
+        if (cudaSetDevice(dev) != cudaSuccess) { rc = fail(c, TGB_ERR_CUDA, "cudaSetDevice(%d) failed", dev); break; }
+        if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { rc = fail(c, TGB_ERR_CUDA, "cudaStreamCreate failed"); break; }
+        for (cudaEvent_t *e : {&c->ev0, &c->ev1, &c->evt0, &c->evt1}) cudaEventCreate(e);
+        if ((rc = upload_scene(c, d))) break;
+        uint32_t cap = d->settings.max_paths_in_flight ? d->settings.max_paths_in_flight : (1u << 22);
+        cap = std::max(cap, 1024u);
+        if ((rc = alloc_wavefront(c, cap))) break;
+    } while (0);
+    if (rc) { g_create_error = c->error; tgb200_destroy(c); return rc; }
+    *out = c;
+    return TGB_OK;
+}
+
+int tgb200_clear_framebuffer(tgb_ctx *c) {
+    if (!c) return TGB_ERR_INVALID;
+    CU(cudaSetDevice(c->device));
+    size_t npx = size_t(c->res_x)*c->res_y;
+    CU(cudaMemsetAsync(c->fb, 0, npx*3*sizeof(float), c->stream));
+    CU(cudaMemsetAsync(c->fb_count, 0, npx*sizeof(uint32_t), c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return TGB_OK;
+}
+
+int tgb200_render_resident(tgb_ctx *c, const tgb_tile *tiles, uint32_t n_tiles, uint32_t seed, uint32_t spp_begin, uint32_t spp_count) {
+    if (!c) return TGB_ERR_INVALID;
+    if (n_tiles && !tiles) return fail(c, TGB_ERR_INVALID, "null tile list");
+    CU(cudaSetDevice(c->device));
+    c->abort_flag.store(0);
+    int rc = set_tiles(c, tiles, n_tiles, seed);
+    if (rc) return rc;
+    return render_device(c, spp_begin, spp_count);
+}
+
+int tgb200_read_framebuffer(tgb_ctx *c, float *rgb_mean, uint32_t *count) {
+    if (!c || !rgb_mean) return TGB_ERR_INVALID;
+    CU(cudaSetDevice(c->device));
+    size_t npx = size_t(c->res_x)*c->res_y;
+    CU(cudaMemcpyAsync(c->h_fb, c->fb, npx*3*sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    if (count) CU(cudaMemcpyAsync(c->h_fb_count, c->fb_count, npx*sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    std::memcpy(rgb_mean, c->h_fb, npx*3*sizeof(float));
+    if (count) std::memcpy(count, c->h_fb_count, npx*sizeof(uint32_t));
+    return TGB_OK;
+}
+
+int tgb200_render_tiles(tgb_ctx *c, const tgb_tile *tiles, uint32_t n_tiles, uint32_t seed, uint32_t spp_begin, uint32_t spp_count,
+                        float *rgb_mean, uint32_t *count) {
+    if (!c || !rgb_mean) return c ? fail(c, TGB_ERR_INVALID, "null framebuffer") : TGB_ERR_INVALID;
+    if (n_tiles && !tiles) return fail(c, TGB_ERR_INVALID, "null tile list");
+    CU(cudaSetDevice(c->device));
+    size_t npx = size_t(c->res_x)*c->res_y;
+    // host -> device: the caller's running mean and counts are the input state
+    std::memcpy(c->h_fb, rgb_mean, npx*3*sizeof(float));
+    CU(cudaMemcpyAsync(c->fb, c->h_fb, npx*3*sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    if (count) {
+        std::memcpy(c->h_fb_count, count, npx*sizeof(uint32_t));
+        CU(cudaMemcpyAsync(c->fb_count, c->h_fb_count, npx*sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
+    } else {
+        // without counts the running mean restarts from the sample index range's start
+        std::vector<uint32_t> base(npx, spp_begin);
+        std::memcpy(c->h_fb_count, base.data(), npx*sizeof(uint32_t));
+        CU(cudaMemcpyAsync(c->fb_count, c->h_fb_count, npx*sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
+    }
+    c->abort_flag.store(0);
+    int rc = set_tiles(c, tiles, n_tiles, seed);
+    if (rc) return rc;
+    if ((rc = render_device(c, spp_begin, spp_count))) return rc;
+    return tgb200_read_framebuffer(c, rgb_mean, count);
+}
+
+int tgb200_framebuffer_device_ptr(tgb_ctx *c, void **rgb_mean_dev, uint64_t *n_bytes) {
+    if (!c || !rgb_mean_dev) return TGB_ERR_INVALID;
+    *rgb_mean_dev = c->fb;
+    if (n_bytes) *n_bytes = uint64_t(c->res_x)*c->res_y*3*sizeof(float);
+    return TGB_OK;
+}
+
+int tgb200_trace_closest(tgb_ctx *c, const tgb_ray *rays, tgb_hit *hits, uint32_t n) {
+    if (!c || (n && (!rays || !hits))) return TGB_ERR_INVALID;
+    if (n == 0) return TGB_OK;
+    CU(cudaSetDevice(c->device));
+    tgb_ray *dr = nullptr; tgb_hit *dh = nullptr;
+    CU(cudaMalloc(reinterpret_cast<void **>(&dr), size_t(n)*sizeof(tgb_ray)));
+    cudaError_t e = cudaMalloc(reinterpret_cast<void **>(&dh), size_t(n)*sizeof(tgb_hit));
+    if (e != cudaSuccess) { cudaFree(dr); return fail(c, TGB_ERR_OOM, "cudaMalloc failed: %s", cudaGetErrorString(e)); }
+    int rc = TGB_OK;
+    do {
+        if ((e = cudaMemcpyAsync(dr, rays, size_t(n)*sizeof(tgb_ray), cudaMemcpyHostToDevice, c->stream)) != cudaSuccess) break;
+        k_trace_rays<<<blocks(n, 128), 128, 0, c->stream>>>(c->sc, dr, dh, n);
+        c->stats.kernel_launches++;
+        if ((e = cudaMemcpyAsync(hits, dh, size_t(n)*sizeof(tgb_hit), cudaMemcpyDeviceToHost, c->stream)) != cudaSuccess) break;
+        e = cudaStreamSynchronize(c->stream);
+    } while (0);
+    if (e != cudaSuccess) rc = fail(c, TGB_ERR_CUDA, "trace_closest failed: %s", cudaGetErrorString(e));
+    cudaFree(dr); cudaFree(dh);
+    return rc;
+}
+
+int tgb200_get_stats(tgb_ctx *c, tgb_stats *out) {
+    if (!c || !out) return TGB_ERR_INVALID;
+    *out = c->stats;
+    return TGB_OK;
+}
+
+int tgb200_reset_stats(tgb_ctx *c) {
+    if (!c) return TGB_ERR_INVALID;
+    CU(cudaSetDevice(c->device));
+    c->stats = tgb_stats{};
+    CU(cudaMemsetAsync(c->ctr, 0, sizeof(Counters), c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return TGB_OK;
+}
+
+int tgb200_set_profiling(tgb_ctx *c, int enable) {
+    if (!c) return TGB_ERR_INVALID;
+    c->profiling = enable != 0;
+    return TGB_OK;
+}
+
+int tgb200_scene_info(tgb_ctx *c, uint32_t *n_tris, uint32_t *n_nodes, uint32_t *bvh_depth, uint64_t *geom_bytes, uint32_t *capacity) {
+    if (!c) return TGB_ERR_INVALID;
+    if (n_tris) *n_tris = c->n_tris;
+    if (n_nodes) *n_nodes = c->sc.n_nodes;
+    if (bvh_depth) *bvh_depth = c->bvh_depth;
+    if (geom_bytes) *geom_bytes = c->geom_bytes;
+    if (capacity) *capacity = c->capacity;
+    return TGB_OK;
+}
+
+int tgb200_abort(tgb_ctx *c) {
+    if (!c) return TGB_ERR_INVALID;
+    c->abort_flag.store(1);
+    return TGB_OK;
+}
+
+}  // extern "C"

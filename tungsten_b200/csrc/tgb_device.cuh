@@ -1,0 +1,741 @@
+// Device-side building blocks of the wavefront path tracer: fp32 vector math with the reference's
+// operation order, Sobol/PCG sampling, textures, BSDF lobes, light sampling.
+// Compiled with -fmad=false: the reference is built without FMA contraction (CMakeLists.txt:17-19),
+// and radiance parity is judged against it.  Every function cites the reference code it replaces
+// (paths relative to /root/reference/src/core).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <math.h>
+
+#include "../../include/tgb200.h"
+
+namespace tgb {
+
+// ---------------------------------------------------------------- math (math/Vec.hpp:140-193)
+struct V3 { float x, y, z; };
+#define TGB_HD __host__ __device__ __forceinline__
+#define TGB_D  __device__ __forceinline__
+
+constexpr float PI_F = 3.1415926536f;             // math/Angle.hpp:8-16 (fp32 constexpr products)
+constexpr float TWO_PI_F = PI_F*2.0f;
+constexpr float INV_PI_F = 1.0f/PI_F;
+constexpr float INV_TWO_PI_F = 0.5f*INV_PI_F;
+constexpr float INV_FOUR_PI_F = 0.25f*INV_PI_F;
+
+TGB_HD V3 v3(float x, float y, float z) { V3 r; r.x = x; r.y = y; r.z = z; return r; }
+TGB_HD V3 v3s(float a) { return v3(a, a, a); }
+TGB_HD V3 operator+(V3 a, V3 b) { return v3(a.x + b.x, a.y + b.y, a.z + b.z); }
+TGB_HD V3 operator-(V3 a, V3 b) { return v3(a.x - b.x, a.y - b.y, a.z - b.z); }
+TGB_HD V3 operator*(V3 a, V3 b) { return v3(a.x*b.x, a.y*b.y, a.z*b.z); }
+TGB_HD V3 operator/(V3 a, V3 b) { return v3(a.x/b.x, a.y/b.y, a.z/b.z); }
+TGB_HD V3 operator*(V3 a, float s) { return v3(a.x*s, a.y*s, a.z*s); }
+TGB_HD V3 operator/(V3 a, float s) { return v3(a.x/s, a.y/s, a.z/s); }
+TGB_HD V3 operator-(V3 a) { return v3(-a.x, -a.y, -a.z); }
+TGB_HD float dot(V3 a, V3 b) { float s = a.x*b.x; s += a.y*b.y; s += a.z*b.z; return s; }
+TGB_HD V3 cross(V3 a, V3 b) { return v3(a.y*b.z - a.z*b.y, a.z*b.x - a.x*b.z, a.x*b.y - a.y*b.x); }
+TGB_HD float length_sq(V3 a) { return dot(a, a); }
+TGB_HD float length(V3 a) { return sqrtf(dot(a, a)); }
+TGB_HD V3 normalize(V3 a) { float inv = 1.0f/length(a); return v3(a.x*inv, a.y*inv, a.z*inv); }
+TGB_HD float max_comp(V3 a) { float m = a.x; if (a.y > m) m = a.y; if (a.z > m) m = a.z; return m; }
+TGB_HD float sum(V3 a) { float s = a.x; s += a.y; s += a.z; return s; }
+TGB_HD float avg(V3 a) { return sum(a)*(1.0f/3.0f); }
+TGB_HD bool is_zero(V3 a) { return a.x == 0.0f && a.y == 0.0f && a.z == 0.0f; }       // Vec.hpp:429-435
+TGB_HD V3 vabs(V3 a) { return v3(fabsf(a.x), fabsf(a.y), fabsf(a.z)); }
+TGB_HD float maxf(float a, float b) { return a > b ? a : b; }                         // math/MathUtil.hpp max/min
+TGB_HD float minf(float a, float b) { return a < b ? a : b; }
+TGB_HD float sqr(float a) { return a*a; }
+TGB_HD float sgnE(float x) { return x < 0.0f ? -1.0f : 1.0f; }
+TGB_HD V3 m3mul(const float *m, V3 b) {                                               // Mat4f::transformVector
+    return v3(m[0]*b.x + m[1]*b.y + m[2]*b.z, m[3]*b.x + m[4]*b.y + m[5]*b.z, m[6]*b.x + m[7]*b.y + m[8]*b.z);
+}
+TGB_HD float comp(V3 a, int i) { return i == 0 ? a.x : (i == 1 ? a.y : a.z); }
+
+struct Frame { V3 n, t, b; };
+TGB_HD Frame frame_from_normal(V3 n) {                                                // math/TangentFrame.hpp:22-31
+    Frame f; f.n = n;
+    float sign = copysignf(1.0f, n.z);
+    const float a = -1.0f/(sign + n.z);
+    const float b = n.x*n.y*a;
+    f.t = v3(1.0f + sign*n.x*n.x*a, sign*b, -sign*n.x);
+    f.b = v3(b, sign + n.y*n.y*a, -n.y);
+    return f;
+}
+TGB_HD V3 to_local(const Frame &f, V3 p) { return v3(dot(f.t, p), dot(f.b, p), dot(f.n, p)); }
+TGB_HD V3 to_global(const Frame &f, V3 p) { return f.t*p.x + f.b*p.y + f.n*p.z; }
+
+// ---------------------------------------------------------------- integer hashing / RNG
+TGB_HD uint32_t hash32(uint32_t x) {                                                  // math/MathUtil.hpp:120-128
+    x = ~x + (x << 15); x = x ^ (x >> 12); x = x + (x << 2); x = x ^ (x >> 4); x = x*2057u; x = x ^ (x >> 16);
+    return x;
+}
+TGB_HD uint32_t pcg_next(uint64_t &state) {                                           // sampling/UniformSampler.hpp:40-47
+    uint64_t old = state;
+    state = old*6364136223846793005ULL + 1ULL;
+    uint32_t xs = uint32_t(((old >> 18u) ^ old) >> 27u);
+    uint32_t rot = uint32_t(old >> 59u);
+    return (xs >> rot) | (xs << (uint32_t(-int32_t(rot)) & 31));
+}
+TGB_HD float normalized_uint(uint32_t i) {                                            // math/BitManip.hpp:47-50
+#ifdef __CUDA_ARCH__
+    return __uint_as_float((i >> 9u) | 0x3F800000u) - 1.0f;
+#else
+    union { uint32_t u; float f; } c; c.u = (i >> 9u) | 0x3F800000u; return c.f - 1.0f;
+#endif
+}
+
+// ---------------------------------------------------------------- device scene
+enum : uint32_t { LOBE_GLOSSY_R = 1, LOBE_GLOSSY_T = 2, LOBE_DIFFUSE_R = 4, LOBE_DIFFUSE_T = 8, LOBE_SPEC_R = 16,
+                  LOBE_SPEC_T = 32, LOBE_ANISO = 64, LOBE_FORWARD = 128, LOBE_SPECULAR = 48,
+                  LOBE_TRANSMISSIVE = 2 | 8 | 32, LOBE_ALL = 2 | 8 | 32 | 1 | 4 | 16 | 64 };   // bsdfs/BsdfLobes.hpp:13-34
+constexpr uint32_t LOBE_ALL_BUT_SPECULAR = ~uint32_t(LOBE_SPECULAR | LOBE_FORWARD);
+
+struct DTex {
+    uint32_t type; V3 value, value2; int res_u, res_v; uint32_t flags;
+    const float *texels;                                         // bitmap RGB fp32
+    const float *marg_pdf, *marg_cdf, *pdf, *cdf;                // spherical importance map (env lights)
+    V3 avg;
+};
+struct DBsdf {
+    uint32_t type, lobes, dist; int albedo_tex, rough_tex;
+    float ior, inv_ior; V3 eta, k; V3 scaled_sigma_a; float avg_transmittance, diffuse_fresnel, substrate_weight;
+    uint32_t enable_t;
+};
+enum : uint32_t { PF_EMISSIVE = 1, PF_SAMPLABLE = 2, PF_INFINITE = 4, PF_SMOOTH = 8 };
+struct DPrim {
+    uint32_t type, flags; int emission_tex;
+    uint32_t tri_first, n_tris, bsdf_first, bsdf_count;
+    V3 base, edge0, edge1, normal; float inv_uv_sq0, inv_uv_sq1, area;      // quad
+    V3 pos, scale; float rot[9], inv_rot[9];                                // cube / infinite sphere rotation
+    float total_area; const float *tri_pdf, *tri_cdf; const float *light_verts;   // emissive meshes: p0 p1 p2 per tri
+};
+struct DCamera { V3 pos; float m[9]; float plane_dist, ratio, pixel_size_x; uint32_t res_x, res_y, filter; float filter_cdf[32]; float filter_bin; };
+
+struct DScene {
+    DCamera cam; tgb_settings set;
+    const DPrim *prims; uint32_t n_prims;
+    const DBsdf *bsdfs; const uint32_t *slots; const DTex *tex;
+    const int *lights; int n_lights; const int *inf_lights; int n_inf_lights;
+    const int *analytic; int n_analytic;
+    // triangles: intersection records in BVH leaf order (3 x float4 each), leaf order -> global id,
+    // global id -> primitive, shading records by global id (4 x float4 each)
+    const float4 *tri_isect; const uint32_t *tri_global; const uint32_t *tri_prim; const float4 *tri_shade;
+    const float4 *nodes; uint32_t n_nodes; uint32_t n_tris;
+    const uint32_t *sobol;      // 1024 x 32 direction matrices
+};
+
+// ---------------------------------------------------------------- sampler
+// SobolPathSampler (sampling/SobolPathSampler.hpp:12-84) with the per-path reseed of the supplemental
+// PCG stream (parity contract).
+struct Sampler { const uint32_t *sobol; uint64_t pcg; uint32_t scramble, index, dimension; };
+
+TGB_D void sampler_start(Sampler &s, const uint32_t *sobol, uint32_t tile_seed, uint32_t pixel_id, uint32_t sample) {
+    s.sobol = sobol;
+    s.scramble = tile_seed ^ hash32(pixel_id);
+    s.index = sample; s.dimension = 0;
+    s.pcg = (uint64_t(s.scramble) << 32) | uint64_t(hash32(sample));
+}
+TGB_D float sampler_pcg1d(Sampler &s) { return normalized_uint(pcg_next(s.pcg)); }
+TGB_D bool sampler_boolean(Sampler &s, float p_true) { return sampler_pcg1d(s) < p_true; }
+TGB_D float sampler_next1d(Sampler &s) {
+    if (s.dimension >= 1024) return sampler_pcg1d(s);
+    uint32_t index = (s.index & ~0xFFu) | ((s.index + s.scramble) & 0xFFu);
+    uint32_t result = s.scramble;
+    const uint32_t *m = s.sobol + s.dimension*32u;                                    // thirdparty/sobol/sobol.h:39-53
+    s.dimension++;
+    while (index) {
+        int b = __ffs(int(index)) - 1;
+        result ^= __ldg(m + b);
+        index &= index - 1;
+    }
+    return normalized_uint(result);
+}
+
+// ---------------------------------------------------------------- textures
+TGB_D V3 bitmap_texel(const DTex &t, int x, int y) {
+    const float *p = t.texels + 3*(size_t(y)*t.res_u + x);
+    return v3(__ldg(p), __ldg(p + 1), __ldg(p + 2));
+}
+TGB_D V3 tex_eval(const DTex &t, float u, float v) {
+    if (t.type == TGB_TEX_CONSTANT) return t.value;                                   // textures/ConstantTexture.cpp:50-58
+    if (t.type == TGB_TEX_CHECKER) {                                                  // textures/CheckerTexture.cpp:64-69
+        int ui = int(u*float(t.res_u)), vi = int(v*float(t.res_v));
+        return ((ui ^ vi) & 1) ? t.value : t.value2;
+    }
+    // BitmapTexture::operator[] (textures/BitmapTexture.cpp:298-352)
+    float fu = u*t.res_u, fv = (1.0f - v)*t.res_v;
+    bool linear = t.flags & 1, clampm = (t.flags >> 1) & 1;
+    if (linear) { fu -= 0.5f; fv -= 0.5f; }
+    int iu0 = fu < 0.0f ? -int(-fu) - 1 : int(fu);
+    int iv0 = fv < 0.0f ? -int(-fv) - 1 : int(fv);
+    int iu1 = iu0 + 1, iv1 = iv0 + 1;
+    fu -= iu0; fv -= iv0;
+    int w = t.res_u, h = t.res_v;
+    if (clampm) {
+        iu0 = min(max(iu0, 0), w - 1); iu1 = min(max(iu1, 0), w - 1);
+        iv0 = min(max(iv0, 0), h - 1); iv1 = min(max(iv1, 0), h - 1);
+    } else {
+        iu0 = ((iu0 % w) + w) % w; iu1 = ((iu1 % w) + w) % w;
+        iv0 = ((iv0 % h) + h) % h; iv1 = ((iv1 % h) + h) % h;
+    }
+    if (!linear) return bitmap_texel(t, iu0, iv0);
+    V3 x00 = bitmap_texel(t, iu0, iv0), x01 = bitmap_texel(t, iu1, iv0);
+    V3 x10 = bitmap_texel(t, iu0, iv1), x11 = bitmap_texel(t, iu1, iv1);
+    V3 a = x00*(1.0f - fu) + x01*fu;
+    V3 b = x10*(1.0f - fu) + x11*fu;
+    return a*(1.0f - fv) + b*fv;
+}
+
+// ---------------------------------------------------------------- camera filter (cameras/ReconstructionFilter.hpp:86-103)
+TGB_D float filter_sample1(const DCamera &c, float xi) {
+    const int R = 31;
+    bool negative = xi < 0.5f;
+    xi = negative ? xi*2.0f : (xi - 0.5f)*2.0f;
+    int idx = R - 1;
+    for (int i = 0; i < R - 1; ++i) if (xi < c.filter_cdf[i]) { idx = i; break; }
+    float pdf = c.filter_cdf[idx] - c.filter_cdf[idx - 1];
+    float u = c.filter_bin*(idx + (xi - c.filter_cdf[idx - 1])/pdf);
+    return negative ? -u : u;
+}
+
+// ---------------------------------------------------------------- Fresnel / microfacet
+TGB_D float dielectric_reflectance(float eta, float cosThetaI, float &cosThetaT) {    // bsdfs/Fresnel.hpp:75-92
+    if (cosThetaI < 0.0f) { eta = 1.0f/eta; cosThetaI = -cosThetaI; }
+    float sinThetaTSq = eta*eta*(1.0f - cosThetaI*cosThetaI);
+    if (sinThetaTSq > 1.0f) { cosThetaT = 0.0f; return 1.0f; }
+    cosThetaT = sqrtf(maxf(1.0f - sinThetaTSq, 0.0f));
+    float Rs = (eta*cosThetaI - cosThetaT)/(eta*cosThetaI + cosThetaT);
+    float Rp = (eta*cosThetaT - cosThetaI)/(eta*cosThetaT + cosThetaI);
+    return (Rs*Rs + Rp*Rp)*0.5f;
+}
+TGB_D float dielectric_reflectance(float eta, float c) { float t; return dielectric_reflectance(eta, c, t); }
+TGB_D float conductor_reflectance(float eta, float k, float cosThetaI) {              // bsdfs/Fresnel.hpp:102-118
+    float cosThetaISq = cosThetaI*cosThetaI;
+    float sinThetaISq = maxf(1.0f - cosThetaISq, 0.0f);
+    float sinThetaIQu = sinThetaISq*sinThetaISq;
+    float innerTerm = eta*eta - k*k - sinThetaISq;
+    float aSqPlusBSq = sqrtf(maxf(innerTerm*innerTerm + 4.0f*eta*eta*k*k, 0.0f));
+    float a = sqrtf(maxf((aSqPlusBSq + innerTerm)*0.5f, 0.0f));
+    float Rs = ((aSqPlusBSq + cosThetaISq) - (2.0f*a*cosThetaI))/((aSqPlusBSq + cosThetaISq) + (2.0f*a*cosThetaI));
+    float Rp = ((cosThetaISq*aSqPlusBSq + sinThetaIQu) - (2.0f*a*cosThetaI*sinThetaISq))/
+               ((cosThetaISq*aSqPlusBSq + sinThetaIQu) + (2.0f*a*cosThetaI*sinThetaISq));
+    return 0.5f*(Rs + Rs*Rp);
+}
+TGB_D V3 conductor_reflectance(V3 eta, V3 k, float c) {
+    return v3(conductor_reflectance(eta.x, k.x, c), conductor_reflectance(eta.y, k.y, c), conductor_reflectance(eta.z, k.z, c));
+}
+// bsdfs/Microfacet.hpp:27-130
+TGB_D float mf_roughness_to_alpha(uint32_t dist, float roughness) {
+    roughness = maxf(roughness, 1e-3f);
+    if (dist == TGB_DIST_PHONG) return 2.0f/(roughness*roughness) - 2.0f;
+    return roughness;
+}
+TGB_D float mf_D(uint32_t dist, float alpha, V3 m) {
+    if (m.z <= 0.0f) return 0.0f;
+    if (dist == TGB_DIST_PHONG) return (alpha + 2.0f)*INV_TWO_PI_F*float(pow(double(m.z), double(alpha)));
+    float alphaSq = alpha*alpha, cosThetaSq = m.z*m.z;
+    float tanThetaSq = maxf(1.0f - cosThetaSq, 0.0f)/cosThetaSq;
+    float cosThetaQu = cosThetaSq*cosThetaSq;
+    if (dist == TGB_DIST_BECKMANN) return INV_PI_F*expf(-tanThetaSq/alphaSq)/(alphaSq*cosThetaQu);
+    return alphaSq*INV_PI_F/(cosThetaQu*sqr(alphaSq + tanThetaSq));
+}
+TGB_D float mf_G1(uint32_t dist, float alpha, V3 v, V3 m) {
+    if (dot(v, m)*v.z <= 0.0f) return 0.0f;
+    float cosThetaSq = v.z*v.z;
+    if (dist == TGB_DIST_GGX) {
+        float alphaSq = alpha*alpha;
+        float tanThetaSq = maxf(1.0f - cosThetaSq, 0.0f)/cosThetaSq;
+        return 2.0f/(1.0f + sqrtf(1.0f + alphaSq*tanThetaSq));
+    }
+    float tanTheta = fabsf(sqrtf(maxf(1.0f - cosThetaSq, 0.0f))/v.z);
+    float a = dist == TGB_DIST_BECKMANN ? 1.0f/(alpha*tanTheta) : sqrtf(0.5f*alpha + 1.0f)/tanTheta;
+    if (a < 1.6f) return (3.535f*a + 2.181f*a*a)/(1.0f + 2.276f*a + 2.577f*a*a);
+    return 1.0f;
+}
+TGB_D float mf_G(uint32_t dist, float alpha, V3 i, V3 o, V3 m) { return mf_G1(dist, alpha, i, m)*mf_G1(dist, alpha, o, m); }
+TGB_D float mf_pdf(uint32_t dist, float alpha, V3 m) { return mf_D(dist, alpha, m)*m.z; }
+TGB_D V3 mf_sample(uint32_t dist, float alpha, float xix, float xiy) {
+    float phi = xiy*TWO_PI_F;
+    float cosTheta;
+    if (dist == TGB_DIST_BECKMANN) { float tanThetaSq = -alpha*alpha*logf(1.0f - xix); cosTheta = 1.0f/sqrtf(1.0f + tanThetaSq); }
+    else if (dist == TGB_DIST_PHONG) cosTheta = float(pow(double(xix), 1.0/(double(alpha) + 2.0)));
+    else { float tanThetaSq = alpha*alpha*xix/(1.0f - xix); cosTheta = 1.0f/sqrtf(1.0f + tanThetaSq); }
+    float r = sqrtf(maxf(1.0f - cosTheta*cosTheta, 0.0f));
+    return v3(cosf(phi)*r, sinf(phi)*r, cosTheta);
+}
+TGB_D V3 cosine_hemisphere(float xix, float xiy) {                                     // sampling/SampleWarp.hpp:42-52
+    float phi = xix*TWO_PI_F;
+    float r = sqrtf(xiy);
+    return v3(cosf(phi)*r, sinf(phi)*r, sqrtf(maxf(1.0f - xiy, 0.0f)));
+}
+TGB_D float cosine_hemisphere_pdf(V3 p) { return fabsf(p.z)*INV_PI_F; }
+TGB_D float power_heuristic(float a, float b) { return (a*a)/(a*a + b*b); }            // SampleWarp.hpp:189-192
+
+// ---------------------------------------------------------------- surface records
+struct Surface {            // IntersectionInfo (primitives/IntersectionInfo.hpp:11-22) + what evalDirect needs
+    V3 Ng, Ns, p, w; float u, v; int prim, bsdf; bool backside;
+};
+struct Event {              // SurfaceScatterEvent (samplerecords/SurfaceScatterEvent.hpp:14-66)
+    Frame frame; V3 wi, wo, weight; float pdf; uint32_t requested, sampled; bool flipped;
+};
+
+TGB_D V3 bsdf_albedo(const DScene &sc, const DBsdf &b, const Surface &s) { return tex_eval(sc.tex[b.albedo_tex], s.u, s.v); }
+TGB_D float bsdf_roughness(const DScene &sc, const DBsdf &b, const Surface &s) { return tex_eval(sc.tex[b.rough_tex], s.u, s.v).x; }
+TGB_D bool check_reflection_constraint(V3 wi, V3 wo) {                                 // bsdfs/Bsdf.hpp:43-46
+    return fabsf(wi.z*wo.z - wi.x*wo.x - wi.y*wo.y - 1.0f) < 1e-3f;
+}
+TGB_D V3 vexp(V3 a) { return v3(expf(a.x), expf(a.y), expf(a.z)); }
+
+// RoughDielectricBsdf::sampleBase / evalBase / pdfBase (bsdfs/RoughDielectricBsdf.cpp:55-131,133-164,198-234)
+TGB_D bool rd_sample_base(Sampler &smp, Event &e, bool sampleR, bool sampleT, float roughness, float ior, uint32_t dist) {
+    float wiDotN = e.wi.z;
+    float eta = wiDotN < 0.0f ? ior : 1.0f/ior;
+    float sampleRoughness = (1.2f - 0.2f*sqrtf(fabsf(wiDotN)))*roughness;
+    float alpha = mf_roughness_to_alpha(dist, roughness);
+    float sampleAlpha = mf_roughness_to_alpha(dist, sampleRoughness);
+    float xa = sampler_next1d(smp), xb = sampler_next1d(smp);
+    V3 m = mf_sample(dist, sampleAlpha, xa, xb);
+    float pm = mf_pdf(dist, sampleAlpha, m);
+    if (pm < 1e-10f) return false;
+    float wiDotM = dot(e.wi, m);
+    float cosThetaT = 0.0f;
+    float F = dielectric_reflectance(1.0f/ior, wiDotM, cosThetaT);
+    float etaM = wiDotM < 0.0f ? ior : 1.0f/ior;
+    bool reflect;
+    if (sampleR && sampleT) reflect = sampler_boolean(smp, F);
+    else if (sampleT) { if (F == 1.0f) return false; reflect = false; }
+    else if (sampleR) reflect = true;
+    else return false;
+    if (reflect) e.wo = m*(2.0f*wiDotM) - e.wi;
+    else e.wo = m*(etaM*wiDotM - sgnE(wiDotM)*cosThetaT) - e.wi*etaM;
+    float woDotN = e.wo.z;
+    bool reflected = wiDotN*woDotN > 0.0f;
+    if (reflected != reflect) return false;
+    float woDotM = dot(e.wo, m);
+    float G = mf_G(dist, alpha, e.wi, e.wo, m);
+    float D = mf_D(dist, alpha, m);
+    e.weight = v3s(fabsf(wiDotM)*G*D/(fabsf(wiDotN)*pm));
+    if (reflect) { e.pdf = pm*0.25f/fabsf(wiDotM); e.sampled = LOBE_GLOSSY_R; }
+    else { e.pdf = pm*fabsf(woDotM)/sqr(eta*wiDotM + woDotM); e.sampled = LOBE_GLOSSY_T; }
+    if (sampleR && sampleT) { if (reflect) e.pdf *= F; else e.pdf *= 1.0f - F; }
+    else { if (reflect) e.weight = e.weight*F; else e.weight = e.weight*(1.0f - F); }
+    return true;
+}
+TGB_D void rd_microfacet_normal(const Event &e, bool reflect, float eta, float wiDotN, V3 &m) {
+    if (reflect) m = normalize(e.wi + e.wo)*sgnE(wiDotN);
+    else m = -normalize(e.wi*eta + e.wo);
+}
+TGB_D V3 rd_eval_base(const Event &e, bool sampleR, bool sampleT, float roughness, float ior, uint32_t dist) {
+    float wiDotN = e.wi.z, woDotN = e.wo.z;
+    bool reflect = wiDotN*woDotN >= 0.0f;
+    if ((reflect && !sampleR) || (!reflect && !sampleT)) return v3s(0.0f);
+    float alpha = mf_roughness_to_alpha(dist, roughness);
+    float eta = wiDotN < 0.0f ? ior : 1.0f/ior;
+    V3 m; rd_microfacet_normal(e, reflect, eta, wiDotN, m);
+    float wiDotM = dot(e.wi, m), woDotM = dot(e.wo, m);
+    float F = dielectric_reflectance(1.0f/ior, wiDotM);
+    float G = mf_G(dist, alpha, e.wi, e.wo, m);
+    float D = mf_D(dist, alpha, m);
+    if (reflect) return v3s((F*G*D*0.25f)/fabsf(wiDotN));
+    return v3s(fabsf(wiDotM*woDotM)*(1.0f - F)*G*D/(sqr(eta*wiDotM + woDotM)*fabsf(wiDotN)));
+}
+TGB_D float rd_pdf_base(const Event &e, bool sampleR, bool sampleT, float roughness, float ior, uint32_t dist) {
+    float wiDotN = e.wi.z, woDotN = e.wo.z;
+    bool reflect = wiDotN*woDotN >= 0.0f;
+    if ((reflect && !sampleR) || (!reflect && !sampleT)) return 0.0f;
+    float sampleRoughness = (1.2f - 0.2f*sqrtf(fabsf(wiDotN)))*roughness;
+    float sampleAlpha = mf_roughness_to_alpha(dist, sampleRoughness);
+    float eta = wiDotN < 0.0f ? ior : 1.0f/ior;
+    V3 m; rd_microfacet_normal(e, reflect, eta, wiDotN, m);
+    float wiDotM = dot(e.wi, m), woDotM = dot(e.wo, m);
+    float F = dielectric_reflectance(1.0f/ior, wiDotM);
+    float pm = mf_pdf(dist, sampleAlpha, m);
+    float pdf;
+    if (reflect) pdf = pm*0.25f/fabsf(wiDotM);
+    else pdf = pm*fabsf(woDotM)/sqr(eta*wiDotM + woDotM);
+    if (sampleR && sampleT) { if (reflect) pdf *= F; else pdf *= 1.0f - F; }
+    return pdf;
+}
+TGB_D V3 plastic_substrate(const DBsdf &b, V3 albedo, float Fi, float Fo, float eta) {
+    V3 denom = v3s(1.0f) - albedo*b.diffuse_fresnel;
+    return (albedo/denom)*((1.0f - Fi)*(1.0f - Fo)*eta*eta);
+}
+TGB_D float bsdf_eta(const DBsdf &b, const Event &e) {                                 // bsdfs/Bsdf.hpp:99-103; RoughDielectricBsdf.cpp:274-280
+    if (b.type == TGB_BSDF_ROUGH_DIELECTRIC) {
+        if (e.wi.z*e.wo.z >= 0.0f) return 1.0f;
+        return e.wi.z < 0.0f ? b.ior : b.inv_ior;
+    }
+    return 1.0f;
+}
+
+// Bsdf::sample(event, adjoint=false) (bsdfs/Bsdf.hpp:71-83) over the per-lobe sample() bodies
+TGB_D bool bsdf_sample(const DScene &sc, const DBsdf &b, const Surface &s, Sampler &smp, Event &e) {
+    bool ok = false;
+    switch (b.type) {
+    case TGB_BSDF_LAMBERT: {                                                           // bsdfs/LambertBsdf.cpp:27-38
+        if (!(e.requested & LOBE_DIFFUSE_R)) break;
+        if (e.wi.z <= 0.0f) break;
+        float xa = sampler_next1d(smp), xb = sampler_next1d(smp);
+        e.wo = cosine_hemisphere(xa, xb);
+        e.pdf = cosine_hemisphere_pdf(e.wo);
+        e.weight = bsdf_albedo(sc, b, s);
+        e.sampled = LOBE_DIFFUSE_R;
+        ok = true; break; }
+    case TGB_BSDF_ROUGH_CONDUCTOR: {                                                   // bsdfs/RoughConductorBsdf.cpp:60-90
+        if (!(e.requested & LOBE_GLOSSY_R)) break;
+        if (e.wi.z <= 0.0f) break;
+        float roughness = bsdf_roughness(sc, b, s);
+        float alpha = mf_roughness_to_alpha(b.dist, roughness);
+        float xa = sampler_next1d(smp), xb = sampler_next1d(smp);
+        V3 m = mf_sample(b.dist, alpha, xa, xb);
+        float wiDotM = dot(e.wi, m);
+        e.wo = m*(2.0f*wiDotM) - e.wi;
+        if (wiDotM <= 0.0f || e.wo.z <= 0.0f) break;
+        float G = mf_G(b.dist, alpha, e.wi, e.wo, m);
+        float D = mf_D(b.dist, alpha, m);
+        float mPdf = mf_pdf(b.dist, alpha, m);
+        float pdf = mPdf*0.25f/wiDotM;
+        float weight = wiDotM*G*D/(e.wi.z*mPdf);
+        V3 F = conductor_reflectance(b.eta, b.k, wiDotM);
+        e.pdf = pdf;
+        e.weight = bsdf_albedo(sc, b, s)*(F*weight);
+        e.sampled = LOBE_GLOSSY_R;
+        ok = true; break; }
+    case TGB_BSDF_ROUGH_DIELECTRIC: {                                                  // RoughDielectricBsdf.cpp:236-244
+        bool sampleR = (e.requested & LOBE_GLOSSY_R) != 0;
+        bool sampleT = (e.requested & LOBE_GLOSSY_T) != 0 && b.enable_t;
+        float roughness = bsdf_roughness(sc, b, s);
+        ok = rd_sample_base(smp, e, sampleR, sampleT, roughness, b.ior, b.dist);
+        e.weight = e.weight*bsdf_albedo(sc, b, s);
+        break; }
+    case TGB_BSDF_PLASTIC: {                                                           // bsdfs/PlasticBsdf.cpp:45-88
+        if (e.wi.z <= 0.0f) break;
+        bool sampleR = (e.requested & LOBE_SPEC_R) != 0, sampleT = (e.requested & LOBE_DIFFUSE_R) != 0;
+        V3 wi = e.wi;
+        float eta = 1.0f/b.ior;
+        float Fi = dielectric_reflectance(eta, wi.z);
+        float substrateWeight = b.avg_transmittance*(1.0f - Fi);
+        float specularWeight = Fi;
+        float specularProbability;
+        if (sampleR && sampleT) specularProbability = specularWeight/(specularWeight + substrateWeight);
+        else if (sampleR) specularProbability = 1.0f;
+        else if (sampleT) specularProbability = 0.0f;
+        else break;
+        if (sampleR && sampler_boolean(smp, specularProbability)) {
+            e.wo = v3(-wi.x, -wi.y, wi.z);
+            e.pdf = specularProbability;
+            e.weight = v3s(Fi/specularProbability);
+            e.sampled = LOBE_SPEC_R;
+        } else {
+            float xa = sampler_next1d(smp), xb = sampler_next1d(smp);
+            V3 wo = cosine_hemisphere(xa, xb);
+            float Fo = dielectric_reflectance(eta, wo.z);
+            V3 diffuseAlbedo = bsdf_albedo(sc, b, s);
+            e.wo = wo;
+            e.weight = plastic_substrate(b, diffuseAlbedo, Fi, Fo, eta);
+            if (max_comp(b.scaled_sigma_a) > 0.0f)
+                e.weight = e.weight*vexp(b.scaled_sigma_a*(-1.0f/e.wo.z - 1.0f/e.wi.z));
+            e.pdf = cosine_hemisphere_pdf(e.wo)*(1.0f - specularProbability);
+            e.weight = e.weight/(1.0f - specularProbability);
+            e.sampled = LOBE_DIFFUSE_R;
+        }
+        ok = true; break; }
+    case TGB_BSDF_ROUGH_PLASTIC: {                                                     // bsdfs/RoughPlasticBsdf.cpp:54-113
+        if (e.wi.z <= 0.0f) break;
+        bool sampleR = (e.requested & LOBE_GLOSSY_R) != 0, sampleT = (e.requested & LOBE_DIFFUSE_R) != 0;
+        if (!sampleR && !sampleT) break;
+        V3 wi = e.wi;
+        float eta = 1.0f/b.ior;
+        float Fi = dielectric_reflectance(eta, wi.z);
+        float substrateWeight = b.substrate_weight*b.avg_transmittance*(1.0f - Fi);
+        float specularWeight = Fi;
+        float specularProbability = specularWeight/(specularWeight + substrateWeight);
+        if (sampleR && (sampler_boolean(smp, specularProbability) || !sampleT)) {
+            float roughness = bsdf_roughness(sc, b, s);
+            if (!rd_sample_base(smp, e, true, false, roughness, b.ior, b.dist)) break;
+            if (sampleT) {
+                V3 diffuseAlbedo = bsdf_albedo(sc, b, s);
+                float Fo = dielectric_reflectance(eta, e.wo.z);
+                V3 brdfSubstrate = (plastic_substrate(b, diffuseAlbedo, Fi, Fo, eta)*INV_PI_F)*e.wo.z;
+                V3 brdfSpecular = e.weight*e.pdf;
+                float pdfSubstrate = cosine_hemisphere_pdf(e.wo)*(1.0f - specularProbability);
+                float pdfSpecular = e.pdf*specularProbability;
+                e.weight = (brdfSpecular + brdfSubstrate)/(pdfSpecular + pdfSubstrate);
+                e.pdf = pdfSpecular + pdfSubstrate;
+            }
+        } else {
+            float xa = sampler_next1d(smp), xb = sampler_next1d(smp);
+            V3 wo = cosine_hemisphere(xa, xb);
+            float Fo = dielectric_reflectance(eta, wo.z);
+            V3 diffuseAlbedo = bsdf_albedo(sc, b, s);
+            e.wo = wo;
+            e.weight = plastic_substrate(b, diffuseAlbedo, Fi, Fo, eta);
+            if (max_comp(b.scaled_sigma_a) > 0.0f)
+                e.weight = e.weight*vexp(b.scaled_sigma_a*(-1.0f/e.wo.z - 1.0f/e.wi.z));
+            e.pdf = cosine_hemisphere_pdf(e.wo);
+            if (sampleR) {
+                float roughness = bsdf_roughness(sc, b, s);
+                V3 brdfSubstrate = e.weight*e.pdf;
+                float pdfSubstrate = e.pdf*(1.0f - specularProbability);
+                V3 brdfSpecular = rd_eval_base(e, true, false, roughness, b.ior, b.dist);
+                float pdfSpecular = rd_pdf_base(e, true, false, roughness, b.ior, b.dist);
+                pdfSpecular *= specularProbability;
+                e.weight = (brdfSpecular + brdfSubstrate)/(pdfSpecular + pdfSubstrate);
+                e.pdf = pdfSpecular + pdfSubstrate;
+            }
+            e.sampled = LOBE_DIFFUSE_R;
+        }
+        ok = true; break; }
+    default: break;                                                                    // bsdfs/NullBsdf.cpp: sample() == false
+    }
+    if (!ok) return false;
+    e.weight = e.weight*sqr(bsdf_eta(b, e));
+    return true;
+}
+
+// Bsdf::eval(event, adjoint=false) (bsdfs/Bsdf.hpp:85-97)
+TGB_D V3 bsdf_eval(const DScene &sc, const DBsdf &b, const Surface &s, const Event &e) {
+    V3 f = v3s(0.0f);
+    switch (b.type) {
+    case TGB_BSDF_LAMBERT:                                                             // LambertBsdf.cpp:40-47
+        if (!(e.requested & LOBE_DIFFUSE_R)) break;
+        if (e.wi.z <= 0.0f || e.wo.z <= 0.0f) break;
+        f = (bsdf_albedo(sc, b, s)*INV_PI_F)*e.wo.z;
+        break;
+    case TGB_BSDF_ROUGH_CONDUCTOR: {                                                   // RoughConductorBsdf.cpp:92-110
+        if (!(e.requested & LOBE_GLOSSY_R)) break;
+        if (e.wi.z <= 0.0f || e.wo.z <= 0.0f) break;
+        float alpha = mf_roughness_to_alpha(b.dist, bsdf_roughness(sc, b, s));
+        V3 hr = normalize(e.wi + e.wo);
+        float cosThetaM = dot(e.wi, hr);
+        V3 F = conductor_reflectance(b.eta, b.k, cosThetaM);
+        float G = mf_G(b.dist, alpha, e.wi, e.wo, hr);
+        float D = mf_D(b.dist, alpha, hr);
+        float fr = (G*D*0.25f)/e.wi.z;
+        f = bsdf_albedo(sc, b, s)*(F*fr);
+        break; }
+    case TGB_BSDF_ROUGH_DIELECTRIC: {                                                  // RoughDielectricBsdf.cpp:246-252
+        bool sampleR = (e.requested & LOBE_GLOSSY_R) != 0;
+        bool sampleT = (e.requested & LOBE_GLOSSY_T) != 0 && b.enable_t;
+        f = rd_eval_base(e, sampleR, sampleT, bsdf_roughness(sc, b, s), b.ior, b.dist)*bsdf_albedo(sc, b, s);
+        break; }
+    case TGB_BSDF_PLASTIC: {                                                           // PlasticBsdf.cpp:125-151
+        if (e.wi.z <= 0.0f || e.wo.z <= 0.0f) break;
+        bool evalR = (e.requested & LOBE_SPEC_R) != 0, evalT = (e.requested & LOBE_DIFFUSE_R) != 0;
+        float eta = 1.0f/b.ior;
+        float Fi = dielectric_reflectance(eta, e.wi.z);
+        float Fo = dielectric_reflectance(eta, e.wo.z);
+        if (evalR && check_reflection_constraint(e.wi, e.wo)) f = v3s(Fi);
+        else if (evalT) {
+            V3 diffuseAlbedo = bsdf_albedo(sc, b, s);
+            V3 denom = v3s(1.0f) - diffuseAlbedo*b.diffuse_fresnel;
+            V3 brdf = (diffuseAlbedo/denom)*((1.0f - Fi)*(1.0f - Fo)*eta*eta*e.wo.z*INV_PI_F);
+            if (max_comp(b.scaled_sigma_a) > 0.0f)
+                brdf = brdf*vexp(b.scaled_sigma_a*(-1.0f/e.wo.z - 1.0f/e.wi.z));
+            f = brdf;
+        }
+        break; }
+    case TGB_BSDF_ROUGH_PLASTIC: {                                                     // RoughPlasticBsdf.cpp:115-140
+        bool sampleR = (e.requested & LOBE_GLOSSY_R) != 0, sampleT = (e.requested & LOBE_DIFFUSE_R) != 0;
+        if (!sampleR && !sampleT) break;
+        if (e.wi.z <= 0.0f || e.wo.z <= 0.0f) break;
+        V3 glossyR = v3s(0.0f);
+        if (sampleR) glossyR = rd_eval_base(e, true, false, bsdf_roughness(sc, b, s), b.ior, b.dist);
+        V3 diffuseR = v3s(0.0f);
+        if (sampleT) {
+            float eta = 1.0f/b.ior;
+            float Fi = dielectric_reflectance(eta, e.wi.z);
+            float Fo = dielectric_reflectance(eta, e.wo.z);
+            V3 diffuseAlbedo = bsdf_albedo(sc, b, s);
+            V3 denom = v3s(1.0f) - diffuseAlbedo*b.diffuse_fresnel;
+            diffuseR = (diffuseAlbedo/denom)*((1.0f - Fi)*(1.0f - Fo)*eta*eta*e.wo.z*INV_PI_F);
+            if (max_comp(b.scaled_sigma_a) > 0.0f)
+                diffuseR = diffuseR*vexp(b.scaled_sigma_a*(-1.0f/e.wo.z - 1.0f/e.wi.z));
+        }
+        f = glossyR + diffuseR;
+        break; }
+    default: break;
+    }
+    return f*sqr(bsdf_eta(b, e));
+}
+
+TGB_D float bsdf_pdf(const DScene &sc, const DBsdf &b, const Surface &s, const Event &e) {
+    switch (b.type) {
+    case TGB_BSDF_LAMBERT:                                                             // LambertBsdf.cpp:61-68
+        if (!(e.requested & LOBE_DIFFUSE_R)) return 0.0f;
+        if (e.wi.z <= 0.0f || e.wo.z <= 0.0f) return 0.0f;
+        return cosine_hemisphere_pdf(e.wo);
+    case TGB_BSDF_ROUGH_CONDUCTOR: {                                                   // RoughConductorBsdf.cpp:128-143
+        if (!(e.requested & LOBE_GLOSSY_R)) return 0.0f;
+        if (e.wi.z <= 0.0f || e.wo.z <= 0.0f) return 0.0f;
+        float sampleAlpha = mf_roughness_to_alpha(b.dist, bsdf_roughness(sc, b, s));
+        V3 hr = normalize(e.wi + e.wo);
+        return mf_pdf(b.dist, sampleAlpha, hr)*0.25f/dot(e.wi, hr); }
+    case TGB_BSDF_ROUGH_DIELECTRIC: {                                                  // RoughDielectricBsdf.cpp:266-272
+        bool sampleR = (e.requested & LOBE_GLOSSY_R) != 0;
+        bool sampleT = (e.requested & LOBE_GLOSSY_T) != 0 && b.enable_t;
+        return rd_pdf_base(e, sampleR, sampleT, bsdf_roughness(sc, b, s), b.ior, b.dist); }
+    case TGB_BSDF_PLASTIC: {                                                           // PlasticBsdf.cpp:153-177
+        if (e.wi.z <= 0.0f || e.wo.z <= 0.0f) return 0.0f;
+        bool sampleR = (e.requested & LOBE_SPEC_R) != 0, sampleT = (e.requested & LOBE_DIFFUSE_R) != 0;
+        if (sampleR && sampleT) {
+            float Fi = dielectric_reflectance(1.0f/b.ior, e.wi.z);
+            float substrateWeight = b.avg_transmittance*(1.0f - Fi);
+            float specularWeight = Fi;
+            float specularProbability = specularWeight/(specularWeight + substrateWeight);
+            if (check_reflection_constraint(e.wi, e.wo)) return specularProbability;
+            return cosine_hemisphere_pdf(e.wo)*(1.0f - specularProbability);
+        } else if (sampleT) return cosine_hemisphere_pdf(e.wo);
+        else if (sampleR) return check_reflection_constraint(e.wi, e.wo) ? 1.0f : 0.0f;
+        return 0.0f; }
+    case TGB_BSDF_ROUGH_PLASTIC: {                                                     // RoughPlasticBsdf.cpp:186-213
+        bool sampleR = (e.requested & LOBE_GLOSSY_R) != 0, sampleT = (e.requested & LOBE_DIFFUSE_R) != 0;
+        if (!sampleR && !sampleT) return 0.0f;
+        if (e.wi.z <= 0.0f || e.wo.z <= 0.0f) return 0.0f;
+        float glossyPdf = 0.0f;
+        if (sampleR) glossyPdf = rd_pdf_base(e, true, false, bsdf_roughness(sc, b, s), b.ior, b.dist);
+        float diffusePdf = 0.0f;
+        if (sampleT) diffusePdf = cosine_hemisphere_pdf(e.wo);
+        if (sampleT && sampleR) {
+            float Fi = dielectric_reflectance(1.0f/b.ior, e.wi.z);
+            float substrateWeight = b.substrate_weight*b.avg_transmittance*(1.0f - Fi);
+            float specularWeight = Fi;
+            float specularProbability = specularWeight/(specularWeight + substrateWeight);
+            diffusePdf *= (1.0f - specularProbability);
+            glossyPdf *= specularProbability;
+        }
+        return glossyPdf + diffusePdf; }
+    default: return 0.0f;
+    }
+}
+
+// ---------------------------------------------------------------- lights
+struct LightSample { V3 d; float dist, pdf; };
+
+TGB_D int dist1d_warp(const float *cdf, const float *pdf, int n, float &u) {           // sampling/Distribution1D.hpp:37-41
+    int lo = 0, hi = n + 1;
+    while (lo < hi) { int mid = (lo + hi) >> 1; if (u < __ldg(cdf + mid)) hi = mid; else lo = mid + 1; }
+    int idx = lo - 1;
+    float r = (u - __ldg(cdf + idx))/__ldg(pdf + idx);
+    u = r < 0.0f ? 0.0f : (r > 1.0f ? 1.0f : r);
+    return idx;
+}
+TGB_D float bitmap_pdf_uv(const DTex &t, float u, float v) {                           // textures/BitmapTexture.cpp pdf(MAP_SPHERICAL)
+    int w = t.res_u, h = t.res_v;
+    int col = min(max(int(w*u), 0), w - 1);
+    int row = min(max(int(h*(1.0f - v)), 0), h - 1);
+    return __ldg(t.pdf + size_t(row)*w + col)*__ldg(t.marg_pdf + row)*w*h;
+}
+TGB_D void direction_to_uv(const DPrim &p, V3 wi, float &u, float &v, float *sinTheta) {    // primitives/InfiniteSphere.cpp:27-39
+    V3 wl = m3mul(p.inv_rot, wi);
+    if (sinTheta) *sinTheta = sqrtf(maxf(1.0f - wl.y*wl.y, 0.0f));
+    u = atan2f(wl.z, wl.x)*INV_TWO_PI_F + 0.5f;
+    v = acosf(-wl.y)*INV_PI_F;
+}
+
+TGB_D bool light_sample_direct(const DScene &sc, const DPrim &l, V3 p, Sampler &smp, LightSample &out) {
+    if (l.type == TGB_PRIM_QUAD) {                                                     // primitives/Quad.cpp:172-188
+        if (dot(l.normal, p - l.base) <= 0.0f) return false;
+        float xa = sampler_next1d(smp), xb = sampler_next1d(smp);
+        V3 q = l.base + l.edge0*xa + l.edge1*xb;
+        out.d = q - p;
+        float rSq = length_sq(out.d);
+        out.dist = sqrtf(rSq);
+        out.d = out.d/out.dist;
+        float cosTheta = -dot(l.normal, out.d);
+        out.pdf = rSq/(cosTheta*l.area);
+        return true;
+    }
+    if (l.type == TGB_PRIM_MESH) {                                                     // primitives/TriangleMesh.cpp:413-436,448-465
+        float u = sampler_next1d(smp);
+        int idx = dist1d_warp(l.tri_cdf, l.tri_pdf, int(l.n_tris), u);
+        const float *lv = l.light_verts + 9*size_t(idx);
+        V3 p0 = v3(__ldg(lv), __ldg(lv + 1), __ldg(lv + 2)), p1 = v3(__ldg(lv + 3), __ldg(lv + 4), __ldg(lv + 5));
+        V3 p2 = v3(__ldg(lv + 6), __ldg(lv + 7), __ldg(lv + 8));
+        V3 normal = normalize(cross(p1 - p0, p2 - p0));
+        float xa = sampler_next1d(smp), xb = sampler_next1d(smp);
+        float uSqrt = sqrtf(xa);                                                       // SampleWarp::uniformTriangleUv
+        float alpha = 1.0f - uSqrt, beta = (1.0f - xb)*uSqrt;
+        V3 pp = p0*alpha + p1*beta + p2*(1.0f - alpha - beta);
+        V3 L = pp - p;
+        float rSq = length_sq(L);
+        out.dist = sqrtf(rSq);
+        out.d = L/out.dist;
+        float cosTheta = -dot(normal, out.d);
+        if (cosTheta <= 0.0f) return false;
+        out.pdf = rSq/(cosTheta*l.total_area);
+        return true;
+    }
+    if (l.type == TGB_PRIM_INFINITE_SPHERE) {                                          // primitives/InfiniteSphere.cpp:161-176
+        const DTex &em = sc.tex[l.emission_tex];
+        float xa = sampler_next1d(smp), xb = sampler_next1d(smp);
+        if (em.type == TGB_TEX_CONSTANT) {
+            float phi = xa*TWO_PI_F, z = xb*2.0f - 1.0f;                               // SampleWarp::uniformSphere
+            float r = sqrtf(maxf(1.0f - z*z, 0.0f));
+            out.d = v3(cosf(phi)*r, sinf(phi)*r, z);
+            out.dist = INFINITY; out.pdf = INV_FOUR_PI_F;
+            return true;
+        }
+        // BitmapTexture::sample(MAP_SPHERICAL) via Distribution2D::warp
+        float u = xa, v = xb;
+        int row = dist1d_warp(em.marg_cdf, em.marg_pdf, em.res_v, v);
+        int col = dist1d_warp(em.cdf + size_t(row)*(em.res_u + 1), em.pdf + size_t(row)*em.res_u, em.res_u, u);
+        float tu = (u + col)/em.res_u, tv = 1.0f - (v + row)/em.res_v;
+        float phi = (tu - 0.5f)*TWO_PI_F, theta = tv*PI_F;                             // uvToDirection (InfiniteSphere.cpp:41-51)
+        float sinTheta = sinf(theta);
+        out.d = m3mul(l.rot, v3(cosf(phi)*sinTheta, -cosf(theta), sinf(phi)*sinTheta));
+        out.pdf = INV_PI_F*INV_TWO_PI_F*bitmap_pdf_uv(em, tu, tv)/sinTheta;
+        out.dist = INFINITY;
+        return out.pdf != 0.0f;
+    }
+    return false;
+}
+
+TGB_D float light_approx_radiance(const DScene &sc, const DPrim &l, V3 p) {
+    if (l.type == TGB_PRIM_QUAD) {                                                     // primitives/Quad.cpp:256-278
+        if (!(l.flags & PF_EMISSIVE)) return 0.0f;
+        V3 R0 = l.base - p;
+        if (dot(R0, l.normal) >= 0.0f) return 0.0f;
+        V3 R1 = R0 + l.edge0, R2 = R1 + l.edge1, R3 = R0 + l.edge1;
+        V3 n0 = normalize(cross(R0, R1)), n1 = normalize(cross(R1, R2));
+        V3 n2 = normalize(cross(R2, R3)), n3 = normalize(cross(R3, R0));
+        float Q = acosf(dot(n0, n1)) + acosf(dot(n1, n2)) + acosf(dot(n2, n3)) + acosf(dot(n3, n0));
+        return (TWO_PI_F - fabsf(Q))*max_comp(sc.tex[l.emission_tex].avg);
+    }
+    if (l.type == TGB_PRIM_MESH) return -1.0f;                                         // primitives/TriangleMesh.cpp:514-517
+    if (l.type == TGB_PRIM_INFINITE_SPHERE) {                                          // primitives/InfiniteSphere.cpp:261-266
+        if (!(l.flags & PF_EMISSIVE) || !(l.flags & PF_SAMPLABLE)) return 0.0f;
+        return TWO_PI_F*max_comp(sc.tex[l.emission_tex].avg);
+    }
+    return 0.0f;
+}
+
+// TraceBase::chooseLight (integrators/TraceBase.cpp:416-459).  Returns the primitive index or -1.
+TGB_D int choose_light(const DScene &sc, V3 p, Sampler &smp, float &weight) {
+    int n = sc.n_lights;
+    if (n == 0) return -1;
+    if (n == 1) { weight = 1.0f; return sc.lights[0]; }
+    float pdfs[16];
+    if (n > 16) n = 16;
+    float total = 0.0f; unsigned numNonNegative = 0;
+    for (int i = 0; i < n; ++i) {
+        pdfs[i] = light_approx_radiance(sc, sc.prims[sc.lights[i]], p);
+        if (pdfs[i] >= 0.0f) { total += pdfs[i]; numNonNegative++; }
+    }
+    if (numNonNegative == 0) { for (int i = 0; i < n; ++i) pdfs[i] = 1.0f; total = float(n); }
+    else if (numNonNegative < unsigned(n)) {
+        for (int i = 0; i < n; ++i) {
+            float uniformWeight = (total == 0.0f ? 1.0f : total)/numNonNegative;
+            if (pdfs[i] < 0.0f) { pdfs[i] = uniformWeight; total += uniformWeight; }
+        }
+    }
+    if (total == 0.0f) return -1;
+    float t = sampler_next1d(smp)*total;
+    for (int i = 0; i < n; ++i) {
+        if (t < pdfs[i] || i == n - 1) { weight = total/pdfs[i]; return sc.lights[i]; }
+        t -= pdfs[i];
+    }
+    return -1;
+}
+
+}  // namespace tgb

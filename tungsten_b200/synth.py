@@ -1,0 +1,207 @@
+"""Procedural scenes in Tungsten's own JSON + .wo3 formats.
+
+BASELINE.json's configs name assets that are not in the reference repository (Stanford dragon,
+"living-room", a 10M-triangle forest) and there is no network, so the bench and the parity tests
+synthesise stand-ins of the stated size and material mix.  Everything is written as ordinary scene
+files so that the reference binary (oracle/_ref), the CPU restatement and the CUDA path all load
+exactly the same inputs.  Deterministic: no RNG state outside the explicit seeds.
+"""
+import json
+import os
+
+import numpy as np
+
+from .scene import VERTEX_DTYPE, TRI_DTYPE, save_wo3
+
+
+# ---- meshes -----------------------------------------------------------------------------------
+def icosphere(subdiv, radius=1.0, displace=0.0, seed=1, lobes=0.0):
+    """Unit icosahedron subdivided `subdiv` times (20*4^subdiv triangles), optional smooth
+    deterministic displacement so that the surface is not a trivial sphere."""
+    t = (1.0 + 5.0**0.5)/2.0
+    v = np.array([[-1, t, 0], [1, t, 0], [-1, -t, 0], [1, -t, 0], [0, -1, t], [0, 1, t], [0, -1, -t], [0, 1, -t],
+                  [t, 0, -1], [t, 0, 1], [-t, 0, -1], [-t, 0, 1]], dtype=np.float64)
+    v /= np.linalg.norm(v, axis=1, keepdims=True)
+    f = np.array([[0, 11, 5], [0, 5, 1], [0, 1, 7], [0, 7, 10], [0, 10, 11], [1, 5, 9], [5, 11, 4], [11, 10, 2],
+                  [10, 7, 6], [7, 1, 8], [3, 9, 4], [3, 4, 2], [3, 2, 6], [3, 6, 8], [3, 8, 9], [4, 9, 5],
+                  [2, 4, 11], [6, 2, 10], [8, 6, 7], [9, 8, 1]], dtype=np.int64)
+    for _ in range(subdiv):
+        e = np.concatenate([f[:, [0, 1]], f[:, [1, 2]], f[:, [2, 0]]], axis=0)
+        es = np.sort(e, axis=1)
+        key = es[:, 0]*(len(v) + 1) + es[:, 1]
+        uniq, inv = np.unique(key, return_inverse=True)
+        first = np.zeros(len(uniq), dtype=np.int64); first[inv] = np.arange(len(key))
+        mid = v[es[first, 0]] + v[es[first, 1]]
+        mid /= np.linalg.norm(mid, axis=1, keepdims=True)
+        base = len(v)
+        v = np.concatenate([v, mid], axis=0)
+        n = len(f)
+        m01, m12, m20 = base + inv[:n], base + inv[n:2*n], base + inv[2*n:]
+        f = np.concatenate([np.stack([f[:, 0], m01, m20], 1), np.stack([f[:, 1], m12, m01], 1),
+                            np.stack([f[:, 2], m20, m12], 1), np.stack([m01, m12, m20], 1)], axis=0)
+    r = np.ones(len(v))
+    if displace > 0.0:
+        rng = np.random.RandomState(seed)
+        for k in range(6):
+            d = rng.normal(size=3); d /= np.linalg.norm(d)
+            freq = 2.0 + 3.0*k
+            r += displace/(k + 1)*np.sin(freq*(v @ d) + rng.uniform(0, 6.28))
+    if lobes > 0.0:
+        r += lobes*np.cos(3.0*np.arctan2(v[:, 2], v[:, 0]))*np.sin(2.0*np.arccos(np.clip(v[:, 1], -1, 1)))
+    p = v*(r*radius)[:, None]
+    # smooth normals from area-weighted face normals
+    fn = np.cross(p[f[:, 1]] - p[f[:, 0]], p[f[:, 2]] - p[f[:, 0]])
+    nrm = np.zeros_like(p)
+    for k in range(3):
+        np.add.at(nrm, f[:, k], fn)
+    nrm /= np.maximum(np.linalg.norm(nrm, axis=1, keepdims=True), 1e-20)
+    verts = np.zeros(len(p), dtype=VERTEX_DTYPE)
+    verts["pos"] = p.astype(np.float32); verts["normal"] = nrm.astype(np.float32)
+    verts["uv"][:, 0] = (np.arctan2(v[:, 2], v[:, 0])/(2*np.pi) + 0.5).astype(np.float32)
+    verts["uv"][:, 1] = (np.arccos(np.clip(v[:, 1], -1, 1))/np.pi).astype(np.float32)
+    tris = np.zeros(len(f), dtype=TRI_DTYPE)
+    tris["v0"], tris["v1"], tris["v2"] = f[:, 0], f[:, 1], f[:, 2]
+    return verts, tris
+
+
+def grid_mesh(nx, nz, size=1.0, height=0.0, seed=3):
+    """(nx x nz) quads -> 2*nx*nz triangles in the XZ plane, optional height field."""
+    xs = np.linspace(-0.5, 0.5, nx + 1)*size; zs = np.linspace(-0.5, 0.5, nz + 1)*size
+    X, Z = np.meshgrid(xs, zs, indexing="xy")
+    Y = np.zeros_like(X)
+    if height > 0.0:
+        rng = np.random.RandomState(seed)
+        for k in range(4):
+            a, b = rng.uniform(2, 9, 2); ph = rng.uniform(0, 6.28, 2)
+            Y += height/(k + 1)*np.sin(a*X/size*6.28 + ph[0])*np.cos(b*Z/size*6.28 + ph[1])
+    verts = np.zeros(X.size, dtype=VERTEX_DTYPE)
+    verts["pos"] = np.stack([X.ravel(), Y.ravel(), Z.ravel()], 1).astype(np.float32)
+    verts["normal"][:, 1] = 1.0
+    verts["uv"] = np.stack([(X.ravel()/size + 0.5), (Z.ravel()/size + 0.5)], 1).astype(np.float32)
+    i = np.arange(nx)[None, :] + (nx + 1)*np.arange(nz)[:, None]
+    i = i.ravel()
+    tris = np.zeros(2*nx*nz, dtype=TRI_DTYPE)
+    tris["v0"][0::2], tris["v1"][0::2], tris["v2"][0::2] = i, i + nx + 1, i + 1
+    tris["v0"][1::2], tris["v1"][1::2], tris["v2"][1::2] = i + 1, i + nx + 1, i + nx + 2
+    return verts, tris
+
+
+# ---- scenes -----------------------------------------------------------------------------------
+def _lambert(name, albedo):
+    return {"name": name, "albedo": albedo, "type": "lambert"}
+
+
+def _renderer(spp):
+    return {"output_file": "out.png", "hdr_output_file": "out.pfm", "overwrite_output_files": True,
+            "adaptive_sampling": False, "enable_resume_render": False, "stratified_sampler": True,
+            "scene_bvh": True, "spp": spp, "spp_step": spp}
+
+
+def cornell_box(res=(128, 128), spp=16, max_bounces=64, extra_bsdfs=(), extra_prims=(), boxes=True,
+                light_emission=(17, 12, 4), filter_name="tent"):
+    """The classic Cornell box laid out with Tungsten primitives: 5 wall quads, 2 cubes, 1 quad light
+    (same construction as the reference's data/example-scenes/cornell-box, dimensions are the
+    well-known Cornell measurements rescaled to a 2-unit box)."""
+    white = [0.725, 0.71, 0.68]
+    bsdfs = [_lambert("leftWall", [0.63, 0.065, 0.05]), _lambert("rightWall", [0.14, 0.45, 0.091]),
+             _lambert("floor", white), _lambert("ceiling", white), _lambert("backWall", white),
+             _lambert("shortBox", white), _lambert("tallBox", white),
+             {"name": "light", "albedo": 1, "type": "null"}] + list(extra_bsdfs)
+    def quad(name, pos, rot, scale=(2, 4, 2), **kw):
+        d = {"name": name, "transform": {"position": list(pos), "scale": list(scale), "rotation": list(rot)},
+             "type": "quad", "bsdf": name}
+        d.update(kw); return d
+    prims = [quad("floor", (0, 0, 0), (0, 90, 0)), quad("ceiling", (0, 2, 0), (0, 0, -180)),
+             quad("backWall", (0, 1, -1), (0, 90, 90)), quad("rightWall", (1, 1, 0), (0, 180, 90)),
+             quad("leftWall", (-1, 1, 0), (0, 0, 90))]
+    if boxes:
+        prims += [{"name": "shortBox", "type": "cube", "bsdf": "shortBox",
+                   "transform": {"position": [0.328631, 0.3, 0.374592], "scale": [0.594811, 0.604394, 0.6],
+                                 "rotation": [90, 90, -163.36]}},
+                  {"name": "tallBox", "type": "cube", "bsdf": "tallBox",
+                   "transform": {"position": [-0.335439, 0.6, -0.291415], "scale": [0.607289, 0.597739, 1.2],
+                                 "rotation": [90, 180, 160.812]}}]
+    prims += [quad("light", (-0.005, 1.98, -0.03), (0, 180, 180), scale=(0.47, 0.1786, 0.38),
+                   emission=list(light_emission))]
+    prims += list(extra_prims)
+    return {"media": [], "bsdfs": bsdfs, "primitives": prims,
+            "camera": {"tonemap": "filmic", "resolution": list(res), "reconstruction_filter": filter_name,
+                       "transform": {"position": [0, 1, 6.8], "look_at": [0, 1, 0], "up": [0, 1, 0]},
+                       "type": "pinhole", "fov": 35},
+            "integrator": {"type": "path_tracer", "min_bounces": 0, "max_bounces": max_bounces,
+                           "enable_consistency_checks": False, "enable_two_sided_shading": True,
+                           "enable_light_sampling": True},
+            "renderer": _renderer(spp)}
+
+
+def write_scene(out_dir, name, scene, meshes=None):
+    """Write <out_dir>/<name>.json (+ .wo3 files named by `meshes`: {filename: (verts, tris)})."""
+    os.makedirs(out_dir, exist_ok=True)
+    for fn, (v, t) in (meshes or {}).items():
+        save_wo3(os.path.join(out_dir, fn), v, t)
+    path = os.path.join(out_dir, name + ".json")
+    with open(path, "w") as f:
+        json.dump(scene, f, indent=1)
+    return path
+
+
+def cornell_mesh(out_dir, name="cornell_mesh", subdiv=3, res=(128, 128), spp=16, max_bounces=64,
+                 bsdf=None, smooth=True, displace=0.15):
+    """Cornell box (no cubes) + one displaced-icosphere mesh: the C1 stand-in (subdiv 7 -> 327,680 and
+    subdiv 8 -> 1,310,720 triangles; the bench uses ~870k via two meshes)."""
+    v, t = icosphere(subdiv, 1.0, displace=displace)
+    b = bsdf or _lambert("blob", [0.6, 0.55, 0.7])
+    b = dict(b); b["name"] = "blob"
+    prim = {"name": "blob", "type": "mesh", "file": name + "_blob.wo3", "smooth": smooth, "bsdf": "blob",
+            "transform": {"position": [0.0, 0.72, 0.0], "scale": [0.62, 0.62, 0.62], "rotation": [0, 30, 0]}}
+    sc = cornell_box(res, spp, max_bounces, extra_bsdfs=[b], extra_prims=[prim], boxes=False)
+    return write_scene(out_dir, name, sc, {name + "_blob.wo3": (v, t)})
+
+
+def cornell_dragon_standin(out_dir, name="cornell_dragon", res=(1920, 1080), spp=1024, max_bounces=64):
+    """BASELINE.json config C1: Cornell box + ~870k-triangle Lambert mesh.  The Stanford dragon is not in
+    the reference repository; the stand-in is a lobed, displaced icosphere at subdivision 7 (327,680
+    triangles) plus a 520x520 height-field "plinth" (540,800 triangles): 868,480 triangles."""
+    v, t = icosphere(7, 1.0, displace=0.22, lobes=0.25)
+    gv, gt = grid_mesh(520, 520, 1.0, height=0.03)
+    bs = [_lambert("dragon", [0.55, 0.62, 0.45]), _lambert("plinth", [0.7, 0.6, 0.5])]
+    prims = [{"name": "dragon", "type": "mesh", "file": name + "_body.wo3", "smooth": True, "bsdf": "dragon",
+              "transform": {"position": [0.0, 0.85, -0.05], "scale": [0.55, 0.55, 0.55], "rotation": [0, 25, 0]}},
+             {"name": "plinth", "type": "mesh", "file": name + "_plinth.wo3", "smooth": False, "bsdf": "plinth",
+              "transform": {"position": [0.0, 0.12, 0.0], "scale": [1.5, 1.0, 1.5]}}]
+    sc = cornell_box(res, spp, max_bounces, extra_bsdfs=bs, extra_prims=prims, boxes=False)
+    return write_scene(out_dir, name, sc, {name + "_body.wo3": (v, t), name + "_plinth.wo3": (gv, gt)})
+
+
+def material_room(out_dir, name="materials", res=(128, 128), spp=16, max_bounces=16, subdiv=3, env=None):
+    """Cornell-like room with one blob per in-scope lobe model (rough conductor / rough dielectric /
+    plastic / rough plastic), a checker floor and a second (mesh) light: exercises chooseLight with
+    several lights, mesh-light NEE, textured albedo and every BSDF on the path."""
+    bsdfs = [
+        {"name": "metal", "type": "rough_conductor", "albedo": 1.0, "material": "Cu", "distribution": "ggx", "roughness": 0.25},
+        {"name": "glass", "type": "rough_dielectric", "albedo": 1.0, "ior": 1.5, "distribution": "ggx", "roughness": 0.15},
+        {"name": "plast", "type": "plastic", "albedo": [0.2, 0.4, 0.8], "ior": 1.5, "thickness": 1.0, "sigma_a": [0.0, 0.0, 0.0]},
+        {"name": "rplast", "type": "rough_plastic", "albedo": [0.8, 0.3, 0.2], "ior": 1.4, "thickness": 1.0,
+         "sigma_a": [0.1, 0.2, 0.3], "distribution": "beckmann", "roughness": 0.3},
+        {"name": "checker", "type": "lambert", "albedo": {"type": "checker", "on_color": [0.8, 0.8, 0.8],
+                                                         "off_color": [0.15, 0.15, 0.2], "res_u": 8, "res_v": 8}},
+        {"name": "lamp", "type": "null", "albedo": 1.0},
+    ]
+    v, t = icosphere(subdiv, 1.0, displace=0.1)
+    lv, lt = grid_mesh(2, 2, 1.0)
+    meshes = {name + "_blob.wo3": (v, t), name + "_lamp.wo3": (lv, lt)}
+    def blob(nm, bsdf, pos, s=0.28):
+        return {"name": nm, "type": "mesh", "file": name + "_blob.wo3", "smooth": True, "bsdf": bsdf,
+                "transform": {"position": list(pos), "scale": [s, s, s]}}
+    prims = [blob("b0", "metal", (-0.55, 0.32, 0.2)), blob("b1", "glass", (0.0, 0.95, 0.3), 0.3),
+             blob("b2", "plast", (0.55, 0.32, 0.2)), blob("b3", "rplast", (0.0, 0.3, -0.45)),
+             {"name": "floor2", "type": "quad", "bsdf": "checker",
+              "transform": {"position": [0, 0.002, 0], "scale": [1.9, 1, 1.9]}},
+             {"name": "lamp", "type": "mesh", "file": name + "_lamp.wo3", "smooth": False, "bsdf": "lamp",
+              "emission": [6.0, 7.0, 9.0],
+              "transform": {"position": [0.6, 1.3, -0.95], "scale": [0.5, 0.5, 0.5], "rotation": [90, 0, 0]}}]
+    sc = cornell_box(res, spp, max_bounces, extra_bsdfs=bsdfs, extra_prims=prims, boxes=False)
+    if env is not None:
+        sc["primitives"].append({"name": "env", "type": "infinite_sphere", "emission": env, "sample": True,
+                                 "transform": {"rotation": [0, 40, 0]}})
+    return write_scene(out_dir, name, sc, meshes)
