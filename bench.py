@@ -1,0 +1,296 @@
+#!/usr/bin/env python
+"""Headline benchmark of the B200 path_tracer hot path (BASELINE.json metric: Msamples/s).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--spp-per-step S]
+
+Workload (config C1 of BASELINE.json): Cornell box + 868,480-triangle Lambert mesh (procedural stand-in for the
+Stanford dragon, see tungsten_b200/synth.py), 1920x1080, path_tracer, max_bounces 64, Sobol sampler,
+target 1024 spp.  One STEP = one pass of the hot path over one batch: 64 samples per pixel of the whole frame
+(132.7 M camera paths); the default 16 timed steps are the complete 1024-spp frame.  With N GPUs the image's
+16x16 tiles are dealt round-robin to the ranks and a step renders 64*N spp (fixed work per GPU: weak scaling),
+followed by the path's single collective, an all-gather of the tile-major float3 framebuffer.
+
+`value`   : whole-job Msamples/s with everything resident in HBM (framebuffer stays on the device).
+`e2e`     : the same metric through the reference-facing C-ABI call tgb200_render_tiles with HOST buffers
+            (running-mean framebuffer + counts copied host->device and back inside every step).
+`roofline`: traversal kernel (k_trace): algorithmic bytes = 48 B per closest-hit query (32 B ray read + 16 B hit
+            write) / CUDA-event duration of the launches in the timed region / measured HBM peak.
+`cpu_baseline`: the reference's own CPU renderer (oracle/_ref/tungsten, built from /root/reference by
+            oracle/ref/Makefile) on this box's host cores, same scene, bounded sample (fewer spp).
+"""
+import argparse
+import json
+import os
+import re
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+W, H = 1920, 1080
+ALG_BYTES_PER_QUERY = 48
+
+
+def _clock_sampler(stop, out, idx):
+    q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    while not stop.is_set():
+        try:
+            r = subprocess.run(["nvidia-smi", "-i", str(idx), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
+                               stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True, timeout=5)
+            f = [x.strip() for x in r.stdout.strip().split(",")]
+            if len(f) >= 6:
+                out.append(f)
+        except Exception:
+            pass
+        stop.wait(0.2)
+
+
+def _summarise_clocks(samples):
+    if not samples:
+        return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+    sm = sorted(int(s[0]) for s in samples if s[0].isdigit())
+    names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+    reasons = [n for i, n in enumerate(names) if any(s[2 + i].lower().startswith("active") for s in samples)]
+    return {"sm_mhz": sm[len(sm)//2] if sm else None, "sm_max_mhz": int(samples[0][1]) if samples[0][1].isdigit() else None,
+            "reasons": reasons, "samples": len(samples)}
+
+
+def _scene_dir():
+    d = os.path.join(tempfile.gettempdir(), "tgb200_bench_scene")
+    os.makedirs(d, exist_ok=True)
+    return d
+
+
+def make_scene(spp):
+    from tungsten_b200 import synth
+    d = _scene_dir()
+    path = os.path.join(d, "cornell_dragon.json")
+    marker = os.path.join(d, "cornell_dragon_body.wo3")
+    if not (os.path.exists(path) and os.path.exists(marker)):
+        synth.cornell_dragon_standin(d, res=(W, H), spp=spp)
+    return path
+
+
+def hbm_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def run_reference_binary(scene_path, spp, threads):
+    """Times oracle/_ref/tungsten (the unmodified reference) on `spp` samples per pixel of the bench scene."""
+    exe = os.path.join(ROOT, "oracle", "_ref", "tungsten")
+    if not os.path.exists(exe):
+        return None
+    js = json.load(open(scene_path))
+    js["renderer"].update(spp=spp, spp_step=spp, adaptive_sampling=False, stratified_sampler=True,
+                          hdr_output_file="ref.pfm", output_file="ref.png")
+    d = os.path.dirname(scene_path)
+    rp = os.path.join(d, "ref_run.json")
+    json.dump(js, open(rp, "w"))
+    out = subprocess.run([exe, "-t", str(threads), "-d", os.path.join(d, "ref_out"), rp], stdout=subprocess.PIPE,
+                         stderr=subprocess.STDOUT, text=True)
+    m = re.search(r"Render time ([0-9.]+)\s*s", out.stdout)
+    m2 = re.search(r"Render time (?:(\d+)h )?(?:(\d+)m )?([0-9.]+)s", out.stdout)
+    if m2:
+        secs = float(m2.group(3)) + 60.0*float(m2.group(2) or 0) + 3600.0*float(m2.group(1) or 0)
+    elif m:
+        secs = float(m.group(1))
+    else:
+        return None
+    return W*H*spp/secs/1e6, secs
+
+
+def bench_reference(args, rank, world):
+    """--impl reference: the reference's own CPU path on the host cores (rank 0 only)."""
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    scene_path = make_scene(1024)
+    spp = args.ref_spp
+    vals = []
+    for i in range(args.warmup + args.steps):
+        r = run_reference_binary(scene_path, spp, cores)
+        if r is None:
+            print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/tungsten is missing (run make -C oracle/ref)"}))
+            return
+        if i >= args.warmup:
+            vals.append(r)
+    secs = sum(v[1] for v in vals)
+    value = W*H*spp*len(vals)/secs/1e6
+    line = {"impl": "reference", "metric": "Msamples/sec (paths x spp)", "value": value, "unit": "Msamples/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3*secs/len(vals),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "C1: Cornell box + 868,480-tri Lambert mesh, 1920x1080, path_tracer, max_bounces 64, Sobol",
+                       "step": "%d spp of the whole frame (bounded sample of the 1024-spp job)" % spp},
+            "cpu_baseline": {"value": value, "unit": "Msamples/s", "cores": cores, "kind": "reference",
+                             "sample": "%d spp x 1920x1080 per step, tungsten -t %d (SSE4.2 Embree build, no AVX: the reference's own ISA policy)" % (spp, cores)},
+            "e2e": {"value": value, "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=16)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours")
+    ap.add_argument("--spp-per-step", type=int, default=64)
+    ap.add_argument("--ref-spp", type=int, default=4)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        return bench_reference(args, rank, world)
+
+    import numpy as np
+    import torch
+    from tungsten_b200 import scene, lib, abi, integrator
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the CUDA library is the only implementation")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    scene_path = make_scene(1024) if rank == 0 else None
+    if world > 1:
+        dist.barrier()
+        scene_path = make_scene(1024)
+    fs = scene.load_scene(scene_path)
+    ctx = lib.Context(fs, device=local_rank)
+    info = ctx.scene_info()
+    seed = 0xBA5EBA11
+    all_tiles = integrator.dice_tiles(W, H, seed)
+    my_tiles = integrator.shard_tiles(all_tiles, rank, world)
+    spp_step = args.spp_per_step*world
+    n_my_pix = sum(t.w*t.h for t in my_tiles)
+
+    # multi-GPU: one all-gather of the tile-major framebuffer (the only collective on the path)
+    if world > 1:
+        max_pix = max(sum(t.w*t.h for t in integrator.shard_tiles(all_tiles, r, world)) for r in range(world))
+        send = torch.zeros(max_pix*3, dtype=torch.float32, device="cuda")
+        recv = torch.zeros(world*max_pix*3, dtype=torch.float32, device="cuda")
+
+    def step(i, resident=True, mean=None, count=None):
+        if resident:
+            ctx.render_resident(spp_step, seed=seed, spp_begin=i*spp_step, tiles=my_tiles)
+        else:
+            ctx.render_tiles(spp_step, seed=seed, spp_begin=i*spp_step, tiles=my_tiles, mean=mean, count=count)
+        if world > 1:
+            ctx.pack_tiles(my_tiles, send.data_ptr())
+            dist.all_gather_into_tensor(recv, send)
+
+    def timed(n_steps, first, resident, mean=None, count=None):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for i in range(n_steps):
+            step(first + i, resident, mean, count)
+        torch.cuda.synchronize()
+        t = time.perf_counter() - t0
+        if world > 1:
+            tt = torch.tensor([t], dtype=torch.float64, device="cuda")
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            t = float(tt.item())
+        return t
+
+    # ---- device-resident measurement -----------------------------------------------------------
+    ctx.clear()
+    for i in range(args.warmup):
+        step(i)
+    ctx.clear(); ctx.reset_stats(); ctx.set_profiling(True)
+    stop = threading.Event(); clk = []
+    th = threading.Thread(target=_clock_sampler, args=(stop, clk, local_rank), daemon=True); th.start()
+    wall = timed(args.steps, 0, True)
+    stop.set(); th.join()
+    st = ctx.stats()
+    dev_ms = st.total_ms
+    if world > 1:
+        tt = torch.tensor([float(st.samples), float(st.rays), float(st.hits), float(st.kernel_launches)], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tt)
+        tot_samples, tot_rays, tot_hits, tot_launches = [float(x) for x in tt.tolist()]
+        de = torch.tensor([dev_ms], dtype=torch.float64, device="cuda"); dist.all_reduce(de, op=dist.ReduceOp.MAX)
+        dev_ms_max = float(de.item())
+    else:
+        tot_samples, tot_rays, tot_hits, tot_launches = float(st.samples), float(st.rays), float(st.hits), float(st.kernel_launches)
+        dev_ms_max = dev_ms
+    value = tot_samples/wall/1e6
+    peak, peak_src = hbm_peak()
+    trace_gbs = (st.path_rays*ALG_BYTES_PER_QUERY/1e9)/(st.trace_ms/1e3) if st.trace_ms > 0 else 0.0
+    shadow_gbs = (st.shadow_rays*ALG_BYTES_PER_QUERY/1e9)/(st.shadow_ms/1e3) if st.shadow_ms > 0 else 0.0
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "k_trace_dram_bytes_per_launch.json")
+    if os.path.exists(tp):
+        try:
+            traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+
+    # ---- end to end through the C ABI with host buffers ------------------------------------------
+    ctx.set_profiling(False)
+    mean = np.zeros((H, W, 3), dtype=np.float32); count = np.zeros((H, W), dtype=np.uint32)
+    e2e_steps = max(2, min(args.steps, 4))
+    timed(1, 0, False, mean, count)
+    mean[:] = 0; count[:] = 0
+    ctx.reset_stats()
+    e2e_wall = timed(e2e_steps, 0, False, mean, count)
+    e2e_samples = float(ctx.stats().samples)
+    if world > 1:
+        tt = torch.tensor([e2e_samples], dtype=torch.float64, device="cuda"); dist.all_reduce(tt); e2e_samples = float(tt.item())
+    e2e_value = e2e_samples/e2e_wall/1e6
+    fb_bytes = W*H*(12 + 4)
+
+    if rank == 0:
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            cores = os.cpu_count() or 1
+            r = run_reference_binary(scene_path, args.ref_spp, cores)
+            if r is not None:
+                cpu = {"value": r[0], "unit": "Msamples/s", "cores": cores, "kind": "reference",
+                       "sample": "%d spp x 1920x1080 of the same scene in %.1f s, oracle/_ref/tungsten -t %d" % (args.ref_spp, r[1], cores)}
+        line = {
+            "metric": "Msamples/sec (paths x spp)", "value": value, "unit": "Msamples/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3*wall/args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "C1: Cornell box + 868,480-tri Lambert mesh (procedural dragon stand-in), 1920x1080, path_tracer, "
+                                   "max_bounces 64, Sobol, %d spp per step (x%d steps = %d spp)" % (spp_step, args.steps, spp_step*args.steps),
+                       "tiles": "16x16, round-robin over %d rank(s)" % world, "paths_in_flight": info["capacity"],
+                       "triangles": info["n_tris"], "bvh_nodes": info["n_nodes"], "geom_bytes": info["geom_bytes"],
+                       "l2": "per-batch path state (%.0f MB) and geometry exceed the 126 MB L2; no explicit flush" % (info["capacity"]*230/1e6)},
+            "mrays_per_s": tot_rays/wall/1e6, "mray_hits_per_s": tot_hits/wall/1e6,
+            "device_ms": dev_ms_max, "gpu_launches": int(tot_launches),
+            "e2e": {"value": e2e_value, "unit": "Msamples/s", "h2d_bytes_per_step": fb_bytes, "d2h_bytes_per_step": fb_bytes,
+                    "steps": e2e_steps},
+            "roofline": {"bound": "hbm", "kernel": "k_trace (closest-hit BVH2 traversal of path rays)",
+                         "achieved": trace_gbs, "peak": peak, "unit": "GB/s", "frac": trace_gbs/peak, "traffic": traffic,
+                         "peak_source": peak_src, "alg_bytes_per_query": ALG_BYTES_PER_QUERY,
+                         "queries": int(st.path_rays), "kernel_ms": st.trace_ms, "launches": int(st.trace_launches),
+                         "mqueries_per_s": st.path_rays/st.trace_ms/1e3 if st.trace_ms > 0 else 0.0,
+                         "k_shadow": {"achieved": shadow_gbs, "frac": shadow_gbs/peak, "queries": int(st.shadow_rays), "kernel_ms": st.shadow_ms},
+                         "note": "traversal is latency/divergence bound with an L2-resident BVH; see DESIGN.md section 6"},
+            "cpu_baseline": cpu,
+            "clocks": _summarise_clocks(clk),
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    ctx.close()
+
+
+if __name__ == "__main__":
+    main()

@@ -151,9 +151,13 @@ typedef struct tgb_stats {
     uint64_t rays;
     uint64_t hits;
     uint64_t kernel_launches;   /* launches of this library's own kernels                           */
-    double   trace_ms;          /* CUDA-event time inside trace kernels (closest + shadow)          */
+    double   trace_ms;          /* CUDA-event time inside k_trace (path rays), profiling mode only  */
     uint64_t trace_launches;
     double   total_ms;          /* CUDA-event time of the whole device section                      */
+    uint64_t path_rays;         /* queries issued by k_trace (primary + continuation)               */
+    uint64_t shadow_rays;       /* queries issued by k_shadow (NEE + MIS)                           */
+    double   shadow_ms;         /* CUDA-event time inside k_shadow, profiling mode only             */
+    uint64_t shadow_launches;
 } tgb_stats;
 
 typedef struct tgb_ctx tgb_ctx;
@@ -181,6 +185,14 @@ int tgb200_clear_framebuffer(tgb_ctx *ctx);
 int tgb200_read_framebuffer(tgb_ctx *ctx, float *rgb_mean, uint32_t *count);
 /* Device address of the resident fp32 RGB framebuffer (w*h*3) for zero-copy hand-off to NCCL.       */
 int tgb200_framebuffer_device_ptr(tgb_ctx *ctx, void **rgb_mean_dev, uint64_t *n_bytes);
+
+/* Multi-GPU hand-off: pack the resident pixels of `tiles` tile-major (3 floats per
+ * pixel, tiles in list order, rows top-down inside a tile) into a DEVICE buffer -- the send buffer of the
+ * single all-gather on this path -- and the inverse (de-tile a received buffer into the resident
+ * framebuffer, setting the per-pixel sample count).  Both return after the work has completed.      */
+int tgb200_pack_tiles(tgb_ctx *ctx, const tgb_tile *tiles, uint32_t n_tiles, void *rgb_out_dev);
+int tgb200_unpack_tiles(tgb_ctx *ctx, const tgb_tile *tiles, uint32_t n_tiles, const void *rgb_in_dev,
+                        uint32_t sample_count);
 
 /* Batch of closest-hit queries through the same traversal kernel the renderer uses.                 */
 int tgb200_trace_closest(tgb_ctx *ctx, const tgb_ray *rays, tgb_hit *hits, uint32_t n);

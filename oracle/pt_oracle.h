@@ -40,6 +40,7 @@ float    oracle_normalized_uint(uint32_t i);
 uint32_t oracle_sobol_sample(const uint32_t *sobol, uint32_t index, uint32_t dim, uint32_t scramble);
 void     oracle_filter_cdf(uint32_t filter, float *cdf32, float *bin_size);
 float    oracle_diffuse_fresnel(float ior, int sample_count);
+int      oracle_kat_eval(int which, const float *in, float *out);
 
 #ifdef __cplusplus
 }

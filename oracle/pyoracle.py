@@ -39,6 +39,7 @@ def lib():
         L.oracle_sobol_sample.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32]
         L.oracle_filter_cdf.argtypes = [C.c_uint32, C.c_void_p, C.POINTER(C.c_float)]
         L.oracle_diffuse_fresnel.restype = C.c_float; L.oracle_diffuse_fresnel.argtypes = [C.c_float, C.c_int]
+        L.oracle_kat_eval.restype = C.c_int; L.oracle_kat_eval.argtypes = [C.c_int, C.c_void_p, C.c_void_p]
         _LIB = L
     return _LIB
 
@@ -94,3 +95,9 @@ class Oracle:
         hits = (abi.Hit*len(rays))()
         lib().oracle_trace_closest(self.h, rays.ctypes.data, hits, len(rays))
         return np.ctypeslib.as_array(hits).copy() if len(rays) else np.zeros(0)
+
+
+def kat_eval(which, args):
+    a = np.array(args, dtype=np.float32); out = np.zeros(8, dtype=np.float32)
+    n = lib().oracle_kat_eval(which, a.ctypes.data, out.ctypes.data)
+    return out[:n]

@@ -1,0 +1,142 @@
+"""Host-side logic: scene flattening (fp32, reference operation order), formats, spp stepping of the Integrator
+mirror, tile sharding.  No GPU, no oracle compute."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from tungsten_b200 import abi, scene, synth, integrator, lib
+
+
+def test_wo3_roundtrip(tmp_path):
+    v, t = synth.icosphere(2)
+    p = str(tmp_path/"m.wo3")
+    scene.save_wo3(p, v, t)
+    assert os.path.getsize(p) == 8 + 32*len(v) + 8 + 16*len(t)
+    v2, t2 = scene.load_wo3(p)
+    assert np.array_equal(v2, v) and np.array_equal(t2, t)
+    assert len(t) == 20*4**2
+
+
+def test_pfm_roundtrip(tmp_path):
+    img = np.random.RandomState(0).rand(5, 7, 3).astype(np.float32)
+    p = str(tmp_path/"a.pfm")
+    scene.save_pfm(p, img)
+    assert np.array_equal(scene.load_pfm(p), img)
+
+
+def test_cornell_flattening():
+    fs = scene.load_scene(synth.cornell_box(res=(100, 50), spp=4))
+    assert fs.resolution == (100, 50)
+    assert len(fs.primitives) == 8 and len(fs.bsdfs) == 8
+    floor = fs.primitives[0]
+    assert floor.type == abi.PRIM_QUAD
+    # floor: scale (2,4,2), rotation (0,90,0): 2x2 square at y=0
+    e0 = np.array(floor.edge0[:]); e1 = np.array(floor.edge1[:]); base = np.array(floor.base[:])
+    assert abs(np.linalg.norm(e0) - 2) < 1e-6 and abs(np.linalg.norm(e1) - 2) < 1e-6
+    assert abs(base[1]) < 1e-6 and np.allclose(np.abs(base[[0, 2]]), 1, atol=1e-6)
+    n = np.cross(e1, e0)
+    assert n[1] > 0                                    # floor normal points up
+    light = fs.primitives[-1]
+    assert light.emission_tex >= 0 and fs.textures[light.emission_tex].value[0] == 17
+    ln = np.cross(np.array(light.edge1[:]), np.array(light.edge0[:]))
+    assert ln[1] < 0                                   # light faces down
+    cube = fs.primitives[5]
+    assert cube.type == abi.PRIM_CUBE
+    r = np.array(cube.rot[:]).reshape(3, 3)
+    assert np.allclose(r @ r.T, np.eye(3), atol=1e-5)
+    assert np.allclose(np.array(cube.scale[:])*2, [0.594811, 0.604394, 0.6], atol=1e-6)
+    cam = fs.camera
+    assert np.allclose(cam.pos[:], [0, 1, 6.8]) and cam.fov_deg == 35 and cam.filter == abi.FILTER_TENT
+    m = np.array(cam.xform[:]).reshape(3, 3)
+    assert np.allclose(m[:, 2], [0, 0, -1], atol=1e-6)  # looks down -z
+    assert np.allclose(m[:, 0], [1, 0, 0], atol=1e-6)   # right vector after setRight(-right)
+    s = fs.settings
+    assert (s.max_bounces, s.min_bounces, s.enable_light_sampling, s.use_sobol) == (64, 0, 1, 1)
+    assert fs.spp == 4 and fs.adaptive is False
+
+
+def test_transform_parse_variants():
+    ident = scene.parse_transform(None)
+    assert np.array_equal(ident, np.eye(4, dtype=np.float32))
+    m = scene.parse_transform({"position": [1, 2, 3], "scale": 2, "rotation": [0, 0, 0]})
+    assert np.allclose(m, [[2, 0, 0, 1], [0, 2, 0, 2], [0, 0, 2, 3], [0, 0, 0, 1]])
+    m = scene.parse_transform({"position": [0, 0, 0], "rotation": [0, 90, 0]})
+    assert np.allclose(m[:3, :3] @ m[:3, :3].T, np.eye(3), atol=1e-6)
+    assert np.allclose(m[:3, 0], [0, 0, 1], atol=1e-6) or np.allclose(m[:3, 0], [0, 0, -1], atol=1e-6)
+    m16 = scene.parse_transform(list(range(16)))
+    assert m16[1, 2] == 6
+    with pytest.raises(scene.SceneError):
+        scene.parse_transform([1, 2, 3])
+
+
+def test_out_of_scope_features_are_rejected(tmp_path):
+    base = synth.cornell_box(res=(8, 8), spp=1)
+    for mut in [lambda s: s.__setitem__("media", [{"type": "homogeneous"}]),
+                lambda s: s["integrator"].__setitem__("type", "bidirectional_path_tracer"),
+                lambda s: s["camera"].__setitem__("type", "thinlens"),
+                lambda s: s["bsdfs"].append({"name": "x", "type": "phong"}),
+                lambda s: s["primitives"].append({"type": "sphere", "bsdf": "floor"}),
+                lambda s: s["bsdfs"][0].__setitem__("bump", 0.5)]:
+        s = json.loads(json.dumps(base)); mut(s)
+        with pytest.raises(scene.SceneError):
+            scene.load_scene(s)
+
+
+def test_mesh_transform_and_material_clamp(tmp_path):
+    p = synth.cornell_mesh(str(tmp_path), subdiv=1, res=(8, 8), spp=1)
+    fs = scene.load_scene(p)
+    mesh = [q for q in fs.primitives if q.type == abi.PRIM_MESH][0]
+    assert mesh.n_tris == 80 and mesh.smooth == 1
+    pos = np.ctypeslib.as_array(mesh.verts, (mesh.n_verts,))["pos"]
+    assert pos[:, 1].min() > 0.0 and pos[:, 1].max() < 2.0      # inside the box
+    tris = np.ctypeslib.as_array(mesh.tris, (mesh.n_tris,))
+    assert tris["material"].min() == 0 and tris["material"].max() == 0
+
+
+class _FakeCtx:
+    def __init__(self): self.calls = []; self.aborted = False
+    def render_resident(self, count, seed, spp_begin, tiles): self.calls.append((spp_begin, count, len(tiles)))
+    def clear(self): pass
+    def close(self): pass
+    def abort(self): self.aborted = True
+    def read_framebuffer(self): return np.zeros((1, 1, 3), np.float32), None
+
+
+def test_integrator_spp_stepping(monkeypatch):
+    """Integrator::advanceSpp / done / startRender (Integrator.cpp:51, PathTraceIntegrator.cpp:220-239)."""
+    sc = synth.cornell_box(res=(40, 24), spp=40); sc["renderer"]["spp_step"] = 16
+    fs = scene.load_scene(sc)
+    fake = _FakeCtx()
+    monkeypatch.setattr(lib, "Context", lambda *a, **k: fake)
+    it = integrator.B200PathTraceIntegrator()
+    it.prepareForRender(fs, 0xBA5EBA11)
+    assert (it.currentSpp(), it.nextSpp(), it.done()) == (0, 16, False)
+    fired = []
+    while not it.done():
+        it.startRender(lambda: fired.append(1)); it.waitForCompletion()
+    assert fake.calls == [(0, 16, 6), (16, 16, 6), (32, 8, 6)]
+    assert it.currentSpp() == 40 and len(fired) == 3
+    it.startRender(lambda: fired.append(1))            # no work left: callback fires synchronously
+    assert len(fired) == 4
+    it.teardownAfterRender()
+
+
+def test_integrator_rejects_adaptive(monkeypatch):
+    sc = synth.cornell_box(res=(16, 16), spp=4); sc["renderer"]["adaptive_sampling"] = True
+    fs = scene.load_scene(sc)
+    with pytest.raises(lib.TgbError):
+        integrator.B200PathTraceIntegrator().prepareForRender(fs, 1)
+
+
+def test_tile_sharding_partitions_the_image():
+    tiles = integrator.dice_tiles(100, 50, 5)
+    assert len(tiles) == 7*4
+    seen = np.zeros((50, 100), dtype=int)
+    for r in range(3):
+        for t in integrator.shard_tiles(tiles, r, 3):
+            seen[t.y:t.y + t.h, t.x:t.x + t.w] += 1
+    assert (seen == 1).all()
+    assert tiles[6].w == 4 and tiles[21].h == 2
+    assert len({t.sampler_seed for t in tiles}) == len(tiles)

@@ -86,12 +86,13 @@ class Hit(C.Structure):
 
 class Stats(C.Structure):
     _fields_ = [("samples", u64), ("rays", u64), ("hits", u64), ("kernel_launches", u64),
-                ("trace_ms", C.c_double), ("trace_launches", u64), ("total_ms", C.c_double)]
+                ("trace_ms", C.c_double), ("trace_launches", u64), ("total_ms", C.c_double),
+                ("path_rays", u64), ("shadow_rays", u64), ("shadow_ms", C.c_double), ("shadow_launches", u64)]
 
 
 EXPORTS = [
     "tgb200_create", "tgb200_render_tiles", "tgb200_render_resident", "tgb200_clear_framebuffer",
-    "tgb200_read_framebuffer", "tgb200_framebuffer_device_ptr", "tgb200_trace_closest",
+    "tgb200_read_framebuffer", "tgb200_framebuffer_device_ptr", "tgb200_trace_closest", "tgb200_pack_tiles", "tgb200_unpack_tiles",
     "tgb200_get_stats", "tgb200_set_profiling", "tgb200_scene_info", "tgb200_reset_stats", "tgb200_abort", "tgb200_destroy", "tgb200_last_error",
     "tgb200_abi_version",
 ]

@@ -49,7 +49,7 @@ struct tgb_ctx {
     std::vector<tgb_tile> tiles_cached; uint32_t *pix_id = nullptr, *pix_seed = nullptr; uint32_t n_pix = 0, pix_capacity = 0;
     tgb_stats stats{};
     bool profiling = false;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr, evt0 = nullptr, evt1 = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, evt0 = nullptr, evt1 = nullptr, evs0 = nullptr, evs1 = nullptr;
     uint32_t bvh_depth = 0; uint32_t n_tris = 0; double bvh_sah = 0.0; size_t geom_bytes = 0;
 };
 
@@ -490,7 +490,7 @@ int render_device(tgb_ctx *c, uint32_t spp_begin, uint32_t spp_count) {
     const DScene &sc = c->sc;
     CU(cudaEventRecord(c->ev0, c->stream));
     uint64_t launches = 0;
-    float trace_ms = 0.0f; uint64_t trace_launches = 0;
+    float trace_ms = 0.0f, shadow_ms = 0.0f; uint64_t trace_launches = 0;
     for (uint32_t pix0 = 0; pix0 < c->n_pix; pix0 += c->capacity) {
         uint32_t npx = std::min(c->capacity, c->n_pix - pix0);
         uint32_t chunk = std::max(1u, c->capacity/npx);
@@ -509,11 +509,16 @@ int render_device(tgb_ctx *c, uint32_t spp_begin, uint32_t spp_count) {
                 k_trace<<<blocks(n_active, 128), 128, 0, c->stream>>>(sc, c->st, qa, ca, c->ctr); launches++;
                 if (c->profiling) CU(cudaEventRecord(c->evt1, c->stream));
                 k_shade<<<blocks(n_active, 128), 128, 0, c->stream>>>(sc, c->st, bi, qa, ca, c->squeue, cs); launches++;
+                if (c->profiling) CU(cudaEventRecord(c->evs0, c->stream));
                 k_shadow<<<blocks(2*n_active, 128), 128, 0, c->stream>>>(sc, c->st, c->squeue, cs, c->ctr); launches++;
+                if (c->profiling) CU(cudaEventRecord(c->evs1, c->stream));
                 k_accum<<<blocks(n_active, 256), 256, 0, c->stream>>>(sc, c->st, qa, ca, qb, cb); launches++;
                 CU(cudaMemcpyAsync(c->h_counts, c->counts, 3*sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
                 CU(cudaStreamSynchronize(c->stream));
-                if (c->profiling) { float ms = 0.0f; cudaEventElapsedTime(&ms, c->evt0, c->evt1); trace_ms += ms; trace_launches++; }
+                if (c->profiling) {
+                    float ms = 0.0f; cudaEventElapsedTime(&ms, c->evt0, c->evt1); trace_ms += ms; trace_launches++;
+                    cudaEventElapsedTime(&ms, c->evs0, c->evs1); shadow_ms += ms;
+                }
                 n_active = c->h_counts[cb - c->counts];
                 std::swap(qa, qb); std::swap(ca, cb);
                 if (bounce > 4096) return fail(c, TGB_ERR_CUDA, "wavefront loop did not terminate");
@@ -527,7 +532,9 @@ int render_device(tgb_ctx *c, uint32_t spp_begin, uint32_t spp_count) {
     CU(cudaGetLastError());
     float ms = 0.0f; cudaEventElapsedTime(&ms, c->ev0, c->ev1);
     c->stats.samples += uint64_t(c->n_pix)*spp_count;
-    c->stats.rays = c->h_ctr->rays; c->stats.hits = c->h_ctr->hits;
+    c->stats.path_rays = c->h_ctr->rays; c->stats.shadow_rays = c->h_ctr->shadow_rays;
+    c->stats.rays = c->h_ctr->rays + c->h_ctr->shadow_rays; c->stats.hits = c->h_ctr->hits + c->h_ctr->shadow_hits;
+    c->stats.shadow_ms += shadow_ms; c->stats.shadow_launches += trace_launches;
     c->stats.kernel_launches += launches;
     c->stats.total_ms += ms; c->stats.trace_ms += trace_ms; c->stats.trace_launches += trace_launches;
     return TGB_OK;
@@ -550,7 +557,7 @@ void tgb200_destroy(tgb_ctx *c) {
     if (c->h_ctr) cudaFreeHost(c->h_ctr);
     if (c->h_fb) cudaFreeHost(c->h_fb);
     if (c->h_fb_count) cudaFreeHost(c->h_fb_count);
-    for (cudaEvent_t e : {c->ev0, c->ev1, c->evt0, c->evt1}) if (e) cudaEventDestroy(e);
+    for (cudaEvent_t e : {c->ev0, c->ev1, c->evt0, c->evt1, c->evs0, c->evs1}) if (e) cudaEventDestroy(e);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -578,7 +585,7 @@ int tgb200_create(const tgb_scene_desc *d, tgb_ctx **out) {
     do {
         if (cudaSetDevice(dev) != cudaSuccess) { rc = fail(c, TGB_ERR_CUDA, "cudaSetDevice(%d) failed", dev); break; }
         if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { rc = fail(c, TGB_ERR_CUDA, "cudaStreamCreate failed"); break; }
-        for (cudaEvent_t *e : {&c->ev0, &c->ev1, &c->evt0, &c->evt1}) cudaEventCreate(e);
+        for (cudaEvent_t *e : {&c->ev0, &c->ev1, &c->evt0, &c->evt1, &c->evs0, &c->evs1}) cudaEventCreate(e);
         if ((rc = upload_scene(c, d))) break;
         uint32_t cap = d->settings.max_paths_in_flight ? d->settings.max_paths_in_flight : (1u << 22);
         cap = std::max(cap, 1024u);
@@ -702,6 +709,50 @@ int tgb200_scene_info(tgb_ctx *c, uint32_t *n_tris, uint32_t *n_nodes, uint32_t 
     if (bvh_depth) *bvh_depth = c->bvh_depth;
     if (geom_bytes) *geom_bytes = c->geom_bytes;
     if (capacity) *capacity = c->capacity;
+    return TGB_OK;
+}
+
+static int tile_pixels(tgb_ctx *c, const tgb_tile *tiles, uint32_t n_tiles, uint32_t **dev, uint32_t *n_out) {
+    std::vector<uint32_t> pid;
+    for (uint32_t t = 0; t < n_tiles; ++t) {
+        const tgb_tile &tl = tiles[t];
+        if (tl.x + tl.w > c->res_x || tl.y + tl.h > c->res_y) return fail(c, TGB_ERR_INVALID, "tile %u lies outside the image", t);
+        for (uint32_t y = 0; y < tl.h; ++y) for (uint32_t x = 0; x < tl.w; ++x) pid.push_back((tl.x + x) + (tl.y + y)*c->res_x);
+    }
+    *n_out = uint32_t(pid.size()); *dev = nullptr;
+    if (pid.empty()) return TGB_OK;
+    CU(cudaMalloc(reinterpret_cast<void **>(dev), pid.size()*4));
+    cudaError_t e = cudaMemcpyAsync(*dev, pid.data(), pid.size()*4, cudaMemcpyHostToDevice, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    if (e != cudaSuccess) { cudaFree(*dev); *dev = nullptr; return fail(c, TGB_ERR_CUDA, "tile upload failed: %s", cudaGetErrorString(e)); }
+    return TGB_OK;
+}
+
+int tgb200_pack_tiles(tgb_ctx *c, const tgb_tile *tiles, uint32_t n_tiles, void *rgb_out_dev) {
+    if (!c || !tiles || !rgb_out_dev) return TGB_ERR_INVALID;
+    CU(cudaSetDevice(c->device));
+    uint32_t *pid = nullptr, n = 0;
+    int rc = tile_pixels(c, tiles, n_tiles, &pid, &n);
+    if (rc || !n) return rc;
+    k_pack_tiles<<<blocks(n, 256), 256, 0, c->stream>>>(pid, n, c->fb, static_cast<float *>(rgb_out_dev));
+    c->stats.kernel_launches++;
+    cudaError_t e = cudaStreamSynchronize(c->stream);
+    cudaFree(pid);
+    if (e != cudaSuccess) return fail(c, TGB_ERR_CUDA, "pack_tiles failed: %s", cudaGetErrorString(e));
+    return TGB_OK;
+}
+
+int tgb200_unpack_tiles(tgb_ctx *c, const tgb_tile *tiles, uint32_t n_tiles, const void *rgb_in_dev, uint32_t sample_count) {
+    if (!c || !tiles || !rgb_in_dev) return TGB_ERR_INVALID;
+    CU(cudaSetDevice(c->device));
+    uint32_t *pid = nullptr, n = 0;
+    int rc = tile_pixels(c, tiles, n_tiles, &pid, &n);
+    if (rc || !n) return rc;
+    k_unpack_tiles<<<blocks(n, 256), 256, 0, c->stream>>>(pid, n, static_cast<const float *>(rgb_in_dev), c->fb, c->fb_count, sample_count);
+    c->stats.kernel_launches++;
+    cudaError_t e = cudaStreamSynchronize(c->stream);
+    cudaFree(pid);
+    if (e != cudaSuccess) return fail(c, TGB_ERR_CUDA, "unpack_tiles failed: %s", cudaGetErrorString(e));
     return TGB_OK;
 }
 

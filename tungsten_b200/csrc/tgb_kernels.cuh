@@ -33,7 +33,7 @@ enum : uint32_t { F_WAS_SPECULAR = 1u << 24, F_ALIVE = 1u << 25, F_FINAL_CHECK =
                   F_HAS_SURF = 1u << 28 };
 constexpr int HID_MISS = -1;
 
-struct Counters { unsigned long long rays, hits; };
+struct Counters { unsigned long long rays, hits, shadow_rays, shadow_hits; };   // path queries / NEE+MIS queries
 
 // ---- closest-hit traversal -------------------------------------------------------------------
 struct Hit { float t, u, v; int id; };
@@ -258,12 +258,12 @@ __global__ void __launch_bounds__(256) k_raygen(DScene sc, PathState st, BatchIn
     queue[i] = i;
 }
 
-template <int BLOCK>
+template <bool SHADOW>
 TGB_D void count_rays(Counters *ctr, bool valid, bool hit) {
     unsigned mv = __ballot_sync(0xffffffffu, valid), mh = __ballot_sync(0xffffffffu, valid && hit);
     if ((threadIdx.x & 31) == 0 && mv) {
-        atomicAdd(&ctr->rays, (unsigned long long)__popc(mv));
-        if (mh) atomicAdd(&ctr->hits, (unsigned long long)__popc(mh));
+        atomicAdd(SHADOW ? &ctr->shadow_rays : &ctr->rays, (unsigned long long)__popc(mv));
+        if (mh) atomicAdd(SHADOW ? &ctr->shadow_hits : &ctr->hits, (unsigned long long)__popc(mh));
     }
 }
 
@@ -277,7 +277,7 @@ __global__ void __launch_bounds__(128) k_trace(DScene sc, PathState st, const ui
         h = trace_closest(sc, o, d, st.tmin[s], INFINITY);
         st.ht[s] = h.t; st.hu[s] = h.u; st.hv[s] = h.v; st.hid[s] = h.id;
     }
-    count_rays<128>(ctr, valid, h.id != HID_MISS);
+    count_rays<false>(ctr, valid, h.id != HID_MISS);
 }
 
 // Parity hook: rays in AoS tgb_ray, hits out as tgb_hit (tgb200_trace_closest).
@@ -556,7 +556,7 @@ __global__ void __launch_bounds__(128) k_shadow(DScene sc, PathState st, const u
             }
         }
     }
-    count_rays<128>(ctr, valid, anyhit);
+    count_rays<true>(ctr, valid, anyhit);
 }
 
 // Fold this bounce's direct light + surface emission into the path (order as in handleSurface:537-543),
@@ -619,6 +619,22 @@ __global__ void __launch_bounds__(256) k_resolve(PathState st, BatchInfo bi, uin
     }
     fb[3*size_t(pid)] = mx; fb[3*size_t(pid) + 1] = my; fb[3*size_t(pid) + 2] = mz;
     fb_count[pid] = cnt;
+}
+
+// Tile-major pack / unpack of the resident framebuffer: the send/receive side of the one collective on
+// this path (all-gather of the rendered tiles across GPUs).
+__global__ void __launch_bounds__(256) k_pack_tiles(const uint32_t *pix_id, uint32_t n_pix, const float *fb, float *out) {
+    uint32_t i = blockIdx.x*blockDim.x + threadIdx.x;
+    if (i >= n_pix) return;
+    size_t p = size_t(pix_id[i])*3;
+    out[3*size_t(i)] = fb[p]; out[3*size_t(i) + 1] = fb[p + 1]; out[3*size_t(i) + 2] = fb[p + 2];
+}
+__global__ void __launch_bounds__(256) k_unpack_tiles(const uint32_t *pix_id, uint32_t n_pix, const float *in, float *fb, uint32_t *fb_count, uint32_t count) {
+    uint32_t i = blockIdx.x*blockDim.x + threadIdx.x;
+    if (i >= n_pix) return;
+    size_t p = size_t(pix_id[i])*3;
+    fb[p] = in[3*size_t(i)]; fb[p + 1] = in[3*size_t(i) + 1]; fb[p + 2] = in[3*size_t(i) + 2];
+    fb_count[pix_id[i]] = count;
 }
 
 }  // namespace tgb

@@ -1,0 +1,177 @@
+"""Host-side mirror of the reference's Integrator interface for the path_tracer hot path.
+
+`B200PathTraceIntegrator` has the reference's method names, argument meaning and error behaviour
+(reference: src/core/integrators/Integrator.hpp:16-63, Integrator.cpp:51;
+integrators/path_tracer/PathTraceIntegrator.cpp:27-42,110-134,184-254) and drives the CUDA library through the
+C ABI.  It is the Python twin of the C++ adapter in integration/B200PathTraceIntegrator.{hpp,cpp};
+the parity tests use it the way `StandaloneRenderer::renderScene` uses an Integrator (src/tungsten/Shared.hpp:255-319).
+
+Host logic only (tile dicing, tile seeds, spp stepping, async start/wait/abort, tile sharding across ranks);
+no rendering arithmetic lives here.
+"""
+import threading
+
+import numpy as np
+
+from . import abi, lib
+
+TILE_SIZE = 16            # PathTraceIntegrator::TileSize (PathTraceIntegrator.hpp:27)
+MASK32 = 0xFFFFFFFF
+
+
+def hash32(x):
+    """MathUtil::hash32 (math/MathUtil.hpp:120-128)."""
+    x &= MASK32
+    x = (~x + (x << 15)) & MASK32
+    x ^= x >> 12
+    x = (x + (x << 2)) & MASK32
+    x ^= x >> 4
+    x = (x*2057) & MASK32
+    x ^= x >> 16
+    return x
+
+
+class UniformSampler:
+    """PCG32 (sampling/UniformSampler.hpp:40-52), sequence 0."""
+
+    def __init__(self, seed):
+        self.state = seed & 0xFFFFFFFFFFFFFFFF
+
+    def next_i(self):
+        old = self.state
+        self.state = (old*6364136223846793005 + 1) & 0xFFFFFFFFFFFFFFFF
+        xs = (((old >> 18) ^ old) >> 27) & MASK32
+        rot = old >> 59
+        return ((xs >> rot) | (xs << ((-rot) & 31))) & MASK32
+
+
+def dice_tiles(w, h, seed):
+    """PathTraceIntegrator::diceTiles with the sampler seeded as in prepareForRender
+    (PathTraceIntegrator.cpp:27-42,187): row-major 16x16 tiles, tile sampler seed = hash32(_sampler.nextI())."""
+    s = UniformSampler(hash32(seed))
+    n = ((w + TILE_SIZE - 1)//TILE_SIZE)*((h + TILE_SIZE - 1)//TILE_SIZE)
+    tiles = (abi.Tile*n)()
+    i = 0
+    for y in range(0, h, TILE_SIZE):
+        for x in range(0, w, TILE_SIZE):
+            tiles[i] = abi.Tile(x, y, min(TILE_SIZE, w - x), min(TILE_SIZE, h - y), hash32(s.next_i()))
+            i += 1
+    return tiles
+
+
+def shard_tiles(tiles, rank, world):
+    """Deal tiles round-robin to ranks (tile id mod world): scenes shard by image tile only."""
+    mine = [tiles[i] for i in range(rank, len(tiles), world)]
+    return (abi.Tile*len(mine))(*mine)
+
+
+class B200PathTraceIntegrator:
+    """prepareForRender / startRender / waitForCompletion / abortRender / teardownAfterRender / done /
+    currentSpp / nextSpp -- same contract as the reference's PathTraceIntegrator, GPU underneath."""
+
+    def __init__(self, rank=0, world=1, device=-1, max_paths_in_flight=0):
+        self._scene = None
+        self._ctx = None
+        self._current_spp = 0
+        self._next_spp = 0
+        self._thread = None
+        self._error = None
+        self.rank, self.world, self.device = rank, world, device
+        self.max_paths_in_flight = max_paths_in_flight
+        self.tiles = None
+        self.all_tiles = None
+        self.seed = 0
+
+    # -- Integrator.cpp:51
+    def _advance_spp(self):
+        self._next_spp = min(self._current_spp + self._scene.spp_step, self._scene.spp)
+
+    def prepareForRender(self, flat_scene, seed):
+        """PathTraceIntegrator::prepareForRender (PathTraceIntegrator.cpp:184-201)."""
+        if flat_scene.adaptive:
+            raise lib.TgbError(abi.TGB_ERR_UNSUPPORTED, "adaptive sampling is outside the hot path (set renderer.adaptive_sampling=false)")
+        self._scene = flat_scene
+        self.seed = seed & MASK32
+        self._current_spp = 0
+        self._advance_spp()
+        self._ctx = lib.Context(flat_scene, device=self.device, max_paths_in_flight=self.max_paths_in_flight)
+        w, h = flat_scene.resolution
+        self.all_tiles = dice_tiles(w, h, self.seed)
+        self.tiles = shard_tiles(self.all_tiles, self.rank, self.world)
+        self._ctx.clear()
+
+    def teardownAfterRender(self):
+        self.waitForCompletion_noraise()
+        if self._ctx is not None:
+            self._ctx.close()
+        self._ctx = None
+        self.tiles = self.all_tiles = None
+
+    def done(self):
+        return self._current_spp >= self._next_spp
+
+    def currentSpp(self):
+        return self._current_spp
+
+    def nextSpp(self):
+        return self._next_spp
+
+    def startRender(self, completionCallback=lambda: None):
+        """Asynchronous like the reference (PathTraceIntegrator.cpp:220-239): returns after enqueueing; the
+        callback fires when the step's samples are in the framebuffer (or immediately if there is no work)."""
+        if self.done():
+            self._current_spp = self._next_spp
+            self._advance_spp()
+            completionCallback()
+            return
+        begin, count = self._current_spp, self._next_spp - self._current_spp
+
+        def work():
+            try:
+                self._ctx.render_resident(count, seed=self.seed, spp_begin=begin, tiles=self.tiles)
+                self._current_spp = self._next_spp
+                self._advance_spp()
+            except Exception as e:      # captured and rethrown from waitForCompletion (thread/TaskGroup.hpp:57-74)
+                self._error = e
+            finally:
+                completionCallback()
+        self._thread = threading.Thread(target=work, daemon=True)
+        self._thread.start()
+
+    def waitForCompletion_noraise(self):
+        if self._thread is not None:
+            self._thread.join()
+            self._thread = None
+
+    def waitForCompletion(self):
+        self.waitForCompletion_noraise()
+        if self._error is not None:
+            e, self._error = self._error, None
+            if isinstance(e, lib.TgbError) and e.code == abi.TGB_ERR_ABORTED:
+                return
+            raise e
+
+    def abortRender(self):
+        """PathTraceIntegrator::abortRender (PathTraceIntegrator.cpp:249-254): abort + wait."""
+        if self._ctx is not None and self._thread is not None:
+            self._ctx.abort()
+        self.waitForCompletion()
+
+    def framebuffer(self):
+        """Camera::getLinear for every pixel (cameras/Camera.hpp:163-172): float32 (h, w, 3), top row first."""
+        return self._ctx.read_framebuffer()[0]
+
+    def render(self, flat_scene, seed=0xBA5EBA11):
+        """The loop of StandaloneRenderer::renderScene (src/tungsten/Shared.hpp:283-296)."""
+        self.prepareForRender(flat_scene, seed)
+        try:
+            while not self.done():
+                self.startRender()
+                self.waitForCompletion()
+            return self.framebuffer()
+        finally:
+            self.teardownAfterRender()
+
+    @property
+    def context(self):
+        return self._ctx

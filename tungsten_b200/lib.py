@@ -33,6 +33,8 @@ def load():
     L.tgb200_read_framebuffer.argtypes = [vp, vp, vp]
     L.tgb200_framebuffer_device_ptr.argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_uint64)]
     L.tgb200_trace_closest.argtypes = [vp, vp, vp, u32]
+    L.tgb200_pack_tiles.argtypes = [vp, vp, u32, vp]
+    L.tgb200_unpack_tiles.argtypes = [vp, vp, u32, vp, u32]
     L.tgb200_get_stats.argtypes = [vp, C.POINTER(abi.Stats)]
     L.tgb200_set_profiling.argtypes = [vp, C.c_int]
     L.tgb200_scene_info.argtypes = [vp, C.POINTER(u32), C.POINTER(u32), C.POINTER(u32), C.POINTER(C.c_uint64), C.POINTER(u32)]
@@ -103,6 +105,12 @@ class Context:
         p = C.c_void_p(); n = C.c_uint64()
         self._check(self.L.tgb200_framebuffer_device_ptr(self.h, C.byref(p), C.byref(n)))
         return p.value, n.value
+
+    def pack_tiles(self, tiles, dev_ptr):
+        self._check(self.L.tgb200_pack_tiles(self.h, tiles, len(tiles), dev_ptr))
+
+    def unpack_tiles(self, tiles, dev_ptr, sample_count):
+        self._check(self.L.tgb200_unpack_tiles(self.h, tiles, len(tiles), dev_ptr, sample_count))
 
     def trace_closest(self, rays):
         rays = np.ascontiguousarray(rays, dtype=np.float32).reshape(-1, 8)
