@@ -25,6 +25,18 @@ def needs_build():
     return any(os.path.getmtime(d) > t for d in deps)
 
 
+def build_variant(name, defines):
+    """Experimental build with extra -D flags -> tungsten_b200/libtgb200_<name>.so (load with TGB200_LIB)."""
+    out = os.path.join(HERE, "libtgb200_%s.so" % name)
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    cmd = [nvcc] + NVCC_FLAGS + ["-D" + d for d in defines] + [os.path.join(CSRC, s) for s in SOURCES] + ["-o", out, "-ccbin", "/usr/bin/g++"]
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if r.returncode != 0:
+        sys.stderr.write(r.stdout)
+        raise RuntimeError("nvcc failed")
+    return out
+
+
 def build(force=False, verbose=False):
     if not force and not needs_build():
         return OUT

@@ -101,14 +101,14 @@ inline float pad_up(float v) { return std::nextafter(std::nextafter(v, std::nume
 
 }  // namespace
 
-void build_bvh2(const BuildTri *tris, uint32_t n, Bvh2 &out, int threads) {
+void build_bvh2(const BuildTri *tris, uint32_t n, Bvh2 &out, int threads, float abs_pad) {
     out.nodes.clear(); out.order.clear(); out.root_link = 0; out.max_depth = 0; out.sah_cost = 0.0;
     for (int a = 0; a < 3; ++a) { out.lo[a] = std::numeric_limits<float>::infinity(); out.hi[a] = -out.lo[a]; }
     if (n == 0) return;
     std::vector<Box> tb(n); std::vector<float> cent(3*size_t(n));
     for (uint32_t i = 0; i < n; ++i) {
         Box b; b.reset(); b.grow(tris[i].v0); b.grow(tris[i].v1); b.grow(tris[i].v2);
-        for (int a = 0; a < 3; ++a) { cent[3*size_t(i) + a] = 0.5f*b.lo[a] + 0.5f*b.hi[a]; b.lo[a] = pad_down(b.lo[a]); b.hi[a] = pad_up(b.hi[a]); }
+        for (int a = 0; a < 3; ++a) { cent[3*size_t(i) + a] = 0.5f*b.lo[a] + 0.5f*b.hi[a]; b.lo[a] = pad_down(b.lo[a] - abs_pad); b.hi[a] = pad_up(b.hi[a] + abs_pad); }
         tb[i] = b;
     }
     out.order.resize(n);

@@ -34,6 +34,7 @@ struct Bvh2 {
 };
 
 // threads <= 0: hardware concurrency.
-void build_bvh2(const BuildTri *tris, uint32_t n, Bvh2 &out, int threads = 0);
+// abs_pad: every triangle box is grown by this absolute amount (covers the slab test's rounding).
+void build_bvh2(const BuildTri *tris, uint32_t n, Bvh2 &out, int threads = 0, float abs_pad = 0.0f);
 
 }  // namespace tgb

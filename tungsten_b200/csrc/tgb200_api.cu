@@ -371,7 +371,12 @@ int upload_scene(tgb_ctx *c, const tgb_scene_desc *d) {
 
     // ---- BVH over every mesh triangle
     Bvh2 bvh;
-    build_bvh2(btris.data(), uint32_t(btris.size()), bvh, 0);
+    // Box padding that covers the rounding of the fused slab test t = fma(lo, 1/d, -(o/d)): spatial error
+    // <= (2|o| + |lo|) * 2^-24, so 1e-6 x the largest coordinate magnitude in play (scene or camera) is ample.
+    float extent = std::max(std::max(std::fabs(sc.cam.pos.x), std::fabs(sc.cam.pos.y)), std::fabs(sc.cam.pos.z));
+    for (const BuildTri &t : btris) for (int k = 0; k < 3; ++k)
+        extent = std::max(extent, std::max(std::fabs(t.v0[k]), std::max(std::fabs(t.v1[k]), std::fabs(t.v2[k]))));
+    build_bvh2(btris.data(), uint32_t(btris.size()), bvh, 0, 1e-6f*extent);
     if (bvh.max_depth + 2 > uint32_t(kStackSize)) return fail(c, TGB_ERR_UNSUPPORTED, "BVH depth %u exceeds the traversal stack", bvh.max_depth);
     c->bvh_depth = bvh.max_depth; c->n_tris = uint32_t(btris.size()); c->bvh_sah = bvh.sah_cost;
     std::vector<float4> tri_isect(3*btris.size());

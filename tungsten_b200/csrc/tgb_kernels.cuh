@@ -79,11 +79,20 @@ constexpr int kStackSize = 64;
 
 // Closest hit over the whole scene.  Triangle test = Embree's MoellerTrumboreIntersector1
 // (thirdparty/embree/kernels/geometry/triangle_intersector_moeller.h:75-111) with IEEE division for t,u,v.
+#ifndef TGB_TRAV
+#define TGB_TRAV 0
+#endif
+#ifndef TGB_FMA_SLAB
+#define TGB_FMA_SLAB 0
+#endif
+#if TGB_TRAV == 0
+// Per-lane while-while traversal (independent thread scheduling interleaves the divergent lane groups).
 // ANY = true: occlusion query for a light whose own hit was already resolved analytically -- returns at the
 // first surface in [tnear, tfar] other than primitive `ignore` (generalizedShadowRay's blocker test).
 template <bool ANY>
-TGB_D Hit trace_scene(const DScene &sc, V3 o, V3 d, float tnear, float tfar, int ignore) {
+TGB_D Hit trace_scene(const DScene &sc, bool active, V3 o, V3 d, float tnear, float tfar, int ignore) {
     Hit h; h.t = tfar; h.u = 0.0f; h.v = 0.0f; h.id = HID_MISS;
+    if (!active) return h;
     for (int i = 0; i < sc.n_analytic; ++i) {
         int pi = sc.analytic[i];
         if (ANY && pi == ignore) continue;
@@ -155,7 +164,190 @@ TGB_D Hit trace_scene(const DScene &sc, V3 o, V3 d, float tnear, float tfar, int
     }
 }
 
-TGB_D Hit trace_closest(const DScene &sc, V3 o, V3 d, float tnear, float tfar) { return trace_scene<false>(sc, o, d, tnear, tfar, -1); }
+#elif TGB_TRAV == 1
+// ANY = true: occlusion query for a light whose own hit was already resolved analytically -- stops at the
+// first surface in [tnear, tfar] other than primitive `ignore` (generalizedShadowRay's blocker test).
+//
+// WARP-SYNCHRONOUS: must be called by all 32 lanes of a converged warp; lanes without a ray pass active=false.
+// Traversal is the "speculative while-while" scheme: all lanes walk inner nodes together until every lane
+// has found a leaf (one leaf may be postponed so a lane can keep descending), then all lanes intersect their
+// leaves together.  Warp votes (__any_sync) keep the two phases converged; without them leaf tests ran with
+// ~1.6 of 32 lanes active (profiles/r01_k_trace_baseline.md).  The stack lives in local memory (L1-resident).
+constexpr int TRAV_DONE = int(0x80000000u);
+
+template <bool ANY>
+TGB_D Hit trace_scene(const DScene &sc, bool active, V3 o, V3 d, float tnear, float tfar, int ignore) {
+    const unsigned FULL = 0xffffffffu;
+    Hit h; h.t = tfar; h.u = 0.0f; h.v = 0.0f; h.id = HID_MISS;
+    if (active) {
+        for (int i = 0; i < sc.n_analytic; ++i) {
+            int pi = sc.analytic[i];
+            if (ANY && pi == ignore) continue;
+            const DPrim &p = sc.prims[pi];
+            if (p.type == TGB_PRIM_QUAD) quad_intersect(p, pi, o, d, tnear, h);
+            else cube_intersect(p, pi, o, d, tnear, h);
+            if (ANY && h.id != HID_MISS) break;
+        }
+    }
+    int cur = (active && sc.n_nodes != 0 && !(ANY && h.id != HID_MISS)) ? 0 : TRAV_DONE;
+    if (!__any_sync(FULL, cur != TRAV_DONE)) return h;
+
+    const float ooeps = 1e-30f;
+    float idx = 1.0f/(fabsf(d.x) > ooeps ? d.x : copysignf(ooeps, d.x));
+    float idy = 1.0f/(fabsf(d.y) > ooeps ? d.y : copysignf(ooeps, d.y));
+    float idz = 1.0f/(fabsf(d.z) > ooeps ? d.z : copysignf(ooeps, d.z));
+    int stack[kStackSize]; int sp = 0;
+    int leaf = 0;                                   // postponed leaf (negative code) or 0
+    const float4 *nodes = sc.nodes;
+    while (true) {
+        // ---- phase 1: inner nodes, until every lane holds a leaf or is done
+        while (__any_sync(FULL, cur >= 0)) {
+            if (cur >= 0) {
+                const float4 n0 = __ldg(nodes + 4*cur), n1 = __ldg(nodes + 4*cur + 1), n2 = __ldg(nodes + 4*cur + 2);
+                const float4 lk = __ldg(nodes + 4*cur + 3);
+                float c0lox = (n0.x - o.x)*idx, c0hix = (n0.y - o.x)*idx, c0loy = (n0.z - o.y)*idy, c0hiy = (n0.w - o.y)*idy;
+                float c1lox = (n1.x - o.x)*idx, c1hix = (n1.y - o.x)*idx, c1loy = (n1.z - o.y)*idy, c1hiy = (n1.w - o.y)*idy;
+                float c0loz = (n2.x - o.z)*idz, c0hiz = (n2.y - o.z)*idz, c1loz = (n2.z - o.z)*idz, c1hiz = (n2.w - o.z)*idz;
+                float c0min = fmaxf(fmaxf(fminf(c0lox, c0hix), fminf(c0loy, c0hiy)), fmaxf(fminf(c0loz, c0hiz), tnear));
+                float c0max = fminf(fminf(fmaxf(c0lox, c0hix), fmaxf(c0loy, c0hiy)), fminf(fmaxf(c0loz, c0hiz), h.t));
+                float c1min = fmaxf(fmaxf(fminf(c1lox, c1hix), fminf(c1loy, c1hiy)), fmaxf(fminf(c1loz, c1hiz), tnear));
+                float c1max = fminf(fminf(fmaxf(c1lox, c1hix), fmaxf(c1loy, c1hiy)), fminf(fmaxf(c1loz, c1hiz), h.t));
+                // 2-ulp slack on the far side: slab rounding must never cull a triangle the exact test accepts
+                bool t0 = c0min <= c0max*1.0000003f, t1 = c1min <= c1max*1.0000003f;
+                int l0 = __float_as_int(lk.x), l1 = __float_as_int(lk.y);
+                if (t0 && t1) {
+                    bool swp = c1min < c0min;
+                    cur = swp ? l1 : l0;
+                    if (sp < kStackSize) stack[sp++] = swp ? l0 : l1;
+                } else if (t0) cur = l0;
+                else if (t1) cur = l1;
+                else cur = sp ? stack[--sp] : TRAV_DONE;
+                if (cur < 0 && cur != TRAV_DONE && leaf == 0) {        // postpone the first leaf, keep descending
+                    leaf = cur;
+                    cur = sp ? stack[--sp] : TRAV_DONE;
+                }
+            }
+        }
+        // ---- phase 2: every lane intersects the leaves it holds (postponed first, then current)
+#pragma unroll 1
+        for (int k = 0; k < 2; ++k) {
+            int code;
+            if (k == 0) { code = leaf; leaf = 0; }
+            else { code = (cur != TRAV_DONE) ? cur : 0; if (code) cur = sp ? stack[--sp] : TRAV_DONE; }
+            if (!__any_sync(FULL, code != 0)) continue;
+            int first = (~code) >> 3, count = code ? ((~code) & 7) + 1 : 0;
+#pragma unroll 1
+            for (int i = 0; i < 4; ++i) {
+                if (!__any_sync(FULL, i < count)) break;
+                if (i < count) {
+                    const float4 *tr = sc.tri_isect + 3*size_t(first + i);
+                    const float4 a = __ldg(tr), b = __ldg(tr + 1), c = __ldg(tr + 2);
+                    V3 v0 = v3(a.x, a.y, a.z), e1 = v3(a.w, b.x, b.y), e2 = v3(b.z, b.w, c.x), ng = v3(c.y, c.z, c.w);
+                    V3 C = v0 - o;
+                    V3 R = cross(d, C);
+                    float den = edot(ng, d);
+                    float absDen = fabsf(den);
+                    uint32_t sgn = __float_as_uint(den) & 0x80000000u;
+                    float U = xor_sign(edot(R, e2), sgn);
+                    float V = xor_sign(edot(R, e1), sgn);
+                    if (den != 0.0f && U >= 0.0f && V >= 0.0f && U + V <= absDen) {
+                        float T = xor_sign(edot(ng, C), sgn);
+                        if (T > absDen*tnear && T < absDen*h.t) {
+                            h.t = T/absDen; h.u = U/absDen; h.v = V/absDen; h.id = first + i;
+                        }
+                    }
+                }
+            }
+            if (ANY && h.id != HID_MISS) { cur = TRAV_DONE; leaf = 0; sp = 0; }
+        }
+        if (!__any_sync(FULL, cur != TRAV_DONE)) break;
+    }
+    return h;
+}
+
+#else
+// "if-if" traversal: every loop iteration a lane performs ONE step -- either one inner-node visit (two child
+// slab tests) or one triangle test of its current leaf -- and the lanes reconverge at the end of the
+// iteration.  Compared with the per-lane while-while above this keeps the triangle tests from running with
+// 1-2 active lanes (profiles/r01_a_k_trace_baseline.md).
+template <bool ANY>
+TGB_D Hit trace_scene(const DScene &sc, bool active, V3 o, V3 d, float tnear, float tfar, int ignore) {
+    Hit h; h.t = tfar; h.u = 0.0f; h.v = 0.0f; h.id = HID_MISS;
+    if (!active) return h;
+    for (int i = 0; i < sc.n_analytic; ++i) {
+        int pi = sc.analytic[i];
+        if (ANY && pi == ignore) continue;
+        const DPrim &p = sc.prims[pi];
+        if (p.type == TGB_PRIM_QUAD) quad_intersect(p, pi, o, d, tnear, h);
+        else cube_intersect(p, pi, o, d, tnear, h);
+        if (ANY && h.id != HID_MISS) return h;
+    }
+    if (sc.n_nodes == 0) return h;
+    const float ooeps = 1e-30f;
+    float idx = 1.0f/(fabsf(d.x) > ooeps ? d.x : copysignf(ooeps, d.x));
+    float idy = 1.0f/(fabsf(d.y) > ooeps ? d.y : copysignf(ooeps, d.y));
+    float idz = 1.0f/(fabsf(d.z) > ooeps ? d.z : copysignf(ooeps, d.z));
+#if TGB_FMA_SLAB
+    float oodx = o.x*idx, oody = o.y*idy, oodz = o.z*idz;
+#endif
+    int stack[kStackSize]; int sp = 0;
+    int cur = 0;
+    const float4 *nodes = sc.nodes;
+    const int DONE = int(0x80000000u);
+    while (cur != DONE) {
+        if (cur >= 0) {
+            const float4 n0 = __ldg(nodes + 4*cur), n1 = __ldg(nodes + 4*cur + 1), n2 = __ldg(nodes + 4*cur + 2);
+            const float4 lk = __ldg(nodes + 4*cur + 3);
+#if TGB_FMA_SLAB
+            float c0lox = __fmaf_rn(n0.x, idx, -oodx), c0hix = __fmaf_rn(n0.y, idx, -oodx), c0loy = __fmaf_rn(n0.z, idy, -oody), c0hiy = __fmaf_rn(n0.w, idy, -oody);
+            float c1lox = __fmaf_rn(n1.x, idx, -oodx), c1hix = __fmaf_rn(n1.y, idx, -oodx), c1loy = __fmaf_rn(n1.z, idy, -oody), c1hiy = __fmaf_rn(n1.w, idy, -oody);
+            float c0loz = __fmaf_rn(n2.x, idz, -oodz), c0hiz = __fmaf_rn(n2.y, idz, -oodz), c1loz = __fmaf_rn(n2.z, idz, -oodz), c1hiz = __fmaf_rn(n2.w, idz, -oodz);
+#else
+            float c0lox = (n0.x - o.x)*idx, c0hix = (n0.y - o.x)*idx, c0loy = (n0.z - o.y)*idy, c0hiy = (n0.w - o.y)*idy;
+            float c1lox = (n1.x - o.x)*idx, c1hix = (n1.y - o.x)*idx, c1loy = (n1.z - o.y)*idy, c1hiy = (n1.w - o.y)*idy;
+            float c0loz = (n2.x - o.z)*idz, c0hiz = (n2.y - o.z)*idz, c1loz = (n2.z - o.z)*idz, c1hiz = (n2.w - o.z)*idz;
+#endif
+            float c0min = fmaxf(fmaxf(fminf(c0lox, c0hix), fminf(c0loy, c0hiy)), fmaxf(fminf(c0loz, c0hiz), tnear));
+            float c0max = fminf(fminf(fmaxf(c0lox, c0hix), fmaxf(c0loy, c0hiy)), fminf(fmaxf(c0loz, c0hiz), h.t));
+            float c1min = fmaxf(fmaxf(fminf(c1lox, c1hix), fminf(c1loy, c1hiy)), fmaxf(fminf(c1loz, c1hiz), tnear));
+            float c1max = fminf(fminf(fmaxf(c1lox, c1hix), fmaxf(c1loy, c1hiy)), fminf(fmaxf(c1loz, c1hiz), h.t));
+            bool t0 = c0min <= c0max*1.0000003f, t1 = c1min <= c1max*1.0000003f;
+            int l0 = __float_as_int(lk.x), l1 = __float_as_int(lk.y);
+            if (t0 && t1) {
+                bool swp = c1min < c0min;
+                cur = swp ? l1 : l0;
+                if (sp < kStackSize) stack[sp++] = swp ? l0 : l1;
+            } else if (t0) cur = l0;
+            else if (t1) cur = l1;
+            else cur = sp ? stack[--sp] : DONE;
+        } else {
+            int code = ~cur;
+            int first = code >> 3, rem = code & 7;            // rem = triangles left after this one
+            const float4 *tr = sc.tri_isect + 3*size_t(first);
+            const float4 a = __ldg(tr), b = __ldg(tr + 1), c = __ldg(tr + 2);
+            V3 v0 = v3(a.x, a.y, a.z), e1 = v3(a.w, b.x, b.y), e2 = v3(b.z, b.w, c.x), ng = v3(c.y, c.z, c.w);
+            V3 C = v0 - o;
+            V3 R = cross(d, C);
+            float den = edot(ng, d);
+            float absDen = fabsf(den);
+            uint32_t sgn = __float_as_uint(den) & 0x80000000u;
+            float U = xor_sign(edot(R, e2), sgn);
+            float V = xor_sign(edot(R, e1), sgn);
+            bool hit = false;
+            if (den != 0.0f && U >= 0.0f && V >= 0.0f && U + V <= absDen) {
+                float T = xor_sign(edot(ng, C), sgn);
+                if (T > absDen*tnear && T < absDen*h.t) {
+                    h.t = T/absDen; h.u = U/absDen; h.v = V/absDen; h.id = first; hit = true;
+                }
+            }
+            if (ANY && hit) return h;
+            cur = rem ? ~(((first + 1) << 3) | (rem - 1)) : (sp ? stack[--sp] : DONE);
+        }
+    }
+    return h;
+}
+#endif
+TGB_D Hit trace_closest(const DScene &sc, bool active, V3 o, V3 d, float tnear, float tfar) { return trace_scene<false>(sc, active, o, d, tnear, tfar, -1); }
 
 // Fill a Surface from a hit: Primitive::intersectionInfo for mesh/quad/cube
 // (TriangleMesh.cpp:323-331,344-355; Quad.cpp:112-120; Cube.cpp:157-171) + TraceableScene::intersect (:183-188)
@@ -270,22 +462,24 @@ TGB_D void count_rays(Counters *ctr, bool valid, bool hit) {
 __global__ void __launch_bounds__(128) k_trace(DScene sc, PathState st, const uint32_t *queue, const uint32_t *count, Counters *ctr) {
     uint32_t i = blockIdx.x*blockDim.x + threadIdx.x;
     bool valid = i < *count;
-    Hit h; h.id = HID_MISS;
+    uint32_t s = 0; V3 o = v3s(0.0f), d = v3(0.0f, 0.0f, 1.0f); float tmin = 0.0f;
     if (valid) {
-        uint32_t s = queue[i];
-        V3 o = v3(st.ox[s], st.oy[s], st.oz[s]), d = v3(st.dx[s], st.dy[s], st.dz[s]);
-        h = trace_closest(sc, o, d, st.tmin[s], INFINITY);
-        st.ht[s] = h.t; st.hu[s] = h.u; st.hv[s] = h.v; st.hid[s] = h.id;
+        s = queue[i];
+        o = v3(st.ox[s], st.oy[s], st.oz[s]); d = v3(st.dx[s], st.dy[s], st.dz[s]); tmin = st.tmin[s];
     }
+    Hit h = trace_closest(sc, valid, o, d, tmin, INFINITY);
+    if (valid) { st.ht[s] = h.t; st.hu[s] = h.u; st.hv[s] = h.v; st.hid[s] = h.id; }
     count_rays<false>(ctr, valid, h.id != HID_MISS);
 }
 
 // Parity hook: rays in AoS tgb_ray, hits out as tgb_hit (tgb200_trace_closest).
 __global__ void __launch_bounds__(128) k_trace_rays(DScene sc, const tgb_ray *rays, tgb_hit *hits, uint32_t n) {
     uint32_t i = blockIdx.x*blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    V3 o = v3(rays[i].o[0], rays[i].o[1], rays[i].o[2]), d = v3(rays[i].d[0], rays[i].d[1], rays[i].d[2]);
-    Hit h = trace_closest(sc, o, d, rays[i].tmin, rays[i].tmax);
+    bool valid = i < n;
+    V3 o = v3s(0.0f), d = v3(0.0f, 0.0f, 1.0f); float t0 = 0.0f, t1 = 0.0f;
+    if (valid) { o = v3(rays[i].o[0], rays[i].o[1], rays[i].o[2]); d = v3(rays[i].d[0], rays[i].d[1], rays[i].d[2]); t0 = rays[i].tmin; t1 = rays[i].tmax; }
+    Hit h = trace_closest(sc, valid, o, d, t0, t1);
+    if (!valid) return;
     tgb_hit out; out.primitive = -1; out.prim_id = 0; out.t = h.t; out.u = 0.0f; out.v = 0.0f; out.backside = 0;
     if (h.id != HID_MISS) {
         Surface s; make_surface(sc, h, o, d, s);
@@ -512,23 +706,32 @@ __global__ void __launch_bounds__(128) k_shade(DScene sc, PathState st, BatchInf
 __global__ void __launch_bounds__(128) k_shadow(DScene sc, PathState st, const uint32_t *squeue, const uint32_t *scount, Counters *ctr) {
     uint32_t i = blockIdx.x*blockDim.x + threadIdx.x;
     bool valid = i < *scount;
-    bool anyhit = false;
+    uint32_t s = 0; bool mis = false, any = false; int li = -1;
+    V3 p = v3s(0.0f), d = v3(0.0f, 0.0f, 1.0f); float tfar = INFINITY;
     if (valid) {
-        uint32_t q = squeue[i], s = q >> 2; bool mis = q & 1u, any = q & 2u;
-        V3 p = v3(st.px[s], st.py[s], st.pz[s]);
-        V3 d = mis ? v3(st.mdx[s], st.mdy[s], st.mdz[s]) : v3(st.ndx[s], st.ndy[s], st.ndz[s]);
-        int li = st.qlight[s];
-        if (any) {
-            float tfar = mis ? st.mpb[s] : st.ndist[s];
-            Hit h = trace_scene<true>(sc, p, d, 5e-4f, tfar, li);
+        uint32_t q = squeue[i]; s = q >> 2; mis = q & 1u; any = q & 2u;
+        p = v3(st.px[s], st.py[s], st.pz[s]);
+        d = mis ? v3(st.mdx[s], st.mdy[s], st.mdz[s]) : v3(st.ndx[s], st.ndy[s], st.ndz[s]);
+        li = st.qlight[s];
+        if (any) tfar = mis ? st.mpb[s] : st.ndist[s];
+    }
+    // both query kinds can share a warp (scenes mixing mesh lights with quad/environment lights): run the
+    // occlusion traversal for the "any" lanes, then the closest-hit traversal for the rest
+    bool anyhit = false;
+    if (__any_sync(0xffffffffu, valid && any)) {
+        Hit h = trace_scene<true>(sc, valid && any, p, d, 5e-4f, tfar, li);
+        if (valid && any) {
             anyhit = h.id != HID_MISS;
             if (!anyhit) {
                 if (!mis) { st.lx[s] = st.nfx[s]; st.ly[s] = st.nfy[s]; st.lz[s] = st.nfz[s]; }
                 else { st.bx[s] = st.mwx[s]; st.by[s] = st.mwy[s]; st.bz[s] = st.mwz[s]; }
             }
-        } else {
+        }
+    }
+    if (__any_sync(0xffffffffu, valid && !any)) {
+        Hit h = trace_scene<false>(sc, valid && !any, p, d, 5e-4f, INFINITY, -1);
+        if (valid && !any) {
             const DPrim &l = sc.prims[li];
-            Hit h = trace_scene<false>(sc, p, d, 5e-4f, INFINITY, -1);
             anyhit = h.id != HID_MISS;
             if (anyhit) {
                 Surface ls; make_surface(sc, h, p, d, ls);

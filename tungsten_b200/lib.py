@@ -7,7 +7,7 @@ import numpy as np
 from . import abi
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libtgb200.so")
+LIB_PATH = os.environ.get("TGB200_LIB", os.path.join(_HERE, "libtgb200.so"))   # TGB200_LIB: experimental variant builds
 _lib = None
 
 
