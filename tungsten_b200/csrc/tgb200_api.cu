@@ -38,9 +38,11 @@ struct tgb_ctx {
     uint32_t res_x = 0, res_y = 0;
     // wavefront storage
     uint32_t capacity = 0;
-    PathState st{};
-    uint32_t *queue_a = nullptr, *queue_b = nullptr, *squeue = nullptr;
-    uint32_t *counts = nullptr;          // [0]=count A, [1]=count B, [2]=shadow count
+    PathState st{}, st2{};      // st2 = second copy of the persistent arrays (ray, throughput, emission, rng, hit, pid)
+    uint32_t *queue_a = nullptr, *queue_b = nullptr, *squeue = nullptr, *squeue2 = nullptr, *free_list = nullptr;
+    size_t res_capacity = 0;
+    ShadowState ss{};
+    uint32_t *counts = nullptr;          // [0]=count A, [1]=count B, [2]=shadow count, [3]=compacted shadow count
     uint32_t *h_counts = nullptr;        // pinned
     Counters *ctr = nullptr; Counters *h_ctr = nullptr;
     float *fb = nullptr; uint32_t *fb_count = nullptr;
@@ -391,7 +393,7 @@ int upload_scene(tgb_ctx *c, const tgb_scene_desc *d) {
     }
     std::vector<float4> nodes(4*bvh.nodes.size());
     std::memcpy(nodes.data(), bvh.nodes.data(), bvh.nodes.size()*sizeof(Node2));
-    c->geom_bytes = nodes.size()*16 + tri_isect.size()*16 + tri_shade.size()*16;
+    c->geom_bytes = nodes.size()*16 + tri_isect.size()*16 + tri_shade.size()*16 + bvh.order.size()*8;
 
     int rc;
     if ((rc = dev_upload(c, &sc.prims, prims))) return rc;
@@ -427,12 +429,23 @@ int alloc_wavefront(tgb_ctx *c, uint32_t capacity) {
     ALLOCF(px) ALLOCF(py) ALLOCF(pz)
     ALLOCF(lx) ALLOCF(ly) ALLOCF(lz) ALLOCF(bx) ALLOCF(by) ALLOCF(bz) ALLOCF(wl) ALLOCF(sx) ALLOCF(sy) ALLOCF(sz) ALLOCF(ux) ALLOCF(uy) ALLOCF(uz)
     ALLOCF(ndx) ALLOCF(ndy) ALLOCF(ndz) ALLOCF(ndist) ALLOCF(nfx) ALLOCF(nfy) ALLOCF(nfz) ALLOCF(npl) ALLOCF(npb)
-    ALLOCF(mdx) ALLOCF(mdy) ALLOCF(mdz) ALLOCF(mwx) ALLOCF(mwy) ALLOCF(mwz) ALLOCF(mpb) ALLOCF(qlight)
+    ALLOCF(mdx) ALLOCF(mdy) ALLOCF(mdz) ALLOCF(mwx) ALLOCF(mwy) ALLOCF(mwz) ALLOCF(mpb) ALLOCF(qlight) ALLOCF(pid)
 #undef ALLOCF
+    c->st2 = c->st;
+#define ALLOC2(name) if ((rc = dev_alloc(c, &c->st2.name, capacity))) return rc;
+    ALLOC2(ox) ALLOC2(oy) ALLOC2(oz) ALLOC2(dx) ALLOC2(dy) ALLOC2(dz) ALLOC2(tmin) ALLOC2(tx) ALLOC2(ty) ALLOC2(tz)
+    ALLOC2(ex) ALLOC2(ey) ALLOC2(ez) ALLOC2(pcg) ALLOC2(info) ALLOC2(ht) ALLOC2(hu) ALLOC2(hv) ALLOC2(hid) ALLOC2(pid)
+#undef ALLOC2
     (void)fp;
     if ((rc = dev_alloc(c, &c->queue_a, capacity))) return rc;
     if ((rc = dev_alloc(c, &c->queue_b, capacity))) return rc;
+    if ((rc = dev_alloc(c, &c->free_list, capacity))) return rc;
     if ((rc = dev_alloc(c, &c->squeue, size_t(capacity)*2))) return rc;
+    if ((rc = dev_alloc(c, &c->squeue2, size_t(capacity)*2))) return rc;
+    if ((rc = dev_alloc(c, &c->ss.qt, size_t(capacity)*2))) return rc;
+    if ((rc = dev_alloc(c, &c->ss.qu, size_t(capacity)*2))) return rc;
+    if ((rc = dev_alloc(c, &c->ss.qv, size_t(capacity)*2))) return rc;
+    if ((rc = dev_alloc(c, &c->ss.qid, size_t(capacity)*2))) return rc;
     if ((rc = dev_alloc(c, &c->counts, 4))) return rc;
     if ((rc = dev_alloc(c, &c->ctr, 1))) return rc;
     CU(cudaMemset(c->ctr, 0, sizeof(Counters)));
@@ -488,48 +501,82 @@ int set_tiles(tgb_ctx *c, const tgb_tile *tiles, uint32_t n_tiles, uint32_t seed
 }
 
 inline unsigned blocks(uint32_t n, unsigned bs) { return n ? (n + bs - 1)/bs : 1; }
+// Rays per lane of the persistent traversal kernels: as many as keep >= ~8 blocks per SM in flight (148 SMs).
+inline uint32_t rays_per_lane(uint32_t n) { const char *e = getenv("TGB_K"); uint32_t kmax = e ? uint32_t(atoi(e)) : 1u; return std::max(1u, std::min(kmax, n/(148u*8u*uint32_t(kTraceBlock)))); }
 
-// The wavefront loop: the GPU analogue of renderTile over (pixels of the tiles) x (sample range).
+// The wavefront loop: the GPU analogue of renderTile over (pixels of the tiles) x (sample range), with path
+// regeneration: whenever paths finish, their slots are refilled with the next camera paths of the step, so every
+// iteration traces a full batch until the step's paths run out (one drain tail per step instead of one per batch).
+int ensure_results(tgb_ctx *c, size_t n_paths) {
+    if (n_paths <= c->res_capacity) return TGB_OK;
+    for (float **p : {&c->st.rx, &c->st.ry, &c->st.rz}) { if (*p) cudaFree(*p); *p = nullptr; }
+    c->res_capacity = 0;
+    for (float **p : {&c->st.rx, &c->st.ry, &c->st.rz}) CU(cudaMalloc(reinterpret_cast<void **>(p), n_paths*sizeof(float)));
+    c->res_capacity = n_paths;
+    return TGB_OK;
+}
+
 int render_device(tgb_ctx *c, uint32_t spp_begin, uint32_t spp_count) {
     if (c->n_pix == 0 || spp_count == 0) return TGB_OK;
     const DScene &sc = c->sc;
     CU(cudaEventRecord(c->ev0, c->stream));
     uint64_t launches = 0;
     float trace_ms = 0.0f, shadow_ms = 0.0f; uint64_t trace_launches = 0;
-    for (uint32_t pix0 = 0; pix0 < c->n_pix; pix0 += c->capacity) {
-        uint32_t npx = std::min(c->capacity, c->n_pix - pix0);
-        uint32_t chunk = std::max(1u, c->capacity/npx);
-        for (uint32_t s0 = 0; s0 < spp_count; s0 += chunk) {
-            uint32_t ns = std::min(chunk, spp_count - s0);
-            BatchInfo bi; bi.pix_id = c->pix_id + pix0; bi.pix_seed = c->pix_seed + pix0; bi.n_pix = npx;
-            bi.spp_begin = spp_begin + s0; bi.n_paths = npx*ns;
-            uint32_t *qa = c->queue_a, *qb = c->queue_b; uint32_t *ca = c->counts, *cb = c->counts + 1, *cs = c->counts + 2;
-            k_raygen<<<blocks(bi.n_paths, 256), 256, 0, c->stream>>>(sc, c->st, bi, qa, ca); launches++;
-            uint32_t n_active = bi.n_paths;
-            for (int bounce = 0; n_active > 0; ++bounce) {
-                if (c->abort_flag.load()) { cudaStreamSynchronize(c->stream); return fail(c, TGB_ERR_ABORTED, "render aborted"); }
-                CU(cudaMemsetAsync(cb, 0, sizeof(uint32_t), c->stream));         // next queue count
-                CU(cudaMemsetAsync(cs, 0, sizeof(uint32_t), c->stream));         // shadow query count
-                if (c->profiling) CU(cudaEventRecord(c->evt0, c->stream));
-                k_trace<<<blocks(n_active, 128), 128, 0, c->stream>>>(sc, c->st, qa, ca, c->ctr); launches++;
-                if (c->profiling) CU(cudaEventRecord(c->evt1, c->stream));
-                k_shade<<<blocks(n_active, 128), 128, 0, c->stream>>>(sc, c->st, bi, qa, ca, c->squeue, cs); launches++;
-                if (c->profiling) CU(cudaEventRecord(c->evs0, c->stream));
-                k_shadow<<<blocks(2*n_active, 128), 128, 0, c->stream>>>(sc, c->st, c->squeue, cs, c->ctr); launches++;
-                if (c->profiling) CU(cudaEventRecord(c->evs1, c->stream));
-                k_accum<<<blocks(n_active, 256), 256, 0, c->stream>>>(sc, c->st, qa, ca, qb, cb); launches++;
-                CU(cudaMemcpyAsync(c->h_counts, c->counts, 3*sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
-                CU(cudaStreamSynchronize(c->stream));
-                if (c->profiling) {
-                    float ms = 0.0f; cudaEventElapsedTime(&ms, c->evt0, c->evt1); trace_ms += ms; trace_launches++;
-                    cudaEventElapsedTime(&ms, c->evs0, c->evs1); shadow_ms += ms;
-                }
-                n_active = c->h_counts[cb - c->counts];
-                std::swap(qa, qb); std::swap(ca, cb);
-                if (bounce > 4096) return fail(c, TGB_ERR_CUDA, "wavefront loop did not terminate");
+    const bool has_bvh = sc.n_nodes != 0;
+    // a step's finished radiances are kept per path (12 B each) until k_resolve folds them in sample order;
+    // split the sample range so that this buffer stays below ~6 GB and path ids fit 32 bits
+    const uint64_t max_paths = std::min<uint64_t>(512ull << 20, 0xFFFFFFFFull);
+    uint32_t spp_sub = uint32_t(std::max<uint64_t>(1, std::min<uint64_t>(spp_count, max_paths/c->n_pix)));
+    if (uint64_t(c->n_pix)*spp_sub > 0xFFFFFFFFull) return fail(c, TGB_ERR_UNSUPPORTED, "tile list too large");
+    for (uint32_t s0 = 0; s0 < spp_count; s0 += spp_sub) {
+        uint32_t ns = std::min(spp_sub, spp_count - s0);
+        uint32_t total = c->n_pix*ns, issued = 0;
+        int rc = ensure_results(c, total);
+        if (rc) return rc;
+        BatchInfo bi; bi.pix_id = c->pix_id; bi.pix_seed = c->pix_seed; bi.n_pix = c->n_pix; bi.spp_begin = spp_begin + s0;
+        PathState cur = c->st, nxt = c->st2;
+        cur.rx = nxt.rx = c->st.rx; cur.ry = nxt.ry = c->st.ry; cur.rz = nxt.rz = c->st.rz;
+        uint32_t *cs = c->counts + 2;                 // counts: [0] survivors, [2] shadow queries, [3] compacted shadow queries
+        uint32_t n_alive = 0;
+        for (uint32_t iter = 0;; ++iter) {
+            if (c->abort_flag.load()) { cudaStreamSynchronize(c->stream); return fail(c, TGB_ERR_ABORTED, "render aborted"); }
+            // refill: survivors occupy slots [0, n_alive) of `cur`; new camera paths are appended behind them
+            uint32_t m = std::min(c->capacity - n_alive, total - issued);
+            if (m) {
+                k_regen<<<blocks(m, 256), 256, 0, c->stream>>>(sc, cur, bi, n_alive, issued, m); launches++;
+                issued += m;
             }
-            k_resolve<<<blocks(npx, 256), 256, 0, c->stream>>>(c->st, bi, ns, c->fb, c->fb_count); launches++;
+            uint32_t n = n_alive + m;
+            if (n == 0) break;
+            CU(cudaMemsetAsync(c->counts, 0, 4*sizeof(uint32_t), c->stream));
+            if (c->profiling) CU(cudaEventRecord(c->evt0, c->stream));
+            if (has_bvh) {
+                uint32_t K = rays_per_lane(n);
+                k_trace<<<blocks(n, kTraceBlock*K), kTraceBlock, kTraceSmem, c->stream>>>(sc, cur, n, K); launches++;
+            }
+            if (c->profiling) CU(cudaEventRecord(c->evt1, c->stream));
+            k_shade<<<blocks(n, 128), 128, 0, c->stream>>>(sc, cur, bi, n, c->squeue, cs, c->ctr); launches++;
+            if (c->profiling) CU(cudaEventRecord(c->evs0, c->stream));
+            k_shadow_prep<<<blocks(2*n, 256), 256, 0, c->stream>>>(sc, cur, c->ss, c->squeue, cs, c->squeue2, cs + 1, c->ctr); launches++;
+            if (has_bvh) {
+                uint32_t K = rays_per_lane(2*n);
+                k_shadow_bvh<<<blocks(2*n, kTraceBlock*K), kTraceBlock, kTraceSmem, c->stream>>>(sc, cur, c->ss, c->squeue2, cs + 1, c->ctr, K); launches++;
+            }
+            if (c->profiling) CU(cudaEventRecord(c->evs1, c->stream));
+            k_accum<<<blocks(n, 256), 256, 0, c->stream>>>(sc, cur, nxt, n, c->counts); launches++;
+            CU(cudaMemcpyAsync(c->h_counts, c->counts, 4*sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+            CU(cudaStreamSynchronize(c->stream));
+            if (c->profiling) {
+                float ms = 0.0f; cudaEventElapsedTime(&ms, c->evt0, c->evt1); trace_ms += ms; trace_launches++;
+                cudaEventElapsedTime(&ms, c->evs0, c->evs1); shadow_ms += ms;
+            }
+            if (getenv("TGB_TRACE_BOUNCES")) fprintf(stderr, "iter %u n %u (new %u) shadow %u/%u -> alive %u\n", iter, n, m, c->h_counts[3], c->h_counts[2], c->h_counts[0]);
+            n_alive = c->h_counts[0];
+            std::swap(cur, nxt);
+            if (iter > (1u << 24)) return fail(c, TGB_ERR_CUDA, "wavefront loop did not terminate");
         }
+        c->st.rx = cur.rx;
+        k_resolve<<<blocks(c->n_pix, 256), 256, 0, c->stream>>>(c->st, bi, ns, c->fb, c->fb_count); launches++;
     }
     CU(cudaEventRecord(c->ev1, c->stream));
     CU(cudaMemcpyAsync(c->h_ctr, c->ctr, sizeof(Counters), cudaMemcpyDeviceToHost, c->stream));
@@ -558,6 +605,7 @@ void tgb200_destroy(tgb_ctx *c) {
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     for (void *p : c->allocs) cudaFree(p);
+    for (float *p : {c->st.rx, c->st.ry, c->st.rz}) if (p) cudaFree(p);
     if (c->h_counts) cudaFreeHost(c->h_counts);
     if (c->h_ctr) cudaFreeHost(c->h_ctr);
     if (c->h_fb) cudaFreeHost(c->h_fb);
@@ -669,20 +717,28 @@ int tgb200_trace_closest(tgb_ctx *c, const tgb_ray *rays, tgb_hit *hits, uint32_
     if (!c || (n && (!rays || !hits))) return TGB_ERR_INVALID;
     if (n == 0) return TGB_OK;
     CU(cudaSetDevice(c->device));
-    tgb_ray *dr = nullptr; tgb_hit *dh = nullptr;
+    tgb_ray *dr = nullptr; tgb_hit *dh = nullptr; Hit *dx = nullptr;
     CU(cudaMalloc(reinterpret_cast<void **>(&dr), size_t(n)*sizeof(tgb_ray)));
     cudaError_t e = cudaMalloc(reinterpret_cast<void **>(&dh), size_t(n)*sizeof(tgb_hit));
-    if (e != cudaSuccess) { cudaFree(dr); return fail(c, TGB_ERR_OOM, "cudaMalloc failed: %s", cudaGetErrorString(e)); }
+    if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void **>(&dx), size_t(n)*sizeof(Hit));
+    if (e != cudaSuccess) { cudaFree(dr); cudaFree(dh); return fail(c, TGB_ERR_OOM, "cudaMalloc failed: %s", cudaGetErrorString(e)); }
     int rc = TGB_OK;
     do {
         if ((e = cudaMemcpyAsync(dr, rays, size_t(n)*sizeof(tgb_ray), cudaMemcpyHostToDevice, c->stream)) != cudaSuccess) break;
-        k_trace_rays<<<blocks(n, 128), 128, 0, c->stream>>>(c->sc, dr, dh, n);
-        c->stats.kernel_launches++;
+        k_hook_analytic<<<blocks(n, 256), 256, 0, c->stream>>>(c->sc, dr, dx, n);
+        if (c->sc.n_nodes) {
+            uint32_t K = rays_per_lane(n);
+            k_hook_bvh<<<blocks(n, kTraceBlock*K), kTraceBlock, kTraceSmem, c->stream>>>(c->sc, dr, dx, n, K);
+            c->stats.kernel_launches++;
+        }
+        k_hook_finish<<<blocks(n, 256), 256, 0, c->stream>>>(c->sc, dr, dx, dh, n);
+        c->stats.kernel_launches += 2;
         if ((e = cudaMemcpyAsync(hits, dh, size_t(n)*sizeof(tgb_hit), cudaMemcpyDeviceToHost, c->stream)) != cudaSuccess) break;
         e = cudaStreamSynchronize(c->stream);
+        if (e == cudaSuccess) e = cudaGetLastError();
     } while (0);
     if (e != cudaSuccess) rc = fail(c, TGB_ERR_CUDA, "trace_closest failed: %s", cudaGetErrorString(e));
-    cudaFree(dr); cudaFree(dh);
+    cudaFree(dr); cudaFree(dh); cudaFree(dx);
     return rc;
 }
 

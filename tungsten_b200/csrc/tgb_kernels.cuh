@@ -26,6 +26,8 @@ struct PathState {
     float *ndx, *ndy, *ndz, *ndist, *nfx, *nfy, *nfz, *npl, *npb;
     float *mdx, *mdy, *mdz, *mwx, *mwy, *mwz, *mpb;
     int *qlight;                                        // light primitive of this bounce's queries
+    uint32_t *pid;                                      // path index within the step: sample_rel*n_pix + pixel_list_index
+    float *rx, *ry, *rz;                                // finished radiance per path of the step, indexed by pid (not by slot)
 };
 constexpr int kPathFloatArrays = 7 + 3 + 3 + 3 + 3 + 13 + 9 + 7;   // float-sized arrays in PathState (excl. pcg/info/hid/qlight)
 
@@ -75,70 +77,111 @@ TGB_D void cube_intersect(const DPrim &c, int self, V3 o, V3 d, float tnear, Hit
     }
 }
 
-constexpr int kStackSize = 64;
-
-// Closest hit over the whole scene.  Triangle test = Embree's MoellerTrumboreIntersector1
-// (thirdparty/embree/kernels/geometry/triangle_intersector_moeller.h:75-111) with IEEE division for t,u,v.
-#ifndef TGB_TRAV
-#define TGB_TRAV 0
-#endif
-#ifndef TGB_FMA_SLAB
-#define TGB_FMA_SLAB 0
-#endif
-#if TGB_TRAV == 0
-// Per-lane while-while traversal (independent thread scheduling interleaves the divergent lane groups).
-// ANY = true: occlusion query for a light whose own hit was already resolved analytically -- returns at the
-// first surface in [tnear, tfar] other than primitive `ignore` (generalizedShadowRay's blocker test).
-template <bool ANY>
-TGB_D Hit trace_scene(const DScene &sc, bool active, V3 o, V3 d, float tnear, float tfar, int ignore) {
+// Analytic primitives (quads, cubes) are few and are tested coherently -- every lane runs the same loop -- by the
+// kernel that CREATES a ray (k_raygen, k_accum, k_shadow_prep); the BVH kernels then start from that hit.
+TGB_D Hit analytic_closest(const DScene &sc, V3 o, V3 d, float tnear, float tfar) {
     Hit h; h.t = tfar; h.u = 0.0f; h.v = 0.0f; h.id = HID_MISS;
-    if (!active) return h;
     for (int i = 0; i < sc.n_analytic; ++i) {
         int pi = sc.analytic[i];
-        if (ANY && pi == ignore) continue;
         const DPrim &p = sc.prims[pi];
         if (p.type == TGB_PRIM_QUAD) quad_intersect(p, pi, o, d, tnear, h);
         else cube_intersect(p, pi, o, d, tnear, h);
-        if (ANY && h.id != HID_MISS) return h;
     }
-    if (sc.n_nodes == 0) return h;
+    return h;
+}
+// first blocker among the analytic primitives other than `ignore` (generalizedShadowRay's test, TraceBase.cpp:79-83)
+TGB_D bool analytic_any(const DScene &sc, V3 o, V3 d, float tnear, float tfar, int ignore) {
+    Hit h; h.t = tfar; h.u = 0.0f; h.v = 0.0f; h.id = HID_MISS;
+    for (int i = 0; i < sc.n_analytic; ++i) {
+        int pi = sc.analytic[i];
+        if (pi == ignore) continue;
+        const DPrim &p = sc.prims[pi];
+        if (p.type == TGB_PRIM_QUAD) quad_intersect(p, pi, o, d, tnear, h);
+        else cube_intersect(p, pi, o, d, tnear, h);
+        if (h.id != HID_MISS) return true;
+    }
+    return false;
+}
 
-    const float ooeps = 1e-30f;
-    float idx = 1.0f/(fabsf(d.x) > ooeps ? d.x : copysignf(ooeps, d.x));
-    float idy = 1.0f/(fabsf(d.y) > ooeps ? d.y : copysignf(ooeps, d.y));
-    float idz = 1.0f/(fabsf(d.z) > ooeps ? d.z : copysignf(ooeps, d.z));
-    int stack[kStackSize]; int sp = 0;
-    int cur = 0;
+// Traversal stack: the first kSmemStack entries of every lane live in shared memory, laid out [entry][thread] so
+// that lane i always hits bank i (conflict-free whatever the lanes' depths); deeper entries spill to local memory.
+constexpr int kSmemStack = 32;
+constexpr int kLocalStack = 48;
+constexpr int kStackSize = kSmemStack + kLocalStack;
+constexpr int kTraceBlock = 128;
+#ifndef TGB_MINB
+#define TGB_MINB 1
+#endif
+constexpr size_t kTraceSmem = size_t(kSmemStack)*kTraceBlock*sizeof(int);
+
+struct TravStack {
+    int *smem;                       // this thread's column of the shared stack
+    int local[kLocalStack];
+    int sp;
+    TGB_D void push(int v) {
+        if (sp < kSmemStack) smem[sp*kTraceBlock] = v;
+        else if (sp < kStackSize) local[sp - kSmemStack] = v;
+        sp++;
+    }
+    TGB_D int pop() {
+        --sp;
+        return sp < kSmemStack ? smem[sp*kTraceBlock] : local[sp - kSmemStack];
+    }
+};
+
+// BVH traversal over the mesh triangles, K rays per lane (ray index = warp chunk + j*32 + lane), per-lane
+// while-while: walk inner nodes until a leaf, intersect the leaf, pop.  Node visit = one 64-byte node (4 x 16 B
+// loads) and two fused slab tests t = lo/d - o/d (boxes are padded at build time to cover the FMA rounding).
+// Triangle test = Embree's MoellerTrumboreIntersector1 (thirdparty/embree/kernels/geometry/
+// triangle_intersector_moeller.h:75-111) with IEEE division for t,u,v.
+// P::fetch(idx, o, d, tnear, h, any) loads ray `idx` with its initial hit (from the analytic pass; false = nothing to
+// traverse) and says whether it is an occlusion query (any = stop at the first triangle hit); P::finish(h) stores it.
+// Alternatives measured and rejected (profiles/r01_a_k_trace_baseline.md): warp-synchronous speculative traversal,
+// if-if state machines with and without several rays per lane, 32-byte quantised nodes.
+template <class P>
+TGB_D void bvh_traverse_multi(const DScene &sc, int *smem_stack, P &pol, uint32_t n, uint32_t K) {
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t gw = (blockIdx.x*blockDim.x + threadIdx.x) >> 5;
+    const uint64_t chunk = uint64_t(gw)*32u*K;
+    if (chunk >= n) return;
+    const uint64_t chunk_end = chunk + 32ull*K;
+    const uint32_t end = chunk_end < uint64_t(n) ? uint32_t(chunk_end) : n;
     const float4 *nodes = sc.nodes;
-    while (true) {
-        while (cur >= 0) {
-            const float4 n0 = __ldg(nodes + 4*cur), n1 = __ldg(nodes + 4*cur + 1), n2 = __ldg(nodes + 4*cur + 2);
-            const float4 lk = __ldg(nodes + 4*cur + 3);
-            float c0lox = (n0.x - o.x)*idx, c0hix = (n0.y - o.x)*idx, c0loy = (n0.z - o.y)*idy, c0hiy = (n0.w - o.y)*idy;
-            float c1lox = (n1.x - o.x)*idx, c1hix = (n1.y - o.x)*idx, c1loy = (n1.z - o.y)*idy, c1hiy = (n1.w - o.y)*idy;
-            float c0loz = (n2.x - o.z)*idz, c0hiz = (n2.y - o.z)*idz, c1loz = (n2.z - o.z)*idz, c1hiz = (n2.w - o.z)*idz;
-            float c0min = fmaxf(fmaxf(fminf(c0lox, c0hix), fminf(c0loy, c0hiy)), fmaxf(fminf(c0loz, c0hiz), tnear));
-            float c0max = fminf(fminf(fmaxf(c0lox, c0hix), fmaxf(c0loy, c0hiy)), fminf(fmaxf(c0loz, c0hiz), h.t));
-            float c1min = fmaxf(fmaxf(fminf(c1lox, c1hix), fminf(c1loy, c1hiy)), fmaxf(fminf(c1loz, c1hiz), tnear));
-            float c1max = fminf(fminf(fmaxf(c1lox, c1hix), fmaxf(c1loy, c1hiy)), fminf(fmaxf(c1loz, c1hiz), h.t));
-            // 2-ulp slack on the far side: slab rounding must never cull a triangle the exact test accepts
-            bool t0 = c0min <= c0max*1.0000003f, t1 = c1min <= c1max*1.0000003f;
-            int l0 = __float_as_int(lk.x), l1 = __float_as_int(lk.y);
-            if (t0 && t1) {
-                bool swp = c1min < c0min;
-                int nearc = swp ? l1 : l0, farc = swp ? l0 : l1;
-                cur = nearc;
-                if (sp < kStackSize) stack[sp++] = farc;
-            } else if (t0) cur = l0;
-            else if (t1) cur = l1;
-            else {
-                if (sp == 0) return h;
-                cur = stack[--sp];
+    TravStack stk; stk.smem = smem_stack + threadIdx.x;
+    for (uint32_t my = uint32_t(chunk) + lane; my < end; my += 32u) {
+        V3 o, d; float tnear; Hit h; bool any;
+        if (!pol.fetch(my, o, d, tnear, h, any)) continue;
+        const float ooeps = 1e-30f;
+        const float idx = 1.0f/(fabsf(d.x) > ooeps ? d.x : copysignf(ooeps, d.x));
+        const float idy = 1.0f/(fabsf(d.y) > ooeps ? d.y : copysignf(ooeps, d.y));
+        const float idz = 1.0f/(fabsf(d.z) > ooeps ? d.z : copysignf(ooeps, d.z));
+        const float oodx = o.x*idx, oody = o.y*idy, oodz = o.z*idz;
+        stk.sp = 0;
+        int cur = 0;
+        bool done = false;
+        while (!done) {
+            while (cur >= 0) {
+                const float4 n0 = __ldg(nodes + 4*cur), n1 = __ldg(nodes + 4*cur + 1), n2 = __ldg(nodes + 4*cur + 2);
+                const float4 lk = __ldg(nodes + 4*cur + 3);
+                float c0lox = __fmaf_rn(n0.x, idx, -oodx), c0hix = __fmaf_rn(n0.y, idx, -oodx), c0loy = __fmaf_rn(n0.z, idy, -oody), c0hiy = __fmaf_rn(n0.w, idy, -oody);
+                float c1lox = __fmaf_rn(n1.x, idx, -oodx), c1hix = __fmaf_rn(n1.y, idx, -oodx), c1loy = __fmaf_rn(n1.z, idy, -oody), c1hiy = __fmaf_rn(n1.w, idy, -oody);
+                float c0loz = __fmaf_rn(n2.x, idz, -oodz), c0hiz = __fmaf_rn(n2.y, idz, -oodz), c1loz = __fmaf_rn(n2.z, idz, -oodz), c1hiz = __fmaf_rn(n2.w, idz, -oodz);
+                float c0min = fmaxf(fmaxf(fminf(c0lox, c0hix), fminf(c0loy, c0hiy)), fmaxf(fminf(c0loz, c0hiz), tnear));
+                float c0max = fminf(fminf(fmaxf(c0lox, c0hix), fmaxf(c0loy, c0hiy)), fminf(fmaxf(c0loz, c0hiz), h.t));
+                float c1min = fmaxf(fmaxf(fminf(c1lox, c1hix), fminf(c1loy, c1hiy)), fmaxf(fminf(c1loz, c1hiz), tnear));
+                float c1max = fminf(fminf(fmaxf(c1lox, c1hix), fmaxf(c1loy, c1hiy)), fminf(fmaxf(c1loz, c1hiz), h.t));
+                bool t0 = c0min <= c0max, t1 = c1min <= c1max;
+                int l0 = __float_as_int(lk.x), l1 = __float_as_int(lk.y);
+                if (t0 && t1) {
+                    bool swp = c1min < c0min;
+                    cur = swp ? l1 : l0;
+                    stk.push(swp ? l0 : l1);
+                } else if (t0) cur = l0;
+                else if (t1) cur = l1;
+                else if (stk.sp) cur = stk.pop();
+                else { done = true; break; }
             }
-            if (cur < 0) break;
-        }
-        // leaf
-        {
+            if (done) break;
             int code = ~cur;
             int first = code >> 3, count = (code & 7) + 1;
             for (int i = 0; i < count; ++i) {
@@ -156,198 +199,14 @@ TGB_D Hit trace_scene(const DScene &sc, bool active, V3 o, V3 d, float tnear, fl
                 float T = xor_sign(edot(ng, C), sgn);
                 if (!(T > absDen*tnear && T < absDen*h.t)) continue;
                 h.t = T/absDen; h.u = U/absDen; h.v = V/absDen; h.id = first + i;
-                if (ANY) return h;
+                if (any) { done = true; break; }
             }
-            if (sp == 0) return h;
-            cur = stack[--sp];
+            if (done) break;
+            if (stk.sp) cur = stk.pop(); else done = true;
         }
+        pol.finish(h);
     }
 }
-
-#elif TGB_TRAV == 1
-// ANY = true: occlusion query for a light whose own hit was already resolved analytically -- stops at the
-// first surface in [tnear, tfar] other than primitive `ignore` (generalizedShadowRay's blocker test).
-//
-// WARP-SYNCHRONOUS: must be called by all 32 lanes of a converged warp; lanes without a ray pass active=false.
-// Traversal is the "speculative while-while" scheme: all lanes walk inner nodes together until every lane
-// has found a leaf (one leaf may be postponed so a lane can keep descending), then all lanes intersect their
-// leaves together.  Warp votes (__any_sync) keep the two phases converged; without them leaf tests ran with
-// ~1.6 of 32 lanes active (profiles/r01_k_trace_baseline.md).  The stack lives in local memory (L1-resident).
-constexpr int TRAV_DONE = int(0x80000000u);
-
-template <bool ANY>
-TGB_D Hit trace_scene(const DScene &sc, bool active, V3 o, V3 d, float tnear, float tfar, int ignore) {
-    const unsigned FULL = 0xffffffffu;
-    Hit h; h.t = tfar; h.u = 0.0f; h.v = 0.0f; h.id = HID_MISS;
-    if (active) {
-        for (int i = 0; i < sc.n_analytic; ++i) {
-            int pi = sc.analytic[i];
-            if (ANY && pi == ignore) continue;
-            const DPrim &p = sc.prims[pi];
-            if (p.type == TGB_PRIM_QUAD) quad_intersect(p, pi, o, d, tnear, h);
-            else cube_intersect(p, pi, o, d, tnear, h);
-            if (ANY && h.id != HID_MISS) break;
-        }
-    }
-    int cur = (active && sc.n_nodes != 0 && !(ANY && h.id != HID_MISS)) ? 0 : TRAV_DONE;
-    if (!__any_sync(FULL, cur != TRAV_DONE)) return h;
-
-    const float ooeps = 1e-30f;
-    float idx = 1.0f/(fabsf(d.x) > ooeps ? d.x : copysignf(ooeps, d.x));
-    float idy = 1.0f/(fabsf(d.y) > ooeps ? d.y : copysignf(ooeps, d.y));
-    float idz = 1.0f/(fabsf(d.z) > ooeps ? d.z : copysignf(ooeps, d.z));
-    int stack[kStackSize]; int sp = 0;
-    int leaf = 0;                                   // postponed leaf (negative code) or 0
-    const float4 *nodes = sc.nodes;
-    while (true) {
-        // ---- phase 1: inner nodes, until every lane holds a leaf or is done
-        while (__any_sync(FULL, cur >= 0)) {
-            if (cur >= 0) {
-                const float4 n0 = __ldg(nodes + 4*cur), n1 = __ldg(nodes + 4*cur + 1), n2 = __ldg(nodes + 4*cur + 2);
-                const float4 lk = __ldg(nodes + 4*cur + 3);
-                float c0lox = (n0.x - o.x)*idx, c0hix = (n0.y - o.x)*idx, c0loy = (n0.z - o.y)*idy, c0hiy = (n0.w - o.y)*idy;
-                float c1lox = (n1.x - o.x)*idx, c1hix = (n1.y - o.x)*idx, c1loy = (n1.z - o.y)*idy, c1hiy = (n1.w - o.y)*idy;
-                float c0loz = (n2.x - o.z)*idz, c0hiz = (n2.y - o.z)*idz, c1loz = (n2.z - o.z)*idz, c1hiz = (n2.w - o.z)*idz;
-                float c0min = fmaxf(fmaxf(fminf(c0lox, c0hix), fminf(c0loy, c0hiy)), fmaxf(fminf(c0loz, c0hiz), tnear));
-                float c0max = fminf(fminf(fmaxf(c0lox, c0hix), fmaxf(c0loy, c0hiy)), fminf(fmaxf(c0loz, c0hiz), h.t));
-                float c1min = fmaxf(fmaxf(fminf(c1lox, c1hix), fminf(c1loy, c1hiy)), fmaxf(fminf(c1loz, c1hiz), tnear));
-                float c1max = fminf(fminf(fmaxf(c1lox, c1hix), fmaxf(c1loy, c1hiy)), fminf(fmaxf(c1loz, c1hiz), h.t));
-                // 2-ulp slack on the far side: slab rounding must never cull a triangle the exact test accepts
-                bool t0 = c0min <= c0max*1.0000003f, t1 = c1min <= c1max*1.0000003f;
-                int l0 = __float_as_int(lk.x), l1 = __float_as_int(lk.y);
-                if (t0 && t1) {
-                    bool swp = c1min < c0min;
-                    cur = swp ? l1 : l0;
-                    if (sp < kStackSize) stack[sp++] = swp ? l0 : l1;
-                } else if (t0) cur = l0;
-                else if (t1) cur = l1;
-                else cur = sp ? stack[--sp] : TRAV_DONE;
-                if (cur < 0 && cur != TRAV_DONE && leaf == 0) {        // postpone the first leaf, keep descending
-                    leaf = cur;
-                    cur = sp ? stack[--sp] : TRAV_DONE;
-                }
-            }
-        }
-        // ---- phase 2: every lane intersects the leaves it holds (postponed first, then current)
-#pragma unroll 1
-        for (int k = 0; k < 2; ++k) {
-            int code;
-            if (k == 0) { code = leaf; leaf = 0; }
-            else { code = (cur != TRAV_DONE) ? cur : 0; if (code) cur = sp ? stack[--sp] : TRAV_DONE; }
-            if (!__any_sync(FULL, code != 0)) continue;
-            int first = (~code) >> 3, count = code ? ((~code) & 7) + 1 : 0;
-#pragma unroll 1
-            for (int i = 0; i < 4; ++i) {
-                if (!__any_sync(FULL, i < count)) break;
-                if (i < count) {
-                    const float4 *tr = sc.tri_isect + 3*size_t(first + i);
-                    const float4 a = __ldg(tr), b = __ldg(tr + 1), c = __ldg(tr + 2);
-                    V3 v0 = v3(a.x, a.y, a.z), e1 = v3(a.w, b.x, b.y), e2 = v3(b.z, b.w, c.x), ng = v3(c.y, c.z, c.w);
-                    V3 C = v0 - o;
-                    V3 R = cross(d, C);
-                    float den = edot(ng, d);
-                    float absDen = fabsf(den);
-                    uint32_t sgn = __float_as_uint(den) & 0x80000000u;
-                    float U = xor_sign(edot(R, e2), sgn);
-                    float V = xor_sign(edot(R, e1), sgn);
-                    if (den != 0.0f && U >= 0.0f && V >= 0.0f && U + V <= absDen) {
-                        float T = xor_sign(edot(ng, C), sgn);
-                        if (T > absDen*tnear && T < absDen*h.t) {
-                            h.t = T/absDen; h.u = U/absDen; h.v = V/absDen; h.id = first + i;
-                        }
-                    }
-                }
-            }
-            if (ANY && h.id != HID_MISS) { cur = TRAV_DONE; leaf = 0; sp = 0; }
-        }
-        if (!__any_sync(FULL, cur != TRAV_DONE)) break;
-    }
-    return h;
-}
-
-#else
-// "if-if" traversal: every loop iteration a lane performs ONE step -- either one inner-node visit (two child
-// slab tests) or one triangle test of its current leaf -- and the lanes reconverge at the end of the
-// iteration.  Compared with the per-lane while-while above this keeps the triangle tests from running with
-// 1-2 active lanes (profiles/r01_a_k_trace_baseline.md).
-template <bool ANY>
-TGB_D Hit trace_scene(const DScene &sc, bool active, V3 o, V3 d, float tnear, float tfar, int ignore) {
-    Hit h; h.t = tfar; h.u = 0.0f; h.v = 0.0f; h.id = HID_MISS;
-    if (!active) return h;
-    for (int i = 0; i < sc.n_analytic; ++i) {
-        int pi = sc.analytic[i];
-        if (ANY && pi == ignore) continue;
-        const DPrim &p = sc.prims[pi];
-        if (p.type == TGB_PRIM_QUAD) quad_intersect(p, pi, o, d, tnear, h);
-        else cube_intersect(p, pi, o, d, tnear, h);
-        if (ANY && h.id != HID_MISS) return h;
-    }
-    if (sc.n_nodes == 0) return h;
-    const float ooeps = 1e-30f;
-    float idx = 1.0f/(fabsf(d.x) > ooeps ? d.x : copysignf(ooeps, d.x));
-    float idy = 1.0f/(fabsf(d.y) > ooeps ? d.y : copysignf(ooeps, d.y));
-    float idz = 1.0f/(fabsf(d.z) > ooeps ? d.z : copysignf(ooeps, d.z));
-#if TGB_FMA_SLAB
-    float oodx = o.x*idx, oody = o.y*idy, oodz = o.z*idz;
-#endif
-    int stack[kStackSize]; int sp = 0;
-    int cur = 0;
-    const float4 *nodes = sc.nodes;
-    const int DONE = int(0x80000000u);
-    while (cur != DONE) {
-        if (cur >= 0) {
-            const float4 n0 = __ldg(nodes + 4*cur), n1 = __ldg(nodes + 4*cur + 1), n2 = __ldg(nodes + 4*cur + 2);
-            const float4 lk = __ldg(nodes + 4*cur + 3);
-#if TGB_FMA_SLAB
-            float c0lox = __fmaf_rn(n0.x, idx, -oodx), c0hix = __fmaf_rn(n0.y, idx, -oodx), c0loy = __fmaf_rn(n0.z, idy, -oody), c0hiy = __fmaf_rn(n0.w, idy, -oody);
-            float c1lox = __fmaf_rn(n1.x, idx, -oodx), c1hix = __fmaf_rn(n1.y, idx, -oodx), c1loy = __fmaf_rn(n1.z, idy, -oody), c1hiy = __fmaf_rn(n1.w, idy, -oody);
-            float c0loz = __fmaf_rn(n2.x, idz, -oodz), c0hiz = __fmaf_rn(n2.y, idz, -oodz), c1loz = __fmaf_rn(n2.z, idz, -oodz), c1hiz = __fmaf_rn(n2.w, idz, -oodz);
-#else
-            float c0lox = (n0.x - o.x)*idx, c0hix = (n0.y - o.x)*idx, c0loy = (n0.z - o.y)*idy, c0hiy = (n0.w - o.y)*idy;
-            float c1lox = (n1.x - o.x)*idx, c1hix = (n1.y - o.x)*idx, c1loy = (n1.z - o.y)*idy, c1hiy = (n1.w - o.y)*idy;
-            float c0loz = (n2.x - o.z)*idz, c0hiz = (n2.y - o.z)*idz, c1loz = (n2.z - o.z)*idz, c1hiz = (n2.w - o.z)*idz;
-#endif
-            float c0min = fmaxf(fmaxf(fminf(c0lox, c0hix), fminf(c0loy, c0hiy)), fmaxf(fminf(c0loz, c0hiz), tnear));
-            float c0max = fminf(fminf(fmaxf(c0lox, c0hix), fmaxf(c0loy, c0hiy)), fminf(fmaxf(c0loz, c0hiz), h.t));
-            float c1min = fmaxf(fmaxf(fminf(c1lox, c1hix), fminf(c1loy, c1hiy)), fmaxf(fminf(c1loz, c1hiz), tnear));
-            float c1max = fminf(fminf(fmaxf(c1lox, c1hix), fmaxf(c1loy, c1hiy)), fminf(fmaxf(c1loz, c1hiz), h.t));
-            bool t0 = c0min <= c0max*1.0000003f, t1 = c1min <= c1max*1.0000003f;
-            int l0 = __float_as_int(lk.x), l1 = __float_as_int(lk.y);
-            if (t0 && t1) {
-                bool swp = c1min < c0min;
-                cur = swp ? l1 : l0;
-                if (sp < kStackSize) stack[sp++] = swp ? l0 : l1;
-            } else if (t0) cur = l0;
-            else if (t1) cur = l1;
-            else cur = sp ? stack[--sp] : DONE;
-        } else {
-            int code = ~cur;
-            int first = code >> 3, rem = code & 7;            // rem = triangles left after this one
-            const float4 *tr = sc.tri_isect + 3*size_t(first);
-            const float4 a = __ldg(tr), b = __ldg(tr + 1), c = __ldg(tr + 2);
-            V3 v0 = v3(a.x, a.y, a.z), e1 = v3(a.w, b.x, b.y), e2 = v3(b.z, b.w, c.x), ng = v3(c.y, c.z, c.w);
-            V3 C = v0 - o;
-            V3 R = cross(d, C);
-            float den = edot(ng, d);
-            float absDen = fabsf(den);
-            uint32_t sgn = __float_as_uint(den) & 0x80000000u;
-            float U = xor_sign(edot(R, e2), sgn);
-            float V = xor_sign(edot(R, e1), sgn);
-            bool hit = false;
-            if (den != 0.0f && U >= 0.0f && V >= 0.0f && U + V <= absDen) {
-                float T = xor_sign(edot(ng, C), sgn);
-                if (T > absDen*tnear && T < absDen*h.t) {
-                    h.t = T/absDen; h.u = U/absDen; h.v = V/absDen; h.id = first; hit = true;
-                }
-            }
-            if (ANY && hit) return h;
-            cur = rem ? ~(((first + 1) << 3) | (rem - 1)) : (sp ? stack[--sp] : DONE);
-        }
-    }
-    return h;
-}
-#endif
-TGB_D Hit trace_closest(const DScene &sc, bool active, V3 o, V3 d, float tnear, float tfar) { return trace_scene<false>(sc, active, o, d, tnear, tfar, -1); }
 
 // Fill a Surface from a hit: Primitive::intersectionInfo for mesh/quad/cube
 // (TriangleMesh.cpp:323-331,344-355; Quad.cpp:112-120; Cube.cpp:157-171) + TraceableScene::intersect (:183-188)
@@ -421,13 +280,19 @@ TGB_D bool quad_light_hit(const DPrim &l, V3 p, V3 d, float tnear, float &t, flo
 }
 
 // ---- kernels ---------------------------------------------------------------------------------
-struct BatchInfo { const uint32_t *pix_id, *pix_seed; uint32_t n_pix, spp_begin, n_paths; };
+struct BatchInfo { const uint32_t *pix_id, *pix_seed; uint32_t n_pix, spp_begin; };
 
-__global__ void __launch_bounds__(256) k_raygen(DScene sc, PathState st, BatchInfo bi, uint32_t *queue, uint32_t *count) {
-    uint32_t i = blockIdx.x*blockDim.x + threadIdx.x;
-    if (i == 0) *count = bi.n_paths;
-    if (i >= bi.n_paths) return;
-    uint32_t pix = i % bi.n_pix, smp_i = bi.spp_begin + i/bi.n_pix;
+// Path (re)generation: paths [first_path, first_path + m) of the step start in slots [slot_base, slot_base + m),
+// right behind the survivors that k_accum compacted to the front of the same buffer.  Consecutive slots are
+// neighbouring pixels of one sample index, so the primary rays stay coherent and every state access is coalesced.
+// = SobolPathSampler::startPath + ReconstructionFilter::sample + PinholeCamera::sampleDirection + the analytic
+// part of the first TraceableScene::intersect.
+__global__ void __launch_bounds__(256) k_regen(DScene sc, PathState st, BatchInfo bi, uint32_t slot_base, uint32_t first_path, uint32_t m) {
+    uint32_t j = blockIdx.x*blockDim.x + threadIdx.x;
+    if (j >= m) return;
+    uint32_t i = slot_base + j;
+    uint32_t path = first_path + j;
+    uint32_t pix = path % bi.n_pix, smp_i = bi.spp_begin + path/bi.n_pix;
     uint32_t pixel_id = __ldg(bi.pix_id + pix);
     Sampler smp; sampler_start(smp, sc.sobol, __ldg(bi.pix_seed + pix), pixel_id, smp_i);
     uint32_t px = pixel_id % sc.cam.res_x, py = pixel_id/sc.cam.res_x;
@@ -447,39 +312,64 @@ __global__ void __launch_bounds__(256) k_raygen(DScene sc, PathState st, BatchIn
     st.ex[i] = 0.0f; st.ey[i] = 0.0f; st.ez[i] = 0.0f;
     st.pcg[i] = smp.pcg;
     st.info[i] = smp.dimension | F_WAS_SPECULAR | F_ALIVE;
-    queue[i] = i;
+    st.pid[i] = path;
+    Hit h = analytic_closest(sc, sc.cam.pos, d, 1e-4f, INFINITY);
+    st.ht[i] = h.t; st.hu[i] = h.u; st.hv[i] = h.v; st.hid[i] = h.id;
 }
 
-template <bool SHADOW>
-TGB_D void count_rays(Counters *ctr, bool valid, bool hit) {
+TGB_D void count_block(unsigned long long *rays, unsigned long long *hits, bool valid, bool hit) {
     unsigned mv = __ballot_sync(0xffffffffu, valid), mh = __ballot_sync(0xffffffffu, valid && hit);
     if ((threadIdx.x & 31) == 0 && mv) {
-        atomicAdd(SHADOW ? &ctr->shadow_rays : &ctr->rays, (unsigned long long)__popc(mv));
-        if (mh) atomicAdd(SHADOW ? &ctr->shadow_hits : &ctr->hits, (unsigned long long)__popc(mh));
+        atomicAdd(rays, (unsigned long long)__popc(mv));
+        if (mh) atomicAdd(hits, (unsigned long long)__popc(mh));
     }
 }
 
-__global__ void __launch_bounds__(128) k_trace(DScene sc, PathState st, const uint32_t *queue, const uint32_t *count, Counters *ctr) {
-    uint32_t i = blockIdx.x*blockDim.x + threadIdx.x;
-    bool valid = i < *count;
-    uint32_t s = 0; V3 o = v3s(0.0f), d = v3(0.0f, 0.0f, 1.0f); float tmin = 0.0f;
-    if (valid) {
-        s = queue[i];
-        o = v3(st.ox[s], st.oy[s], st.oz[s]); d = v3(st.dx[s], st.dy[s], st.dz[s]); tmin = st.tmin[s];
+// TraceableScene::intersect for the path rays: the analytic part of the query was done by the kernel that made the
+// ray (k_raygen / k_accum); this kernel walks the triangle BVH, K rays per lane.
+struct PathRayPolicy {
+    PathState st; uint32_t s;
+    TGB_D bool fetch(uint32_t i, V3 &o, V3 &d, float &tnear, Hit &h, bool &any) {
+        s = i;
+        o = v3(st.ox[s], st.oy[s], st.oz[s]); d = v3(st.dx[s], st.dy[s], st.dz[s]); tnear = st.tmin[s];
+        h.t = st.ht[s]; h.u = st.hu[s]; h.v = st.hv[s]; h.id = st.hid[s]; any = false;
+        return true;
     }
-    Hit h = trace_closest(sc, valid, o, d, tmin, INFINITY);
-    if (valid) { st.ht[s] = h.t; st.hu[s] = h.u; st.hv[s] = h.v; st.hid[s] = h.id; }
-    count_rays<false>(ctr, valid, h.id != HID_MISS);
+    TGB_D void finish(const Hit &h) { st.ht[s] = h.t; st.hu[s] = h.u; st.hv[s] = h.v; st.hid[s] = h.id; }
+};
+__global__ void __launch_bounds__(kTraceBlock, TGB_MINB) k_trace(DScene sc, PathState st, uint32_t n, uint32_t K) {
+    extern __shared__ int smem_stack[];
+    PathRayPolicy pol; pol.st = st; pol.s = 0;
+    bvh_traverse_multi(sc, smem_stack, pol, n, K);
 }
 
-// Parity hook: rays in AoS tgb_ray, hits out as tgb_hit (tgb200_trace_closest).
-__global__ void __launch_bounds__(128) k_trace_rays(DScene sc, const tgb_ray *rays, tgb_hit *hits, uint32_t n) {
+// Parity hook (tgb200_trace_closest): rays in AoS tgb_ray, hits out as tgb_hit, through the same analytic pass and
+// the same BVH kernel code as the renderer.
+struct HookPolicy {
+    const tgb_ray *rays; Hit *out; uint32_t i;
+    TGB_D bool fetch(uint32_t idx, V3 &o, V3 &d, float &tnear, Hit &h, bool &any) {
+        i = idx;
+        o = v3(rays[i].o[0], rays[i].o[1], rays[i].o[2]); d = v3(rays[i].d[0], rays[i].d[1], rays[i].d[2]); tnear = rays[i].tmin;
+        h = out[i]; any = false;
+        return true;
+    }
+    TGB_D void finish(const Hit &h) { out[i] = h; }
+};
+__global__ void __launch_bounds__(256) k_hook_analytic(DScene sc, const tgb_ray *rays, Hit *out, uint32_t n) {
     uint32_t i = blockIdx.x*blockDim.x + threadIdx.x;
-    bool valid = i < n;
-    V3 o = v3s(0.0f), d = v3(0.0f, 0.0f, 1.0f); float t0 = 0.0f, t1 = 0.0f;
-    if (valid) { o = v3(rays[i].o[0], rays[i].o[1], rays[i].o[2]); d = v3(rays[i].d[0], rays[i].d[1], rays[i].d[2]); t0 = rays[i].tmin; t1 = rays[i].tmax; }
-    Hit h = trace_closest(sc, valid, o, d, t0, t1);
-    if (!valid) return;
+    if (i >= n) return;
+    out[i] = analytic_closest(sc, v3(rays[i].o[0], rays[i].o[1], rays[i].o[2]), v3(rays[i].d[0], rays[i].d[1], rays[i].d[2]), rays[i].tmin, rays[i].tmax);
+}
+__global__ void __launch_bounds__(kTraceBlock) k_hook_bvh(DScene sc, const tgb_ray *rays, Hit *out, uint32_t n, uint32_t K) {
+    extern __shared__ int smem_stack[];
+    HookPolicy pol; pol.rays = rays; pol.out = out; pol.i = 0;
+    bvh_traverse_multi(sc, smem_stack, pol, n, K);
+}
+__global__ void __launch_bounds__(256) k_hook_finish(DScene sc, const tgb_ray *rays, const Hit *in, tgb_hit *hits, uint32_t n) {
+    uint32_t i = blockIdx.x*blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    V3 o = v3(rays[i].o[0], rays[i].o[1], rays[i].o[2]), d = v3(rays[i].d[0], rays[i].d[1], rays[i].d[2]);
+    Hit h = in[i];
     tgb_hit out; out.primitive = -1; out.prim_id = 0; out.t = h.t; out.u = 0.0f; out.v = 0.0f; out.backside = 0;
     if (h.id != HID_MISS) {
         Surface s; make_surface(sc, h, o, d, s);
@@ -491,14 +381,16 @@ __global__ void __launch_bounds__(128) k_trace_rays(DScene sc, const tgb_ray *ra
 }
 
 // handleSurface (integrators/TraceBase.cpp:516-568) + the loop tail of traceSample (PathTracer.cpp:108-126)
-__global__ void __launch_bounds__(128) k_shade(DScene sc, PathState st, BatchInfo bi, const uint32_t *queue, const uint32_t *count,
-                                               uint32_t *squeue, uint32_t *scount) {
+__global__ void __launch_bounds__(128) k_shade(DScene sc, PathState st, BatchInfo bi, uint32_t n,
+                                               uint32_t *squeue, uint32_t *scount, Counters *ctr) {
     uint32_t i = blockIdx.x*blockDim.x + threadIdx.x;
-    bool valid = i < *count;
+    bool valid = i < n;
     bool qn = false, qm = false, qn_any = false, qm_any = false;
     uint32_t s = 0;
+    // one path query (TraceableScene::intersect) was completed for every slot in the queue
+    count_block(&ctr->rays, &ctr->hits, valid, valid && st.hid[valid ? i : 0] != HID_MISS);
     if (valid) {
-        s = queue[i];
+        s = i;
         uint32_t info = st.info[s];
         int bounce = int((info >> 16) & 0xFFu);
         bool wasSpecular = (info & F_WAS_SPECULAR) != 0;
@@ -523,8 +415,9 @@ __global__ void __launch_bounds__(128) k_shade(DScene sc, PathState st, BatchInf
         } else {
             Sampler smp; smp.sobol = sc.sobol; smp.pcg = st.pcg[s]; smp.dimension = info & 0xFFFFu;
             {
-                uint32_t pix = s % bi.n_pix;
-                smp.index = bi.spp_begin + s/bi.n_pix;
+                uint32_t path = st.pid[s];
+                uint32_t pix = path % bi.n_pix;
+                smp.index = bi.spp_begin + path/bi.n_pix;
                 smp.scramble = __ldg(bi.pix_seed + pix) ^ hash32(__ldg(bi.pix_id + pix));
             }
             Surface sf; make_surface(sc, h, o, d, sf);
@@ -698,89 +591,122 @@ __global__ void __launch_bounds__(128) k_shade(DScene sc, PathState st, BatchInf
     }
 }
 
-// attenuatedEmission + generalizedShadowRay (TraceBase.cpp:144-174,62-125) for one NEE or MIS query.
-//  * "any" queries (quad / environment lights): lightF / bsdfF were finished by k_shade; this kernel only looks for
-//    a blocker in [epsilon, t_light] other than the light and stores the value if there is none;
+// attenuatedEmission + generalizedShadowRay (TraceBase.cpp:144-174,62-125) for the NEE and MIS queries.
+//  * "any" queries (quad / environment lights): lightF / bsdfF were finished by k_shade; what remains is the
+//    search for a blocker in [epsilon, t_light] other than the light; the value is stored if there is none;
 //  * mesh-light queries: one closest-hit query decides visibility (the light is part of the scene) and the epilogue
 //    evaluates evalDirect / directPdf on the light hit: lightF (TraceBase.cpp:279-284) or bsdfF (:316-320).
-__global__ void __launch_bounds__(128) k_shadow(DScene sc, PathState st, const uint32_t *squeue, const uint32_t *scount, Counters *ctr) {
+// k_shadow_prep tests the analytic primitives coherently, resolves what it can and compacts the rest for
+// k_shadow_bvh (persistent multi-ray traversal of the triangle BVH).
+struct ShadowState { float *qt, *qu, *qv; int *qid; };      // initial hit of a compacted closest-hit query
+
+TGB_D void shadow_store_any(PathState &st, uint32_t s, bool mis) {
+    if (!mis) { st.lx[s] = st.nfx[s]; st.ly[s] = st.nfy[s]; st.lz[s] = st.nfz[s]; }
+    else { st.bx[s] = st.mwx[s]; st.by[s] = st.mwy[s]; st.bz[s] = st.mwz[s]; }
+}
+TGB_D void shadow_resolve_closest(const DScene &sc, PathState &st, uint32_t s, bool mis, int li, V3 p, V3 d, const Hit &h) {
+    if (h.id == HID_MISS) return;
+    const DPrim &l = sc.prims[li];
+    Surface ls; make_surface(sc, h, p, d, ls);
+    bool visible = ls.prim == li;
+    if (visible && !mis && h.t*(1.0f + 1e-3f) < st.ndist[s]) visible = false;                   // TraceBase.cpp:160
+    if (!visible) return;
+    V3 em = eval_direct(sc, ls);
+    if (is_zero(em)) return;
+    if (!mis) {
+        V3 f = v3(st.nfx[s], st.nfy[s], st.nfz[s]);
+        float pdfL = st.npl[s];
+        V3 lightF = (f*em)/pdfL;
+        lightF = lightF*power_heuristic(pdfL, st.npb[s]);
+        st.lx[s] = lightF.x; st.ly[s] = lightF.y; st.lz[s] = lightF.z;
+    } else {
+        float directPdf = length_sq(p - ls.p)/(-dot(d, ls.Ng)*l.total_area);                    // TriangleMesh.cpp:477-481
+        V3 w = v3(st.mwx[s], st.mwy[s], st.mwz[s]);
+        V3 bsdfF = em*w;
+        bsdfF = bsdfF*power_heuristic(st.mpb[s], directPdf);
+        st.bx[s] = bsdfF.x; st.by[s] = bsdfF.y; st.bz[s] = bsdfF.z;
+    }
+}
+
+__global__ void __launch_bounds__(256) k_shadow_prep(DScene sc, PathState st, ShadowState ss, const uint32_t *squeue, const uint32_t *scount,
+                                                      uint32_t *squeue2, uint32_t *scount2, Counters *ctr) {
     uint32_t i = blockIdx.x*blockDim.x + threadIdx.x;
     bool valid = i < *scount;
-    uint32_t s = 0; bool mis = false, any = false; int li = -1;
-    V3 p = v3s(0.0f), d = v3(0.0f, 0.0f, 1.0f); float tfar = INFINITY;
+    bool keep = false, blocked = false; uint32_t q = 0; Hit h; h.t = INFINITY; h.u = h.v = 0.0f; h.id = HID_MISS;
     if (valid) {
-        uint32_t q = squeue[i]; s = q >> 2; mis = q & 1u; any = q & 2u;
+        q = squeue[i];
+        uint32_t s = q >> 2; bool mis = q & 1u, any = q & 2u;
+        V3 p = v3(st.px[s], st.py[s], st.pz[s]);
+        V3 d = mis ? v3(st.mdx[s], st.mdy[s], st.mdz[s]) : v3(st.ndx[s], st.ndy[s], st.ndz[s]);
+        int li = st.qlight[s];
+        if (any) {
+            float tfar = mis ? st.mpb[s] : st.ndist[s];
+            blocked = analytic_any(sc, p, d, 5e-4f, tfar, li);
+            if (!blocked) { if (sc.n_nodes == 0) shadow_store_any(st, s, mis); else keep = true; }
+        } else {
+            h = analytic_closest(sc, p, d, 5e-4f, INFINITY);
+            if (sc.n_nodes == 0) { blocked = h.id != HID_MISS; shadow_resolve_closest(sc, st, s, mis, li, p, d, h); }
+            else keep = true;
+        }
+    }
+    count_block(&ctr->shadow_rays, &ctr->shadow_hits, valid, blocked);
+    unsigned m = __ballot_sync(0xffffffffu, keep);
+    if (m) {
+        unsigned lane = threadIdx.x & 31, base = 0;
+        if (lane == 0) base = atomicAdd(scount2, unsigned(__popc(m)));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (keep) {
+            uint32_t at = base + __popc(m & ((1u << lane) - 1u));
+            squeue2[at] = q;
+            if (!(q & 2u)) { ss.qt[at] = h.t; ss.qu[at] = h.u; ss.qv[at] = h.v; ss.qid[at] = h.id; }
+        }
+    }
+}
+
+struct ShadowPolicy {
+    DScene sc; PathState st; ShadowState ss; const uint32_t *squeue2; unsigned long long *hits;
+    uint32_t s; bool mis, any; int li; V3 p, d;
+    TGB_D bool fetch(uint32_t i, V3 &o, V3 &dd, float &tnear, Hit &h, bool &anyq) {
+        uint32_t q = squeue2[i];
+        s = q >> 2; mis = q & 1u; any = q & 2u;
         p = v3(st.px[s], st.py[s], st.pz[s]);
         d = mis ? v3(st.mdx[s], st.mdy[s], st.mdz[s]) : v3(st.ndx[s], st.ndy[s], st.ndz[s]);
         li = st.qlight[s];
-        if (any) tfar = mis ? st.mpb[s] : st.ndist[s];
+        o = p; dd = d; tnear = 5e-4f; anyq = any;
+        if (any) { h.t = mis ? st.mpb[s] : st.ndist[s]; h.u = 0.0f; h.v = 0.0f; h.id = HID_MISS; }
+        else { h.t = ss.qt[i]; h.u = ss.qu[i]; h.v = ss.qv[i]; h.id = ss.qid[i]; }
+        return true;
     }
-    // both query kinds can share a warp (scenes mixing mesh lights with quad/environment lights): run the
-    // occlusion traversal for the "any" lanes, then the closest-hit traversal for the rest
-    bool anyhit = false;
-    if (__any_sync(0xffffffffu, valid && any)) {
-        Hit h = trace_scene<true>(sc, valid && any, p, d, 5e-4f, tfar, li);
-        if (valid && any) {
-            anyhit = h.id != HID_MISS;
-            if (!anyhit) {
-                if (!mis) { st.lx[s] = st.nfx[s]; st.ly[s] = st.nfy[s]; st.lz[s] = st.nfz[s]; }
-                else { st.bx[s] = st.mwx[s]; st.by[s] = st.mwy[s]; st.bz[s] = st.mwz[s]; }
-            }
-        }
+    TGB_D void finish(const Hit &h) {
+        if (h.id != HID_MISS) atomicAdd(hits, 1ull);
+        if (any) { if (h.id == HID_MISS) shadow_store_any(st, s, mis); }
+        else shadow_resolve_closest(sc, st, s, mis, li, p, d, h);
     }
-    if (__any_sync(0xffffffffu, valid && !any)) {
-        Hit h = trace_scene<false>(sc, valid && !any, p, d, 5e-4f, INFINITY, -1);
-        if (valid && !any) {
-            const DPrim &l = sc.prims[li];
-            anyhit = h.id != HID_MISS;
-            if (anyhit) {
-                Surface ls; make_surface(sc, h, p, d, ls);
-                bool visible = ls.prim == li;
-                if (visible && !mis && h.t*(1.0f + 1e-3f) < st.ndist[s]) visible = false;       // TraceBase.cpp:160
-                if (visible) {
-                    V3 em = eval_direct(sc, ls);
-                    if (!is_zero(em)) {
-                        if (!mis) {
-                            V3 f = v3(st.nfx[s], st.nfy[s], st.nfz[s]);
-                            float pdfL = st.npl[s];
-                            V3 lightF = (f*em)/pdfL;
-                            lightF = lightF*power_heuristic(pdfL, st.npb[s]);
-                            st.lx[s] = lightF.x; st.ly[s] = lightF.y; st.lz[s] = lightF.z;
-                        } else {
-                            // TriangleMesh::directPdf (TriangleMesh.cpp:477-481)
-                            float directPdf = length_sq(p - ls.p)/(-dot(d, ls.Ng)*l.total_area);
-                            V3 w = v3(st.mwx[s], st.mwy[s], st.mwz[s]);
-                            V3 bsdfF = em*w;
-                            bsdfF = bsdfF*power_heuristic(st.mpb[s], directPdf);
-                            st.bx[s] = bsdfF.x; st.by[s] = bsdfF.y; st.bz[s] = bsdfF.z;
-                        }
-                    }
-                }
-            }
-        }
-    }
-    count_rays<true>(ctr, valid, anyhit);
+};
+__global__ void __launch_bounds__(kTraceBlock, TGB_MINB) k_shadow_bvh(DScene sc, PathState st, ShadowState ss, const uint32_t *squeue2, const uint32_t *scount2,
+                                                            Counters *ctr, uint32_t K) {
+    extern __shared__ int smem_stack[];
+    ShadowPolicy pol; pol.sc = sc; pol.st = st; pol.ss = ss; pol.squeue2 = squeue2; pol.hits = &ctr->shadow_hits;
+    bvh_traverse_multi(sc, smem_stack, pol, *scount2, K);
 }
 
-// Fold this bounce's direct light + surface emission into the path (order as in handleSurface:537-543),
-// apply the NaN guards of traceSample (PathTracer.cpp:119-122,130) and compact the survivors.
-__global__ void __launch_bounds__(256) k_accum(DScene sc, PathState st, const uint32_t *queue, const uint32_t *count,
-                                               uint32_t *next_queue, uint32_t *next_count) {
-    uint32_t i = blockIdx.x*blockDim.x + threadIdx.x;
-    bool valid = i < *count;
-    bool alive = false; uint32_t s = 0;
+// Fold this bounce's direct light + surface emission into the path (order as in handleSurface:537-543), apply the
+// NaN guards of traceSample (PathTracer.cpp:119-122,130), store finished samples, and MOVE the survivors' persistent
+// state to the front of the other state buffer (physical compaction: all later accesses are coalesced, no slot
+// indirection).  The survivors' next ray gets the analytic part of its TraceableScene::intersect here.
+__global__ void __launch_bounds__(256) k_accum(DScene sc, PathState st, PathState dst, uint32_t n, uint32_t *next_count) {
+    uint32_t s = blockIdx.x*blockDim.x + threadIdx.x;
+    bool valid = s < n;
+    bool alive = false; uint32_t info = 0; V3 em = v3s(0.0f);
     if (valid) {
-        s = queue[i];
-        uint32_t info = st.info[s];
-        V3 em = v3(st.ex[s], st.ey[s], st.ez[s]);
-        bool touched = false;
+        info = st.info[s];
+        em = v3(st.ex[s], st.ey[s], st.ez[s]);
         if (info & F_HAS_NEE) {
-            // generalizedShadowRay's `bounce >= minBounces` test (TraceBase.cpp:117) on bounce+1 of the shading bounce
             V3 L = v3(st.lx[s], st.ly[s], st.lz[s]), B = v3(st.bx[s], st.by[s], st.bz[s]);
             V3 r = ((L + B)*st.wl[s])*v3(st.ux[s], st.uy[s], st.uz[s]);
-            em = em + r; touched = true;
+            em = em + r;
         }
-        if (info & F_HAS_SURF) { em = em + v3(st.sx[s], st.sy[s], st.sz[s]); touched = true; }
+        if (info & F_HAS_SURF) em = em + v3(st.sx[s], st.sy[s], st.sz[s]);
         alive = (info & F_ALIVE) != 0;
         bool finalCheck = (info & F_FINAL_CHECK) != 0;
         if (alive || finalCheck) {
@@ -791,18 +717,27 @@ __global__ void __launch_bounds__(256) k_accum(DScene sc, PathState st, const ui
                 bad = isnan(sum(d) + sum(o));
             }
             bad = bad || isnan(sum(thr) + sum(em));
-            if (bad) { em = v3s(0.0f); alive = false; touched = true; }
+            if (bad) { em = v3s(0.0f); alive = false; }
         }
         if (alive && finalCheck) alive = false;                  // bounce reached maxBounces: loop exits
-        if (touched) { st.ex[s] = em.x; st.ey[s] = em.y; st.ez[s] = em.z; }
-        st.info[s] = (info & ~(F_HAS_NEE | F_HAS_SURF | F_ALIVE | F_FINAL_CHECK)) | (alive ? F_ALIVE : 0u);
+        if (!alive) { uint32_t path = st.pid[s]; st.rx[path] = em.x; st.ry[path] = em.y; st.rz[path] = em.z; }   // the sample's radiance
     }
     unsigned m = __ballot_sync(0xffffffffu, alive);
     if (m) {
         unsigned lane = threadIdx.x & 31, base = 0;
         if (lane == 0) base = atomicAdd(next_count, unsigned(__popc(m)));
         base = __shfl_sync(0xffffffffu, base, 0);
-        if (alive) next_queue[base + __popc(m & ((1u << lane) - 1u))] = s;
+        if (alive) {
+            uint32_t t = base + __popc(m & ((1u << lane) - 1u));
+            V3 o = v3(st.ox[s], st.oy[s], st.oz[s]), d = v3(st.dx[s], st.dy[s], st.dz[s]); float tmin = st.tmin[s];
+            dst.ox[t] = o.x; dst.oy[t] = o.y; dst.oz[t] = o.z; dst.dx[t] = d.x; dst.dy[t] = d.y; dst.dz[t] = d.z; dst.tmin[t] = tmin;
+            dst.tx[t] = st.tx[s]; dst.ty[t] = st.ty[s]; dst.tz[t] = st.tz[s];
+            dst.ex[t] = em.x; dst.ey[t] = em.y; dst.ez[t] = em.z;
+            dst.pcg[t] = st.pcg[s]; dst.pid[t] = st.pid[s];
+            dst.info[t] = (info & ~(F_HAS_NEE | F_HAS_SURF | F_ALIVE | F_FINAL_CHECK)) | F_ALIVE;
+            Hit h = analytic_closest(sc, o, d, tmin, INFINITY);
+            dst.ht[t] = h.t; dst.hu[t] = h.u; dst.hv[t] = h.v; dst.hid[t] = h.id;
+        }
     }
 }
 
@@ -815,7 +750,7 @@ __global__ void __launch_bounds__(256) k_resolve(PathState st, BatchInfo bi, uin
     uint32_t cnt = fb_count[pid];
     for (uint32_t k = 0; k < spp_count; ++k) {
         size_t s = size_t(k)*bi.n_pix + pix;
-        float cx = st.ex[s], cy = st.ey[s], cz = st.ez[s];
+        float cx = st.rx[s], cy = st.ry[s], cz = st.rz[s];
         if (isnan(cx) || isnan(cy) || isnan(cz) || isinf(cx) || isinf(cy) || isinf(cz)) continue;
         float n = float(cnt + 1u); cnt++;
         mx += (cx - mx)/n; my += (cy - my)/n; mz += (cz - mz)/n;
