@@ -103,6 +103,7 @@ def make_scenes():
     scenes["cornell_mesh"] = synth.cornell_mesh(os.path.join(HERE, "cornell_mesh"), "scene", subdiv=2, res=res, spp=spp)
     scenes["materials"] = synth.material_room(os.path.join(HERE, "materials"), "scene", res=res, spp=spp, subdiv=2)
     scenes["materials_env"] = synth.material_room(os.path.join(HERE, "materials_env"), "scene", res=res, spp=spp, subdiv=2, env=[0.4, 0.5, 0.7])
+    scenes["coat_env"] = synth.materialtest_standin(os.path.join(HERE, "coat_env"), "scene", res=res, spp=spp, subdiv=2, env_res=(64, 32))
     for name, path in scenes.items():
         d = os.path.dirname(path)
         for exe, tag in (("tungsten_pathseed", "ref_pathseed"), ("tungsten", "ref_stock")):

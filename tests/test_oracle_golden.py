@@ -38,7 +38,7 @@ def test_analytic_scenes_bit_exact(name, mode, ref):
     assert np.array_equal(img, want)
 
 
-@pytest.mark.parametrize("name", ["cornell_mesh", "materials", "materials_env"])
+@pytest.mark.parametrize("name", ["cornell_mesh", "materials", "materials_env", "coat_env"])
 @pytest.mark.parametrize("mode,ref", [(0, "ref_pathseed.pfm"), (1, "ref_stock.pfm")])
 def test_mesh_scenes_close(name, mode, ref):
     img = _render(name, mode)
@@ -56,3 +56,28 @@ def test_pathseed_and_stock_references_differ():
     a = scene.load_pfm(os.path.join(G, "cornell", "ref_pathseed.pfm"))
     b = scene.load_pfm(os.path.join(G, "cornell", "ref_stock.pfm"))
     assert not np.array_equal(a, b)        # Russian roulette draws differ -> the contract matters
+
+
+@pytest.mark.skipif(not os.path.exists("/root/reference/data/materialtest/materialtest.json") or
+                    not os.path.exists(os.path.join(os.path.dirname(HERE), "oracle", "_ref", "tungsten_pathseed")),
+                    reason="needs the mounted reference (build container only)")
+def test_real_materialtest_scene_against_reference_binary(tmp_path):
+    """BASELINE.json config C0, the reference's own shipped scene (80,768 triangles, smooth_coat over rough_conductor,
+    checker floor, envmap.hdr importance sampling): oracle vs the reference binary at 96x96, 8 spp."""
+    import json, shutil, subprocess
+    src = "/root/reference/data/materialtest"
+    for f in os.listdir(src):
+        shutil.copy(os.path.join(src, f), tmp_path)
+    js = json.load(open(tmp_path/"materialtest.json"))
+    js["camera"]["resolution"] = [96, 96]
+    js["renderer"].update(spp=8, spp_step=8, adaptive_sampling=False, stratified_sampler=True, hdr_output_file="out.pfm",
+                          output_file="out.png", overwrite_output_files=True)
+    json.dump(js, open(tmp_path/"mt.json", "w"))
+    exe = os.path.join(os.path.dirname(HERE), "oracle", "_ref", "tungsten_pathseed")
+    subprocess.check_call([exe, "-t", "4", "-d", str(tmp_path/"ref"), str(tmp_path/"mt.json")], stdout=subprocess.DEVNULL)
+    want = scene.load_pfm(str(tmp_path/"ref"/"out.pfm"))
+    fs = scene.load_scene(str(tmp_path/"mt.json"))
+    o = pyoracle.Oracle(fs); img, _ = o.render(8); o.close()
+    d = np.abs(img - want).max(axis=2)
+    assert float((d == 0).mean()) >= 0.7
+    assert float((d <= 1e-5*(1.0 + np.abs(want).max(axis=2))).mean()) >= 0.99

@@ -154,6 +154,7 @@ uint32_t bsdf_lobes(const tgb_bsdf &b) {
     case TGB_BSDF_ROUGH_DIELECTRIC: return b.enable_refraction ? (LOBE_GLOSSY_R | LOBE_GLOSSY_T) : LOBE_GLOSSY_R;
     case TGB_BSDF_PLASTIC: return LOBE_SPEC_R | LOBE_DIFFUSE_R;
     case TGB_BSDF_ROUGH_PLASTIC: return LOBE_GLOSSY_R | LOBE_DIFFUSE_R;
+    case TGB_BSDF_SMOOTH_COAT: return LOBE_SPEC_R;          // | substrate lobes, added by upload_scene
     default: return 0xFFFFFFFFu;
     }
 }
@@ -163,41 +164,45 @@ struct HostTex { DTex d; V3 maxv; std::vector<float> marg_pdf, marg_cdf, pdf, cd
 // BitmapTexture::makeSamplable(MAP_SPHERICAL) + Distribution2D (textures/BitmapTexture.cpp:400-431,
 // sampling/Distribution2D.hpp:18-46)
 void build_spherical_distribution(const tgb_texture &t, HostTex &ht) {
-    int w = int(t.res_u), h = int(t.res_v);
-    std::vector<float> weights(size_t(w)*h), tmp(size_t(w)*h);
-    for (int y = 0; y < h; ++y) {
-        float rowWeight = std::sin((y*PI_F)/h);
-        for (int x = 0; x < w; ++x) {
-            const float *p = t.texels + 3*(size_t(y)*w + x);
-            weights[size_t(y)*w + x] = std::max(p[0], std::max(p[1], p[2]))*rowWeight;
+    int w = int(t.res_u), h = int(t.res_v); bool clampm = (t.flags >> 1) & 1;
+    std::vector<float> weights(size_t(w)*h);
+    for (int y = 0, idx = 0; y < h; ++y) {
+        float rowWeight = 1.0f;
+        rowWeight *= std::sin((y*PI_F)/h);
+        for (int x = 0; x < w; ++x, ++idx) {
+            const float *p = t.texels + 3*size_t(idx);
+            weights[idx] = max_comp(v3(p[0], p[1], p[2]))*rowWeight;
         }
     }
-    for (int y = 0; y < h; ++y) for (int x = 0; x < w; ++x) {
-        float m = weights[size_t(y)*w + x];
-        if (x < w - 1) m = std::max(m, weights[size_t(y)*w + x + 1]);
-        if (x > 0) m = std::max(m, weights[size_t(y)*w + x - 1]);
-        tmp[size_t(y)*w + x] = m;
+    // in-place max dilation, x then y, wrapping unless the texture clamps (BitmapTexture.cpp:411-428)
+    for (int y = 0; y < h; ++y) {
+        for (int x = 0; x < w - 1; ++x) weights[x + y*w] = std::max(weights[x + y*w], weights[x + 1 + y*w]);
+        if (!clampm) weights[y*w] = weights[w - 1 + y*w] = std::max(weights[w - 1 + y*w], weights[y*w]);
+        for (int x = w - 1; x > 0; --x) weights[x + y*w] = std::max(weights[x + y*w], weights[x - 1 + y*w]);
     }
-    for (int y = 0; y < h; ++y) for (int x = 0; x < w; ++x) {
-        float m = tmp[size_t(y)*w + x];
-        if (y < h - 1) m = std::max(m, tmp[size_t(y + 1)*w + x]);
-        if (y > 0) m = std::max(m, tmp[size_t(y - 1)*w + x]);
-        weights[size_t(y)*w + x] = m;
+    for (int x = 0; x < w; ++x) {
+        for (int y = 0; y < h - 1; ++y) weights[x + y*w] = std::max(weights[x + y*w], weights[x + (y + 1)*w]);
+        if (!clampm) weights[x] = weights[x + (h - 1)*w] = std::max(weights[x], weights[x + (h - 1)*w]);
+        for (int y = h - 1; y > 0; --y) weights[x + y*w] = std::max(weights[x + y*w], weights[x + (y - 1)*w]);
     }
+    // Distribution2D (sampling/Distribution2D.hpp:18-60)
     ht.pdf = weights; ht.cdf.assign(size_t(w + 1)*h, 0.0f); ht.marg_pdf.assign(h, 0.0f); ht.marg_cdf.assign(h + 1, 0.0f);
     for (int y = 0; y < h; ++y) {
-        float *pdf = ht.pdf.data() + size_t(y)*w, *cdf = ht.cdf.data() + size_t(y)*(w + 1);
-        cdf[0] = 0.0f;
-        for (int x = 0; x < w; ++x) cdf[x + 1] = cdf[x] + pdf[x];
-        ht.marg_pdf[y] = cdf[w];
+        int idxP = y*w, idxC = y*(w + 1);
+        ht.cdf[idxC] = 0.0f;
+        for (int x = 0; x < w; ++x, ++idxP, ++idxC) { ht.marg_pdf[y] += ht.pdf[idxP]; ht.cdf[idxC + 1] = ht.cdf[idxC] + ht.pdf[idxP]; }
         ht.marg_cdf[y + 1] = ht.marg_cdf[y] + ht.marg_pdf[y];
     }
     for (int y = 0; y < h; ++y) {
-        float *pdf = ht.pdf.data() + size_t(y)*w, *cdf = ht.cdf.data() + size_t(y)*(w + 1);
-        if (ht.marg_pdf[y] > 0.0f) { float scale = 1.0f/ht.marg_pdf[y]; for (int x = 0; x < w; ++x) { pdf[x] *= scale; cdf[x] *= scale; } }
-        cdf[w] = 1.0f;
+        int idxP = y*w, idxC = y*(w + 1), idxTail = idxC + w;
+        float rowWeight = ht.cdf[idxTail];
+        if (rowWeight < 1e-4f) { for (int x = 0; x < w; ++x, ++idxP, ++idxC) { ht.pdf[idxP] = 1.0f/w; ht.cdf[idxC] = x/float(w); } }
+        else { for (int x = 0; x < w; ++x, ++idxP, ++idxC) { ht.pdf[idxP] /= rowWeight; ht.cdf[idxC] /= rowWeight; } }
+        ht.cdf[idxTail] = 1.0f;
     }
-    if (ht.marg_cdf[h] > 0.0f) { float scale = 1.0f/ht.marg_cdf[h]; for (int y = 0; y < h; ++y) { ht.marg_pdf[y] *= scale; ht.marg_cdf[y] *= scale; } }
+    float totalWeight = ht.marg_cdf[h];
+    for (float &p : ht.marg_pdf) p /= totalWeight;
+    for (float &cc : ht.marg_cdf) cc /= totalWeight;
     ht.marg_cdf[h] = 1.0f;
     ht.has_dist = true;
 }
@@ -249,7 +254,14 @@ int upload_scene(tgb_ctx *c, const tgb_scene_desc *d) {
         bool rough = b.type == TGB_BSDF_ROUGH_CONDUCTOR || b.type == TGB_BSDF_ROUGH_DIELECTRIC || b.type == TGB_BSDF_ROUGH_PLASTIC;
         if (rough && (b.roughness_tex < 0 || uint32_t(b.roughness_tex) >= d->n_textures)) return fail(c, TGB_ERR_INVALID, "bsdf %u: bad roughness texture", i);
         o.dist = b.distribution; o.albedo_tex = b.albedo_tex; o.rough_tex = b.roughness_tex;
-        o.ior = b.ior; o.inv_ior = 1.0f/b.ior; o.eta = f3(b.eta); o.k = f3(b.k); o.enable_t = b.enable_refraction;
+        o.ior = b.ior; o.inv_ior = 1.0f/b.ior; o.eta = f3(b.eta); o.k = f3(b.k); o.enable_t = b.enable_refraction; o.substrate = b.substrate;
+        if (b.type == TGB_BSDF_SMOOTH_COAT) {                                             // bsdfs/SmoothCoatBsdf.cpp:218-223
+            if (b.substrate < 0 || uint32_t(b.substrate) >= d->n_bsdfs || d->bsdfs[b.substrate].type == TGB_BSDF_SMOOTH_COAT)
+                return fail(c, TGB_ERR_UNSUPPORTED, "bsdf %u: smooth_coat needs a non-coat substrate", i);
+            o.scaled_sigma_a = f3(b.sigma_a)*b.thickness;
+            o.avg_transmittance = std::exp(-2.0f*avg(o.scaled_sigma_a));
+            o.lobes = LOBE_SPEC_R | bsdf_lobes(d->bsdfs[b.substrate]);
+        }
         if (b.type == TGB_BSDF_PLASTIC || b.type == TGB_BSDF_ROUGH_PLASTIC) {             // bsdfs/PlasticBsdf.cpp:179-185
             o.scaled_sigma_a = f3(b.sigma_a)*b.thickness;
             o.avg_transmittance = std::exp(-2.0f*avg(o.scaled_sigma_a));

@@ -99,7 +99,7 @@ struct DTex {
 struct DBsdf {
     uint32_t type, lobes, dist; int albedo_tex, rough_tex;
     float ior, inv_ior; V3 eta, k; V3 scaled_sigma_a; float avg_transmittance, diffuse_fresnel, substrate_weight;
-    uint32_t enable_t;
+    uint32_t enable_t; int substrate;
 };
 enum : uint32_t { PF_EMISSIVE = 1, PF_SAMPLABLE = 2, PF_INFINITE = 4, PF_SMOOTH = 8 };
 struct DPrim {
@@ -369,7 +369,7 @@ TGB_D float bsdf_eta(const DBsdf &b, const Event &e) {                          
 }
 
 // Bsdf::sample(event, adjoint=false) (bsdfs/Bsdf.hpp:71-83) over the per-lobe sample() bodies
-TGB_D bool bsdf_sample(const DScene &sc, const DBsdf &b, const Surface &s, Sampler &smp, Event &e) {
+TGB_D bool bsdf_sample_base(const DScene &sc, const DBsdf &b, const Surface &s, Sampler &smp, Event &e) {
     bool ok = false;
     switch (b.type) {
     case TGB_BSDF_LAMBERT: {                                                           // bsdfs/LambertBsdf.cpp:27-38
@@ -488,13 +488,11 @@ TGB_D bool bsdf_sample(const DScene &sc, const DBsdf &b, const Surface &s, Sampl
         ok = true; break; }
     default: break;                                                                    // bsdfs/NullBsdf.cpp: sample() == false
     }
-    if (!ok) return false;
-    e.weight = e.weight*sqr(bsdf_eta(b, e));
-    return true;
+    return ok;
 }
 
 // Bsdf::eval(event, adjoint=false) (bsdfs/Bsdf.hpp:85-97)
-TGB_D V3 bsdf_eval(const DScene &sc, const DBsdf &b, const Surface &s, const Event &e) {
+TGB_D V3 bsdf_eval_base(const DScene &sc, const DBsdf &b, const Surface &s, const Event &e) {
     V3 f = v3s(0.0f);
     switch (b.type) {
     case TGB_BSDF_LAMBERT:                                                             // LambertBsdf.cpp:40-47
@@ -556,10 +554,10 @@ TGB_D V3 bsdf_eval(const DScene &sc, const DBsdf &b, const Surface &s, const Eve
         break; }
     default: break;
     }
-    return f*sqr(bsdf_eta(b, e));
+    return f;
 }
 
-TGB_D float bsdf_pdf(const DScene &sc, const DBsdf &b, const Surface &s, const Event &e) {
+TGB_D float bsdf_pdf_base(const DScene &sc, const DBsdf &b, const Surface &s, const Event &e) {
     switch (b.type) {
     case TGB_BSDF_LAMBERT:                                                             // LambertBsdf.cpp:61-68
         if (!(e.requested & LOBE_DIFFUSE_R)) return 0.0f;
@@ -609,6 +607,95 @@ TGB_D float bsdf_pdf(const DScene &sc, const DBsdf &b, const Surface &s, const E
     }
 }
 
+// SmoothCoatBsdf (bsdfs/SmoothCoatBsdf.cpp:41-100,146-179,181-216): a Dirac dielectric coat over a substrate lobe
+// (one level of nesting: the substrate is never a coat) + the public Bsdf::sample/eval wrappers (bsdfs/Bsdf.hpp:71-97).
+TGB_D void coat_warp(const DBsdf &b, const Event &e, Event &q, float &Fi, float &Fo, float &cosThetaTi, float &cosThetaTo) {
+    float eta = 1.0f/b.ior;
+    Fi = dielectric_reflectance(eta, e.wi.z, cosThetaTi);
+    Fo = dielectric_reflectance(eta, e.wo.z, cosThetaTo);
+    q = e;
+    q.wi = v3(e.wi.x*eta, e.wi.y*eta, copysignf(cosThetaTi, e.wi.z));
+    q.wo = v3(e.wo.x*eta, e.wo.y*eta, copysignf(cosThetaTo, e.wo.z));
+}
+TGB_D bool bsdf_sample(const DScene &sc, const DBsdf &b, const Surface &s, Sampler &smp, Event &e) {
+    if (b.type != TGB_BSDF_SMOOTH_COAT) {
+        if (!bsdf_sample_base(sc, b, s, smp, e)) return false;
+        e.weight = e.weight*sqr(bsdf_eta(b, e));
+        return true;
+    }
+    const DBsdf &sub = sc.bsdfs[b.substrate];
+    if (e.wi.z <= 0.0f) return false;
+    bool sampleR = (e.requested & LOBE_SPEC_R) != 0, sampleT = (e.requested & sub.lobes) != 0;
+    if (!sampleR && !sampleT) return false;
+    V3 wi = e.wi;
+    float eta = 1.0f/b.ior;
+    float cosThetaTi;
+    float Fi = dielectric_reflectance(eta, wi.z, cosThetaTi);
+    float substrateWeight = b.avg_transmittance*(1.0f - Fi);
+    float specularWeight = Fi;
+    float specularProbability;
+    if (sampleR && sampleT) specularProbability = specularWeight/(specularWeight + substrateWeight);
+    else if (sampleR) specularProbability = 1.0f;
+    else specularProbability = 0.0f;
+    if (sampleR && sampler_boolean(smp, specularProbability)) {
+        e.wo = v3(-wi.x, -wi.y, wi.z);
+        e.pdf = specularProbability;
+        e.weight = v3s(Fi/specularProbability);
+        e.sampled = LOBE_SPEC_R;
+    } else {
+        e.wi = v3(wi.x*eta, wi.y*eta, cosThetaTi);
+        bool success = bsdf_sample_base(sc, sub, s, smp, e);
+        e.wi = wi;
+        if (!success) return false;
+        float cosThetaTo;
+        float Fo = dielectric_reflectance(b.ior, e.wo.z, cosThetaTo);
+        if (Fo == 1.0f) return false;
+        float cosThetaSubstrate = e.wo.z;
+        e.wo = v3(e.wo.x*b.ior, e.wo.y*b.ior, cosThetaTo);
+        e.weight = e.weight*((1.0f - Fi)*(1.0f - Fo));
+        if (max_comp(b.scaled_sigma_a) > 0.0f)
+            e.weight = e.weight*vexp(b.scaled_sigma_a*(-1.0f/cosThetaSubstrate - 1.0f/cosThetaTi));
+        e.weight = e.weight/(1.0f - specularProbability);
+        e.pdf *= 1.0f - specularProbability;
+        e.pdf *= eta*eta*cosThetaTo/cosThetaSubstrate;
+    }
+    return true;
+}
+TGB_D V3 bsdf_eval(const DScene &sc, const DBsdf &b, const Surface &s, const Event &e) {
+    if (b.type != TGB_BSDF_SMOOTH_COAT) return bsdf_eval_base(sc, b, s, e)*sqr(bsdf_eta(b, e));
+    const DBsdf &sub = sc.bsdfs[b.substrate];
+    if (e.wi.z <= 0.0f || e.wo.z <= 0.0f) return v3s(0.0f);
+    bool evalR = (e.requested & LOBE_SPEC_R) != 0, evalT = (e.requested & sub.lobes) != 0;
+    float eta = 1.0f/b.ior, Fi, Fo, cosThetaTi, cosThetaTo; Event q;
+    coat_warp(b, e, q, Fi, Fo, cosThetaTi, cosThetaTo);
+    if (evalR && check_reflection_constraint(e.wi, e.wo)) return v3s(Fi);
+    if (evalT) {
+        float laplacian = eta*eta*e.wo.z/cosThetaTo;
+        V3 substrateF = bsdf_eval_base(sc, sub, s, q);
+        if (max_comp(b.scaled_sigma_a) > 0.0f)
+            substrateF = substrateF*vexp(b.scaled_sigma_a*(-1.0f/cosThetaTo - 1.0f/cosThetaTi));
+        return substrateF*(laplacian*(1.0f - Fi)*(1.0f - Fo));
+    }
+    return v3s(0.0f);
+}
+TGB_D float bsdf_pdf(const DScene &sc, const DBsdf &b, const Surface &s, const Event &e) {
+    if (b.type != TGB_BSDF_SMOOTH_COAT) return bsdf_pdf_base(sc, b, s, e);
+    const DBsdf &sub = sc.bsdfs[b.substrate];
+    if (e.wi.z <= 0.0f || e.wo.z <= 0.0f) return 0.0f;
+    bool sampleR = (e.requested & LOBE_SPEC_R) != 0, sampleT = (e.requested & sub.lobes) != 0;
+    float eta = 1.0f/b.ior, Fi, Fo, cosThetaTi, cosThetaTo; Event q;
+    coat_warp(b, e, q, Fi, Fo, cosThetaTi, cosThetaTo);
+    if (sampleR && sampleT) {
+        float substrateWeight = b.avg_transmittance*(1.0f - Fi);
+        float specularWeight = Fi;
+        float specularProbability = specularWeight/(specularWeight + substrateWeight);
+        if (check_reflection_constraint(e.wi, e.wo)) return specularProbability;
+        return bsdf_pdf_base(sc, sub, s, q)*(1.0f - specularProbability)*eta*eta*fabsf(e.wo.z/cosThetaTo);
+    } else if (sampleT) return bsdf_pdf_base(sc, sub, s, q)*eta*eta*fabsf(e.wo.z/cosThetaTo);
+    else if (sampleR) return check_reflection_constraint(e.wi, e.wo) ? 1.0f : 0.0f;
+    return 0.0f;
+}
+
 // ---------------------------------------------------------------- lights
 struct LightSample { V3 d; float dist, pdf; };
 
@@ -622,8 +709,8 @@ TGB_D int dist1d_warp(const float *cdf, const float *pdf, int n, float &u) {    
 }
 TGB_D float bitmap_pdf_uv(const DTex &t, float u, float v) {                           // textures/BitmapTexture.cpp pdf(MAP_SPHERICAL)
     int w = t.res_u, h = t.res_v;
-    int col = min(max(int(w*u), 0), w - 1);
-    int row = min(max(int(h*(1.0f - v)), 0), h - 1);
+    int col = min(max(int(u*w), 0), w - 1);
+    int row = min(max(int((1.0f - v)*h), 0), h - 1);
     return __ldg(t.pdf + size_t(row)*w + col)*__ldg(t.marg_pdf + row)*w*h;
 }
 TGB_D void direction_to_uv(const DPrim &p, V3 wi, float &u, float &v, float *sinTheta) {    // primitives/InfiniteSphere.cpp:27-39

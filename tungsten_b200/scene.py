@@ -358,6 +358,20 @@ class FlatScene:
             if ty == "rough_plastic":
                 o.distribution = _DIST[b.get("distribution", "ggx")]
                 o.roughness_tex = self.add_texture(b.get("roughness", 0.02), base_dir)
+        elif ty == "smooth_coat":
+            o.type = abi.BSDF_SMOOTH_COAT
+            o.ior = float(f32(b.get("ior", 1.3)))
+            o.thickness = float(f32(b.get("thickness", 1.0)))
+            o.sigma_a[:] = [float(x) for x in (_vec3_field(b, "sigma_a") if "sigma_a" in b else v3(0.0))]
+            sub = b.get("substrate", {"type": "rough_conductor"})
+            if isinstance(sub, str):
+                if named is None or sub not in named:
+                    raise SceneError("unknown substrate bsdf '%s'" % sub)
+                o.substrate = named[sub]
+            else:
+                o.substrate = self.add_bsdf(sub, base_dir, named)
+            if self.bsdfs[o.substrate].type == abi.BSDF_SMOOTH_COAT:
+                raise SceneError("nested coats are outside the hot path")
         else:
             raise SceneError("bsdf type outside the hot path: %r" % ty)
         if "bump" in b:
@@ -474,7 +488,7 @@ def load_scene(path_or_dict, base_dir=None):
     fs = FlatScene(); fs.source = js
     named = {}
     for b in js.get("bsdfs", []):
-        idx = fs.add_bsdf(b, base_dir)
+        idx = fs.add_bsdf(b, base_dir, named)
         if "name" in b:
             named[b["name"]] = idx
 
@@ -483,7 +497,7 @@ def load_scene(path_or_dict, base_dir=None):
             if v not in named:
                 raise SceneError("unknown bsdf '%s'" % v)
             return named[v]
-        return fs.add_bsdf(v, base_dir)
+        return fs.add_bsdf(v, base_dir, named)
 
     default_bsdf = None
     for p in js.get("primitives", []):

@@ -205,3 +205,70 @@ def material_room(out_dir, name="materials", res=(128, 128), spp=16, max_bounces
         sc["primitives"].append({"name": "env", "type": "infinite_sphere", "emission": env, "sample": True,
                                  "transform": {"rotation": [0, 40, 0]}})
     return write_scene(out_dir, name, sc, meshes)
+
+
+# ---- HDR environment maps ----------------------------------------------------------------------
+def save_rgbe(path, img):
+    """Flat (non-RLE) Radiance .hdr writer; rows top-down ("-Y h +X w")."""
+    img = np.asarray(img, dtype=np.float64)
+    h, w, _ = img.shape
+    m = img.max(axis=2)
+    e = np.zeros((h, w), dtype=np.int32)
+    nz = m > 1e-32
+    mant, ex = np.frexp(np.where(nz, m, 1.0))
+    scale = np.where(nz, mant*256.0/np.where(nz, m, 1.0), 0.0)
+    rgbe = np.zeros((h, w, 4), dtype=np.uint8)
+    rgbe[..., :3] = np.clip(img*scale[..., None], 0, 255).astype(np.uint8)
+    rgbe[..., 3] = np.where(nz, ex + 128, 0).astype(np.uint8)
+    with open(path, "wb") as f:
+        f.write(b"#?RADIANCE\nFORMAT=32-bit_rle_rgbe\n\n-Y %d +X %d\n" % (h, w))
+        f.write(rgbe.tobytes())
+
+
+def sky_envmap(w=128, h=64, sun=(0.62, 0.35), sun_power=60.0):
+    """Procedural lat-long sky: gradient + a small bright sun + a darker ground, strong enough contrast that
+    the importance map (BitmapTexture::makeSamplable) matters."""
+    v = (np.arange(h) + 0.5)/h
+    u = (np.arange(w) + 0.5)/w
+    U, V = np.meshgrid(u, v)
+    up = np.cos(V*np.pi)                     # +1 at the top row
+    sky = np.stack([0.25 + 0.35*np.clip(up, 0, 1), 0.35 + 0.45*np.clip(up, 0, 1), 0.6 + 0.5*np.clip(up, 0, 1)], axis=2)
+    ground = np.stack([0.12 + 0*up, 0.10 + 0*up, 0.08 + 0*up], axis=2)
+    img = np.where((up > 0)[..., None], sky, ground)
+    d2 = ((U - sun[0])*2.0)**2 + (V - sun[1])**2
+    img = img + sun_power*np.exp(-d2/0.0012)[..., None]*np.array([1.0, 0.9, 0.7])
+    return img.astype(np.float32)
+
+
+def materialtest_standin(out_dir, name="coat_env", res=(128, 128), spp=16, max_bounces=64, subdiv=3, env_res=(128, 64)):
+    """Stand-in for BASELINE.json config C0 (data/materialtest/materialtest.json): a smooth_coat(ior 1.7, absorbing)
+    over a Beckmann rough_conductor(Cu) blob, a Lambert stand, a checker-textured Lambert floor quad and an HDR
+    environment map lit through importance sampling -- the same lobe / emitter / texture mix, with procedural assets."""
+    v, t = icosphere(subdiv, 1.0, displace=0.12, lobes=0.2)
+    sv, st = icosphere(max(subdiv - 1, 0), 1.0)
+    os.makedirs(out_dir, exist_ok=True)
+    save_rgbe(os.path.join(out_dir, name + "_env.hdr"), sky_envmap(*env_res))
+    bsdfs = [
+        {"name": "rough_metal", "albedo": 1, "type": "rough_conductor", "material": "Cu", "distribution": "beckmann", "roughness": 0.1},
+        {"name": "Material", "albedo": 1, "type": "smooth_coat", "ior": 1.7, "thickness": 5, "sigma_a": [0.1, 0.2, 0.5], "substrate": "rough_metal"},
+        {"name": "Stand", "albedo": 0.2, "type": "lambert"},
+        {"name": "Floor", "type": "lambert", "albedo": {"type": "checker", "on_color": [0.725, 0.71, 0.68],
+                                                        "off_color": [0.325, 0.31, 0.25], "res_u": 20, "res_v": 20}},
+    ]
+    prims = [
+        {"name": "Floor", "type": "quad", "bsdf": "Floor", "transform": {"position": [-0.7, 0, -0.7], "scale": 5.4, "rotation": [0, 46.15, 180]}},
+        {"name": "Envmap", "type": "infinite_sphere", "emission": name + "_env.hdr", "sample": True,
+         "transform": {"rotation": [0, -67.26, 0]}},
+        {"name": "Ball", "type": "mesh", "file": name + "_ball.wo3", "smooth": True, "bsdf": "Material",
+         "transform": {"position": [0.15, 0.78, 0.16], "scale": 0.45}},
+        {"name": "Stand", "type": "mesh", "file": name + "_stand.wo3", "smooth": True, "bsdf": "Stand",
+         "transform": {"position": [0.12, 0.2, 0.13], "scale": [0.3, 0.2, 0.3]}},
+    ]
+    sc = {"media": [], "bsdfs": bsdfs, "primitives": prims,
+          "camera": {"tonemap": "filmic", "resolution": list(res), "reconstruction_filter": "tent",
+                     "transform": {"position": [3.04, 3.17, 3.2], "look_at": [0.12, 0.47, 0.16], "up": [0, 1, 0]},
+                     "type": "pinhole", "fov": 35},
+          "integrator": {"type": "path_tracer", "min_bounces": 0, "max_bounces": max_bounces, "enable_light_sampling": True,
+                         "enable_consistency_checks": False, "enable_two_sided_shading": True},
+          "renderer": _renderer(spp)}
+    return write_scene(out_dir, name, sc, {name + "_ball.wo3": (v, t), name + "_stand.wo3": (sv, st)})
