@@ -1,0 +1,366 @@
+#include "B200PathTraceIntegrator.hpp"
+
+#include "tgb200.h"
+
+#include "renderer/TraceableScene.hpp"
+#include "cameras/PinholeCamera.hpp"
+#include "primitives/InfiniteSphere.hpp"
+#include "primitives/TriangleMesh.hpp"
+#include "primitives/Quad.hpp"
+#include "primitives/Cube.hpp"
+#include "bsdfs/RoughDielectricBsdf.hpp"
+#include "bsdfs/RoughConductorBsdf.hpp"
+#include "bsdfs/RoughPlasticBsdf.hpp"
+#include "bsdfs/SmoothCoatBsdf.hpp"
+#include "bsdfs/PlasticBsdf.hpp"
+#include "bsdfs/LambertBsdf.hpp"
+#include "bsdfs/NullBsdf.hpp"
+#include "textures/ConstantTexture.hpp"
+#include "textures/CheckerTexture.hpp"
+#include "textures/BitmapTexture.hpp"
+#include "io/JsonObject.hpp"
+#include "Debug.hpp"
+
+#include <cstring>
+#include <map>
+#include <sstream>
+#include <vector>
+
+namespace Tungsten {
+
+namespace {
+
+// Owns every buffer a tgb_scene_desc points to for the duration of tgb200_create().
+struct Flattener
+{
+    std::vector<tgb_texture> textures;
+    std::vector<tgb_bsdf> bsdfs;
+    std::vector<tgb_primitive> prims;
+    std::vector<uint32_t> slots;
+    std::vector<std::vector<float>> texelStore;
+    std::vector<std::vector<tgb_vertex>> vertStore;
+    std::vector<std::vector<tgb_triangle>> triStore;
+    std::map<const Bsdf *, int> bsdfIds;
+    std::map<const Texture *, int> texIds;
+
+    static void put(float *dst, const Vec3f &v) { dst[0] = v.x(); dst[1] = v.y(); dst[2] = v.z(); }
+
+    int texture(const Texture *t)
+    {
+        auto iter = texIds.find(t);
+        if (iter != texIds.end())
+            return iter->second;
+        tgb_texture o;
+        std::memset(&o, 0, sizeof(o));
+        if (const CheckerTexture *c = dynamic_cast<const CheckerTexture *>(t)) {
+            o.type = TGB_TEX_CHECKER;
+            put(o.value, c->onColor());
+            put(o.value2, c->offColor());
+            o.res_u = c->resU();
+            o.res_v = c->resV();
+        } else if (const BitmapTexture *b = dynamic_cast<const BitmapTexture *>(t)) {
+            // texel centres through the public operator[]: (x+0.5)/w, 1-(y+0.5)/h reproduce the stored texels exactly
+            o.type = TGB_TEX_BITMAP;
+            o.res_u = b->w();
+            o.res_v = b->h();
+            o.flags = (b->linear() ? 1u : 0u) | (b->clamp() ? 2u : 0u);
+            texelStore.emplace_back(size_t(b->w())*b->h()*3);
+            std::vector<float> &tx = texelStore.back();
+            for (int y = 0; y < b->h(); ++y) {
+                for (int x = 0; x < b->w(); ++x) {
+                    Vec3f c = (*b)[Vec2f((x + 0.5f)/b->w(), 1.0f - (y + 0.5f)/b->h())];
+                    put(&tx[3*(size_t(y)*b->w() + x)], c);
+                }
+            }
+            o.texels = tx.data();
+        } else if (t->isConstant()) {
+            o.type = TGB_TEX_CONSTANT;
+            put(o.value, t->average());
+        } else {
+            FAIL("b200_path_tracer: texture type outside the hot path");
+        }
+        textures.push_back(o);
+        texIds[t] = int(textures.size()) - 1;
+        return texIds[t];
+    }
+
+    static uint32_t distribution(const char *name)
+    {
+        if (std::strcmp(name, "beckmann") == 0) return TGB_DIST_BECKMANN;
+        if (std::strcmp(name, "phong") == 0) return TGB_DIST_PHONG;
+        return TGB_DIST_GGX;
+    }
+
+    int bsdf(const Bsdf *b)
+    {
+        auto iter = bsdfIds.find(b);
+        if (iter != bsdfIds.end())
+            return iter->second;
+        if (b->bump() && !b->bump()->isConstant())
+            FAIL("b200_path_tracer: bump maps are outside the hot path");
+        tgb_bsdf o;
+        std::memset(&o, 0, sizeof(o));
+        o.albedo_tex = texture(b->albedo().get());
+        o.roughness_tex = -1;
+        o.substrate = -1;
+        o.ior = 1.5f;
+        o.thickness = 1.0f;
+        o.enable_refraction = 1;
+        if (dynamic_cast<const NullBsdf *>(b)) {
+            o.type = TGB_BSDF_NULL;
+        } else if (dynamic_cast<const LambertBsdf *>(b)) {
+            o.type = TGB_BSDF_LAMBERT;
+        } else if (const RoughConductorBsdf *c = dynamic_cast<const RoughConductorBsdf *>(b)) {
+            o.type = TGB_BSDF_ROUGH_CONDUCTOR;
+            o.distribution = distribution(c->distributionName());
+            o.roughness_tex = texture(c->roughness().get());
+            put(o.eta, c->eta());
+            put(o.k, c->k());
+        } else if (const RoughDielectricBsdf *d = dynamic_cast<const RoughDielectricBsdf *>(b)) {
+            o.type = TGB_BSDF_ROUGH_DIELECTRIC;
+            o.distribution = distribution(d->distributionName());
+            o.roughness_tex = texture(d->roughness().get());
+            o.ior = d->ior();
+            o.enable_refraction = d->enableTransmission() ? 1 : 0;
+        } else if (const RoughPlasticBsdf *rp = dynamic_cast<const RoughPlasticBsdf *>(b)) {
+            o.type = TGB_BSDF_ROUGH_PLASTIC;
+            o.distribution = distribution(rp->distributionName());
+            o.roughness_tex = texture(rp->roughness().get());
+            o.ior = rp->ior();
+            o.thickness = rp->thickness();
+            put(o.sigma_a, rp->sigmaA());
+        } else if (const PlasticBsdf *p = dynamic_cast<const PlasticBsdf *>(b)) {
+            o.type = TGB_BSDF_PLASTIC;
+            o.ior = p->ior();
+            o.thickness = p->thickness();
+            put(o.sigma_a, p->sigmaA());
+        } else if (const SmoothCoatBsdf *sc = dynamic_cast<const SmoothCoatBsdf *>(b)) {
+            o.type = TGB_BSDF_SMOOTH_COAT;
+            o.ior = sc->ior();
+            o.thickness = sc->thickness();
+            put(o.sigma_a, sc->sigmaA());
+            o.substrate = bsdf(sc->substrate().get());
+        } else {
+            FAIL("b200_path_tracer: BSDF type outside the hot path");
+        }
+        bsdfs.push_back(o);
+        bsdfIds[b] = int(bsdfs.size()) - 1;
+        return bsdfIds[b];
+    }
+
+    void primitive(Primitive &p)
+    {
+        tgb_primitive o;
+        std::memset(&o, 0, sizeof(o));
+        o.emission_tex = p.emission() ? texture(p.emission().get()) : -1;
+        o.bsdf_first = uint32_t(slots.size());
+        o.bsdf_count = uint32_t(p.numBsdfs());
+        for (int i = 0; i < p.numBsdfs(); ++i)
+            slots.push_back(uint32_t(bsdf(p.bsdf(i).get())));
+        const Mat4f &tform = p.transform();
+        if (TriangleMesh *m = dynamic_cast<TriangleMesh *>(&p)) {
+            // TriangleMesh::prepareForRender (TriangleMesh.cpp:539-552) with the reference's own Mat4f arithmetic
+            o.type = TGB_PRIM_MESH;
+            o.smooth = m->smoothed() ? 1 : 0;
+            Mat4f normalTform(tform.toNormalMatrix());
+            vertStore.emplace_back(m->verts().size());
+            triStore.emplace_back(m->tris().size());
+            std::vector<tgb_vertex> &vs = vertStore.back();
+            std::vector<tgb_triangle> &ts = triStore.back();
+            for (size_t i = 0; i < vs.size(); ++i) {
+                const Vertex &v = m->verts()[i];
+                put(vs[i].pos, tform*v.pos());
+                put(vs[i].normal, normalTform.transformVector(v.normal()));
+                vs[i].uv[0] = v.uv().x();
+                vs[i].uv[1] = v.uv().y();
+            }
+            for (size_t i = 0; i < ts.size(); ++i) {
+                const TriangleI &t = m->tris()[i];
+                ts[i].v0 = t.v0; ts[i].v1 = t.v1; ts[i].v2 = t.v2; ts[i].material = t.material;
+            }
+            o.verts = vs.data(); o.n_verts = uint32_t(vs.size());
+            o.tris = ts.data(); o.n_tris = uint32_t(ts.size());
+        } else if (dynamic_cast<Quad *>(&p)) {
+            // Quad::prepareForRender (Quad.cpp:298-305)
+            o.type = TGB_PRIM_QUAD;
+            Vec3f base = tform*Vec3f(0.0f);
+            Vec3f edge0 = tform.transformVector(Vec3f(1.0f, 0.0f, 0.0f));
+            Vec3f edge1 = tform.transformVector(Vec3f(0.0f, 0.0f, 1.0f));
+            base -= edge0*0.5f;
+            base -= edge1*0.5f;
+            put(o.base, base); put(o.edge0, edge0); put(o.edge1, edge1);
+        } else if (dynamic_cast<Cube *>(&p)) {
+            // Cube::prepareForRender (Cube.cpp:351-355)
+            o.type = TGB_PRIM_CUBE;
+            put(o.pos, tform*Vec3f(0.0f));
+            put(o.scale, tform.extractScale()*Vec3f(0.5f));
+            Mat4f rot = tform.extractRotation();
+            for (int r = 0; r < 3; ++r)
+                for (int c = 0; c < 3; ++c)
+                    o.rot[r*3 + c] = rot[r*4 + c];
+        } else if (dynamic_cast<InfiniteSphere *>(&p)) {
+            o.type = TGB_PRIM_INFINITE_SPHERE;
+            Mat4f rot = tform.extractRotation();
+            for (int r = 0; r < 3; ++r)
+                for (int c = 0; c < 3; ++c)
+                    o.rot[r*3 + c] = rot[r*4 + c];
+            o.do_sample = p.isSamplable() ? 1 : 0;
+            o.bsdf_count = 0;
+        } else {
+            FAIL("b200_path_tracer: primitive type outside the hot path");
+        }
+        prims.push_back(o);
+    }
+};
+
+}
+
+B200PathTraceIntegrator::B200PathTraceIntegrator()
+: Integrator(),
+  _ctx(nullptr),
+  _seed(0xBA5EBA11)
+{
+}
+
+B200PathTraceIntegrator::~B200PathTraceIntegrator()
+{
+    if (_ctx)
+        tgb200_destroy(_ctx);
+}
+
+void B200PathTraceIntegrator::fromJson(JsonPtr value, const Scene &/*scene*/)
+{
+    _settings.fromJson(value);
+}
+
+rapidjson::Value B200PathTraceIntegrator::toJson(Allocator &allocator) const
+{
+    rapidjson::Value v = _settings.toJson(allocator);
+    v["type"].SetString("b200_path_tracer");
+    return v;
+}
+
+void B200PathTraceIntegrator::saveState(OutputStreamHandle &/*out*/) {}
+void B200PathTraceIntegrator::loadState(InputStreamHandle &/*in*/) {}
+
+void B200PathTraceIntegrator::prepareForRender(TraceableScene &scene, uint32 seed)
+{
+    _currentSpp = 0;
+    _seed = seed;
+    _scene = &scene;
+    advanceSpp();
+    scene.cam().requestColorBuffer();
+
+    if (scene.rendererSettings().useAdaptiveSampling() || !scene.rendererSettings().useSobol())
+        FAIL("b200_path_tracer needs renderer.adaptive_sampling=false and renderer.stratified_sampler=true");
+    if (!scene.media().empty() || scene.cam().medium())
+        FAIL("b200_path_tracer: participating media are outside the hot path");
+    PinholeCamera *cam = dynamic_cast<PinholeCamera *>(&scene.cam());
+    if (!cam)
+        FAIL("b200_path_tracer: only the pinhole camera is on the hot path");
+
+    Flattener f;
+    for (const std::shared_ptr<Primitive> &p : scene.primitives())
+        f.primitive(*p);
+
+    tgb_scene_desc desc;
+    std::memset(&desc, 0, sizeof(desc));
+    desc.abi_version = TGB200_ABI_VERSION;
+    Flattener::put(desc.camera.pos, cam->pos());
+    const Mat4f &t = cam->transform();                // already has setRight(-right) applied (Camera.cpp:62)
+    for (int r = 0; r < 3; ++r)
+        for (int c = 0; c < 3; ++c)
+            desc.camera.xform[r*3 + c] = t[r*4 + c];
+    desc.camera.fov_deg = cam->fovDeg();
+    desc.camera.res_x = cam->resolution().x();
+    desc.camera.res_y = cam->resolution().y();
+    const std::string filter = cam->reconstructionFilter().name();
+    const char *names[] = {"dirac", "box", "tent", "gaussian", "mitchell_netravali", "catmull_rom", "lanczos"};
+    for (uint32_t i = 0; i < 7; ++i)
+        if (filter == names[i])
+            desc.camera.filter = i;
+    desc.settings.min_bounces = _settings.minBounces;
+    desc.settings.max_bounces = _settings.maxBounces;
+    desc.settings.enable_light_sampling = _settings.enableLightSampling;
+    desc.settings.enable_two_sided_shading = _settings.enableTwoSidedShading;
+    desc.settings.enable_consistency_checks = _settings.enableConsistencyChecks;
+    desc.settings.use_sobol = 1;
+    desc.settings.supplemental_mode = 0;
+    desc.settings.device = -1;
+    desc.primitives = f.prims.data(); desc.n_primitives = uint32_t(f.prims.size());
+    desc.bsdfs = f.bsdfs.data(); desc.n_bsdfs = uint32_t(f.bsdfs.size());
+    desc.bsdf_slots = f.slots.data(); desc.n_bsdf_slots = uint32_t(f.slots.size());
+    desc.textures = f.textures.data(); desc.n_textures = uint32_t(f.textures.size());
+
+    if (tgb200_create(&desc, &_ctx) != TGB_OK)
+        FAIL("b200_path_tracer: %s", tgb200_last_error(nullptr));
+    tgb200_clear_framebuffer(_ctx);
+}
+
+void B200PathTraceIntegrator::teardownAfterRender()
+{
+    waitForCompletion();
+    if (_ctx)
+        tgb200_destroy(_ctx);
+    _ctx = nullptr;
+}
+
+// Camera::colorBuffer() <- GPU running mean + counts, through OutputBuffer's public deserialize()
+void B200PathTraceIntegrator::uploadFramebuffer()
+{
+    Vec2u res = _scene->cam().resolution();
+    size_t n = size_t(res.x())*res.y();
+    std::string blob(n*(sizeof(Vec3f) + sizeof(uint32)), '\0');
+    float *rgb = reinterpret_cast<float *>(&blob[0]);
+    uint32 *count = reinterpret_cast<uint32 *>(&blob[n*sizeof(Vec3f)]);
+    if (tgb200_read_framebuffer(_ctx, rgb, count) != TGB_OK) {
+        _error = tgb200_last_error(_ctx);
+        return;
+    }
+    InputStreamHandle in(new std::istringstream(blob, std::ios_base::in | std::ios_base::binary));
+    _scene->cam().colorBuffer()->deserialize(in);
+}
+
+void B200PathTraceIntegrator::startRender(std::function<void()> completionCallback)
+{
+    if (done()) {
+        _currentSpp = _nextSpp;
+        advanceSpp();
+        completionCallback();
+        return;
+    }
+    uint32 begin = _currentSpp, count = _nextSpp - _currentSpp;
+    _worker.reset(new std::thread([this, begin, count, completionCallback]() {
+        int rc = tgb200_render_resident(_ctx, nullptr, 0, _seed, begin, count);
+        if (rc == TGB_OK) {
+            uploadFramebuffer();
+            _currentSpp = _nextSpp;
+            advanceSpp();
+        } else if (rc != TGB_ERR_ABORTED) {
+            _error = tgb200_last_error(_ctx);
+        }
+        completionCallback();
+    }));
+}
+
+void B200PathTraceIntegrator::waitForCompletion()
+{
+    if (_worker) {
+        _worker->join();
+        _worker.reset();
+    }
+    if (!_error.empty()) {
+        std::string e;
+        e.swap(_error);
+        FAIL("b200_path_tracer: %s", e);
+    }
+}
+
+void B200PathTraceIntegrator::abortRender()
+{
+    if (_worker && _ctx)
+        tgb200_abort(_ctx);
+    waitForCompletion();
+}
+
+}

@@ -1,0 +1,54 @@
+// In-tree adapter: a Tungsten `Integrator` whose render loop runs on a B200 through libtgb200.so.
+//
+// Drop-in for `PathTraceIntegrator` (reference: src/core/integrators/path_tracer/PathTraceIntegrator.{hpp,cpp});
+// registered in IntegratorFactory as "b200_path_tracer" (INTEGRATION.md).  It reads the scene ONLY through
+// TraceableScene / Primitive / Bsdf / Texture public accessors, hands the prepared world-space geometry to
+// tgb200_create(), renders spp steps with tgb200_render_resident() and loads the resulting running mean into
+// the camera's OutputBuffer through its public deserialize() (the same path resume files use).
+#ifndef B200PATHTRACEINTEGRATOR_HPP_
+#define B200PATHTRACEINTEGRATOR_HPP_
+
+#include "integrators/Integrator.hpp"
+#include "integrators/path_tracer/PathTracerSettings.hpp"
+
+#include <atomic>
+#include <memory>
+#include <string>
+#include <thread>
+
+struct tgb_ctx;
+
+namespace Tungsten {
+
+class B200PathTraceIntegrator : public Integrator
+{
+    PathTracerSettings _settings;
+    tgb_ctx *_ctx;
+    uint32 _seed;
+    std::unique_ptr<std::thread> _worker;
+    std::string _error;
+
+    void uploadFramebuffer();
+
+protected:
+    virtual void saveState(OutputStreamHandle &out) override;
+    virtual void loadState(InputStreamHandle &in) override;
+
+public:
+    B200PathTraceIntegrator();
+    virtual ~B200PathTraceIntegrator();
+
+    virtual void fromJson(JsonPtr value, const Scene &scene) override;
+    virtual rapidjson::Value toJson(Allocator &allocator) const override;
+
+    virtual void prepareForRender(TraceableScene &scene, uint32 seed) override;
+    virtual void teardownAfterRender() override;
+
+    virtual void startRender(std::function<void()> completionCallback) override;
+    virtual void waitForCompletion() override;
+    virtual void abortRender() override;
+};
+
+}
+
+#endif /* B200PATHTRACEINTEGRATOR_HPP_ */

@@ -1,0 +1,40 @@
+"""The literal drop-in: the reference renderer's own binary with `B200PathTraceIntegrator` linked in
+(integration/_build/tungsten_b200, built by `make -C oracle/ref dropin` where /root/reference is mounted) renders
+scenes whose integrator type is "b200_path_tracer" on the GPU; its PFM output is compared with the framebuffers the
+reference's CPU integrator produced for the same scenes (tests/golden/*/ref_pathseed.pfm)."""
+import json
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from tungsten_b200 import scene
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+EXE = os.path.join(ROOT, "integration", "_build", "tungsten_b200")
+G = os.path.join(ROOT, "tests", "golden")
+
+
+@pytest.mark.skipif(not os.path.exists(EXE), reason="drop-in binary not built (needs /root/reference at build time)")
+@pytest.mark.parametrize("name", ["cornell", "materials", "coat_env"])
+def test_reference_binary_with_b200_integrator(name, tmp_path):
+    src = os.path.join(G, name)
+    for f in os.listdir(src):
+        if not f.endswith(".pfm"):
+            os.symlink(os.path.join(src, f), tmp_path/f)
+    js = json.load(open(os.path.join(src, "scene.json")))
+    js["integrator"]["type"] = "b200_path_tracer"
+    js["renderer"]["spp_step"] = 3                     # exercises spp stepping: 3 + 3 + 2
+    json.dump(js, open(tmp_path/"b200.json", "w"))
+    out = subprocess.run([EXE, "-t", "2", "-d", str(tmp_path/"out"), str(tmp_path/"b200.json")], stdout=subprocess.PIPE,
+                         stderr=subprocess.STDOUT, text=True)
+    assert out.returncode == 0, out.stdout
+    assert "Completed 8/8 spp" in out.stdout, out.stdout
+    got = scene.load_pfm(str(tmp_path/"out"/"out.pfm"))
+    want = scene.load_pfm(os.path.join(src, "ref_pathseed.pfm"))
+    d = np.abs(got - want).max(axis=2)
+    close = float((d <= 1e-5*(1.0 + np.abs(want).max(axis=2))).mean())
+    print(name, "exact %.4f close %.4f" % (float((d == 0).mean()), close))
+    assert close >= 0.985
