@@ -1,11 +1,10 @@
-# One GPU session: parity tests, smoke, bench, ncu launch list + full capture of the traversal kernel.
+# One GPU session: parity tests, smoke, bench (both arms), ncu launch list + full capture of the traversal kernel.
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv,noheader
-nproc; grep -m1 "model name" /proc/cpuinfo
-python -m pytest tests -m gpu -x -q 2>&1 | tail -5
-python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -3
-python bench.py --steps 8 --warmup 3 > gpurun_out/bench.json 2> gpurun_out/bench.err; tail -c 3000 gpurun_out/bench.json; tail -5 gpurun_out/bench.err
-python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_ref.json 2>> gpurun_out/bench.err; cat gpurun_out/bench_ref.json
-ncu --metrics gpu__time_duration.sum --clock-control none -c 300 --csv --log-file gpurun_out/launches.csv python bench.py --steps 1 --warmup 1 --spp-per-step 4 --no-cpu-baseline > gpurun_out/ncu_bench.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:k_trace -s 4 -c 2 -o gpurun_out/prof_trace python bench.py --steps 1 --warmup 1 --spp-per-step 2 --no-cpu-baseline > gpurun_out/ncu_full.log 2>&1
-ls -la gpurun_out
+python -m pytest tests -m gpu -x -q 2>&1 | tail -6
+python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2
+python bench.py --impl reference --steps 2 --warmup 1 --ref-spp 16 > gpurun_out/bench_ref.json 2>> gpurun_out/bench.err; cat gpurun_out/bench_ref.json | cut -c1-300
+python bench.py > gpurun_out/bench.json 2> gpurun_out/bench.err; cat gpurun_out/bench.json; tail -5 gpurun_out/bench.err
+ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file gpurun_out/launches.csv python bench.py --steps 1 --warmup 1 --spp-per-step 8 --no-cpu-baseline > gpurun_out/ncu_bench.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:k_trace -s 3 -c 2 -o gpurun_out/prof_trace python bench.py --steps 1 --warmup 1 --spp-per-step 8 --no-cpu-baseline > gpurun_out/ncu_full.log 2>&1
+ls -la gpurun_out | tail -8
