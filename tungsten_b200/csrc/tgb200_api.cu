@@ -785,7 +785,12 @@ int tgb200_scene_info(tgb_ctx *c, uint32_t *n_tris, uint32_t *n_nodes, uint32_t 
     return TGB_OK;
 }
 
-static int tile_pixels(tgb_ctx *c, const tgb_tile *tiles, uint32_t n_tiles, uint32_t **dev, uint32_t *n_out) {
+static int tile_pixels(tgb_ctx *c, const tgb_tile *tiles, uint32_t n_tiles, uint32_t **dev, uint32_t *n_out, bool *owned) {
+    *owned = true;
+    if (c->tiles_cached.size() == n_tiles && n_tiles && std::memcmp(c->tiles_cached.data(), tiles, n_tiles*sizeof(tgb_tile)) == 0) {
+        *dev = c->pix_id; *n_out = c->n_pix; *owned = false;      // same tile list as the last render: reuse its pixel list
+        return TGB_OK;
+    }
     std::vector<uint32_t> pid;
     for (uint32_t t = 0; t < n_tiles; ++t) {
         const tgb_tile &tl = tiles[t];
@@ -804,13 +809,13 @@ static int tile_pixels(tgb_ctx *c, const tgb_tile *tiles, uint32_t n_tiles, uint
 int tgb200_pack_tiles(tgb_ctx *c, const tgb_tile *tiles, uint32_t n_tiles, void *rgb_out_dev) {
     if (!c || !tiles || !rgb_out_dev) return TGB_ERR_INVALID;
     CU(cudaSetDevice(c->device));
-    uint32_t *pid = nullptr, n = 0;
-    int rc = tile_pixels(c, tiles, n_tiles, &pid, &n);
+    uint32_t *pid = nullptr, n = 0; bool owned = true;
+    int rc = tile_pixels(c, tiles, n_tiles, &pid, &n, &owned);
     if (rc || !n) return rc;
     k_pack_tiles<<<blocks(n, 256), 256, 0, c->stream>>>(pid, n, c->fb, static_cast<float *>(rgb_out_dev));
     c->stats.kernel_launches++;
     cudaError_t e = cudaStreamSynchronize(c->stream);
-    cudaFree(pid);
+    if (owned) cudaFree(pid);
     if (e != cudaSuccess) return fail(c, TGB_ERR_CUDA, "pack_tiles failed: %s", cudaGetErrorString(e));
     return TGB_OK;
 }
@@ -818,13 +823,13 @@ int tgb200_pack_tiles(tgb_ctx *c, const tgb_tile *tiles, uint32_t n_tiles, void 
 int tgb200_unpack_tiles(tgb_ctx *c, const tgb_tile *tiles, uint32_t n_tiles, const void *rgb_in_dev, uint32_t sample_count) {
     if (!c || !tiles || !rgb_in_dev) return TGB_ERR_INVALID;
     CU(cudaSetDevice(c->device));
-    uint32_t *pid = nullptr, n = 0;
-    int rc = tile_pixels(c, tiles, n_tiles, &pid, &n);
+    uint32_t *pid = nullptr, n = 0; bool owned = true;
+    int rc = tile_pixels(c, tiles, n_tiles, &pid, &n, &owned);
     if (rc || !n) return rc;
     k_unpack_tiles<<<blocks(n, 256), 256, 0, c->stream>>>(pid, n, static_cast<const float *>(rgb_in_dev), c->fb, c->fb_count, sample_count);
     c->stats.kernel_launches++;
     cudaError_t e = cudaStreamSynchronize(c->stream);
-    cudaFree(pid);
+    if (owned) cudaFree(pid);
     if (e != cudaSuccess) return fail(c, TGB_ERR_CUDA, "unpack_tiles failed: %s", cudaGetErrorString(e));
     return TGB_OK;
 }
