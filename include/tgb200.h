@@ -205,6 +205,9 @@ int  tgb200_set_profiling(tgb_ctx *ctx, int enable);
 int  tgb200_scene_info(tgb_ctx *ctx, uint32_t *n_tris, uint32_t *n_nodes, uint32_t *bvh_depth,
                        uint64_t *geom_bytes, uint32_t *capacity);
 int  tgb200_reset_stats(tgb_ctx *ctx);
+/* Host-only self-check of the BVH builder (no GPU): n triangles, 9 floats each (v0 v1 v2).  Returns TGB_OK when every
+ * triangle sits in exactly one leaf and inside every box of its root-to-leaf chain.                    */
+int  tgb200_bvh_selftest(const float *tri_verts, uint32_t n, uint32_t *n_nodes, uint32_t *depth, uint32_t *max_leaf);
 int  tgb200_abort(tgb_ctx *ctx);
 void tgb200_destroy(tgb_ctx *ctx);
 /* Last error text of the context; with ctx == NULL the text of the last failed tgb200_create.       */

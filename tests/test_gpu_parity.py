@@ -85,6 +85,13 @@ def test_golden_scenes_against_reference_fixtures():
         assert exact >= exact_min and close >= 0.985
 
 
+def test_instanced_forest(scratch):
+    """C3 stand-in: rigid instances (quaternion + translation, Instance.cpp:290-334) flattened into world space."""
+    fs = scene.load_scene(synth.instanced_forest(scratch, res=(96, 96), spp=8, n_instances=30))
+    assert fs.n_triangles == 30*(320 + 80)
+    _compare(fs, 8, frac_ok=0.985, same_ray_count=False)
+
+
 def test_incremental_spp_matches_one_shot(scratch):
     fs = scene.load_scene(synth.cornell_box(res=(64, 64), spp=8))
     ctx = lib.Context(fs)

@@ -140,3 +140,52 @@ def test_tile_sharding_partitions_the_image():
     assert (seen == 1).all()
     assert tiles[6].w == 4 and tiles[21].h == 2
     assert len({t.sampler_seed for t in tiles}) == len(tiles)
+
+
+def test_quaternion_helpers_match_rotation_matrices():
+    """QuaternionF::fromMatrix / operator* restated in fp32 (math/Quaternion.hpp:68-88,111-146)."""
+    rng = np.random.RandomState(3)
+    for rot in ([0, 0, 0], [10, 200, -35], [90, 0, 0], [0, 180, 0], [179, 179, 179]):
+        m = scene.parse_transform({"rotation": rot})[:3, :3]
+        q = scene.quat_from_matrix(m)
+        assert abs(float(np.dot(q, q)) - 1.0) < 1e-5
+        p = rng.normal(size=(7, 3)).astype(np.float32)
+        assert np.allclose(scene.quat_rotate(q, p), p @ m.T, atol=2e-6)
+    a = scene.quat_from_matrix(scene.parse_transform({"rotation": [0, 30, 0]})[:3, :3])
+    b = scene.quat_from_matrix(scene.parse_transform({"rotation": [0, 45, 0]})[:3, :3])
+    ab = scene.quat_from_matrix(scene.parse_transform({"rotation": [0, 75, 0]})[:3, :3])
+    assert np.allclose(scene.quat_mul(a, b), ab, atol=1e-6) or np.allclose(scene.quat_mul(a, b), -ab, atol=1e-6)
+
+
+def test_instances_flatten_to_world_space(tmp_path):
+    p = synth.instanced_forest(str(tmp_path), n_instances=5, tree_subdiv=1, res=(8, 8), spp=1)
+    fs = scene.load_scene(p)
+    mesh = [q for q in fs.primitives if q.type == abi.PRIM_MESH][0]
+    assert mesh.n_tris == 5*(80 + 20) and mesh.bsdf_count == 2
+    pos = np.ctypeslib.as_array(mesh.verts, (mesh.n_verts,))["pos"]
+    assert pos[:, 1].min() > -0.2 and pos[:, 1].max() < 2.5          # trees stand on the ground
+    nrm = np.ctypeslib.as_array(mesh.verts, (mesh.n_verts,))["normal"]
+    assert np.isfinite(nrm).all()
+
+
+@pytest.mark.parametrize("n", [0, 1, 3, 4, 5, 64, 1280, 20480])
+def test_bvh_builder_selftest(n):
+    """bvh_build.cpp (host C++): every triangle in exactly one leaf, boxes nest, leaves <= 4 triangles."""
+    import ctypes as C
+    L = lib.load()
+    L.tgb200_bvh_selftest.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
+    if n >= 1280:
+        v, t = synth.icosphere(3 if n == 1280 else 5, displace=0.2)
+        tri = np.ascontiguousarray(np.stack([v["pos"][t["v0"]], v["pos"][t["v1"]], v["pos"][t["v2"]]], axis=1), dtype=np.float32)
+    else:
+        rng = np.random.RandomState(n)
+        c = rng.uniform(-1, 1, (n, 1, 3)); tri = (c + rng.normal(scale=0.05, size=(n, 3, 3))).astype(np.float32)
+        if n >= 4:
+            tri[1] = tri[0]                      # duplicates: coincident centroids must still split
+            tri[2] = tri[0]
+    assert len(tri) == n
+    nodes, depth, leaf = C.c_uint32(), C.c_uint32(), C.c_uint32()
+    rc = L.tgb200_bvh_selftest(tri.ctypes.data if n else None, n, C.byref(nodes), C.byref(depth), C.byref(leaf))
+    assert rc == 0
+    if n:
+        assert leaf.value <= 4 and nodes.value >= 1 and depth.value <= 40

@@ -101,8 +101,8 @@ inline float pad_up(float v) { return std::nextafter(std::nextafter(v, std::nume
 
 }  // namespace
 
-void build_bvh2(const BuildTri *tris, uint32_t n, Bvh2 &out, int threads, float abs_pad) {
-    out.nodes.clear(); out.order.clear(); out.root_link = 0; out.max_depth = 0; out.sah_cost = 0.0;
+void build_bvh4(const BuildTri *tris, uint32_t n, Bvh4 &out, int threads, float abs_pad) {
+    out.nodes.clear(); out.order.clear(); out.max_depth = 0; out.sah_cost = 0.0;
     for (int a = 0; a < 3; ++a) { out.lo[a] = std::numeric_limits<float>::infinity(); out.hi[a] = -out.lo[a]; }
     if (n == 0) return;
     std::vector<Box> tb(n); std::vector<float> cent(3*size_t(n));
@@ -119,55 +119,63 @@ void build_bvh2(const BuildTri *tris, uint32_t n, Bvh2 &out, int threads, float 
     bl.free_threads = std::max(0, threads - 1);
     uint32_t root = bl.alloc();
     bl.build(root, 0, n, 0);
-
     for (int a = 0; a < 3; ++a) { out.lo[a] = bl.nodes[root].box.lo[a]; out.hi[a] = bl.nodes[root].box.hi[a]; }
 
-    // flatten: every inner Tmp node becomes one Node2 carrying its two children's boxes
     auto leaf_link = [](const Tmp &t) { return ~int32_t((t.first << 3) | (t.count - 1)); };
-    // leaves may hold more than 8 only if all centroids coincide and SAH refused: force-split guard
-    struct Item { uint32_t tmp; int32_t out_index; uint32_t depth; };
     const Tmp &rt = bl.nodes[root];
-    if (rt.left < 0) {
-        out.root_link = leaf_link(rt);
-        out.max_depth = 1;
-        // a single-leaf scene still gets one node so the kernel has something to read
-        Node2 nd; std::memset(&nd, 0, sizeof(nd));
-        for (int k = 0; k < 12; ++k) nd.f[k] = 0.0f;
-        nd.f[0] = rt.box.lo[0]; nd.f[1] = rt.box.hi[0]; nd.f[2] = rt.box.lo[1]; nd.f[3] = rt.box.hi[1];
-        nd.f[8] = rt.box.lo[2]; nd.f[9] = rt.box.hi[2];
-        nd.f[4] = 1.0f; nd.f[5] = -1.0f; nd.f[6] = 1.0f; nd.f[7] = -1.0f; nd.f[10] = 1.0f; nd.f[11] = -1.0f;  // empty c1
-        nd.link[0] = leaf_link(rt); nd.link[1] = leaf_link(rt);
+    double root_area = std::max(double(rt.box.half_area()), 1e-30);
+    auto set_child = [](Node4 &nd, int k, const Box &b, int32_t link) {
+        nd.f[k] = b.lo[0]; nd.f[4 + k] = b.hi[0]; nd.f[8 + k] = b.lo[1]; nd.f[12 + k] = b.hi[1]; nd.f[16 + k] = b.lo[2]; nd.f[20 + k] = b.hi[2];
+        nd.link[k] = link;
+    };
+    auto empty_node = []() {
+        Node4 nd; std::memset(&nd, 0, sizeof(nd));
+        for (int k = 0; k < 4; ++k) nd.link[k] = kEmptyLink;
+        return nd;
+    };
+    if (rt.left < 0) {                       // the whole scene fits one leaf
+        Node4 nd = empty_node();
+        set_child(nd, 0, rt.box, leaf_link(rt));
         out.nodes.push_back(nd);
-        out.root_link = 0;
+        out.max_depth = 1;
         return;
     }
+    struct Item { uint32_t tmp; int32_t out_index; uint32_t depth; };
     std::vector<Item> stack; stack.push_back({root, 0, 1});
     out.nodes.resize(1);
-    double root_area = std::max(double(rt.box.half_area()), 1e-30);
     while (!stack.empty()) {
         Item it = stack.back(); stack.pop_back();
         const Tmp &t = bl.nodes[it.tmp];
-        const Tmp &c0 = bl.nodes[t.left], &c1 = bl.nodes[t.right];
-        Node2 nd; std::memset(&nd, 0, sizeof(nd));
-        nd.f[0] = c0.box.lo[0]; nd.f[1] = c0.box.hi[0]; nd.f[2] = c0.box.lo[1]; nd.f[3] = c0.box.hi[1];
-        nd.f[4] = c1.box.lo[0]; nd.f[5] = c1.box.hi[0]; nd.f[6] = c1.box.lo[1]; nd.f[7] = c1.box.hi[1];
-        nd.f[8] = c0.box.lo[2]; nd.f[9] = c0.box.hi[2]; nd.f[10] = c1.box.lo[2]; nd.f[11] = c1.box.hi[2];
+        // collapse: start with the two children, split the largest inner child until four
+        uint32_t ch[4]; int nc = 0;
+        ch[nc++] = uint32_t(t.left); ch[nc++] = uint32_t(t.right);
+        while (nc < 4) {
+            int best = -1; float best_area = -1.0f;
+            for (int k = 0; k < nc; ++k) {
+                const Tmp &c = bl.nodes[ch[k]];
+                if (c.left >= 0 && c.box.half_area() > best_area) { best_area = c.box.half_area(); best = k; }
+            }
+            if (best < 0) break;
+            const Tmp &c = bl.nodes[ch[best]];
+            ch[best] = uint32_t(c.left); ch[nc++] = uint32_t(c.right);
+        }
+        Node4 nd = empty_node();
         out.sah_cost += kTraversalCost*t.box.half_area()/root_area;
         out.max_depth = std::max(out.max_depth, it.depth + 1);
-        const Tmp *cs[2] = {&c0, &c1}; const int32_t ci[2] = {t.left, t.right};
-        for (int k = 0; k < 2; ++k) {
-            if (cs[k]->left < 0) {
-                nd.link[k] = leaf_link(*cs[k]);
-                out.sah_cost += kIntersectCost*cs[k]->count*cs[k]->box.half_area()/root_area;
+        for (int k = 0; k < nc; ++k) {
+            const Tmp &c = bl.nodes[ch[k]];
+            if (c.left < 0) {
+                set_child(nd, k, c.box, leaf_link(c));
+                out.sah_cost += kIntersectCost*c.count*c.box.half_area()/root_area;
             } else {
-                nd.link[k] = int32_t(out.nodes.size());
+                int32_t idx = int32_t(out.nodes.size());
+                set_child(nd, k, c.box, idx);
                 out.nodes.emplace_back();
-                stack.push_back({uint32_t(ci[k]), nd.link[k], it.depth + 1});
+                stack.push_back({ch[k], idx, it.depth + 1});
             }
         }
         out.nodes[size_t(it.out_index)] = nd;
     }
-    out.root_link = 0;
 }
 
 }  // namespace tgb

@@ -384,14 +384,14 @@ int upload_scene(tgb_ctx *c, const tgb_scene_desc *d) {
     }
 
     // ---- BVH over every mesh triangle
-    Bvh2 bvh;
+    Bvh4 bvh;
     // Box padding that covers the rounding of the fused slab test t = fma(lo, 1/d, -(o/d)): spatial error
     // <= (2|o| + |lo|) * 2^-24, so 1e-6 x the largest coordinate magnitude in play (scene or camera) is ample.
     float extent = std::max(std::max(std::fabs(sc.cam.pos.x), std::fabs(sc.cam.pos.y)), std::fabs(sc.cam.pos.z));
     for (const BuildTri &t : btris) for (int k = 0; k < 3; ++k)
         extent = std::max(extent, std::max(std::fabs(t.v0[k]), std::max(std::fabs(t.v1[k]), std::fabs(t.v2[k]))));
-    build_bvh2(btris.data(), uint32_t(btris.size()), bvh, 0, 1e-6f*extent);
-    if (bvh.max_depth + 2 > uint32_t(kStackSize)) return fail(c, TGB_ERR_UNSUPPORTED, "BVH depth %u exceeds the traversal stack", bvh.max_depth);
+    build_bvh4(btris.data(), uint32_t(btris.size()), bvh, 0, 1e-6f*extent);
+    if (3*bvh.max_depth + 2 > uint32_t(kStackSize)) return fail(c, TGB_ERR_UNSUPPORTED, "BVH depth %u exceeds the traversal stack", bvh.max_depth);
     c->bvh_depth = bvh.max_depth; c->n_tris = uint32_t(btris.size()); c->bvh_sah = bvh.sah_cost;
     std::vector<float4> tri_isect(3*btris.size());
     for (size_t k = 0; k < bvh.order.size(); ++k) {
@@ -403,8 +403,8 @@ int upload_scene(tgb_ctx *c, const tgb_scene_desc *d) {
         tri_isect[3*k + 1] = make_float4(e1.y, e1.z, e2.x, e2.y);
         tri_isect[3*k + 2] = make_float4(e2.z, ng.x, ng.y, ng.z);
     }
-    std::vector<float4> nodes(4*bvh.nodes.size());
-    std::memcpy(nodes.data(), bvh.nodes.data(), bvh.nodes.size()*sizeof(Node2));
+    std::vector<float4> nodes(8*bvh.nodes.size());
+    std::memcpy(nodes.data(), bvh.nodes.data(), bvh.nodes.size()*sizeof(Node4));
     c->geom_bytes = nodes.size()*16 + tri_isect.size()*16 + tri_shade.size()*16 + bvh.order.size()*8;
 
     int rc;
@@ -831,6 +831,53 @@ int tgb200_unpack_tiles(tgb_ctx *c, const tgb_tile *tiles, uint32_t n_tiles, con
     cudaError_t e = cudaStreamSynchronize(c->stream);
     if (owned) cudaFree(pid);
     if (e != cudaSuccess) return fail(c, TGB_ERR_CUDA, "unpack_tiles failed: %s", cudaGetErrorString(e));
+    return TGB_OK;
+}
+
+// Host-only self-check of the BVH builder (no GPU needed): builds the 4-ary BVH over n triangles (9 floats each) and
+// verifies that every triangle is referenced by exactly one leaf and lies inside every box on its root-to-leaf chain.
+int tgb200_bvh_selftest(const float *tri_verts, uint32_t n, uint32_t *n_nodes, uint32_t *depth, uint32_t *max_leaf) {
+    if (n && !tri_verts) return TGB_ERR_INVALID;
+    std::vector<BuildTri> tris(n);
+    for (uint32_t i = 0; i < n; ++i) std::memcpy(&tris[i], tri_verts + 9*size_t(i), sizeof(BuildTri));
+    Bvh4 bvh;
+    build_bvh4(tris.data(), n, bvh, 0, 0.0f);
+    if (n_nodes) *n_nodes = uint32_t(bvh.nodes.size());
+    if (depth) *depth = bvh.max_depth;
+    if (n == 0) return bvh.nodes.empty() ? TGB_OK : TGB_ERR_INVALID;
+    if (bvh.order.size() != n) return TGB_ERR_INVALID;
+    std::vector<uint32_t> seen(n, 0);
+    uint32_t worst_leaf = 0;
+    struct It { int32_t node; float lo[3], hi[3]; };
+    std::vector<It> stack;
+    It root; root.node = 0;
+    for (int a = 0; a < 3; ++a) { root.lo[a] = bvh.lo[a]; root.hi[a] = bvh.hi[a]; }
+    stack.push_back(root);
+    while (!stack.empty()) {
+        It it = stack.back(); stack.pop_back();
+        if (it.node < 0 || size_t(it.node) >= bvh.nodes.size()) return TGB_ERR_INVALID;
+        const Node4 &nd = bvh.nodes[size_t(it.node)];
+        for (int k = 0; k < 4; ++k) {
+            if (nd.link[k] == kEmptyLink) continue;
+            It ch; ch.node = nd.link[k];
+            ch.lo[0] = nd.f[k]; ch.hi[0] = nd.f[4 + k]; ch.lo[1] = nd.f[8 + k]; ch.hi[1] = nd.f[12 + k]; ch.lo[2] = nd.f[16 + k]; ch.hi[2] = nd.f[20 + k];
+            for (int a = 0; a < 3; ++a) if (ch.lo[a] < it.lo[a] || ch.hi[a] > it.hi[a]) return TGB_ERR_INVALID;   // child box inside parent box
+            if (nd.link[k] >= 0) { stack.push_back(ch); continue; }
+            int code = ~nd.link[k]; uint32_t first = uint32_t(code >> 3), count = uint32_t(code & 7) + 1;
+            worst_leaf = std::max(worst_leaf, count);
+            for (uint32_t i = 0; i < count; ++i) {
+                if (first + i >= n) return TGB_ERR_INVALID;
+                uint32_t t = bvh.order[first + i];
+                if (t >= n) return TGB_ERR_INVALID;
+                seen[t]++;
+                const float *v[3] = {tris[t].v0, tris[t].v1, tris[t].v2};
+                for (int q = 0; q < 3; ++q) for (int a = 0; a < 3; ++a)
+                    if (v[q][a] < ch.lo[a] || v[q][a] > ch.hi[a]) return TGB_ERR_INVALID;                          // triangle inside its leaf box
+            }
+        }
+    }
+    for (uint32_t i = 0; i < n; ++i) if (seen[i] != 1) return TGB_ERR_INVALID;
+    if (max_leaf) *max_leaf = worst_leaf;
     return TGB_OK;
 }
 

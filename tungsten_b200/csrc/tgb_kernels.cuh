@@ -129,83 +129,87 @@ struct TravStack {
     }
 };
 
-// BVH traversal over the mesh triangles, K rays per lane (ray index = warp chunk + j*32 + lane), per-lane
-// while-while: walk inner nodes until a leaf, intersect the leaf, pop.  Node visit = one 64-byte node (4 x 16 B
-// loads) and two fused slab tests t = lo/d - o/d (boxes are padded at build time to cover the FMA rounding).
+// BVH traversal over the mesh triangles: one ray per thread, per-lane while-while over the 4-ary BVH.
+// Node visit = one 128-byte node (7 x 16 B loads): four fused slab tests t = lo/d - o/d per axis (boxes are padded at
+// build time to cover the FMA rounding), the hit children are ordered near-to-far with a 5-exchange sorting network,
+// the nearest is entered and the others are pushed far-to-near.
 // Triangle test = Embree's MoellerTrumboreIntersector1 (thirdparty/embree/kernels/geometry/
 // triangle_intersector_moeller.h:75-111) with IEEE division for t,u,v.
-// P::fetch(idx, o, d, tnear, h, any) loads ray `idx` with its initial hit (from the analytic pass; false = nothing to
-// traverse) and says whether it is an occlusion query (any = stop at the first triangle hit); P::finish(h) stores it.
+// `any`: occlusion query, stop at the first triangle hit.
 // Alternatives measured and rejected (profiles/r01_a_k_trace_baseline.md): warp-synchronous speculative traversal,
-// if-if state machines with and without several rays per lane, 32-byte quantised nodes.
-template <class P>
-TGB_D void bvh_traverse_multi(const DScene &sc, int *smem_stack, P &pol, uint32_t n, uint32_t K) {
-    const uint32_t lane = threadIdx.x & 31u;
-    const uint32_t gw = (blockIdx.x*blockDim.x + threadIdx.x) >> 5;
-    const uint64_t chunk = uint64_t(gw)*32u*K;
-    if (chunk >= n) return;
-    const uint64_t chunk_end = chunk + 32ull*K;
-    const uint32_t end = chunk_end < uint64_t(n) ? uint32_t(chunk_end) : n;
+// if-if state machines with and without several rays per lane, 32-byte quantised binary nodes, higher occupancy.
+#define TGB_CSWAP(ta, la, tb, lb) { bool sw_ = tb < ta; float tt_ = sw_ ? tb : ta; tb = sw_ ? ta : tb; ta = tt_; \
+                                    int ll_ = sw_ ? lb : la; lb = sw_ ? la : lb; la = ll_; }
+TGB_D void bvh_traverse(const DScene &sc, int *smem_stack, V3 o, V3 d, float tnear, bool any, Hit &h) {
     const float4 *nodes = sc.nodes;
-    TravStack stk; stk.smem = smem_stack + threadIdx.x;
-    for (uint32_t my = uint32_t(chunk) + lane; my < end; my += 32u) {
-        V3 o, d; float tnear; Hit h; bool any;
-        if (!pol.fetch(my, o, d, tnear, h, any)) continue;
-        const float ooeps = 1e-30f;
-        const float idx = 1.0f/(fabsf(d.x) > ooeps ? d.x : copysignf(ooeps, d.x));
-        const float idy = 1.0f/(fabsf(d.y) > ooeps ? d.y : copysignf(ooeps, d.y));
-        const float idz = 1.0f/(fabsf(d.z) > ooeps ? d.z : copysignf(ooeps, d.z));
-        const float oodx = o.x*idx, oody = o.y*idy, oodz = o.z*idz;
-        stk.sp = 0;
-        int cur = 0;
-        bool done = false;
-        while (!done) {
-            while (cur >= 0) {
-                const float4 n0 = __ldg(nodes + 4*cur), n1 = __ldg(nodes + 4*cur + 1), n2 = __ldg(nodes + 4*cur + 2);
-                const float4 lk = __ldg(nodes + 4*cur + 3);
-                float c0lox = __fmaf_rn(n0.x, idx, -oodx), c0hix = __fmaf_rn(n0.y, idx, -oodx), c0loy = __fmaf_rn(n0.z, idy, -oody), c0hiy = __fmaf_rn(n0.w, idy, -oody);
-                float c1lox = __fmaf_rn(n1.x, idx, -oodx), c1hix = __fmaf_rn(n1.y, idx, -oodx), c1loy = __fmaf_rn(n1.z, idy, -oody), c1hiy = __fmaf_rn(n1.w, idy, -oody);
-                float c0loz = __fmaf_rn(n2.x, idz, -oodz), c0hiz = __fmaf_rn(n2.y, idz, -oodz), c1loz = __fmaf_rn(n2.z, idz, -oodz), c1hiz = __fmaf_rn(n2.w, idz, -oodz);
-                float c0min = fmaxf(fmaxf(fminf(c0lox, c0hix), fminf(c0loy, c0hiy)), fmaxf(fminf(c0loz, c0hiz), tnear));
-                float c0max = fminf(fminf(fmaxf(c0lox, c0hix), fmaxf(c0loy, c0hiy)), fminf(fmaxf(c0loz, c0hiz), h.t));
-                float c1min = fmaxf(fmaxf(fminf(c1lox, c1hix), fminf(c1loy, c1hiy)), fmaxf(fminf(c1loz, c1hiz), tnear));
-                float c1max = fminf(fminf(fmaxf(c1lox, c1hix), fmaxf(c1loy, c1hiy)), fminf(fmaxf(c1loz, c1hiz), h.t));
-                bool t0 = c0min <= c0max, t1 = c1min <= c1max;
-                int l0 = __float_as_int(lk.x), l1 = __float_as_int(lk.y);
-                if (t0 && t1) {
-                    bool swp = c1min < c0min;
-                    cur = swp ? l1 : l0;
-                    stk.push(swp ? l0 : l1);
-                } else if (t0) cur = l0;
-                else if (t1) cur = l1;
-                else if (stk.sp) cur = stk.pop();
-                else { done = true; break; }
+    TravStack stk; stk.smem = smem_stack + threadIdx.x; stk.sp = 0;
+    const float ooeps = 1e-30f;
+    const float idx = 1.0f/(fabsf(d.x) > ooeps ? d.x : copysignf(ooeps, d.x));
+    const float idy = 1.0f/(fabsf(d.y) > ooeps ? d.y : copysignf(ooeps, d.y));
+    const float idz = 1.0f/(fabsf(d.z) > ooeps ? d.z : copysignf(ooeps, d.z));
+    const float oodx = o.x*idx, oody = o.y*idy, oodz = o.z*idz;
+    const int EMPTY = int(0x80000000u);
+    int cur = 0;
+    while (true) {
+        while (cur >= 0) {
+            const float4 *nd = nodes + 8*size_t(cur);
+            const float4 lox = __ldg(nd), hix = __ldg(nd + 1), loy = __ldg(nd + 2), hiy = __ldg(nd + 3), loz = __ldg(nd + 4), hiz = __ldg(nd + 5);
+            const int4 lk = __ldg(reinterpret_cast<const int4 *>(nd + 6));
+            float t0, t1, t2, t3;
+#define TGB_SLAB(K, OUT) { \
+                float ax = __fmaf_rn(lox.K, idx, -oodx), bx = __fmaf_rn(hix.K, idx, -oodx); \
+                float ay = __fmaf_rn(loy.K, idy, -oody), by = __fmaf_rn(hiy.K, idy, -oody); \
+                float az = __fmaf_rn(loz.K, idz, -oodz), bz = __fmaf_rn(hiz.K, idz, -oodz); \
+                float tmn = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fmaxf(fminf(az, bz), tnear)); \
+                float tmx = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fminf(fmaxf(az, bz), h.t)); \
+                OUT = (tmn <= tmx && lk.K != EMPTY) ? tmn : INFINITY; }
+            TGB_SLAB(x, t0) TGB_SLAB(y, t1) TGB_SLAB(z, t2) TGB_SLAB(w, t3)
+#undef TGB_SLAB
+            int l0 = lk.x, l1 = lk.y, l2 = lk.z, l3 = lk.w;
+            TGB_CSWAP(t0, l0, t1, l1) TGB_CSWAP(t2, l2, t3, l3) TGB_CSWAP(t0, l0, t2, l2) TGB_CSWAP(t1, l1, t3, l3) TGB_CSWAP(t1, l1, t2, l2)
+            if (t0 == INFINITY) {
+                if (stk.sp == 0) return;
+                cur = stk.pop();
+            } else {
+                if (t3 != INFINITY) stk.push(l3);
+                if (t2 != INFINITY) stk.push(l2);
+                if (t1 != INFINITY) stk.push(l1);
+                cur = l0;
             }
-            if (done) break;
-            int code = ~cur;
-            int first = code >> 3, count = (code & 7) + 1;
-            for (int i = 0; i < count; ++i) {
-                const float4 *tr = sc.tri_isect + 3*size_t(first + i);
-                const float4 a = __ldg(tr), b = __ldg(tr + 1), c = __ldg(tr + 2);
-                V3 v0 = v3(a.x, a.y, a.z), e1 = v3(a.w, b.x, b.y), e2 = v3(b.z, b.w, c.x), ng = v3(c.y, c.z, c.w);
-                V3 C = v0 - o;
-                V3 R = cross(d, C);
-                float den = edot(ng, d);
-                float absDen = fabsf(den);
-                uint32_t sgn = __float_as_uint(den) & 0x80000000u;
-                float U = xor_sign(edot(R, e2), sgn);
-                float V = xor_sign(edot(R, e1), sgn);
-                if (!(den != 0.0f && U >= 0.0f && V >= 0.0f && U + V <= absDen)) continue;
-                float T = xor_sign(edot(ng, C), sgn);
-                if (!(T > absDen*tnear && T < absDen*h.t)) continue;
-                h.t = T/absDen; h.u = U/absDen; h.v = V/absDen; h.id = first + i;
-                if (any) { done = true; break; }
-            }
-            if (done) break;
-            if (stk.sp) cur = stk.pop(); else done = true;
         }
-        pol.finish(h);
+        int code = ~cur;
+        int first = code >> 3, count = (code & 7) + 1;
+        for (int i = 0; i < count; ++i) {
+            const float4 *tr = sc.tri_isect + 3*size_t(first + i);
+            const float4 a = __ldg(tr), b = __ldg(tr + 1), c = __ldg(tr + 2);
+            V3 v0 = v3(a.x, a.y, a.z), e1 = v3(a.w, b.x, b.y), e2 = v3(b.z, b.w, c.x), ng = v3(c.y, c.z, c.w);
+            V3 C = v0 - o;
+            V3 R = cross(d, C);
+            float den = edot(ng, d);
+            float absDen = fabsf(den);
+            uint32_t sgn = __float_as_uint(den) & 0x80000000u;
+            float U = xor_sign(edot(R, e2), sgn);
+            float V = xor_sign(edot(R, e1), sgn);
+            if (!(den != 0.0f && U >= 0.0f && V >= 0.0f && U + V <= absDen)) continue;
+            float T = xor_sign(edot(ng, C), sgn);
+            if (!(T > absDen*tnear && T < absDen*h.t)) continue;
+            h.t = T/absDen; h.u = U/absDen; h.v = V/absDen; h.id = first + i;
+            if (any) return;
+        }
+        if (stk.sp == 0) return;
+        cur = stk.pop();
     }
+}
+
+// Policy wrapper kept for the three users (path rays, shadow queries, parity hook): one ray per thread.
+template <class P>
+TGB_D void bvh_traverse_multi(const DScene &sc, int *smem_stack, P &pol, uint32_t n, uint32_t /*K*/) {
+    uint32_t i = blockIdx.x*blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    V3 o, d; float tnear; Hit h; bool any;
+    if (!pol.fetch(i, o, d, tnear, h, any)) return;
+    bvh_traverse(sc, smem_stack, o, d, tnear, any, h);
+    pol.finish(h);
 }
 
 // Fill a Surface from a hit: Primitive::intersectionInfo for mesh/quad/cube

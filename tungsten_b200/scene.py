@@ -91,6 +91,41 @@ def rot_yxz(rot):       # Mat4f::rotYXZ (math/Mat4f.cpp:118-131)
     return m
 
 
+def quat_from_matrix(a):      # QuaternionF::fromMatrix (math/Quaternion.hpp:111-146); a = 3x3 rotation, fp32
+    a = np.asarray(a, dtype=f32)
+    trace = f32(f32(a[0, 0] + a[1, 1]) + a[2, 2])
+    if trace > 0.0:
+        s = f32(f32(0.5)/np.sqrt(f32(trace + f32(1.0))))
+        return np.array([f32(f32(0.25)/s), f32(f32(a[2, 1] - a[1, 2])*s), f32(f32(a[0, 2] - a[2, 0])*s), f32(f32(a[1, 0] - a[0, 1])*s)], dtype=f32)
+    if a[0, 0] > a[1, 1] and a[0, 0] > a[2, 2]:
+        s = f32(f32(2.0)*np.sqrt(f32(f32(f32(f32(1.0) + a[0, 0]) - a[1, 1]) - a[2, 2])))
+        return np.array([f32(f32(a[2, 1] - a[1, 2])/s), f32(f32(0.25)*s), f32(f32(a[0, 1] + a[1, 0])/s), f32(f32(a[0, 2] + a[2, 0])/s)], dtype=f32)
+    if a[1, 1] > a[2, 2]:
+        s = f32(f32(2.0)*np.sqrt(f32(f32(f32(f32(1.0) + a[1, 1]) - a[0, 0]) - a[2, 2])))
+        return np.array([f32(f32(a[0, 2] - a[2, 0])/s), f32(f32(a[0, 1] + a[1, 0])/s), f32(f32(0.25)*s), f32(f32(a[1, 2] + a[2, 1])/s)], dtype=f32)
+    s = f32(f32(2.0)*np.sqrt(f32(f32(f32(f32(1.0) + a[2, 2]) - a[0, 0]) - a[1, 1])))
+    return np.array([f32(f32(a[1, 0] - a[0, 1])/s), f32(f32(a[0, 2] + a[2, 0])/s), f32(f32(a[1, 2] + a[2, 1])/s), f32(f32(0.25)*s)], dtype=f32)
+
+
+def quat_mul(a, o):            # Quaternion::operator*(Quaternion) (math/Quaternion.hpp:68-76)
+    return np.array([
+        f32(f32(f32(a[0]*o[0]) - f32(a[1]*o[1])) - f32(a[2]*o[2])) - f32(a[3]*o[3]),
+        f32(f32(f32(a[0]*o[1]) + f32(a[1]*o[0])) + f32(a[2]*o[3])) - f32(a[3]*o[2]),
+        f32(f32(f32(a[0]*o[2]) - f32(a[1]*o[3])) + f32(a[2]*o[0])) + f32(a[3]*o[1]),
+        f32(f32(f32(a[0]*o[3]) + f32(a[1]*o[2])) - f32(a[2]*o[1])) + f32(a[3]*o[0])], dtype=f32)
+
+
+def quat_rotate(q, o):         # Quaternion::operator*(Vec3) (math/Quaternion.hpp:78-88), vectorised over rows of o
+    o = np.asarray(o, dtype=f32)
+    two = f32(2.0)
+    tx = two*(q[2]*o[:, 2] - q[3]*o[:, 1]); ty = two*(q[3]*o[:, 0] - q[1]*o[:, 2]); tz = two*(q[1]*o[:, 1] - q[2]*o[:, 0])
+    r = np.empty_like(o)
+    r[:, 0] = ((o[:, 0] + q[0]*tx) + q[2]*tz) - q[3]*ty
+    r[:, 1] = ((o[:, 1] + q[0]*ty) + q[3]*tx) - q[1]*tz
+    r[:, 2] = ((o[:, 2] + q[0]*tz) + q[1]*ty) - q[2]*tx
+    return r
+
+
 def _random_ortho(a):   # io/JsonPtr.cpp:78-89
     if abs(a[0]) > abs(a[1]):
         res = v3(0.0, 1.0, 0.0)
@@ -429,6 +464,55 @@ class FlatScene:
         self.slots += list(bsdfs); self.primitives.append(p)
         self.n_triangles += len(t)
 
+    def add_instances(self, transform, masters, ids, inst_transforms):
+        """Instance primitive (primitives/Instance.cpp:54-75,392-420): rigid copies (quaternion + translation, no scale) of
+        master meshes.  B200-first: with 180 GB of HBM the instances are simply FLATTENED into one world-space triangle
+        mesh (no two-level BVH, no per-ray transform): world = pos_i + rot_i*(master_transform*v), exactly the point
+        the reference reaches through `Instance::intersectionInfo` (Instance.cpp:325-334).
+        masters: list of (verts, tris, bsdf_index, smooth, master_transform); ids: master index per instance;
+        inst_transforms: (n, 4, 4) float32."""
+        m = transform
+        rot_p = quat_from_matrix(np.stack([normalized(v3(m[:3, 0])), normalized(v3(m[:3, 1])), normalized(v3(m[:3, 2]))], axis=1))
+        prepared = []
+        for (verts, tris, bsdf, smooth, mt) in masters:
+            pos = verts["pos"].astype(np.float32); nrm = verts["normal"].astype(np.float32)
+            wp = np.zeros_like(pos); wn = np.zeros_like(nrm)
+            for i in range(3):
+                wp[:, i] = ((mt[i, 0]*pos[:, 0] + mt[i, 1]*pos[:, 1]) + mt[i, 2]*pos[:, 2]) + mt[i, 3]
+            inv = [f32(1.0)/dot(v3(mt[:3, c]), v3(mt[:3, c])) for c in range(3)]
+            for i in range(3):
+                r = [f32(inv[i]*mt[i, c]) for c in range(3)]
+                wn[:, i] = (r[0]*nrm[:, 0] + r[1]*nrm[:, 1]) + r[2]*nrm[:, 2]
+            prepared.append((wp, wn, verts["uv"].astype(np.float32), tris, bsdf, smooth))
+        vparts, tparts, bsdfs, voff = [], [], [], 0
+        smooth_any = any(p[5] for p in prepared)
+        for k, mid in enumerate(ids):
+            wp, wn, uv, tris, bsdf, smooth = prepared[int(mid)]
+            it = np.asarray(inst_transforms[k], dtype=np.float32)
+            ipos = v3(it[:3, 3])
+            irot = quat_from_matrix(np.stack([normalized(v3(it[:3, 0])), normalized(v3(it[:3, 1])), normalized(v3(it[:3, 2]))], axis=1))
+            p_w = mat4_point(m, ipos)                             # _instancePos[i] = _transform*_instancePos[i]
+            q_w = quat_mul(rot_p, irot)                           # _instanceRot[i] = rot*_instanceRot[i]
+            out = np.zeros(len(wp), dtype=VERTEX_DTYPE)
+            out["pos"] = quat_rotate(q_w, wp) + p_w[None, :]
+            out["normal"] = quat_rotate(q_w, wn)
+            out["uv"] = uv
+            t = np.array(tris, dtype=TRI_DTYPE, copy=True)
+            t["v0"] += voff; t["v1"] += voff; t["v2"] += voff
+            if bsdf not in bsdfs:
+                bsdfs.append(bsdf)
+            t["material"] = bsdfs.index(bsdf)
+            vparts.append(out); tparts.append(t); voff += len(out)
+        verts = np.concatenate(vparts) if vparts else np.zeros(0, dtype=VERTEX_DTYPE)
+        tris = np.concatenate(tparts) if tparts else np.zeros(0, dtype=TRI_DTYPE)
+        self._keep += [verts, tris]
+        p = abi.Primitive(type=abi.PRIM_MESH, emission_tex=-1, smooth=1 if smooth_any else 0,
+                          bsdf_first=len(self.slots), bsdf_count=max(len(bsdfs), 1), n_verts=len(verts), n_tris=len(tris))
+        p.verts = verts.ctypes.data_as(C.POINTER(abi.Vertex)); p.tris = tris.ctypes.data_as(C.POINTER(abi.Triangle))
+        self.slots += list(bsdfs) if bsdfs else [0]
+        self.primitives.append(p)
+        self.n_triangles += len(tris)
+
     def add_infinite_sphere(self, transform, emission_tex, sample=True):
         m = transform
         rot = np.stack([normalized(v3(m[:3, 0])), normalized(v3(m[:3, 1])), normalized(v3(m[:3, 2]))], axis=1)
@@ -507,6 +591,24 @@ def load_scene(path_or_dict, base_dir=None):
         tf = parse_transform(p.get("transform"))
         if ty == "infinite_sphere":
             fs.add_infinite_sphere(tf, fs._emission(p, base_dir), p.get("sample", True))
+            continue
+        if ty == "instances":
+            masters = []
+            for mp in p.get("masters", []):
+                if mp.get("type") != "mesh":
+                    raise SceneError("instance masters other than meshes are outside the hot path")
+                mb = mp.get("bsdf")
+                if isinstance(mb, list):
+                    raise SceneError("multi-material instance masters are outside the hot path")
+                mv, mt_ = load_wo3(os.path.join(base_dir, mp["file"]))
+                masters.append((mv, mt_, fetch_bsdf(mb) if mb is not None else fs.add_bsdf({"type": "lambert"}),
+                                mp.get("smooth", False), parse_transform(mp.get("transform"))))
+            inst = p.get("instances", [])
+            if isinstance(inst, str) or "instancesA" in p or "instancesB" in p:
+                raise SceneError("binary instance files are outside the hot path (list the instances inline)")
+            ids = [int(i.get("id", 0)) for i in inst]
+            its = np.stack([parse_transform(i.get("transform")) for i in inst]) if inst else np.zeros((0, 4, 4), np.float32)
+            fs.add_instances(tf, masters, ids, its)
             continue
         if "bsdf" in p:
             bs = p["bsdf"]

@@ -272,3 +272,39 @@ def materialtest_standin(out_dir, name="coat_env", res=(128, 128), spp=16, max_b
                          "enable_consistency_checks": False, "enable_two_sided_shading": True},
           "renderer": _renderer(spp)}
     return write_scene(out_dir, name, sc, {name + "_ball.wo3": (v, t), name + "_stand.wo3": (sv, st)})
+
+
+def instanced_forest(out_dir, name="forest", n_instances=64, tree_subdiv=2, res=(128, 128), spp=16, max_bounces=16, seed=5,
+                     extent=6.0):
+    """Stand-in for BASELINE.json config C3: a few tree-like masters (trunk + crown blobs) scattered as rigid instances
+    (rotation about Y + translation, no scale -- `Instance` cannot scale) over a ground quad, Lambert + rough plastic,
+    sky environment.  tree_subdiv 4 -> 10,240-triangle masters: 1,000 instances = 10.2 M triangles."""
+    rng = np.random.RandomState(seed)
+    crown_v, crown_t = icosphere(tree_subdiv, 1.0, displace=0.25, seed=7)
+    trunk_v, trunk_t = icosphere(max(tree_subdiv - 1, 0), 1.0)
+    os.makedirs(out_dir, exist_ok=True)
+    save_rgbe(os.path.join(out_dir, name + "_env.hdr"), sky_envmap(64, 32, sun_power=25.0))
+    bsdfs = [{"name": "leaf", "type": "rough_plastic", "albedo": [0.15, 0.45, 0.12], "ior": 1.5, "distribution": "ggx", "roughness": 0.25},
+             {"name": "bark", "type": "lambert", "albedo": [0.35, 0.22, 0.12]},
+             {"name": "ground", "type": "lambert", "albedo": {"type": "checker", "on_color": [0.45, 0.4, 0.3], "off_color": [0.3, 0.32, 0.2], "res_u": 24, "res_v": 24}}]
+    masters = [{"type": "mesh", "file": name + "_crown.wo3", "smooth": True, "bsdf": "leaf",
+                "transform": {"position": [0, 1.1, 0], "scale": [0.55, 0.8, 0.55]}},
+               {"type": "mesh", "file": name + "_trunk.wo3", "smooth": True, "bsdf": "bark",
+                "transform": {"position": [0, 0.3, 0], "scale": [0.09, 0.35, 0.09]}}]
+    inst = []
+    for i in range(n_instances):
+        x, z = rng.uniform(-extent/2, extent/2, 2)
+        ang = float(rng.uniform(0, 360))
+        for mid in (0, 1):
+            inst.append({"id": mid, "transform": {"position": [float(x), 0.0, float(z)], "rotation": [0, ang, 0]}})
+    prims = [{"name": "ground", "type": "quad", "bsdf": "ground", "transform": {"scale": [extent*1.6, 1, extent*1.6]}},
+             {"name": "forest", "type": "instances", "masters": masters, "instances": inst, "bsdf": "ground",
+              "transform": {"position": [0, 0, 0], "rotation": [0, 15, 0]}},
+             {"name": "sky", "type": "infinite_sphere", "emission": name + "_env.hdr", "sample": True}]
+    sc = {"media": [], "bsdfs": bsdfs, "primitives": prims,
+          "camera": {"tonemap": "filmic", "resolution": list(res), "reconstruction_filter": "tent",
+                     "transform": {"position": [0.0, 2.6, extent*0.95], "look_at": [0, 0.6, 0], "up": [0, 1, 0]}, "type": "pinhole", "fov": 40},
+          "integrator": {"type": "path_tracer", "min_bounces": 0, "max_bounces": max_bounces, "enable_light_sampling": True,
+                         "enable_consistency_checks": False, "enable_two_sided_shading": True},
+          "renderer": _renderer(spp)}
+    return write_scene(out_dir, name, sc, {name + "_crown.wo3": (crown_v, crown_t), name + "_trunk.wo3": (trunk_v, trunk_t)})
