@@ -40,6 +40,7 @@ struct tgb_ctx {
     uint32_t capacity = 0;
     PathState st{}, st2{};      // st2 = second copy of the persistent arrays (ray, throughput, emission, rng, hit, pid)
     uint32_t *queue_a = nullptr, *queue_b = nullptr, *squeue = nullptr, *squeue2 = nullptr, *free_list = nullptr;
+    uint32_t *bin_keys = nullptr, *bin_hist = nullptr;      // queue_a doubles as the ray-coherence visiting order of k_trace
     size_t res_capacity = 0;
     ShadowState ss{};
     uint32_t *counts = nullptr;          // [0]=count A, [1]=count B, [2]=shadow count, [3]=compacted shadow count
@@ -391,6 +392,19 @@ int upload_scene(tgb_ctx *c, const tgb_scene_desc *d) {
     for (const BuildTri &t : btris) for (int k = 0; k < 3; ++k)
         extent = std::max(extent, std::max(std::fabs(t.v0[k]), std::max(std::fabs(t.v1[k]), std::fabs(t.v2[k]))));
     build_bvh4(btris.data(), uint32_t(btris.size()), bvh, 0, 1e-6f*extent);
+    {   // ray-binning grid: bounds of every finite primitive (TraceableScene::_sceneBounds, TraceableScene.hpp:104-110)
+        float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+        auto grow = [&](V3 p) { float q[3] = {p.x, p.y, p.z}; for (int a = 0; a < 3; ++a) { lo[a] = std::min(lo[a], q[a]); hi[a] = std::max(hi[a], q[a]); } };
+        if (!btris.empty()) { grow(f3(bvh.lo)); grow(f3(bvh.hi)); }
+        for (int pi : analytic) {
+            const DPrim &p = prims[pi];
+            if (p.type == TGB_PRIM_QUAD) { grow(p.base); grow(p.base + p.edge0); grow(p.base + p.edge1); grow(p.base + p.edge0 + p.edge1); }
+            else for (int k = 0; k < 8; ++k) grow(p.pos + m3mul(p.rot, v3((k & 1 ? p.scale.x : -p.scale.x), (k & 2 ? p.scale.y : -p.scale.y), (k & 4 ? p.scale.z : -p.scale.z))));
+        }
+        for (int a = 0; a < 3; ++a) if (!(hi[a] > lo[a])) { lo[a] = -1.0f; hi[a] = 1.0f; }
+        sc.bin_lo = v3(lo[0], lo[1], lo[2]);
+        sc.bin_inv = v3(16.0f/(hi[0] - lo[0]), 16.0f/(hi[1] - lo[1]), 16.0f/(hi[2] - lo[2]));
+    }
     if (3*bvh.max_depth + 2 > uint32_t(kStackSize)) return fail(c, TGB_ERR_UNSUPPORTED, "BVH depth %u exceeds the traversal stack", bvh.max_depth);
     c->bvh_depth = bvh.max_depth; c->n_tris = uint32_t(btris.size()); c->bvh_sah = bvh.sah_cost;
     std::vector<float4> tri_isect(3*btris.size());
@@ -437,7 +451,7 @@ int alloc_wavefront(tgb_ctx *c, uint32_t capacity) {
 #define ALLOCF(name) if ((rc = dev_alloc(c, &c->st.name, capacity))) return rc;
     ALLOCF(ox) ALLOCF(oy) ALLOCF(oz) ALLOCF(dx) ALLOCF(dy) ALLOCF(dz) ALLOCF(tmin)
     ALLOCF(tx) ALLOCF(ty) ALLOCF(tz) ALLOCF(ex) ALLOCF(ey) ALLOCF(ez)
-    ALLOCF(pcg) ALLOCF(info) ALLOCF(ht) ALLOCF(hu) ALLOCF(hv) ALLOCF(hid)
+    ALLOCF(pcg) ALLOCF(info) ALLOCF(ra) ALLOCF(rb) ALLOCF(h4)
     ALLOCF(px) ALLOCF(py) ALLOCF(pz)
     ALLOCF(lx) ALLOCF(ly) ALLOCF(lz) ALLOCF(bx) ALLOCF(by) ALLOCF(bz) ALLOCF(wl) ALLOCF(sx) ALLOCF(sy) ALLOCF(sz) ALLOCF(ux) ALLOCF(uy) ALLOCF(uz)
     ALLOCF(ndx) ALLOCF(ndy) ALLOCF(ndz) ALLOCF(ndist) ALLOCF(nfx) ALLOCF(nfy) ALLOCF(nfz) ALLOCF(npl) ALLOCF(npb)
@@ -446,12 +460,14 @@ int alloc_wavefront(tgb_ctx *c, uint32_t capacity) {
     c->st2 = c->st;
 #define ALLOC2(name) if ((rc = dev_alloc(c, &c->st2.name, capacity))) return rc;
     ALLOC2(ox) ALLOC2(oy) ALLOC2(oz) ALLOC2(dx) ALLOC2(dy) ALLOC2(dz) ALLOC2(tmin) ALLOC2(tx) ALLOC2(ty) ALLOC2(tz)
-    ALLOC2(ex) ALLOC2(ey) ALLOC2(ez) ALLOC2(pcg) ALLOC2(info) ALLOC2(ht) ALLOC2(hu) ALLOC2(hv) ALLOC2(hid) ALLOC2(pid)
+    ALLOC2(ex) ALLOC2(ey) ALLOC2(ez) ALLOC2(pcg) ALLOC2(info) ALLOC2(ra) ALLOC2(rb) ALLOC2(h4) ALLOC2(pid)
 #undef ALLOC2
     (void)fp;
     if ((rc = dev_alloc(c, &c->queue_a, capacity))) return rc;
     if ((rc = dev_alloc(c, &c->queue_b, capacity))) return rc;
     if ((rc = dev_alloc(c, &c->free_list, capacity))) return rc;
+    if ((rc = dev_alloc(c, &c->bin_keys, capacity))) return rc;
+    if ((rc = dev_alloc(c, &c->bin_hist, size_t(kBins)))) return rc;
     if ((rc = dev_alloc(c, &c->squeue, size_t(capacity)*2))) return rc;
     if ((rc = dev_alloc(c, &c->squeue2, size_t(capacity)*2))) return rc;
     if ((rc = dev_alloc(c, &c->ss.qt, size_t(capacity)*2))) return rc;
@@ -555,7 +571,7 @@ int render_device(tgb_ctx *c, uint32_t spp_begin, uint32_t spp_count) {
             // refill: survivors occupy slots [0, n_alive) of `cur`; new camera paths are appended behind them
             uint32_t m = std::min(c->capacity - n_alive, total - issued);
             if (m) {
-                k_regen<<<blocks(m, 256), 256, 0, c->stream>>>(sc, cur, bi, n_alive, issued, m); launches++;
+                k_regen<<<blocks(m, 256), 256, 0, c->stream>>>(sc, cur, bi, n_alive, issued, m, c->queue_a); launches++;
                 issued += m;
             }
             uint32_t n = n_alive + m;
@@ -564,7 +580,7 @@ int render_device(tgb_ctx *c, uint32_t spp_begin, uint32_t spp_count) {
             if (c->profiling) CU(cudaEventRecord(c->evt0, c->stream));
             if (has_bvh) {
                 uint32_t K = rays_per_lane(n);
-                k_trace<<<blocks(n, kTraceBlock*K), kTraceBlock, kTraceSmem, c->stream>>>(sc, cur, n, K); launches++;
+                k_trace<<<blocks(n, kTraceBlock*K), kTraceBlock, kTraceSmem, c->stream>>>(sc, cur, c->queue_a, n, K); launches++;
             }
             if (c->profiling) CU(cudaEventRecord(c->evt1, c->stream));
             k_shade<<<blocks(n, 128), 128, 0, c->stream>>>(sc, cur, bi, n, c->squeue, cs, c->ctr); launches++;
@@ -575,7 +591,12 @@ int render_device(tgb_ctx *c, uint32_t spp_begin, uint32_t spp_count) {
                 k_shadow_bvh<<<blocks(2*n, kTraceBlock*K), kTraceBlock, kTraceSmem, c->stream>>>(sc, cur, c->ss, c->squeue2, cs + 1, c->ctr, K); launches++;
             }
             if (c->profiling) CU(cudaEventRecord(c->evs1, c->stream));
-            k_accum<<<blocks(n, 256), 256, 0, c->stream>>>(sc, cur, nxt, n, c->counts); launches++;
+            CU(cudaMemsetAsync(c->bin_hist, 0, kBins*sizeof(uint32_t), c->stream));
+            k_accum<<<blocks(n, 256), 256, 0, c->stream>>>(sc, cur, nxt, n, c->counts, c->bin_keys, c->bin_hist); launches++;
+            if (has_bvh) {          // visiting order of the next k_trace: survivors sorted by ray-coherence key
+                k_bin_scan<<<1, 1024, 0, c->stream>>>(c->bin_hist); launches++;
+                k_bin_scatter<<<blocks(n, 256), 256, 0, c->stream>>>(c->bin_keys, c->bin_hist, c->counts, c->queue_a); launches++;
+            }
             CU(cudaMemcpyAsync(c->h_counts, c->counts, 4*sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
             CU(cudaStreamSynchronize(c->stream));
             if (c->profiling) {

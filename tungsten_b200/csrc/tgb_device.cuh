@@ -121,6 +121,7 @@ struct DScene {
     // global id -> primitive, shading records by global id (4 x float4 each)
     const float4 *tri_isect; const uint32_t *tri_global; const uint32_t *tri_prim; const float4 *tri_shade;
     const float4 *nodes; uint32_t n_nodes; uint32_t n_tris;
+    V3 bin_lo, bin_inv;         // ray-binning grid over the scene bounds: cell = (o - bin_lo)*bin_inv, 16 cells per axis
     const uint32_t *sobol;      // 1024 x 32 direction matrices
 };
 

@@ -18,7 +18,6 @@ struct PathState {
     float *ex, *ey, *ez;                                // accumulated emission (the sample's radiance)
     uint64_t *pcg;                                      // supplemental PCG state
     uint32_t *info;                                     // dimension[0:16) | bounce[16:24) | flags[24:32)
-    float *ht, *hu, *hv; int *hid;                      // closest hit of the current ray
     float *px, *py, *pz;                                // shading point of this bounce (origin of NEE/MIS queries)
     // direct-light estimate of this bounce, folded in by k_accum
     float *lx, *ly, *lz, *bx, *by, *bz, *wl, *sx, *sy, *sz, *ux, *uy, *uz;   // L, B, light weight, surface emission term, throughput before
@@ -27,6 +26,9 @@ struct PathState {
     float *mdx, *mdy, *mdz, *mwx, *mwy, *mwz, *mpb;
     int *qlight;                                        // light primitive of this bounce's queries
     uint32_t *pid;                                      // path index within the step: sample_rel*n_pix + pixel_list_index
+    // packed copies for the traversal kernel, which visits the paths in ray-coherence order (gathers 32 B + 16 B per ray):
+    float4 *ra, *rb;                                    // (o.xyz, tmin), (d.xyz, 0)
+    float4 *h4;                                         // closest hit (t, u, v, id as bits): written by the analytic pass, updated by k_trace
     float *rx, *ry, *rz;                                // finished radiance per path of the step, indexed by pid (not by slot)
 };
 constexpr int kPathFloatArrays = 7 + 3 + 3 + 3 + 3 + 13 + 9 + 7;   // float-sized arrays in PathState (excl. pcg/info/hid/qlight)
@@ -283,6 +285,22 @@ TGB_D bool quad_light_hit(const DPrim &l, V3 p, V3 d, float tnear, float &t, flo
     return true;
 }
 
+TGB_D float4 pack_hit(const Hit &h) { return make_float4(h.t, h.u, h.v, __int_as_float(h.id)); }
+TGB_D Hit unpack_hit(float4 v) { Hit h; h.t = v.x; h.u = v.y; h.v = v.z; h.id = __float_as_int(v.w); return h; }
+
+// Ray-coherence key of a path ray: direction octant (3 bits) + origin cell on a 16^3 grid over the scene bounds (12 bits).
+// k_trace visits the survivors in key order (counting sort of slot indices: k_accum histogram, k_bin_scan, k_bin_scatter),
+// so the lanes of a warp start close together and walk the BVH in the same front-to-back order; only the 48 bytes of
+// packed ray + hit record are gathered through the index, all other state stays in slot order (coalesced).
+constexpr uint32_t kBinBits = 15, kBins = 1u << kBinBits;
+TGB_D uint32_t ray_bin(const DScene &sc, V3 o, V3 d) {
+    uint32_t oct = (d.x < 0.0f ? 1u : 0u) | (d.y < 0.0f ? 2u : 0u) | (d.z < 0.0f ? 4u : 0u);
+    int cx = min(max(int((o.x - sc.bin_lo.x)*sc.bin_inv.x), 0), 15);
+    int cy = min(max(int((o.y - sc.bin_lo.y)*sc.bin_inv.y), 0), 15);
+    int cz = min(max(int((o.z - sc.bin_lo.z)*sc.bin_inv.z), 0), 15);
+    return (oct << 12) | (uint32_t(cx) << 8) | (uint32_t(cy) << 4) | uint32_t(cz);
+}
+
 // ---- kernels ---------------------------------------------------------------------------------
 struct BatchInfo { const uint32_t *pix_id, *pix_seed; uint32_t n_pix, spp_begin; };
 
@@ -291,7 +309,7 @@ struct BatchInfo { const uint32_t *pix_id, *pix_seed; uint32_t n_pix, spp_begin;
 // neighbouring pixels of one sample index, so the primary rays stay coherent and every state access is coalesced.
 // = SobolPathSampler::startPath + ReconstructionFilter::sample + PinholeCamera::sampleDirection + the analytic
 // part of the first TraceableScene::intersect.
-__global__ void __launch_bounds__(256) k_regen(DScene sc, PathState st, BatchInfo bi, uint32_t slot_base, uint32_t first_path, uint32_t m) {
+__global__ void __launch_bounds__(256) k_regen(DScene sc, PathState st, BatchInfo bi, uint32_t slot_base, uint32_t first_path, uint32_t m, uint32_t *order) {
     uint32_t j = blockIdx.x*blockDim.x + threadIdx.x;
     if (j >= m) return;
     uint32_t i = slot_base + j;
@@ -318,7 +336,9 @@ __global__ void __launch_bounds__(256) k_regen(DScene sc, PathState st, BatchInf
     st.info[i] = smp.dimension | F_WAS_SPECULAR | F_ALIVE;
     st.pid[i] = path;
     Hit h = analytic_closest(sc, sc.cam.pos, d, 1e-4f, INFINITY);
-    st.ht[i] = h.t; st.hu[i] = h.u; st.hv[i] = h.v; st.hid[i] = h.id;
+    st.ra[i] = make_float4(sc.cam.pos.x, sc.cam.pos.y, sc.cam.pos.z, 1e-4f); st.rb[i] = make_float4(d.x, d.y, d.z, 0.0f);
+    st.h4[i] = pack_hit(h);
+    order[i] = i;                    // new camera paths are already coherent: visited in slot order, after the sorted survivors
 }
 
 TGB_D void count_block(unsigned long long *rays, unsigned long long *hits, bool valid, bool hit) {
@@ -332,18 +352,19 @@ TGB_D void count_block(unsigned long long *rays, unsigned long long *hits, bool 
 // TraceableScene::intersect for the path rays: the analytic part of the query was done by the kernel that made the
 // ray (k_raygen / k_accum); this kernel walks the triangle BVH, K rays per lane.
 struct PathRayPolicy {
-    PathState st; uint32_t s;
+    PathState st; const uint32_t *order; uint32_t s;
     TGB_D bool fetch(uint32_t i, V3 &o, V3 &d, float &tnear, Hit &h, bool &any) {
-        s = i;
-        o = v3(st.ox[s], st.oy[s], st.oz[s]); d = v3(st.dx[s], st.dy[s], st.dz[s]); tnear = st.tmin[s];
-        h.t = st.ht[s]; h.u = st.hu[s]; h.v = st.hv[s]; h.id = st.hid[s]; any = false;
+        s = order[i];
+        float4 a = st.ra[s], b = st.rb[s];
+        o = v3(a.x, a.y, a.z); tnear = a.w; d = v3(b.x, b.y, b.z);
+        h = unpack_hit(st.h4[s]); any = false;
         return true;
     }
-    TGB_D void finish(const Hit &h) { st.ht[s] = h.t; st.hu[s] = h.u; st.hv[s] = h.v; st.hid[s] = h.id; }
+    TGB_D void finish(const Hit &h) { st.h4[s] = pack_hit(h); }
 };
-__global__ void __launch_bounds__(kTraceBlock, TGB_MINB) k_trace(DScene sc, PathState st, uint32_t n, uint32_t K) {
+__global__ void __launch_bounds__(kTraceBlock, TGB_MINB) k_trace(DScene sc, PathState st, const uint32_t *order, uint32_t n, uint32_t K) {
     extern __shared__ int smem_stack[];
-    PathRayPolicy pol; pol.st = st; pol.s = 0;
+    PathRayPolicy pol; pol.st = st; pol.order = order; pol.s = 0;
     bvh_traverse_multi(sc, smem_stack, pol, n, K);
 }
 
@@ -392,7 +413,7 @@ __global__ void __launch_bounds__(128) k_shade(DScene sc, PathState st, BatchInf
     bool qn = false, qm = false, qn_any = false, qm_any = false;
     uint32_t s = 0;
     // one path query (TraceableScene::intersect) was completed for every slot in the queue
-    count_block(&ctr->rays, &ctr->hits, valid, valid && st.hid[valid ? i : 0] != HID_MISS);
+    count_block(&ctr->rays, &ctr->hits, valid, valid && __float_as_int(st.h4[valid ? i : 0].w) != HID_MISS);
     if (valid) {
         s = i;
         uint32_t info = st.info[s];
@@ -400,7 +421,7 @@ __global__ void __launch_bounds__(128) k_shade(DScene sc, PathState st, BatchInf
         bool wasSpecular = (info & F_WAS_SPECULAR) != 0;
         V3 o = v3(st.ox[s], st.oy[s], st.oz[s]), d = v3(st.dx[s], st.dy[s], st.dz[s]);
         V3 thr = v3(st.tx[s], st.ty[s], st.tz[s]);
-        Hit h; h.t = st.ht[s]; h.u = st.hu[s]; h.v = st.hv[s]; h.id = st.hid[s];
+        Hit h = unpack_hit(st.h4[s]);
         const tgb_settings &set = sc.set;
         uint32_t flags = 0;
 
@@ -698,7 +719,7 @@ __global__ void __launch_bounds__(kTraceBlock, TGB_MINB) k_shadow_bvh(DScene sc,
 // NaN guards of traceSample (PathTracer.cpp:119-122,130), store finished samples, and MOVE the survivors' persistent
 // state to the front of the other state buffer (physical compaction: all later accesses are coalesced, no slot
 // indirection).  The survivors' next ray gets the analytic part of its TraceableScene::intersect here.
-__global__ void __launch_bounds__(256) k_accum(DScene sc, PathState st, PathState dst, uint32_t n, uint32_t *next_count) {
+__global__ void __launch_bounds__(256) k_accum(DScene sc, PathState st, PathState dst, uint32_t n, uint32_t *next_count, uint32_t *keys, uint32_t *hist) {
     uint32_t s = blockIdx.x*blockDim.x + threadIdx.x;
     bool valid = s < n;
     bool alive = false; uint32_t info = 0; V3 em = v3s(0.0f);
@@ -740,9 +761,39 @@ __global__ void __launch_bounds__(256) k_accum(DScene sc, PathState st, PathStat
             dst.pcg[t] = st.pcg[s]; dst.pid[t] = st.pid[s];
             dst.info[t] = (info & ~(F_HAS_NEE | F_HAS_SURF | F_ALIVE | F_FINAL_CHECK)) | F_ALIVE;
             Hit h = analytic_closest(sc, o, d, tmin, INFINITY);
-            dst.ht[t] = h.t; dst.hu[t] = h.u; dst.hv[t] = h.v; dst.hid[t] = h.id;
+            dst.ra[t] = make_float4(o.x, o.y, o.z, tmin); dst.rb[t] = make_float4(d.x, d.y, d.z, 0.0f); dst.h4[t] = pack_hit(h);
+            uint32_t key = ray_bin(sc, o, d);
+            keys[t] = key;
+            atomicAdd(hist + key, 1u);
         }
     }
+}
+
+// Counting sort of the survivors' slot indices by ray-coherence key: exclusive scan of the histogram (one block) ...
+__global__ void __launch_bounds__(1024) k_bin_scan(uint32_t *hist) {
+    __shared__ uint32_t part[1024];
+    const uint32_t per = kBins/1024u;
+    uint32_t t = threadIdx.x, sum = 0;
+    uint32_t local[per];
+#pragma unroll
+    for (uint32_t i = 0; i < per; ++i) { local[i] = hist[t*per + i]; sum += local[i]; }
+    part[t] = sum;
+    __syncthreads();
+    for (uint32_t off = 1; off < 1024u; off <<= 1) {
+        uint32_t v = t >= off ? part[t - off] : 0u;
+        __syncthreads();
+        part[t] += v;
+        __syncthreads();
+    }
+    uint32_t base = part[t] - sum;
+#pragma unroll
+    for (uint32_t i = 0; i < per; ++i) { hist[t*per + i] = base; base += local[i]; }
+}
+// ... and scatter of the slot indices (4 bytes each) to their sorted positions.
+__global__ void __launch_bounds__(256) k_bin_scatter(const uint32_t *keys, uint32_t *cursor, const uint32_t *n_alive, uint32_t *order) {
+    uint32_t t = blockIdx.x*blockDim.x + threadIdx.x;
+    if (t >= *n_alive) return;
+    order[atomicAdd(cursor + keys[t], 1u)] = t;
 }
 
 // OutputBuffer::addSample (cameras/OutputBuffer.hpp:104-132): running mean in sample order, NaN/Inf samples dropped
