@@ -33,6 +33,10 @@ sys.path.insert(0, ROOT)
 
 W, H = 1920, 1080
 ALG_BYTES_PER_QUERY = 48
+CONFIGS = {
+    "c1": {"res": (1920, 1080), "label": "C1: Cornell box + 868,480-tri Lambert mesh (procedural dragon stand-in), 1920x1080, path_tracer, max_bounces 64, Sobol"},
+    "c3": {"res": (3840, 2160), "label": "C3: 12,544,000-triangle instanced forest (490 trees x 2 masters, flattened), Lambert + rough plastic + HDR sky, 3840x2160, max_bounces 16, Sobol"},
+}
 
 
 def _clock_sampler(stop, out, idx):
@@ -66,9 +70,14 @@ def _scene_dir():
     return d
 
 
-def make_scene(spp):
+def make_scene(spp, config="c1"):
     from tungsten_b200 import synth
     d = _scene_dir()
+    if config == "c3":
+        path = os.path.join(d, "forest10m.json")
+        if not os.path.exists(path):
+            synth.instanced_forest(d, "forest10m", n_instances=490, tree_subdiv=5, res=CONFIGS["c3"]["res"], spp=spp, extent=40.0)
+        return path
     path = os.path.join(d, "cornell_dragon.json")
     marker = os.path.join(d, "cornell_dragon_body.wo3")
     if not (os.path.exists(path) and os.path.exists(marker)):
@@ -148,10 +157,17 @@ def main():
     ap.add_argument("--spp-per-step", type=int, default=64)
     ap.add_argument("--ref-spp", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--config", default="c1", choices=sorted(CONFIGS))
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    global W, H
+    W, H = CONFIGS[args.config]["res"]
     if args.impl == "reference":
+        if args.config != "c1":
+            if rank == 0:
+                print(json.dumps({"impl": "reference", "unavailable": "the stock reference cannot load mesh-instanced scenes from JSON (Instance::loadResources never loads its masters)"}))
+            return
         return bench_reference(args, rank, world)
 
     import numpy as np
@@ -165,10 +181,10 @@ def main():
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
-    scene_path = make_scene(1024) if rank == 0 else None
+    scene_path = make_scene(1024, args.config) if rank == 0 else None
     if world > 1:
         dist.barrier()
-        scene_path = make_scene(1024)
+        scene_path = make_scene(1024, args.config)
     fs = scene.load_scene(scene_path)
     ctx = lib.Context(fs, device=local_rank)
     info = ctx.scene_info()
@@ -256,7 +272,7 @@ def main():
 
     if rank == 0:
         cpu = None
-        if world == 1 and not args.no_cpu_baseline:
+        if world == 1 and not args.no_cpu_baseline and args.config == "c1":
             cores = os.cpu_count() or 1
             r = run_reference_binary(scene_path, args.ref_spp, cores)
             if r is not None:
@@ -266,8 +282,7 @@ def main():
             "metric": "Msamples/sec (paths x spp)", "value": value, "unit": "Msamples/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3*wall/args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "C1: Cornell box + 868,480-tri Lambert mesh (procedural dragon stand-in), 1920x1080, path_tracer, "
-                                   "max_bounces 64, Sobol, %d spp per step (x%d steps = %d spp)" % (spp_step, args.steps, spp_step*args.steps),
+            "config": {"workload": CONFIGS[args.config]["label"] + ", %d spp per step (x%d steps = %d spp)" % (spp_step, args.steps, spp_step*args.steps),
                        "tiles": "16x16, round-robin over %d rank(s)" % world, "paths_in_flight": info["capacity"],
                        "triangles": info["n_tris"], "bvh_nodes": info["n_nodes"], "geom_bytes": info["geom_bytes"],
                        "l2": "per-batch path state (%.0f MB) and geometry exceed the 126 MB L2; no explicit flush" % (info["capacity"]*230/1e6)},
@@ -275,7 +290,7 @@ def main():
             "device_ms": dev_ms_max, "gpu_launches": int(tot_launches),
             "e2e": {"value": e2e_value, "unit": "Msamples/s", "h2d_bytes_per_step": fb_bytes, "d2h_bytes_per_step": fb_bytes,
                     "steps": e2e_steps},
-            "roofline": {"bound": "hbm", "kernel": "k_trace (closest-hit BVH2 traversal of path rays)",
+            "roofline": {"bound": "hbm", "kernel": "k_trace (closest-hit 4-ary BVH traversal of path rays)",
                          "achieved": trace_gbs, "peak": peak, "unit": "GB/s", "frac": trace_gbs/peak, "traffic": traffic,
                          "peak_source": peak_src, "alg_bytes_per_query": ALG_BYTES_PER_QUERY,
                          "queries": int(st.path_rays), "kernel_ms": st.trace_ms, "launches": int(st.trace_launches),

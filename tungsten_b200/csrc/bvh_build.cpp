@@ -1,4 +1,4 @@
-// Binned-SAH BVH2 builder (host, multi-threaded).  See bvh_build.h for what it replaces.
+// Binned-SAH builder (host, multi-threaded) + collapse to the 4-ary device layout.  See bvh_build.h for what it replaces.
 #include "bvh_build.h"
 
 #include <algorithm>

@@ -1,6 +1,6 @@
 // Wavefront kernels of the B200 path tracer (sm_100a).  One thread per path / per ray query.
 //   k_raygen  : SobolPathSampler::startPath + ReconstructionFilter::sample + PinholeCamera::sampleDirection
-//   k_trace   : TraceableScene::intersect  (closest hit; analytic prims + BVH2 over all mesh triangles)
+//   k_trace   : TraceableScene::intersect  (closest hit; analytic prims + 4-ary BVH over all mesh triangles)
 //   k_shade   : makeLocalScatterEvent + handleSurface (NEE/MIS query generation, emission, BSDF sample, RR)
 //   k_shadow  : attenuatedEmission/generalizedShadowRay for the NEE and MIS queries (same traversal + epilogue)
 //   k_accum   : folds the bounce's direct-light estimate into the path, NaN guards, compacts survivors
