@@ -246,8 +246,8 @@ def main():
         dev_ms_max = dev_ms
     value = tot_samples/wall/1e6
     peak, peak_src = hbm_peak()
-    trace_gbs = (st.path_rays*ALG_BYTES_PER_QUERY/1e9)/(st.trace_ms/1e3) if st.trace_ms > 0 else 0.0
-    shadow_gbs = (st.shadow_rays*ALG_BYTES_PER_QUERY/1e9)/(st.shadow_ms/1e3) if st.shadow_ms > 0 else 0.0
+    trace_gbs = (st.path_rays_traversed*ALG_BYTES_PER_QUERY/1e9)/(st.trace_ms/1e3) if st.trace_ms > 0 else 0.0
+    shadow_gbs = (st.shadow_rays_traversed*ALG_BYTES_PER_QUERY/1e9)/(st.shadow_ms/1e3) if st.shadow_ms > 0 else 0.0
     traffic = None
     tp = os.path.join(ROOT, "profiles", "k_trace_dram_bytes_per_launch.json")
     if os.path.exists(tp):
@@ -293,9 +293,9 @@ def main():
             "roofline": {"bound": "hbm", "kernel": "k_trace (closest-hit 4-ary BVH traversal of path rays)",
                          "achieved": trace_gbs, "peak": peak, "unit": "GB/s", "frac": trace_gbs/peak, "traffic": traffic,
                          "peak_source": peak_src, "alg_bytes_per_query": ALG_BYTES_PER_QUERY,
-                         "queries": int(st.path_rays), "kernel_ms": st.trace_ms, "launches": int(st.trace_launches),
-                         "mqueries_per_s": st.path_rays/st.trace_ms/1e3 if st.trace_ms > 0 else 0.0,
-                         "k_shadow": {"achieved": shadow_gbs, "frac": shadow_gbs/peak, "queries": int(st.shadow_rays), "kernel_ms": st.shadow_ms},
+                         "queries": int(st.path_rays_traversed), "path_rays_total": int(st.path_rays), "kernel_ms": st.trace_ms, "launches": int(st.trace_launches),
+                         "mqueries_per_s": st.path_rays_traversed/st.trace_ms/1e3 if st.trace_ms > 0 else 0.0,
+                         "k_shadow": {"achieved": shadow_gbs, "frac": shadow_gbs/peak, "queries": int(st.shadow_rays_traversed), "shadow_rays_total": int(st.shadow_rays), "kernel_ms": st.shadow_ms},
                          "note": "traversal is latency/divergence bound with an L2-resident BVH; see DESIGN.md section 6"},
             "cpu_baseline": cpu,
             "clocks": _summarise_clocks(clk),

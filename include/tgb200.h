@@ -158,6 +158,8 @@ typedef struct tgb_stats {
     uint64_t shadow_rays;       /* queries issued by k_shadow (NEE + MIS)                           */
     double   shadow_ms;         /* CUDA-event time inside k_shadow, profiling mode only             */
     uint64_t shadow_launches;
+    uint64_t path_rays_traversed;    /* path rays that reached k_trace (the rest miss the BVH's top-level cut) */
+    uint64_t shadow_rays_traversed;  /* queries that reached k_shadow_bvh (not resolved by k_shadow_prep)         */
 } tgb_stats;
 
 typedef struct tgb_ctx tgb_ctx;

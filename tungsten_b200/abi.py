@@ -87,7 +87,8 @@ class Hit(C.Structure):
 class Stats(C.Structure):
     _fields_ = [("samples", u64), ("rays", u64), ("hits", u64), ("kernel_launches", u64),
                 ("trace_ms", C.c_double), ("trace_launches", u64), ("total_ms", C.c_double),
-                ("path_rays", u64), ("shadow_rays", u64), ("shadow_ms", C.c_double), ("shadow_launches", u64)]
+                ("path_rays", u64), ("shadow_rays", u64), ("shadow_ms", C.c_double), ("shadow_launches", u64),
+                ("path_rays_traversed", u64), ("shadow_rays_traversed", u64)]
 
 
 EXPORTS = [

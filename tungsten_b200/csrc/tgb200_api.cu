@@ -405,6 +405,27 @@ int upload_scene(tgb_ctx *c, const tgb_scene_desc *d) {
         sc.bin_lo = v3(lo[0], lo[1], lo[2]);
         sc.bin_inv = v3(16.0f/(hi[0] - lo[0]), 16.0f/(hi[1] - lo[1]), 16.0f/(hi[2] - lo[2]));
     }
+    sc.n_cut = 0;
+    if (!bvh.nodes.empty()) {
+        // top-level cut: start from the root's children, keep splitting the inner child with the largest surface area
+        struct CutBox { float lo[3], hi[3]; int32_t link; };
+        auto child = [&](const Node4 &nd, int k) { CutBox b; for (int a = 0; a < 3; ++a) { b.lo[a] = nd.f[8*a + k]; b.hi[a] = nd.f[8*a + 4 + k]; } b.link = nd.link[k]; return b; };
+        auto area = [](const CutBox &b) { float e[3] = {b.hi[0] - b.lo[0], b.hi[1] - b.lo[1], b.hi[2] - b.lo[2]}; return e[0]*e[1] + e[1]*e[2] + e[2]*e[0]; };
+        std::vector<CutBox> cut;
+        for (int k = 0; k < 4; ++k) if (bvh.nodes[0].link[k] != kEmptyLink) cut.push_back(child(bvh.nodes[0], k));
+        while (true) {
+            int best = -1;
+            for (size_t i = 0; i < cut.size(); ++i) if (cut[i].link >= 0 && (best < 0 || area(cut[i]) > area(cut[size_t(best)]))) best = int(i);
+            if (best < 0) break;
+            const Node4 &nd = bvh.nodes[size_t(cut[size_t(best)].link)];
+            int kids = 0; for (int k = 0; k < 4; ++k) kids += nd.link[k] != kEmptyLink;
+            if (cut.size() - 1 + size_t(kids) > 16) break;
+            cut.erase(cut.begin() + best);
+            for (int k = 0; k < 4; ++k) if (nd.link[k] != kEmptyLink) cut.push_back(child(nd, k));
+        }
+        sc.n_cut = int(cut.size());
+        for (int i = 0; i < sc.n_cut; ++i) for (int a = 0; a < 3; ++a) { sc.cut[2*a][i] = cut[size_t(i)].lo[a]; sc.cut[2*a + 1][i] = cut[size_t(i)].hi[a]; }
+    }
     if (3*bvh.max_depth + 2 > uint32_t(kStackSize)) return fail(c, TGB_ERR_UNSUPPORTED, "BVH depth %u exceeds the traversal stack", bvh.max_depth);
     c->bvh_depth = bvh.max_depth; c->n_tris = uint32_t(btris.size()); c->bvh_sah = bvh.sah_cost;
     std::vector<float4> tri_isect(3*btris.size());
@@ -467,7 +488,7 @@ int alloc_wavefront(tgb_ctx *c, uint32_t capacity) {
     if ((rc = dev_alloc(c, &c->queue_b, capacity))) return rc;
     if ((rc = dev_alloc(c, &c->free_list, capacity))) return rc;
     if ((rc = dev_alloc(c, &c->bin_keys, capacity))) return rc;
-    if ((rc = dev_alloc(c, &c->bin_hist, size_t(kBins)))) return rc;
+    if ((rc = dev_alloc(c, &c->bin_hist, size_t(kBins) + 2))) return rc;     // + cull bin + number of sorted survivors
     if ((rc = dev_alloc(c, &c->squeue, size_t(capacity)*2))) return rc;
     if ((rc = dev_alloc(c, &c->squeue2, size_t(capacity)*2))) return rc;
     if ((rc = dev_alloc(c, &c->ss.qt, size_t(capacity)*2))) return rc;
@@ -549,7 +570,7 @@ int render_device(tgb_ctx *c, uint32_t spp_begin, uint32_t spp_count) {
     const DScene &sc = c->sc;
     CU(cudaEventRecord(c->ev0, c->stream));
     uint64_t launches = 0;
-    float trace_ms = 0.0f, shadow_ms = 0.0f; uint64_t trace_launches = 0;
+    float trace_ms = 0.0f, shadow_ms = 0.0f; uint64_t trace_launches = 0, traversed = 0, shadow_traversed = 0;
     const bool has_bvh = sc.n_nodes != 0;
     // a step's finished radiances are kept per path (12 B each) until k_resolve folds them in sample order;
     // split the sample range so that this buffer stays below ~6 GB and path ids fit 32 bits
@@ -565,7 +586,8 @@ int render_device(tgb_ctx *c, uint32_t spp_begin, uint32_t spp_count) {
         PathState cur = c->st, nxt = c->st2;
         cur.rx = nxt.rx = c->st.rx; cur.ry = nxt.ry = c->st.ry; cur.rz = nxt.rz = c->st.rz;
         uint32_t *cs = c->counts + 2;                 // counts: [0] survivors, [2] shadow queries, [3] compacted shadow queries
-        uint32_t n_alive = 0;
+        uint32_t n_alive = 0, n_sorted = 0;
+        CU(cudaMemsetAsync(c->bin_hist + kBins + 1, 0, sizeof(uint32_t), c->stream));
         for (uint32_t iter = 0;; ++iter) {
             if (c->abort_flag.load()) { cudaStreamSynchronize(c->stream); return fail(c, TGB_ERR_ABORTED, "render aborted"); }
             // refill: survivors occupy slots [0, n_alive) of `cur`; new camera paths are appended behind them
@@ -580,7 +602,7 @@ int render_device(tgb_ctx *c, uint32_t spp_begin, uint32_t spp_count) {
             if (c->profiling) CU(cudaEventRecord(c->evt0, c->stream));
             if (has_bvh) {
                 uint32_t K = rays_per_lane(n);
-                k_trace<<<blocks(n, kTraceBlock*K), kTraceBlock, kTraceSmem, c->stream>>>(sc, cur, c->queue_a, n, K); launches++;
+                k_trace<<<blocks(n, kTraceBlock*K), kTraceBlock, kTraceSmem, c->stream>>>(sc, cur, c->queue_a, c->bin_hist + kBins + 1, n_alive, n, K); launches++;
             }
             if (c->profiling) CU(cudaEventRecord(c->evt1, c->stream));
             k_shade<<<blocks(n, 128), 128, 0, c->stream>>>(sc, cur, bi, n, c->squeue, cs, c->ctr); launches++;
@@ -591,10 +613,10 @@ int render_device(tgb_ctx *c, uint32_t spp_begin, uint32_t spp_count) {
                 k_shadow_bvh<<<blocks(2*n, kTraceBlock*K), kTraceBlock, kTraceSmem, c->stream>>>(sc, cur, c->ss, c->squeue2, cs + 1, c->ctr, K); launches++;
             }
             if (c->profiling) CU(cudaEventRecord(c->evs1, c->stream));
-            CU(cudaMemsetAsync(c->bin_hist, 0, kBins*sizeof(uint32_t), c->stream));
+            CU(cudaMemsetAsync(c->bin_hist, 0, (kBins + 1)*sizeof(uint32_t), c->stream));
             k_accum<<<blocks(n, 256), 256, 0, c->stream>>>(sc, cur, nxt, n, c->counts, c->bin_keys, c->bin_hist); launches++;
             if (has_bvh) {          // visiting order of the next k_trace: survivors sorted by ray-coherence key
-                k_bin_scan<<<1, 1024, 0, c->stream>>>(c->bin_hist); launches++;
+                k_bin_scan<<<1, 1024, 0, c->stream>>>(c->bin_hist, c->bin_hist + kBins + 1, c->counts + 1); launches++;
                 k_bin_scatter<<<blocks(n, 256), 256, 0, c->stream>>>(c->bin_keys, c->bin_hist, c->counts, c->queue_a); launches++;
             }
             CU(cudaMemcpyAsync(c->h_counts, c->counts, 4*sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
@@ -603,8 +625,9 @@ int render_device(tgb_ctx *c, uint32_t spp_begin, uint32_t spp_count) {
                 float ms = 0.0f; cudaEventElapsedTime(&ms, c->evt0, c->evt1); trace_ms += ms; trace_launches++;
                 cudaEventElapsedTime(&ms, c->evs0, c->evs1); shadow_ms += ms;
             }
-            if (getenv("TGB_TRACE_BOUNCES")) fprintf(stderr, "iter %u n %u (new %u) shadow %u/%u -> alive %u\n", iter, n, m, c->h_counts[3], c->h_counts[2], c->h_counts[0]);
-            n_alive = c->h_counts[0];
+            if (getenv("TGB_TRACE_BOUNCES")) { uint32_t ns = 0; cudaMemcpy(&ns, c->bin_hist + kBins + 1, 4, cudaMemcpyDeviceToHost); fprintf(stderr, "iter %u n %u (new %u) shadow %u/%u -> alive %u (to traverse %u)\n", iter, n, m, c->h_counts[3], c->h_counts[2], c->h_counts[0], ns); }
+            if (has_bvh) { traversed += n_sorted + m; shadow_traversed += c->h_counts[3]; }
+            n_alive = c->h_counts[0]; n_sorted = c->h_counts[1];
             std::swap(cur, nxt);
             if (iter > (1u << 24)) return fail(c, TGB_ERR_CUDA, "wavefront loop did not terminate");
         }
@@ -621,6 +644,7 @@ int render_device(tgb_ctx *c, uint32_t spp_begin, uint32_t spp_count) {
     c->stats.rays = c->h_ctr->rays + c->h_ctr->shadow_rays; c->stats.hits = c->h_ctr->hits + c->h_ctr->shadow_hits;
     c->stats.shadow_ms += shadow_ms; c->stats.shadow_launches += trace_launches;
     c->stats.kernel_launches += launches;
+    c->stats.path_rays_traversed += traversed; c->stats.shadow_rays_traversed += shadow_traversed;
     c->stats.total_ms += ms; c->stats.trace_ms += trace_ms; c->stats.trace_launches += trace_launches;
     return TGB_OK;
 }

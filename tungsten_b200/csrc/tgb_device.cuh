@@ -121,6 +121,9 @@ struct DScene {
     // global id -> primitive, shading records by global id (4 x float4 each)
     const float4 *tri_isect; const uint32_t *tri_global; const uint32_t *tri_prim; const float4 *tri_shade;
     const float4 *nodes; uint32_t n_nodes; uint32_t n_tris;
+    // "cut": <= 16 boxes of the BVH's top levels that together cover every triangle (same padded boxes the nodes hold).
+    // A ray that misses all of them is answered by the kernel that creates it and never reaches a traversal kernel.
+    int n_cut; float cut[6][16];        // lo.x, hi.x, lo.y, hi.y, lo.z, hi.z
     V3 bin_lo, bin_inv;         // ray-binning grid over the scene bounds: cell = (o - bin_lo)*bin_inv, 16 cells per axis
     const uint32_t *sobol;      // 1024 x 32 direction matrices
 };

@@ -203,6 +203,27 @@ TGB_D void bvh_traverse(const DScene &sc, int *smem_stack, V3 o, V3 d, float tne
     }
 }
 
+// Coherent pre-test of a new ray against the BVH's top-level cut (DScene::cut), with the arithmetic of the node test
+// above: false means the traversal would cull every subtree, i.e. its answer is the ray's analytic hit.
+TGB_D bool mesh_cut_hit(const DScene &sc, V3 o, V3 d, float tnear, float tfar) {
+    const float ooeps = 1e-30f;
+    const float idx = 1.0f/(fabsf(d.x) > ooeps ? d.x : copysignf(ooeps, d.x));
+    const float idy = 1.0f/(fabsf(d.y) > ooeps ? d.y : copysignf(ooeps, d.y));
+    const float idz = 1.0f/(fabsf(d.z) > ooeps ? d.z : copysignf(ooeps, d.z));
+    const float oodx = o.x*idx, oody = o.y*idy, oodz = o.z*idz;
+    bool hit = false;
+#pragma unroll                              // static indices: the boxes are read straight from the kernel parameters
+    for (int k = 0; k < 16; ++k) {
+        float ax = __fmaf_rn(sc.cut[0][k], idx, -oodx), bx = __fmaf_rn(sc.cut[1][k], idx, -oodx);
+        float ay = __fmaf_rn(sc.cut[2][k], idy, -oody), by = __fmaf_rn(sc.cut[3][k], idy, -oody);
+        float az = __fmaf_rn(sc.cut[4][k], idz, -oodz), bz = __fmaf_rn(sc.cut[5][k], idz, -oodz);
+        float tmn = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fmaxf(fminf(az, bz), tnear));
+        float tmx = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fminf(fmaxf(az, bz), tfar));
+        hit = hit || (k < sc.n_cut && tmn <= tmx);
+    }
+    return hit;
+}
+
 // Policy wrapper kept for the three users (path rays, shadow queries, parity hook): one ray per thread.
 template <class P>
 TGB_D void bvh_traverse_multi(const DScene &sc, int *smem_stack, P &pol, uint32_t n, uint32_t /*K*/) {
@@ -352,8 +373,11 @@ TGB_D void count_block(unsigned long long *rays, unsigned long long *hits, bool 
 // TraceableScene::intersect for the path rays: the analytic part of the query was done by the kernel that made the
 // ray (k_raygen / k_accum); this kernel walks the triangle BVH, K rays per lane.
 struct PathRayPolicy {
-    PathState st; const uint32_t *order; uint32_t s;
+    PathState st; const uint32_t *order; const uint32_t *n_sorted; uint32_t n_surv, n_all; uint32_t s;
     TGB_D bool fetch(uint32_t i, V3 &o, V3 &d, float &tnear, Hit &h, bool &any) {
+        // order[] = [survivors to trace, key order | unused (survivors that miss the BVH cut) | new camera paths]
+        uint32_t ns = *n_sorted;
+        if (i >= ns) { i += n_surv - ns; if (i >= n_all) return false; }
         s = order[i];
         float4 a = st.ra[s], b = st.rb[s];
         o = v3(a.x, a.y, a.z); tnear = a.w; d = v3(b.x, b.y, b.z);
@@ -362,9 +386,10 @@ struct PathRayPolicy {
     }
     TGB_D void finish(const Hit &h) { st.h4[s] = pack_hit(h); }
 };
-__global__ void __launch_bounds__(kTraceBlock, TGB_MINB) k_trace(DScene sc, PathState st, const uint32_t *order, uint32_t n, uint32_t K) {
+__global__ void __launch_bounds__(kTraceBlock, TGB_MINB) k_trace(DScene sc, PathState st, const uint32_t *order, const uint32_t *n_sorted,
+                                                                 uint32_t n_surv, uint32_t n, uint32_t K) {
     extern __shared__ int smem_stack[];
-    PathRayPolicy pol; pol.st = st; pol.order = order; pol.s = 0;
+    PathRayPolicy pol; pol.st = st; pol.order = order; pol.n_sorted = n_sorted; pol.n_surv = n_surv; pol.n_all = n; pol.s = 0;
     bvh_traverse_multi(sc, smem_stack, pol, n, K);
 }
 
@@ -667,10 +692,10 @@ __global__ void __launch_bounds__(256) k_shadow_prep(DScene sc, PathState st, Sh
         if (any) {
             float tfar = mis ? st.mpb[s] : st.ndist[s];
             blocked = analytic_any(sc, p, d, 5e-4f, tfar, li);
-            if (!blocked) { if (sc.n_nodes == 0) shadow_store_any(st, s, mis); else keep = true; }
+            if (!blocked) { if (!mesh_cut_hit(sc, p, d, 5e-4f, tfar)) shadow_store_any(st, s, mis); else keep = true; }
         } else {
             h = analytic_closest(sc, p, d, 5e-4f, INFINITY);
-            if (sc.n_nodes == 0) { blocked = h.id != HID_MISS; shadow_resolve_closest(sc, st, s, mis, li, p, d, h); }
+            if (!mesh_cut_hit(sc, p, d, 5e-4f, h.t)) { blocked = h.id != HID_MISS; shadow_resolve_closest(sc, st, s, mis, li, p, d, h); }
             else keep = true;
         }
     }
@@ -762,15 +787,15 @@ __global__ void __launch_bounds__(256) k_accum(DScene sc, PathState st, PathStat
             dst.info[t] = (info & ~(F_HAS_NEE | F_HAS_SURF | F_ALIVE | F_FINAL_CHECK)) | F_ALIVE;
             Hit h = analytic_closest(sc, o, d, tmin, INFINITY);
             dst.ra[t] = make_float4(o.x, o.y, o.z, tmin); dst.rb[t] = make_float4(d.x, d.y, d.z, 0.0f); dst.h4[t] = pack_hit(h);
-            uint32_t key = ray_bin(sc, o, d);
+            uint32_t key = mesh_cut_hit(sc, o, d, tmin, h.t) ? ray_bin(sc, o, d) : kBins;       // kBins: nothing to traverse
             keys[t] = key;
-            atomicAdd(hist + key, 1u);
+            if (key != kBins) atomicAdd(hist + key, 1u);
         }
     }
 }
 
 // Counting sort of the survivors' slot indices by ray-coherence key: exclusive scan of the histogram (one block) ...
-__global__ void __launch_bounds__(1024) k_bin_scan(uint32_t *hist) {
+__global__ void __launch_bounds__(1024) k_bin_scan(uint32_t *hist, uint32_t *n_sorted, uint32_t *n_sorted_host) {
     __shared__ uint32_t part[1024];
     const uint32_t per = kBins/1024u;
     uint32_t t = threadIdx.x, sum = 0;
@@ -788,12 +813,14 @@ __global__ void __launch_bounds__(1024) k_bin_scan(uint32_t *hist) {
     uint32_t base = part[t] - sum;
 #pragma unroll
     for (uint32_t i = 0; i < per; ++i) { hist[t*per + i] = base; base += local[i]; }
+    if (t == 1023u) { *n_sorted = base; *n_sorted_host = base; }      // the culled survivors follow the sorted ones
 }
 // ... and scatter of the slot indices (4 bytes each) to their sorted positions.
 __global__ void __launch_bounds__(256) k_bin_scatter(const uint32_t *keys, uint32_t *cursor, const uint32_t *n_alive, uint32_t *order) {
     uint32_t t = blockIdx.x*blockDim.x + threadIdx.x;
     if (t >= *n_alive) return;
-    order[atomicAdd(cursor + keys[t], 1u)] = t;
+    uint32_t key = keys[t];
+    if (key != kBins) order[atomicAdd(cursor + key, 1u)] = t;     // culled survivors are not visited: no entry needed
 }
 
 // OutputBuffer::addSample (cameras/OutputBuffer.hpp:104-132): running mean in sample order, NaN/Inf samples dropped
