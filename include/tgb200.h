@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define TGB200_ABI_VERSION 1
+#define TGB200_ABI_VERSION 2
 
 /* ---- return codes -------------------------------------------------------------------------- */
 enum {
@@ -54,7 +54,8 @@ typedef struct tgb_texture {
 enum {
     TGB_BSDF_NULL = 0, TGB_BSDF_LAMBERT = 1, TGB_BSDF_ROUGH_CONDUCTOR = 2,
     TGB_BSDF_ROUGH_DIELECTRIC = 3, TGB_BSDF_PLASTIC = 4, TGB_BSDF_ROUGH_PLASTIC = 5,
-    TGB_BSDF_SMOOTH_COAT = 6, TGB_BSDF_CONDUCTOR = 7, TGB_BSDF_DIELECTRIC = 8, TGB_BSDF_MIRROR = 9
+    TGB_BSDF_SMOOTH_COAT = 6, TGB_BSDF_CONDUCTOR = 7, TGB_BSDF_DIELECTRIC = 8, TGB_BSDF_MIRROR = 9,
+    TGB_BSDF_HAIR = 10          /* bsdfs/HairBcsdf.cpp; only on CURVES primitives                  */
 };
 enum { TGB_DIST_BECKMANN = 0, TGB_DIST_PHONG = 1, TGB_DIST_GGX = 2 };
 
@@ -69,6 +70,8 @@ typedef struct tgb_bsdf {
     float    sigma_a[3];        /* plastic / coat absorption                                       */
     int32_t  substrate;         /* SMOOTH_COAT: index of the substrate bsdf, else -1               */
     uint32_t enable_refraction; /* (rough) dielectric "enable_refraction"                          */
+    /* HAIR: sigma_a[] = HairBcsdf::_sigmaA as prepared (HairBcsdf.cpp:435-443), plus:              */
+    float    hair_scale_angle_deg, hair_roughness;
 } tgb_bsdf;
 
 /* ---- geometry ------------------------------------------------------------------------------- */
@@ -77,7 +80,9 @@ typedef struct tgb_bsdf {
 typedef struct tgb_vertex   { float pos[3]; float normal[3]; float uv[2]; } tgb_vertex;
 typedef struct tgb_triangle { uint32_t v0, v1, v2; int32_t material; } tgb_triangle;
 
-enum { TGB_PRIM_MESH = 0, TGB_PRIM_QUAD = 1, TGB_PRIM_CUBE = 2, TGB_PRIM_INFINITE_SPHERE = 3 };
+enum { TGB_PRIM_MESH = 0, TGB_PRIM_QUAD = 1, TGB_PRIM_CUBE = 2, TGB_PRIM_INFINITE_SPHERE = 3, TGB_PRIM_CURVES = 4 };
+/* Curves::CurveMode (primitives/Curves.cpp:20-25); "ribbon" is outside the hot path                 */
+enum { TGB_CURVE_CYLINDER = 0, TGB_CURVE_HALF_CYLINDER = 1, TGB_CURVE_BCSDF_CYLINDER = 2 };
 
 /* One entry per scene primitive, in the reference's Scene::primitives() order.                    */
 typedef struct tgb_primitive {
@@ -94,6 +99,12 @@ typedef struct tgb_primitive {
     float pos[3], rot[9], scale[3];
     /* INFINITE_SPHERE: rotation (row-major 3x3, InfiniteSphere::_rotTransform), sample flag        */
     uint32_t do_sample;
+    /* CURVES: quadratic B-spline nodes (x, y, z, width) in WORLD space as Curves::prepareForRender leaves
+     * them (Curves.cpp:572-587); segment k spans nodes curve_segments[k]-2 .. curve_segments[k], in the
+     * order prepareForRender emits them (after the `subsample` draw, :589-611); one bsdf slot.       */
+    const float    *curve_nodes;    uint32_t n_curve_nodes;
+    const uint32_t *curve_segments; uint32_t n_curve_segments;
+    uint32_t curve_mode;        /* TGB_CURVE_*                                                      */
 } tgb_primitive;
 
 /* ---- camera (reference: cameras/PinholeCamera.cpp:28-35,70-86; Camera.cpp:44-68) ------------ */
@@ -139,8 +150,8 @@ typedef struct tgb_tile { uint32_t x, y, w, h; uint32_t sampler_seed; } tgb_tile
 typedef struct tgb_ray { float o[3]; float d[3]; float tmin, tmax; } tgb_ray;
 typedef struct tgb_hit {
     int32_t  primitive;         /* index into primitives[], -1 = miss                               */
-    int32_t  prim_id;           /* triangle index within the mesh (0 for quad/cube)                 */
-    float    t, u, v;
+    int32_t  prim_id;           /* triangle index within the mesh / segment index within the curves (0 for quad/cube) */
+    float    t, u, v;           /* curves: u = position along the segment, v = interpolated width   */
     uint32_t backside;
 } tgb_hit;
 

@@ -5,16 +5,17 @@ sizes against the values the library itself reports.
 """
 import ctypes as C
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 TGB_OK, TGB_ERR_INVALID, TGB_ERR_UNSUPPORTED, TGB_ERR_NO_DEVICE, TGB_ERR_CUDA, TGB_ERR_ABORTED, TGB_ERR_OOM = \
     0, -1, -2, -3, -4, -5, -6
 
 TEX_CONSTANT, TEX_CHECKER, TEX_BITMAP = 0, 1, 2
 (BSDF_NULL, BSDF_LAMBERT, BSDF_ROUGH_CONDUCTOR, BSDF_ROUGH_DIELECTRIC, BSDF_PLASTIC, BSDF_ROUGH_PLASTIC,
- BSDF_SMOOTH_COAT, BSDF_CONDUCTOR, BSDF_DIELECTRIC, BSDF_MIRROR) = range(10)
+ BSDF_SMOOTH_COAT, BSDF_CONDUCTOR, BSDF_DIELECTRIC, BSDF_MIRROR, BSDF_HAIR) = range(11)
 DIST_BECKMANN, DIST_PHONG, DIST_GGX = 0, 1, 2
-PRIM_MESH, PRIM_QUAD, PRIM_CUBE, PRIM_INFINITE_SPHERE = 0, 1, 2, 3
+PRIM_MESH, PRIM_QUAD, PRIM_CUBE, PRIM_INFINITE_SPHERE, PRIM_CURVES = 0, 1, 2, 3, 4
+CURVE_CYLINDER, CURVE_HALF_CYLINDER, CURVE_BCSDF_CYLINDER = 0, 1, 2
 (FILTER_DIRAC, FILTER_BOX, FILTER_TENT, FILTER_GAUSSIAN, FILTER_MITCHELL, FILTER_CATMULL_ROM,
  FILTER_LANCZOS) = range(7)
 
@@ -30,7 +31,8 @@ class Texture(C.Structure):
 class Bsdf(C.Structure):
     _fields_ = [("type", u32), ("albedo_tex", i32), ("distribution", u32), ("roughness_tex", i32),
                 ("ior", f32), ("eta", F3), ("k", F3), ("thickness", f32), ("sigma_a", F3),
-                ("substrate", i32), ("enable_refraction", u32)]
+                ("substrate", i32), ("enable_refraction", u32),
+                ("hair_scale_angle_deg", f32), ("hair_roughness", f32)]
 
 
 class Vertex(C.Structure):
@@ -48,7 +50,10 @@ class Primitive(C.Structure):
                 ("smooth", u32), ("bsdf_first", u32), ("bsdf_count", u32),
                 ("base", F3), ("edge0", F3), ("edge1", F3),
                 ("pos", F3), ("rot", F9), ("scale", F3),
-                ("do_sample", u32)]
+                ("do_sample", u32),
+                ("curve_nodes", C.POINTER(f32)), ("n_curve_nodes", u32),
+                ("curve_segments", C.POINTER(u32)), ("n_curve_segments", u32),
+                ("curve_mode", u32)]
 
 
 class Camera(C.Structure):

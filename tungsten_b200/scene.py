@@ -225,6 +225,70 @@ def save_wo3(path, verts, tris):
         f.write(struct.pack("<Q", len(tris))); f.write(np.ascontiguousarray(tris, dtype=TRI_DTYPE).tobytes())
 
 
+_FIBER_MAGIC = bytes([0x80, 0xBF, 0x80, 0x46, 0x49, 0x42, 0x45, 0x52])
+_FIBER_SIZES = [1, 1, 2, 2, 4, 4, 8, 8, 4, 8]
+
+
+def load_fiber(path):
+    """`.fiber` curve file (io/CurveIO.cpp:343-403): returns (curve_ends uint32[n_curves], nodes float32[n_nodes,4]);
+    node width is 0 where the file has no `width` attribute (CurveIO leaves it to `curve_thickness`)."""
+    import struct
+    with open(path, "rb") as f:
+        data = f.read()
+    if data[:8] != _FIBER_MAGIC:
+        raise SceneError("%s: not a .fiber file" % path)
+    major, _minor, content = struct.unpack_from("<HHI", data, 8)
+    if major != 1 or content != 0:
+        raise SceneError("%s: unsupported .fiber version/content" % path)
+    header_len, n_verts, n_curves = struct.unpack_from("<QQQ", data, 16)
+    ends, nodes = None, np.zeros((n_verts, 4), np.float32)
+    off = header_len
+    while True:
+        (desc_len,) = struct.unpack_from("<Q", data, off)
+        if desc_len == 0:
+            break
+        data_len, flags, vtype, vper = struct.unpack_from("<QHBB", data, off + 8)
+        name_end = data.index(b"\0", off + 20)
+        name = data[off + 20:name_end].decode()
+        off += desc_len
+        present = data_len//(_FIBER_SIZES[vtype]*vper) if vtype < len(_FIBER_SIZES) and vper else 0
+        per_curve = bool(flags & 1)
+
+        def column(dtype, need):     # FiberAttribute::load: copy-extend a short attribute (:332-341)
+            a = np.frombuffer(data, dtype=dtype, count=present*vper, offset=off).reshape(present, vper)
+            if present < need:
+                a = np.concatenate([a, np.repeat(a[-1:], need - present, axis=0)])
+            return a[:need]
+        if present > 0:
+            if name == "num_vertices" and per_curve and vtype == 3 and vper == 1:
+                ends = np.cumsum(column("<u2", n_curves)[:, 0].astype(np.uint64)).astype(np.uint32)
+            elif name == "position" and not per_curve and vtype == 8 and vper == 3:
+                nodes[:, :3] = column("<f4", n_verts)
+            elif name == "width" and not per_curve and vtype == 8 and vper == 1:
+                nodes[:, 3] = column("<f4", n_verts)[:, 0]
+        off += data_len
+    if ends is None:
+        raise SceneError("%s: no num_vertices attribute" % path)
+    return ends, nodes
+
+
+def save_fiber(path, curve_ends, nodes):
+    """Writes what load_fiber / CurveIO::loadFiber read back (per-curve node counts, positions, widths)."""
+    import struct
+    ends = np.asarray(curve_ends, np.uint32); nodes = np.asarray(nodes, np.float32)
+    counts = np.diff(np.concatenate([[0], ends])).astype("<u2")
+    blocks = [("num_vertices", 1, 3, 1, counts.tobytes()),
+              ("position", 0, 8, 3, np.ascontiguousarray(nodes[:, :3], "<f4").tobytes()),
+              ("width", 0, 8, 1, np.ascontiguousarray(nodes[:, 3], "<f4").tobytes())]
+    out = bytearray(_FIBER_MAGIC) + struct.pack("<HHI", 1, 0, 0) + struct.pack("<QQQ", 40, len(nodes), len(ends))
+    for name, flags, vtype, vper, payload in blocks:
+        nm = name.encode() + b"\0"
+        out += struct.pack("<QQHBB", 20 + len(nm), len(payload), flags, vtype, vper) + nm + payload
+    out += struct.pack("<Q", 0)
+    with open(path, "wb") as f:
+        f.write(bytes(out))
+
+
 def load_pfm(path):
     """Returns (h, w, 3) float32, top row first (io/ImageIO.cpp:528-544 writes rows bottom-up)."""
     with open(path, "rb") as f:
@@ -297,6 +361,7 @@ COMPLEX_IOR = {
     "Cu": ((0.2004376970, 0.9240334304, 1.1022119527), (3.9129485033, 2.4528477015, 2.1421879552)),
     "W":  ((4.3707029924, 3.3002972445, 2.9982666528), (3.5006778591, 2.6048652781, 2.2731930614)),
 }
+_CURVE_MODE = {"cylinder": abi.CURVE_CYLINDER, "half_cylinder": abi.CURVE_HALF_CYLINDER, "bcsdf_cylinder": abi.CURVE_BCSDF_CYLINDER}
 _DIST = {"beckmann": abi.DIST_BECKMANN, "phong": abi.DIST_PHONG, "ggx": abi.DIST_GGX}
 _FILTER = {"dirac": abi.FILTER_DIRAC, "box": abi.FILTER_BOX, "tent": abi.FILTER_TENT,
            "gaussian": abi.FILTER_GAUSSIAN, "mitchell_netravali": abi.FILTER_MITCHELL,
@@ -407,6 +472,18 @@ class FlatScene:
                 o.substrate = self.add_bsdf(sub, base_dir, named)
             if self.bsdfs[o.substrate].type == abi.BSDF_SMOOTH_COAT:
                 raise SceneError("nested coats are outside the hot path")
+        elif ty == "hair":
+            # HairBcsdf ctor defaults + fromJson + the sigma_a part of prepareForRender (bsdfs/HairBcsdf.cpp:13-21,163-171,435-443)
+            o.type = abi.BSDF_HAIR
+            o.hair_scale_angle_deg = float(f32(b.get("scale_angle", 2.0)))
+            o.hair_roughness = float(f32(b.get("roughness", 0.1)))
+            if "sigma_a" in b:
+                sa = _vec3_field(b, "sigma_a")
+            else:
+                ratio, conc = f32(b.get("melanin_ratio", 0.5)), f32(b.get("melanin_concentration", 0.25))
+                eu, pheo = v3(0.419, 0.697, 1.37), v3(0.187, 0.4, 1.05)
+                sa = conc*(eu*(f32(1.0) - ratio) + pheo*ratio)
+            o.sigma_a[:] = [float(f32(x)) for x in sa]
         else:
             raise SceneError("bsdf type outside the hot path: %r" % ty)
         if "bump" in b:
@@ -512,6 +589,49 @@ class FlatScene:
         self.slots += list(bsdfs) if bsdfs else [0]
         self.primitives.append(p)
         self.n_triangles += len(tris)
+
+    def add_curves(self, transform, curve_ends, nodes, bsdf, mode="half_cylinder", thickness=None, taper=False,
+                   subsample=0.0, emission_tex=-1):
+        """Curves::loadCurves + prepareForRender (primitives/Curves.cpp:268-296,572-611): thickness override / taper,
+        nodes to world space (width times the mean scale), then the list of segments that survive `subsample`."""
+        from .integrator import UniformSampler
+        if mode not in _CURVE_MODE:
+            raise SceneError("curve mode outside the hot path: %r" % mode)
+        if self.bsdfs[bsdf].type == abi.BSDF_HAIR and emission_tex >= 0:
+            raise SceneError("emissive curves are outside the hot path")
+        ends = np.asarray(curve_ends, np.uint32); nd = np.array(nodes, np.float32, copy=True)
+        starts = np.concatenate([[0], ends[:-1]]).astype(np.int64)
+        if thickness is not None or taper:
+            for i in range(len(ends)):
+                s, e = int(starts[i]), int(ends[i])
+                w = np.full(e - s, f32(thickness), np.float32) if thickness is not None else nd[s:e, 3].copy()
+                if taper:
+                    t = np.arange(e - s, dtype=np.float32)          # uint32 -> float, then the fp32 expression of :288
+                    w = w*(f32(1.0) - (t - f32(0.5))/f32(e - s - 1))
+                nd[s:e, 3] = w
+        m = transform
+        sx, sy, sz = length(v3(m[:3, 0])), length(v3(m[:3, 1])), length(v3(m[:3, 2]))
+        width_scale = f32(f32(f32(sx + sy) + sz)*f32(1.0/3.0))                                  # Vec::avg()
+        pos = nd[:, :3].copy()
+        for i in range(3):
+            nd[:, i] = ((m[i, 0]*pos[:, 0] + m[i, 1]*pos[:, 1]) + m[i, 2]*pos[:, 2]) + m[i, 3]
+        nd[:, 3] = nd[:, 3]*width_scale
+        rng = UniformSampler(0xBA5EBA11)                                                                   # UniformSampler() default seed
+        segs = []
+        for i in range(len(ends)):
+            if subsample > 0.0:
+                xi = f32(np.uint32((rng.next_i() >> 9) | 0x3F800000).view(np.float32) - f32(1.0))
+                if xi < f32(subsample):
+                    continue
+            segs.append(np.arange(int(starts[i]) + 2, int(ends[i]), dtype=np.uint32))
+        segs = np.concatenate(segs) if segs else np.zeros(0, np.uint32)
+        nd = np.ascontiguousarray(nd); segs = np.ascontiguousarray(segs)
+        self._keep += [nd, segs]
+        p = abi.Primitive(type=abi.PRIM_CURVES, emission_tex=emission_tex, bsdf_first=len(self.slots), bsdf_count=1,
+                          n_curve_nodes=len(nd), n_curve_segments=len(segs), curve_mode=_CURVE_MODE[mode])
+        p.curve_nodes = nd.ctypes.data_as(C.POINTER(abi.f32)); p.curve_segments = segs.ctypes.data_as(C.POINTER(abi.u32))
+        self.slots.append(bsdf); self.primitives.append(p)
+        self.n_curve_segments = getattr(self, "n_curve_segments", 0) + len(segs)
 
     def add_infinite_sphere(self, transform, emission_tex, sample=True):
         m = transform
@@ -622,6 +742,11 @@ def load_scene(path_or_dict, base_dir=None):
             fs.add_quad(tf, bsdfs[0], em)
         elif ty == "cube":
             fs.add_cube(tf, bsdfs[0], em)
+        elif ty == "curves":
+            ends, nodes = load_fiber(os.path.join(base_dir, p["file"]))
+            fs.add_curves(tf, ends, nodes, bsdfs[0], p.get("mode", "half_cylinder"),
+                          f32(p["curve_thickness"]) if "curve_thickness" in p else None, p.get("curve_taper", False),
+                          float(p.get("subsample", 0.0)), em)
         elif ty == "mesh":
             if p.get("recompute_normals", False) and p.get("smooth", False):
                 raise SceneError("recompute_normals is outside the hot path (bake normals into the .wo3)")

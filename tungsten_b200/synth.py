@@ -308,3 +308,57 @@ def instanced_forest(out_dir, name="forest", n_instances=64, tree_subdiv=2, res=
                          "enable_consistency_checks": False, "enable_two_sided_shading": True},
           "renderer": _renderer(spp)}
     return write_scene(out_dir, name, sc, {name + "_crown.wo3": (crown_v, crown_t), name + "_trunk.wo3": (trunk_v, trunk_t)})
+
+
+def curly_fibers(n_curves=200, nodes_per_curve=14, radius=0.45, length=1.1, width=0.01, seed=11):
+    """Curly strands hanging from a cap: returns (curve_ends uint32[n], nodes float32[n*k, 4]) for save_fiber."""
+    rng = np.random.RandomState(seed)
+    nodes = np.zeros((n_curves*nodes_per_curve, 4), np.float32)
+    ends = (np.arange(n_curves, dtype=np.uint32) + 1)*nodes_per_curve
+    s = np.linspace(0.0, 1.0, nodes_per_curve)
+    for c in range(n_curves):
+        a, r = rng.uniform(0, 2*np.pi), radius*np.sqrt(rng.uniform(0.02, 1.0))
+        root = np.array([r*np.cos(a), 0.0, r*np.sin(a)])
+        out = np.array([np.cos(a), 0.0, np.sin(a)])
+        curl_r, turns, ph = rng.uniform(0.02, 0.07), rng.uniform(1.5, 4.0), rng.uniform(0, 2*np.pi)
+        ang = ph + 2*np.pi*turns*s
+        p = root[None, :] + np.stack([out[0]*0.25*s*s + curl_r*np.cos(ang)*s, -length*rng.uniform(0.7, 1.0)*s,
+                                      out[2]*0.25*s*s + curl_r*np.sin(ang)*s], axis=1)
+        nodes[c*nodes_per_curve:(c + 1)*nodes_per_curve, :3] = p
+        nodes[c*nodes_per_curve:(c + 1)*nodes_per_curve, 3] = width*rng.uniform(0.6, 1.4)
+    return ends, nodes
+
+
+def hair_scene(out_dir, name="hair", n_curves=200, nodes_per_curve=14, mode="bcsdf_cylinder", bsdf=None, res=(128, 128),
+               spp=16, max_bounces=16, thickness=None, taper=False, subsample=0.0, env=(0.35, 0.4, 0.5), width=0.01):
+    """C4 stand-in: curly strands (`curves` primitive + `.fiber` file) with the hair BCSDF over a Lambert floor, lit by a
+    quad light and a constant environment.  (The shipped hair scene's emitters, infinite_sphere_cap + skydome, are
+    outside the hot path)"""
+    from .scene import save_fiber
+    os.makedirs(out_dir, exist_ok=True)
+    ends, nodes = curly_fibers(n_curves, nodes_per_curve, width=width)
+    save_fiber(os.path.join(out_dir, name + ".fiber"), ends, nodes)
+    hb = dict(bsdf or {"type": "hair", "albedo": 1, "scale_angle": 2.5, "melanin_ratio": 0.6,
+                       "melanin_concentration": 0.8, "roughness": 0.3}); hb["name"] = "strand"
+    curves = {"name": "strands", "type": "curves", "file": name + ".fiber", "mode": mode, "bsdf": "strand",
+              "curve_taper": taper, "subsample": subsample,
+              "transform": {"position": [0.0, 1.55, 0.0], "scale": [1.0, 1.1, 1.0], "rotation": [0, 20, 0]}}
+    if thickness is not None:
+        curves["curve_thickness"] = thickness
+    prims = [{"name": "floor", "type": "quad", "bsdf": "floor",
+              "transform": {"position": [0, 0, 0], "scale": [6, 1, 6], "rotation": [0, 0, 0]}},
+             curves,
+             {"name": "light", "type": "quad", "bsdf": "light", "emission": [30, 28, 24],
+              "transform": {"position": [0.9, 2.6, 1.2], "scale": [0.7, 1, 0.7], "rotation": [0, 0, 150]}}]
+    if env is not None:
+        prims.append({"name": "env", "type": "infinite_sphere", "emission": list(env), "sample": True})
+    sc = {"media": [], "bsdfs": [_lambert("floor", [0.5, 0.5, 0.5]), hb, {"name": "light", "albedo": 1, "type": "null"}],
+          "primitives": prims,
+          "camera": {"tonemap": "filmic", "resolution": list(res), "reconstruction_filter": "tent",
+                     "transform": {"position": [0.3, 1.2, 3.4], "look_at": [0, 0.95, 0], "up": [0, 1, 0]},
+                     "type": "pinhole", "fov": 35},
+          "integrator": {"type": "path_tracer", "min_bounces": 0, "max_bounces": max_bounces,
+                         "enable_consistency_checks": False, "enable_two_sided_shading": True,
+                         "enable_light_sampling": True},
+          "renderer": _renderer(spp)}
+    return write_scene(out_dir, name, sc)
