@@ -221,6 +221,9 @@ int  tgb200_reset_stats(tgb_ctx *ctx);
 /* Host-only self-check of the BVH builder (no GPU): n triangles, 9 floats each (v0 v1 v2).  Returns TGB_OK when every
  * triangle sits in exactly one leaf and inside every box of its root-to-leaf chain.                    */
 int  tgb200_bvh_selftest(const float *tri_verts, uint32_t n, uint32_t *n_nodes, uint32_t *depth, uint32_t *max_leaf);
+/* Host-only: the hair BCSDF tables tgb200_create precomputes for one material (HairBcsdf.cpp:318-446): tables = 3 lobes
+ * (R, TT, TRT) x 64 x 64 x RGB, sums = 3 x 64 row sums of the sampling weights, v = the three longitudinal variances. */
+int  tgb200_hair_selftest(float roughness, float scale_angle_deg, const float *sigma_a, float *tables, float *sums, float *v);
 int  tgb200_abort(tgb_ctx *ctx);
 void tgb200_destroy(tgb_ctx *ctx);
 /* Last error text of the context; with ctx == NULL the text of the last failed tgb200_create.       */

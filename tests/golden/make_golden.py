@@ -104,6 +104,15 @@ def make_scenes():
     scenes["materials"] = synth.material_room(os.path.join(HERE, "materials"), "scene", res=res, spp=spp, subdiv=2)
     scenes["materials_env"] = synth.material_room(os.path.join(HERE, "materials_env"), "scene", res=res, spp=spp, subdiv=2, env=[0.4, 0.5, 0.7])
     scenes["coat_env"] = synth.materialtest_standin(os.path.join(HERE, "coat_env"), "scene", res=res, spp=spp, subdiv=2, env_res=(64, 32))
+    # C4 stand-ins: curves primitive + hair BCSDF (bcsdf_cylinder), and the two other curve modes with ordinary lobes
+    scenes["hair"] = synth.hair_scene(os.path.join(HERE, "hair"), "scene", n_curves=400, res=res, spp=spp)
+    scenes["hair_dark"] = synth.hair_scene(os.path.join(HERE, "hair_dark"), "scene", n_curves=300, res=res, spp=spp, thickness=0.008,
+                                           subsample=0.5, env=None, bsdf={"type": "hair", "roughness": 0.1, "scale_angle": 3, "sigma_a": [0.1, 0.2, 0.5]})
+    scenes["curves_lambert"] = synth.hair_scene(os.path.join(HERE, "curves_lambert"), "scene", n_curves=300, res=res, spp=spp, mode="half_cylinder",
+                                                bsdf={"type": "lambert", "albedo": [0.6, 0.4, 0.2]}, width=0.02)
+    scenes["curves_plastic"] = synth.hair_scene(os.path.join(HERE, "curves_plastic"), "scene", n_curves=300, res=res, spp=spp, mode="cylinder",
+                                                bsdf={"type": "rough_plastic", "albedo": [0.6, 0.4, 0.2], "roughness": 0.2}, thickness=0.015,
+                                                taper=True, subsample=0.3)
     for name, path in scenes.items():
         d = os.path.dirname(path)
         for exe, tag in (("tungsten_pathseed", "ref_pathseed"), ("tungsten", "ref_stock")):

@@ -189,3 +189,50 @@ def test_bvh_builder_selftest(n):
     assert rc == 0
     if n:
         assert leaf.value <= 4 and nodes.value >= 1 and depth.value <= 40
+
+
+def test_fiber_roundtrip_and_curve_flattening(tmp_path):
+    """.fiber reader/writer (io/CurveIO.cpp:343-403) and Curves::loadCurves/prepareForRender bookkeeping
+    (Curves.cpp:268-296,572-611): thickness override, taper, subsample with the default UniformSampler seed."""
+    ends, nodes = synth.curly_fibers(n_curves=40, nodes_per_curve=9)
+    p = str(tmp_path/"c.fiber")
+    scene.save_fiber(p, ends, nodes)
+    e2, n2 = scene.load_fiber(p)
+    assert np.array_equal(e2, ends) and np.array_equal(n2, nodes)
+    fs = scene.FlatScene(); b = fs.add_bsdf({"type": "lambert"})
+    fs.add_curves(np.eye(4, dtype=np.float32), ends, nodes, b, mode="cylinder")
+    pr = fs.primitives[-1]
+    assert pr.n_curve_segments == 40*(9 - 2) and pr.n_curve_nodes == len(nodes)
+    segs = np.ctypeslib.as_array(pr.curve_segments, (pr.n_curve_segments,))
+    assert segs[0] == 2 and segs[6] == 8 and segs[7] == 11          # a curve of k nodes has k-2 segments ending at nodes 2..k-1
+    # subsample drops whole curves with the reference's PCG stream: same draw sequence -> same survivors every time
+    fs2 = scene.FlatScene(); b2 = fs2.add_bsdf({"type": "lambert"})
+    fs2.add_curves(np.eye(4, dtype=np.float32), ends, nodes, b2, thickness=np.float32(0.02), taper=True, subsample=0.5)
+    pr2 = fs2.primitives[-1]
+    assert 0 < pr2.n_curve_segments < pr.n_curve_segments and pr2.n_curve_segments % 7 == 0
+    w = np.ctypeslib.as_array(pr2.curve_nodes, (pr2.n_curve_nodes*4,)).reshape(-1, 4)[:, 3]
+    assert np.isclose(w[0], 0.02*(1.0 + 0.5/8.0)) and w[8] < w[0]       # taper: 1 - (t - 0.5)/(k - 1)
+    with pytest.raises(scene.SceneError):
+        fs.add_curves(np.eye(4, dtype=np.float32), ends, nodes, b, mode="ribbon")
+
+
+def test_hair_tables_host_precompute_matches_oracle():
+    """tgb200_hair_selftest (host C++ of the library) vs the oracle's restatement of HairBcsdf::precomputeAzimuthalDistributions:
+    same libm, same operation order -> identical tables, sampling sums and lobe variances."""
+    import ctypes as C
+    from oracle import pyoracle
+    L = lib.load(); O = pyoracle.lib()
+    out = []
+    for fn in (L.tgb200_hair_selftest, O.oracle_hair_tables):
+        fn.restype = C.c_int; fn.argtypes = [C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        sa = np.array([0.25, 0.45, 1.1], np.float32)
+        t = np.zeros(3*64*64*3, np.float32); s = np.zeros(3*64, np.float32); v = np.zeros(3, np.float32)
+        assert fn(0.3, 2.5, sa.ctypes.data, t.ctypes.data, s.ctypes.data, v.ctypes.data) == 0
+        out.append((t, s, v))
+    for a, b in zip(out[0], out[1]):
+        assert np.array_equal(a, b)
+    t = out[0][0].reshape(3, 64, 64, 3)
+    assert np.isfinite(t[:, 1:]).all() and (t[:, 1:] >= 0).all()
+    assert np.allclose(out[0][2], [(np.pi/2*0.3)**2, (np.pi/4*0.3)**2, (np.pi*0.3)**2], rtol=1e-5)
+    assert (t[0, 1:, :, 0] == t[0, 1:, :, 1]).all()                 # the R lobe is colourless
+    assert t[1, 32, :, 2].sum() < t[1, 32, :, 0].sum()              # TT is tinted by absorption (blue absorbed most)

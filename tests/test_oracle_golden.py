@@ -52,6 +52,24 @@ def test_mesh_scenes_close(name, mode, ref):
     assert abs(float(img.mean()) - float(want.mean())) <= 5e-3*float(want.mean())
 
 
+@pytest.mark.parametrize("name", ["hair", "hair_dark", "curves_lambert", "curves_plastic"])
+@pytest.mark.parametrize("mode,ref", [(0, "ref_pathseed.pfm"), (1, "ref_stock.pfm")])
+def test_curve_scenes_close(name, mode, ref):
+    """Curves (Curves.cpp) + hair BCSDF (HairBcsdf.cpp) against the reference's own renders.  The oracle's segment BVH
+    is not the reference's, and the reference's per-segment bisection prunes with a bound that is not strictly
+    conservative, so a few grazing rays resolve differently: >= 98.5% of pixels bit-exact under the per-path reseed contract;
+    with the stock serial PCG stream one such ray also shifts the Russian-roulette draws of the rest of its tile: >= 95%."""
+    img = _render(name, mode)
+    want = scene.load_pfm(os.path.join(G, name, ref))
+    d = np.abs(img - want).max(axis=2)
+    exact = float((d == 0).mean())
+    close = float((d <= 1e-5*(1.0 + np.abs(want).max(axis=2))).mean())
+    print(name, mode, "exact %.4f close %.4f" % (exact, close))
+    assert exact >= (0.985 if mode == 0 else 0.95)
+    assert close >= (0.985 if mode == 0 else 0.95)
+    assert abs(float(img.mean()) - float(want.mean())) <= 5e-3*float(want.mean())
+
+
 def test_pathseed_and_stock_references_differ():
     a = scene.load_pfm(os.path.join(G, "cornell", "ref_pathseed.pfm"))
     b = scene.load_pfm(os.path.join(G, "cornell", "ref_stock.pfm"))

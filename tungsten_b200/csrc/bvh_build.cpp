@@ -101,6 +101,8 @@ inline float pad_up(float v) { return std::nextafter(std::nextafter(v, std::nume
 
 }  // namespace
 
+static void build_from_boxes(std::vector<Box> &tb, std::vector<float> &cent, uint32_t n, Bvh4 &out, int threads);
+
 void build_bvh4(const BuildTri *tris, uint32_t n, Bvh4 &out, int threads, float abs_pad) {
     out.nodes.clear(); out.order.clear(); out.max_depth = 0; out.sah_cost = 0.0;
     for (int a = 0; a < 3; ++a) { out.lo[a] = std::numeric_limits<float>::infinity(); out.hi[a] = -out.lo[a]; }
@@ -111,6 +113,23 @@ void build_bvh4(const BuildTri *tris, uint32_t n, Bvh4 &out, int threads, float 
         for (int a = 0; a < 3; ++a) { cent[3*size_t(i) + a] = 0.5f*b.lo[a] + 0.5f*b.hi[a]; b.lo[a] = pad_down(b.lo[a] - abs_pad); b.hi[a] = pad_up(b.hi[a] + abs_pad); }
         tb[i] = b;
     }
+    build_from_boxes(tb, cent, n, out, threads);
+}
+
+void build_bvh4_boxes(const BuildBox *boxes, uint32_t n, Bvh4 &out, int threads, float abs_pad) {
+    out.nodes.clear(); out.order.clear(); out.max_depth = 0; out.sah_cost = 0.0;
+    for (int a = 0; a < 3; ++a) { out.lo[a] = std::numeric_limits<float>::infinity(); out.hi[a] = -out.lo[a]; }
+    if (n == 0) return;
+    std::vector<Box> tb(n); std::vector<float> cent(3*size_t(n));
+    for (uint32_t i = 0; i < n; ++i)
+        for (int a = 0; a < 3; ++a) {
+            cent[3*size_t(i) + a] = boxes[i].centroid[a];
+            tb[i].lo[a] = pad_down(boxes[i].lo[a] - abs_pad); tb[i].hi[a] = pad_up(boxes[i].hi[a] + abs_pad);
+        }
+    build_from_boxes(tb, cent, n, out, threads);
+}
+
+static void build_from_boxes(std::vector<Box> &tb, std::vector<float> &cent, uint32_t n, Bvh4 &out, int threads) {
     out.order.resize(n);
     for (uint32_t i = 0; i < n; ++i) out.order[i] = i;
     Builder bl; bl.tb = tb.data(); bl.cent = cent.data(); bl.idx = out.order.data();

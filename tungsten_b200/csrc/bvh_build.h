@@ -34,8 +34,12 @@ struct Bvh4 {
     double sah_cost = 0.0;
 };
 
+// A primitive given by its bounds and the point the SAH binning sorts it by (curve segments).
+struct BuildBox { float lo[3], hi[3], centroid[3]; };
+
 // threads <= 0: hardware concurrency.
 // abs_pad: every triangle box is grown by this absolute amount (covers the slab test's rounding).
 void build_bvh4(const BuildTri *tris, uint32_t n, Bvh4 &out, int threads = 0, float abs_pad = 0.0f);
+void build_bvh4_boxes(const BuildBox *boxes, uint32_t n, Bvh4 &out, int threads = 0, float abs_pad = 0.0f);
 
 }  // namespace tgb

@@ -12,6 +12,7 @@
 #include <vector>
 
 #include "bvh_build.h"
+#include "hair_tables.h"
 #include "tgb_kernels.cuh"
 
 extern "C" const unsigned char tgb_sobol_blob[];      // sobol_blob.cpp (.incbin of data/sobol_1024x32.u32)
@@ -40,6 +41,7 @@ struct tgb_ctx {
     uint32_t capacity = 0;
     PathState st{}, st2{};      // st2 = second copy of the persistent arrays (ray, throughput, emission, rng, hit, pid)
     uint32_t *queue_a = nullptr, *queue_b = nullptr, *squeue = nullptr, *squeue2 = nullptr, *free_list = nullptr;
+    bool has_curves = false;        // selects the kernel instantiations with the curve-segment test and per-hit epsilon
     uint32_t *bin_keys = nullptr, *bin_hist = nullptr;      // queue_a doubles as the ray-coherence visiting order of k_trace
     size_t res_capacity = 0;
     ShadowState ss{};
@@ -156,6 +158,7 @@ uint32_t bsdf_lobes(const tgb_bsdf &b) {
     case TGB_BSDF_PLASTIC: return LOBE_SPEC_R | LOBE_DIFFUSE_R;
     case TGB_BSDF_ROUGH_PLASTIC: return LOBE_GLOSSY_R | LOBE_DIFFUSE_R;
     case TGB_BSDF_SMOOTH_COAT: return LOBE_SPEC_R;          // | substrate lobes, added by upload_scene
+    case TGB_BSDF_HAIR: return LOBE_GLOSSY_R | LOBE_GLOSSY_T | LOBE_ANISO;                  // bsdfs/HairBcsdf.cpp:20
     default: return 0xFFFFFFFFu;
     }
 }
@@ -263,6 +266,18 @@ int upload_scene(tgb_ctx *c, const tgb_scene_desc *d) {
             o.avg_transmittance = std::exp(-2.0f*avg(o.scaled_sigma_a));
             o.lobes = LOBE_SPEC_R | bsdf_lobes(d->bsdfs[b.substrate]);
         }
+        if (b.type == TGB_BSDF_HAIR) {                                                    // bsdfs/HairBcsdf.cpp:422-446
+            HairTables ht;
+            hair_precompute(b.hair_roughness, b.hair_scale_angle_deg, b.sigma_a, ht);
+            for (int p = 0; p < 3; ++p) {
+                o.hair_v[p] = ht.v[p];
+                int rc = dev_upload(c, &o.hair_table[p], ht.lobe[p].table); if (rc) return rc;
+                rc = dev_upload(c, &o.hair_pdfs[p], ht.lobe[p].pdfs); if (rc) return rc;
+                rc = dev_upload(c, &o.hair_cdfs[p], ht.lobe[p].cdfs); if (rc) return rc;
+                rc = dev_upload(c, &o.hair_sums[p], ht.lobe[p].sums); if (rc) return rc;
+            }
+            o.hair_scale_rad = ht.scale_angle_rad;
+        }
         if (b.type == TGB_BSDF_PLASTIC || b.type == TGB_BSDF_ROUGH_PLASTIC) {             // bsdfs/PlasticBsdf.cpp:179-185
             o.scaled_sigma_a = f3(b.sigma_a)*b.thickness;
             o.avg_transmittance = std::exp(-2.0f*avg(o.scaled_sigma_a));
@@ -275,6 +290,7 @@ int upload_scene(tgb_ctx *c, const tgb_scene_desc *d) {
     std::vector<DPrim> prims(d->n_primitives);
     std::vector<int> lights, inf_lights, analytic;
     std::vector<BuildTri> btris; std::vector<uint32_t> tri_prim; std::vector<float4> tri_shade;
+    std::vector<BuildBox> cboxes; std::vector<float4> crecs; std::vector<uint32_t> cseg_prim;     // curve segments of all primitives
     int lightCount = 0;
     for (uint32_t i = 0; i < d->n_primitives; ++i) {
         const tgb_primitive &p = d->primitives[i]; DPrim &o = prims[i];
@@ -347,6 +363,35 @@ int upload_scene(tgb_ctx *c, const tgb_scene_desc *d) {
             samplable = p.do_sample != 0; infinite = true;
             if (emissive && tex[p.emission_tex].d.type == TGB_TEX_CHECKER) return fail(c, TGB_ERR_UNSUPPORTED, "checker environment maps are outside the hot path");
             break; }
+        case TGB_PRIM_CURVES: {                                                           // primitives/Curves.cpp:572-613 (nodes arrive prepared)
+            if (p.curve_mode > TGB_CURVE_BCSDF_CYLINDER) return fail(c, TGB_ERR_UNSUPPORTED, "curves %u: mode outside the hot path", i);
+            if (emissive) return fail(c, TGB_ERR_UNSUPPORTED, "emissive curves are outside the hot path");
+            if (p.n_curve_segments && (!p.curve_nodes || !p.curve_segments)) return fail(c, TGB_ERR_INVALID, "curves %u has null buffers", i);
+            if (tex[d->bsdfs[d->bsdf_slots[p.bsdf_first]].albedo_tex].d.type != TGB_TEX_CONSTANT)
+                return fail(c, TGB_ERR_UNSUPPORTED, "curves %u: textured materials on curves are outside the hot path", i);
+            o.curve_mode = p.curve_mode; o.tri_first = uint32_t(cboxes.size()); o.n_tris = p.n_curve_segments;      // rebased below
+            for (uint32_t k = 0; k < p.n_curve_segments; ++k) {
+                uint32_t t = p.curve_segments[k];
+                if (t < 2 || t >= p.n_curve_nodes) return fail(c, TGB_ERR_INVALID, "curves %u: segment index out of range", i);
+                const float *n0 = p.curve_nodes + 4*size_t(t - 2), *n1 = n0 + 4, *n2 = n0 + 8;
+                BuildBox bb;                                                               // curveBox (Curves.cpp:231-243)
+                float maxW = std::max(std::max(n0[3], n1[3]), n2[3]);
+                for (int a = 0; a < 3; ++a) {
+                    float lo = (n0[a] + n1[a])*0.5f, hi = (n1[a] + n2[a])*0.5f;           // BSpline::quadraticMinMax
+                    if (lo > hi) std::swap(lo, hi);
+                    float tFlat = (n0[a] - n1[a])/(n0[a] - 2.0f*n1[a] + n2[a]);
+                    if (tFlat > 0.0f && tFlat < 1.0f) {
+                        float xFlat = (0.5f*n0[a] - n1[a] + 0.5f*n2[a])*tFlat*tFlat + (n1[a] - n0[a])*tFlat + 0.5f*(n0[a] + n1[a]);
+                        lo = std::min(lo, xFlat); hi = std::max(hi, xFlat);
+                    }
+                    bb.lo[a] = lo - maxW; bb.hi[a] = hi + maxW;
+                    bb.centroid[a] = (n0[a] + n1[a] + n2[a])*(1.0f/3.0f);
+                }
+                cboxes.push_back(bb); cseg_prim.push_back(i);
+                crecs.push_back(make_float4(n0[0], n0[1], n0[2], n0[3])); crecs.push_back(make_float4(n1[0], n1[1], n1[2], n1[3]));
+                crecs.push_back(make_float4(n2[0], n2[1], n2[2], n2[3]));
+            }
+            break; }
         default: return fail(c, TGB_ERR_UNSUPPORTED, "primitive type %u is outside the hot path", p.type);
         }
         if (emissive) {                                                                   // renderer/TraceableScene.hpp:89-96
@@ -391,11 +436,55 @@ int upload_scene(tgb_ctx *c, const tgb_scene_desc *d) {
     float extent = std::max(std::max(std::fabs(sc.cam.pos.x), std::fabs(sc.cam.pos.y)), std::fabs(sc.cam.pos.z));
     for (const BuildTri &t : btris) for (int k = 0; k < 3; ++k)
         extent = std::max(extent, std::max(std::fabs(t.v0[k]), std::max(std::fabs(t.v1[k]), std::fabs(t.v2[k]))));
+    for (const float4 &q : crecs) extent = std::max(extent, std::max(std::fabs(q.x), std::max(std::fabs(q.y), std::fabs(q.z))) + q.w);
     build_bvh4(btris.data(), uint32_t(btris.size()), bvh, 0, 1e-6f*extent);
+    const uint32_t n_tris_total = uint32_t(btris.size()), n_segs_total = uint32_t(cboxes.size());
+    if (n_segs_total) {
+        // Curve segments get their own SAH tree (leaf bit 2 = "curve leaf", records stored behind the triangles); with
+        // triangles present the two trees hang under a new root, so one traversal answers TraceableScene::intersect.
+        Bvh4 cb;
+        build_bvh4_boxes(cboxes.data(), n_segs_total, cb, 0, 1e-6f*extent);
+        const bool both = !bvh.nodes.empty();
+        const int32_t tri_base = both ? 1 : 0, curve_base = tri_base + int32_t(bvh.nodes.size());
+        std::vector<Node4> merged(size_t(curve_base) + cb.nodes.size());
+        for (size_t k = 0; k < bvh.nodes.size(); ++k) {
+            Node4 nd = bvh.nodes[k];
+            for (int j = 0; j < 4; ++j) if (nd.link[j] >= 0) nd.link[j] += tri_base;
+            merged[size_t(tri_base) + k] = nd;
+        }
+        for (size_t k = 0; k < cb.nodes.size(); ++k) {
+            Node4 nd = cb.nodes[k];
+            for (int j = 0; j < 4; ++j) {
+                if (nd.link[j] >= 0) nd.link[j] += curve_base;
+                else if (nd.link[j] != kEmptyLink) { int32_t code = ~nd.link[j]; nd.link[j] = ~int32_t((((code >> 3) + int32_t(n_tris_total)) << 3) | 4 | (code & 3)); }
+            }
+            merged[size_t(curve_base) + k] = nd;
+        }
+        if (both) {
+            Node4 root; std::memset(&root, 0, sizeof(root));
+            for (int j = 0; j < 4; ++j) root.link[j] = kEmptyLink;
+            for (int a = 0; a < 3; ++a) {
+                root.f[8*a] = bvh.lo[a]; root.f[8*a + 4] = bvh.hi[a];
+                root.f[8*a + 1] = cb.lo[a]; root.f[8*a + 5] = cb.hi[a];
+            }
+            root.link[0] = tri_base; root.link[1] = curve_base;
+            merged[0] = root;
+            bvh.max_depth = std::max(bvh.max_depth, cb.max_depth) + 1;
+            for (int a = 0; a < 3; ++a) { bvh.lo[a] = std::min(bvh.lo[a], cb.lo[a]); bvh.hi[a] = std::max(bvh.hi[a], cb.hi[a]); }
+        } else {
+            bvh.max_depth = cb.max_depth;
+            for (int a = 0; a < 3; ++a) { bvh.lo[a] = cb.lo[a]; bvh.hi[a] = cb.hi[a]; }
+        }
+        bvh.nodes.swap(merged);
+        for (uint32_t k : cb.order) bvh.order.push_back(n_tris_total + k);
+        bvh.sah_cost += cb.sah_cost;
+        for (uint32_t pi : cseg_prim) tri_prim.push_back(pi);
+        for (DPrim &p : prims) if (p.type == TGB_PRIM_CURVES) p.tri_first += n_tris_total;
+    }
     {   // ray-binning grid: bounds of every finite primitive (TraceableScene::_sceneBounds, TraceableScene.hpp:104-110)
         float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
         auto grow = [&](V3 p) { float q[3] = {p.x, p.y, p.z}; for (int a = 0; a < 3; ++a) { lo[a] = std::min(lo[a], q[a]); hi[a] = std::max(hi[a], q[a]); } };
-        if (!btris.empty()) { grow(f3(bvh.lo)); grow(f3(bvh.hi)); }
+        if (!bvh.nodes.empty()) { grow(f3(bvh.lo)); grow(f3(bvh.hi)); }
         for (int pi : analytic) {
             const DPrim &p = prims[pi];
             if (p.type == TGB_PRIM_QUAD) { grow(p.base); grow(p.base + p.edge0); grow(p.base + p.edge1); grow(p.base + p.edge0 + p.edge1); }
@@ -428,8 +517,12 @@ int upload_scene(tgb_ctx *c, const tgb_scene_desc *d) {
     }
     if (3*bvh.max_depth + 2 > uint32_t(kStackSize)) return fail(c, TGB_ERR_UNSUPPORTED, "BVH depth %u exceeds the traversal stack", bvh.max_depth);
     c->bvh_depth = bvh.max_depth; c->n_tris = uint32_t(btris.size()); c->bvh_sah = bvh.sah_cost;
-    std::vector<float4> tri_isect(3*btris.size());
-    for (size_t k = 0; k < bvh.order.size(); ++k) {
+    std::vector<float4> tri_isect(3*(btris.size() + cboxes.size()));
+    for (size_t k = btris.size(); k < bvh.order.size(); ++k) {      // curve records: the segment's three nodes, leaf order
+        size_t seg = bvh.order[k] - btris.size();
+        for (int j = 0; j < 3; ++j) tri_isect[3*k + j] = crecs[3*seg + j];
+    }
+    for (size_t k = 0; k < btris.size(); ++k) {
         const BuildTri &t = btris[bvh.order[k]];
         // Embree TriangleM: v0, e1 = v0-v1, e2 = v2-v0, Ng = cross(e1, e2) (kernels/geometry/triangle.h:54)
         V3 v0 = f3(t.v0), v1 = f3(t.v1), v2 = f3(t.v2);
@@ -461,6 +554,7 @@ int upload_scene(tgb_ctx *c, const tgb_scene_desc *d) {
     if ((rc = dev_upload(c, &sc.sobol, sobol))) return rc;
     sc.n_prims = uint32_t(prims.size()); sc.n_lights = int(lights.size()); sc.n_inf_lights = int(inf_lights.size());
     sc.n_analytic = int(analytic.size()); sc.n_nodes = uint32_t(bvh.nodes.size()); sc.n_tris = uint32_t(btris.size());
+    sc.n_curve_segs = uint32_t(cboxes.size()); c->has_curves = !cboxes.empty();
     return TGB_OK;
 }
 
@@ -477,6 +571,7 @@ int alloc_wavefront(tgb_ctx *c, uint32_t capacity) {
     ALLOCF(lx) ALLOCF(ly) ALLOCF(lz) ALLOCF(bx) ALLOCF(by) ALLOCF(bz) ALLOCF(wl) ALLOCF(sx) ALLOCF(sy) ALLOCF(sz) ALLOCF(ux) ALLOCF(uy) ALLOCF(uz)
     ALLOCF(ndx) ALLOCF(ndy) ALLOCF(ndz) ALLOCF(ndist) ALLOCF(nfx) ALLOCF(nfy) ALLOCF(nfz) ALLOCF(npl) ALLOCF(npb)
     ALLOCF(mdx) ALLOCF(mdy) ALLOCF(mdz) ALLOCF(mwx) ALLOCF(mwy) ALLOCF(mwz) ALLOCF(mpb) ALLOCF(qlight) ALLOCF(pid)
+    if (c->has_curves) { ALLOCF(eps) }
 #undef ALLOCF
     c->st2 = c->st;
 #define ALLOC2(name) if ((rc = dev_alloc(c, &c->st2.name, capacity))) return rc;
@@ -571,7 +666,7 @@ int render_device(tgb_ctx *c, uint32_t spp_begin, uint32_t spp_count) {
     CU(cudaEventRecord(c->ev0, c->stream));
     uint64_t launches = 0;
     float trace_ms = 0.0f, shadow_ms = 0.0f; uint64_t trace_launches = 0, traversed = 0, shadow_traversed = 0;
-    const bool has_bvh = sc.n_nodes != 0;
+    const bool has_bvh = sc.n_nodes != 0, curves = c->has_curves;
     // a step's finished radiances are kept per path (12 B each) until k_resolve folds them in sample order;
     // split the sample range so that this buffer stays below ~6 GB and path ids fit 32 bits
     const uint64_t max_paths = std::min<uint64_t>(512ull << 20, 0xFFFFFFFFull);
@@ -602,15 +697,23 @@ int render_device(tgb_ctx *c, uint32_t spp_begin, uint32_t spp_count) {
             if (c->profiling) CU(cudaEventRecord(c->evt0, c->stream));
             if (has_bvh) {
                 uint32_t K = rays_per_lane(n);
-                k_trace<<<blocks(n, kTraceBlock*K), kTraceBlock, kTraceSmem, c->stream>>>(sc, cur, c->queue_a, c->bin_hist + kBins + 1, n_alive, n, K); launches++;
+                if (curves) k_trace<true><<<blocks(n, kTraceBlock*K), kTraceBlock, kTraceSmem, c->stream>>>(sc, cur, c->queue_a, c->bin_hist + kBins + 1, n_alive, n, K);
+                else k_trace<false><<<blocks(n, kTraceBlock*K), kTraceBlock, kTraceSmem, c->stream>>>(sc, cur, c->queue_a, c->bin_hist + kBins + 1, n_alive, n, K);
+                launches++;
             }
             if (c->profiling) CU(cudaEventRecord(c->evt1, c->stream));
-            k_shade<<<blocks(n, 128), 128, 0, c->stream>>>(sc, cur, bi, n, c->squeue, cs, c->ctr); launches++;
+            if (curves) k_shade<true><<<blocks(n, 128), 128, 0, c->stream>>>(sc, cur, bi, n, c->squeue, cs, c->ctr);
+            else k_shade<false><<<blocks(n, 128), 128, 0, c->stream>>>(sc, cur, bi, n, c->squeue, cs, c->ctr);
+            launches++;
             if (c->profiling) CU(cudaEventRecord(c->evs0, c->stream));
-            k_shadow_prep<<<blocks(2*n, 256), 256, 0, c->stream>>>(sc, cur, c->ss, c->squeue, cs, c->squeue2, cs + 1, c->ctr); launches++;
+            if (curves) k_shadow_prep<true><<<blocks(2*n, 256), 256, 0, c->stream>>>(sc, cur, c->ss, c->squeue, cs, c->squeue2, cs + 1, c->ctr);
+            else k_shadow_prep<false><<<blocks(2*n, 256), 256, 0, c->stream>>>(sc, cur, c->ss, c->squeue, cs, c->squeue2, cs + 1, c->ctr);
+            launches++;
             if (has_bvh) {
                 uint32_t K = rays_per_lane(2*n);
-                k_shadow_bvh<<<blocks(2*n, kTraceBlock*K), kTraceBlock, kTraceSmem, c->stream>>>(sc, cur, c->ss, c->squeue2, cs + 1, c->ctr, K); launches++;
+                if (curves) k_shadow_bvh<true><<<blocks(2*n, kTraceBlock*K), kTraceBlock, kTraceSmem, c->stream>>>(sc, cur, c->ss, c->squeue2, cs + 1, c->ctr, K);
+                else k_shadow_bvh<false><<<blocks(2*n, kTraceBlock*K), kTraceBlock, kTraceSmem, c->stream>>>(sc, cur, c->ss, c->squeue2, cs + 1, c->ctr, K);
+                launches++;
             }
             if (c->profiling) CU(cudaEventRecord(c->evs1, c->stream));
             CU(cudaMemsetAsync(c->bin_hist, 0, (kBins + 1)*sizeof(uint32_t), c->stream));
@@ -785,7 +888,8 @@ int tgb200_trace_closest(tgb_ctx *c, const tgb_ray *rays, tgb_hit *hits, uint32_
         k_hook_analytic<<<blocks(n, 256), 256, 0, c->stream>>>(c->sc, dr, dx, n);
         if (c->sc.n_nodes) {
             uint32_t K = rays_per_lane(n);
-            k_hook_bvh<<<blocks(n, kTraceBlock*K), kTraceBlock, kTraceSmem, c->stream>>>(c->sc, dr, dx, n, K);
+            if (c->has_curves) k_hook_bvh<true><<<blocks(n, kTraceBlock*K), kTraceBlock, kTraceSmem, c->stream>>>(c->sc, dr, dx, n, K);
+            else k_hook_bvh<false><<<blocks(n, kTraceBlock*K), kTraceBlock, kTraceSmem, c->stream>>>(c->sc, dr, dx, n, K);
             c->stats.kernel_launches++;
         }
         k_hook_finish<<<blocks(n, 256), 256, 0, c->stream>>>(c->sc, dr, dx, dh, n);
@@ -876,6 +980,20 @@ int tgb200_unpack_tiles(tgb_ctx *c, const tgb_tile *tiles, uint32_t n_tiles, con
     cudaError_t e = cudaStreamSynchronize(c->stream);
     if (owned) cudaFree(pid);
     if (e != cudaSuccess) return fail(c, TGB_ERR_CUDA, "unpack_tiles failed: %s", cudaGetErrorString(e));
+    return TGB_OK;
+}
+
+// Host-only: the hair BCSDF tables tgb200_create would upload for one material (no GPU needed).
+// tables = 3 lobes (R, TT, TRT) x 64 x 64 x RGB, sums = 3 x 64 row sums, v = the three longitudinal variances.
+int tgb200_hair_selftest(float roughness, float scale_angle_deg, const float *sigma_a, float *tables, float *sums, float *v) {
+    if (!sigma_a || !tables || !sums || !v) return TGB_ERR_INVALID;
+    HairTables ht;
+    hair_precompute(roughness, scale_angle_deg, sigma_a, ht);
+    for (int p = 0; p < 3; ++p) {
+        std::memcpy(tables + size_t(p)*64*64*3, ht.lobe[p].table.data(), sizeof(float)*64*64*3);
+        std::memcpy(sums + p*64, ht.lobe[p].sums.data(), sizeof(float)*64);
+        v[p] = ht.v[p];
+    }
     return TGB_OK;
 }
 

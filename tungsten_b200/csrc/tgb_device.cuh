@@ -100,6 +100,9 @@ struct DBsdf {
     uint32_t type, lobes, dist; int albedo_tex, rough_tex;
     float ior, inv_ior; V3 eta, k; V3 scaled_sigma_a; float avg_transmittance, diffuse_fresnel, substrate_weight;
     uint32_t enable_t; int substrate;
+    // hair (HairBcsdf.cpp:422-446): lobe variances v_p = beta_p^2, cuticle tilt, and per lobe p = R, TT, TRT the 64x64 RGB table,
+    // the 64 normalised row pdfs / cdfs (65 entries per row) and the row sums
+    float hair_v[3], hair_scale_rad; const float *hair_table[3], *hair_pdfs[3], *hair_cdfs[3], *hair_sums[3];
 };
 enum : uint32_t { PF_EMISSIVE = 1, PF_SAMPLABLE = 2, PF_INFINITE = 4, PF_SMOOTH = 8 };
 struct DPrim {
@@ -108,6 +111,7 @@ struct DPrim {
     V3 base, edge0, edge1, normal; float inv_uv_sq0, inv_uv_sq1, area;      // quad
     V3 pos, scale; float rot[9], inv_rot[9];                                // cube / infinite sphere rotation
     float total_area; const float *tri_pdf, *tri_cdf; const float *light_verts;   // emissive meshes: p0 p1 p2 per tri
+    uint32_t curve_mode;                                                    // curves: TGB_CURVE_*; tri_first/n_tris = its segments' global ids
 };
 struct DCamera { V3 pos; float m[9]; float plane_dist, ratio, pixel_size_x; uint32_t res_x, res_y, filter; float filter_cdf[32]; float filter_bin; };
 
@@ -121,6 +125,9 @@ struct DScene {
     // global id -> primitive, shading records by global id (4 x float4 each)
     const float4 *tri_isect; const uint32_t *tri_global; const uint32_t *tri_prim; const float4 *tri_shade;
     const float4 *nodes; uint32_t n_nodes; uint32_t n_tris;
+    // curve segments share the arrays above: records n_tris.. of tri_isect hold a segment's three nodes (x, y, z, width),
+    // tri_global / tri_prim continue with global ids n_tris + segment
+    uint32_t n_curve_segs;
     // "cut": <= 16 boxes of the BVH's top levels that together cover every triangle (same padded boxes the nodes hold).
     // A ray that misses all of them is answered by the kernel that creates it and never reaches a traversal kernel.
     int n_cut; float cut[6][16];        // lo.x, hi.x, lo.y, hi.y, lo.z, hi.z
@@ -278,6 +285,8 @@ TGB_D float power_heuristic(float a, float b) { return (a*a)/(a*a + b*b); }     
 // ---------------------------------------------------------------- surface records
 struct Surface {            // IntersectionInfo (primitives/IntersectionInfo.hpp:11-22) + what evalDirect needs
     V3 Ng, Ns, p, w; float u, v; int prim, bsdf; bool backside;
+    float eps;              // IntersectionInfo::epsilon: 5e-4 (TraceableScene.hpp:39), raised by curves (Curves.cpp:512-515)
+    bool curve; V3 tangent; // curve hits: unnormalised BSpline::quadraticDeriv at the hit (for Curves::tangentSpace)
 };
 struct Event {              // SurfaceScatterEvent (samplerecords/SurfaceScatterEvent.hpp:14-66)
     Frame frame; V3 wi, wo, weight; float pdf; uint32_t requested, sampled; bool flipped;
@@ -621,7 +630,144 @@ TGB_D void coat_warp(const DBsdf &b, const Event &e, Event &q, float &Fi, float 
     q.wi = v3(e.wi.x*eta, e.wi.y*eta, copysignf(cosThetaTi, e.wi.z));
     q.wo = v3(e.wo.x*eta, e.wo.y*eta, copysignf(cosThetaTo, e.wo.z));
 }
+// HairBcsdf (bsdfs/HairBcsdf.cpp:24-160,183-315): longitudinal lobes M_p in closed form, azimuthal lobes N_p from the three
+// 64x64 tables the host precomputes (PrecomputedAzimuthalLobe + InterpolatedDistribution1D); the tables stay in L2.
+// Local frame: y along the fibre, z the shading normal.
+constexpr int kHairRes = 64;
+TGB_D float trig_inverse(float x) { return minf(sqrtf(maxf(1.0f - x*x, 0.0f)), 1.0f); }                  // MathUtil.hpp:100-103
+TGB_D float clampf(float v, float lo, float hi) { return minf(maxf(v, lo), hi); }
+TGB_D int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
+TGB_D float hair_I0(float x) {
+    float result = 1.0f, xSq = x*x, xi = xSq, denom = 4.0f;
+    for (int i = 1; i <= 10; ++i) { result += xi/denom; xi *= xSq; denom *= 4.0f*float((i + 1)*(i + 1)); }
+    return result;
+}
+TGB_D float hair_logI0(float x) {
+    if (x > 12.0f) return x + 0.5f*(logf(1.0f/(TWO_PI_F*x)) + 1.0f/(8.0f*x));
+    return logf(hair_I0(x));
+}
+TGB_D float hair_M(float v, float sinThetaI, float sinThetaO, float cosThetaI, float cosThetaO) {
+    float a = cosThetaI*cosThetaO/v;
+    float b = sinThetaI*sinThetaO/v;
+    if (v < 0.1f) return expf(-b + hair_logI0(a) - 1.0f/v + 0.6931f + logf(1.0f/(2.0f*v)));
+    return expf(-b)*hair_I0(a)/(2.0f*v*sinhf(1.0f/v));
+}
+TGB_D float hair_sampleM(float v, float sinThetaI, float cosThetaI, float xi1, float xi2) {
+    float cosTheta = 1.0f + v*logf(xi1 + (1.0f - xi1)*expf(-2.0f/v));
+    float sinTheta = trig_inverse(cosTheta);
+    float cosPhi = cosf(TWO_PI_F*xi2);
+    return -cosTheta*sinThetaI + sinTheta*cosPhi*cosThetaI;
+}
+struct HairLobe { const float *table, *pdfs, *cdfs, *sums; };
+TGB_D HairLobe hair_lobe(const DBsdf &b, int p) { HairLobe l; l.table = b.hair_table[p]; l.pdfs = b.hair_pdfs[p]; l.cdfs = b.hair_cdfs[p]; l.sums = b.hair_sums[p]; return l; }
+TGB_D void lobe_dist(float distribution, int &d0, int &d1, float &v) {          // InterpolatedDistribution1D.hpp:74-78
+    d0 = clampi(int(distribution), 0, kHairRes - 1);
+    d1 = d0 + 1 < kHairRes - 1 ? d0 + 1 : kHairRes - 1;
+    v = clampf(distribution - float(d0), 0.0f, 1.0f);
+}
+TGB_D float lobe_dist_pdf(const HairLobe &l, float distribution, int x) {
+    int d0, d1; float v; lobe_dist(distribution, d0, d1, v);
+    return __ldg(l.pdfs + x + d0*kHairRes)*(1.0f - v) + __ldg(l.pdfs + x + d1*kHairRes)*v;
+}
+TGB_D float lobe_weight(const HairLobe &l, float cosThetaD) {                   // PrecomputedAzimuthalLobe.hpp:64-68
+    float dist = float(kHairRes - 1)*cosThetaD;
+    int d0, d1; float v; lobe_dist(dist, d0, d1, v);
+    return (__ldg(l.sums + d0)*(1.0f - v) + __ldg(l.sums + d1)*v)*(TWO_PI_F/float(kHairRes));
+}
+TGB_D void lobe_sample(const HairLobe &l, float cosThetaD, float xi, float &phi, float &pdf) {   // :29-38 + warp (:74-99)
+    float dist = float(kHairRes - 1)*cosThetaD;
+    int d0, d1; float v; lobe_dist(dist, d0, d1, v);
+    int lower = 0, upper = kHairRes; float lowerU = 0.0f, upperU = 1.0f;
+    while (upper - lower != 1) {
+        int midpoint = (upper + lower)/2;
+        float midpointU = __ldg(l.cdfs + midpoint + d0*(kHairRes + 1))*(1.0f - v) + __ldg(l.cdfs + midpoint + d1*(kHairRes + 1))*v;
+        if (midpointU < xi) { lower = midpoint; lowerU = midpointU; } else { upper = midpoint; upperU = midpointU; }
+    }
+    xi = clampf((xi - lowerU)/(upperU - lowerU), 0.0f, 1.0f);
+    phi = TWO_PI_F*(float(lower) + xi)*(1.0f/float(kHairRes));
+    pdf = lobe_dist_pdf(l, dist, lower)*(float(kHairRes)*INV_TWO_PI_F);
+}
+TGB_D V3 lobe_eval(const HairLobe &l, float phi, float cosThetaD) {              // :40-54
+    float u = float(kHairRes - 1)*phi*INV_TWO_PI_F;
+    float v = float(kHairRes - 1)*cosThetaD;
+    int x0 = clampi(int(u), 0, kHairRes - 2), y0 = clampi(int(v), 0, kHairRes - 2);
+    int x1 = x0 + 1, y1 = y0 + 1;
+    u = clampf(u - float(x0), 0.0f, 1.0f); v = clampf(v - float(y0), 0.0f, 1.0f);
+    auto T = [&](int x, int y) { const float *t = l.table + 3*(x + y*kHairRes); return v3(__ldg(t), __ldg(t + 1), __ldg(t + 2)); };
+    return (T(x0, y0)*(1.0f - u) + T(x1, y0)*u)*(1.0f - v) + (T(x0, y1)*(1.0f - u) + T(x1, y1)*u)*v;
+}
+TGB_D float lobe_pdf(const HairLobe &l, float phi, float cosThetaD) {            // :56-61
+    float u = float(kHairRes - 1)*phi*INV_TWO_PI_F;
+    float v = float(kHairRes - 1)*cosThetaD;
+    return lobe_dist_pdf(l, v, int(u))*(float(kHairRes)*INV_TWO_PI_F);
+}
+struct HairAngles { float sinThetaO, cosThetaO, cosThetaI, cosThetaD, phi, thetaIR, thetaITT, thetaITRT; };
+TGB_D HairAngles hair_angles(const DBsdf &b, const Event &e) {
+    HairAngles a;
+    float sinThetaI = e.wi.y; a.sinThetaO = e.wo.y;
+    a.cosThetaI = trig_inverse(sinThetaI); a.cosThetaO = trig_inverse(a.sinThetaO);
+    float thetaI = asinf(clampf(sinThetaI, -1.0f, 1.0f)), thetaO = asinf(clampf(a.sinThetaO, -1.0f, 1.0f));
+    float thetaD = (thetaO - thetaI)*0.5f;
+    a.cosThetaD = cosf(thetaD);
+    a.phi = atan2f(e.wo.x, e.wo.z);
+    if (a.phi < 0.0f) a.phi += TWO_PI_F;
+    a.thetaIR = thetaI - 2.0f*b.hair_scale_rad; a.thetaITT = thetaI + b.hair_scale_rad; a.thetaITRT = thetaI + 4.0f*b.hair_scale_rad;
+    return a;
+}
+TGB_D V3 hair_eval(const DBsdf &b, const Event &e) {                             // HairBcsdf.cpp:183-216
+    if (!(e.requested & (LOBE_GLOSSY_R | LOBE_GLOSSY_T))) return v3s(0.0f);
+    HairAngles a = hair_angles(b, e);
+    float MR   = hair_M(b.hair_v[0], sinf(a.thetaIR),   a.sinThetaO, cosf(a.thetaIR),   a.cosThetaO);
+    float MTT  = hair_M(b.hair_v[1], sinf(a.thetaITT),  a.sinThetaO, cosf(a.thetaITT),  a.cosThetaO);
+    float MTRT = hair_M(b.hair_v[2], sinf(a.thetaITRT), a.sinThetaO, cosf(a.thetaITRT), a.cosThetaO);
+    return lobe_eval(hair_lobe(b, 0), a.phi, a.cosThetaD)*MR + lobe_eval(hair_lobe(b, 1), a.phi, a.cosThetaD)*MTT
+         + lobe_eval(hair_lobe(b, 2), a.phi, a.cosThetaD)*MTRT;
+}
+TGB_D float hair_pdf(const DBsdf &b, const Event &e) {                           // :280-315
+    if (!(e.requested & (LOBE_GLOSSY_R | LOBE_GLOSSY_T))) return 0.0f;
+    HairAngles a = hair_angles(b, e);
+    float weightR = lobe_weight(hair_lobe(b, 0), a.cosThetaI), weightTT = lobe_weight(hair_lobe(b, 1), a.cosThetaI),
+          weightTRT = lobe_weight(hair_lobe(b, 2), a.cosThetaI);
+    float weightSum = weightR + weightTT + weightTRT;
+    float pdfR   = weightR  *hair_M(b.hair_v[0], sinf(a.thetaIR),   a.sinThetaO, cosf(a.thetaIR),   a.cosThetaO);
+    float pdfTT  = weightTT *hair_M(b.hair_v[1], sinf(a.thetaITT),  a.sinThetaO, cosf(a.thetaITT),  a.cosThetaO);
+    float pdfTRT = weightTRT*hair_M(b.hair_v[2], sinf(a.thetaITRT), a.sinThetaO, cosf(a.thetaITRT), a.cosThetaO);
+    return (1.0f/weightSum)*(pdfR*lobe_pdf(hair_lobe(b, 0), a.phi, a.cosThetaD) + pdfTT*lobe_pdf(hair_lobe(b, 1), a.phi, a.cosThetaD)
+                             + pdfTRT*lobe_pdf(hair_lobe(b, 2), a.phi, a.cosThetaD));
+}
+TGB_D bool hair_sample(const DBsdf &b, Sampler &smp, Event &e) {                 // :218-278 (4 Sobol dimensions)
+    if (!(e.requested & (LOBE_GLOSSY_R | LOBE_GLOSSY_T))) return false;
+    float xiNx = sampler_next1d(smp), xiNy = sampler_next1d(smp);
+    float xiMx = sampler_next1d(smp), xiMy = sampler_next1d(smp);
+    float sinThetaI = e.wi.y;
+    float cosThetaI = trig_inverse(sinThetaI);
+    float thetaI = asinf(clampf(sinThetaI, -1.0f, 1.0f));
+    float thetaIR = thetaI - 2.0f*b.hair_scale_rad, thetaITT = thetaI + b.hair_scale_rad, thetaITRT = thetaI + 4.0f*b.hair_scale_rad;
+    float weightR = lobe_weight(hair_lobe(b, 0), cosThetaI), weightTT = lobe_weight(hair_lobe(b, 1), cosThetaI),
+          weightTRT = lobe_weight(hair_lobe(b, 2), cosThetaI);
+    int p; float theta;
+    float target = xiNx*(weightR + weightTT + weightTRT);
+    if (target < weightR) { p = 0; theta = thetaIR; }
+    else if (target < weightR + weightTT) { p = 1; theta = thetaITT; }
+    else { p = 2; theta = thetaITRT; }
+    float sinThetaO = hair_sampleM(b.hair_v[p], sinf(theta), cosf(theta), xiMx, xiMy);
+    float cosThetaO = trig_inverse(sinThetaO);
+    float thetaO = asinf(clampf(sinThetaO, -1.0f, 1.0f));
+    float thetaD = (thetaO - thetaI)*0.5f;
+    float cosThetaD = cosf(thetaD);
+    float phi, phiPdf;
+    lobe_sample(hair_lobe(b, p), cosThetaD, xiNy, phi, phiPdf);
+    float sinPhi = sinf(phi), cosPhi = cosf(phi);
+    e.wo = v3(sinPhi*cosThetaO, sinThetaO, cosPhi*cosThetaO);
+    e.pdf = hair_pdf(b, e);
+    e.weight = hair_eval(b, e)/e.pdf;
+    e.sampled = LOBE_GLOSSY_R | LOBE_GLOSSY_T;
+    return true;
+}
+
+template <bool HAIR = false>
 TGB_D bool bsdf_sample(const DScene &sc, const DBsdf &b, const Surface &s, Sampler &smp, Event &e) {
+    if (HAIR && b.type == TGB_BSDF_HAIR) return hair_sample(b, smp, e);      // Bsdf::eta() is 1 for the BCSDF
     if (b.type != TGB_BSDF_SMOOTH_COAT) {
         if (!bsdf_sample_base(sc, b, s, smp, e)) return false;
         e.weight = e.weight*sqr(bsdf_eta(b, e));
@@ -665,7 +811,9 @@ TGB_D bool bsdf_sample(const DScene &sc, const DBsdf &b, const Surface &s, Sampl
     }
     return true;
 }
+template <bool HAIR = false>
 TGB_D V3 bsdf_eval(const DScene &sc, const DBsdf &b, const Surface &s, const Event &e) {
+    if (HAIR && b.type == TGB_BSDF_HAIR) return hair_eval(b, e);
     if (b.type != TGB_BSDF_SMOOTH_COAT) return bsdf_eval_base(sc, b, s, e)*sqr(bsdf_eta(b, e));
     const DBsdf &sub = sc.bsdfs[b.substrate];
     if (e.wi.z <= 0.0f || e.wo.z <= 0.0f) return v3s(0.0f);
@@ -682,7 +830,9 @@ TGB_D V3 bsdf_eval(const DScene &sc, const DBsdf &b, const Surface &s, const Eve
     }
     return v3s(0.0f);
 }
+template <bool HAIR = false>
 TGB_D float bsdf_pdf(const DScene &sc, const DBsdf &b, const Surface &s, const Event &e) {
+    if (HAIR && b.type == TGB_BSDF_HAIR) return hair_pdf(b, e);
     if (b.type != TGB_BSDF_SMOOTH_COAT) return bsdf_pdf_base(sc, b, s, e);
     const DBsdf &sub = sc.bsdfs[b.substrate];
     if (e.wi.z <= 0.0f || e.wo.z <= 0.0f) return 0.0f;

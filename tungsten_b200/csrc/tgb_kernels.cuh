@@ -25,6 +25,7 @@ struct PathState {
     float *ndx, *ndy, *ndz, *ndist, *nfx, *nfy, *nfz, *npl, *npb;
     float *mdx, *mdy, *mdz, *mwx, *mwy, *mwz, *mpb;
     int *qlight;                                        // light primitive of this bounce's queries
+    float *eps;                                         // IntersectionInfo::epsilon of the shading point (scenes with curves only)
     uint32_t *pid;                                      // path index within the step: sample_rel*n_pix + pixel_list_index
     // packed copies for the traversal kernel, which visits the paths in ray-coherence order (gathers 32 B + 16 B per ray):
     float4 *ra, *rb;                                    // (o.xyz, tmin), (d.xyz, 0)
@@ -105,6 +106,93 @@ TGB_D bool analytic_any(const DScene &sc, V3 o, V3 d, float tnear, float tfar, i
     return false;
 }
 
+
+// ---- curve segments (primitives/Curves.cpp:51-99,134-221,223-227,431-470) ---------------------
+// A segment = three consecutive B-spline nodes (x, y, z, width), projected into the ray's frame (x, y across the ray,
+// z along it) and bisected five times (Nakamaru & Ohno); the 32 leaf pieces are tested as half cylinders.
+struct CurveFrame { V3 lx, ly; };
+TGB_D CurveFrame curve_frame(V3 lz) {
+    CurveFrame f;
+    float d = sqrtf(lz.x*lz.x + lz.z*lz.z);
+    if (d == 0.0f) { f.lx = v3(1.0f, 0.0f, 0.0f); f.ly = v3(0.0f, 0.0f, -lz.y); }
+    else { f.lx = v3(lz.z/d, 0.0f, -lz.x/d); f.ly = v3(f.lx.z*lz.y, d, -lz.y*f.lx.x); }
+    return f;
+}
+TGB_D float4 f4add(float4 a, float4 b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
+TGB_D float4 f4sub(float4 a, float4 b) { return make_float4(a.x - b.x, a.y - b.y, a.z - b.z, a.w - b.w); }
+TGB_D float4 f4scale(float4 a, float s) { return make_float4(a.x*s, a.y*s, a.z*s, a.w*s); }
+TGB_D float4 curve_project(V3 o, const CurveFrame &f, V3 lz, float4 q) {
+    V3 p = v3(q.x - o.x, q.y - o.y, q.z - o.z);
+    return make_float4(dot(f.lx, p), dot(f.ly, p), dot(lz, p), q.w);
+}
+struct CurvePiece { float4 p0, p1; float tMin, tMax; int depth; };
+// intersectHalfCylinder: updates (t, u, w) and the closest depth when the flattened piece is hit in (tMin, tMax)
+TGB_D void curve_half_cylinder(const CurvePiece &node, float tMin, float &tMax, float &ht, float &hu, float &hw) {
+    float vx = node.p1.x - node.p0.x, vy = node.p1.y - node.p0.y;
+    float lengthSq = 0.0f; lengthSq += vx*vx; lengthSq += vy*vy;
+    float invLengthSq = 1.0f/lengthSq;
+    float invLength = sqrtf(invLengthSq);
+    float d0 = node.p0.x*vx; d0 += node.p0.y*vy;
+    float segmentT = -d0*invLengthSq;
+    float signedUnnormalized = node.p0.x*vy - node.p0.y*vx;
+    float distance = fabsf(signedUnnormalized)*invLength;
+    float width = node.p0.w*(1.0f - segmentT) + node.p1.w*segmentT;
+    if (distance > width) return;
+    float depth = node.p0.z*(1.0f - segmentT) + node.p1.z*segmentT;
+    float dz = node.p1.z - node.p0.z;
+    float ySq = sqr(width) - sqr(distance);
+    float lSq = ySq*(1.0f + dz*dz*invLengthSq);
+    float deltaT = sqrtf(maxf(lSq, 0.0f));
+    float t0 = depth - deltaT;
+    V3 w3 = v3(node.p0.x - node.p1.x, node.p0.y - node.p1.y, node.p0.z - node.p1.z);
+    lengthSq = 0.0f; lengthSq += w3.x*w3.x; lengthSq += w3.y*w3.y; lengthSq += w3.z*w3.z;
+    segmentT = dot(v3(node.p0.x, node.p0.y, node.p0.z - t0), w3)/lengthSq;
+    if (segmentT < 0.0f || t0 >= tMax || t0 <= tMin) return;
+    float newT = segmentT*(node.tMax - node.tMin) + node.tMin;
+    if (newT >= 0.0f && newT <= 1.0f) { hu = newT; ht = t0; hw = width; tMax = t0; }
+}
+// pointOnSpline<false>: p0..p2 are the projected nodes; true when a hit closer than tMax was found (t, u, w are set)
+TGB_D bool curve_point_on_spline(float4 p0, float4 p1, float4 p2, float tMin, float tMax, float &ht, float &hu, float &hw) {
+    constexpr int MaxDepth = 5;
+    CurvePiece stack[MaxDepth]; int sp = 0;
+    float4 q0 = f4add(f4sub(f4scale(p0, 0.5f), p1), f4scale(p2, 0.5f));
+    float4 q1 = f4sub(p1, p0);
+    float4 q2 = f4scale(f4add(p0, p1), 0.5f);
+    float tFlatX = -q1.x*0.5f/q0.x, tFlatY = -q1.y*0.5f/q0.y;
+    float xFlat = q0.x*tFlatX*tFlatX + q1.x*tFlatX + q2.x;
+    float yFlat = q0.y*tFlatY*tFlatY + q1.y*tFlatY + q2.y;
+    CurvePiece cur; cur.p0 = q2; cur.p1 = f4add(f4add(q0, q1), q2); cur.tMin = 0.0f; cur.tMax = 1.0f; cur.depth = 0;
+    float closestDepth = tMax;
+    for (;;) {
+        float pMinX = cur.p1.x < cur.p0.x ? cur.p1.x : cur.p0.x, pMinY = cur.p1.y < cur.p0.y ? cur.p1.y : cur.p0.y;
+        float pMaxX = cur.p1.x > cur.p0.x ? cur.p1.x : cur.p0.x, pMaxY = cur.p1.y > cur.p0.y ? cur.p1.y : cur.p0.y;
+        if (tFlatX > cur.tMin && tFlatX < cur.tMax) { pMinX = minf(pMinX, xFlat); pMaxX = maxf(pMaxX, xFlat); }
+        if (tFlatY > cur.tMin && tFlatY < cur.tMax) { pMinY = minf(pMinY, yFlat); pMaxY = maxf(pMaxY, yFlat); }
+        float maxWidth = maxf(cur.p0.w, cur.p1.w);
+        if (pMinX <= maxWidth && pMinY <= maxWidth && pMaxX >= -maxWidth && pMaxY >= -maxWidth) {
+            if (cur.depth >= MaxDepth) {
+                curve_half_cylinder(cur, tMin, closestDepth, ht, hu, hw);
+            } else {
+                float splitT = (cur.tMin + cur.tMax)*0.5f;
+                float4 qSplit = f4add(f4add(f4scale(q0, splitT*splitT), f4scale(q1, splitT)), q2);
+                CurvePiece &top = stack[sp++];
+                if (cur.p0.z < qSplit.z) {
+                    top.tMin = splitT; top.tMax = cur.tMax; top.p0 = qSplit; top.p1 = cur.p1; top.depth = cur.depth + 1;
+                    cur.tMax = splitT; cur.p1 = qSplit; cur.depth = cur.depth + 1;
+                } else {
+                    top.tMin = cur.tMin; top.tMax = splitT; top.p0 = cur.p0; top.p1 = qSplit; top.depth = cur.depth + 1;
+                    cur.tMin = splitT; cur.p0 = qSplit; cur.depth = cur.depth + 1;
+                }
+                continue;
+            }
+        }
+        do {
+            if (sp == 0) return closestDepth < tMax;
+            cur = stack[--sp];
+        } while (minf(cur.p0.z - cur.p0.w, cur.p1.z - cur.p1.w) > closestDepth);
+    }
+}
+
 // Traversal stack: the first kSmemStack entries of every lane live in shared memory, laid out [entry][thread] so
 // that lane i always hits bank i (conflict-free whatever the lanes' depths); deeper entries spill to local memory.
 constexpr int kSmemStack = 32;
@@ -144,8 +232,13 @@ struct TravStack {
 #define TGB_SLAB_T float tmn = fmaxf(fmaxf(fmaxf(ax, ay), az), tnear); float tmx = fminf(fminf(fminf(bx, by), bz), h.t);
 #define TGB_CSWAP(ta, la, tb, lb) { bool sw_ = tb < ta; float tt_ = sw_ ? tb : ta; tb = sw_ ? ta : tb; ta = tt_; \
                                     int ll_ = sw_ ? lb : la; lb = sw_ ? la : lb; la = ll_; }
+// CURVES: leaves whose code has bit 2 set hold curve segments (three float4 nodes per record, stored after the triangles);
+// a curve hit keeps (t, position along the segment, interpolated width) in (t, u, v) and id >= n_tris.
+template <bool CURVES>
 TGB_D void bvh_traverse(const DScene &sc, int *smem_stack, V3 o, V3 d, float tnear, bool any, Hit &h) {
     const float4 *nodes = sc.nodes;
+    CurveFrame cf;
+    if (CURVES) cf = curve_frame(d);
     TravStack stk; stk.smem = smem_stack + threadIdx.x; stk.sp = 0;
     const float ooeps = 1e-30f;
     const float idx = 1.0f/(fabsf(d.x) > ooeps ? d.x : copysignf(ooeps, d.x));
@@ -185,7 +278,18 @@ TGB_D void bvh_traverse(const DScene &sc, int *smem_stack, V3 o, V3 d, float tne
             }
         }
         int code = ~cur;
-        int first = code >> 3, count = (code & 7) + 1;
+        int first = code >> 3, count = (code & 3) + 1;
+        if (CURVES && (code & 4)) {
+            for (int i = 0; i < count; ++i) {
+                const float4 *cr = sc.tri_isect + 3*size_t(first + i);
+                float4 q0 = curve_project(o, cf, d, __ldg(cr)), q1 = curve_project(o, cf, d, __ldg(cr + 1)), q2 = curve_project(o, cf, d, __ldg(cr + 2));
+                float ht, hu, hw;
+                if (curve_point_on_spline(q0, q1, q2, tnear, h.t, ht, hu, hw)) {
+                    h.t = ht; h.u = hu; h.v = hw; h.id = first + i;
+                    if (any) return;
+                }
+            }
+        } else
         for (int i = 0; i < count; ++i) {
             const float4 *tr = sc.tri_isect + 3*size_t(first + i);
             const float4 a = __ldg(tr), b = __ldg(tr + 1), c = __ldg(tr + 2);
@@ -230,22 +334,48 @@ TGB_D bool mesh_cut_hit(const DScene &sc, V3 o, V3 d, float tnear, float tfar) {
 }
 
 // Policy wrapper kept for the three users (path rays, shadow queries, parity hook): one ray per thread.
-template <class P>
+template <bool CURVES, class P>
 TGB_D void bvh_traverse_multi(const DScene &sc, int *smem_stack, P &pol, uint32_t n, uint32_t /*K*/) {
     uint32_t i = blockIdx.x*blockDim.x + threadIdx.x;
     if (i >= n) return;
     V3 o, d; float tnear; Hit h; bool any;
     if (!pol.fetch(i, o, d, tnear, h, any)) return;
-    bvh_traverse(sc, smem_stack, o, d, tnear, any, h);
+    bvh_traverse<CURVES>(sc, smem_stack, o, d, tnear, any, h);
     pol.finish(h);
 }
 
 // Fill a Surface from a hit: Primitive::intersectionInfo for mesh/quad/cube
 // (TriangleMesh.cpp:323-331,344-355; Quad.cpp:112-120; Cube.cpp:157-171) + TraceableScene::intersect (:183-188)
+template <bool CURVES>
 TGB_D void make_surface(const DScene &sc, const Hit &h, V3 o, V3 d, Surface &s) {
     s.p = o + d*h.t;
     s.w = d;
-    if (h.id >= 0) {
+    s.eps = 5e-4f; s.curve = false;
+    if (CURVES && h.id >= int(sc.n_tris)) {
+        // Curves::intersectionInfo (primitives/Curves.cpp:484-516); the record holds the segment's three nodes
+        uint32_t g = __ldg(sc.tri_global + h.id);
+        int pi = int(__ldg(sc.tri_prim + g));
+        const DPrim &c = sc.prims[pi];
+        s.prim = pi; s.curve = true; s.backside = false;
+        const float4 *cr = sc.tri_isect + 3*size_t(h.id);
+        const float4 n0 = __ldg(cr), n1 = __ldg(cr + 1), n2 = __ldg(cr + 2);
+        float t = h.u;
+        V3 a0 = v3(n0.x, n0.y, n0.z), a1 = v3(n1.x, n1.y, n1.z), a2 = v3(n2.x, n2.y, n2.z);
+        s.tangent = (a0 - a1*2.0f + a2)*t + (a1 - a0);                                       // BSpline::quadraticDeriv
+        V3 tangent = normalize(s.tangent);
+        if (c.curve_mode == TGB_CURVE_BCSDF_CYLINDER) {
+            V3 mw = -d;
+            s.Ng = s.Ns = normalize(mw - tangent*dot(tangent, mw));
+        } else {
+            V3 point = (a0*0.5f - a1 + a2*0.5f)*t*t + (a1 - a0)*t + (a0 + a1)*0.5f;          // BSpline::quadratic
+            V3 localP = s.p - point;
+            localP = localP - tangent*dot(localP, tangent);
+            s.Ng = s.Ns = normalize(localP);
+        }
+        s.u = h.u; s.v = 0.5f;            // CurveIntersection::uv.y (distance across the strand) is not kept: constant textures only
+        s.bsdf = int(__ldg(sc.slots + c.bsdf_first));
+        s.eps = maxf(s.eps, (c.curve_mode == TGB_CURVE_CYLINDER ? 0.1f : 0.01f)*h.v);
+    } else if (h.id >= 0) {
         uint32_t g = __ldg(sc.tri_global + h.id);
         int pi = int(__ldg(sc.tri_prim + g));
         const DPrim &m = sc.prims[pi];
@@ -391,11 +521,12 @@ struct PathRayPolicy {
     }
     TGB_D void finish(const Hit &h) { st.h4[s] = pack_hit(h); }
 };
+template <bool CURVES>
 __global__ void __launch_bounds__(kTraceBlock, TGB_MINB) k_trace(DScene sc, PathState st, const uint32_t *order, const uint32_t *n_sorted,
                                                                  uint32_t n_surv, uint32_t n, uint32_t K) {
     extern __shared__ int smem_stack[];
     PathRayPolicy pol; pol.st = st; pol.order = order; pol.n_sorted = n_sorted; pol.n_surv = n_surv; pol.n_all = n; pol.s = 0;
-    bvh_traverse_multi(sc, smem_stack, pol, n, K);
+    bvh_traverse_multi<CURVES>(sc, smem_stack, pol, n, K);
 }
 
 // Parity hook (tgb200_trace_closest): rays in AoS tgb_ray, hits out as tgb_hit, through the same analytic pass and
@@ -415,10 +546,11 @@ __global__ void __launch_bounds__(256) k_hook_analytic(DScene sc, const tgb_ray 
     if (i >= n) return;
     out[i] = analytic_closest(sc, v3(rays[i].o[0], rays[i].o[1], rays[i].o[2]), v3(rays[i].d[0], rays[i].d[1], rays[i].d[2]), rays[i].tmin, rays[i].tmax);
 }
+template <bool CURVES>
 __global__ void __launch_bounds__(kTraceBlock) k_hook_bvh(DScene sc, const tgb_ray *rays, Hit *out, uint32_t n, uint32_t K) {
     extern __shared__ int smem_stack[];
     HookPolicy pol; pol.rays = rays; pol.out = out; pol.i = 0;
-    bvh_traverse_multi(sc, smem_stack, pol, n, K);
+    bvh_traverse_multi<CURVES>(sc, smem_stack, pol, n, K);
 }
 __global__ void __launch_bounds__(256) k_hook_finish(DScene sc, const tgb_ray *rays, const Hit *in, tgb_hit *hits, uint32_t n) {
     uint32_t i = blockIdx.x*blockDim.x + threadIdx.x;
@@ -427,7 +559,7 @@ __global__ void __launch_bounds__(256) k_hook_finish(DScene sc, const tgb_ray *r
     Hit h = in[i];
     tgb_hit out; out.primitive = -1; out.prim_id = 0; out.t = h.t; out.u = 0.0f; out.v = 0.0f; out.backside = 0;
     if (h.id != HID_MISS) {
-        Surface s; make_surface(sc, h, o, d, s);
+        Surface s; make_surface<true>(sc, h, o, d, s);
         out.primitive = s.prim; out.backside = s.backside ? 1u : 0u;
         if (h.id >= 0) { uint32_t g = sc.tri_global[h.id]; out.prim_id = int(g - sc.prims[s.prim].tri_first); out.u = h.u; out.v = h.v; }
         else if (sc.prims[s.prim].type == TGB_PRIM_QUAD) { out.u = h.u; out.v = h.v; }
@@ -436,6 +568,7 @@ __global__ void __launch_bounds__(256) k_hook_finish(DScene sc, const tgb_ray *r
 }
 
 // handleSurface (integrators/TraceBase.cpp:516-568) + the loop tail of traceSample (PathTracer.cpp:108-126)
+template <bool CURVES>
 __global__ void __launch_bounds__(128) k_shade(DScene sc, PathState st, BatchInfo bi, uint32_t n,
                                                uint32_t *squeue, uint32_t *scount, Counters *ctr) {
     uint32_t i = blockIdx.x*blockDim.x + threadIdx.x;
@@ -475,14 +608,22 @@ __global__ void __launch_bounds__(128) k_shade(DScene sc, PathState st, BatchInf
                 smp.index = bi.spp_begin + path/bi.n_pix;
                 smp.scramble = __ldg(bi.pix_seed + pix) ^ hash32(__ldg(bi.pix_id + pix));
             }
-            Surface sf; make_surface(sc, h, o, d, sf);
+            Surface sf; make_surface<CURVES>(sc, h, o, d, sf);
             const DBsdf &b = sc.bsdfs[sf.bsdf];
-            const float epsilon = 5e-4f;                                                     // TraceableScene.hpp:39
+            const float epsilon = sf.eps;                                                    // IntersectionInfo::epsilon
+            if (CURVES) st.eps[s] = epsilon;
 
             // makeLocalScatterEvent (TraceBase.cpp:24-51)
             Event e;
             {
                 Frame frame = frame_from_normal(sf.Ns);
+                if (CURVES && sf.curve && (b.lobes & LOBE_ANISO)) {
+                    // anisotropic lobe: Curves::tangentSpace (Curves.cpp:518-530) + Primitive::setupTangentFrame (Primitive.cpp:134-162)
+                    V3 B = normalize(sf.tangent);
+                    V3 T = cross(B, sf.Ng), N = sf.Ns;
+                    T = T - N*dot(N, T);
+                    if (!is_zero(T)) { T = normalize(T); frame.n = N; frame.t = T; frame.b = cross(N, T); }
+                }
                 bool hitBackside = dot(frame.n, d) > 0.0f;
                 bool isTransmissive = (b.lobes & LOBE_TRANSMISSIVE) != 0;
                 bool flipFrame = set.enable_two_sided_shading && hitBackside && !isTransmissive;
@@ -512,9 +653,9 @@ __global__ void __launch_bounds__(128) k_shade(DScene sc, PathState st, BatchInf
                             ok = (dot(ls.d, sf.Ng) < 0.0f) == ((e.wo.z < 0.0f) != e.flipped);
                         if (ok) {
                             e.requested = LOBE_ALL_BUT_SPECULAR;
-                            V3 f = bsdf_eval(sc, b, sf, e);
+                            V3 f = bsdf_eval<CURVES>(sc, b, sf, e);
                             if (!is_zero(f)) {
-                                float pdfB = bsdf_pdf(sc, b, sf, e);
+                                float pdfB = bsdf_pdf<CURVES>(sc, b, sf, e);
                                 if (l.type == TGB_PRIM_MESH) {
                                     qn = true; qn_any = false;
                                     st.ndist[s] = ls.dist; st.nfx[s] = f.x; st.nfy[s] = f.y; st.nfz[s] = f.z;
@@ -543,7 +684,7 @@ __global__ void __launch_bounds__(128) k_shade(DScene sc, PathState st, BatchInf
                     }
                     // bsdfSample (TraceBase.cpp:287-321)
                     e.requested = LOBE_ALL_BUT_SPECULAR;
-                    if (bsdf_sample(sc, b, sf, smp, e) && !is_zero(e.weight)) {
+                    if (bsdf_sample<CURVES>(sc, b, sf, smp, e) && !is_zero(e.weight)) {
                         V3 wo = to_global(e.frame, e.wo);
                         bool ok = true;
                         if (set.enable_consistency_checks)
@@ -600,7 +741,7 @@ __global__ void __launch_bounds__(128) k_shade(DScene sc, PathState st, BatchInf
             // continuation sample (TraceBase.cpp:545-565)
             uint32_t status = 0;
             e.requested = LOBE_ALL;
-            bool cont = bsdf_sample(sc, b, sf, smp, e);
+            bool cont = bsdf_sample<CURVES>(sc, b, sf, smp, e);
             V3 wo = v3s(0.0f);
             if (cont) {
                 wo = to_global(e.frame, e.wo);
@@ -659,10 +800,11 @@ TGB_D void shadow_store_any(PathState &st, uint32_t s, bool mis) {
     if (!mis) { st.lx[s] = st.nfx[s]; st.ly[s] = st.nfy[s]; st.lz[s] = st.nfz[s]; }
     else { st.bx[s] = st.mwx[s]; st.by[s] = st.mwy[s]; st.bz[s] = st.mwz[s]; }
 }
+template <bool CURVES>
 TGB_D void shadow_resolve_closest(const DScene &sc, PathState &st, uint32_t s, bool mis, int li, V3 p, V3 d, const Hit &h) {
     if (h.id == HID_MISS) return;
     const DPrim &l = sc.prims[li];
-    Surface ls; make_surface(sc, h, p, d, ls);
+    Surface ls; make_surface<CURVES>(sc, h, p, d, ls);
     bool visible = ls.prim == li;
     if (visible && !mis && h.t*(1.0f + 1e-3f) < st.ndist[s]) visible = false;                   // TraceBase.cpp:160
     if (!visible) return;
@@ -683,6 +825,7 @@ TGB_D void shadow_resolve_closest(const DScene &sc, PathState &st, uint32_t s, b
     }
 }
 
+template <bool CURVES>
 __global__ void __launch_bounds__(256) k_shadow_prep(DScene sc, PathState st, ShadowState ss, const uint32_t *squeue, const uint32_t *scount,
                                                       uint32_t *squeue2, uint32_t *scount2, Counters *ctr) {
     uint32_t i = blockIdx.x*blockDim.x + threadIdx.x;
@@ -694,13 +837,14 @@ __global__ void __launch_bounds__(256) k_shadow_prep(DScene sc, PathState st, Sh
         V3 p = v3(st.px[s], st.py[s], st.pz[s]);
         V3 d = mis ? v3(st.mdx[s], st.mdy[s], st.mdz[s]) : v3(st.ndx[s], st.ndy[s], st.ndz[s]);
         int li = st.qlight[s];
+        const float eps = CURVES ? st.eps[s] : 5e-4f;                 // info.epsilon of the shading point (TraceBase.cpp:254,295)
         if (any) {
             float tfar = mis ? st.mpb[s] : st.ndist[s];
-            blocked = analytic_any(sc, p, d, 5e-4f, tfar, li);
-            if (!blocked) { if (!mesh_cut_hit(sc, p, d, 5e-4f, tfar)) shadow_store_any(st, s, mis); else keep = true; }
+            blocked = analytic_any(sc, p, d, eps, tfar, li);
+            if (!blocked) { if (!mesh_cut_hit(sc, p, d, eps, tfar)) shadow_store_any(st, s, mis); else keep = true; }
         } else {
-            h = analytic_closest(sc, p, d, 5e-4f, INFINITY);
-            if (!mesh_cut_hit(sc, p, d, 5e-4f, h.t)) { blocked = h.id != HID_MISS; shadow_resolve_closest(sc, st, s, mis, li, p, d, h); }
+            h = analytic_closest(sc, p, d, eps, INFINITY);
+            if (!mesh_cut_hit(sc, p, d, eps, h.t)) { blocked = h.id != HID_MISS; shadow_resolve_closest<CURVES>(sc, st, s, mis, li, p, d, h); }
             else keep = true;
         }
     }
@@ -718,6 +862,7 @@ __global__ void __launch_bounds__(256) k_shadow_prep(DScene sc, PathState st, Sh
     }
 }
 
+template <bool CURVES>
 struct ShadowPolicy {
     DScene sc; PathState st; ShadowState ss; const uint32_t *squeue2; unsigned long long *hits;
     uint32_t s; bool mis, any; int li; V3 p, d;
@@ -727,7 +872,7 @@ struct ShadowPolicy {
         p = v3(st.px[s], st.py[s], st.pz[s]);
         d = mis ? v3(st.mdx[s], st.mdy[s], st.mdz[s]) : v3(st.ndx[s], st.ndy[s], st.ndz[s]);
         li = st.qlight[s];
-        o = p; dd = d; tnear = 5e-4f; anyq = any;
+        o = p; dd = d; tnear = CURVES ? st.eps[s] : 5e-4f; anyq = any;
         if (any) { h.t = mis ? st.mpb[s] : st.ndist[s]; h.u = 0.0f; h.v = 0.0f; h.id = HID_MISS; }
         else { h.t = ss.qt[i]; h.u = ss.qu[i]; h.v = ss.qv[i]; h.id = ss.qid[i]; }
         return true;
@@ -735,14 +880,15 @@ struct ShadowPolicy {
     TGB_D void finish(const Hit &h) {
         if (h.id != HID_MISS) atomicAdd(hits, 1ull);
         if (any) { if (h.id == HID_MISS) shadow_store_any(st, s, mis); }
-        else shadow_resolve_closest(sc, st, s, mis, li, p, d, h);
+        else shadow_resolve_closest<CURVES>(sc, st, s, mis, li, p, d, h);
     }
 };
+template <bool CURVES>
 __global__ void __launch_bounds__(kTraceBlock, TGB_MINB) k_shadow_bvh(DScene sc, PathState st, ShadowState ss, const uint32_t *squeue2, const uint32_t *scount2,
                                                             Counters *ctr, uint32_t K) {
     extern __shared__ int smem_stack[];
-    ShadowPolicy pol; pol.sc = sc; pol.st = st; pol.ss = ss; pol.squeue2 = squeue2; pol.hits = &ctr->shadow_hits;
-    bvh_traverse_multi(sc, smem_stack, pol, *scount2, K);
+    ShadowPolicy<CURVES> pol; pol.sc = sc; pol.st = st; pol.ss = ss; pol.squeue2 = squeue2; pol.hits = &ctr->shadow_hits;
+    bvh_traverse_multi<CURVES>(sc, smem_stack, pol, *scount2, K);
 }
 
 // Fold this bounce's direct light + surface emission into the path (order as in handleSurface:537-543), apply the
