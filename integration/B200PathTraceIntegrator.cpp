@@ -6,6 +6,10 @@
 #include "cameras/PinholeCamera.hpp"
 #include "primitives/InfiniteSphere.hpp"
 #include "primitives/TriangleMesh.hpp"
+#include "primitives/Curves.hpp"
+#include "bsdfs/HairBcsdf.hpp"
+#include "io/CurveIO.hpp"
+#include "sampling/UniformSampler.hpp"
 #include "primitives/Quad.hpp"
 #include "primitives/Cube.hpp"
 #include "bsdfs/RoughDielectricBsdf.hpp"
@@ -40,6 +44,9 @@ struct Flattener
     std::vector<std::vector<float>> texelStore;
     std::vector<std::vector<tgb_vertex>> vertStore;
     std::vector<std::vector<tgb_triangle>> triStore;
+    std::vector<std::vector<Vec4f>> nodeStore;
+    std::vector<std::vector<uint32_t>> segStore;
+    rapidjson::Document jsonDoc;    // allocator for the toJson() calls that read back private parameters
     std::map<const Bsdf *, int> bsdfIds;
     std::map<const Texture *, int> texIds;
 
@@ -140,6 +147,25 @@ struct Flattener
             o.thickness = sc->thickness();
             put(o.sigma_a, sc->sigmaA());
             o.substrate = bsdf(sc->substrate().get());
+        } else if (const HairBcsdf *hb = dynamic_cast<const HairBcsdf *>(b)) {
+            // HairBcsdf keeps its parameters private; its own toJson() returns them (HairBcsdf.cpp:173-181),
+            // the melanin mix is HairBcsdf::prepareForRender's (:435-443)
+            o.type = TGB_BSDF_HAIR;
+            rapidjson::Value v = hb->toJson(jsonDoc.GetAllocator());
+            o.hair_scale_angle_deg = float(v["scale_angle"].GetDouble());
+            o.hair_roughness = float(v["roughness"].GetDouble());
+            Vec3f sigmaA;
+            if (v.HasMember("sigma_a")) {
+                const rapidjson::Value &s = v["sigma_a"];
+                sigmaA = s.IsArray() ? Vec3f(float(s[0u].GetDouble()), float(s[1u].GetDouble()), float(s[2u].GetDouble()))
+                                     : Vec3f(float(s.GetDouble()));
+            } else {
+                const Vec3f eumelaninSigmaA = Vec3f(0.419f, 0.697f, 1.37f);
+                const Vec3f pheomelaninSigmaA = Vec3f(0.187f, 0.4f, 1.05f);
+                sigmaA = float(v["melanin_concentration"].GetDouble())
+                        *lerp(eumelaninSigmaA, pheomelaninSigmaA, float(v["melanin_ratio"].GetDouble()));
+            }
+            put(o.sigma_a, sigmaA);
         } else {
             FAIL("b200_path_tracer: BSDF type outside the hot path");
         }
@@ -180,6 +206,59 @@ struct Flattener
             }
             o.verts = vs.data(); o.n_verts = uint32_t(vs.size());
             o.tris = ts.data(); o.n_tris = uint32_t(ts.size());
+        } else if (Curves *cv = dynamic_cast<Curves *>(&p)) {
+            // Curves exposes neither its nodes nor its settings; the scene's own Curves::prepareForRender has already
+            // moved the (private) nodes to world space.  Re-read the .fiber file through the reference's CurveIO and redo
+            // Curves::loadCurves + prepareForRender (Curves.cpp:268-296,572-611) with the parameters toJson() reports.
+            o.type = TGB_PRIM_CURVES;
+            rapidjson::Value v = cv->toJson(jsonDoc.GetAllocator());
+            std::string mode = v["mode"].GetString();
+            if (mode == "cylinder") o.curve_mode = TGB_CURVE_CYLINDER;
+            else if (mode == "half_cylinder") o.curve_mode = TGB_CURVE_HALF_CYLINDER;
+            else if (mode == "bcsdf_cylinder") o.curve_mode = TGB_CURVE_BCSDF_CYLINDER;
+            else FAIL("b200_path_tracer: curve mode '%s' is outside the hot path", mode);
+            bool taper = v["curve_taper"].GetBool();
+            float subsample = float(v["subsample"].GetDouble());
+            bool overrideThickness = v.HasMember("curve_thickness");
+            float thickness = overrideThickness ? float(v["curve_thickness"].GetDouble()) : 0.0f;
+            std::vector<uint32> curveEnds;
+            nodeStore.emplace_back();
+            std::vector<Vec4f> &nodes = nodeStore.back();
+            CurveIO::CurveData data;
+            data.curveEnds = &curveEnds;
+            data.nodeData = &nodes;
+            if (!cv->path() || !CurveIO::load(*cv->path(), data))
+                FAIL("b200_path_tracer: cannot read the curve file of '%s'", p.name());
+            if (overrideThickness || taper) {
+                for (size_t i = 0; i < curveEnds.size(); ++i) {
+                    uint32 start = i ? curveEnds[i - 1] : 0;
+                    for (uint32 t = start; t < curveEnds[i]; ++t) {
+                        float w = overrideThickness ? thickness : nodes[t].w();
+                        if (taper)
+                            w *= 1.0f - (t - start - 0.5f)/(curveEnds[i] - start - 1);
+                        nodes[t].w() = w;
+                    }
+                }
+            }
+            float widthScale = tform.extractScaleVec().avg();
+            for (Vec4f &n : nodes) {
+                Vec3f q = tform*n.xyz();
+                n = Vec4f(q.x(), q.y(), q.z(), n.w()*widthScale);
+            }
+            segStore.emplace_back();
+            std::vector<uint32_t> &segs = segStore.back();
+            UniformSampler rand;
+            for (size_t i = 0; i < curveEnds.size(); ++i) {
+                uint32 start = i ? curveEnds[i - 1] : 0;
+                if (subsample > 0.0f && rand.next1D() < subsample)
+                    continue;
+                for (uint32 t = start + 2; t < curveEnds[i]; ++t)
+                    segs.push_back(t);
+            }
+            o.curve_nodes = reinterpret_cast<const float *>(nodes.data());
+            o.n_curve_nodes = uint32_t(nodes.size());
+            o.curve_segments = segs.data();
+            o.n_curve_segments = uint32_t(segs.size());
         } else if (dynamic_cast<Quad *>(&p)) {
             // Quad::prepareForRender (Quad.cpp:298-305)
             o.type = TGB_PRIM_QUAD;

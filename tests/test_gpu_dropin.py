@@ -18,7 +18,7 @@ G = os.path.join(ROOT, "tests", "golden")
 
 
 @pytest.mark.skipif(not os.path.exists(EXE), reason="drop-in binary not built (needs /root/reference at build time)")
-@pytest.mark.parametrize("name", ["cornell", "materials", "coat_env"])
+@pytest.mark.parametrize("name", ["cornell", "materials", "coat_env", "hair", "curves_plastic"])
 def test_reference_binary_with_b200_integrator(name, tmp_path):
     src = os.path.join(G, name)
     for f in os.listdir(src):
@@ -37,4 +37,4 @@ def test_reference_binary_with_b200_integrator(name, tmp_path):
     d = np.abs(got - want).max(axis=2)
     close = float((d <= 1e-5*(1.0 + np.abs(want).max(axis=2))).mean())
     print(name, "exact %.4f close %.4f" % (float((d == 0).mean()), close))
-    assert close >= 0.985
+    assert close >= (0.97 if name in ("hair", "curves_plastic") else 0.985)     # curve scenes: see tests/test_gpu_parity.py::test_curves_and_hair
