@@ -36,6 +36,7 @@ ALG_BYTES_PER_QUERY = 48
 CONFIGS = {
     "c1": {"res": (1920, 1080), "label": "C1: Cornell box + 868,480-tri Lambert mesh (procedural dragon stand-in), 1920x1080, path_tracer, max_bounces 64, Sobol"},
     "c3": {"res": (3840, 2160), "label": "C3: 12,544,000-triangle instanced forest (490 trees x 2 masters, flattened), Lambert + rough plastic + HDR sky, 3840x2160, max_bounces 16, Sobol"},
+    "c4": {"res": (1920, 1080), "label": "C4: 650,000 quadratic B-spline curve segments (10,000 curly strands x 67 nodes, bcsdf_cylinder) with the hair BCSDF over a Lambert floor, quad light + constant sky, 1920x1080, max_bounces 16, Sobol"},
 }
 
 
@@ -77,6 +78,11 @@ def make_scene(spp, config="c1"):
         path = os.path.join(d, "forest10m.json")
         if not os.path.exists(path):
             synth.instanced_forest(d, "forest10m", n_instances=490, tree_subdiv=5, res=CONFIGS["c3"]["res"], spp=spp, extent=40.0)
+        return path
+    if config == "c4":
+        path = os.path.join(d, "hair650k.json")
+        if not os.path.exists(path):
+            synth.hair_scene(d, "hair650k", n_curves=10000, nodes_per_curve=67, res=CONFIGS["c4"]["res"], spp=spp, width=0.004)
         return path
     path = os.path.join(d, "cornell_dragon.json")
     marker = os.path.join(d, "cornell_dragon_body.wo3")
@@ -124,7 +130,7 @@ def bench_reference(args, rank, world):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    scene_path = make_scene(1024)
+    scene_path = make_scene(1024, args.config)
     spp = args.ref_spp
     vals = []
     for i in range(args.warmup + args.steps):
@@ -139,10 +145,10 @@ def bench_reference(args, rank, world):
     line = {"impl": "reference", "metric": "Msamples/sec (paths x spp)", "value": value, "unit": "Msamples/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3*secs/len(vals),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "C1: Cornell box + 868,480-tri Lambert mesh, 1920x1080, path_tracer, max_bounces 64, Sobol",
+            "config": {"workload": CONFIGS[args.config]["label"],
                        "step": "%d spp of the whole frame (bounded sample of the 1024-spp job)" % spp},
             "cpu_baseline": {"value": value, "unit": "Msamples/s", "cores": cores, "kind": "reference",
-                             "sample": "%d spp x 1920x1080 per step, tungsten -t %d (SSE4.2 Embree build, no AVX: the reference's own ISA policy)" % (spp, cores)},
+                             "sample": "%d spp of the whole frame per step, tungsten -t %d (SSE4.2 Embree build, no AVX: the reference's own ISA policy)" % (spp, cores)},
             "e2e": {"value": value, "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line))
@@ -164,7 +170,7 @@ def main():
     global W, H
     W, H = CONFIGS[args.config]["res"]
     if args.impl == "reference":
-        if args.config != "c1":
+        if args.config == "c3":
             if rank == 0:
                 print(json.dumps({"impl": "reference", "unavailable": "the stock reference cannot load mesh-instanced scenes from JSON (Instance::loadResources never loads its masters)"}))
             return

@@ -290,7 +290,7 @@ int upload_scene(tgb_ctx *c, const tgb_scene_desc *d) {
     std::vector<DPrim> prims(d->n_primitives);
     std::vector<int> lights, inf_lights, analytic;
     std::vector<BuildTri> btris; std::vector<uint32_t> tri_prim; std::vector<float4> tri_shade;
-    std::vector<BuildBox> cboxes; std::vector<float4> crecs; std::vector<uint32_t> cseg_prim;     // curve segments of all primitives
+    std::vector<BuildBox> cboxes; std::vector<float4> crecs; std::vector<uint32_t> cseg_prim;   // curve BVH primitives (kCurvePieces per segment) of all primitives
     int lightCount = 0;
     for (uint32_t i = 0; i < d->n_primitives; ++i) {
         const tgb_primitive &p = d->primitives[i]; DPrim &o = prims[i];
@@ -369,27 +369,32 @@ int upload_scene(tgb_ctx *c, const tgb_scene_desc *d) {
             if (p.n_curve_segments && (!p.curve_nodes || !p.curve_segments)) return fail(c, TGB_ERR_INVALID, "curves %u has null buffers", i);
             if (tex[d->bsdfs[d->bsdf_slots[p.bsdf_first]].albedo_tex].d.type != TGB_TEX_CONSTANT)
                 return fail(c, TGB_ERR_UNSUPPORTED, "curves %u: textured materials on curves are outside the hot path", i);
-            o.curve_mode = p.curve_mode; o.tri_first = uint32_t(cboxes.size()); o.n_tris = p.n_curve_segments;      // rebased below
+            o.curve_mode = p.curve_mode; o.tri_first = uint32_t(cboxes.size()); o.n_tris = p.n_curve_segments*kCurvePieces;   // rebased below
             for (uint32_t k = 0; k < p.n_curve_segments; ++k) {
                 uint32_t t = p.curve_segments[k];
                 if (t < 2 || t >= p.n_curve_nodes) return fail(c, TGB_ERR_INVALID, "curves %u: segment index out of range", i);
                 const float *n0 = p.curve_nodes + 4*size_t(t - 2), *n1 = n0 + 4, *n2 = n0 + 8;
-                BuildBox bb;                                                               // curveBox (Curves.cpp:231-243)
+                // One BVH primitive per quarter of the segment's parameter range (the reference bounds the whole segment,
+                // curveBox, Curves.cpp:231-243): bounds of the quadratic on [ta, tb] = its end values + the interior extremum,
+                // grown by the largest node width (the width spline is a convex combination of the node widths).
                 float maxW = std::max(std::max(n0[3], n1[3]), n2[3]);
-                for (int a = 0; a < 3; ++a) {
-                    float lo = (n0[a] + n1[a])*0.5f, hi = (n1[a] + n2[a])*0.5f;           // BSpline::quadraticMinMax
-                    if (lo > hi) std::swap(lo, hi);
-                    float tFlat = (n0[a] - n1[a])/(n0[a] - 2.0f*n1[a] + n2[a]);
-                    if (tFlat > 0.0f && tFlat < 1.0f) {
-                        float xFlat = (0.5f*n0[a] - n1[a] + 0.5f*n2[a])*tFlat*tFlat + (n1[a] - n0[a])*tFlat + 0.5f*(n0[a] + n1[a]);
-                        lo = std::min(lo, xFlat); hi = std::max(hi, xFlat);
+                for (int piece = 0; piece < kCurvePieces; ++piece) {
+                    BuildBox bb;
+                    float ta = float(piece)/kCurvePieces, tb = float(piece + 1)/kCurvePieces;
+                    for (int a = 0; a < 3; ++a) {
+                        float qa = 0.5f*n0[a] - n1[a] + 0.5f*n2[a], qb = n1[a] - n0[a], qc = 0.5f*(n0[a] + n1[a]);
+                        float fa = (qa*ta + qb)*ta + qc, fb = (qa*tb + qb)*tb + qc;
+                        float lo = std::min(fa, fb), hi = std::max(fa, fb);
+                        float tFlat = -qb/(2.0f*qa);
+                        if (tFlat > ta && tFlat < tb) { float f = (qa*tFlat + qb)*tFlat + qc; lo = std::min(lo, f); hi = std::max(hi, f); }
+                        float slack = 4e-7f*std::max(std::fabs(lo), std::fabs(hi));            // Horner vs the kernel's expanded form
+                        bb.lo[a] = lo - maxW - slack; bb.hi[a] = hi + maxW + slack;
+                        bb.centroid[a] = 0.5f*(lo + hi);
                     }
-                    bb.lo[a] = lo - maxW; bb.hi[a] = hi + maxW;
-                    bb.centroid[a] = (n0[a] + n1[a] + n2[a])*(1.0f/3.0f);
+                    cboxes.push_back(bb); cseg_prim.push_back(i);
+                    crecs.push_back(make_float4(n0[0], n0[1], n0[2], n0[3])); crecs.push_back(make_float4(n1[0], n1[1], n1[2], n1[3]));
+                    crecs.push_back(make_float4(n2[0], n2[1], n2[2], n2[3]));
                 }
-                cboxes.push_back(bb); cseg_prim.push_back(i);
-                crecs.push_back(make_float4(n0[0], n0[1], n0[2], n0[3])); crecs.push_back(make_float4(n1[0], n1[1], n1[2], n1[3]));
-                crecs.push_back(make_float4(n2[0], n2[1], n2[2], n2[3]));
             }
             break; }
         default: return fail(c, TGB_ERR_UNSUPPORTED, "primitive type %u is outside the hot path", p.type);
@@ -518,7 +523,7 @@ int upload_scene(tgb_ctx *c, const tgb_scene_desc *d) {
     if (3*bvh.max_depth + 2 > uint32_t(kStackSize)) return fail(c, TGB_ERR_UNSUPPORTED, "BVH depth %u exceeds the traversal stack", bvh.max_depth);
     c->bvh_depth = bvh.max_depth; c->n_tris = uint32_t(btris.size()); c->bvh_sah = bvh.sah_cost;
     std::vector<float4> tri_isect(3*(btris.size() + cboxes.size()));
-    for (size_t k = btris.size(); k < bvh.order.size(); ++k) {      // curve records: the segment's three nodes, leaf order
+    for (size_t k = btris.size(); k < bvh.order.size(); ++k) {      // curve records: the segment's three nodes + which quarter, leaf order
         size_t seg = bvh.order[k] - btris.size();
         for (int j = 0; j < 3; ++j) tri_isect[3*k + j] = crecs[3*seg + j];
     }

@@ -127,7 +127,7 @@ struct DScene {
     const float4 *nodes; uint32_t n_nodes; uint32_t n_tris;
     // curve segments share the arrays above: records n_tris.. of tri_isect hold a segment's three nodes (x, y, z, width),
     // tri_global / tri_prim continue with global ids n_tris + segment
-    uint32_t n_curve_segs;
+    uint32_t n_curve_segs;          // BVH primitives for curves = kCurvePieces sub-ranges per segment
     // "cut": <= 16 boxes of the BVH's top levels that together cover every triangle (same padded boxes the nodes hold).
     // A ray that misses all of them is answered by the kernel that creates it and never reaches a traversal kernel.
     int n_cut; float cut[6][16];        // lo.x, hi.x, lo.y, hi.y, lo.z, hi.z
