@@ -41,6 +41,7 @@ struct tgb_ctx {
     uint32_t capacity = 0;
     PathState st{}, st2{};      // st2 = second copy of the persistent arrays (ray, throughput, emission, rng, hit, pid)
     uint32_t *queue_a = nullptr, *queue_b = nullptr, *squeue = nullptr, *squeue2 = nullptr, *free_list = nullptr;
+    size_t l2_window_bytes = 0;     // bytes of BVH data pinned in L2 through the stream's access-policy window (0 = none)
     bool has_curves = false;        // selects the kernel instantiations with the curve-segment test and per-hit epsilon
     uint32_t *bin_keys = nullptr, *bin_hist = nullptr;      // queue_a doubles as the ray-coherence visiting order of k_trace
     size_t res_capacity = 0;
@@ -549,11 +550,37 @@ int upload_scene(tgb_ctx *c, const tgb_scene_desc *d) {
     if ((rc = dev_upload(c, &sc.lights, lights))) return rc;
     if ((rc = dev_upload(c, &sc.inf_lights, inf_lights))) return rc;
     if ((rc = dev_upload(c, &sc.analytic, analytic))) return rc;
-    if ((rc = dev_upload(c, &sc.tri_isect, tri_isect))) return rc;
     if ((rc = dev_upload(c, &sc.tri_global, bvh.order))) return rc;
     if ((rc = dev_upload(c, &sc.tri_prim, tri_prim))) return rc;
     if ((rc = dev_upload(c, &sc.tri_shade, tri_shade))) return rc;
-    if ((rc = dev_upload(c, &sc.nodes, nodes))) return rc;
+    {   // BVH nodes + intersection records in ONE allocation, so that a single L2 access-policy window can pin them.
+        // The traversal kernels re-read this working set (C1: 78 MB) for every wavefront while ~2 GB of path state streams
+        // through the same L2 in between, which is why ncu shows 5x the algorithmic DRAM bytes for k_trace.  Measured
+        // (tools/gpu_env_ab.sh, C1): with the window k_trace gains 1.7 % (it is not waiting on DRAM) and the streaming
+        // kernels lose more than that to the carved-out L2 (505 -> 480 Msamples/s), so the window is opt-in: TGB_L2_PERSIST=1.
+        size_t nb = nodes.size()*sizeof(float4), tb = tri_isect.size()*sizeof(float4);
+        size_t nb_al = (nb + 255) & ~size_t(255);
+        char *slab = nullptr;
+        if ((rc = dev_alloc(c, &slab, nb_al + std::max<size_t>(tb, 16)))) return rc;
+        if (nb) CU(cudaMemcpy(slab, nodes.data(), nb, cudaMemcpyHostToDevice));
+        if (tb) CU(cudaMemcpy(slab + nb_al, tri_isect.data(), tb, cudaMemcpyHostToDevice));
+        sc.nodes = reinterpret_cast<const float4 *>(slab); sc.tri_isect = reinterpret_cast<const float4 *>(slab + nb_al);
+        const char *env = getenv("TGB_L2_PERSIST");
+        if (nb + tb > 0 && env && env[0] == '1') {
+            cudaDeviceProp prop; CU(cudaGetDeviceProperties(&prop, c->device));
+            size_t window = std::min<size_t>(nb_al + tb, size_t(prop.accessPolicyMaxWindowSize));
+            size_t carve = std::min<size_t>(window, size_t(prop.persistingL2CacheMaxSize));
+            if (window && carve && cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, carve) == cudaSuccess) {
+                cudaStreamAttrValue attr; std::memset(&attr, 0, sizeof(attr));
+                attr.accessPolicyWindow.base_ptr = slab; attr.accessPolicyWindow.num_bytes = window;
+                attr.accessPolicyWindow.hitRatio = float(std::min(1.0, double(carve)/double(window)));
+                attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+                attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+                if (cudaStreamSetAttribute(c->stream, cudaStreamAttributeAccessPolicyWindow, &attr) == cudaSuccess) c->l2_window_bytes = carve;
+            }
+            cudaGetLastError();
+        }
+    }
     std::vector<uint32_t> sobol(1024*32);
     std::memcpy(sobol.data(), tgb_sobol_blob, sobol.size()*4);
     if ((rc = dev_upload(c, &sc.sobol, sobol))) return rc;
@@ -769,6 +796,7 @@ void tgb200_destroy(tgb_ctx *c) {
     if (!c) return;
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
+    if (c->l2_window_bytes) cudaCtxResetPersistingL2Cache();
     for (void *p : c->allocs) cudaFree(p);
     for (float *p : {c->st.rx, c->st.ry, c->st.rz}) if (p) cudaFree(p);
     if (c->h_counts) cudaFreeHost(c->h_counts);

@@ -962,24 +962,37 @@ __global__ void __launch_bounds__(256) k_accum(DScene sc, PathState st, PathStat
 
 // Counting sort of the survivors' slot indices by ray-coherence key: exclusive scan of the histogram (one block) ...
 __global__ void __launch_bounds__(1024) k_bin_scan(uint32_t *hist, uint32_t *n_sorted, uint32_t *n_sorted_host) {
-    __shared__ uint32_t part[1024];
-    const uint32_t per = kBins/1024u;
-    uint32_t t = threadIdx.x, sum = 0;
-    uint32_t local[per];
+    // 32 Ki bins, 32 consecutive bins per thread (8 x 16-byte loads), block-wide scan of the 1024 partial sums with
+    // warp shuffles (two levels), exclusive bases written back in place
+    __shared__ uint32_t warp_sum[32];
+    constexpr uint32_t per = kBins/1024u;
+    static_assert(per % 4u == 0u, "vector loads");
+    const uint32_t t = threadIdx.x, lane = t & 31u, warp = t >> 5;
+    uint4 *h4 = reinterpret_cast<uint4 *>(hist) + size_t(t)*(per/4u);
+    uint4 v[per/4u];
+    uint32_t sum = 0;
 #pragma unroll
-    for (uint32_t i = 0; i < per; ++i) { local[i] = hist[t*per + i]; sum += local[i]; }
-    part[t] = sum;
+    for (uint32_t i = 0; i < per/4u; ++i) { v[i] = h4[i]; sum += v[i].x + v[i].y + v[i].z + v[i].w; }
+    uint32_t incl = sum;
+#pragma unroll
+    for (uint32_t off = 1; off < 32u; off <<= 1) { uint32_t n = __shfl_up_sync(0xffffffffu, incl, off); if (lane >= off) incl += n; }
+    if (lane == 31u) warp_sum[warp] = incl;
     __syncthreads();
-    for (uint32_t off = 1; off < 1024u; off <<= 1) {
-        uint32_t v = t >= off ? part[t - off] : 0u;
-        __syncthreads();
-        part[t] += v;
-        __syncthreads();
-    }
-    uint32_t base = part[t] - sum;
+    if (warp == 0) {
+        uint32_t w = warp_sum[lane], wi = w;
 #pragma unroll
-    for (uint32_t i = 0; i < per; ++i) { hist[t*per + i] = base; base += local[i]; }
-    if (t == 1023u) { *n_sorted = base; *n_sorted_host = base; }      // the culled survivors follow the sorted ones
+        for (uint32_t off = 1; off < 32u; off <<= 1) { uint32_t n = __shfl_up_sync(0xffffffffu, wi, off); if (lane >= off) wi += n; }
+        warp_sum[lane] = wi - w;                       // exclusive base of each warp
+        if (lane == 31u) { *n_sorted = wi; *n_sorted_host = wi; }      // total = the culled survivors follow the sorted ones
+    }
+    __syncthreads();
+    uint32_t base = warp_sum[warp] + incl - sum;
+#pragma unroll
+    for (uint32_t i = 0; i < per/4u; ++i) {
+        uint4 o;
+        o.x = base; base += v[i].x; o.y = base; base += v[i].y; o.z = base; base += v[i].z; o.w = base; base += v[i].w;
+        h4[i] = o;
+    }
 }
 // ... and scatter of the slot indices (4 bytes each) to their sorted positions.
 __global__ void __launch_bounds__(256) k_bin_scatter(const uint32_t *keys, uint32_t *cursor, const uint32_t *n_alive, uint32_t *order) {
