@@ -41,6 +41,7 @@ struct tgb_ctx {
     uint32_t capacity = 0;
     PathState st{}, st2{};      // st2 = second copy of the persistent arrays (ray, throughput, emission, rng, hit, pid)
     uint32_t *queue_a = nullptr, *queue_b = nullptr, *squeue = nullptr, *squeue2 = nullptr, *free_list = nullptr;
+    uint32_t persist_blocks = 0;    // grid of the persistent traversal kernels (0 = one thread per ray)
     size_t l2_window_bytes = 0;     // bytes of BVH data pinned in L2 through the stream's access-policy window (0 = none)
     bool has_curves = false;        // selects the kernel instantiations with the curve-segment test and per-hit epsilon
     uint32_t *bin_keys = nullptr, *bin_hist = nullptr;      // queue_a doubles as the ray-coherence visiting order of k_trace
@@ -622,7 +623,7 @@ int alloc_wavefront(tgb_ctx *c, uint32_t capacity) {
     if ((rc = dev_alloc(c, &c->ss.qu, size_t(capacity)*2))) return rc;
     if ((rc = dev_alloc(c, &c->ss.qv, size_t(capacity)*2))) return rc;
     if ((rc = dev_alloc(c, &c->ss.qid, size_t(capacity)*2))) return rc;
-    if ((rc = dev_alloc(c, &c->counts, 4))) return rc;
+    if ((rc = dev_alloc(c, &c->counts, 6))) return rc;          // [4], [5]: ray cursors of the persistent traversal kernels
     if ((rc = dev_alloc(c, &c->ctr, 1))) return rc;
     CU(cudaMemset(c->ctr, 0, sizeof(Counters)));
     CU(cudaMallocHost(reinterpret_cast<void **>(&c->h_counts), 4*sizeof(uint32_t)));
@@ -698,7 +699,7 @@ int render_device(tgb_ctx *c, uint32_t spp_begin, uint32_t spp_count) {
     CU(cudaEventRecord(c->ev0, c->stream));
     uint64_t launches = 0;
     float trace_ms = 0.0f, shadow_ms = 0.0f; uint64_t trace_launches = 0, traversed = 0, shadow_traversed = 0;
-    const bool has_bvh = sc.n_nodes != 0, curves = c->has_curves;
+    const bool has_bvh = sc.n_nodes != 0, curves = c->has_curves, persist = c->persist_blocks != 0;
     // a step's finished radiances are kept per path (12 B each) until k_resolve folds them in sample order;
     // split the sample range so that this buffer stays below ~6 GB and path ids fit 32 bits
     const uint64_t max_paths = std::min<uint64_t>(512ull << 20, 0xFFFFFFFFull);
@@ -725,13 +726,18 @@ int render_device(tgb_ctx *c, uint32_t spp_begin, uint32_t spp_count) {
             }
             uint32_t n = n_alive + m;
             if (n == 0) break;
-            CU(cudaMemsetAsync(c->counts, 0, 4*sizeof(uint32_t), c->stream));
+            CU(cudaMemsetAsync(c->counts, 0, 6*sizeof(uint32_t), c->stream));
             if (c->profiling) CU(cudaEventRecord(c->evt0, c->stream));
             if (has_bvh) {
                 uint32_t K = rays_per_lane(n);
-                if (curves) k_trace<true><<<blocks(n, kTraceBlock*K), kTraceBlock, kTraceSmem, c->stream>>>(sc, cur, c->queue_a, c->bin_hist + kBins + 1, n_alive, n, K);
-                else k_trace<false><<<blocks(n, kTraceBlock*K), kTraceBlock, kTraceSmem, c->stream>>>(sc, cur, c->queue_a, c->bin_hist + kBins + 1, n_alive, n, K);
+                // persistent: a fixed grid pulls rays from counts[4]; else one thread per ray
+                uint32_t grid = persist ? std::min(blocks(n, kTraceBlock), c->persist_blocks) : blocks(n, kTraceBlock);
+                if (curves) { if (persist) k_trace<true, true><<<grid, kTraceBlock, kTraceSmem, c->stream>>>(sc, cur, c->queue_a, c->bin_hist + kBins + 1, n_alive, n, c->counts + 4);
+                              else k_trace<true, false><<<grid, kTraceBlock, kTraceSmem, c->stream>>>(sc, cur, c->queue_a, c->bin_hist + kBins + 1, n_alive, n, c->counts + 4); }
+                else { if (persist) k_trace<false, true><<<grid, kTraceBlock, kTraceSmem, c->stream>>>(sc, cur, c->queue_a, c->bin_hist + kBins + 1, n_alive, n, c->counts + 4);
+                       else k_trace<false, false><<<grid, kTraceBlock, kTraceSmem, c->stream>>>(sc, cur, c->queue_a, c->bin_hist + kBins + 1, n_alive, n, c->counts + 4); }
                 launches++;
+                (void)K;
             }
             if (c->profiling) CU(cudaEventRecord(c->evt1, c->stream));
             if (curves) k_shade<true><<<blocks(n, 128), 128, 0, c->stream>>>(sc, cur, bi, n, c->squeue, cs, c->ctr);
@@ -743,9 +749,13 @@ int render_device(tgb_ctx *c, uint32_t spp_begin, uint32_t spp_count) {
             launches++;
             if (has_bvh) {
                 uint32_t K = rays_per_lane(2*n);
-                if (curves) k_shadow_bvh<true><<<blocks(2*n, kTraceBlock*K), kTraceBlock, kTraceSmem, c->stream>>>(sc, cur, c->ss, c->squeue2, cs + 1, c->ctr, K);
-                else k_shadow_bvh<false><<<blocks(2*n, kTraceBlock*K), kTraceBlock, kTraceSmem, c->stream>>>(sc, cur, c->ss, c->squeue2, cs + 1, c->ctr, K);
+                uint32_t grid = persist ? std::min(blocks(2*n, kTraceBlock), c->persist_blocks) : blocks(2*n, kTraceBlock);
+                if (curves) { if (persist) k_shadow_bvh<true, true><<<grid, kTraceBlock, kTraceSmem, c->stream>>>(sc, cur, c->ss, c->squeue2, cs + 1, c->ctr, c->counts + 5);
+                              else k_shadow_bvh<true, false><<<grid, kTraceBlock, kTraceSmem, c->stream>>>(sc, cur, c->ss, c->squeue2, cs + 1, c->ctr, c->counts + 5); }
+                else { if (persist) k_shadow_bvh<false, true><<<grid, kTraceBlock, kTraceSmem, c->stream>>>(sc, cur, c->ss, c->squeue2, cs + 1, c->ctr, c->counts + 5);
+                       else k_shadow_bvh<false, false><<<grid, kTraceBlock, kTraceSmem, c->stream>>>(sc, cur, c->ss, c->squeue2, cs + 1, c->ctr, c->counts + 5); }
                 launches++;
+                (void)K;
             }
             if (c->profiling) CU(cudaEventRecord(c->evs1, c->stream));
             CU(cudaMemsetAsync(c->bin_hist, 0, (kBins + 1)*sizeof(uint32_t), c->stream));
@@ -836,6 +846,21 @@ int tgb200_create(const tgb_scene_desc *d, tgb_ctx **out) {
         uint32_t cap = d->settings.max_paths_in_flight ? d->settings.max_paths_in_flight : (1u << 22);
         cap = std::max(cap, 1024u);
         if ((rc = alloc_wavefront(c, cap))) break;
+        {   // persistent traversal grid = what is resident at once (blocks per SM x SMs), smaller of the two kernels
+            const char *env = getenv("TGB_PERSIST");
+            if (!(env && env[0] == '0')) {
+                int sms = 0, b1 = 0, b2 = 0;
+                cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+                if (c->has_curves) {
+                    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b1, k_trace<true, true>, kTraceBlock, kTraceSmem);
+                    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b2, k_shadow_bvh<true, true>, kTraceBlock, kTraceSmem);
+                } else {
+                    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b1, k_trace<false, true>, kTraceBlock, kTraceSmem);
+                    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b2, k_shadow_bvh<false, true>, kTraceBlock, kTraceSmem);
+                }
+                if (cudaGetLastError() == cudaSuccess && sms > 0 && b1 > 0 && b2 > 0) c->persist_blocks = uint32_t(sms*std::min(b1, b2));
+            }
+        }
     } while (0);
     if (rc) { g_create_error = c->error; tgb200_destroy(c); return rc; }
     *out = c;

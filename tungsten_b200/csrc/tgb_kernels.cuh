@@ -208,8 +208,11 @@ constexpr int kSmemStack = 32;
 constexpr int kLocalStack = 48;
 constexpr int kStackSize = kSmemStack + kLocalStack;
 constexpr int kTraceBlock = 128;
+// resident blocks per SM the traversal kernels are compiled for: 6 x 128 threads caps them at 85 registers, which keeps the
+// persistent kernels' per-lane ray state in registers without losing occupancy (measured on C1: 5 -> 527, 6 -> 564, 7 -> 561,
+// 8 -> 557 Msamples/s)
 #ifndef TGB_MINB
-#define TGB_MINB 1
+#define TGB_MINB 6
 #endif
 constexpr size_t kTraceSmem = size_t(kSmemStack)*kTraceBlock*sizeof(int);
 
@@ -243,24 +246,36 @@ struct TravStack {
                                     int ll_ = sw_ ? lb : la; lb = sw_ ? la : lb; la = ll_; }
 // CURVES: leaves whose code has bit 2 set hold curve segments (three float4 nodes per record, stored after the triangles);
 // a curve hit keeps (t, position along the segment, interpolated width) in (t, u, v) and id >= n_tris.
+// The traversal is a resumable object: run() walks until the ray is finished (true) or until `yield()` asks for a pause
+// after a leaf (false) -- the persistent kernels pause to hand new rays to the lanes whose ray has finished.
 template <bool CURVES>
-TGB_D void bvh_traverse(const DScene &sc, int *smem_stack, V3 o, V3 d, float tnear, bool any, Hit &h) {
-    const float4 *nodes = sc.nodes;
-    CurveFrame cf; int last_seg = -1;
-    if (CURVES) cf = curve_frame(d);
-    TravStack stk; stk.smem = smem_stack + threadIdx.x; stk.sp = 0;
-    const float ooeps = 1e-30f;
-    const float idx = 1.0f/(fabsf(d.x) > ooeps ? d.x : copysignf(ooeps, d.x));
-    const float idy = 1.0f/(fabsf(d.y) > ooeps ? d.y : copysignf(ooeps, d.y));
-    const float idz = 1.0f/(fabsf(d.z) > ooeps ? d.z : copysignf(ooeps, d.z));
-    const float oodx = o.x*idx, oody = o.y*idy, oodz = o.z*idz;
-    const int EMPTY = int(0x80000000u);
-    // The entry plane of a slab is its lo plane when the direction component is positive, else its hi plane (fma is
-    // monotone, so this IS min(a, b) / max(a, b) of the two plane distances): pick the float4 to load per axis once per ray.
-    const int nx = idx < 0.0f ? 1 : 0, ny = idy < 0.0f ? 3 : 2, nz = idz < 0.0f ? 5 : 4;
-    const int fx = nx ^ 1, fy = ny ^ 1, fz = nz ^ 1;
-    int cur = 0;
-    while (true) {
+struct Traversal {
+    V3 o, d; float tnear; bool any; Hit h;
+    float idx, idy, idz, oodx, oody, oodz; int nx, ny, nz, fx, fy, fz;
+    CurveFrame cf; int last_seg; int cur;
+    // (the stack is a separate object: its dynamically indexed spill array would drag this whole struct into local memory)
+
+    TGB_D void begin(V3 o_, V3 d_, float tnear_, bool any_, const Hit &h_) {
+        o = o_; d = d_; tnear = tnear_; any = any_; h = h_;
+        const float ooeps = 1e-30f;
+        idx = 1.0f/(fabsf(d.x) > ooeps ? d.x : copysignf(ooeps, d.x));
+        idy = 1.0f/(fabsf(d.y) > ooeps ? d.y : copysignf(ooeps, d.y));
+        idz = 1.0f/(fabsf(d.z) > ooeps ? d.z : copysignf(ooeps, d.z));
+        oodx = o.x*idx; oody = o.y*idy; oodz = o.z*idz;
+        // The entry plane of a slab is its lo plane when the direction component is positive, else its hi plane (fma is
+        // monotone, so this IS min(a, b) / max(a, b) of the two plane distances): pick the float4 to load per axis once per ray.
+        nx = idx < 0.0f ? 1 : 0; ny = idy < 0.0f ? 3 : 2; nz = idz < 0.0f ? 5 : 4;
+        fx = nx ^ 1; fy = ny ^ 1; fz = nz ^ 1;
+        last_seg = -1;
+        if (CURVES) cf = curve_frame(d);
+        cur = 0;
+    }
+
+    template <class Y>
+    TGB_D bool run(const DScene &sc, TravStack &stk, Y yield) {
+        const float4 *nodes = sc.nodes;
+        const int EMPTY = int(0x80000000u);
+        while (true) {
         while (cur >= 0) {
             const float4 *nd = nodes + 8*size_t(cur);
             const float4 nrx = __ldg(nd + nx), frx = __ldg(nd + fx), nry = __ldg(nd + ny), fry = __ldg(nd + fy), nrz = __ldg(nd + nz), frz = __ldg(nd + fz);
@@ -277,7 +292,7 @@ TGB_D void bvh_traverse(const DScene &sc, int *smem_stack, V3 o, V3 d, float tne
             int l0 = lk.x, l1 = lk.y, l2 = lk.z, l3 = lk.w;
             TGB_CSWAP(t0, l0, t1, l1) TGB_CSWAP(t2, l2, t3, l3) TGB_CSWAP(t0, l0, t2, l2) TGB_CSWAP(t1, l1, t3, l3) TGB_CSWAP(t1, l1, t2, l2)
             if (t0 == INFINITY) {
-                if (stk.sp == 0) return;
+                if (stk.sp == 0) return true;
                 cur = stk.pop();
             } else {
                 if (t3 != INFINITY) stk.push(l3);
@@ -298,7 +313,7 @@ TGB_D void bvh_traverse(const DScene &sc, int *smem_stack, V3 o, V3 d, float tne
                 float ht, hu, hw;
                 if (curve_point_on_spline(q0, q1, q2, tnear, h.t, ht, hu, hw)) {
                     h.t = ht; h.u = hu; h.v = hw; h.id = first + i;
-                    if (any) return;
+                    if (any) return true;
                 }
             }
         } else
@@ -317,10 +332,55 @@ TGB_D void bvh_traverse(const DScene &sc, int *smem_stack, V3 o, V3 d, float tne
             float T = xor_sign(edot(ng, C), sgn);
             if (!(T > absDen*tnear && T < absDen*h.t)) continue;
             h.t = T/absDen; h.u = U/absDen; h.v = V/absDen; h.id = first + i;
-            if (any) return;
+            if (any) return true;
         }
-        if (stk.sp == 0) return;
-        cur = stk.pop();
+        if (stk.sp == 0) return true;
+            cur = stk.pop();
+            if (yield()) return false;
+        }
+    }
+};
+
+template <bool CURVES>
+TGB_D void bvh_traverse(const DScene &sc, int *smem_stack, V3 o, V3 d, float tnear, bool any, Hit &h) {
+    Traversal<CURVES> tr; TravStack stk; stk.smem = smem_stack + threadIdx.x; stk.sp = 0;
+    tr.begin(o, d, tnear, any, h);
+    tr.run(sc, stk, [] { return false; });
+    h = tr.h;
+}
+
+// Persistent form used by the renderer's traversal kernels: a fixed grid of warps pulls rays from a shared counter.  A
+// ray's traversal length is heavy-tailed, so with one ray per lane a warp spends most of its life with a quarter of its
+// lanes alive (ncu: 8.3 of 32 threads per instruction); here, whenever fewer than kRefillBelow lanes are still walking,
+// the warp pauses at the next leaf boundary and the idle lanes fetch the next rays of the (coherence-sorted) queue.
+#ifndef TGB_REFILL_BELOW
+#define TGB_REFILL_BELOW 20
+#endif
+template <bool CURVES, class P>
+TGB_D void bvh_traverse_persistent(const DScene &sc, int *smem_stack, P &pol, uint32_t n, uint32_t *counter) {
+    const unsigned FULL = 0xffffffffu, lane = threadIdx.x & 31u;
+    Traversal<CURVES> tr; TravStack stk; stk.smem = smem_stack + threadIdx.x; stk.sp = 0;
+    bool active = false, exhausted = false;
+    for (;;) {
+        unsigned need = __ballot_sync(FULL, !active);
+        if (need && !exhausted) {
+            unsigned cnt = unsigned(__popc(need)), leader = unsigned(__ffs(int(need))) - 1u;
+            uint32_t base = 0;
+            if (lane == leader) base = atomicAdd(counter, cnt);
+            base = __shfl_sync(FULL, base, int(leader));
+            exhausted = base + cnt >= n;
+            if (!active) {
+                uint32_t i = base + unsigned(__popc(need & ((1u << lane) - 1u)));
+                V3 o, d; float tnear; Hit h; bool any;
+                if (i < n && pol.fetch(i, o, d, tnear, h, any)) { tr.begin(o, d, tnear, any, h); stk.sp = 0; active = true; }
+            }
+        }
+        if (!__any_sync(FULL, active)) break;
+        if (active) {
+            const bool may_refill = !exhausted;
+            bool done = tr.run(sc, stk, [=] { return may_refill && __popc(__activemask()) < TGB_REFILL_BELOW; });
+            if (done) { pol.finish(tr.h); active = false; }
+        }
     }
 }
 
@@ -533,12 +593,13 @@ struct PathRayPolicy {
     }
     TGB_D void finish(const Hit &h) { st.h4[s] = pack_hit(h); }
 };
-template <bool CURVES>
+template <bool CURVES, bool PERSIST>
 __global__ void __launch_bounds__(kTraceBlock, TGB_MINB) k_trace(DScene sc, PathState st, const uint32_t *order, const uint32_t *n_sorted,
-                                                                 uint32_t n_surv, uint32_t n, uint32_t K) {
+                                                                 uint32_t n_surv, uint32_t n, uint32_t *counter) {
     extern __shared__ int smem_stack[];
     PathRayPolicy pol; pol.st = st; pol.order = order; pol.n_sorted = n_sorted; pol.n_surv = n_surv; pol.n_all = n; pol.s = 0;
-    bvh_traverse_multi<CURVES>(sc, smem_stack, pol, n, K);
+    if (PERSIST) bvh_traverse_persistent<CURVES>(sc, smem_stack, pol, n, counter);
+    else bvh_traverse_multi<CURVES>(sc, smem_stack, pol, n, 1);
 }
 
 // Parity hook (tgb200_trace_closest): rays in AoS tgb_ray, hits out as tgb_hit, through the same analytic pass and
@@ -898,12 +959,13 @@ struct ShadowPolicy {
         else shadow_resolve_closest<CURVES>(sc, st, s, mis, li, p, d, h);
     }
 };
-template <bool CURVES>
+template <bool CURVES, bool PERSIST>
 __global__ void __launch_bounds__(kTraceBlock, TGB_MINB) k_shadow_bvh(DScene sc, PathState st, ShadowState ss, const uint32_t *squeue2, const uint32_t *scount2,
-                                                            Counters *ctr, uint32_t K) {
+                                                            Counters *ctr, uint32_t *counter) {
     extern __shared__ int smem_stack[];
     ShadowPolicy<CURVES> pol; pol.sc = sc; pol.st = st; pol.ss = ss; pol.squeue2 = squeue2; pol.hits = &ctr->shadow_hits;
-    bvh_traverse_multi<CURVES>(sc, smem_stack, pol, *scount2, K);
+    if (PERSIST) bvh_traverse_persistent<CURVES>(sc, smem_stack, pol, *scount2, counter);
+    else bvh_traverse_multi<CURVES>(sc, smem_stack, pol, *scount2, 1);
 }
 
 // Fold this bounce's direct light + surface emission into the path (order as in handleSurface:537-543), apply the
