@@ -846,7 +846,8 @@ int tgb200_create(const tgb_scene_desc *d, tgb_ctx **out) {
         uint32_t cap = d->settings.max_paths_in_flight ? d->settings.max_paths_in_flight : (1u << 22);
         cap = std::max(cap, 1024u);
         if ((rc = alloc_wavefront(c, cap))) break;
-        {   // persistent traversal grid = what is resident at once (blocks per SM x SMs), smaller of the two kernels
+        {   // persistent traversal grid = twice what is resident at once (blocks per SM x SMs, smaller of the two kernels): the
+            // second wave evens out the end of a launch (C1: x1 575, x2 580 Msamples/s)
             const char *env = getenv("TGB_PERSIST");
             if (!(env && env[0] == '0')) {
                 int sms = 0, b1 = 0, b2 = 0;
@@ -858,7 +859,8 @@ int tgb200_create(const tgb_scene_desc *d, tgb_ctx **out) {
                     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b1, k_trace<false, true>, kTraceBlock, kTraceSmem);
                     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b2, k_shadow_bvh<false, true>, kTraceBlock, kTraceSmem);
                 }
-                if (cudaGetLastError() == cudaSuccess && sms > 0 && b1 > 0 && b2 > 0) c->persist_blocks = uint32_t(sms*std::min(b1, b2));
+                const char *mult = getenv("TGB_PERSIST_MULT");
+                if (cudaGetLastError() == cudaSuccess && sms > 0 && b1 > 0 && b2 > 0) c->persist_blocks = uint32_t(sms*std::min(b1, b2))*uint32_t(mult ? std::max(1, atoi(mult)) : 2);
             }
         }
     } while (0);

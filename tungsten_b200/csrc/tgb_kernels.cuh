@@ -526,7 +526,7 @@ TGB_D uint32_t ray_bin(const DScene &sc, V3 o, V3 d) {
     int cx = min(max(int((o.x - sc.bin_lo.x)*sc.bin_inv.x), 0), 15);
     int cy = min(max(int((o.y - sc.bin_lo.y)*sc.bin_inv.y), 0), 15);
     int cz = min(max(int((o.z - sc.bin_lo.z)*sc.bin_inv.z), 0), 15);
-    return (oct << 12) | (uint32_t(cx) << 8) | (uint32_t(cy) << 4) | uint32_t(cz);
+    return (oct << 12) | (uint32_t(cx) << 8) | (uint32_t(cy) << 4) | uint32_t(cz);       // (Morton order of the cell: no gain)
 }
 
 // ---- kernels ---------------------------------------------------------------------------------
@@ -644,8 +644,13 @@ __global__ void __launch_bounds__(256) k_hook_finish(DScene sc, const tgb_ray *r
 }
 
 // handleSurface (integrators/TraceBase.cpp:516-568) + the loop tail of traceSample (PathTracer.cpp:108-126)
+// k_shade is latency bound (scattered shading-record gathers): 8 resident blocks (64 registers, no spills) beat the
+// compiler's free choice of 95 registers / 5 blocks (C1: 564 -> 576 Msamples/s)
+#ifndef TGB_SHADE_MINB
+#define TGB_SHADE_MINB 8
+#endif
 template <bool CURVES>
-__global__ void __launch_bounds__(128) k_shade(DScene sc, PathState st, BatchInfo bi, uint32_t n,
+__global__ void __launch_bounds__(128, TGB_SHADE_MINB) k_shade(DScene sc, PathState st, BatchInfo bi, uint32_t n,
                                                uint32_t *squeue, uint32_t *scount, Counters *ctr) {
     uint32_t i = blockIdx.x*blockDim.x + threadIdx.x;
     bool valid = i < n;
