@@ -9,7 +9,7 @@ python bench.py --config c3 --steps 4 --warmup 3 --spp-per-step 8 --no-cpu-basel
 python bench.py --config c4 --steps 4 --warmup 3 --spp-per-step 8 --no-cpu-baseline > gpurun_out/bench_c4.json 2>> gpurun_out/bench.err
 python bench.py --impl reference --config c4 --steps 1 --warmup 0 --ref-spp 4 > gpurun_out/bench_c4_ref.json 2>> gpurun_out/bench.err
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv python bench.py --steps 1 --warmup 1 --spp-per-step 8 --no-cpu-baseline > gpurun_out/ncu_bench.log 2>&1
-for k in k_trace k_shadow_bvh k_shade; do
+for k in k_trace k_shadow_bvh; do
   ncu --set full --clock-control none --import-source on -k regex:$k -s 6 -c 1 -f -o gpurun_out/prof_$k python bench.py --steps 1 --warmup 1 --spp-per-step 8 --no-cpu-baseline > gpurun_out/ncu_$k.log 2>&1
 done
 ls -la gpurun_out | tail -12
