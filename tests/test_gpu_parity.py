@@ -102,7 +102,8 @@ def test_instanced_forest(scratch):
     dict(n_curves=300, mode="half_cylinder", bsdf={"type": "lambert", "albedo": [0.6, 0.4, 0.2]}, width=0.02),
     dict(n_curves=300, mode="cylinder", bsdf={"type": "rough_plastic", "albedo": [0.6, 0.4, 0.2], "roughness": 0.2},
          thickness=0.015, taper=True, subsample=0.3),
-], ids=["hair", "hair_dark", "half_cylinder_lambert", "cylinder_plastic"])
+    dict(n_curves=300, head=True),                                                                   # triangles + curves in one BVH
+], ids=["hair", "hair_dark", "half_cylinder_lambert", "cylinder_plastic", "hair_over_mesh"])
 def test_curves_and_hair(scratch, kw):
     """C4 stand-ins: quadratic B-spline curve segments (Curves.cpp) in the three cylinder modes, hair BCSDF (HairBcsdf.cpp).
     A few grazing rays resolve differently than in the oracle (different segment BVH + the bisection's pruning bound, see

@@ -99,3 +99,37 @@ def test_real_materialtest_scene_against_reference_binary(tmp_path):
     d = np.abs(img - want).max(axis=2)
     assert float((d == 0).mean()) >= 0.7
     assert float((d <= 1e-5*(1.0 + np.abs(want).max(axis=2))).mean()) >= 0.99
+
+
+@pytest.mark.skipif(not os.path.exists("/root/reference/data/example-scenes/hair/scene.json") or
+                    not os.path.exists(os.path.join(os.path.dirname(HERE), "oracle", "_ref", "tungsten_pathseed")),
+                    reason="needs the mounted reference (build container only)")
+def test_real_hair_scene_against_reference_binary(tmp_path):
+    """BASELINE.json config C4, the reference's own shipped hair scene (curl.fiber: 670,000 nodes / 10,000 curves, `subsample`
+    0.5, hair BCSDF, bcsdf_cylinder) with its two out-of-scope emitters (infinite_sphere_cap + skydome) replaced by an
+    environment sphere and a quad light: oracle vs the reference binary at 90x300, 2 spp."""
+    import json, subprocess
+    src = "/root/reference/data/example-scenes/hair"
+    os.symlink(os.path.join(src, "curl.fiber"), tmp_path/"curl.fiber")
+    js = json.load(open(os.path.join(src, "scene.json")))
+    js["primitives"] = [p for p in js["primitives"] if p["type"] == "curves"] + [
+        {"name": "env", "type": "infinite_sphere", "emission": [0.5, 0.6, 0.8], "sample": True},
+        {"name": "key", "type": "quad", "emission": [60, 55, 50], "bsdf": {"type": "null"},
+         "transform": {"position": [3.0, 9.0, 6.0], "scale": [3, 1, 3], "rotation": [0, 0, 140]}}]
+    js["camera"]["resolution"] = [90, 300]
+    js["integrator"]["min_bounces"] = 0            # the shipped value 1 hides directly visible emitters: show the sky
+    js["renderer"].update(spp=2, spp_step=2, adaptive_sampling=False, stratified_sampler=True, hdr_output_file="out.pfm",
+                          output_file="out.png", overwrite_output_files=True)
+    json.dump(js, open(tmp_path/"hair.json", "w"))
+    exe = os.path.join(os.path.dirname(HERE), "oracle", "_ref", "tungsten_pathseed")
+    subprocess.check_call([exe, "-t", "8", "-d", str(tmp_path/"ref"), str(tmp_path/"hair.json")], stdout=subprocess.DEVNULL)
+    want = scene.load_pfm(str(tmp_path/"ref"/"out.pfm"))
+    fs = scene.load_scene(str(tmp_path/"hair.json"))
+    assert 300000 < fs.n_curve_segments < 350000                 # `subsample` 0.5 drops about half of the 650,000 segments
+    o = pyoracle.Oracle(fs); img, _ = o.render(2); o.close()
+    d = np.abs(img - want).max(axis=2)
+    exact = float((d == 0).mean()); close = float((d <= 1e-5*(1.0 + np.abs(want).max(axis=2))).mean())
+    print("real hair scene: exact %.4f close %.4f mean %.4f/%.4f" % (exact, close, img.mean(), want.mean()))
+    assert float((want.max(axis=2) > 0).mean()) > 0.9          # not a black frame
+    assert close >= 0.97
+    assert abs(float(img.mean()) - float(want.mean())) <= 1e-2*float(want.mean())

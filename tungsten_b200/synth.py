@@ -330,7 +330,7 @@ def curly_fibers(n_curves=200, nodes_per_curve=14, radius=0.45, length=1.1, widt
 
 
 def hair_scene(out_dir, name="hair", n_curves=200, nodes_per_curve=14, mode="bcsdf_cylinder", bsdf=None, res=(128, 128),
-               spp=16, max_bounces=16, thickness=None, taper=False, subsample=0.0, env=(0.35, 0.4, 0.5), width=0.01):
+               spp=16, max_bounces=16, thickness=None, taper=False, subsample=0.0, env=(0.35, 0.4, 0.5), width=0.01, head=False):
     """C4 stand-in: curly strands (`curves` primitive + `.fiber` file) with the hair BCSDF over a Lambert floor, lit by a
     quad light and a constant environment.  (The shipped hair scene's emitters, infinite_sphere_cap + skydome, are
     outside the hot path)"""
@@ -352,7 +352,13 @@ def hair_scene(out_dir, name="hair", n_curves=200, nodes_per_curve=14, mode="bcs
               "transform": {"position": [0.9, 2.6, 1.2], "scale": [0.7, 1, 0.7], "rotation": [0, 0, 150]}}]
     if env is not None:
         prims.append({"name": "env", "type": "infinite_sphere", "emission": list(env), "sample": True})
-    sc = {"media": [], "bsdfs": [_lambert("floor", [0.5, 0.5, 0.5]), hb, {"name": "light", "albedo": 1, "type": "null"}],
+    meshes = {}
+    if head:        # a triangle mesh under the strands: triangles and curve segments then share one BVH (joint root)
+        meshes[name + "_head.wo3"] = icosphere(2, 1.0, displace=0.05)
+        prims.append({"name": "head", "type": "mesh", "file": name + "_head.wo3", "smooth": True, "bsdf": "head",
+                      "transform": {"position": [0.0, 1.3, 0.0], "scale": [0.42, 0.5, 0.42], "rotation": [0, 0, 0]}})
+    sc = {"media": [], "bsdfs": [_lambert("floor", [0.5, 0.5, 0.5]), hb, {"name": "light", "albedo": 1, "type": "null"},
+                                 {"name": "head", "type": "rough_plastic", "albedo": [0.7, 0.5, 0.4], "roughness": 0.3}],
           "primitives": prims,
           "camera": {"tonemap": "filmic", "resolution": list(res), "reconstruction_filter": "tent",
                      "transform": {"position": [0.3, 1.2, 3.4], "look_at": [0, 0.95, 0], "up": [0, 1, 0]},
@@ -361,4 +367,4 @@ def hair_scene(out_dir, name="hair", n_curves=200, nodes_per_curve=14, mode="bcs
                          "enable_consistency_checks": False, "enable_two_sided_shading": True,
                          "enable_light_sampling": True},
           "renderer": _renderer(spp)}
-    return write_scene(out_dir, name, sc)
+    return write_scene(out_dir, name, sc, meshes)
