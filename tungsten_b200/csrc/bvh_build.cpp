@@ -26,12 +26,12 @@ struct Box {
 struct Tmp { Box box; int32_t left, right; uint32_t first, count; };
 
 constexpr int kBins = 16;
-constexpr uint32_t kMaxLeaf = 4;
-constexpr float kTraversalCost = 1.0f, kIntersectCost = 1.0f;
+constexpr float kTraversalCost = 1.0f;
 
 struct Builder {
     const Box *tb; const float *cent; uint32_t *idx; std::vector<Tmp> nodes; std::atomic<uint32_t> n_nodes{0};
     std::atomic<int> free_threads{0};
+    uint32_t kMaxLeaf = 4; float kIntersectCost = 1.0f;      // leaf size cap (<= 4: two bits in the leaf link) and SAH cost of one primitive test
 
     uint32_t alloc() { return n_nodes.fetch_add(1); }
 
@@ -101,7 +101,7 @@ inline float pad_up(float v) { return std::nextafter(std::nextafter(v, std::nume
 
 }  // namespace
 
-static void build_from_boxes(std::vector<Box> &tb, std::vector<float> &cent, uint32_t n, Bvh4 &out, int threads);
+static void build_from_boxes(std::vector<Box> &tb, std::vector<float> &cent, uint32_t n, Bvh4 &out, int threads, uint32_t max_leaf = 4, float isect_cost = 1.0f);
 
 void build_bvh4(const BuildTri *tris, uint32_t n, Bvh4 &out, int threads, float abs_pad) {
     out.nodes.clear(); out.order.clear(); out.max_depth = 0; out.sah_cost = 0.0;
@@ -116,7 +116,7 @@ void build_bvh4(const BuildTri *tris, uint32_t n, Bvh4 &out, int threads, float 
     build_from_boxes(tb, cent, n, out, threads);
 }
 
-void build_bvh4_boxes(const BuildBox *boxes, uint32_t n, Bvh4 &out, int threads, float abs_pad) {
+void build_bvh4_boxes(const BuildBox *boxes, uint32_t n, Bvh4 &out, int threads, float abs_pad, uint32_t max_leaf, float isect_cost) {
     out.nodes.clear(); out.order.clear(); out.max_depth = 0; out.sah_cost = 0.0;
     for (int a = 0; a < 3; ++a) { out.lo[a] = std::numeric_limits<float>::infinity(); out.hi[a] = -out.lo[a]; }
     if (n == 0) return;
@@ -126,13 +126,14 @@ void build_bvh4_boxes(const BuildBox *boxes, uint32_t n, Bvh4 &out, int threads,
             cent[3*size_t(i) + a] = boxes[i].centroid[a];
             tb[i].lo[a] = pad_down(boxes[i].lo[a] - abs_pad); tb[i].hi[a] = pad_up(boxes[i].hi[a] + abs_pad);
         }
-    build_from_boxes(tb, cent, n, out, threads);
+    build_from_boxes(tb, cent, n, out, threads, std::min<uint32_t>(std::max<uint32_t>(max_leaf, 1), 4), isect_cost);
 }
 
-static void build_from_boxes(std::vector<Box> &tb, std::vector<float> &cent, uint32_t n, Bvh4 &out, int threads) {
+static void build_from_boxes(std::vector<Box> &tb, std::vector<float> &cent, uint32_t n, Bvh4 &out, int threads, uint32_t max_leaf, float isect_cost) {
     out.order.resize(n);
     for (uint32_t i = 0; i < n; ++i) out.order[i] = i;
-    Builder bl; bl.tb = tb.data(); bl.cent = cent.data(); bl.idx = out.order.data();
+    Builder bl; bl.tb = tb.data(); bl.cent = cent.data(); bl.idx = out.order.data(); bl.kMaxLeaf = max_leaf; bl.kIntersectCost = isect_cost;
+    const float kIntersectCost = isect_cost;
     bl.nodes.resize(2*size_t(n) + 1);
     if (threads <= 0) threads = int(std::thread::hardware_concurrency());
     bl.free_threads = std::max(0, threads - 1);

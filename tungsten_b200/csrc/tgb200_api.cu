@@ -450,7 +450,12 @@ int upload_scene(tgb_ctx *c, const tgb_scene_desc *d) {
         // Curve segments get their own SAH tree (leaf bit 2 = "curve leaf", records stored behind the triangles); with
         // triangles present the two trees hang under a new root, so one traversal answers TraceableScene::intersect.
         Bvh4 cb;
-        build_bvh4_boxes(cboxes.data(), n_segs_total, cb, 0, 1e-6f*extent);
+        // a segment test (3 projections + up to 32 half-cylinder pieces) costs far more than a triangle test: small leaves
+        // (the reference's BinaryBvh also keeps <= 2 segments per leaf, Curves.cpp:613)
+        uint32_t curve_leaf = 2; float curve_cost = 4.0f;
+        if (const char *e = getenv("TGB_CURVE_LEAF")) curve_leaf = uint32_t(atoi(e));
+        if (const char *e = getenv("TGB_CURVE_COST")) curve_cost = float(atof(e));
+        build_bvh4_boxes(cboxes.data(), n_segs_total, cb, 0, 1e-6f*extent, curve_leaf, curve_cost);
         const bool both = !bvh.nodes.empty();
         const int32_t tri_base = both ? 1 : 0, curve_base = tri_base + int32_t(bvh.nodes.size());
         std::vector<Node4> merged(size_t(curve_base) + cb.nodes.size());
