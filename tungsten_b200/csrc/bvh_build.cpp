@@ -103,7 +103,7 @@ inline float pad_up(float v) { return std::nextafter(std::nextafter(v, std::nume
 
 static void build_from_boxes(std::vector<Box> &tb, std::vector<float> &cent, uint32_t n, Bvh4 &out, int threads, uint32_t max_leaf = 4, float isect_cost = 1.0f);
 
-void build_bvh4(const BuildTri *tris, uint32_t n, Bvh4 &out, int threads, float abs_pad) {
+void build_bvh4(const BuildTri *tris, uint32_t n, Bvh4 &out, int threads, float abs_pad, uint32_t max_leaf, float isect_cost) {
     out.nodes.clear(); out.order.clear(); out.max_depth = 0; out.sah_cost = 0.0;
     for (int a = 0; a < 3; ++a) { out.lo[a] = std::numeric_limits<float>::infinity(); out.hi[a] = -out.lo[a]; }
     if (n == 0) return;
@@ -113,7 +113,7 @@ void build_bvh4(const BuildTri *tris, uint32_t n, Bvh4 &out, int threads, float 
         for (int a = 0; a < 3; ++a) { cent[3*size_t(i) + a] = 0.5f*b.lo[a] + 0.5f*b.hi[a]; b.lo[a] = pad_down(b.lo[a] - abs_pad); b.hi[a] = pad_up(b.hi[a] + abs_pad); }
         tb[i] = b;
     }
-    build_from_boxes(tb, cent, n, out, threads);
+    build_from_boxes(tb, cent, n, out, threads, std::min<uint32_t>(std::max<uint32_t>(max_leaf, 1), 4), isect_cost);
 }
 
 void build_bvh4_boxes(const BuildBox *boxes, uint32_t n, Bvh4 &out, int threads, float abs_pad, uint32_t max_leaf, float isect_cost) {

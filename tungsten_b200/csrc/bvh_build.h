@@ -39,7 +39,8 @@ struct BuildBox { float lo[3], hi[3], centroid[3]; };
 
 // threads <= 0: hardware concurrency.
 // abs_pad: every triangle box is grown by this absolute amount (covers the slab test's rounding).
-void build_bvh4(const BuildTri *tris, uint32_t n, Bvh4 &out, int threads = 0, float abs_pad = 0.0f);
+void build_bvh4(const BuildTri *tris, uint32_t n, Bvh4 &out, int threads = 0, float abs_pad = 0.0f,
+                uint32_t max_leaf = 4, float isect_cost = 1.0f);
 // max_leaf (1..4) and isect_cost (SAH cost of one primitive test relative to one node visit) let expensive primitives get
 // smaller leaves.
 void build_bvh4_boxes(const BuildBox *boxes, uint32_t n, Bvh4 &out, int threads = 0, float abs_pad = 0.0f,
