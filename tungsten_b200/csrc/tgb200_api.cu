@@ -40,7 +40,7 @@ struct tgb_ctx {
     // wavefront storage
     uint32_t capacity = 0;
     PathState st{}, st2{};      // st2 = second copy of the persistent arrays (ray, throughput, emission, rng, hit, pid)
-    uint32_t *queue_a = nullptr, *queue_b = nullptr, *squeue = nullptr, *squeue2 = nullptr, *free_list = nullptr;
+    uint32_t *queue_a = nullptr, *squeue = nullptr, *squeue2 = nullptr;
     uint32_t persist_blocks = 0;    // grid of the persistent traversal kernels (0 = one thread per ray)
     size_t l2_window_bytes = 0;     // bytes of BVH data pinned in L2 through the stream's access-policy window (0 = none)
     bool has_curves = false;        // selects the kernel instantiations with the curve-segment test and per-hit epsilon
@@ -623,8 +623,6 @@ int alloc_wavefront(tgb_ctx *c, uint32_t capacity) {
 #undef ALLOC2
     (void)fp;
     if ((rc = dev_alloc(c, &c->queue_a, capacity))) return rc;
-    if ((rc = dev_alloc(c, &c->queue_b, capacity))) return rc;
-    if ((rc = dev_alloc(c, &c->free_list, capacity))) return rc;
     if ((rc = dev_alloc(c, &c->bin_keys, capacity))) return rc;
     if ((rc = dev_alloc(c, &c->bin_hist, size_t(kBins) + 2))) return rc;     // + cull bin + number of sorted survivors
     if ((rc = dev_alloc(c, &c->squeue, size_t(capacity)*2))) return rc;
@@ -689,7 +687,6 @@ int set_tiles(tgb_ctx *c, const tgb_tile *tiles, uint32_t n_tiles, uint32_t seed
 
 inline unsigned blocks(uint32_t n, unsigned bs) { return n ? (n + bs - 1)/bs : 1; }
 // Rays per lane of the persistent traversal kernels: as many as keep >= ~8 blocks per SM in flight (148 SMs).
-inline uint32_t rays_per_lane(uint32_t n) { const char *e = getenv("TGB_K"); uint32_t kmax = e ? uint32_t(atoi(e)) : 1u; return std::max(1u, std::min(kmax, n/(148u*8u*uint32_t(kTraceBlock)))); }
 
 // The wavefront loop: the GPU analogue of renderTile over (pixels of the tiles) x (sample range), with path
 // regeneration: whenever paths finish, their slots are refilled with the next camera paths of the step, so every
@@ -739,7 +736,6 @@ int render_device(tgb_ctx *c, uint32_t spp_begin, uint32_t spp_count) {
             CU(cudaMemsetAsync(c->counts, 0, 6*sizeof(uint32_t), c->stream));
             if (c->profiling) CU(cudaEventRecord(c->evt0, c->stream));
             if (has_bvh) {
-                uint32_t K = rays_per_lane(n);
                 // persistent: a fixed grid pulls rays from counts[4]; else one thread per ray
                 uint32_t grid = persist ? std::min(blocks(n, kTraceBlock), c->persist_blocks) : blocks(n, kTraceBlock);
                 if (curves) { if (persist) k_trace<true, true><<<grid, kTraceBlock, kTraceSmem, c->stream>>>(sc, cur, c->queue_a, c->bin_hist + kBins + 1, n_alive, n, c->counts + 4);
@@ -747,7 +743,6 @@ int render_device(tgb_ctx *c, uint32_t spp_begin, uint32_t spp_count) {
                 else { if (persist) k_trace<false, true><<<grid, kTraceBlock, kTraceSmem, c->stream>>>(sc, cur, c->queue_a, c->bin_hist + kBins + 1, n_alive, n, c->counts + 4);
                        else k_trace<false, false><<<grid, kTraceBlock, kTraceSmem, c->stream>>>(sc, cur, c->queue_a, c->bin_hist + kBins + 1, n_alive, n, c->counts + 4); }
                 launches++;
-                (void)K;
             }
             if (c->profiling) CU(cudaEventRecord(c->evt1, c->stream));
             if (curves) k_shade<true><<<blocks(n, 128), 128, 0, c->stream>>>(sc, cur, bi, n, c->squeue, cs, c->ctr);
@@ -758,14 +753,12 @@ int render_device(tgb_ctx *c, uint32_t spp_begin, uint32_t spp_count) {
             else k_shadow_prep<false><<<blocks(2*n, 256), 256, 0, c->stream>>>(sc, cur, c->ss, c->squeue, cs, c->squeue2, cs + 1, c->ctr);
             launches++;
             if (has_bvh) {
-                uint32_t K = rays_per_lane(2*n);
                 uint32_t grid = persist ? std::min(blocks(2*n, kTraceBlock), c->persist_blocks) : blocks(2*n, kTraceBlock);
                 if (curves) { if (persist) k_shadow_bvh<true, true><<<grid, kTraceBlock, kTraceSmem, c->stream>>>(sc, cur, c->ss, c->squeue2, cs + 1, c->ctr, c->counts + 5);
                               else k_shadow_bvh<true, false><<<grid, kTraceBlock, kTraceSmem, c->stream>>>(sc, cur, c->ss, c->squeue2, cs + 1, c->ctr, c->counts + 5); }
                 else { if (persist) k_shadow_bvh<false, true><<<grid, kTraceBlock, kTraceSmem, c->stream>>>(sc, cur, c->ss, c->squeue2, cs + 1, c->ctr, c->counts + 5);
                        else k_shadow_bvh<false, false><<<grid, kTraceBlock, kTraceSmem, c->stream>>>(sc, cur, c->ss, c->squeue2, cs + 1, c->ctr, c->counts + 5); }
                 launches++;
-                (void)K;
             }
             if (c->profiling) CU(cudaEventRecord(c->evs1, c->stream));
             CU(cudaMemsetAsync(c->bin_hist, 0, (kBins + 1)*sizeof(uint32_t), c->stream));
@@ -957,9 +950,8 @@ int tgb200_trace_closest(tgb_ctx *c, const tgb_ray *rays, tgb_hit *hits, uint32_
         if ((e = cudaMemcpyAsync(dr, rays, size_t(n)*sizeof(tgb_ray), cudaMemcpyHostToDevice, c->stream)) != cudaSuccess) break;
         k_hook_analytic<<<blocks(n, 256), 256, 0, c->stream>>>(c->sc, dr, dx, n);
         if (c->sc.n_nodes) {
-            uint32_t K = rays_per_lane(n);
-            if (c->has_curves) k_hook_bvh<true><<<blocks(n, kTraceBlock*K), kTraceBlock, kTraceSmem, c->stream>>>(c->sc, dr, dx, n, K);
-            else k_hook_bvh<false><<<blocks(n, kTraceBlock*K), kTraceBlock, kTraceSmem, c->stream>>>(c->sc, dr, dx, n, K);
+            if (c->has_curves) k_hook_bvh<true><<<blocks(n, kTraceBlock), kTraceBlock, kTraceSmem, c->stream>>>(c->sc, dr, dx, n);
+            else k_hook_bvh<false><<<blocks(n, kTraceBlock), kTraceBlock, kTraceSmem, c->stream>>>(c->sc, dr, dx, n);
             c->stats.kernel_launches++;
         }
         k_hook_finish<<<blocks(n, 256), 256, 0, c->stream>>>(c->sc, dr, dx, dh, n);

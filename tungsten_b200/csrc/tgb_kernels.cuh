@@ -1,11 +1,17 @@
-// Wavefront kernels of the B200 path tracer (sm_100a).  One thread per path / per ray query.
-//   k_raygen  : SobolPathSampler::startPath + ReconstructionFilter::sample + PinholeCamera::sampleDirection
-//   k_trace   : TraceableScene::intersect  (closest hit; analytic prims + 4-ary BVH over all mesh triangles)
-//   k_shade   : makeLocalScatterEvent + handleSurface (NEE/MIS query generation, emission, BSDF sample, RR)
-//   k_shadow  : attenuatedEmission/generalizedShadowRay for the NEE and MIS queries (same traversal + epilogue)
-//   k_accum   : folds the bounce's direct-light estimate into the path, NaN guards, compacts survivors
-//   k_resolve : OutputBuffer::addSample running mean, samples folded in sample-index order
-// State lives in SoA arrays indexed by a fixed path slot; queues hold slot ids.
+// Wavefront kernels of the B200 path tracer (sm_100a).
+//   k_regen        : SobolPathSampler::startPath + ReconstructionFilter::sample + PinholeCamera::sampleDirection for the camera
+//                    paths that replace finished ones (appended behind the compacted survivors)
+//   k_trace        : TraceableScene::intersect (closest hit): persistent warps pull rays from the coherence-sorted queue and
+//                    walk the 4-ary BVH over all mesh triangles (+ curve segments); analytic primitives were tested by the
+//                    kernel that created the ray
+//   k_shade        : makeLocalScatterEvent + handleSurface (NEE/MIS query generation, emission, BSDF sample, Russian roulette)
+//   k_shadow_prep  : analytic part of the NEE/MIS queries, top-level BVH cut, compaction of what is left
+//   k_shadow_bvh   : attenuatedEmission / generalizedShadowRay for those (same traversal + epilogue)
+//   k_accum        : folds the bounce's direct-light estimate into the path, NaN guards, compacts survivors into the other
+//                    state buffer, analytic test + BVH cut + coherence key of their next ray
+//   k_bin_scan/k_bin_scatter : counting sort of the survivors' slot indices by that key
+//   k_resolve      : OutputBuffer::addSample running mean, samples folded in sample-index order
+// Path state lives in SoA arrays indexed by slot (survivors first, new camera paths behind them).
 #pragma once
 #include "tgb_device.cuh"
 
@@ -405,9 +411,9 @@ TGB_D bool mesh_cut_hit(const DScene &sc, V3 o, V3 d, float tnear, float tfar) {
     return hit;
 }
 
-// Policy wrapper kept for the three users (path rays, shadow queries, parity hook): one ray per thread.
+// One ray per thread (parity hook; the renderer's kernels when TGB_PERSIST=0): a policy object supplies the ray and takes the hit.
 template <bool CURVES, class P>
-TGB_D void bvh_traverse_multi(const DScene &sc, int *smem_stack, P &pol, uint32_t n, uint32_t /*K*/) {
+TGB_D void bvh_traverse_multi(const DScene &sc, int *smem_stack, P &pol, uint32_t n) {
     uint32_t i = blockIdx.x*blockDim.x + threadIdx.x;
     if (i >= n) return;
     V3 o, d; float tnear; Hit h; bool any;
@@ -599,7 +605,7 @@ __global__ void __launch_bounds__(kTraceBlock, TGB_MINB) k_trace(DScene sc, Path
     extern __shared__ int smem_stack[];
     PathRayPolicy pol; pol.st = st; pol.order = order; pol.n_sorted = n_sorted; pol.n_surv = n_surv; pol.n_all = n; pol.s = 0;
     if (PERSIST) bvh_traverse_persistent<CURVES>(sc, smem_stack, pol, n, counter);
-    else bvh_traverse_multi<CURVES>(sc, smem_stack, pol, n, 1);
+    else bvh_traverse_multi<CURVES>(sc, smem_stack, pol, n);
 }
 
 // Parity hook (tgb200_trace_closest): rays in AoS tgb_ray, hits out as tgb_hit, through the same analytic pass and
@@ -620,10 +626,10 @@ __global__ void __launch_bounds__(256) k_hook_analytic(DScene sc, const tgb_ray 
     out[i] = analytic_closest(sc, v3(rays[i].o[0], rays[i].o[1], rays[i].o[2]), v3(rays[i].d[0], rays[i].d[1], rays[i].d[2]), rays[i].tmin, rays[i].tmax);
 }
 template <bool CURVES>
-__global__ void __launch_bounds__(kTraceBlock) k_hook_bvh(DScene sc, const tgb_ray *rays, Hit *out, uint32_t n, uint32_t K) {
+__global__ void __launch_bounds__(kTraceBlock) k_hook_bvh(DScene sc, const tgb_ray *rays, Hit *out, uint32_t n) {
     extern __shared__ int smem_stack[];
     HookPolicy pol; pol.rays = rays; pol.out = out; pol.i = 0;
-    bvh_traverse_multi<CURVES>(sc, smem_stack, pol, n, K);
+    bvh_traverse_multi<CURVES>(sc, smem_stack, pol, n);
 }
 __global__ void __launch_bounds__(256) k_hook_finish(DScene sc, const tgb_ray *rays, const Hit *in, tgb_hit *hits, uint32_t n) {
     uint32_t i = blockIdx.x*blockDim.x + threadIdx.x;
@@ -970,7 +976,7 @@ __global__ void __launch_bounds__(kTraceBlock, TGB_MINB) k_shadow_bvh(DScene sc,
     extern __shared__ int smem_stack[];
     ShadowPolicy<CURVES> pol; pol.sc = sc; pol.st = st; pol.ss = ss; pol.squeue2 = squeue2; pol.hits = &ctr->shadow_hits;
     if (PERSIST) bvh_traverse_persistent<CURVES>(sc, smem_stack, pol, *scount2, counter);
-    else bvh_traverse_multi<CURVES>(sc, smem_stack, pol, *scount2, 1);
+    else bvh_traverse_multi<CURVES>(sc, smem_stack, pol, *scount2);
 }
 
 // Fold this bounce's direct light + surface emission into the path (order as in handleSurface:537-543), apply the
