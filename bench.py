@@ -35,6 +35,7 @@ W, H = 1920, 1080
 ALG_BYTES_PER_QUERY = 48
 CONFIGS = {
     "c1": {"res": (1920, 1080), "label": "C1: Cornell box + 868,480-tri Lambert mesh (procedural dragon stand-in), 1920x1080, path_tracer, max_bounces 64, Sobol"},
+    "c2": {"res": (1920, 1080), "label": "C2: room with 327,680-triangle furniture stand-ins in rough conductor / rough dielectric / plastic / rough plastic, checker floor, quad + mesh lights + importance-sampled HDR environment, 1920x1080, max_bounces 16, Sobol"},
     "c3": {"res": (3840, 2160), "label": "C3: 12,544,000-triangle instanced forest (490 trees x 2 masters, flattened), Lambert + rough plastic + HDR sky, 3840x2160, max_bounces 16, Sobol"},
     "c4": {"res": (1920, 1080), "label": "C4: 650,000 quadratic B-spline curve segments (10,000 curly strands x 67 nodes, bcsdf_cylinder) with the hair BCSDF over a Lambert floor, quad light + constant sky, 1920x1080, max_bounces 16, Sobol"},
 }
@@ -78,6 +79,12 @@ def make_scene(spp, config="c1"):
         path = os.path.join(d, "forest10m.json")
         if not os.path.exists(path):
             synth.instanced_forest(d, "forest10m", n_instances=490, tree_subdiv=5, res=CONFIGS["c3"]["res"], spp=spp, extent=40.0)
+        return path
+    if config == "c2":
+        path = os.path.join(d, "room.json")
+        if not os.path.exists(path):
+            synth.save_rgbe(os.path.join(d, "room_env.hdr"), synth.sky_envmap(512, 256))
+            synth.material_room(d, "room", res=CONFIGS["c2"]["res"], spp=spp, max_bounces=16, subdiv=6, env="room_env.hdr")
         return path
     if config == "c4":
         path = os.path.join(d, "hair650k.json")

@@ -43,6 +43,7 @@ struct tgb_ctx {
     uint32_t *queue_a = nullptr, *squeue = nullptr, *squeue2 = nullptr;
     uint32_t persist_blocks = 0;    // grid of the persistent traversal kernels (0 = one thread per ray)
     size_t l2_window_bytes = 0;     // bytes of BVH data pinned in L2 through the stream's access-policy window (0 = none)
+    bool sort_materials = false;    // >= 2 lobe models in use: k_shade deals the paths of a block to its threads by BSDF type
     bool has_curves = false;        // selects the kernel instantiations with the curve-segment test and per-hit epsilon
     uint32_t *bin_keys = nullptr, *bin_hist = nullptr;      // queue_a doubles as the ray-coherence visiting order of k_trace
     size_t res_capacity = 0;
@@ -598,6 +599,19 @@ int upload_scene(tgb_ctx *c, const tgb_scene_desc *d) {
     sc.n_prims = uint32_t(prims.size()); sc.n_lights = int(lights.size()); sc.n_inf_lights = int(inf_lights.size());
     sc.n_analytic = int(analytic.size()); sc.n_nodes = uint32_t(bvh.nodes.size()); sc.n_tris = uint32_t(btris.size());
     sc.n_curve_segs = uint32_t(cboxes.size()); c->has_curves = !cboxes.empty();
+    {
+        uint32_t types = 0;
+        for (uint32_t i = 0; i < d->n_primitives; ++i) {
+            const tgb_primitive &p = d->primitives[i];
+            if (p.type == TGB_PRIM_INFINITE_SPHERE) continue;
+            for (uint32_t k = 0; k < p.bsdf_count; ++k) {
+                uint32_t t = d->bsdfs[d->bsdf_slots[p.bsdf_first + k]].type;
+                if (t != TGB_BSDF_NULL) types |= 1u << std::min(t, 31u);
+            }
+        }
+        const char *env = getenv("TGB_SORT_MATERIALS");
+        c->sort_materials = env ? env[0] == '1' : __builtin_popcount(types) >= 2;
+    }
     return TGB_OK;
 }
 
@@ -745,8 +759,13 @@ int render_device(tgb_ctx *c, uint32_t spp_begin, uint32_t spp_count) {
                 launches++;
             }
             if (c->profiling) CU(cudaEventRecord(c->evt1, c->stream));
-            if (curves) k_shade<true><<<blocks(n, 128), 128, 0, c->stream>>>(sc, cur, bi, n, c->squeue, cs, c->ctr);
-            else k_shade<false><<<blocks(n, 128), 128, 0, c->stream>>>(sc, cur, bi, n, c->squeue, cs, c->ctr);
+            if (c->sort_materials) {
+                if (curves) k_shade<true, true><<<blocks(n, kShadeSortBlock), kShadeSortBlock, 0, c->stream>>>(sc, cur, bi, n, c->squeue, cs, c->ctr);
+                else k_shade<false, true><<<blocks(n, kShadeSortBlock), kShadeSortBlock, 0, c->stream>>>(sc, cur, bi, n, c->squeue, cs, c->ctr);
+            } else {
+                if (curves) k_shade<true, false><<<blocks(n, 128), 128, 0, c->stream>>>(sc, cur, bi, n, c->squeue, cs, c->ctr);
+                else k_shade<false, false><<<blocks(n, 128), 128, 0, c->stream>>>(sc, cur, bi, n, c->squeue, cs, c->ctr);
+            }
             launches++;
             if (c->profiling) CU(cudaEventRecord(c->evs0, c->stream));
             if (curves) k_shadow_prep<true><<<blocks(2*n, 256), 256, 0, c->stream>>>(sc, cur, c->ss, c->squeue, cs, c->squeue2, cs + 1, c->ctr);

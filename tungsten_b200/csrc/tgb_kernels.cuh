@@ -655,15 +655,48 @@ __global__ void __launch_bounds__(256) k_hook_finish(DScene sc, const tgb_ray *r
 #ifndef TGB_SHADE_MINB
 #define TGB_SHADE_MINB 8
 #endif
-template <bool CURVES>
-__global__ void __launch_bounds__(128, TGB_SHADE_MINB) k_shade(DScene sc, PathState st, BatchInfo bi, uint32_t n,
-                                               uint32_t *squeue, uint32_t *scount, Counters *ctr) {
+// MATSORT ("active-ray sort by material" of the path): scenes with several lobe models make the lanes of a warp run
+// different BSDF code one after the other (C2: k_shade 20x slower per path than on the Lambert-only C1).  The paths of a
+// block are therefore dealt to its threads by BSDF type (block-local counting sort in shared memory: 512 consecutive
+// slots, so every state array is still read in full sectors by the block as a whole); which thread shades which slot
+// cannot change a result.  The key costs the hit -> primitive -> material gathers once more, so scenes with a single
+// lobe model keep the unsorted kernel.
+constexpr int kShadeSortBlock = 512;
+TGB_D uint32_t shade_sort_key(const DScene &sc, const Hit &h) {
+    if (h.id == HID_MISS) return 0u;
+    int bsdf;
+    if (h.id >= 0) {
+        uint32_t g = __ldg(sc.tri_global + h.id);
+        const DPrim &m = sc.prims[__ldg(sc.tri_prim + g)];
+        int mat = (uint32_t(h.id) >= sc.n_tris) ? 0 : __float_as_int(__ldg(sc.tri_shade + 4*size_t(g) + 3).w);
+        bsdf = int(__ldg(sc.slots + m.bsdf_first + mat));
+    } else bsdf = int(__ldg(sc.slots + sc.prims[-h.id - 2].bsdf_first));
+    return 1u + min(sc.bsdfs[bsdf].type, 13u);
+}
+template <bool CURVES, bool MATSORT>
+__global__ void __launch_bounds__(MATSORT ? kShadeSortBlock : 128, MATSORT ? 2 : TGB_SHADE_MINB)
+k_shade(DScene sc, PathState st, BatchInfo bi, uint32_t n, uint32_t *squeue, uint32_t *scount, Counters *ctr) {
     uint32_t i = blockIdx.x*blockDim.x + threadIdx.x;
     bool valid = i < n;
     bool qn = false, qm = false, qn_any = false, qm_any = false;
     uint32_t s = 0;
     // one path query (TraceableScene::intersect) was completed for every slot in the queue
     count_block(&ctr->rays, &ctr->hits, valid, valid && __float_as_int(st.h4[valid ? i : 0].w) != HID_MISS);
+    if (MATSORT) {
+        __shared__ uint32_t bucket[16];
+        __shared__ uint16_t perm[kShadeSortBlock];
+        if (threadIdx.x < 16) bucket[threadIdx.x] = 0u;
+        __syncthreads();
+        uint32_t key = valid ? shade_sort_key(sc, unpack_hit(st.h4[i])) : 15u;      // slots past the end sort last
+        uint32_t rank = atomicAdd(&bucket[key], 1u);
+        __syncthreads();
+        uint32_t before = 0;
+        for (uint32_t k = 0; k < key; ++k) before += bucket[k];
+        perm[before + rank] = uint16_t(threadIdx.x);
+        __syncthreads();
+        i = blockIdx.x*blockDim.x + perm[threadIdx.x];
+        valid = i < n;
+    }
     if (valid) {
         s = i;
         uint32_t info = st.info[s];
