@@ -92,6 +92,102 @@ def make_kat():
     shutil.rmtree(d)
 
 
+KAT_CURVES_CPP = r"""
+#include <cstdio>
+#include <cstdlib>
+#include <cmath>
+#include <memory>
+#include <new>
+#include <vector>
+#include "bsdfs/HairBcsdf.hpp"
+#include "primitives/Curves.hpp"
+#include "primitives/IntersectionInfo.hpp"
+#include "primitives/IntersectionTemporary.hpp"
+#include "samplerecords/SurfaceScatterEvent.hpp"
+#include "math/TangentFrame.hpp"
+#include "math/Ray.hpp"
+using namespace Tungsten;
+static unsigned bits(float v) { union { float f; unsigned u; } c; c.f = v; return c.u; }
+struct CurveIsect { uint32 curveP0; float t; Vec2f uv; float w; };      // mirror of the struct private to Curves.cpp:27-33
+int main() {
+    // ---- HairBcsdf with its constructor defaults (scale_angle 2, melanin 0.5 / 0.25, roughness 0.1)
+    HairBcsdf hair;
+    hair.prepareForRender();
+    IntersectionInfo info;
+    printf("{\n\"hair\": [");
+    for (int k = 0; k < 48; ++k) {
+        float a = 0.37f*k, b = 1.13f*k + 0.5f;
+        Vec3f wi(std::cos(a)*std::cos(0.61f*k), std::sin(0.61f*k)*0.9f, std::sin(a)*std::cos(0.61f*k));
+        Vec3f wo(std::cos(b)*std::cos(0.23f*k + 1.0f), std::sin(0.23f*k + 1.0f)*0.95f, std::sin(b)*std::cos(0.23f*k + 1.0f));
+        wi.normalize(); wo.normalize();
+        SurfaceScatterEvent ev(&info, nullptr, TangentFrame(Vec3f(0.0f, 0.0f, 1.0f)), wi, BsdfLobes::AllLobes, false);
+        ev.wo = wo;
+        Vec3f f = hair.eval(ev);
+        float pdf = hair.pdf(ev);
+        printf("%s[%u, %u, %u, %u, %u, %u, %u, %u, %u, %u]", k ? ", " : "", bits(wi.x()), bits(wi.y()), bits(wi.z()), bits(wo.x()), bits(wo.y()),
+               bits(wo.z()), bits(f.x()), bits(f.y()), bits(f.z()), bits(pdf));
+    }
+    // ---- Curves::intersect (half_cylinder) on 6 curly strands x 9 nodes
+    std::vector<uint32> ends; std::vector<Vec4f> nodes;
+    for (int c = 0; c < 6; ++c) {
+        for (int i = 0; i < 9; ++i) {
+            float s = i/8.0f, ang = 5.0f*s + c;
+            nodes.emplace_back(0.4f*c - 1.0f + 0.15f*std::cos(ang), 1.0f - 1.8f*s, 0.15f*std::sin(ang) + 0.05f*c, 0.02f + 0.004f*((c + i) % 3));
+        }
+        ends.push_back(uint32(nodes.size()));
+    }
+    printf("],\n\"nodes\": [");
+    for (size_t i = 0; i < nodes.size(); ++i) printf("%s[%u, %u, %u, %u]", i ? ", " : "", bits(nodes[i].x()), bits(nodes[i].y()), bits(nodes[i].z()), bits(nodes[i].w()));
+    printf("],\n\"ends\": [");
+    for (size_t i = 0; i < ends.size(); ++i) printf("%s%u", i ? ", " : "", ends[i]);
+    std::shared_ptr<Bsdf> bsdf = std::make_shared<HairBcsdf>();
+    // this constructor leaves Curves::_subsample uninitialised (Curves.cpp:278-291); zeroed storage makes it 0 = keep every curve
+    void *mem = calloc(1, sizeof(Curves));
+    Curves &curves = *new (mem) Curves(ends, nodes, bsdf, "kat");
+    curves.prepareForRender();
+    printf("],\n\"rays\": [");
+    for (int k = 0; k < 400; ++k) {
+        Vec3f o(-2.0f + 0.01f*k, 1.5f - 0.007f*k, 2.5f + 0.3f*std::sin(0.7f*k));
+        // aim near the curve: a quadratic B-spline segment starts at the midpoint of its first two nodes
+        int c = k % 6, i = (k/6) % 8;
+        Vec3f mid = (nodes[c*9 + i].xyz() + nodes[c*9 + i + 1].xyz())*0.5f;
+        Vec3f tgt = mid + Vec3f(0.03f*std::sin(1.3f*k), 0.02f*std::cos(0.9f*k), 0.0f);
+        Vec3f d = (tgt - o).normalized();
+        Ray ray(o, d, 1e-4f);
+        IntersectionTemporary tmp;
+        bool hit = curves.intersect(ray, tmp);
+        const CurveIsect *is = tmp.as<CurveIsect>();
+        printf("%s[%u, %u, %u, %u, %u, %u, %d, %u, %u, %u, %u, %u]", k ? ", " : "", bits(o.x()), bits(o.y()), bits(o.z()), bits(d.x()), bits(d.y()), bits(d.z()),
+               hit ? 1 : 0, hit ? bits(ray.farT()) : 0u, hit ? is->curveP0 : 0u, hit ? bits(is->uv.x()) : 0u, hit ? bits(is->uv.y()) : 0u, hit ? bits(is->w) : 0u);
+    }
+    printf("]\n}\n");
+}
+"""
+
+
+def make_kat_curves():
+    """Known answers of HairBcsdf::eval/pdf and Curves::intersect from the reference's own classes -> kat_curves.json."""
+    import glob
+    d = tempfile.mkdtemp()
+    src = os.path.join(d, "kat_curves.cpp")
+    open(src, "w").write(KAT_CURVES_CPP)
+    exe = os.path.join(d, "kat_curves")
+    obj = os.path.join(ROOT, "oracle", "_ref", "obj")
+    objs = [o for o in glob.glob(os.path.join(obj, "**", "*.o"), recursive=True)
+            if not o.endswith("tungsten_main.o") and os.sep + "pathseed" + os.sep not in o]
+    cmd = ["/opt/gcc/bin/g++", "-std=c++11", "-O2", "-march=core2", "-mssse3", "-mno-fma", "-DCONSTEXPR=constexpr", "-DRAPIDJSON_HAS_STDSTRING=1",
+           "-I" + REF + "/src/core", "-I" + REF + "/src/thirdparty", "-I" + REF + "/src/thirdparty/embree/include", "-I" + REF + "/src", "-w", src] + objs + \
+          ["-o", exe, "-lpthread", "-ldl"]
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if r.returncode != 0:
+        print(r.stdout[-3000:])
+        raise SystemExit("curve KAT program failed to build")
+    out = subprocess.check_output([exe], text=True)
+    json.loads(out)
+    open(os.path.join(HERE, "kat_curves.json"), "w").write(out)
+    shutil.rmtree(d)
+
+
 def make_scenes():
     from tungsten_b200 import synth
     scenes = {}
@@ -125,4 +221,5 @@ def make_scenes():
 
 if __name__ == "__main__":
     make_kat()
+    make_kat_curves()
     make_scenes()
