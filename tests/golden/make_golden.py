@@ -165,6 +165,91 @@ int main() {
 """
 
 
+KAT_BSDF_CPP = r"""
+#include <cstdio>
+#include <cmath>
+#include <memory>
+#include <vector>
+#include "bsdfs/LambertBsdf.hpp"
+#include "bsdfs/RoughConductorBsdf.hpp"
+#include "bsdfs/RoughDielectricBsdf.hpp"
+#include "bsdfs/PlasticBsdf.hpp"
+#include "bsdfs/RoughPlasticBsdf.hpp"
+#include "bsdfs/SmoothCoatBsdf.hpp"
+#include "textures/ConstantTexture.hpp"
+#include "primitives/IntersectionInfo.hpp"
+#include "samplerecords/SurfaceScatterEvent.hpp"
+#include "math/TangentFrame.hpp"
+using namespace Tungsten;
+static unsigned bits(float v) { union { float f; unsigned u; } c; c.f = v; return c.u; }
+int main() {
+    std::vector<std::shared_ptr<Bsdf>> list;
+    { auto b = std::make_shared<LambertBsdf>(); b->setAlbedo(std::make_shared<ConstantTexture>(Vec3f(0.7f, 0.5f, 0.3f))); list.push_back(b); }
+    { auto b = std::make_shared<RoughConductorBsdf>(); list.push_back(b); }
+    { auto b = std::make_shared<RoughConductorBsdf>(); b->setDistributionName("beckmann"); b->setRoughness(std::make_shared<ConstantTexture>(0.3f));
+      b->setEta(Vec3f(0.143f, 0.375f, 1.442f)); b->setK(Vec3f(3.98f, 2.39f, 1.6f)); list.push_back(b); }
+    { auto b = std::make_shared<RoughConductorBsdf>(); b->setDistributionName("phong"); b->setRoughness(std::make_shared<ConstantTexture>(0.2f)); list.push_back(b); }
+    { auto b = std::make_shared<RoughDielectricBsdf>(); list.push_back(b); }
+    { auto b = std::make_shared<RoughDielectricBsdf>(); b->setDistributionName("beckmann"); b->setRoughness(std::make_shared<ConstantTexture>(0.25f)); b->setIor(1.33f); list.push_back(b); }
+    { auto b = std::make_shared<PlasticBsdf>(); b->setIor(1.5f); b->setThickness(2.0f); b->setSigmaA(Vec3f(0.1f, 0.2f, 0.3f));
+      b->setAlbedo(std::make_shared<ConstantTexture>(Vec3f(0.2f, 0.4f, 0.8f))); list.push_back(b); }
+    { auto b = std::make_shared<RoughPlasticBsdf>(); b->setDistributionName("beckmann"); b->setRoughness(std::make_shared<ConstantTexture>(0.3f)); b->setIor(1.4f);
+      b->setSigmaA(Vec3f(0.1f, 0.2f, 0.3f)); b->setAlbedo(std::make_shared<ConstantTexture>(Vec3f(0.8f, 0.3f, 0.2f))); list.push_back(b); }
+    { auto sub = std::make_shared<RoughConductorBsdf>(); sub->setDistributionName("beckmann");
+      auto b = std::make_shared<SmoothCoatBsdf>(); b->setIor(1.7f); b->setThickness(5.0f); b->setSigmaA(Vec3f(0.1f, 0.2f, 0.5f)); b->setSubstrate(sub); list.push_back(b); }
+    IntersectionInfo info; info.uv = Vec2f(0.3f, 0.4f);
+    printf("{\n\"bsdfs\": [");
+    for (size_t n = 0; n < list.size(); ++n) {
+        list[n]->prepareForRender();
+        printf("%s[", n ? ",\n" : "");
+        for (int k = 0; k < 40; ++k) {
+            float a = 0.37f*k + 0.1f*n, b = 1.13f*k + 0.5f;
+            float zi = 0.05f + 0.9f*std::fabs(std::sin(0.61f*k + 0.3f)), zo = std::sin(0.23f*k + 1.0f);      // wi above, wo on both sides
+            if (k % 5 == 0) zi = -zi;                                                                            // and a few wi from below
+            Vec3f wi(std::cos(a)*std::sqrt(1.0f - zi*zi), std::sin(a)*std::sqrt(1.0f - zi*zi), zi);
+            Vec3f wo(std::cos(b)*std::sqrt(1.0f - zo*zo), std::sin(b)*std::sqrt(1.0f - zo*zo), zo);
+            if (k % 7 == 3) wo = Vec3f(-wi.x(), -wi.y(), wi.z());                                                // exact mirror direction
+            SurfaceScatterEvent ev(&info, nullptr, TangentFrame(Vec3f(0.0f, 0.0f, 1.0f)), wi, BsdfLobes::AllLobes, false);
+            ev.wo = wo;
+            Vec3f f = list[n]->eval(ev);
+            float pdf = list[n]->pdf(ev);
+            printf("%s[%u, %u, %u, %u, %u, %u, %u, %u, %u, %u]", k ? ", " : "", bits(wi.x()), bits(wi.y()), bits(wi.z()), bits(wo.x()), bits(wo.y()),
+                   bits(wo.z()), bits(f.x()), bits(f.y()), bits(f.z()), bits(pdf));
+        }
+        printf("]");
+    }
+    printf("]\n}\n");
+}
+"""
+
+
+def _build_and_run_kat(source, name, out_json):
+    import glob
+    d = tempfile.mkdtemp()
+    src = os.path.join(d, name + ".cpp")
+    open(src, "w").write(source)
+    exe = os.path.join(d, name)
+    obj = os.path.join(ROOT, "oracle", "_ref", "obj")
+    objs = [o for o in glob.glob(os.path.join(obj, "**", "*.o"), recursive=True)
+            if not o.endswith("tungsten_main.o") and os.sep + "pathseed" + os.sep not in o]
+    cmd = ["/opt/gcc/bin/g++", "-std=c++11", "-O2", "-march=core2", "-mssse3", "-mno-fma", "-DCONSTEXPR=constexpr", "-DRAPIDJSON_HAS_STDSTRING=1",
+           "-I" + REF + "/src/core", "-I" + REF + "/src/thirdparty", "-I" + REF + "/src/thirdparty/embree/include", "-I" + REF + "/src", "-w", src] + objs + \
+          ["-o", exe, "-lpthread", "-ldl"]
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if r.returncode != 0:
+        print(r.stdout[-3000:])
+        raise SystemExit(name + ": KAT program failed to build")
+    out = subprocess.check_output([exe], text=True)
+    json.loads(out)
+    open(os.path.join(HERE, out_json), "w").write(out)
+    shutil.rmtree(d)
+
+
+def make_kat_bsdfs():
+    """Known answers of eval()/pdf() of the reference's own BSDF classes (nine parameterisations) -> kat_bsdfs.json."""
+    _build_and_run_kat(KAT_BSDF_CPP, "kat_bsdfs", "kat_bsdfs.json")
+
+
 def make_kat_curves():
     """Known answers of HairBcsdf::eval/pdf and Curves::intersect from the reference's own classes -> kat_curves.json."""
     import glob
@@ -222,4 +307,5 @@ def make_scenes():
 if __name__ == "__main__":
     make_kat()
     make_kat_curves()
+    make_kat_bsdfs()
     make_scenes()

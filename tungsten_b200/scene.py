@@ -434,7 +434,9 @@ class FlatScene:
             o.type = abi.BSDF_LAMBERT
         elif ty == "rough_conductor":
             o.type = abi.BSDF_ROUGH_CONDUCTOR
-            eta, k = COMPLEX_IOR["Cu"]
+            # the constructor's own (rounded) copper constants; the table is consulted only when "material" is given
+            # (RoughConductorBsdf.cpp:17-25,32-39)
+            eta, k = (0.200438, 0.924033, 1.10221), (3.91295, 2.45285, 2.14219)
             if "eta" in b and "k" in b:
                 eta, k = _vec3_field(b, "eta"), _vec3_field(b, "k")
             if "material" in b:
