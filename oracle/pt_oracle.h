@@ -42,6 +42,8 @@ void     oracle_filter_cdf(uint32_t filter, float *cdf32, float *bin_size);
 float    oracle_diffuse_fresnel(float ior, int sample_count);
 int      oracle_kat_eval(int which, const float *in, float *out);
 int      oracle_bsdf_eval(oracle_scene *s, int index, float u, float v, const float *wi_wo, int n, float *out);
+int      oracle_bsdf_sample(oracle_scene *s, uint32_t seed, int n, const int *bsdf_index, const uint32_t *pixel_id, uint32_t sample,
+                            float u, float v, const float *wi, float *out, uint32_t *lobes);
 int      oracle_hair_eval(float roughness, float scale_angle_deg, const float *sigma_a, const float *wi_wo, int n, float *out);
 int      oracle_hair_tables(float roughness, float scale_angle_deg, const float *sigma_a, float *tables, float *sums, float *v);
 

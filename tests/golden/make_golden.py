@@ -179,9 +179,17 @@ KAT_BSDF_CPP = r"""
 #include "textures/ConstantTexture.hpp"
 #include "primitives/IntersectionInfo.hpp"
 #include "samplerecords/SurfaceScatterEvent.hpp"
+#include "sampling/SobolPathSampler.hpp"
 #include "math/TangentFrame.hpp"
 using namespace Tungsten;
 static unsigned bits(float v) { union { float f; unsigned u; } c; c.f = v; return c.u; }
+static unsigned lobe_mask(BsdfLobes l) {       // BsdfLobes keeps its bits private: rebuild the mask (bsdfs/BsdfLobes.hpp:13-34)
+    unsigned m = 0;
+    const BsdfLobes::Lobe all[] = {BsdfLobes::GlossyReflectionLobe, BsdfLobes::GlossyTransmissionLobe, BsdfLobes::DiffuseReflectionLobe,
+        BsdfLobes::DiffuseTransmissionLobe, BsdfLobes::SpecularReflectionLobe, BsdfLobes::SpecularTransmissionLobe};
+    for (int i = 0; i < 6; ++i) if (l.test(BsdfLobes(all[i]))) m |= 1u << i;
+    return m;
+}
 int main() {
     std::vector<std::shared_ptr<Bsdf>> list;
     { auto b = std::make_shared<LambertBsdf>(); b->setAlbedo(std::make_shared<ConstantTexture>(Vec3f(0.7f, 0.5f, 0.3f))); list.push_back(b); }
@@ -215,6 +223,26 @@ int main() {
             float pdf = list[n]->pdf(ev);
             printf("%s[%u, %u, %u, %u, %u, %u, %u, %u, %u, %u]", k ? ", " : "", bits(wi.x()), bits(wi.y()), bits(wi.z()), bits(wo.x()), bits(wo.y()),
                    bits(wo.z()), bits(f.x()), bits(f.y()), bits(f.z()), bits(pdf));
+        }
+        printf("]");
+    }
+    // ---- sample(): the reference's own SobolPathSampler (stock header: ONE supplemental PCG stream for the whole run),
+    //      path (pixel k, sample 7) per draw; output success, wo, weight, pdf, sampled lobe mask
+    printf("],\n\"sample_seed\": %u,\n\"samples\": [", 0x5EED1234u);
+    SobolPathSampler sampler(0x5EED1234u);
+    for (size_t n = 0; n < list.size(); ++n) {
+        printf("%s[", n ? ",\n" : "");
+        for (int k = 0; k < 40; ++k) {
+            float a = 0.37f*k + 0.1f*n;
+            float zi = 0.05f + 0.9f*std::fabs(std::sin(0.61f*k + 0.3f));
+            if (k % 5 == 0) zi = -zi;
+            Vec3f wi(std::cos(a)*std::sqrt(1.0f - zi*zi), std::sin(a)*std::sqrt(1.0f - zi*zi), zi);
+            sampler.startPath(uint32(k), 7);
+            SurfaceScatterEvent ev(&info, &sampler, TangentFrame(Vec3f(0.0f, 0.0f, 1.0f)), wi, BsdfLobes::AllLobes, false);
+            bool ok = list[n]->sample(ev);
+            printf("%s[%u, %u, %u, %d, %u, %u, %u, %u, %u, %u, %u, %u]", k ? ", " : "", bits(wi.x()), bits(wi.y()), bits(wi.z()), ok ? 1 : 0,
+                   ok ? bits(ev.wo.x()) : 0u, ok ? bits(ev.wo.y()) : 0u, ok ? bits(ev.wo.z()) : 0u, ok ? bits(ev.weight.x()) : 0u,
+                   ok ? bits(ev.weight.y()) : 0u, ok ? bits(ev.weight.z()) : 0u, ok ? bits(ev.pdf) : 0u, ok ? lobe_mask(ev.sampledLobe) : 0u);
         }
         printf("]");
     }
