@@ -104,6 +104,7 @@ KAT_CURVES_CPP = r"""
 #include "primitives/IntersectionInfo.hpp"
 #include "primitives/IntersectionTemporary.hpp"
 #include "samplerecords/SurfaceScatterEvent.hpp"
+#include "sampling/SobolPathSampler.hpp"
 #include "math/TangentFrame.hpp"
 #include "math/Ray.hpp"
 using namespace Tungsten;
@@ -126,6 +127,19 @@ int main() {
         float pdf = hair.pdf(ev);
         printf("%s[%u, %u, %u, %u, %u, %u, %u, %u, %u, %u]", k ? ", " : "", bits(wi.x()), bits(wi.y()), bits(wi.z()), bits(wo.x()), bits(wo.y()),
                bits(wo.z()), bits(f.x()), bits(f.y()), bits(f.z()), bits(pdf));
+    }
+    // ---- HairBcsdf::sample through the reference's SobolPathSampler (4 Sobol dimensions per draw)
+    printf("],\n\"hair_sample_seed\": %u,\n\"hair_samples\": [", 0x0BADC0DEu);
+    SobolPathSampler sampler(0x0BADC0DEu);
+    for (int k = 0; k < 48; ++k) {
+        float a = 0.37f*k;
+        Vec3f wi(std::cos(a)*std::cos(0.61f*k), std::sin(0.61f*k)*0.9f, std::sin(a)*std::cos(0.61f*k));
+        wi.normalize();
+        sampler.startPath(uint32(k), 3);
+        SurfaceScatterEvent ev(&info, &sampler, TangentFrame(Vec3f(0.0f, 0.0f, 1.0f)), wi, BsdfLobes::AllLobes, false);
+        bool ok = hair.sample(ev);
+        printf("%s[%u, %u, %u, %d, %u, %u, %u, %u, %u, %u, %u]", k ? ", " : "", bits(wi.x()), bits(wi.y()), bits(wi.z()), ok ? 1 : 0,
+               bits(ev.wo.x()), bits(ev.wo.y()), bits(ev.wo.z()), bits(ev.weight.x()), bits(ev.weight.y()), bits(ev.weight.z()), bits(ev.pdf));
     }
     // ---- Curves::intersect (half_cylinder) on 6 curly strands x 9 nodes
     std::vector<uint32> ends; std::vector<Vec4f> nodes;
