@@ -44,6 +44,7 @@ int      oracle_kat_eval(int which, const float *in, float *out);
 int      oracle_bsdf_eval(oracle_scene *s, int index, float u, float v, const float *wi_wo, int n, float *out);
 int      oracle_bsdf_sample(oracle_scene *s, uint32_t seed, int n, const int *bsdf_index, const uint32_t *pixel_id, uint32_t sample,
                             float u, float v, const float *wi, float *out, uint32_t *lobes);
+int      oracle_light_probe(oracle_scene *s, int prim, uint32_t seed, int n, uint32_t sample, const float *p, float *out);
 int      oracle_hair_eval(float roughness, float scale_angle_deg, const float *sigma_a, const float *wi_wo, int n, float *out);
 int      oracle_hair_tables(float roughness, float scale_angle_deg, const float *sigma_a, float *tables, float *sums, float *v);
 

@@ -292,6 +292,95 @@ def make_kat_bsdfs():
     _build_and_run_kat(KAT_BSDF_CPP, "kat_bsdfs", "kat_bsdfs.json")
 
 
+KAT_LIGHTS_CPP = r"""
+#include <cstdio>
+#include <cstdlib>
+#include <cmath>
+#include <memory>
+#include <vector>
+#include "primitives/Quad.hpp"
+#include "primitives/TriangleMesh.hpp"
+#include "primitives/InfiniteSphere.hpp"
+#include "primitives/EmbreeUtil.hpp"
+#include "primitives/IntersectionInfo.hpp"
+#include "primitives/IntersectionTemporary.hpp"
+#include "samplerecords/LightSample.hpp"
+#include "sampling/SobolPathSampler.hpp"
+#include "textures/ConstantTexture.hpp"
+#include "textures/BitmapTexture.hpp"
+#include "bsdfs/LambertBsdf.hpp"
+#include "math/Ray.hpp"
+using namespace Tungsten;
+static unsigned bits(float v) { union { float f; unsigned u; } c; c.f = v; return c.u; }
+// sampleDirect from point p, then the light's own intersect + intersectionInfo + directPdf + evalDirect along the sampled
+// direction (what TraceBase::lightSample / attenuatedEmission / bsdfSample use), one Sobol path per draw
+static void probe(Primitive &light, SobolPathSampler &sampler, int n, int sampleIndex) {
+    for (int k = 0; k < n; ++k) {
+        Vec3f p(-0.8f + 0.07f*k, 0.9f + 0.05f*(k % 7), 0.6f - 0.04f*k);
+        sampler.startPath(uint32(k), uint32(sampleIndex));
+        LightSample ls;
+        bool ok = light.sampleDirect(0, p, sampler, ls);
+        unsigned hit = 0; float pdf2 = 0.0f; Vec3f em(0.0f); float t = 0.0f;
+        if (ok) {
+            Ray ray(p, ls.d, 5e-4f);
+            IntersectionTemporary data; IntersectionInfo info;
+            if (light.intersect(ray, data)) {
+                hit = 1; t = ray.farT();
+                info.p = ray.pos() + ray.dir()*ray.farT(); info.w = ray.dir(); info.epsilon = 5e-4f;
+                light.intersectionInfo(data, info);
+                pdf2 = light.directPdf(0, data, info, p);
+                em = light.evalDirect(data, info);
+            }
+        }
+        printf("%s[%u, %u, %u, %d, %u, %u, %u, %u, %u, %u, %u, %u, %u, %u, %u]", k ? ", " : "", bits(p.x()), bits(p.y()), bits(p.z()), ok ? 1 : 0,
+               bits(ok ? ls.d.x() : 0.0f), bits(ok ? ls.d.y() : 0.0f), bits(ok ? ls.d.z() : 0.0f), bits(ok ? ls.dist : 0.0f), bits(ok ? ls.pdf : 0.0f),
+               hit, bits(t), bits(pdf2), bits(em.x()), bits(em.y()), bits(em.z()));
+    }
+}
+int main() {
+    const TraceableScene *noScene = nullptr;                 // makeSamplable of quads and meshes ignores its scene argument
+    EmbreeUtil::initDevice();                                 // as the renderer does at start-up (src/tungsten/Shared.hpp:165)
+    std::shared_ptr<Bsdf> bsdf = std::make_shared<LambertBsdf>();
+    SobolPathSampler sampler(0xC0FFEE11u);
+    printf("{\n\"seed\": %u,\n", 0xC0FFEE11u);
+    // ---- quad light, identity orientation (normal +y), 1.5 x 1 at y = 0
+    Quad quad;
+    quad.setTransform(Mat4f::translate(Vec3f(0.1f, 0.0f, -0.2f))*Mat4f::scale(Vec3f(1.5f, 1.0f, 1.0f)));
+    quad.setEmission(std::make_shared<ConstantTexture>(Vec3f(3.0f, 2.0f, 1.0f)));
+    quad.prepareForRender();
+    quad.makeSamplable(*noScene, 0);
+    printf("\"quad\": ["); probe(quad, sampler, 40, 2); printf("],\n");
+    // ---- mesh light: 5 triangles of different areas facing up / tilted
+    std::vector<Vertex> verts = {Vertex(Vec3f(-1.0f, 0.0f, -1.0f)), Vertex(Vec3f(1.0f, 0.0f, -1.0f)), Vertex(Vec3f(1.0f, 0.1f, 1.0f)), Vertex(Vec3f(-1.0f, 0.0f, 1.0f)),
+                                 Vertex(Vec3f(0.0f, 0.4f, 0.0f)), Vertex(Vec3f(2.0f, 0.3f, 0.5f))};
+    std::vector<TriangleI> tris = {TriangleI(0, 2, 1, 0), TriangleI(0, 3, 2, 0), TriangleI(0, 4, 1, 0), TriangleI(1, 5, 2, 0), TriangleI(3, 4, 2, 0)};
+    TriangleMesh mesh(verts, tris, bsdf, "kat", false, false);
+    mesh.setTransform(Mat4f::translate(Vec3f(0.0f, -0.3f, 0.0f)));
+    mesh.setEmission(std::make_shared<ConstantTexture>(Vec3f(1.0f, 4.0f, 2.0f)));
+    mesh.prepareForRender();
+    mesh.makeSamplable(*noScene, 0);
+    printf("\"mesh\": ["); probe(mesh, sampler, 40, 3); printf("],\n");
+    // ---- environment sphere with a 32x16 RGB bitmap (exactly representable texels), importance sampled
+    const int W = 32, H = 16;
+    Vec3f *texels = new Vec3f[W*H];
+    for (int y = 0; y < H; ++y) for (int x = 0; x < W; ++x)
+        texels[x + y*W] = Vec3f(1.0f + float((x*7 + y*3) % 11), 0.5f + float((x*5 + y) % 7), 0.25f*float((x + y) % 5));
+    auto tex = std::make_shared<BitmapTexture>(texels, W, H, BitmapTexture::TexelType::RGB_HDR, true, false);
+    InfiniteSphere sphere;
+    sphere.setEmission(tex);
+    sphere.prepareForRender();
+    tex->makeSamplable(MAP_SPHERICAL);                       // what InfiniteSphere::makeSamplable does besides caching the scene bounds
+    printf("\"env\": ["); probe(sphere, sampler, 48, 4); printf("]\n}\n");
+}
+"""
+
+
+def make_kat_lights():
+    """Known answers of sampleDirect / intersect / directPdf / evalDirect of the reference's Quad, TriangleMesh and
+    InfiniteSphere(+BitmapTexture importance map) classes -> kat_lights.json."""
+    _build_and_run_kat(KAT_LIGHTS_CPP, "kat_lights", "kat_lights.json")
+
+
 def make_kat_curves():
     """Known answers of HairBcsdf::eval/pdf and Curves::intersect from the reference's own classes -> kat_curves.json."""
     import glob
@@ -350,4 +439,5 @@ if __name__ == "__main__":
     make_kat()
     make_kat_curves()
     make_kat_bsdfs()
+    make_kat_lights()
     make_scenes()

@@ -416,13 +416,19 @@ class FlatScene:
                 raise SceneError("bitmap format outside the hot path: %s" % ext)
             if value.get("gamma_correct", True) is False:
                 pass  # HDR inputs are linear either way (BitmapTexture: gamma only applies to LDR)
-            img = np.ascontiguousarray(img, dtype=np.float32)
-            self._keep.append(img)
-            t = abi.Texture(type=abi.TEX_BITMAP, res_u=img.shape[1], res_v=img.shape[0])
-            t.flags = (1 if value.get("interpolate", True) else 0) | (2 if value.get("clamp", False) else 0)
-            t.texels = img.ctypes.data_as(C.POINTER(C.c_float))
-            self.textures.append(t); return len(self.textures) - 1
+            return self.add_bitmap_texture(img, value.get("interpolate", True), value.get("clamp", False))
         raise SceneError("texture type outside the hot path: %r" % ty)
+
+    def add_bitmap_texture(self, img, linear=True, clamp=False):
+        """BitmapTexture over in-memory RGB fp32 texels, shape (h, w, 3), top row first (textures/BitmapTexture.cpp:52-59)."""
+        img = np.ascontiguousarray(img, dtype=np.float32)
+        if img.ndim != 3 or img.shape[2] != 3:
+            raise SceneError("bitmap texels must have shape (h, w, 3)")
+        self._keep.append(img)
+        t = abi.Texture(type=abi.TEX_BITMAP, res_u=img.shape[1], res_v=img.shape[0])
+        t.flags = (1 if linear else 0) | (2 if clamp else 0)
+        t.texels = img.ctypes.data_as(C.POINTER(C.c_float))
+        self.textures.append(t); return len(self.textures) - 1
 
     def add_bsdf(self, b, base_dir=".", named=None):
         ty = b.get("type", "lambert")
