@@ -4,6 +4,11 @@ needs /root/reference and the binaries built by `make -C oracle/ref`).
   kat.json            known-answer values printed by a ~60-line host program compiled against the reference's
                       own headers (hash32, PCG32, normalizedUint, sobol::sample, cosineHemisphere, Fresnel terms,
                       computeDiffuseFresnel, the tent filter CDF, TangentFrame)
+  kat_bsdfs.json      eval / pdf / sample of the reference's own BSDF classes (nine parameterisations, 40 direction pairs and 40
+                      draws each through its SobolPathSampler), from a host program linked against the reference's objects
+  kat_lights.json     sampleDirect / intersect / directPdf / evalDirect of its Quad, TriangleMesh and InfiniteSphere (+ BitmapTexture
+                      importance map) classes
+  kat_curves.json     HairBcsdf eval / pdf / sample and Curves::intersect (400 rays at 6 strands) of its classes
   <scene>/            scene JSON + .wo3 written by tungsten_b200.synth, plus
   <scene>/ref_pathseed.pfm   framebuffer of oracle/_ref/tungsten_pathseed (per-path reseed contract)
   <scene>/ref_stock.pfm      framebuffer of the UNMODIFIED reference binary
