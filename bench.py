@@ -108,8 +108,58 @@ def hbm_peak():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def parse_duration(text):
+    """Seconds from the reference's `durationToString` (src/core/io/StringUtils.cpp:51-68):
+    "[Dd ][Hh ][Mm ]Ss MSms" when >= 1 s, else the plain double followed by "s"."""
+    m = re.search(r"Render time ((?:\d+d )?(?:\d+h )?(?:\d+m )?)(\d+)s (\d+)ms", text)
+    if m:
+        secs = float(m.group(2)) + float(m.group(3))/1e3
+        for tok in m.group(1).split():
+            secs += float(tok[:-1])*{"d": 86400.0, "h": 3600.0, "m": 60.0}[tok[-1]]
+        return secs
+    m = re.search(r"Render time ([0-9.eE+-]+)s", text)
+    return float(m.group(1)) if m else None
+
+
+def host_cpu_info():
+    """What the CPU arm can actually use: affinity mask, cgroup quota, model string."""
+    info = {"os_cpu_count": os.cpu_count() or 1}
+    try:
+        info["affinity"] = len(os.sched_getaffinity(0))
+    except Exception:
+        info["affinity"] = info["os_cpu_count"]
+    quota = None
+    for p in ("/sys/fs/cgroup/cpu.max", "/sys/fs/cgroup/cpu/cpu.cfs_quota_us"):
+        try:
+            txt = open(p).read().split()
+            if p.endswith("cpu.max"):
+                if txt[0] != "max":
+                    quota = float(txt[0])/float(txt[1])
+            else:
+                q = float(txt[0])
+                if q > 0:
+                    quota = q/float(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+            break
+        except Exception:
+            continue
+    info["cgroup_cpus"] = quota
+    try:
+        for ln in open("/proc/cpuinfo"):
+            if ln.startswith("model name"):
+                info["model"] = ln.split(":", 1)[1].strip(); break
+    except Exception:
+        pass
+    usable = info["affinity"]
+    if quota:
+        usable = max(1, min(usable, int(quota + 0.5)))
+    info["usable"] = usable
+    return info
+
+
 def run_reference_binary(scene_path, spp, threads):
-    """Times oracle/_ref/tungsten (the unmodified reference) on `spp` samples per pixel of the bench scene."""
+    """Times oracle/_ref/tungsten (the unmodified reference) on `spp` samples per pixel of the bench scene.
+    Returns (Msamples/s, render seconds): the reference's own "Render time", which excludes scene load and its
+    Embree BVH build (src/tungsten/Shared.hpp:255-319) -- as our arm's timed region excludes tgb200_create."""
     exe = os.path.join(ROOT, "oracle", "_ref", "tungsten")
     if not os.path.exists(exe):
         return None
@@ -121,41 +171,46 @@ def run_reference_binary(scene_path, spp, threads):
     json.dump(js, open(rp, "w"))
     out = subprocess.run([exe, "-t", str(threads), "-d", os.path.join(d, "ref_out"), rp], stdout=subprocess.PIPE,
                          stderr=subprocess.STDOUT, text=True)
-    m = re.search(r"Render time ([0-9.]+)\s*s", out.stdout)
-    m2 = re.search(r"Render time (?:(\d+)h )?(?:(\d+)m )?([0-9.]+)s", out.stdout)
-    if m2:
-        secs = float(m2.group(3)) + 60.0*float(m2.group(2) or 0) + 3600.0*float(m2.group(1) or 0)
-    elif m:
-        secs = float(m.group(1))
-    else:
+    secs = parse_duration(out.stdout)
+    if not secs:
         return None
     return W*H*spp/secs/1e6, secs
 
 
 def bench_reference(args, rank, world):
-    """--impl reference: the reference's own CPU path on the host cores (rank 0 only)."""
+    """--impl reference: the reference's own CPU path on the host cores (rank 0 only).  One step = one run of the
+    unmodified binary on a bounded sample (spp chosen from a calibration run so that a step RENDERS for >= ~6 s)."""
     if rank != 0:
         return
-    cores = os.cpu_count() or 1
+    cpu = host_cpu_info()
+    threads = cpu["usable"]
     scene_path = make_scene(1024, args.config)
-    spp = args.ref_spp
-    vals = []
+    cal = run_reference_binary(scene_path, 2, threads)          # calibration, untimed
+    if cal is None:
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/tungsten is missing (run make -C oracle/ref)"}))
+        return
+    spp = args.ref_spp if args.ref_spp > 0 else int(min(256, max(4, round(cal[0]*1e6*args.ref_seconds/(W*H)))))
+    runs = []
     for i in range(args.warmup + args.steps):
-        r = run_reference_binary(scene_path, spp, cores)
+        r = run_reference_binary(scene_path, spp if i >= args.warmup else 1, threads)
         if r is None:
-            print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/tungsten is missing (run make -C oracle/ref)"}))
+            print(json.dumps({"impl": "reference", "unavailable": "the reference binary printed no render time"}))
             return
         if i >= args.warmup:
-            vals.append(r)
-    secs = sum(v[1] for v in vals)
-    value = W*H*spp*len(vals)/secs/1e6
+            runs.append(r)
+    secs = sum(v[1] for v in runs)
+    value = W*H*spp*len(runs)/secs/1e6
+    rates = sorted(v[0] for v in runs)
     line = {"impl": "reference", "metric": "Msamples/sec (paths x spp)", "value": value, "unit": "Msamples/s",
-            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3*secs/len(vals),
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3*secs/len(runs),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": CONFIGS[args.config]["label"],
-                       "step": "%d spp of the whole frame (bounded sample of the 1024-spp job)" % spp},
-            "cpu_baseline": {"value": value, "unit": "Msamples/s", "cores": cores, "kind": "reference",
-                             "sample": "%d spp of the whole frame per step, tungsten -t %d (SSE4.2 Embree build, no AVX: the reference's own ISA policy)" % (spp, cores)},
+            "config": {"workload": CONFIGS[args.config]["label"]},
+            "cpu_baseline": {"value": value, "unit": "Msamples/s", "cores": threads, "kind": "reference",
+                             "sample": "%d spp of the whole %dx%d frame per step (bounded sample of the job; non-adaptive, so the per-sample rate is "
+                                       "spp independent), tungsten -t %d, SSE4.2 Embree build without AVX (the reference's own ISA policy); time = the "
+                                       "binary's 'Render time' (excludes scene load + BVH build, as our arm excludes tgb200_create)" % (spp, W, H, threads),
+                             "min": rates[0], "median": rates[len(rates)//2], "max": rates[-1], "runs": len(rates),
+                             "host": cpu},
             "e2e": {"value": value, "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line))
@@ -168,7 +223,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--spp-per-step", type=int, default=64)
-    ap.add_argument("--ref-spp", type=int, default=4)
+    ap.add_argument("--ref-spp", type=int, default=0, help="samples per pixel of one reference step (0 = calibrate to --ref-seconds)")
+    ap.add_argument("--ref-seconds", type=float, default=6.0, help="target render time of one reference step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--config", default="c1", choices=sorted(CONFIGS))
     args = ap.parse_args()
@@ -285,12 +341,17 @@ def main():
 
     if rank == 0:
         cpu = None
-        if world == 1 and not args.no_cpu_baseline and args.config == "c1":
-            cores = os.cpu_count() or 1
-            r = run_reference_binary(scene_path, args.ref_spp, cores)
-            if r is not None:
-                cpu = {"value": r[0], "unit": "Msamples/s", "cores": cores, "kind": "reference",
-                       "sample": "%d spp x 1920x1080 of the same scene in %.1f s, oracle/_ref/tungsten -t %d" % (args.ref_spp, r[1], cores)}
+        if world == 1 and not args.no_cpu_baseline and args.config != "c3":
+            host = host_cpu_info()
+            cal = run_reference_binary(scene_path, 2, host["usable"])
+            if cal is not None:
+                spp_c = args.ref_spp if args.ref_spp > 0 else int(min(256, max(4, round(cal[0]*1e6*10.0/(W*H)))))
+                r = run_reference_binary(scene_path, spp_c, host["usable"])
+                if r is not None:
+                    cpu = {"value": r[0], "unit": "Msamples/s", "cores": host["usable"], "kind": "reference",
+                           "sample": "%d spp x %dx%d of the same scene rendered in %.2f s by oracle/_ref/tungsten -t %d ('Render time': excludes "
+                                     "scene load + BVH build, as the GPU arm excludes tgb200_create)" % (spp_c, W, H, r[1], host["usable"]),
+                           "host": host}
         line = {
             "metric": "Msamples/sec (paths x spp)", "value": value, "unit": "Msamples/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3*wall/args.steps,

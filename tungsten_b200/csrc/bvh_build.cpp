@@ -198,4 +198,121 @@ static void build_from_boxes(std::vector<Box> &tb, std::vector<float> &cent, uin
     }
 }
 
+// ---- quantised layout -------------------------------------------------------------------------------------------
+namespace {
+inline float node_half_area(const Node4 &nd, int k) {
+    float dx = nd.f[4 + k] - nd.f[k], dy = nd.f[12 + k] - nd.f[8 + k], dz = nd.f[20 + k] - nd.f[16 + k];
+    return dx*dy + dy*dz + dz*dx;
+}
+}  // namespace
+
+void quantize_bvh4(const Bvh4 &in, uint32_t max_treelet, QBvh4 &out) {
+    out.nodes.clear(); out.old_index.clear(); out.treelet_image.clear(); out.n_treelet = 0;
+    const size_t n = in.nodes.size();
+    if (n == 0) return;
+    // ---- order: treelet = repeatedly take the open inner node with the largest surface area (the nodes a random ray is
+    // most likely to visit), parents before children; the rest depth-first under each treelet frontier node.
+    std::vector<int32_t> order; order.reserve(n);
+    std::vector<uint8_t> taken(n, 0);
+    {
+        struct Open { float area; int32_t node; };
+        auto cmp = [](const Open &a, const Open &b) { return a.area < b.area || (a.area == b.area && a.node > b.node); };
+        std::vector<Open> heap; heap.push_back({std::numeric_limits<float>::infinity(), 0});
+        while (!heap.empty() && order.size() < size_t(max_treelet)) {
+            std::pop_heap(heap.begin(), heap.end(), cmp);
+            Open o = heap.back(); heap.pop_back();
+            order.push_back(o.node); taken[size_t(o.node)] = 1;
+            const Node4 &nd = in.nodes[size_t(o.node)];
+            for (int k = 0; k < 4; ++k) if (nd.link[k] >= 0) { heap.push_back({node_half_area(nd, k), nd.link[k]}); std::push_heap(heap.begin(), heap.end(), cmp); }
+        }
+        out.n_treelet = uint32_t(order.size());
+        // remaining nodes: depth-first from every frontier node, in treelet order (children near their parents)
+        std::vector<int32_t> stack;
+        auto dfs = [&](int32_t root) {
+            stack.clear(); stack.push_back(root);
+            while (!stack.empty()) {
+                int32_t x = stack.back(); stack.pop_back();
+                if (taken[size_t(x)]) continue;
+                taken[size_t(x)] = 1; order.push_back(x);
+                const Node4 &nd = in.nodes[size_t(x)];
+                for (int k = 3; k >= 0; --k) if (nd.link[k] >= 0) stack.push_back(nd.link[k]);
+            }
+        };
+        if (out.n_treelet == 0) dfs(0);
+        for (uint32_t i = 0; i < out.n_treelet; ++i) {
+            const Node4 &nd = in.nodes[size_t(order[i])];
+            for (int k = 0; k < 4; ++k) if (nd.link[k] >= 0 && !taken[size_t(nd.link[k])]) dfs(nd.link[k]);
+        }
+    }
+    std::vector<int32_t> new_index(n, -1);
+    for (size_t i = 0; i < order.size(); ++i) new_index[size_t(order[i])] = int32_t(i);
+    out.old_index = order;
+    out.nodes.resize(order.size());
+    for (size_t i = 0; i < order.size(); ++i) {
+        const Node4 &nd = in.nodes[size_t(order[i])];
+        QNode4 q; std::memset(&q, 0, sizeof(q));
+        float org[3], S[3]; uint32_t lo[3] = {0, 0, 0}, hi[3] = {0, 0, 0};
+        for (int a = 0; a < 3; ++a) {
+            double mn = std::numeric_limits<double>::infinity(), mx = -mn;
+            for (int k = 0; k < 4; ++k) if (nd.link[k] != kEmptyLink) { mn = std::min(mn, double(nd.f[8*a + k])); mx = std::max(mx, double(nd.f[8*a + 4 + k])); }
+            if (!(mx >= mn)) { mn = 0.0; mx = 0.0; }
+            // grid: plane(q) = org + q*2^e.  org sits at least 1/128 step below the lowest child plane so that q = 0 keeps the
+            // same 1/256-step guard as every other value; e = the smallest exponent for which the highest plane still maps to <= 255.
+            const double ext = mx - mn;
+            int e = ext > 0.0 ? std::max(-120, int(std::floor(std::log2(ext/255.0))) - 1) : -120;
+            for (;; ++e) {
+                const double st = std::ldexp(1.0, e);
+                float og = float(mn - st/64.0);
+                while (double(og) > mn - st/128.0) og = std::nextafter(og, -std::numeric_limits<float>::infinity());
+                if (std::ceil((mx - double(og))/st + 1.0/256.0) <= 255.0) { org[a] = og; break; }
+            }
+            const double step = std::ldexp(1.0, e);
+            S[a] = float(std::ldexp(1.0, e + 15));
+            for (int k = 0; k < 4; ++k) {
+                uint32_t ql = 255, qh = 0;                      // empty child: inverted box
+                if (nd.link[k] != kEmptyLink) {
+                    double l = (double(nd.f[8*a + k]) - double(org[a]))/step - 1.0/256.0;
+                    double h = (double(nd.f[8*a + 4 + k]) - double(org[a]))/step + 1.0/256.0;
+                    ql = uint32_t(std::min(255.0, std::max(0.0, std::floor(l))));
+                    qh = uint32_t(std::min(255.0, std::max(0.0, std::ceil(h))));
+                }
+                lo[a] |= ql << (8*k); hi[a] |= qh << (8*k);
+            }
+        }
+        q.ox = org[0]; q.oy = org[1]; q.oz = org[2]; q.sx = S[0]; q.sy = S[1]; q.sz = S[2];
+        q.lox = lo[0]; q.hix = hi[0]; q.loy = lo[1]; q.hiy = hi[1]; q.loz = lo[2]; q.hiz = hi[2];
+        for (int k = 0; k < 4; ++k) q.link[k] = nd.link[k] >= 0 ? new_index[size_t(nd.link[k])] : nd.link[k];
+        out.nodes[i] = q;
+    }
+    out.treelet_image.resize(out.n_treelet);
+    for (uint32_t i = 0; i < out.n_treelet; ++i) {
+        const uint32_t *src = reinterpret_cast<const uint32_t *>(&out.nodes[i]);
+        uint32_t *dst = reinterpret_cast<uint32_t *>(&out.treelet_image[i]);
+        for (uint32_t c = 0; c < 4; ++c) std::memcpy(dst + 4*(c ^ ((i >> 1) & 3u)), src + 4*c, 16);
+    }
+}
+
+void qnode_slab_host(const QNode4 &nd, const float o[3], const float inv_d[3], float tnear, float tfar, float t_out[4]) {
+    // mirrors Traversal::visit in tgb_kernels.cuh operation for operation (fmaf = one rounding, as FFMA)
+    const float org[3] = {nd.ox, nd.oy, nd.oz}, S[3] = {nd.sx, nd.sy, nd.sz};
+    const uint32_t lo[3] = {nd.lox, nd.loy, nd.loz}, hi[3] = {nd.hix, nd.hiy, nd.hiz};
+    float a[3], b[3]; uint32_t nearw[3], farw[3];
+    for (int ax = 0; ax < 3; ++ax) {
+        const float ood = o[ax]*inv_d[ax];
+        a[ax] = S[ax]*inv_d[ax];
+        b[ax] = std::fmaf(org[ax], inv_d[ax], -ood) - a[ax];
+        const bool neg = inv_d[ax] < 0.0f;
+        nearw[ax] = neg ? hi[ax] : lo[ax]; farw[ax] = neg ? lo[ax] : hi[ax];
+    }
+    auto F = [](uint32_t w, int k) { uint32_t bits = 0x3F800000u | (((w >> (8*k)) & 0xFFu) << 8); float f; std::memcpy(&f, &bits, 4); return f; };
+    for (int k = 0; k < 4; ++k) {
+        float tn = tnear, tf = tfar;
+        for (int ax = 0; ax < 3; ++ax) {
+            tn = std::fmax(tn, std::fmaf(F(nearw[ax], k), a[ax], b[ax]));
+            tf = std::fmin(tf, std::fmaf(F(farw[ax], k), a[ax], b[ax]));
+        }
+        t_out[k] = (tn <= tf && nd.link[k] != kEmptyLink) ? tn : std::numeric_limits<float>::infinity();
+    }
+}
+
 }  // namespace tgb

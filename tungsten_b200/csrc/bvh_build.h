@@ -34,6 +34,37 @@ struct Bvh4 {
     double sah_cost = 0.0;
 };
 
+// ---- compressed device layout ("QNode4", 64 bytes = 4 x 16-byte loads per visit instead of 7) -------------------
+// The four child boxes are stored as 8-bit offsets from the node's own origin on a power-of-two grid:
+//     plane = origin + q * 2^e   (per axis),   q_lo = floor, q_hi = ceil  ->  the stored box CONTAINS the float box,
+// so a traversal over QNode4 visits a superset of what the float tree visits and finds the same closest hit.
+//   chunk 0: origin.x, origin.y, origin.z, Sx         S = 32768 * 2^e (the kernel builds 1 + q*2^-15 with one PRMT and
+//   chunk 1: Sy, Sz, lo.x[4], hi.x[4]                   evaluates t = fma(1 + q*2^-15, S/d, (origin - o)/d - S/d))
+//   chunk 2: lo.y[4], hi.y[4], lo.z[4], hi.z[4]       one byte per child, child k in bits 8k..8k+7
+//   chunk 3: link[4]                                  as in Node4
+// Rounding of the kernel's evaluation is covered by (a) the builder's abs_pad, exactly as for the float nodes, and
+// (b) 1/256 of a grid step subtracted/added before floor/ceil (the S/d cancellation costs at most 1/512 step).
+struct alignas(64) QNode4 {
+    float ox, oy, oz, sx;
+    float sy, sz; uint32_t lox, hix;
+    uint32_t loy, hiy, loz, hiz;
+    int32_t link[4];
+};
+static_assert(sizeof(QNode4) == 64, "QNode4 layout");
+
+struct QBvh4 {
+    std::vector<QNode4> nodes;        // renumbered: [0, n_treelet) = the top treelet (largest surface area first), rest depth-first
+    std::vector<int32_t> old_index;   // new index -> index in the Node4 array it was made from
+    uint32_t n_treelet = 0;
+    std::vector<QNode4> treelet_image;   // the first n_treelet nodes with their 16-byte chunks XOR-swizzled for shared memory:
+                                         // chunk c of node i sits at chunk c ^ ((i >> 1) & 3)  (conflict-free-ish LDS.128)
+};
+// Quantise `in` (float 4-ary BVH) into `out`; at most max_treelet nodes go to the treelet (0 = none).
+void quantize_bvh4(const Bvh4 &in, uint32_t max_treelet, QBvh4 &out);
+// Host evaluation of one node visit with the kernels' arithmetic (tests + tgb200_qbvh_selftest): entry distance of the
+// four children for the ray (o, 1/d), INFINITY where the slab test fails.
+void qnode_slab_host(const QNode4 &nd, const float o[3], const float inv_d[3], float tnear, float tfar, float t_out[4]);
+
 // A primitive given by its bounds and the point the SAH binning sorts it by (curve segments).
 struct BuildBox { float lo[3], hi[3], centroid[3]; };
 

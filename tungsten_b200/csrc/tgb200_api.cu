@@ -680,7 +680,7 @@ int set_tiles(tgb_ctx *c, const tgb_tile *tiles, uint32_t n_tiles, uint32_t seed
     std::vector<uint32_t> pid, pseed;
     for (uint32_t t = 0; t < n_tiles; ++t) {
         const tgb_tile &tl = tiles[t];
-        if (tl.x + tl.w > c->res_x || tl.y + tl.h > c->res_y) return fail(c, TGB_ERR_INVALID, "tile %u lies outside the image", t);
+        if (tl.x >= c->res_x || tl.w > c->res_x - tl.x || tl.y >= c->res_y || tl.h > c->res_y - tl.y) return fail(c, TGB_ERR_INVALID, "tile %u lies outside the image", t);
         for (uint32_t y = 0; y < tl.h; ++y) for (uint32_t x = 0; x < tl.w; ++x) { pid.push_back((tl.x + x) + (tl.y + y)*c->res_x); pseed.push_back(tl.sampler_seed); }
     }
     if (pid.size() > c->pix_capacity) {
@@ -1024,7 +1024,7 @@ static int tile_pixels(tgb_ctx *c, const tgb_tile *tiles, uint32_t n_tiles, uint
     std::vector<uint32_t> pid;
     for (uint32_t t = 0; t < n_tiles; ++t) {
         const tgb_tile &tl = tiles[t];
-        if (tl.x + tl.w > c->res_x || tl.y + tl.h > c->res_y) return fail(c, TGB_ERR_INVALID, "tile %u lies outside the image", t);
+        if (tl.x >= c->res_x || tl.w > c->res_x - tl.x || tl.y >= c->res_y || tl.h > c->res_y - tl.y) return fail(c, TGB_ERR_INVALID, "tile %u lies outside the image", t);
         for (uint32_t y = 0; y < tl.h; ++y) for (uint32_t x = 0; x < tl.w; ++x) pid.push_back((tl.x + x) + (tl.y + y)*c->res_x);
     }
     *n_out = uint32_t(pid.size()); *dev = nullptr;

@@ -59,9 +59,35 @@ def dice_tiles(w, h, seed):
     return tiles
 
 
-def shard_tiles(tiles, rank, world):
-    """Deal tiles round-robin to ranks (tile id mod world): scenes shard by image tile only."""
-    mine = [tiles[i] for i in range(rank, len(tiles), world)]
+def _morton2(x, y):
+    """Interleave the bits of two 16-bit integers (x in the even bits)."""
+    def part(v):
+        v &= 0xFFFF
+        v = (v | (v << 8)) & 0x00FF00FF
+        v = (v | (v << 4)) & 0x0F0F0F0F
+        v = (v | (v << 2)) & 0x33333333
+        v = (v | (v << 1)) & 0x55555555
+        return v
+    return part(x) | (part(y) << 1)
+
+
+def shard_order(tiles, deal="morton"):
+    """Order in which tiles are dealt to ranks.  "round_robin": the reference's row-major tile ids.  "morton": Z-order of
+    the tile grid, so any `world` consecutive tiles form a compact block and every rank's share samples the whole image
+    evenly (row-major `id mod N` degenerates to column stripes whenever tiles-per-row is a multiple of N)."""
+    idx = list(range(len(tiles)))
+    if deal == "morton":
+        idx.sort(key=lambda i: _morton2(tiles[i].x//TILE_SIZE, tiles[i].y//TILE_SIZE))
+    elif deal != "round_robin":
+        raise ValueError(deal)
+    return idx
+
+
+def shard_tiles(tiles, rank, world, deal="morton"):
+    """Deal tiles to ranks (position in shard_order mod world): scenes shard by image tile only.  Must match
+    tgb200_shard_tiles (csrc/tgb200_api.cu), which the C++ adapter and the library-side multi-GPU path use."""
+    order = shard_order(tiles, deal)
+    mine = [tiles[order[i]] for i in range(rank, len(order), world)]
     return (abi.Tile*len(mine))(*mine)
 
 
