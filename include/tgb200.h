@@ -224,7 +224,16 @@ int  tgb200_bvh_selftest(const float *tri_verts, uint32_t n, uint32_t *n_nodes, 
 /* Host-only: the hair BCSDF tables tgb200_create precomputes for one material (HairBcsdf.cpp:318-446): tables = 3 lobes
  * (R, TT, TRT) x 64 x 64 x RGB, sums = 3 x 64 row sums of the sampling weights, v = the three longitudinal variances. */
 int  tgb200_hair_selftest(float roughness, float scale_angle_deg, const float *sigma_a, float *tables, float *sums, float *v);
+/* Host-only check of the quantised device BVH (QNode4, 8-bit child boxes + shared-memory treelet image): walks it on the host
+ * with the kernels' node arithmetic for n_rays rays (8 floats each: o, d, tmin, tmax) and compares the closest t with brute
+ * force over all triangles, bit for bit.  *mismatches = rays that differ (must be 0).                                   */
+int  tgb200_qbvh_selftest(const float *tri_verts, uint32_t n, const float *rays, uint32_t n_rays, uint32_t max_treelet,
+                          uint32_t *mismatches, uint32_t *n_nodes, uint32_t *n_treelet, uint64_t *node_visits);
+/* tgb200_abort cancels the render in progress (it returns TGB_ERR_ABORTED) or, if none is running, the next one -- so an
+ * abort that lands between an asynchronous start and the worker reaching the render call is not lost.  A caller that
+ * starts renders asynchronously calls tgb200_clear_abort before spawning the worker (the adapter's startRender does).   */
 int  tgb200_abort(tgb_ctx *ctx);
+int  tgb200_clear_abort(tgb_ctx *ctx);
 void tgb200_destroy(tgb_ctx *ctx);
 /* Last error text of the context; with ctx == NULL the text of the last failed tgb200_create.       */
 const char *tgb200_last_error(const tgb_ctx *ctx);

@@ -4,6 +4,7 @@
 
 #include "renderer/TraceableScene.hpp"
 #include "cameras/PinholeCamera.hpp"
+#include "cameras/OutputBufferSettings.hpp"
 #include "primitives/InfiniteSphere.hpp"
 #include "primitives/TriangleMesh.hpp"
 #include "primitives/Curves.hpp"
@@ -334,6 +335,15 @@ void B200PathTraceIntegrator::prepareForRender(TraceableScene &scene, uint32 see
         FAIL("b200_path_tracer needs renderer.adaptive_sampling=false and renderer.stratified_sampler=true");
     if (!scene.media().empty() || scene.cam().medium())
         FAIL("b200_path_tracer: participating media are outside the hot path");
+    // The framebuffer hand-off (uploadFramebuffer) fills ONE plain colour buffer: running mean + sample counts.  Feature
+    // buffers (depth / normal / albedo / visibility) and the colour buffer's two_buffer_variance / sample_variance planes
+    // (cameras/OutputBuffer.hpp:95-132, Camera.cpp:148-160) are not produced by the GPU path: fail loudly, never write garbage.
+    for (const OutputBufferSettings &b : scene.rendererSettings().renderOutputs()) {
+        if (b.type() != OutputColor)
+            FAIL("b200_path_tracer: renderer.output_buffers entry '%s' is outside the hot path (only 'color' is produced)", b.typeString());
+        if (b.twoBufferVariance() || b.sampleVariance())
+            FAIL("b200_path_tracer: two_buffer_variance / sample_variance on the colour buffer are outside the hot path");
+    }
     PinholeCamera *cam = dynamic_cast<PinholeCamera *>(&scene.cam());
     if (!cam)
         FAIL("b200_path_tracer: only the pinhole camera is on the hot path");
@@ -409,6 +419,7 @@ void B200PathTraceIntegrator::startRender(std::function<void()> completionCallba
         return;
     }
     uint32 begin = _currentSpp, count = _nextSpp - _currentSpp;
+    tgb200_clear_abort(_ctx);          // an abortRender() from now on cancels THIS step, even before the worker reaches the library
     _worker.reset(new std::thread([this, begin, count, completionCallback]() {
         int rc = tgb200_render_resident(_ctx, nullptr, 0, _seed, begin, count);
         if (rc == TGB_OK) {

@@ -262,5 +262,11 @@ def test_abort_returns_aborted_code():
             err.append(e.code)
     th = threading.Thread(target=work); th.start(); time.sleep(0.05); ctx.abort(); th.join()
     assert err == [abi.TGB_ERR_ABORTED] or err == []          # (finished before the abort landed)
+    ctx.clear_abort()                                         # an abort that found no render running would cancel the next one
     ctx.render_resident(1)                                    # context stays usable
+    ctx.abort()                                               # abort BEFORE the render call is not lost: the next render is cancelled
+    with pytest.raises(lib.TgbError) as e:
+        ctx.render_resident(1)
+    assert e.value.code == abi.TGB_ERR_ABORTED
+    ctx.render_resident(1)                                    # ... exactly once
     ctx.close()

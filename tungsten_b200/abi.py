@@ -99,6 +99,6 @@ class Stats(C.Structure):
 EXPORTS = [
     "tgb200_create", "tgb200_render_tiles", "tgb200_render_resident", "tgb200_clear_framebuffer",
     "tgb200_read_framebuffer", "tgb200_framebuffer_device_ptr", "tgb200_trace_closest", "tgb200_pack_tiles", "tgb200_unpack_tiles",
-    "tgb200_get_stats", "tgb200_set_profiling", "tgb200_scene_info", "tgb200_reset_stats", "tgb200_bvh_selftest", "tgb200_hair_selftest", "tgb200_abort", "tgb200_destroy", "tgb200_last_error",
+    "tgb200_get_stats", "tgb200_set_profiling", "tgb200_scene_info", "tgb200_reset_stats", "tgb200_bvh_selftest", "tgb200_hair_selftest", "tgb200_qbvh_selftest", "tgb200_abort", "tgb200_clear_abort", "tgb200_destroy", "tgb200_last_error",
     "tgb200_abi_version",
 ]

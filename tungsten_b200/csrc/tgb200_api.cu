@@ -1,6 +1,6 @@
 // C ABI of libtgb200.so (include/tgb200.h): scene preparation, device upload, wavefront render loop.
 // Host logic mirrors the reference's TraceableScene constructor + PathTraceIntegrator (prepare, tile
-// dicing, sample stepping); all rendering arithmetic runs in the CUDA kernels of tgb_kernels.cuh.
+// dicing, sample stepping); all rendering arithmetic runs in the CUDA kernels of tgb_wavefront.cuh.
 // There is NO CPU fallback: without a CUDA device every entry point fails with TGB_ERR_NO_DEVICE.
 #include <atomic>
 #include <cmath>
@@ -13,7 +13,7 @@
 
 #include "bvh_build.h"
 #include "hair_tables.h"
-#include "tgb_kernels.cuh"
+#include "tgb_wavefront.cuh"
 
 extern "C" const unsigned char tgb_sobol_blob[];      // sobol_blob.cpp (.incbin of data/sobol_1024x32.u32)
 
@@ -39,17 +39,19 @@ struct tgb_ctx {
     uint32_t res_x = 0, res_y = 0;
     // wavefront storage
     uint32_t capacity = 0;
-    PathState st{}, st2{};      // st2 = second copy of the persistent arrays (ray, throughput, emission, rng, hit, pid)
-    uint32_t *queue_a = nullptr, *squeue = nullptr, *squeue2 = nullptr;
-    uint32_t persist_blocks = 0;    // grid of the persistent traversal kernels (0 = one thread per ray)
+    PathBuf pb[2]{};                // persistent path state, double buffered (k_accum compacts from one into the other)
+    Scratch sr{};                   // per-bounce scratch records + per-step results
+    uint32_t *order = nullptr, *squeue = nullptr;       // ray-coherence visiting order of k_trace; shadow-query queue
+    uint32_t persist_blocks = 0;    // grid of the persistent traversal kernels
+    size_t trace_smem = 0;          // their dynamic shared memory: treelet image + stacks + mbarrier
     size_t l2_window_bytes = 0;     // bytes of BVH data pinned in L2 through the stream's access-policy window (0 = none)
     bool sort_materials = false;    // >= 2 lobe models in use: k_shade deals the paths of a block to its threads by BSDF type
     bool has_curves = false;        // selects the kernel instantiations with the curve-segment test and per-hit epsilon
-    uint32_t *bin_keys = nullptr, *bin_hist = nullptr;      // queue_a doubles as the ray-coherence visiting order of k_trace
+    uint32_t *bin_keys = nullptr, *bin_hist = nullptr;
     size_t res_capacity = 0;
-    ShadowState ss{};
-    uint32_t *counts = nullptr;          // [0]=count A, [1]=count B, [2]=shadow count, [3]=compacted shadow count
-    uint32_t *h_counts = nullptr;        // pinned
+    Ctl *ctl = nullptr;             // device-resident loop control block
+    Ctl *h_ctl = nullptr;           // pinned: [0..3] snapshot ring (read one iteration late), [4] initial value
+    cudaEvent_t ev_ring[4]{}, ev_t0[4]{}, ev_t1[4]{}, ev_s0[4]{}, ev_s1[4]{};
     Counters *ctr = nullptr; Counters *h_ctr = nullptr;
     float *fb = nullptr; uint32_t *fb_count = nullptr;
     float *h_fb = nullptr; uint32_t *h_fb_count = nullptr;   // pinned staging
@@ -57,7 +59,7 @@ struct tgb_ctx {
     std::vector<tgb_tile> tiles_cached; uint32_t *pix_id = nullptr, *pix_seed = nullptr; uint32_t n_pix = 0, pix_capacity = 0;
     tgb_stats stats{};
     bool profiling = false;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr, evt0 = nullptr, evt1 = nullptr, evs0 = nullptr, evs1 = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     uint32_t bvh_depth = 0; uint32_t n_tris = 0; double bvh_sah = 0.0; size_t geom_bytes = 0;
 };
 
@@ -549,9 +551,26 @@ int upload_scene(tgb_ctx *c, const tgb_scene_desc *d) {
         tri_isect[3*k + 1] = make_float4(e1.y, e1.z, e2.x, e2.y);
         tri_isect[3*k + 2] = make_float4(e2.z, ng.x, ng.y, ng.z);
     }
+    // device node layout: QNode4 (64 B, 8-bit child boxes on a per-node grid), renumbered so that the nodes a random ray is most
+    // likely to visit come first: those are bulk-copied into shared memory by every traversal CTA (the "treelet")
+    QBvh4 qb;
+    {
+        // shared-memory budget of one traversal CTA: 227 KB / resident CTAs - stacks - 1 KB system reserve
+        const long budget = long(227*1024)/TGB_MINB - long(kStackSmemBytes) - 1024 - 16;
+        long want = std::max(0L, budget/64);
+        if (const char *e = getenv("TGB_TREELET")) want = std::min(want, std::max(0L, atol(e)));
+#if !TGB_QNODES
+        want = 0;
+#endif
+        quantize_bvh4(bvh, uint32_t(want), qb);
+    }
+#if TGB_QNODES
+    std::vector<float4> nodes;                                  // float nodes stay on the host (cut construction above)
+#else
     std::vector<float4> nodes(8*bvh.nodes.size());
     std::memcpy(nodes.data(), bvh.nodes.data(), bvh.nodes.size()*sizeof(Node4));
-    c->geom_bytes = nodes.size()*16 + tri_isect.size()*16 + tri_shade.size()*16 + bvh.order.size()*8;
+#endif
+    c->geom_bytes = nodes.size()*16 + qb.nodes.size()*sizeof(QNode4) + tri_isect.size()*16 + tri_shade.size()*16 + bvh.order.size()*8;
 
     int rc;
     if ((rc = dev_upload(c, &sc.prims, prims))) return rc;
@@ -570,13 +589,23 @@ int upload_scene(tgb_ctx *c, const tgb_scene_desc *d) {
         // through the same L2 in between, which is why ncu shows 5x the algorithmic DRAM bytes for k_trace.  Measured
         // (tools/gpu_env_ab.sh, C1): with the window k_trace gains 1.7 % (it is not waiting on DRAM) and the streaming
         // kernels lose more than that to the carved-out L2 (505 -> 480 Msamples/s), so the window is opt-in: TGB_L2_PERSIST=1.
-        size_t nb = nodes.size()*sizeof(float4), tb = tri_isect.size()*sizeof(float4);
-        size_t nb_al = (nb + 255) & ~size_t(255);
+        size_t fb = nodes.size()*sizeof(float4), qbytes = qb.nodes.size()*sizeof(QNode4), tb = tri_isect.size()*sizeof(float4);
+        size_t fb_al = (fb + 255) & ~size_t(255), qb_al = (qbytes + 255) & ~size_t(255);
+        size_t nb = fb_al + qbytes, nb_al = fb_al + qb_al;
         char *slab = nullptr;
         if ((rc = dev_alloc(c, &slab, nb_al + std::max<size_t>(tb, 16)))) return rc;
-        if (nb) CU(cudaMemcpy(slab, nodes.data(), nb, cudaMemcpyHostToDevice));
+        if (fb) CU(cudaMemcpy(slab, nodes.data(), fb, cudaMemcpyHostToDevice));
+        if (qbytes) CU(cudaMemcpy(slab + fb_al, qb.nodes.data(), qbytes, cudaMemcpyHostToDevice));
         if (tb) CU(cudaMemcpy(slab + nb_al, tri_isect.data(), tb, cudaMemcpyHostToDevice));
-        sc.nodes = reinterpret_cast<const float4 *>(slab); sc.tri_isect = reinterpret_cast<const float4 *>(slab + nb_al);
+        sc.nodes = reinterpret_cast<const float4 *>(slab); sc.qnodes = reinterpret_cast<const uint4 *>(slab + fb_al);
+        sc.tri_isect = reinterpret_cast<const float4 *>(slab + nb_al);
+        sc.n_treelet = qb.n_treelet; sc.treelet_img = nullptr;
+        if (qb.n_treelet) {
+            QNode4 *img = nullptr;
+            if ((rc = dev_alloc(c, &img, qb.treelet_image.size()))) return rc;
+            CU(cudaMemcpy(img, qb.treelet_image.data(), qb.treelet_image.size()*sizeof(QNode4), cudaMemcpyHostToDevice));
+            sc.treelet_img = reinterpret_cast<const uint4 *>(img);
+        }
         const char *env = getenv("TGB_L2_PERSIST");
         if (nb + tb > 0 && env && env[0] == '1') {
             cudaDeviceProp prop; CU(cudaGetDeviceProperties(&prop, c->device));
@@ -617,38 +646,25 @@ int upload_scene(tgb_ctx *c, const tgb_scene_desc *d) {
 
 int alloc_wavefront(tgb_ctx *c, uint32_t capacity) {
     c->capacity = capacity;
-    float **fp = reinterpret_cast<float **>(&c->st);
-    // PathState is a struct of pointers; allocate one slab per array in declaration order
     int rc;
-#define ALLOCF(name) if ((rc = dev_alloc(c, &c->st.name, capacity))) return rc;
-    ALLOCF(ox) ALLOCF(oy) ALLOCF(oz) ALLOCF(dx) ALLOCF(dy) ALLOCF(dz) ALLOCF(tmin)
-    ALLOCF(tx) ALLOCF(ty) ALLOCF(tz) ALLOCF(ex) ALLOCF(ey) ALLOCF(ez)
-    ALLOCF(pcg) ALLOCF(info) ALLOCF(ra) ALLOCF(rb) ALLOCF(h4)
-    ALLOCF(px) ALLOCF(py) ALLOCF(pz)
-    ALLOCF(lx) ALLOCF(ly) ALLOCF(lz) ALLOCF(bx) ALLOCF(by) ALLOCF(bz) ALLOCF(wl) ALLOCF(sx) ALLOCF(sy) ALLOCF(sz) ALLOCF(ux) ALLOCF(uy) ALLOCF(uz)
-    ALLOCF(ndx) ALLOCF(ndy) ALLOCF(ndz) ALLOCF(ndist) ALLOCF(nfx) ALLOCF(nfy) ALLOCF(nfz) ALLOCF(npl) ALLOCF(npb)
-    ALLOCF(mdx) ALLOCF(mdy) ALLOCF(mdz) ALLOCF(mwx) ALLOCF(mwy) ALLOCF(mwz) ALLOCF(mpb) ALLOCF(qlight) ALLOCF(pid)
-    if (c->has_curves) { ALLOCF(eps) }
-#undef ALLOCF
-    c->st2 = c->st;
-#define ALLOC2(name) if ((rc = dev_alloc(c, &c->st2.name, capacity))) return rc;
-    ALLOC2(ox) ALLOC2(oy) ALLOC2(oz) ALLOC2(dx) ALLOC2(dy) ALLOC2(dz) ALLOC2(tmin) ALLOC2(tx) ALLOC2(ty) ALLOC2(tz)
-    ALLOC2(ex) ALLOC2(ey) ALLOC2(ez) ALLOC2(pcg) ALLOC2(info) ALLOC2(ra) ALLOC2(rb) ALLOC2(h4) ALLOC2(pid)
-#undef ALLOC2
-    (void)fp;
-    if ((rc = dev_alloc(c, &c->queue_a, capacity))) return rc;
-    if ((rc = dev_alloc(c, &c->bin_keys, capacity))) return rc;
-    if ((rc = dev_alloc(c, &c->bin_hist, size_t(kBins) + 2))) return rc;     // + cull bin + number of sorted survivors
+    for (int k = 0; k < 2; ++k) {
+        if ((rc = dev_alloc(c, &c->pb[k].T, size_t(capacity)*4))) return rc;
+        if ((rc = dev_alloc(c, &c->pb[k].E, capacity))) return rc;
+        if ((rc = dev_alloc(c, &c->pb[k].pcg, capacity))) return rc;
+    }
+    for (float4 **p : {&c->sr.P, &c->sr.N0, &c->sr.N1, &c->sr.M0, &c->sr.M1, &c->sr.D0, &c->sr.D1})
+        if ((rc = dev_alloc(c, p, capacity))) return rc;
+    if ((rc = dev_alloc(c, &c->sr.vis, size_t(capacity)*2))) return rc;
+    if ((rc = dev_alloc(c, &c->sr.SH, size_t(capacity)*2))) return rc;
     if ((rc = dev_alloc(c, &c->squeue, size_t(capacity)*2))) return rc;
-    if ((rc = dev_alloc(c, &c->squeue2, size_t(capacity)*2))) return rc;
-    if ((rc = dev_alloc(c, &c->ss.qt, size_t(capacity)*2))) return rc;
-    if ((rc = dev_alloc(c, &c->ss.qu, size_t(capacity)*2))) return rc;
-    if ((rc = dev_alloc(c, &c->ss.qv, size_t(capacity)*2))) return rc;
-    if ((rc = dev_alloc(c, &c->ss.qid, size_t(capacity)*2))) return rc;
-    if ((rc = dev_alloc(c, &c->counts, 6))) return rc;          // [4], [5]: ray cursors of the persistent traversal kernels
+    if ((rc = dev_alloc(c, &c->order, capacity))) return rc;
+    if ((rc = dev_alloc(c, &c->bin_keys, capacity))) return rc;
+    if ((rc = dev_alloc(c, &c->bin_hist, size_t(kBins) + 4))) return rc;
+    if ((rc = dev_alloc(c, &c->ctl, 1))) return rc;
     if ((rc = dev_alloc(c, &c->ctr, 1))) return rc;
     CU(cudaMemset(c->ctr, 0, sizeof(Counters)));
-    CU(cudaMallocHost(reinterpret_cast<void **>(&c->h_counts), 4*sizeof(uint32_t)));
+    CU(cudaMemset(c->ctl, 0, sizeof(Ctl)));
+    CU(cudaMallocHost(reinterpret_cast<void **>(&c->h_ctl), 5*sizeof(Ctl)));
     CU(cudaMallocHost(reinterpret_cast<void **>(&c->h_ctr), sizeof(Counters)));
     size_t npx = size_t(c->res_x)*c->res_y;
     if ((rc = dev_alloc(c, &c->fb, npx*3))) return rc;
@@ -683,6 +699,10 @@ int set_tiles(tgb_ctx *c, const tgb_tile *tiles, uint32_t n_tiles, uint32_t seed
         if (tl.x >= c->res_x || tl.w > c->res_x - tl.x || tl.y >= c->res_y || tl.h > c->res_y - tl.y) return fail(c, TGB_ERR_INVALID, "tile %u lies outside the image", t);
         for (uint32_t y = 0; y < tl.h; ++y) for (uint32_t x = 0; x < tl.w; ++x) { pid.push_back((tl.x + x) + (tl.y + y)*c->res_x); pseed.push_back(tl.sampler_seed); }
     }
+    {   // tiles must be disjoint: k_resolve owns one pixel per thread
+        std::vector<bool> seen(size_t(c->res_x)*c->res_y, false);
+        for (uint32_t q : pid) { if (seen[q]) return fail(c, TGB_ERR_INVALID, "tile list covers pixel %u twice", q); seen[q] = true; }
+    }
     if (pid.size() > c->pix_capacity) {
         int rc;
         if ((rc = dev_alloc(c, &c->pix_id, pid.size()))) return rc;
@@ -707,99 +727,100 @@ inline unsigned blocks(uint32_t n, unsigned bs) { return n ? (n + bs - 1)/bs : 1
 // iteration traces a full batch until the step's paths run out (one drain tail per step instead of one per batch).
 int ensure_results(tgb_ctx *c, size_t n_paths) {
     if (n_paths <= c->res_capacity) return TGB_OK;
-    for (float **p : {&c->st.rx, &c->st.ry, &c->st.rz}) { if (*p) cudaFree(*p); *p = nullptr; }
-    c->res_capacity = 0;
-    for (float **p : {&c->st.rx, &c->st.ry, &c->st.rz}) CU(cudaMalloc(reinterpret_cast<void **>(p), n_paths*sizeof(float)));
+    if (c->sr.R) cudaFree(c->sr.R);
+    c->sr.R = nullptr; c->res_capacity = 0;
+    CU(cudaMalloc(reinterpret_cast<void **>(&c->sr.R), n_paths*sizeof(float4)));
     c->res_capacity = n_paths;
     return TGB_OK;
 }
 
+// One iteration's kernels.  `bound` >= the iteration's ctl.n: grids are upper bounds, the kernels read the real sizes from
+// the device-resident control block.
+void enqueue_iteration(tgb_ctx *c, const BatchInfo &bi, int cur, uint32_t bound, int slot, uint64_t &launches) {
+    const DScene &sc = c->sc;
+    const bool has_bvh = sc.n_nodes != 0, curves = c->has_curves;
+    PathBuf &pb = c->pb[cur], &nxt = c->pb[cur ^ 1];
+    cudaStream_t st = c->stream;
+    k_regen<<<blocks(bound, 256), 256, 0, st>>>(sc, pb, bi, c->ctl, c->order, c->bin_hist); launches++;
+    if (c->profiling) cudaEventRecord(c->ev_t0[slot], st);
+    if (has_bvh) {
+        uint32_t grid = std::min(blocks(bound, kTraceBlock), c->persist_blocks);
+        if (curves) k_trace<true><<<grid, kTraceBlock, c->trace_smem, st>>>(sc, pb, c->order, c->ctl);
+        else k_trace<false><<<grid, kTraceBlock, c->trace_smem, st>>>(sc, pb, c->order, c->ctl);
+        launches++;
+    }
+    if (c->profiling) cudaEventRecord(c->ev_t1[slot], st);
+    if (c->sort_materials) {
+        if (curves) k_shade<true, true><<<blocks(bound, kShadeSortBlock), kShadeSortBlock, 0, st>>>(sc, pb, c->sr, bi, c->ctl, c->squeue, c->ctr);
+        else k_shade<false, true><<<blocks(bound, kShadeSortBlock), kShadeSortBlock, 0, st>>>(sc, pb, c->sr, bi, c->ctl, c->squeue, c->ctr);
+    } else {
+        if (curves) k_shade<true, false><<<blocks(bound, 128), 128, 0, st>>>(sc, pb, c->sr, bi, c->ctl, c->squeue, c->ctr);
+        else k_shade<false, false><<<blocks(bound, 128), 128, 0, st>>>(sc, pb, c->sr, bi, c->ctl, c->squeue, c->ctr);
+    }
+    launches++;
+    if (c->profiling) cudaEventRecord(c->ev_s0[slot], st);
+    if (has_bvh) {
+        uint32_t grid = std::min(blocks(2*bound, kTraceBlock), c->persist_blocks);
+        if (curves) k_shadow_bvh<true><<<grid, kTraceBlock, c->trace_smem, st>>>(sc, c->sr, c->squeue, c->ctl, c->ctr);
+        else k_shadow_bvh<false><<<grid, kTraceBlock, c->trace_smem, st>>>(sc, c->sr, c->squeue, c->ctl, c->ctr);
+        launches++;
+    }
+    if (c->profiling) cudaEventRecord(c->ev_s1[slot], st);
+    k_accum<<<blocks(bound, 256), 256, 0, st>>>(sc, pb, nxt, c->sr, c->ctl, c->bin_keys, c->bin_hist); launches++;
+    k_iter_end<<<1, 1024, 0, st>>>(c->bin_hist, c->ctl, has_bvh ? 1 : 0); launches++;
+    if (has_bvh) { k_bin_scatter<<<blocks(bound, 256), 256, 0, st>>>(c->bin_keys, c->bin_hist, c->ctl, c->order); launches++; }
+}
+
 int render_device(tgb_ctx *c, uint32_t spp_begin, uint32_t spp_count) {
     if (c->n_pix == 0 || spp_count == 0) return TGB_OK;
-    const DScene &sc = c->sc;
     CU(cudaEventRecord(c->ev0, c->stream));
     uint64_t launches = 0;
     float trace_ms = 0.0f, shadow_ms = 0.0f; uint64_t trace_launches = 0, traversed = 0, shadow_traversed = 0;
-    const bool has_bvh = sc.n_nodes != 0, curves = c->has_curves, persist = c->persist_blocks != 0;
-    // a step's finished radiances are kept per path (12 B each) until k_resolve folds them in sample order;
-    // split the sample range so that this buffer stays below ~6 GB and path ids fit 32 bits
-    const uint64_t max_paths = std::min<uint64_t>(512ull << 20, 0xFFFFFFFFull);
+    // a step's finished radiances are kept per path (16 B each) until k_resolve folds them in sample order;
+    // split the sample range so that this buffer stays below 8 GB and path ids fit 32 bits
+    const uint64_t max_paths = 512ull << 20;
     uint32_t spp_sub = uint32_t(std::max<uint64_t>(1, std::min<uint64_t>(spp_count, max_paths/c->n_pix)));
     if (uint64_t(c->n_pix)*spp_sub > 0xFFFFFFFFull) return fail(c, TGB_ERR_UNSUPPORTED, "tile list too large");
+    const bool trace_bounces = getenv("TGB_TRACE_BOUNCES") != nullptr;
     for (uint32_t s0 = 0; s0 < spp_count; s0 += spp_sub) {
         uint32_t ns = std::min(spp_sub, spp_count - s0);
-        uint32_t total = c->n_pix*ns, issued = 0;
+        uint32_t total = c->n_pix*ns;
         int rc = ensure_results(c, total);
         if (rc) return rc;
         BatchInfo bi; bi.pix_id = c->pix_id; bi.pix_seed = c->pix_seed; bi.n_pix = c->n_pix; bi.spp_begin = spp_begin + s0;
-        PathState cur = c->st, nxt = c->st2;
-        cur.rx = nxt.rx = c->st.rx; cur.ry = nxt.ry = c->st.ry; cur.rz = nxt.rz = c->st.rz;
-        uint32_t *cs = c->counts + 2;                 // counts: [0] survivors, [2] shadow queries, [3] compacted shadow queries
-        uint32_t n_alive = 0, n_sorted = 0;
-        CU(cudaMemsetAsync(c->bin_hist + kBins + 1, 0, sizeof(uint32_t), c->stream));
+        // control block of the first iteration; from then on k_iter_end keeps it
+        Ctl &init = c->h_ctl[4];
+        std::memset(&init, 0, sizeof(Ctl));
+        init.capacity = c->capacity; init.total = total;
+        init.n_new = std::min(c->capacity, total); init.n = init.n_new; init.issued = init.n_new;
+        CU(cudaMemcpyAsync(c->ctl, &init, sizeof(Ctl), cudaMemcpyHostToDevice, c->stream));
+        // The host runs one iteration ahead of the device: after enqueueing iteration i it waits for the snapshot taken after
+        // iteration i-1 (normally long complete), which bounds the grids of iteration i+1 and tells when the step has drained.
+        uint32_t bound = init.n;                              // upper bound of ctl.n for the iteration about to be queued
+        int cur = 0;
         for (uint32_t iter = 0;; ++iter) {
-            if (c->abort_flag.load()) { cudaStreamSynchronize(c->stream); return fail(c, TGB_ERR_ABORTED, "render aborted"); }
-            // refill: survivors occupy slots [0, n_alive) of `cur`; new camera paths are appended behind them
-            uint32_t m = std::min(c->capacity - n_alive, total - issued);
-            if (m) {
-                k_regen<<<blocks(m, 256), 256, 0, c->stream>>>(sc, cur, bi, n_alive, issued, m, c->queue_a); launches++;
-                issued += m;
-            }
-            uint32_t n = n_alive + m;
-            if (n == 0) break;
-            CU(cudaMemsetAsync(c->counts, 0, 6*sizeof(uint32_t), c->stream));
-            if (c->profiling) CU(cudaEventRecord(c->evt0, c->stream));
-            if (has_bvh) {
-                // persistent: a fixed grid pulls rays from counts[4]; else one thread per ray
-                uint32_t grid = persist ? std::min(blocks(n, kTraceBlock), c->persist_blocks) : blocks(n, kTraceBlock);
-                if (curves) { if (persist) k_trace<true, true><<<grid, kTraceBlock, kTraceSmem, c->stream>>>(sc, cur, c->queue_a, c->bin_hist + kBins + 1, n_alive, n, c->counts + 4);
-                              else k_trace<true, false><<<grid, kTraceBlock, kTraceSmem, c->stream>>>(sc, cur, c->queue_a, c->bin_hist + kBins + 1, n_alive, n, c->counts + 4); }
-                else { if (persist) k_trace<false, true><<<grid, kTraceBlock, kTraceSmem, c->stream>>>(sc, cur, c->queue_a, c->bin_hist + kBins + 1, n_alive, n, c->counts + 4);
-                       else k_trace<false, false><<<grid, kTraceBlock, kTraceSmem, c->stream>>>(sc, cur, c->queue_a, c->bin_hist + kBins + 1, n_alive, n, c->counts + 4); }
-                launches++;
-            }
-            if (c->profiling) CU(cudaEventRecord(c->evt1, c->stream));
-            if (c->sort_materials) {
-                if (curves) k_shade<true, true><<<blocks(n, kShadeSortBlock), kShadeSortBlock, 0, c->stream>>>(sc, cur, bi, n, c->squeue, cs, c->ctr);
-                else k_shade<false, true><<<blocks(n, kShadeSortBlock), kShadeSortBlock, 0, c->stream>>>(sc, cur, bi, n, c->squeue, cs, c->ctr);
-            } else {
-                if (curves) k_shade<true, false><<<blocks(n, 128), 128, 0, c->stream>>>(sc, cur, bi, n, c->squeue, cs, c->ctr);
-                else k_shade<false, false><<<blocks(n, 128), 128, 0, c->stream>>>(sc, cur, bi, n, c->squeue, cs, c->ctr);
-            }
-            launches++;
-            if (c->profiling) CU(cudaEventRecord(c->evs0, c->stream));
-            if (curves) k_shadow_prep<true><<<blocks(2*n, 256), 256, 0, c->stream>>>(sc, cur, c->ss, c->squeue, cs, c->squeue2, cs + 1, c->ctr);
-            else k_shadow_prep<false><<<blocks(2*n, 256), 256, 0, c->stream>>>(sc, cur, c->ss, c->squeue, cs, c->squeue2, cs + 1, c->ctr);
-            launches++;
-            if (has_bvh) {
-                uint32_t grid = persist ? std::min(blocks(2*n, kTraceBlock), c->persist_blocks) : blocks(2*n, kTraceBlock);
-                if (curves) { if (persist) k_shadow_bvh<true, true><<<grid, kTraceBlock, kTraceSmem, c->stream>>>(sc, cur, c->ss, c->squeue2, cs + 1, c->ctr, c->counts + 5);
-                              else k_shadow_bvh<true, false><<<grid, kTraceBlock, kTraceSmem, c->stream>>>(sc, cur, c->ss, c->squeue2, cs + 1, c->ctr, c->counts + 5); }
-                else { if (persist) k_shadow_bvh<false, true><<<grid, kTraceBlock, kTraceSmem, c->stream>>>(sc, cur, c->ss, c->squeue2, cs + 1, c->ctr, c->counts + 5);
-                       else k_shadow_bvh<false, false><<<grid, kTraceBlock, kTraceSmem, c->stream>>>(sc, cur, c->ss, c->squeue2, cs + 1, c->ctr, c->counts + 5); }
-                launches++;
-            }
-            if (c->profiling) CU(cudaEventRecord(c->evs1, c->stream));
-            CU(cudaMemsetAsync(c->bin_hist, 0, (kBins + 1)*sizeof(uint32_t), c->stream));
-            k_accum<<<blocks(n, 256), 256, 0, c->stream>>>(sc, cur, nxt, n, c->counts, c->bin_keys, c->bin_hist); launches++;
-            if (has_bvh) {          // visiting order of the next k_trace: survivors sorted by ray-coherence key
-                k_bin_scan<<<1, 1024, 0, c->stream>>>(c->bin_hist, c->bin_hist + kBins + 1, c->counts + 1); launches++;
-                k_bin_scatter<<<blocks(n, 256), 256, 0, c->stream>>>(c->bin_keys, c->bin_hist, c->counts, c->queue_a); launches++;
-            }
-            CU(cudaMemcpyAsync(c->h_counts, c->counts, 4*sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
-            CU(cudaStreamSynchronize(c->stream));
+            if (c->abort_flag.load()) { cudaStreamSynchronize(c->stream); c->abort_flag.store(0); return fail(c, TGB_ERR_ABORTED, "render aborted"); }
+            const int slot = int(iter & 3u);
+            enqueue_iteration(c, bi, cur, bound, slot, launches);
+            cur ^= 1;
+            CU(cudaMemcpyAsync(&c->h_ctl[slot], c->ctl, sizeof(Ctl), cudaMemcpyDeviceToHost, c->stream));
+            CU(cudaEventRecord(c->ev_ring[slot], c->stream));
+            if (iter == 0) { bound = std::min(c->capacity, total); continue; }      // nothing known yet about iteration 1
+            const int p = int((iter - 1) & 3u);
+            CU(cudaEventSynchronize(c->ev_ring[p]));
+            const Ctl S = c->h_ctl[p];                        // state after iteration iter-1 = the sizes of iteration iter
             if (c->profiling) {
-                float ms = 0.0f; cudaEventElapsedTime(&ms, c->evt0, c->evt1); trace_ms += ms; trace_launches++;
-                cudaEventElapsedTime(&ms, c->evs0, c->evs1); shadow_ms += ms;
+                float ms = 0.0f;
+                cudaEventElapsedTime(&ms, c->ev_t0[p], c->ev_t1[p]); trace_ms += ms; trace_launches++;
+                cudaEventElapsedTime(&ms, c->ev_s0[p], c->ev_s1[p]); shadow_ms += ms;
             }
-            if (getenv("TGB_TRACE_BOUNCES")) { uint32_t ns = 0; cudaMemcpy(&ns, c->bin_hist + kBins + 1, 4, cudaMemcpyDeviceToHost); fprintf(stderr, "iter %u n %u (new %u) shadow %u/%u -> alive %u (to traverse %u)\n", iter, n, m, c->h_counts[3], c->h_counts[2], c->h_counts[0], ns); }
-            if (has_bvh) { traversed += n_sorted + m; shadow_traversed += c->h_counts[3]; }
-            n_alive = c->h_counts[0]; n_sorted = c->h_counts[1];
-            std::swap(cur, nxt);
-            if (iter > (1u << 24)) return fail(c, TGB_ERR_CUDA, "wavefront loop did not terminate");
+            if (trace_bounces) fprintf(stderr, "after iter %u: next n %u (survivors %u, new %u, to traverse %u) issued %u/%u\n", iter - 1, S.n, S.n_surv, S.n_new, S.n_sorted, S.issued, S.total);
+            if (S.n == 0) { traversed += S.traversed; shadow_traversed += S.shadow_traversed; break; }   // iteration `iter`, already queued, is empty
+            // n(iter+1) <= n(iter) + the camera paths not yet issued after iteration iter's refill
+            bound = uint32_t(std::min<uint64_t>(c->capacity, uint64_t(S.n) + (S.total - S.issued)));
+            if (iter > (1u << 24)) return fail(c, TGB_ERR_INVALID, "wavefront loop did not terminate");
         }
-        c->st.rx = cur.rx;
-        k_resolve<<<blocks(c->n_pix, 256), 256, 0, c->stream>>>(c->st, bi, ns, c->fb, c->fb_count); launches++;
+        k_resolve<<<blocks(c->n_pix, 256), 256, 0, c->stream>>>(c->sr.R, bi, ns, c->fb, c->fb_count); launches++;
     }
     CU(cudaEventRecord(c->ev1, c->stream));
     CU(cudaMemcpyAsync(c->h_ctr, c->ctr, sizeof(Counters), cudaMemcpyDeviceToHost, c->stream));
@@ -830,12 +851,13 @@ void tgb200_destroy(tgb_ctx *c) {
     if (c->stream) cudaStreamSynchronize(c->stream);
     if (c->l2_window_bytes) cudaCtxResetPersistingL2Cache();
     for (void *p : c->allocs) cudaFree(p);
-    for (float *p : {c->st.rx, c->st.ry, c->st.rz}) if (p) cudaFree(p);
-    if (c->h_counts) cudaFreeHost(c->h_counts);
+    if (c->sr.R) cudaFree(c->sr.R);
+    if (c->h_ctl) cudaFreeHost(c->h_ctl);
     if (c->h_ctr) cudaFreeHost(c->h_ctr);
     if (c->h_fb) cudaFreeHost(c->h_fb);
     if (c->h_fb_count) cudaFreeHost(c->h_fb_count);
-    for (cudaEvent_t e : {c->ev0, c->ev1, c->evt0, c->evt1, c->evs0, c->evs1}) if (e) cudaEventDestroy(e);
+    for (cudaEvent_t e : {c->ev0, c->ev1}) if (e) cudaEventDestroy(e);
+    for (int k = 0; k < 4; ++k) for (cudaEvent_t e : {c->ev_ring[k], c->ev_t0[k], c->ev_t1[k], c->ev_s0[k], c->ev_s1[k]}) if (e) cudaEventDestroy(e);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -863,27 +885,30 @@ int tgb200_create(const tgb_scene_desc *d, tgb_ctx **out) {
     do {
         if (cudaSetDevice(dev) != cudaSuccess) { rc = fail(c, TGB_ERR_CUDA, "cudaSetDevice(%d) failed", dev); break; }
         if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { rc = fail(c, TGB_ERR_CUDA, "cudaStreamCreate failed"); break; }
-        for (cudaEvent_t *e : {&c->ev0, &c->ev1, &c->evt0, &c->evt1, &c->evs0, &c->evs1}) cudaEventCreate(e);
+        for (cudaEvent_t *e : {&c->ev0, &c->ev1}) cudaEventCreate(e);
+        for (int k = 0; k < 4; ++k) {
+            cudaEventCreateWithFlags(&c->ev_ring[k], cudaEventDisableTiming);
+            for (cudaEvent_t *e : {&c->ev_t0[k], &c->ev_t1[k], &c->ev_s0[k], &c->ev_s1[k]}) cudaEventCreate(e);
+        }
         if ((rc = upload_scene(c, d))) break;
         uint32_t cap = d->settings.max_paths_in_flight ? d->settings.max_paths_in_flight : (1u << 22);
         cap = std::max(cap, 1024u);
         if ((rc = alloc_wavefront(c, cap))) break;
         {   // persistent traversal grid = twice what is resident at once (blocks per SM x SMs, smaller of the two kernels): the
-            // second wave evens out the end of a launch (C1: x1 575, x2 580 Msamples/s)
-            const char *env = getenv("TGB_PERSIST");
-            if (!(env && env[0] == '0')) {
-                int sms = 0, b1 = 0, b2 = 0;
-                cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-                if (c->has_curves) {
-                    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b1, k_trace<true, true>, kTraceBlock, kTraceSmem);
-                    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b2, k_shadow_bvh<true, true>, kTraceBlock, kTraceSmem);
-                } else {
-                    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b1, k_trace<false, true>, kTraceBlock, kTraceSmem);
-                    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b2, k_shadow_bvh<false, true>, kTraceBlock, kTraceSmem);
-                }
-                const char *mult = getenv("TGB_PERSIST_MULT");
-                if (cudaGetLastError() == cudaSuccess && sms > 0 && b1 > 0 && b2 > 0) c->persist_blocks = uint32_t(sms*std::min(b1, b2))*uint32_t(mult ? std::max(1, atoi(mult)) : 2);
-            }
+            // second wave evens out the end of a launch (round 1, C1: x1 575, x2 580 Msamples/s)
+            c->trace_smem = trace_smem_bytes(c->sc.n_treelet);
+            int sms = 0, b1 = 0, b2 = 0;
+            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+            cudaError_t e = cudaSuccess;
+            auto prep = [&](auto kern, int *nb) {
+                if (e == cudaSuccess) e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(c->trace_smem));
+                if (e == cudaSuccess && nb) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(nb, kern, kTraceBlock, c->trace_smem);
+            };
+            if (c->has_curves) { prep(k_trace<true>, &b1); prep(k_shadow_bvh<true>, &b2); prep(k_hook_persist<true>, nullptr); }
+            else { prep(k_trace<false>, &b1); prep(k_shadow_bvh<false>, &b2); prep(k_hook_persist<false>, nullptr); }
+            if (e != cudaSuccess || sms <= 0 || b1 <= 0 || b2 <= 0) { rc = fail(c, TGB_ERR_CUDA, "traversal kernels cannot be resident (%s; %zu B of shared memory per block)", cudaGetErrorString(e), c->trace_smem); break; }
+            const char *mult = getenv("TGB_PERSIST_MULT");
+            c->persist_blocks = uint32_t(sms*std::min(b1, b2))*uint32_t(mult ? std::max(1, atoi(mult)) : 2);
         }
     } while (0);
     if (rc) { g_create_error = c->error; tgb200_destroy(c); return rc; }
@@ -905,7 +930,6 @@ int tgb200_render_resident(tgb_ctx *c, const tgb_tile *tiles, uint32_t n_tiles, 
     if (!c) return TGB_ERR_INVALID;
     if (n_tiles && !tiles) return fail(c, TGB_ERR_INVALID, "null tile list");
     CU(cudaSetDevice(c->device));
-    c->abort_flag.store(0);
     int rc = set_tiles(c, tiles, n_tiles, seed);
     if (rc) return rc;
     return render_device(c, spp_begin, spp_count);
@@ -941,7 +965,6 @@ int tgb200_render_tiles(tgb_ctx *c, const tgb_tile *tiles, uint32_t n_tiles, uin
         std::memcpy(c->h_fb_count, base.data(), npx*sizeof(uint32_t));
         CU(cudaMemcpyAsync(c->fb_count, c->h_fb_count, npx*sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
     }
-    c->abort_flag.store(0);
     int rc = set_tiles(c, tiles, n_tiles, seed);
     if (rc) return rc;
     if ((rc = render_device(c, spp_begin, spp_count))) return rc;
@@ -969,8 +992,18 @@ int tgb200_trace_closest(tgb_ctx *c, const tgb_ray *rays, tgb_hit *hits, uint32_
         if ((e = cudaMemcpyAsync(dr, rays, size_t(n)*sizeof(tgb_ray), cudaMemcpyHostToDevice, c->stream)) != cudaSuccess) break;
         k_hook_analytic<<<blocks(n, 256), 256, 0, c->stream>>>(c->sc, dr, dx, n);
         if (c->sc.n_nodes) {
-            if (c->has_curves) k_hook_bvh<true><<<blocks(n, kTraceBlock), kTraceBlock, kTraceSmem, c->stream>>>(c->sc, dr, dx, n);
-            else k_hook_bvh<false><<<blocks(n, kTraceBlock), kTraceBlock, kTraceSmem, c->stream>>>(c->sc, dr, dx, n);
+            // the renderer's own persistent kernel body: treelet staged in shared memory, lane refill (TGB_HOOK_SIMPLE=1: one ray
+            // per thread, nodes from global memory only)
+            const char *simple = getenv("TGB_HOOK_SIMPLE");
+            if (simple && simple[0] == '1') {
+                if (c->has_curves) k_hook_bvh<true><<<blocks(n, kTraceBlock), kTraceBlock, kStackSmemBytes, c->stream>>>(c->sc, dr, dx, n);
+                else k_hook_bvh<false><<<blocks(n, kTraceBlock), kTraceBlock, kStackSmemBytes, c->stream>>>(c->sc, dr, dx, n);
+            } else {
+                if ((e = cudaMemsetAsync(&c->ctl->cursor_trace, 0, sizeof(uint32_t), c->stream)) != cudaSuccess) break;
+                uint32_t grid = std::min(blocks(n, kTraceBlock), c->persist_blocks);
+                if (c->has_curves) k_hook_persist<true><<<grid, kTraceBlock, c->trace_smem, c->stream>>>(c->sc, dr, dx, n, &c->ctl->cursor_trace);
+                else k_hook_persist<false><<<grid, kTraceBlock, c->trace_smem, c->stream>>>(c->sc, dr, dx, n, &c->ctl->cursor_trace);
+            }
             c->stats.kernel_launches++;
         }
         k_hook_finish<<<blocks(n, 256), 256, 0, c->stream>>>(c->sc, dr, dx, dh, n);
@@ -1122,6 +1155,87 @@ int tgb200_bvh_selftest(const float *tri_verts, uint32_t n, uint32_t *n_nodes, u
     }
     for (uint32_t i = 0; i < n; ++i) if (seen[i] != 1) return TGB_ERR_INVALID;
     if (max_leaf) *max_leaf = worst_leaf;
+    return TGB_OK;
+}
+
+// Host-only check of the quantised device BVH (no GPU needed): builds the 4-ary SAH tree over n triangles exactly as
+// tgb200_create does (same padding), quantises it (QNode4 + treelet), and walks it on the HOST with the kernels' node
+// arithmetic (qnode_slab_host mirrors Traversal::visit) and their triangle test for every ray (8 floats: o, d, tmin, tmax).
+// The closest t must equal the brute-force closest t over all triangles bit for bit (ids may differ only on exact ties).
+// Returns the number of rays whose t differs in *mismatches; also verifies the swizzled treelet image and the link remap.
+int tgb200_qbvh_selftest(const float *tri_verts, uint32_t n, const float *rays, uint32_t n_rays, uint32_t max_treelet,
+                         uint32_t *mismatches, uint32_t *n_nodes, uint32_t *n_treelet, uint64_t *node_visits) {
+    if ((n && !tri_verts) || (n_rays && !rays) || !mismatches) return TGB_ERR_INVALID;
+    std::vector<BuildTri> tris(n);
+    float extent = 0.0f;
+    for (uint32_t i = 0; i < n; ++i) { std::memcpy(&tris[i], tri_verts + 9*size_t(i), sizeof(BuildTri)); for (int k = 0; k < 9; ++k) extent = std::max(extent, std::fabs(tri_verts[9*size_t(i) + k])); }
+    for (uint32_t r = 0; r < n_rays; ++r) for (int k = 0; k < 3; ++k) extent = std::max(extent, std::fabs(rays[8*size_t(r) + k]));
+    Bvh4 bvh; build_bvh4(tris.data(), n, bvh, 0, 1e-6f*extent, 4, 0.5f);
+    QBvh4 qb; quantize_bvh4(bvh, max_treelet, qb);
+    if (n_nodes) *n_nodes = uint32_t(qb.nodes.size());
+    if (n_treelet) *n_treelet = qb.n_treelet;
+    if (qb.nodes.size() != bvh.nodes.size() || qb.n_treelet > qb.nodes.size() || qb.treelet_image.size() != qb.n_treelet) return TGB_ERR_INVALID;
+    for (uint32_t i = 0; i < qb.n_treelet; ++i) {                       // un-swizzling the image gives the nodes back
+        const uint32_t *img = reinterpret_cast<const uint32_t *>(&qb.treelet_image[i]), *nd = reinterpret_cast<const uint32_t *>(&qb.nodes[i]);
+        for (uint32_t cch = 0; cch < 4; ++cch) if (std::memcmp(img + 4*(cch ^ ((i >> 1) & 3u)), nd + 4*cch, 16) != 0) return TGB_ERR_INVALID;
+    }
+    for (size_t i = 0; i < qb.nodes.size(); ++i) {                      // links: same leaves, children remapped consistently
+        const Node4 &src = bvh.nodes[size_t(qb.old_index[i])];
+        for (int k = 0; k < 4; ++k) {
+            int32_t l = qb.nodes[i].link[k];
+            if (src.link[k] < 0) { if (l != src.link[k]) return TGB_ERR_INVALID; }
+            else if (l < 0 || size_t(l) >= qb.nodes.size() || qb.old_index[size_t(l)] != src.link[k]) return TGB_ERR_INVALID;
+        }
+    }
+    auto tri_test = [&](uint32_t t, const V3 &o, const V3 &d, float tnear, float &best) {   // Traversal::run's triangle test
+        V3 v0 = f3(tris[t].v0), v1 = f3(tris[t].v1), v2 = f3(tris[t].v2);
+        V3 e1 = v0 - v1, e2 = v2 - v0, ng = cross(e1, e2);
+        V3 C = v0 - o, R = cross(d, C);
+        auto edot = [](V3 a, V3 b) { return a.x*b.x + (a.y*b.y + a.z*b.z); };
+        float den = edot(ng, d), absDen = std::fabs(den);
+        auto xs = [&](float a) { return den < 0.0f || (den == 0.0f && std::signbit(den)) ? -a : a; };
+        float U = xs(edot(R, e2)), V = xs(edot(R, e1));
+        if (!(den != 0.0f && U >= 0.0f && V >= 0.0f && U + V <= absDen)) return;
+        float T = xs(edot(ng, C));
+        if (!(T > absDen*tnear && T < absDen*best)) return;
+        best = T/absDen;
+    };
+    uint32_t bad = 0; uint64_t visits = 0;
+    std::vector<int32_t> stack;
+    for (uint32_t r = 0; r < n_rays; ++r) {
+        const float *ry = rays + 8*size_t(r);
+        V3 o = f3(ry), d = f3(ry + 3); float tnear = ry[6], tfar = ry[7];
+        float brute = tfar;
+        for (uint32_t t = 0; t < n; ++t) tri_test(t, o, d, tnear, brute);
+        float best = tfar;
+        if (!qb.nodes.empty()) {
+            const float ooeps = 1e-30f;
+            float inv[3] = {1.0f/(std::fabs(d.x) > ooeps ? d.x : std::copysign(ooeps, d.x)), 1.0f/(std::fabs(d.y) > ooeps ? d.y : std::copysign(ooeps, d.y)),
+                            1.0f/(std::fabs(d.z) > ooeps ? d.z : std::copysign(ooeps, d.z))};
+            float oo[3] = {o.x, o.y, o.z};
+            stack.clear(); stack.push_back(0);
+            while (!stack.empty()) {
+                int32_t cur = stack.back(); stack.pop_back();
+                if (cur >= 0) {
+                    float t4[4]; visits++;
+                    qnode_slab_host(qb.nodes[size_t(cur)], oo, inv, tnear, best, t4);
+                    for (int k = 0; k < 4; ++k) if (t4[k] != INFINITY) stack.push_back(qb.nodes[size_t(cur)].link[k]);
+                } else {
+                    int code = ~cur; uint32_t first = uint32_t(code >> 3), count = uint32_t(code & 3) + 1;
+                    for (uint32_t i = 0; i < count; ++i) tri_test(bvh.order[first + i], o, d, tnear, best);
+                }
+            }
+        }
+        if (std::memcmp(&best, &brute, 4) != 0) bad++;
+    }
+    *mismatches = bad;
+    if (node_visits) *node_visits = visits;
+    return TGB_OK;
+}
+
+int tgb200_clear_abort(tgb_ctx *c) {
+    if (!c) return TGB_ERR_INVALID;
+    c->abort_flag.store(0);
     return TGB_OK;
 }
 

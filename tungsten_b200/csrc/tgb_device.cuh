@@ -124,7 +124,10 @@ struct DScene {
     // triangles: intersection records in BVH leaf order (3 x float4 each), leaf order -> global id,
     // global id -> primitive, shading records by global id (4 x float4 each)
     const float4 *tri_isect; const uint32_t *tri_global; const uint32_t *tri_prim; const float4 *tri_shade;
-    const float4 *nodes; uint32_t n_nodes; uint32_t n_tris;
+    const float4 *nodes; uint32_t n_nodes; uint32_t n_tris;          // float Node4 array (128 B per node; only read by TGB_QNODES=0 builds)
+    // quantised nodes (QNode4, 64 B = 4 x uint4, bvh_build.h) in treelet-first order, and the swizzled image of the first
+    // n_treelet of them that the traversal kernels bulk-copy into shared memory
+    const uint4 *qnodes; const uint4 *treelet_img; uint32_t n_treelet;
     // curve segments share the arrays above: records n_tris.. of tri_isect hold a segment's three nodes (x, y, z, width),
     // tri_global / tri_prim continue with global ids n_tris + segment
     uint32_t n_curve_segs;          // BVH primitives for curves = kCurvePieces sub-ranges per segment

@@ -1,50 +1,71 @@
-// Wavefront kernels of the B200 path tracer (sm_100a).
+// Wavefront kernels of the B200 path tracer (sm_100a).  One iteration of the loop =
 //   k_regen        : SobolPathSampler::startPath + ReconstructionFilter::sample + PinholeCamera::sampleDirection for the camera
 //                    paths that replace finished ones (appended behind the compacted survivors)
-//   k_trace        : TraceableScene::intersect (closest hit): persistent warps pull rays from the coherence-sorted queue and
-//                    walk the 4-ary BVH over all mesh triangles (+ curve segments); analytic primitives were tested by the
-//                    kernel that created the ray
-//   k_shade        : makeLocalScatterEvent + handleSurface (NEE/MIS query generation, emission, BSDF sample, Russian roulette)
-//   k_shadow_prep  : analytic part of the NEE/MIS queries, top-level BVH cut, compaction of what is left
+//   k_trace        : TraceableScene::intersect (closest hit): persistent CTAs stage the top of the quantised BVH in shared
+//                    memory with one bulk-async copy (TMA engine, mbarrier), pull rays from the coherence-sorted queue and walk
+//                    the 4-ary BVH over all mesh triangles (+ curve segments); analytic primitives were tested by the kernel
+//                    that created the ray
+//   k_shade        : makeLocalScatterEvent + handleSurface (NEE/MIS query generation, emission, BSDF sample, Russian roulette),
+//                    then the analytic part of this bounce's NEE/MIS queries + top-level BVH cut + compaction of what is left
 //   k_shadow_bvh   : attenuatedEmission / generalizedShadowRay for those (same traversal + epilogue)
 //   k_accum        : folds the bounce's direct-light estimate into the path, NaN guards, compacts survivors into the other
 //                    state buffer, analytic test + BVH cut + coherence key of their next ray
-//   k_bin_scan/k_bin_scatter : counting sort of the survivors' slot indices by that key
+//   k_iter_end     : (one block) scan of the key histogram + the loop's bookkeeping: the sizes of the next iteration live in
+//                    a device-resident control block, the host only reads them one iteration late (no sync in the loop)
+//   k_bin_scatter  : counting sort of the survivors' slot indices by ray-coherence key
 //   k_resolve      : OutputBuffer::addSample running mean, samples folded in sample-index order
-// Path state lives in SoA arrays indexed by slot (survivors first, new camera paths behind them).
+// Path state is stored as 16-byte records (one LDG/STG.128 per record): a 64-byte traversal record per slot + 24 bytes of
+// emission / RNG state, double buffered (k_accum compacts from one buffer into the other); per-bounce scratch records for the
+// direct-light estimate.
 #pragma once
 #include "tgb_device.cuh"
 
 namespace tgb {
 
-// ---- path state (SoA, one entry per slot) ----------------------------------------------------
-struct PathState {
-    float *ox, *oy, *oz, *dx, *dy, *dz, *tmin;          // current ray (tmax is always +inf for path rays)
-    float *tx, *ty, *tz;                                // throughput
-    float *ex, *ey, *ez;                                // accumulated emission (the sample's radiance)
-    uint64_t *pcg;                                      // supplemental PCG state
-    uint32_t *info;                                     // dimension[0:16) | bounce[16:24) | flags[24:32)
-    float *px, *py, *pz;                                // shading point of this bounce (origin of NEE/MIS queries)
-    // direct-light estimate of this bounce, folded in by k_accum
-    float *lx, *ly, *lz, *bx, *by, *bz, *wl, *sx, *sy, *sz, *ux, *uy, *uz;   // L, B, light weight, surface emission term, throughput before
-    // NEE query payload: direction, expected distance, f, pdfL, pdfB ; MIS payload: direction, weight, pdfB
-    float *ndx, *ndy, *ndz, *ndist, *nfx, *nfy, *nfz, *npl, *npb;
-    float *mdx, *mdy, *mdz, *mwx, *mwy, *mwz, *mpb;
-    int *qlight;                                        // light primitive of this bounce's queries
-    float *eps;                                         // IntersectionInfo::epsilon of the shading point (scenes with curves only)
-    uint32_t *pid;                                      // path index within the step: sample_rel*n_pix + pixel_list_index
-    // packed copies for the traversal kernel, which visits the paths in ray-coherence order (gathers 32 B + 16 B per ray):
-    float4 *ra, *rb;                                    // (o.xyz, tmin), (d.xyz, 0)
-    float4 *h4;                                         // closest hit (t, u, v, id as bits): written by the analytic pass, updated by k_trace
-    float *rx, *ry, *rz;                                // finished radiance per path of the step, indexed by pid (not by slot)
+// ---- path state ----------------------------------------------------------------------------------
+// Persistent per slot (double buffered).  T = 4 consecutive float4 per slot (one 64-byte line: the traversal kernel reaches a
+// path through the sort index and touches exactly this line):
+//   T[4s+0] = (ray origin, tmin)                  T[4s+1] = (ray direction, info)   info = dimension[0:16) | bounce[16:24) | flags
+//   T[4s+2] = closest hit (t, u, v, id)           T[4s+3] = (throughput, path id)   path id = sample_rel*n_pix + pixel_list_index
+struct PathBuf {
+    float4 *T;
+    float4 *E;          // (emission accumulated so far = the sample's radiance, unused)
+    uint64_t *pcg;      // supplemental PCG state
 };
-constexpr int kPathFloatArrays = 7 + 3 + 3 + 3 + 3 + 13 + 9 + 7;   // float-sized arrays in PathState (excl. pcg/info/hid/qlight)
+// Per-bounce scratch (written by k_shade for the paths that issue NEE/MIS queries, read by k_shadow_bvh and k_accum):
+struct Scratch {
+    float4 *P;          // (shading point, IntersectionInfo::epsilon)
+    float4 *N0, *N1;    // NEE: (direction, distance | t of the light's own hit), (f | finished lightF, pdfL)
+    float4 *M0, *M1;    // MIS: (direction, pdfB | t of the light's own hit), (weight | finished bsdfF, NEE's pdfB)
+    float4 *D0, *D1;    // (throughput before the bounce, light-pick weight), (surface emission term, light primitive)
+    uint32_t *vis;      // vis[2s + mis] = 1 when that query's light term counts (nothing but the light in the way)
+    float4 *SH;         // per shadow-queue entry: the initial (analytic) hit of a closest-hit query
+    float4 *R;          // finished radiance per path of the step, indexed by path id (not by slot)
+};
 
 enum : uint32_t { F_WAS_SPECULAR = 1u << 24, F_ALIVE = 1u << 25, F_FINAL_CHECK = 1u << 26, F_HAS_NEE = 1u << 27,
                   F_HAS_SURF = 1u << 28 };
 constexpr int HID_MISS = -1;
 
 struct Counters { unsigned long long rays, hits, shadow_rays, shadow_hits; };   // path queries / NEE+MIS queries
+
+// Device-resident control block of the wavefront loop.  k_iter_end writes the sizes of the NEXT iteration; every kernel of
+// an iteration reads them from here, its grid is only an upper bound chosen by the host from a snapshot one iteration old.
+struct Ctl {
+    uint32_t n;             // slots in use this iteration: survivors [0, n_surv) + new camera paths [n_surv, n)
+    uint32_t n_surv;
+    uint32_t n_sorted;      // survivors the traversal visits (prefix of order[]); the others miss the BVH's top-level cut
+    uint32_t n_new;
+    uint32_t first_path;    // path id of the first new camera path
+    uint32_t issued;        // camera paths started so far, this iteration included
+    uint32_t total;         // camera paths of the (sub)step
+    uint32_t capacity;
+    uint32_t next_count;    // survivors appended by k_accum
+    uint32_t shadow_count;  // NEE/MIS queries queued for k_shadow_bvh
+    uint32_t cursor_trace, cursor_shadow;       // ray cursors of the persistent traversal kernels
+    unsigned long long traversed, shadow_traversed;   // statistics: queries that reached k_trace / k_shadow_bvh
+    uint32_t iterations, pad;
+};
 
 // ---- closest-hit traversal -------------------------------------------------------------------
 struct Hit { float t, u, v; int id; };
@@ -207,20 +228,31 @@ TGB_D bool curve_point_on_spline(float4 p0, float4 p1, float4 p2, float tMin, fl
         } while (minf(cur.p0.z - cur.p0.w, cur.p1.z - cur.p1.w) > closestDepth);
     }
 }
-
-// Traversal stack: the first kSmemStack entries of every lane live in shared memory, laid out [entry][thread] so
-// that lane i always hits bank i (conflict-free whatever the lanes' depths); deeper entries spill to local memory.
-constexpr int kSmemStack = 32;
-constexpr int kLocalStack = 48;
-constexpr int kStackSize = kSmemStack + kLocalStack;
-constexpr int kTraceBlock = 128;
-// resident blocks per SM the traversal kernels are compiled for: 6 x 128 threads caps them at 85 registers, which keeps the
-// persistent kernels' per-lane ray state in registers without losing occupancy (measured on C1: 5 -> 527, 6 -> 564, 7 -> 561,
-// 8 -> 557 Msamples/s)
+// ---- BVH traversal ------------------------------------------------------------------------------
+// Traversal stack: the first kSmemStack entries of every lane live in shared memory, laid out [entry][thread] so that lane i
+// always hits bank i (conflict-free whatever the lanes' depths); deeper entries spill to local memory.
+#ifndef TGB_TRACE_BLOCK
+#define TGB_TRACE_BLOCK 128
+#endif
+#ifndef TGB_SMEM_STACK
+#define TGB_SMEM_STACK 32
+#endif
+// resident blocks per SM the traversal kernels are compiled for: 6 x 128 threads caps them at 85 registers (round 1, C1: 5 ->
+// 527, 6 -> 564, 7 -> 561, 8 -> 557 Msamples/s)
 #ifndef TGB_MINB
 #define TGB_MINB 6
 #endif
-constexpr size_t kTraceSmem = size_t(kSmemStack)*kTraceBlock*sizeof(int);
+// node layout the traversal reads: 1 = QNode4 (64 B, 8-bit child boxes, 4 x LDG.128 per visit), 0 = float Node4 (128 B, 7 loads)
+#ifndef TGB_QNODES
+#define TGB_QNODES 1
+#endif
+constexpr int kTraceBlock = TGB_TRACE_BLOCK;
+constexpr int kSmemStack = TGB_SMEM_STACK;
+constexpr int kStackSize = 80;
+constexpr int kLocalStack = kStackSize - kSmemStack;
+constexpr size_t kStackSmemBytes = size_t(kSmemStack)*kTraceBlock*sizeof(int);
+// dynamic shared memory of a traversal kernel: [treelet image: n_treelet x 64 B][stack][mbarrier]
+TGB_HD size_t trace_smem_bytes(uint32_t n_treelet) { return size_t(n_treelet)*64 + kStackSmemBytes + 16; }
 
 struct TravStack {
     int *smem;                       // this thread's column of the shared stack
@@ -237,19 +269,54 @@ struct TravStack {
     }
 };
 
+// ---- bulk-async staging of the top treelet (cp.async.bulk + mbarrier: the TMA engine copies, no thread touches the data) ----
+TGB_D uint32_t smem_addr(const void *p) { return uint32_t(__cvta_generic_to_shared(p)); }
+TGB_D void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_addr(bar)), "r"(count) : "memory");
+}
+TGB_D void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+TGB_D void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_addr(bar)), "r"(bytes) : "memory");
+}
+TGB_D void bulk_copy_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(smem_addr(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_addr(bar)) : "memory");
+}
+TGB_D void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile("{\n\t.reg .pred p;\n\tWAIT_%=:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t@p bra DONE_%=;\n\tbra WAIT_%=;\n\tDONE_%=:\n\t}"
+                 :: "r"(smem_addr(bar)), "r"(parity) : "memory");
+}
+// Called by every thread of a traversal CTA before its first node visit; returns the treelet's shared-memory image.
+// Thread 0 arms the barrier with the byte count and issues the copies (<= 32 KB each); all threads wait on phase 0.
+TGB_D const uint4 *stage_treelet(const DScene &sc, unsigned char *smem_raw) {
+    const uint32_t bytes = sc.n_treelet*64u;
+    if (bytes == 0) return nullptr;
+    uint64_t *bar = reinterpret_cast<uint64_t *>(smem_raw + bytes + kStackSmemBytes);
+    if (threadIdx.x == 0) { mbar_init(bar, 1); fence_mbar_init(); }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        mbar_expect_tx(bar, bytes);
+        const unsigned char *src = reinterpret_cast<const unsigned char *>(sc.treelet_img);
+        for (uint32_t off = 0; off < bytes; off += 32768u) bulk_copy_g2s(smem_raw + off, src + off, min(32768u, bytes - off), bar);
+    }
+    mbar_wait(bar, 0);
+    return reinterpret_cast<const uint4 *>(smem_raw);
+}
+
 // BVH traversal over the mesh triangles: one ray per thread, per-lane while-while over the 4-ary BVH.
-// Node visit = one 128-byte node (7 x 16 B loads): four fused slab tests t = lo/d - o/d per axis (boxes are padded at
-// build time to cover the FMA rounding), the hit children are ordered near-to-far with a 5-exchange sorting network,
-// the nearest is entered and the others are pushed far-to-near.
+// Node visit (QNode4, bvh_build.h) = 4 x 16-byte loads -- from the shared-memory treelet for the top nodes, else global --,
+// per axis a = S/d, b = (origin - o)/d - a once per node, then per child plane ONE byte permute (1 + q*2^-15 assembled
+// straight into float bits) and ONE fma; the hit children are ordered near-to-far with a 5-exchange sorting network, the
+// nearest is entered and the others are pushed far-to-near (three predicated shared-memory stores).
 // Triangle test = Embree's MoellerTrumboreIntersector1 (thirdparty/embree/kernels/geometry/
 // triangle_intersector_moeller.h:75-111) with IEEE division for t,u,v.
 // `any`: occlusion query, stop at the first triangle hit.
-// Alternatives measured and rejected (profiles/r01_a_k_trace_baseline.md): warp-synchronous speculative traversal,
-// if-if state machines with and without several rays per lane, 32-byte quantised binary nodes, higher occupancy,
-// branch-free predicated pushes (-2.7 %).
-#define TGB_SLAB_T float tmn = fmaxf(fmaxf(fmaxf(ax, ay), az), tnear); float tmx = fminf(fminf(fminf(bx, by), bz), h.t);
+// Alternatives measured and rejected in round 1 (profiles/r01_a_k_trace_baseline.md): warp-synchronous speculative
+// traversal, if-if state machines with and without several rays per lane, 32-byte quantised BINARY nodes, higher occupancy.
 #define TGB_CSWAP(ta, la, tb, lb) { bool sw_ = tb < ta; float tt_ = sw_ ? tb : ta; tb = sw_ ? ta : tb; ta = tt_; \
                                     int ll_ = sw_ ? lb : la; lb = sw_ ? la : lb; la = ll_; }
+// 1 + q*2^-15 for byte K of word W: bytes (0x3F, 0x80, q, 0x00)
+#define TGB_QF(W, K) __uint_as_float(__byte_perm(W, 0x3F80u, 0x5406u | ((K) << 4)))
 // CURVES: leaves whose code has bit 2 set hold curve segments (three float4 nodes per record, stored after the triangles);
 // a curve hit keeps (t, position along the segment, interpolated width) in (t, u, v) and id >= n_tris.
 // The traversal is a resumable object: run() walks until the ray is finished (true) or until `yield()` asks for a pause
@@ -269,7 +336,7 @@ struct Traversal {
         idz = 1.0f/(fabsf(d.z) > ooeps ? d.z : copysignf(ooeps, d.z));
         oodx = o.x*idx; oody = o.y*idy; oodz = o.z*idz;
         // The entry plane of a slab is its lo plane when the direction component is positive, else its hi plane (fma is
-        // monotone, so this IS min(a, b) / max(a, b) of the two plane distances): pick the float4 to load per axis once per ray.
+        // monotone, so this IS min(a, b) / max(a, b) of the two plane distances): pick which to read per axis once per ray.
         nx = idx < 0.0f ? 1 : 0; ny = idy < 0.0f ? 3 : 2; nz = idz < 0.0f ? 5 : 4;
         fx = nx ^ 1; fy = ny ^ 1; fz = nz ^ 1;
         last_seg = -1;
@@ -277,33 +344,76 @@ struct Traversal {
         cur = 0;
     }
 
-    template <class Y>
-    TGB_D bool run(const DScene &sc, TravStack &stk, Y yield) {
-        const float4 *nodes = sc.nodes;
+    // one node visit: entry distances of the four children (INFINITY = culled) and their links
+    TGB_D void visit(const DScene &sc, const uint4 *treelet, float &t0, float &t1, float &t2, float &t3, int4 &lk) {
         const int EMPTY = int(0x80000000u);
+#if TGB_QNODES
+        uint4 c0, c1, c2;
+        if (uint32_t(cur) < sc.n_treelet && treelet) {
+            const uint4 *nd = treelet + 4*cur; const int sw = (cur >> 1) & 3;
+            c0 = nd[sw]; c1 = nd[1 ^ sw]; c2 = nd[2 ^ sw]; const uint4 l = nd[3 ^ sw];
+            lk = make_int4(int(l.x), int(l.y), int(l.z), int(l.w));
+        } else {
+            const uint4 *nd = sc.qnodes + 4*size_t(cur);
+            c0 = __ldg(nd); c1 = __ldg(nd + 1); c2 = __ldg(nd + 2); lk = __ldg(reinterpret_cast<const int4 *>(nd + 3));
+        }
+        const float ax_ = __uint_as_float(c0.w)*idx, ay_ = __uint_as_float(c1.x)*idy, az_ = __uint_as_float(c1.y)*idz;
+        const float bx_ = __fmaf_rn(__uint_as_float(c0.x), idx, -oodx) - ax_;
+        const float by_ = __fmaf_rn(__uint_as_float(c0.y), idy, -oody) - ay_;
+        const float bz_ = __fmaf_rn(__uint_as_float(c0.z), idz, -oodz) - az_;
+        const uint32_t nxw = nx ? c1.w : c1.z, fxw = nx ? c1.z : c1.w;
+        const uint32_t nyw = (ny & 1) ? c2.y : c2.x, fyw = (ny & 1) ? c2.x : c2.y;
+        const uint32_t nzw = (nz & 1) ? c2.w : c2.z, fzw = (nz & 1) ? c2.z : c2.w;
+#define TGB_SLAB(K, LK, OUT) { \
+            float ax = __fmaf_rn(TGB_QF(nxw, K), ax_, bx_), bx = __fmaf_rn(TGB_QF(fxw, K), ax_, bx_); \
+            float ay = __fmaf_rn(TGB_QF(nyw, K), ay_, by_), by = __fmaf_rn(TGB_QF(fyw, K), ay_, by_); \
+            float az = __fmaf_rn(TGB_QF(nzw, K), az_, bz_), bz = __fmaf_rn(TGB_QF(fzw, K), az_, bz_); \
+            float tmn = fmaxf(fmaxf(fmaxf(ax, ay), az), tnear); float tmx = fminf(fminf(fminf(bx, by), bz), h.t); \
+            OUT = (tmn <= tmx && LK != EMPTY) ? tmn : INFINITY; }
+        TGB_SLAB(0, lk.x, t0) TGB_SLAB(1, lk.y, t1) TGB_SLAB(2, lk.z, t2) TGB_SLAB(3, lk.w, t3)
+#undef TGB_SLAB
+#else
+        const float4 *nd = sc.nodes + 8*size_t(cur);
+        const float4 nrx = __ldg(nd + nx), frx = __ldg(nd + fx), nry = __ldg(nd + ny), fry = __ldg(nd + fy), nrz = __ldg(nd + nz), frz = __ldg(nd + fz);
+        lk = __ldg(reinterpret_cast<const int4 *>(nd + 6));
+#define TGB_SLAB(K, OUT) { \
+            float ax = __fmaf_rn(nrx.K, idx, -oodx), bx = __fmaf_rn(frx.K, idx, -oodx); \
+            float ay = __fmaf_rn(nry.K, idy, -oody), by = __fmaf_rn(fry.K, idy, -oody); \
+            float az = __fmaf_rn(nrz.K, idz, -oodz), bz = __fmaf_rn(frz.K, idz, -oodz); \
+            float tmn = fmaxf(fmaxf(fmaxf(ax, ay), az), tnear); float tmx = fminf(fminf(fminf(bx, by), bz), h.t); \
+            OUT = (tmn <= tmx && lk.K != EMPTY) ? tmn : INFINITY; }
+        TGB_SLAB(x, t0) TGB_SLAB(y, t1) TGB_SLAB(z, t2) TGB_SLAB(w, t3)
+#undef TGB_SLAB
+        (void)treelet;
+#endif
+    }
+
+    template <class Y>
+    TGB_D bool run(const DScene &sc, const uint4 *treelet, TravStack &stk, Y yield) {
         while (true) {
         while (cur >= 0) {
-            const float4 *nd = nodes + 8*size_t(cur);
-            const float4 nrx = __ldg(nd + nx), frx = __ldg(nd + fx), nry = __ldg(nd + ny), fry = __ldg(nd + fy), nrz = __ldg(nd + nz), frz = __ldg(nd + fz);
-            const int4 lk = __ldg(reinterpret_cast<const int4 *>(nd + 6));
-            float t0, t1, t2, t3;
-#define TGB_SLAB(K, OUT) { \
-                float ax = __fmaf_rn(nrx.K, idx, -oodx), bx = __fmaf_rn(frx.K, idx, -oodx); \
-                float ay = __fmaf_rn(nry.K, idy, -oody), by = __fmaf_rn(fry.K, idy, -oody); \
-                float az = __fmaf_rn(nrz.K, idz, -oodz), bz = __fmaf_rn(frz.K, idz, -oodz); \
-                TGB_SLAB_T \
-                OUT = (tmn <= tmx && lk.K != EMPTY) ? tmn : INFINITY; }
-            TGB_SLAB(x, t0) TGB_SLAB(y, t1) TGB_SLAB(z, t2) TGB_SLAB(w, t3)
-#undef TGB_SLAB
+            float t0, t1, t2, t3; int4 lk;
+            visit(sc, treelet, t0, t1, t2, t3, lk);
             int l0 = lk.x, l1 = lk.y, l2 = lk.z, l3 = lk.w;
             TGB_CSWAP(t0, l0, t1, l1) TGB_CSWAP(t2, l2, t3, l3) TGB_CSWAP(t0, l0, t2, l2) TGB_CSWAP(t1, l1, t3, l3) TGB_CSWAP(t1, l1, t2, l2)
             if (t0 == INFINITY) {
                 if (stk.sp == 0) return true;
                 cur = stk.pop();
             } else {
-                if (t3 != INFINITY) stk.push(l3);
-                if (t2 != INFINITY) stk.push(l2);
-                if (t1 != INFINITY) stk.push(l1);
+                // sorted, so the children to push are a prefix of (l1, l2, l3); the nearest of them must end up on top
+                const bool p1 = t1 != INFINITY, p2 = t2 != INFINITY, p3 = t3 != INFINITY;
+                const int c = int(p1) + int(p2) + int(p3);
+                if (stk.sp + 3 <= kSmemStack) {
+                    int *p = stk.smem + stk.sp*kTraceBlock;
+                    if (p3) p[0] = l3;                               // p3 implies c == 3
+                    if (p2) p[(c - 2)*kTraceBlock] = l2;
+                    if (p1) p[(c - 1)*kTraceBlock] = l1;
+                    stk.sp += c;
+                } else {
+                    if (p3) stk.push(l3);
+                    if (p2) stk.push(l2);
+                    if (p1) stk.push(l1);
+                }
                 cur = l0;
             }
         }
@@ -348,10 +458,10 @@ struct Traversal {
 };
 
 template <bool CURVES>
-TGB_D void bvh_traverse(const DScene &sc, int *smem_stack, V3 o, V3 d, float tnear, bool any, Hit &h) {
+TGB_D void bvh_traverse(const DScene &sc, const uint4 *treelet, int *smem_stack, V3 o, V3 d, float tnear, bool any, Hit &h) {
     Traversal<CURVES> tr; TravStack stk; stk.smem = smem_stack + threadIdx.x; stk.sp = 0;
     tr.begin(o, d, tnear, any, h);
-    tr.run(sc, stk, [] { return false; });
+    tr.run(sc, treelet, stk, [] { return false; });
     h = tr.h;
 }
 
@@ -363,7 +473,7 @@ TGB_D void bvh_traverse(const DScene &sc, int *smem_stack, V3 o, V3 d, float tne
 #define TGB_REFILL_BELOW 20
 #endif
 template <bool CURVES, class P>
-TGB_D void bvh_traverse_persistent(const DScene &sc, int *smem_stack, P &pol, uint32_t n, uint32_t *counter) {
+TGB_D void bvh_traverse_persistent(const DScene &sc, const uint4 *treelet, int *smem_stack, P &pol, uint32_t n, uint32_t *counter) {
     const unsigned FULL = 0xffffffffu, lane = threadIdx.x & 31u;
     Traversal<CURVES> tr; TravStack stk; stk.smem = smem_stack + threadIdx.x; stk.sp = 0;
     bool active = false, exhausted = false;
@@ -384,14 +494,15 @@ TGB_D void bvh_traverse_persistent(const DScene &sc, int *smem_stack, P &pol, ui
         if (!__any_sync(FULL, active)) break;
         if (active) {
             const bool may_refill = !exhausted;
-            bool done = tr.run(sc, stk, [=] { return may_refill && __popc(__activemask()) < TGB_REFILL_BELOW; });
+            bool done = tr.run(sc, treelet, stk, [=] { return may_refill && __popc(__activemask()) < TGB_REFILL_BELOW; });
             if (done) { pol.finish(tr.h); active = false; }
         }
     }
 }
 
-// Coherent pre-test of a new ray against the BVH's top-level cut (DScene::cut), with the arithmetic of the node test
-// above: false means the traversal would cull every subtree, i.e. its answer is the ray's analytic hit.
+// Coherent pre-test of a new ray against the BVH's top-level cut (DScene::cut), with fused slab arithmetic on the float
+// boxes the tree was built from (the quantised node boxes contain them): false means every subtree would be culled, i.e.
+// the query's answer is the ray's analytic hit.
 TGB_D bool mesh_cut_hit(const DScene &sc, V3 o, V3 d, float tnear, float tfar) {
     const float ooeps = 1e-30f;
     const float idx = 1.0f/(fabsf(d.x) > ooeps ? d.x : copysignf(ooeps, d.x));
@@ -411,14 +522,14 @@ TGB_D bool mesh_cut_hit(const DScene &sc, V3 o, V3 d, float tnear, float tfar) {
     return hit;
 }
 
-// One ray per thread (parity hook; the renderer's kernels when TGB_PERSIST=0): a policy object supplies the ray and takes the hit.
+// One ray per thread (parity hook): a policy object supplies the ray and takes the hit.
 template <bool CURVES, class P>
 TGB_D void bvh_traverse_multi(const DScene &sc, int *smem_stack, P &pol, uint32_t n) {
     uint32_t i = blockIdx.x*blockDim.x + threadIdx.x;
     if (i >= n) return;
     V3 o, d; float tnear; Hit h; bool any;
     if (!pol.fetch(i, o, d, tnear, h, any)) return;
-    bvh_traverse<CURVES>(sc, smem_stack, o, d, tnear, any, h);
+    bvh_traverse<CURVES>(sc, nullptr, smem_stack, o, d, tnear, any, h);
     pol.finish(h);
 }
 
@@ -534,20 +645,20 @@ TGB_D uint32_t ray_bin(const DScene &sc, V3 o, V3 d) {
     int cz = min(max(int((o.z - sc.bin_lo.z)*sc.bin_inv.z), 0), 15);
     return (oct << 12) | (uint32_t(cx) << 8) | (uint32_t(cy) << 4) | uint32_t(cz);       // (Morton order of the cell: no gain)
 }
-
 // ---- kernels ---------------------------------------------------------------------------------
 struct BatchInfo { const uint32_t *pix_id, *pix_seed; uint32_t n_pix, spp_begin; };
 
-// Path (re)generation: paths [first_path, first_path + m) of the step start in slots [slot_base, slot_base + m),
-// right behind the survivors that k_accum compacted to the front of the same buffer.  Consecutive slots are
-// neighbouring pixels of one sample index, so the primary rays stay coherent and every state access is coalesced.
+// Path (re)generation: the ctl.n_new camera paths [first_path, first_path + n_new) of the step start in slots
+// [n_surv, n_surv + n_new), right behind the survivors that k_accum compacted to the front of the same buffer.  Consecutive
+// slots are neighbouring pixels of one sample index, so the primary rays stay coherent and every state access is coalesced.
 // = SobolPathSampler::startPath + ReconstructionFilter::sample + PinholeCamera::sampleDirection + the analytic
-// part of the first TraceableScene::intersect.
-__global__ void __launch_bounds__(256) k_regen(DScene sc, PathState st, BatchInfo bi, uint32_t slot_base, uint32_t first_path, uint32_t m, uint32_t *order) {
-    uint32_t j = blockIdx.x*blockDim.x + threadIdx.x;
-    if (j >= m) return;
-    uint32_t i = slot_base + j;
-    uint32_t path = first_path + j;
+// part of the first TraceableScene::intersect.  Also clears the ray-coherence histogram for this iteration's k_accum.
+__global__ void __launch_bounds__(256) k_regen(DScene sc, PathBuf pb, BatchInfo bi, const Ctl *ctl, uint32_t *order, uint32_t *hist) {
+    const uint32_t j = blockIdx.x*blockDim.x + threadIdx.x;
+    for (uint32_t k = j; k < kBins; k += gridDim.x*blockDim.x) hist[k] = 0u;
+    if (j >= ctl->n_new) return;
+    const uint32_t i = ctl->n_surv + j;
+    const uint32_t path = ctl->first_path + j;
     uint32_t pix = path % bi.n_pix, smp_i = bi.spp_begin + path/bi.n_pix;
     uint32_t pixel_id = __ldg(bi.pix_id + pix);
     Sampler smp; sampler_start(smp, sc.sobol, __ldg(bi.pix_seed + pix), pixel_id, smp_i);
@@ -562,16 +673,14 @@ __global__ void __launch_bounds__(256) k_regen(DScene sc, PathState st, BatchInf
                              sc.cam.ratio - (float(py) + 0.5f + fv)*2.0f*sc.cam.pixel_size_x,
                              sc.cam.plane_dist));
     V3 d = m3mul(sc.cam.m, localD);
-    st.ox[i] = sc.cam.pos.x; st.oy[i] = sc.cam.pos.y; st.oz[i] = sc.cam.pos.z;
-    st.dx[i] = d.x; st.dy[i] = d.y; st.dz[i] = d.z; st.tmin[i] = 1e-4f;                   // math/Ray.hpp:24
-    st.tx[i] = 1.0f; st.ty[i] = 1.0f; st.tz[i] = 1.0f;
-    st.ex[i] = 0.0f; st.ey[i] = 0.0f; st.ez[i] = 0.0f;
-    st.pcg[i] = smp.pcg;
-    st.info[i] = smp.dimension | F_WAS_SPECULAR | F_ALIVE;
-    st.pid[i] = path;
     Hit h = analytic_closest(sc, sc.cam.pos, d, 1e-4f, INFINITY);
-    st.ra[i] = make_float4(sc.cam.pos.x, sc.cam.pos.y, sc.cam.pos.z, 1e-4f); st.rb[i] = make_float4(d.x, d.y, d.z, 0.0f);
-    st.h4[i] = pack_hit(h);
+    float4 *T = pb.T + 4*size_t(i);
+    T[0] = make_float4(sc.cam.pos.x, sc.cam.pos.y, sc.cam.pos.z, 1e-4f);                      // nearT: math/Ray.hpp:24
+    T[1] = make_float4(d.x, d.y, d.z, __uint_as_float(smp.dimension | F_WAS_SPECULAR | F_ALIVE));
+    T[2] = pack_hit(h);
+    T[3] = make_float4(1.0f, 1.0f, 1.0f, __uint_as_float(path));
+    pb.E[i] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    pb.pcg[i] = smp.pcg;
     order[i] = i;                    // new camera paths are already coherent: visited in slot order, after the sorted survivors
 }
 
@@ -584,32 +693,35 @@ TGB_D void count_block(unsigned long long *rays, unsigned long long *hits, bool 
 }
 
 // TraceableScene::intersect for the path rays: the analytic part of the query was done by the kernel that made the
-// ray (k_raygen / k_accum); this kernel walks the triangle BVH, K rays per lane.
+// ray (k_regen / k_accum); this kernel walks the BVH.  A ray is reached through the sort index and costs one 64-byte line:
+// 48 bytes read (origin, direction, analytic hit) + 16 bytes written (closest hit) = the algorithmic 48 B per query.
 struct PathRayPolicy {
-    PathState st; const uint32_t *order; const uint32_t *n_sorted; uint32_t n_surv, n_all; uint32_t s;
+    float4 *T; const uint32_t *order; uint32_t n_sorted, n_surv, n_all; uint32_t s;
     TGB_D bool fetch(uint32_t i, V3 &o, V3 &d, float &tnear, Hit &h, bool &any) {
         // order[] = [survivors to trace, key order | unused (survivors that miss the BVH cut) | new camera paths]
-        uint32_t ns = *n_sorted;
-        if (i >= ns) { i += n_surv - ns; if (i >= n_all) return false; }
+        if (i >= n_sorted) { i += n_surv - n_sorted; if (i >= n_all) return false; }
         s = order[i];
-        float4 a = st.ra[s], b = st.rb[s];
+        const float4 *r = T + 4*size_t(s);
+        float4 a = r[0], b = r[1];
         o = v3(a.x, a.y, a.z); tnear = a.w; d = v3(b.x, b.y, b.z);
-        h = unpack_hit(st.h4[s]); any = false;
+        h = unpack_hit(r[2]); any = false;
         return true;
     }
-    TGB_D void finish(const Hit &h) { st.h4[s] = pack_hit(h); }
+    TGB_D void finish(const Hit &h) { T[4*size_t(s) + 2] = pack_hit(h); }
 };
-template <bool CURVES, bool PERSIST>
-__global__ void __launch_bounds__(kTraceBlock, TGB_MINB) k_trace(DScene sc, PathState st, const uint32_t *order, const uint32_t *n_sorted,
-                                                                 uint32_t n_surv, uint32_t n, uint32_t *counter) {
-    extern __shared__ int smem_stack[];
-    PathRayPolicy pol; pol.st = st; pol.order = order; pol.n_sorted = n_sorted; pol.n_surv = n_surv; pol.n_all = n; pol.s = 0;
-    if (PERSIST) bvh_traverse_persistent<CURVES>(sc, smem_stack, pol, n, counter);
-    else bvh_traverse_multi<CURVES>(sc, smem_stack, pol, n);
+template <bool CURVES>
+__global__ void __launch_bounds__(kTraceBlock, TGB_MINB) k_trace(DScene sc, PathBuf pb, const uint32_t *order, Ctl *ctl) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const uint4 *treelet = stage_treelet(sc, smem_raw);
+    int *smem_stack = reinterpret_cast<int *>(smem_raw + size_t(sc.n_treelet)*64);
+    PathRayPolicy pol; pol.T = pb.T; pol.order = order; pol.n_sorted = ctl->n_sorted; pol.n_surv = ctl->n_surv; pol.n_all = ctl->n; pol.s = 0;
+    // rays to pull: the sorted survivors + the new camera paths
+    const uint32_t n = ctl->n_sorted + ctl->n_new;
+    bvh_traverse_persistent<CURVES>(sc, treelet, smem_stack, pol, n, &ctl->cursor_trace);
 }
 
 // Parity hook (tgb200_trace_closest): rays in AoS tgb_ray, hits out as tgb_hit, through the same analytic pass and
-// the same BVH kernel code as the renderer.
+// the same BVH traversal code as the renderer (global-memory nodes only).
 struct HookPolicy {
     const tgb_ray *rays; Hit *out; uint32_t i;
     TGB_D bool fetch(uint32_t idx, V3 &o, V3 &d, float &tnear, Hit &h, bool &any) {
@@ -627,9 +739,29 @@ __global__ void __launch_bounds__(256) k_hook_analytic(DScene sc, const tgb_ray 
 }
 template <bool CURVES>
 __global__ void __launch_bounds__(kTraceBlock) k_hook_bvh(DScene sc, const tgb_ray *rays, Hit *out, uint32_t n) {
-    extern __shared__ int smem_stack[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     HookPolicy pol; pol.rays = rays; pol.out = out; pol.i = 0;
-    bvh_traverse_multi<CURVES>(sc, smem_stack, pol, n);
+    bvh_traverse_multi<CURVES>(sc, reinterpret_cast<int *>(smem_raw), pol, n);
+}
+// The same queries through the renderer's PERSISTENT kernel body (treelet staged in shared memory, lane refill): the
+// second half of the hit-id parity check, so the staged copy of the top nodes is pinned as well.
+struct HookPersistPolicy {
+    const tgb_ray *rays; Hit *out; uint32_t i;
+    TGB_D bool fetch(uint32_t idx, V3 &o, V3 &d, float &tnear, Hit &h, bool &any) {
+        i = idx;
+        o = v3(rays[i].o[0], rays[i].o[1], rays[i].o[2]); d = v3(rays[i].d[0], rays[i].d[1], rays[i].d[2]); tnear = rays[i].tmin;
+        h = out[i]; any = false;
+        return true;
+    }
+    TGB_D void finish(const Hit &h) { out[i] = h; }
+};
+template <bool CURVES>
+__global__ void __launch_bounds__(kTraceBlock, TGB_MINB) k_hook_persist(DScene sc, const tgb_ray *rays, Hit *out, uint32_t n, uint32_t *counter) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const uint4 *treelet = stage_treelet(sc, smem_raw);
+    int *smem_stack = reinterpret_cast<int *>(smem_raw + size_t(sc.n_treelet)*64);
+    HookPersistPolicy pol; pol.rays = rays; pol.out = out; pol.i = 0;
+    bvh_traverse_persistent<CURVES>(sc, treelet, smem_stack, pol, n, counter);
 }
 __global__ void __launch_bounds__(256) k_hook_finish(DScene sc, const tgb_ray *rays, const Hit *in, tgb_hit *hits, uint32_t n) {
     uint32_t i = blockIdx.x*blockDim.x + threadIdx.x;
@@ -650,8 +782,8 @@ __global__ void __launch_bounds__(256) k_hook_finish(DScene sc, const tgb_ray *r
 }
 
 // handleSurface (integrators/TraceBase.cpp:516-568) + the loop tail of traceSample (PathTracer.cpp:108-126)
-// k_shade is latency bound (scattered shading-record gathers): 8 resident blocks (64 registers, no spills) beat the
-// compiler's free choice of 95 registers / 5 blocks (C1: 564 -> 576 Msamples/s)
+// k_shade is latency bound (scattered shading-record gathers): 8 resident blocks (64 registers) beat the
+// compiler's free choice of 95 registers / 5 blocks (round 1, C1: 564 -> 576 Msamples/s)
 #ifndef TGB_SHADE_MINB
 #define TGB_SHADE_MINB 8
 #endif
@@ -673,21 +805,60 @@ TGB_D uint32_t shade_sort_key(const DScene &sc, const Hit &h) {
     } else bsdf = int(__ldg(sc.slots + sc.prims[-h.id - 2].bsdf_first));
     return 1u + min(sc.bsdfs[bsdf].type, 13u);
 }
+
+// attenuatedEmission + generalizedShadowRay (TraceBase.cpp:144-174,62-125) for the NEE and MIS queries.
+//  * "any" queries (quad / environment lights): lightF / bsdfF were finished by k_shade; what remains is the
+//    search for a blocker in [epsilon, t_light] other than the light; vis[] is set if there is none;
+//  * mesh-light queries: one closest-hit query decides visibility (the light is part of the scene) and the epilogue
+//    evaluates evalDirect / directPdf on the light hit: lightF (TraceBase.cpp:279-284) or bsdfF (:316-320).
+// The tail of k_shade tests the analytic primitives, resolves what it can and compacts the rest for k_shadow_bvh
+// (persistent traversal of the BVH).
+template <bool CURVES>
+TGB_D void shadow_resolve_closest(const DScene &sc, const Scratch &sr, uint32_t s, bool mis, int li, V3 p, V3 d, const Hit &h) {
+    if (h.id == HID_MISS) return;
+    const DPrim &l = sc.prims[li];
+    Surface ls; make_surface<CURVES>(sc, h, p, d, ls);
+    bool visible = ls.prim == li;
+    if (visible && !mis && h.t*(1.0f + 1e-3f) < sr.N0[s].w) visible = false;                    // TraceBase.cpp:160
+    if (!visible) return;
+    V3 em = eval_direct(sc, ls);
+    if (is_zero(em)) return;
+    if (!mis) {
+        float *n1 = reinterpret_cast<float *>(sr.N1 + s);
+        V3 f = v3(n1[0], n1[1], n1[2]);
+        float pdfL = n1[3], pdfB = reinterpret_cast<const float *>(sr.M1 + s)[3];
+        V3 lightF = (f*em)/pdfL;
+        lightF = lightF*power_heuristic(pdfL, pdfB);
+        n1[0] = lightF.x; n1[1] = lightF.y; n1[2] = lightF.z;
+    } else {
+        float directPdf = length_sq(p - ls.p)/(-dot(d, ls.Ng)*l.total_area);                    // TriangleMesh.cpp:477-481
+        float *m1 = reinterpret_cast<float *>(sr.M1 + s);                                      // (the NEE query of this path may be reading m1[3])
+        V3 w = v3(m1[0], m1[1], m1[2]);
+        V3 bsdfF = em*w;
+        bsdfF = bsdfF*power_heuristic(sr.M0[s].w, directPdf);
+        m1[0] = bsdfF.x; m1[1] = bsdfF.y; m1[2] = bsdfF.z;
+    }
+    sr.vis[2*size_t(s) + (mis ? 1 : 0)] = 1u;
+}
+
 template <bool CURVES, bool MATSORT>
 __global__ void __launch_bounds__(MATSORT ? kShadeSortBlock : 128, MATSORT ? 2 : TGB_SHADE_MINB)
-k_shade(DScene sc, PathState st, BatchInfo bi, uint32_t n, uint32_t *squeue, uint32_t *scount, Counters *ctr) {
+k_shade(DScene sc, PathBuf pb, Scratch sr, BatchInfo bi, Ctl *ctl, uint32_t *squeue, Counters *ctr) {
+    const uint32_t n = ctl->n;
     uint32_t i = blockIdx.x*blockDim.x + threadIdx.x;
     bool valid = i < n;
+    // this bounce's NEE / MIS queries: direction, far end (t of the light for occlusion queries), kind
     bool qn = false, qm = false, qn_any = false, qm_any = false;
+    V3 qp = v3s(0.0f), qnd = v3s(0.0f), qmd = v3s(0.0f); float qeps = 5e-4f, qnt = INFINITY, qmt = INFINITY; int qli = 0;
     uint32_t s = 0;
     // one path query (TraceableScene::intersect) was completed for every slot in the queue
-    count_block(&ctr->rays, &ctr->hits, valid, valid && __float_as_int(st.h4[valid ? i : 0].w) != HID_MISS);
+    count_block(&ctr->rays, &ctr->hits, valid, valid && __float_as_int(pb.T[4*size_t(valid ? i : 0) + 2].w) != HID_MISS);
     if (MATSORT) {
         __shared__ uint32_t bucket[16];
         __shared__ uint16_t perm[kShadeSortBlock];
         if (threadIdx.x < 16) bucket[threadIdx.x] = 0u;
         __syncthreads();
-        uint32_t key = valid ? shade_sort_key(sc, unpack_hit(st.h4[i])) : 15u;      // slots past the end sort last
+        uint32_t key = valid ? shade_sort_key(sc, unpack_hit(pb.T[4*size_t(i) + 2])) : 15u;      // slots past the end sort last
         uint32_t rank = atomicAdd(&bucket[key], 1u);
         __syncthreads();
         uint32_t before = 0;
@@ -699,12 +870,14 @@ k_shade(DScene sc, PathState st, BatchInfo bi, uint32_t n, uint32_t *squeue, uin
     }
     if (valid) {
         s = i;
-        uint32_t info = st.info[s];
+        float4 *T = pb.T + 4*size_t(s);
+        const float4 t0 = T[0], t1 = T[1], t2 = T[2], t3 = T[3];
+        uint32_t info = __float_as_uint(t1.w);
         int bounce = int((info >> 16) & 0xFFu);
         bool wasSpecular = (info & F_WAS_SPECULAR) != 0;
-        V3 o = v3(st.ox[s], st.oy[s], st.oz[s]), d = v3(st.dx[s], st.dy[s], st.dz[s]);
-        V3 thr = v3(st.tx[s], st.ty[s], st.tz[s]);
-        Hit h = unpack_hit(st.h4[s]);
+        V3 o = v3(t0.x, t0.y, t0.z), d = v3(t1.x, t1.y, t1.z);
+        V3 thr = v3(t3.x, t3.y, t3.z);
+        Hit h = unpack_hit(t2);
         const tgb_settings &set = sc.set;
         uint32_t flags = 0;
 
@@ -716,14 +889,16 @@ k_shade(DScene sc, PathState st, BatchInfo bi, uint32_t n, uint32_t *squeue, uin
                 if (!set.enable_light_sampling || wasSpecular || !(l.flags & PF_SAMPLABLE)) {
                     float u, v; direction_to_uv(l, d, u, v, nullptr);
                     V3 em = tex_eval(sc.tex[l.emission_tex], u, v);
-                    st.ex[s] += thr.x*em.x; st.ey[s] += thr.y*em.y; st.ez[s] += thr.z*em.z;
+                    float4 e4 = pb.E[s];
+                    e4.x += thr.x*em.x; e4.y += thr.y*em.y; e4.z += thr.z*em.z;
+                    pb.E[s] = e4;
                 }
             }
-            st.info[s] = (info & 0x00FFFFFFu) | F_FINAL_CHECK;
+            T[1] = make_float4(d.x, d.y, d.z, __uint_as_float((info & 0x00FFFFFFu) | F_FINAL_CHECK));
         } else {
-            Sampler smp; smp.sobol = sc.sobol; smp.pcg = st.pcg[s]; smp.dimension = info & 0xFFFFu;
+            Sampler smp; smp.sobol = sc.sobol; smp.pcg = pb.pcg[s]; smp.dimension = info & 0xFFFFu;
+            const uint32_t path = __float_as_uint(t3.w);
             {
-                uint32_t path = st.pid[s];
                 uint32_t pix = path % bi.n_pix;
                 smp.index = bi.spp_begin + path/bi.n_pix;
                 smp.scramble = __ldg(bi.pix_seed + pix) ^ hash32(__ldg(bi.pix_id + pix));
@@ -731,7 +906,6 @@ k_shade(DScene sc, PathState st, BatchInfo bi, uint32_t n, uint32_t *squeue, uin
             Surface sf; make_surface<CURVES>(sc, h, o, d, sf);
             const DBsdf &b = sc.bsdfs[sf.bsdf];
             const float epsilon = sf.eps;                                                    // IntersectionInfo::epsilon
-            if (CURVES) st.eps[s] = epsilon;
 
             // makeLocalScatterEvent (TraceBase.cpp:24-51)
             Event e;
@@ -740,9 +914,9 @@ k_shade(DScene sc, PathState st, BatchInfo bi, uint32_t n, uint32_t *squeue, uin
                 if (CURVES && sf.curve && (b.lobes & LOBE_ANISO)) {
                     // anisotropic lobe: Curves::tangentSpace (Curves.cpp:518-530) + Primitive::setupTangentFrame (Primitive.cpp:134-162)
                     V3 B = normalize(sf.tangent);
-                    V3 T = cross(B, sf.Ng), N = sf.Ns;
-                    T = T - N*dot(N, T);
-                    if (!is_zero(T)) { T = normalize(T); frame.n = N; frame.t = T; frame.b = cross(N, T); }
+                    V3 T_ = cross(B, sf.Ng), N = sf.Ns;
+                    T_ = T_ - N*dot(N, T_);
+                    if (!is_zero(T_)) { T_ = normalize(T_); frame.n = N; frame.t = T_; frame.b = cross(N, T_); }
                 }
                 bool hitBackside = dot(frame.n, d) > 0.0f;
                 bool isTransmissive = (b.lobes & LOBE_TRANSMISSIVE) != 0;
@@ -754,7 +928,6 @@ k_shade(DScene sc, PathState st, BatchInfo bi, uint32_t n, uint32_t *squeue, uin
             // forward-transparency coin flip: transparency == 0 for every lobe in scope, the draw is still made (:525-529)
             (void)sampler_boolean(smp, 0.0f);
 
-            st.px[s] = sf.p.x; st.py[s] = sf.p.y; st.pz[s] = sf.p.z;
             if (set.enable_light_sampling && bounce < set.max_bounces - 1) {
                 // estimateDirect -> chooseLight -> sampleDirect (TraceBase.cpp:483-494,416-459,383-400)
                 float weight;
@@ -765,6 +938,7 @@ k_shade(DScene sc, PathState st, BatchInfo bi, uint32_t n, uint32_t *squeue, uin
                     // lightSample (TraceBase.cpp:246-285).  For quad / environment lights the light's own hit
                     // (attenuatedEmission, :160-165) and lightF (:279-284) are resolved here and the query that is
                     // traced is a pure blocker test; mesh lights keep the closest-hit query + epilogue.
+                    float4 n1 = make_float4(0.0f, 0.0f, 0.0f, 0.0f), m1 = make_float4(0.0f, 0.0f, 0.0f, 0.0f); float mpb = 0.0f;
                     LightSample ls;
                     if (light_sample_direct(sc, l, sf.p, smp, ls)) {
                         e.wo = to_local(e.frame, ls.d);
@@ -778,8 +952,7 @@ k_shade(DScene sc, PathState st, BatchInfo bi, uint32_t n, uint32_t *squeue, uin
                                 float pdfB = bsdf_pdf<CURVES>(sc, b, sf, e);
                                 if (l.type == TGB_PRIM_MESH) {
                                     qn = true; qn_any = false;
-                                    st.ndist[s] = ls.dist; st.nfx[s] = f.x; st.nfy[s] = f.y; st.nfz[s] = f.z;
-                                    st.npl[s] = ls.pdf; st.npb[s] = pdfB;
+                                    qnt = ls.dist; n1 = make_float4(f.x, f.y, f.z, ls.pdf); m1.w = pdfB;
                                 } else {
                                     V3 em = v3s(0.0f); float tfar = INFINITY; bool hitL = true;
                                     if (l.type == TGB_PRIM_QUAD) {
@@ -795,10 +968,10 @@ k_shade(DScene sc, PathState st, BatchInfo bi, uint32_t n, uint32_t *squeue, uin
                                         V3 lightF = (f*em)/ls.pdf;
                                         lightF = lightF*power_heuristic(ls.pdf, pdfB);
                                         qn = true; qn_any = true;
-                                        st.ndist[s] = tfar; st.nfx[s] = lightF.x; st.nfy[s] = lightF.y; st.nfz[s] = lightF.z;
+                                        qnt = tfar; n1 = make_float4(lightF.x, lightF.y, lightF.z, 0.0f);
                                     }
                                 }
-                                if (qn) { st.ndx[s] = ls.d.x; st.ndy[s] = ls.d.y; st.ndz[s] = ls.d.z; }
+                                if (qn) qnd = ls.d;
                             }
                         }
                     }
@@ -812,7 +985,7 @@ k_shade(DScene sc, PathState st, BatchInfo bi, uint32_t n, uint32_t *squeue, uin
                         if (ok) {
                             if (l.type == TGB_PRIM_MESH) {
                                 qm = true; qm_any = false;
-                                st.mwx[s] = e.weight.x; st.mwy[s] = e.weight.y; st.mwz[s] = e.weight.z; st.mpb[s] = e.pdf;
+                                m1.x = e.weight.x; m1.y = e.weight.y; m1.z = e.weight.z; mpb = e.pdf;
                             } else {
                                 V3 em = v3s(0.0f); float tfar = INFINITY, directPdf; bool hitL = true;
                                 if (l.type == TGB_PRIM_QUAD) {
@@ -831,32 +1004,38 @@ k_shade(DScene sc, PathState st, BatchInfo bi, uint32_t n, uint32_t *squeue, uin
                                     V3 bsdfF = em*e.weight;
                                     bsdfF = bsdfF*power_heuristic(e.pdf, directPdf);
                                     qm = true; qm_any = true;
-                                    st.mwx[s] = bsdfF.x; st.mwy[s] = bsdfF.y; st.mwz[s] = bsdfF.z; st.mpb[s] = tfar;
+                                    m1.x = bsdfF.x; m1.y = bsdfF.y; m1.z = bsdfF.z; mpb = tfar;
                                 }
                             }
-                            if (qm) { st.mdx[s] = wo.x; st.mdy[s] = wo.y; st.mdz[s] = wo.z; }
+                            if (qm) { qmd = wo; qmt = mpb; }
                         }
                     }
                     // generalizedShadowRay returns 0 unless bounce+1 >= minBounces (TraceBase.cpp:117)
                     if (bounce + 1 < set.min_bounces) { qn = false; qm = false; }
                     if (qn || qm) {
                         flags |= F_HAS_NEE;
-                        st.qlight[s] = li; st.wl[s] = weight;
-                        st.ux[s] = thr.x; st.uy[s] = thr.y; st.uz[s] = thr.z;
-                        st.lx[s] = 0.0f; st.ly[s] = 0.0f; st.lz[s] = 0.0f; st.bx[s] = 0.0f; st.by[s] = 0.0f; st.bz[s] = 0.0f;
+                        qp = sf.p; qeps = epsilon; qli = li;
+                        sr.P[s] = make_float4(sf.p.x, sf.p.y, sf.p.z, epsilon);
+                        if (qn) { sr.N0[s] = make_float4(qnd.x, qnd.y, qnd.z, qnt); }
+                        sr.N1[s] = n1;
+                        if (qm) { sr.M0[s] = make_float4(qmd.x, qmd.y, qmd.z, qmt); }
+                        sr.M1[s] = m1;
+                        sr.D0[s] = make_float4(thr.x, thr.y, thr.z, weight);
                     }
                 }
             }
 
             // emission of the surface itself (TraceBase.cpp:540-543)
             const DPrim &prim = sc.prims[sf.prim];
+            float4 d1 = make_float4(0.0f, 0.0f, 0.0f, __int_as_float(qli));
             if ((prim.flags & PF_EMISSIVE) && bounce >= set.min_bounces) {
                 if (!set.enable_light_sampling || wasSpecular || !(prim.flags & PF_SAMPLABLE)) {
                     V3 em = eval_direct(sc, sf)*thr;
-                    st.sx[s] = em.x; st.sy[s] = em.y; st.sz[s] = em.z;
+                    d1.x = em.x; d1.y = em.y; d1.z = em.z;
                     flags |= F_HAS_SURF;
                 }
             }
+            if (flags & (F_HAS_SURF | F_HAS_NEE)) sr.D1[s] = d1;
 
             // continuation sample (TraceBase.cpp:545-565)
             uint32_t status = 0;
@@ -867,11 +1046,11 @@ k_shade(DScene sc, PathState st, BatchInfo bi, uint32_t n, uint32_t *squeue, uin
                 wo = to_global(e.frame, e.wo);
                 if (set.enable_consistency_checks && (dot(wo, sf.Ng) < 0.0f) != ((e.wo.z < 0.0f) != e.flipped)) cont = false;
             }
+            V3 no = o, nd = d; float ntmin = t0.w;
             if (cont) {
                 thr = thr*e.weight;
                 wasSpecular = (e.sampled & LOBE_SPECULAR) != 0;
-                st.ox[s] = sf.p.x; st.oy[s] = sf.p.y; st.oz[s] = sf.p.z;      // ray.hitpoint() == info.p for every primitive in scope
-                st.dx[s] = wo.x; st.dy[s] = wo.y; st.dz[s] = wo.z; st.tmin[s] = epsilon;
+                no = sf.p; nd = wo; ntmin = epsilon;                            // ray.hitpoint() == info.p for every primitive in scope
                 // PathTracer.cpp:108-117
                 if (max_comp(thr) == 0.0f) status = F_FINAL_CHECK;
                 else {
@@ -886,179 +1065,145 @@ k_shade(DScene sc, PathState st, BatchInfo bi, uint32_t n, uint32_t *squeue, uin
                         status = bounce < set.max_bounces ? F_ALIVE : (F_ALIVE | F_FINAL_CHECK);
                     }
                 }
-                st.tx[s] = thr.x; st.ty[s] = thr.y; st.tz[s] = thr.z;
+                T[0] = make_float4(no.x, no.y, no.z, ntmin);
+                T[3] = make_float4(thr.x, thr.y, thr.z, t3.w);
             }
-            st.pcg[s] = smp.pcg;
-            st.info[s] = (smp.dimension & 0xFFFFu) | (uint32_t(bounce) << 16) | (wasSpecular ? F_WAS_SPECULAR : 0u) | status | flags;
+            pb.pcg[s] = smp.pcg;
+            T[1] = make_float4(nd.x, nd.y, nd.z, __uint_as_float((smp.dimension & 0xFFFFu) | (uint32_t(bounce) << 16) | (wasSpecular ? F_WAS_SPECULAR : 0u) | status | flags));
         }
     }
-    // enqueue this bounce's shadow queries: warp-vote compaction, one atomic per warp
+    // ---- this bounce's shadow queries: analytic part + top-level cut here (the data is in registers), the rest is queued
+    // for k_shadow_bvh with warp-vote compaction, one atomic per warp
+    bool keep_n = false, keep_m = false; Hit hn, hm; uint32_t vis_n = 0u, vis_m = 0u; bool blk_n = false, blk_m = false;
+    hn.t = INFINITY; hn.u = hn.v = 0.0f; hn.id = HID_MISS; hm = hn;
+    if (qn) {
+        if (qn_any) {
+            blk_n = analytic_any(sc, qp, qnd, qeps, qnt, qli);
+            if (!blk_n) { if (!mesh_cut_hit(sc, qp, qnd, qeps, qnt)) vis_n = 1u; else keep_n = true; }
+        } else {
+            hn = analytic_closest(sc, qp, qnd, qeps, INFINITY);
+            if (!mesh_cut_hit(sc, qp, qnd, qeps, hn.t)) blk_n = hn.id != HID_MISS;     // an analytic primitive is never the (mesh) light
+            else keep_n = true;
+        }
+    }
+    if (qm) {
+        if (qm_any) {
+            blk_m = analytic_any(sc, qp, qmd, qeps, qmt, qli);
+            if (!blk_m) { if (!mesh_cut_hit(sc, qp, qmd, qeps, qmt)) vis_m = 1u; else keep_m = true; }
+        } else {
+            hm = analytic_closest(sc, qp, qmd, qeps, INFINITY);
+            if (!mesh_cut_hit(sc, qp, qmd, qeps, hm.t)) blk_m = hm.id != HID_MISS;
+            else keep_m = true;
+        }
+    }
+    if (qn || qm) *reinterpret_cast<uint2 *>(sr.vis + 2*size_t(s)) = make_uint2(vis_n, vis_m);
     {
-        unsigned mn = __ballot_sync(0xffffffffu, qn), mm = __ballot_sync(0xffffffffu, qm);
+        const unsigned FULL = 0xffffffffu;
+        unsigned an = __ballot_sync(FULL, qn), am = __ballot_sync(FULL, qm);
+        unsigned bn = __ballot_sync(FULL, blk_n), bm = __ballot_sync(FULL, blk_m);
+        unsigned mn = __ballot_sync(FULL, keep_n), mm = __ballot_sync(FULL, keep_m);
+        unsigned lane = threadIdx.x & 31;
+        if (lane == 0 && (an | am)) {
+            atomicAdd(&ctr->shadow_rays, (unsigned long long)(__popc(an) + __popc(am)));
+            if (bn | bm) atomicAdd(&ctr->shadow_hits, (unsigned long long)(__popc(bn) + __popc(bm)));
+        }
         unsigned total = __popc(mn) + __popc(mm);
         if (total) {
-            unsigned lane = threadIdx.x & 31, base = 0;
-            if (lane == 0) base = atomicAdd(scount, total);
-            base = __shfl_sync(0xffffffffu, base, 0);
+            unsigned base = 0;
+            if (lane == 0) base = atomicAdd(&ctl->shadow_count, total);
+            base = __shfl_sync(FULL, base, 0);
             unsigned lt = (1u << lane) - 1u;
-            if (qn) squeue[base + __popc(mn & lt)] = (s << 2) | (qn_any ? 2u : 0u);
-            if (qm) squeue[base + __popc(mn) + __popc(mm & lt)] = (s << 2) | 1u | (qm_any ? 2u : 0u);
-        }
-    }
-}
-
-// attenuatedEmission + generalizedShadowRay (TraceBase.cpp:144-174,62-125) for the NEE and MIS queries.
-//  * "any" queries (quad / environment lights): lightF / bsdfF were finished by k_shade; what remains is the
-//    search for a blocker in [epsilon, t_light] other than the light; the value is stored if there is none;
-//  * mesh-light queries: one closest-hit query decides visibility (the light is part of the scene) and the epilogue
-//    evaluates evalDirect / directPdf on the light hit: lightF (TraceBase.cpp:279-284) or bsdfF (:316-320).
-// k_shadow_prep tests the analytic primitives coherently, resolves what it can and compacts the rest for
-// k_shadow_bvh (persistent multi-ray traversal of the triangle BVH).
-struct ShadowState { float *qt, *qu, *qv; int *qid; };      // initial hit of a compacted closest-hit query
-
-TGB_D void shadow_store_any(PathState &st, uint32_t s, bool mis) {
-    if (!mis) { st.lx[s] = st.nfx[s]; st.ly[s] = st.nfy[s]; st.lz[s] = st.nfz[s]; }
-    else { st.bx[s] = st.mwx[s]; st.by[s] = st.mwy[s]; st.bz[s] = st.mwz[s]; }
-}
-template <bool CURVES>
-TGB_D void shadow_resolve_closest(const DScene &sc, PathState &st, uint32_t s, bool mis, int li, V3 p, V3 d, const Hit &h) {
-    if (h.id == HID_MISS) return;
-    const DPrim &l = sc.prims[li];
-    Surface ls; make_surface<CURVES>(sc, h, p, d, ls);
-    bool visible = ls.prim == li;
-    if (visible && !mis && h.t*(1.0f + 1e-3f) < st.ndist[s]) visible = false;                   // TraceBase.cpp:160
-    if (!visible) return;
-    V3 em = eval_direct(sc, ls);
-    if (is_zero(em)) return;
-    if (!mis) {
-        V3 f = v3(st.nfx[s], st.nfy[s], st.nfz[s]);
-        float pdfL = st.npl[s];
-        V3 lightF = (f*em)/pdfL;
-        lightF = lightF*power_heuristic(pdfL, st.npb[s]);
-        st.lx[s] = lightF.x; st.ly[s] = lightF.y; st.lz[s] = lightF.z;
-    } else {
-        float directPdf = length_sq(p - ls.p)/(-dot(d, ls.Ng)*l.total_area);                    // TriangleMesh.cpp:477-481
-        V3 w = v3(st.mwx[s], st.mwy[s], st.mwz[s]);
-        V3 bsdfF = em*w;
-        bsdfF = bsdfF*power_heuristic(st.mpb[s], directPdf);
-        st.bx[s] = bsdfF.x; st.by[s] = bsdfF.y; st.bz[s] = bsdfF.z;
-    }
-}
-
-template <bool CURVES>
-__global__ void __launch_bounds__(256) k_shadow_prep(DScene sc, PathState st, ShadowState ss, const uint32_t *squeue, const uint32_t *scount,
-                                                      uint32_t *squeue2, uint32_t *scount2, Counters *ctr) {
-    uint32_t i = blockIdx.x*blockDim.x + threadIdx.x;
-    bool valid = i < *scount;
-    bool keep = false, blocked = false; uint32_t q = 0; Hit h; h.t = INFINITY; h.u = h.v = 0.0f; h.id = HID_MISS;
-    if (valid) {
-        q = squeue[i];
-        uint32_t s = q >> 2; bool mis = q & 1u, any = q & 2u;
-        V3 p = v3(st.px[s], st.py[s], st.pz[s]);
-        V3 d = mis ? v3(st.mdx[s], st.mdy[s], st.mdz[s]) : v3(st.ndx[s], st.ndy[s], st.ndz[s]);
-        int li = st.qlight[s];
-        const float eps = CURVES ? st.eps[s] : 5e-4f;                 // info.epsilon of the shading point (TraceBase.cpp:254,295)
-        if (any) {
-            float tfar = mis ? st.mpb[s] : st.ndist[s];
-            blocked = analytic_any(sc, p, d, eps, tfar, li);
-            if (!blocked) { if (!mesh_cut_hit(sc, p, d, eps, tfar)) shadow_store_any(st, s, mis); else keep = true; }
-        } else {
-            h = analytic_closest(sc, p, d, eps, INFINITY);
-            if (!mesh_cut_hit(sc, p, d, eps, h.t)) { blocked = h.id != HID_MISS; shadow_resolve_closest<CURVES>(sc, st, s, mis, li, p, d, h); }
-            else keep = true;
-        }
-    }
-    count_block(&ctr->shadow_rays, &ctr->shadow_hits, valid, blocked);
-    unsigned m = __ballot_sync(0xffffffffu, keep);
-    if (m) {
-        unsigned lane = threadIdx.x & 31, base = 0;
-        if (lane == 0) base = atomicAdd(scount2, unsigned(__popc(m)));
-        base = __shfl_sync(0xffffffffu, base, 0);
-        if (keep) {
-            uint32_t at = base + __popc(m & ((1u << lane) - 1u));
-            squeue2[at] = q;
-            if (!(q & 2u)) { ss.qt[at] = h.t; ss.qu[at] = h.u; ss.qv[at] = h.v; ss.qid[at] = h.id; }
+            if (keep_n) { unsigned at = base + __popc(mn & lt); squeue[at] = (s << 2) | (qn_any ? 2u : 0u); if (!qn_any) sr.SH[at] = pack_hit(hn); }
+            if (keep_m) { unsigned at = base + __popc(mn) + __popc(mm & lt); squeue[at] = (s << 2) | 1u | (qm_any ? 2u : 0u); if (!qm_any) sr.SH[at] = pack_hit(hm); }
         }
     }
 }
 
 template <bool CURVES>
 struct ShadowPolicy {
-    DScene sc; PathState st; ShadowState ss; const uint32_t *squeue2; unsigned long long *hits;
+    DScene sc; Scratch sr; const uint32_t *squeue; unsigned long long *hits;
     uint32_t s; bool mis, any; int li; V3 p, d;
     TGB_D bool fetch(uint32_t i, V3 &o, V3 &dd, float &tnear, Hit &h, bool &anyq) {
-        uint32_t q = squeue2[i];
+        uint32_t q = squeue[i];
         s = q >> 2; mis = q & 1u; any = q & 2u;
-        p = v3(st.px[s], st.py[s], st.pz[s]);
-        d = mis ? v3(st.mdx[s], st.mdy[s], st.mdz[s]) : v3(st.ndx[s], st.ndy[s], st.ndz[s]);
-        li = st.qlight[s];
-        o = p; dd = d; tnear = CURVES ? st.eps[s] : 5e-4f; anyq = any;
-        if (any) { h.t = mis ? st.mpb[s] : st.ndist[s]; h.u = 0.0f; h.v = 0.0f; h.id = HID_MISS; }
-        else { h.t = ss.qt[i]; h.u = ss.qu[i]; h.v = ss.qv[i]; h.id = ss.qid[i]; }
+        const float4 P = sr.P[s], D = mis ? sr.M0[s] : sr.N0[s];
+        p = v3(P.x, P.y, P.z); d = v3(D.x, D.y, D.z);
+        o = p; dd = d; tnear = P.w; anyq = any; li = 0;
+        if (any) { h.t = D.w; h.u = 0.0f; h.v = 0.0f; h.id = HID_MISS; }
+        else { h = unpack_hit(sr.SH[i]); li = __float_as_int(sr.D1[s].w); }
         return true;
     }
     TGB_D void finish(const Hit &h) {
         if (h.id != HID_MISS) atomicAdd(hits, 1ull);
-        if (any) { if (h.id == HID_MISS) shadow_store_any(st, s, mis); }
-        else shadow_resolve_closest<CURVES>(sc, st, s, mis, li, p, d, h);
+        if (any) { if (h.id == HID_MISS) sr.vis[2*size_t(s) + (mis ? 1 : 0)] = 1u; }
+        else shadow_resolve_closest<CURVES>(sc, sr, s, mis, li, p, d, h);
     }
 };
-template <bool CURVES, bool PERSIST>
-__global__ void __launch_bounds__(kTraceBlock, TGB_MINB) k_shadow_bvh(DScene sc, PathState st, ShadowState ss, const uint32_t *squeue2, const uint32_t *scount2,
-                                                            Counters *ctr, uint32_t *counter) {
-    extern __shared__ int smem_stack[];
-    ShadowPolicy<CURVES> pol; pol.sc = sc; pol.st = st; pol.ss = ss; pol.squeue2 = squeue2; pol.hits = &ctr->shadow_hits;
-    if (PERSIST) bvh_traverse_persistent<CURVES>(sc, smem_stack, pol, *scount2, counter);
-    else bvh_traverse_multi<CURVES>(sc, smem_stack, pol, *scount2);
+template <bool CURVES>
+__global__ void __launch_bounds__(kTraceBlock, TGB_MINB) k_shadow_bvh(DScene sc, Scratch sr, const uint32_t *squeue, Ctl *ctl, Counters *ctr) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const uint4 *treelet = stage_treelet(sc, smem_raw);
+    int *smem_stack = reinterpret_cast<int *>(smem_raw + size_t(sc.n_treelet)*64);
+    ShadowPolicy<CURVES> pol; pol.sc = sc; pol.sr = sr; pol.squeue = squeue; pol.hits = &ctr->shadow_hits;
+    bvh_traverse_persistent<CURVES>(sc, treelet, smem_stack, pol, ctl->shadow_count, &ctl->cursor_shadow);
 }
 
 // Fold this bounce's direct light + surface emission into the path (order as in handleSurface:537-543), apply the
 // NaN guards of traceSample (PathTracer.cpp:119-122,130), store finished samples, and MOVE the survivors' persistent
 // state to the front of the other state buffer (physical compaction: all later accesses are coalesced, no slot
 // indirection).  The survivors' next ray gets the analytic part of its TraceableScene::intersect here.
-__global__ void __launch_bounds__(256) k_accum(DScene sc, PathState st, PathState dst, uint32_t n, uint32_t *next_count, uint32_t *keys, uint32_t *hist) {
+__global__ void __launch_bounds__(256) k_accum(DScene sc, PathBuf pb, PathBuf dst, Scratch sr, Ctl *ctl, uint32_t *keys, uint32_t *hist) {
     uint32_t s = blockIdx.x*blockDim.x + threadIdx.x;
-    bool valid = s < n;
+    bool valid = s < ctl->n;
     bool alive = false; uint32_t info = 0; V3 em = v3s(0.0f);
+    float4 t0 = make_float4(0.0f, 0.0f, 0.0f, 0.0f), t1 = t0, t3 = t0;
     if (valid) {
-        info = st.info[s];
-        em = v3(st.ex[s], st.ey[s], st.ez[s]);
+        const float4 *T = pb.T + 4*size_t(s);
+        t1 = T[1]; t3 = T[3];
+        info = __float_as_uint(t1.w);
+        const float4 e4 = pb.E[s];
+        em = v3(e4.x, e4.y, e4.z);
         if (info & F_HAS_NEE) {
-            V3 L = v3(st.lx[s], st.ly[s], st.lz[s]), B = v3(st.bx[s], st.by[s], st.bz[s]);
-            V3 r = ((L + B)*st.wl[s])*v3(st.ux[s], st.uy[s], st.uz[s]);
+            const uint2 vis = *reinterpret_cast<const uint2 *>(sr.vis + 2*size_t(s));
+            V3 L = v3s(0.0f), B = v3s(0.0f);
+            if (vis.x) { const float4 n1 = sr.N1[s]; L = v3(n1.x, n1.y, n1.z); }
+            if (vis.y) { const float4 m1 = sr.M1[s]; B = v3(m1.x, m1.y, m1.z); }
+            const float4 d0 = sr.D0[s];
+            V3 r = ((L + B)*d0.w)*v3(d0.x, d0.y, d0.z);
             em = em + r;
         }
-        if (info & F_HAS_SURF) em = em + v3(st.sx[s], st.sy[s], st.sz[s]);
+        if (info & F_HAS_SURF) { const float4 d1 = sr.D1[s]; em = em + v3(d1.x, d1.y, d1.z); }
         alive = (info & F_ALIVE) != 0;
         bool finalCheck = (info & F_FINAL_CHECK) != 0;
         if (alive || finalCheck) {
-            V3 thr = v3(st.tx[s], st.ty[s], st.tz[s]);
+            V3 thr = v3(t3.x, t3.y, t3.z);
             bool bad = false;
             if (alive) {
-                V3 o = v3(st.ox[s], st.oy[s], st.oz[s]), d = v3(st.dx[s], st.dy[s], st.dz[s]);
-                bad = isnan(sum(d) + sum(o));
+                t0 = T[0];
+                bad = isnan(sum(v3(t1.x, t1.y, t1.z)) + sum(v3(t0.x, t0.y, t0.z)));
             }
             bad = bad || isnan(sum(thr) + sum(em));
             if (bad) { em = v3s(0.0f); alive = false; }
         }
         if (alive && finalCheck) alive = false;                  // bounce reached maxBounces: loop exits
-        if (!alive) { uint32_t path = st.pid[s]; st.rx[path] = em.x; st.ry[path] = em.y; st.rz[path] = em.z; }   // the sample's radiance
+        if (!alive) sr.R[__float_as_uint(t3.w)] = make_float4(em.x, em.y, em.z, 0.0f);       // the sample's radiance
     }
     unsigned m = __ballot_sync(0xffffffffu, alive);
     if (m) {
         unsigned lane = threadIdx.x & 31, base = 0;
-        if (lane == 0) base = atomicAdd(next_count, unsigned(__popc(m)));
+        if (lane == 0) base = atomicAdd(&ctl->next_count, unsigned(__popc(m)));
         base = __shfl_sync(0xffffffffu, base, 0);
         if (alive) {
             uint32_t t = base + __popc(m & ((1u << lane) - 1u));
-            V3 o = v3(st.ox[s], st.oy[s], st.oz[s]), d = v3(st.dx[s], st.dy[s], st.dz[s]); float tmin = st.tmin[s];
-            dst.ox[t] = o.x; dst.oy[t] = o.y; dst.oz[t] = o.z; dst.dx[t] = d.x; dst.dy[t] = d.y; dst.dz[t] = d.z; dst.tmin[t] = tmin;
-            dst.tx[t] = st.tx[s]; dst.ty[t] = st.ty[s]; dst.tz[t] = st.tz[s];
-            dst.ex[t] = em.x; dst.ey[t] = em.y; dst.ez[t] = em.z;
-            dst.pcg[t] = st.pcg[s]; dst.pid[t] = st.pid[s];
-            dst.info[t] = (info & ~(F_HAS_NEE | F_HAS_SURF | F_ALIVE | F_FINAL_CHECK)) | F_ALIVE;
+            V3 o = v3(t0.x, t0.y, t0.z), d = v3(t1.x, t1.y, t1.z); float tmin = t0.w;
             Hit h = analytic_closest(sc, o, d, tmin, INFINITY);
-            dst.ra[t] = make_float4(o.x, o.y, o.z, tmin); dst.rb[t] = make_float4(d.x, d.y, d.z, 0.0f); dst.h4[t] = pack_hit(h);
+            float4 *D = dst.T + 4*size_t(t);
+            D[0] = t0;
+            D[1] = make_float4(t1.x, t1.y, t1.z, __uint_as_float((info & ~(F_HAS_NEE | F_HAS_SURF | F_ALIVE | F_FINAL_CHECK)) | F_ALIVE));
+            D[2] = pack_hit(h);
+            D[3] = t3;
+            dst.E[t] = make_float4(em.x, em.y, em.z, 0.0f);
+            dst.pcg[t] = pb.pcg[s];
             uint32_t key = mesh_cut_hit(sc, o, d, tmin, h.t) ? ray_bin(sc, o, d) : kBins;       // kBins: nothing to traverse
             keys[t] = key;
             if (key != kBins) atomicAdd(hist + key, 1u);
@@ -1066,58 +1211,73 @@ __global__ void __launch_bounds__(256) k_accum(DScene sc, PathState st, PathStat
     }
 }
 
-// Counting sort of the survivors' slot indices by ray-coherence key: exclusive scan of the histogram (one block) ...
-__global__ void __launch_bounds__(1024) k_bin_scan(uint32_t *hist, uint32_t *n_sorted, uint32_t *n_sorted_host) {
+// End of an iteration (one block): exclusive scan of the ray-coherence histogram -> cursors of the counting sort, then the
+// loop's bookkeeping for the NEXT iteration (what the host used to do after a stream sync).
+__global__ void __launch_bounds__(1024) k_iter_end(uint32_t *hist, Ctl *ctl, int has_bvh) {
     // 32 Ki bins, 32 consecutive bins per thread (8 x 16-byte loads), block-wide scan of the 1024 partial sums with
     // warp shuffles (two levels), exclusive bases written back in place
     __shared__ uint32_t warp_sum[32];
+    __shared__ uint32_t total_sorted;
     constexpr uint32_t per = kBins/1024u;
     static_assert(per % 4u == 0u, "vector loads");
     const uint32_t t = threadIdx.x, lane = t & 31u, warp = t >> 5;
-    uint4 *h4 = reinterpret_cast<uint4 *>(hist) + size_t(t)*(per/4u);
-    uint4 v[per/4u];
-    uint32_t sum = 0;
+    if (t == 0) total_sorted = 0u;
+    if (has_bvh) {
+        uint4 *h4 = reinterpret_cast<uint4 *>(hist) + size_t(t)*(per/4u);
+        uint4 v[per/4u];
+        uint32_t sum = 0;
 #pragma unroll
-    for (uint32_t i = 0; i < per/4u; ++i) { v[i] = h4[i]; sum += v[i].x + v[i].y + v[i].z + v[i].w; }
-    uint32_t incl = sum;
+        for (uint32_t i = 0; i < per/4u; ++i) { v[i] = h4[i]; sum += v[i].x + v[i].y + v[i].z + v[i].w; }
+        uint32_t incl = sum;
 #pragma unroll
-    for (uint32_t off = 1; off < 32u; off <<= 1) { uint32_t n = __shfl_up_sync(0xffffffffu, incl, off); if (lane >= off) incl += n; }
-    if (lane == 31u) warp_sum[warp] = incl;
-    __syncthreads();
-    if (warp == 0) {
-        uint32_t w = warp_sum[lane], wi = w;
+        for (uint32_t off = 1; off < 32u; off <<= 1) { uint32_t n = __shfl_up_sync(0xffffffffu, incl, off); if (lane >= off) incl += n; }
+        if (lane == 31u) warp_sum[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            uint32_t w = warp_sum[lane], wi = w;
 #pragma unroll
-        for (uint32_t off = 1; off < 32u; off <<= 1) { uint32_t n = __shfl_up_sync(0xffffffffu, wi, off); if (lane >= off) wi += n; }
-        warp_sum[lane] = wi - w;                       // exclusive base of each warp
-        if (lane == 31u) { *n_sorted = wi; *n_sorted_host = wi; }      // total = the culled survivors follow the sorted ones
+            for (uint32_t off = 1; off < 32u; off <<= 1) { uint32_t n = __shfl_up_sync(0xffffffffu, wi, off); if (lane >= off) wi += n; }
+            warp_sum[lane] = wi - w;                       // exclusive base of each warp
+            if (lane == 31u) total_sorted = wi;            // the culled survivors follow the sorted ones
+        }
+        __syncthreads();
+        uint32_t base = warp_sum[warp] + incl - sum;
+#pragma unroll
+        for (uint32_t i = 0; i < per/4u; ++i) {
+            uint4 o;
+            o.x = base; base += v[i].x; o.y = base; base += v[i].y; o.z = base; base += v[i].z; o.w = base; base += v[i].w;
+            h4[i] = o;
+        }
     }
     __syncthreads();
-    uint32_t base = warp_sum[warp] + incl - sum;
-#pragma unroll
-    for (uint32_t i = 0; i < per/4u; ++i) {
-        uint4 o;
-        o.x = base; base += v[i].x; o.y = base; base += v[i].y; o.z = base; base += v[i].z; o.w = base; base += v[i].w;
-        h4[i] = o;
+    if (t == 0) {
+        if (has_bvh) { ctl->traversed += (unsigned long long)ctl->n_sorted + ctl->n_new; ctl->shadow_traversed += ctl->shadow_count; }
+        ctl->iterations++;
+        const uint32_t n_surv = ctl->next_count;
+        const uint32_t n_new = min(ctl->capacity - n_surv, ctl->total - ctl->issued);
+        ctl->first_path = ctl->issued; ctl->issued += n_new;
+        ctl->n_surv = n_surv; ctl->n_new = n_new; ctl->n = n_surv + n_new; ctl->n_sorted = total_sorted;
+        ctl->next_count = 0u; ctl->shadow_count = 0u; ctl->cursor_trace = 0u; ctl->cursor_shadow = 0u;
     }
 }
 // ... and scatter of the slot indices (4 bytes each) to their sorted positions.
-__global__ void __launch_bounds__(256) k_bin_scatter(const uint32_t *keys, uint32_t *cursor, const uint32_t *n_alive, uint32_t *order) {
+__global__ void __launch_bounds__(256) k_bin_scatter(const uint32_t *keys, uint32_t *cursor, const Ctl *ctl, uint32_t *order) {
     uint32_t t = blockIdx.x*blockDim.x + threadIdx.x;
-    if (t >= *n_alive) return;
+    if (t >= ctl->n_surv) return;
     uint32_t key = keys[t];
     if (key != kBins) order[atomicAdd(cursor + key, 1u)] = t;     // culled survivors are not visited: no entry needed
 }
 
 // OutputBuffer::addSample (cameras/OutputBuffer.hpp:104-132): running mean in sample order, NaN/Inf samples dropped
-__global__ void __launch_bounds__(256) k_resolve(PathState st, BatchInfo bi, uint32_t spp_count, float *fb, uint32_t *fb_count) {
+__global__ void __launch_bounds__(256) k_resolve(const float4 *R, BatchInfo bi, uint32_t spp_count, float *fb, uint32_t *fb_count) {
     uint32_t pix = blockIdx.x*blockDim.x + threadIdx.x;
     if (pix >= bi.n_pix) return;
     uint32_t pid = bi.pix_id[pix];
     float mx = fb[3*size_t(pid)], my = fb[3*size_t(pid) + 1], mz = fb[3*size_t(pid) + 2];
     uint32_t cnt = fb_count[pid];
     for (uint32_t k = 0; k < spp_count; ++k) {
-        size_t s = size_t(k)*bi.n_pix + pix;
-        float cx = st.rx[s], cy = st.ry[s], cz = st.rz[s];
+        const float4 c = R[size_t(k)*bi.n_pix + pix];
+        float cx = c.x, cy = c.y, cz = c.z;
         if (isnan(cx) || isnan(cy) || isnan(cz) || isinf(cx) || isinf(cy) || isinf(cz)) continue;
         float n = float(cnt + 1u); cnt++;
         mx += (cx - mx)/n; my += (cy - my)/n; mz += (cz - mz)/n;

@@ -40,6 +40,8 @@ def load():
     L.tgb200_scene_info.argtypes = [vp, C.POINTER(u32), C.POINTER(u32), C.POINTER(u32), C.POINTER(C.c_uint64), C.POINTER(u32)]
     L.tgb200_reset_stats.argtypes = [vp]
     L.tgb200_abort.argtypes = [vp]
+    L.tgb200_clear_abort.argtypes = [vp]
+    L.tgb200_qbvh_selftest.argtypes = [vp, u32, vp, u32, u32, C.POINTER(u32), C.POINTER(u32), C.POINTER(u32), C.POINTER(C.c_uint64)]
     L.tgb200_destroy.argtypes = [vp]; L.tgb200_destroy.restype = None
     L.tgb200_last_error.argtypes = [vp]; L.tgb200_last_error.restype = C.c_char_p
     L.tgb200_abi_version.restype = u32
@@ -136,3 +138,6 @@ class Context:
 
     def abort(self):
         self.L.tgb200_abort(self.h)
+
+    def clear_abort(self):
+        self.L.tgb200_clear_abort(self.h)
