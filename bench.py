@@ -216,6 +216,156 @@ def bench_reference(args, rank, world):
     print(json.dumps(line))
 
 
+# ---- algorithmic bytes per unit of the non-traversal kernels (16-byte records T0..T3, E, pcg) -------------
+STREAM_BYTES = {
+    # new camera path: T0..T3 (64) + E (16) + pcg (8) + order (4) written
+    "k_regen": {"bytes_per_unit": 92, "unit": "camera path started"},
+    # path-bounce: T0..T3 + pcg read (72), T0/T1/T3 + pcg written (56), NEE/MIS scratch P,N0,N1,M0,M1,D0,D1 + vis written (120)
+    "k_shade": {"bytes_per_unit": 248, "unit": "path ray shaded"},
+    # path-bounce: T1,T3,E read (48) + vis,N1,M1,D0,D1 (72) ; survivor: T0 + pcg read (24), T0..T3,E,pcg,key written (92)
+    "k_accum": {"bytes_per_unit": 236, "unit": "path ray folded"},
+}
+
+
+def _measure(ctx, args, torch, dist, rank, world, local_rank, W, H, seed, steps, warmup, spp_per_step, e2e=True):
+    """Times `steps` steps of the hot path on this rank's tile share (device-resident), then the same through the host-buffer
+    C-ABI call.  Returns a dict of raw numbers (rank-local + reduced)."""
+    import numpy as np
+    from tungsten_b200 import integrator
+    all_tiles = integrator.dice_tiles(W, H, seed)
+    my_tiles = integrator.shard_tiles(all_tiles, rank, world)
+    shares = [integrator.shard_tiles(all_tiles, r, world) for r in range(world)] if world > 1 else [my_tiles]
+    spp_step = spp_per_step*world
+    stream = torch.cuda.current_stream()
+    ctx.set_stream(stream.cuda_stream)              # renders, NCCL and the timing events share one stream
+    if world > 1:
+        max_pix = max(sum(t.w*t.h for t in sh) for sh in shares)
+        send = torch.zeros(max_pix*3, dtype=torch.float32, device="cuda")
+        recv = torch.zeros(world*max_pix*3, dtype=torch.float32, device="cuda")
+    coll_events = []
+
+    def step(i, resident=True, mean=None, count=None, time_collective=False):
+        if resident:
+            ctx.render_resident(spp_step, seed=seed, spp_begin=i*spp_step, tiles=my_tiles)
+        else:
+            ctx.render_tiles(spp_step, seed=seed, spp_begin=i*spp_step, tiles=my_tiles, mean=mean, count=count)
+        if world > 1:
+            if time_collective:
+                e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True); e0.record(stream)
+            ctx.pack_tiles(my_tiles, send.data_ptr())
+            dist.all_gather_into_tensor(recv, send)
+            if time_collective:
+                e1.record(stream); coll_events.append((e0, e1))
+
+    def timed(n_steps, first, resident, mean=None, count=None, time_collective=False):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        ev0 = torch.cuda.Event(enable_timing=True); ev1 = torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        ev0.record(stream)
+        for i in range(n_steps):
+            step(first + i, resident, mean, count, time_collective)
+        ev1.record(stream)
+        torch.cuda.synchronize()
+        wall = time.perf_counter() - t0
+        dev = ev0.elapsed_time(ev1)/1e3                       # CUDA events on the launching stream
+        mine = dev
+        if world > 1:
+            tt = torch.tensor([dev], dtype=torch.float64, device="cuda")
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            dev = float(tt.item())
+        return dev, mine, wall
+
+    ctx.clear()
+    for i in range(warmup):
+        step(i)
+    ctx.clear(); ctx.reset_stats(); ctx.set_profiling(True)
+    stop = threading.Event(); clk = []
+    th = threading.Thread(target=_clock_sampler, args=(stop, clk, local_rank), daemon=True); th.start()
+    secs, my_secs, wall = timed(steps, 0, True, time_collective=True)
+    stop.set(); th.join()
+    st = ctx.stats()
+    out = {"secs": secs, "wall": wall, "clk": clk, "spp_step": spp_step, "n_my_pix": sum(t.w*t.h for t in my_tiles), "st": st}
+    coll_ms = sum(a.elapsed_time(b) for a, b in coll_events)
+    per_rank = [my_secs*1e3, st.total_ms, st.trace_ms, st.shadow_ms, coll_ms, float(st.samples)]
+    if world > 1:
+        tt = torch.tensor([float(st.samples), float(st.rays), float(st.hits), float(st.kernel_launches)], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tt)
+        out["tot"] = [float(x) for x in tt.tolist()]
+        pr = torch.tensor(per_rank, dtype=torch.float64, device="cuda"); allpr = torch.zeros(world*len(per_rank), dtype=torch.float64, device="cuda")
+        dist.all_gather_into_tensor(allpr, pr)
+        out["per_rank"] = allpr.view(world, len(per_rank)).cpu().tolist()
+    else:
+        out["tot"] = [float(st.samples), float(st.rays), float(st.hits), float(st.kernel_launches)]
+        out["per_rank"] = [per_rank]
+
+    # ---- N > 1: the gathered image is the one-rank image (de-tile every share, compare with rank 0 rendering everything alone)
+    if world > 1:
+        ctx.set_profiling(False)
+        ctx.clear()
+        step(0)
+        torch.cuda.synchronize()
+        for r in range(world):
+            ctx.unpack_tiles(shares[r], recv.data_ptr() + 4*r*max_pix*3, spp_step)
+        got, got_cnt = ctx.read_framebuffer()
+        check = None
+        if rank == 0:
+            ctx.clear()
+            ctx.render_resident(spp_step, seed=seed, spp_begin=0, tiles=all_tiles)
+            want, want_cnt = ctx.read_framebuffer()
+            check = {"equal": bool(np.array_equal(got, want) and np.array_equal(got_cnt, want_cnt)),
+                     "what": "step 0 rendered by %d ranks, packed, all-gathered, unpacked on rank 0 vs the same %d spp of the whole frame rendered by rank 0 alone" % (world, spp_step),
+                     "pixels": int(W*H), "max_abs_diff": float(np.abs(got - want).max())}
+        out["gather_check"] = check
+
+    # ---- end to end through the C ABI with host buffers ------------------------------------------
+    if e2e:
+        ctx.set_profiling(False)
+        mean = np.zeros((H, W, 3), dtype=np.float32); count = np.zeros((H, W), dtype=np.uint32)
+        e2e_steps = max(2, min(steps, 4))
+        timed(1, 0, False, mean, count)
+        mean[:] = 0; count[:] = 0
+        ctx.reset_stats()
+        e2e_secs, _, _ = timed(e2e_steps, 0, False, mean, count)
+        e2e_samples = float(ctx.stats().samples)
+        if world > 1:
+            tt = torch.tensor([e2e_samples], dtype=torch.float64, device="cuda"); dist.all_reduce(tt); e2e_samples = float(tt.item())
+        out["e2e"] = {"value": e2e_samples/e2e_secs/1e6, "unit": "Msamples/s", "h2d_bytes_per_step": W*H*16, "d2h_bytes_per_step": W*H*16,
+                      "steps": e2e_steps}
+    ctx.set_stream(None)
+    return out
+
+
+def _roofline(st, peak, peak_src, traffic):
+    trace_gbs = (st.path_rays_traversed*ALG_BYTES_PER_QUERY/1e9)/(st.trace_ms/1e3) if st.trace_ms > 0 else 0.0
+    shadow_gbs = (st.shadow_rays_traversed*ALG_BYTES_PER_QUERY/1e9)/(st.shadow_ms/1e3) if st.shadow_ms > 0 else 0.0
+    queries_per_launch = st.path_rays_traversed/max(st.trace_launches, 1)
+    r = {"bound": "hbm", "kernel": "k_trace (closest-hit traversal of path rays: 4-ary BVH, 64-byte quantised nodes)",
+         "achieved": trace_gbs, "peak": peak, "unit": "GB/s", "frac": trace_gbs/peak,
+         "traffic": traffic.get("dram_bytes_per_launch") if traffic else None,
+         "traffic_over_algorithmic": (traffic["dram_bytes_per_launch"]/(traffic["queries_in_launch"]*ALG_BYTES_PER_QUERY)
+                                      if traffic and traffic.get("queries_in_launch") else None),
+         "traffic_source": traffic.get("source") if traffic else None,
+         "peak_source": peak_src, "alg_bytes_per_query": ALG_BYTES_PER_QUERY,
+         "queries": int(st.path_rays_traversed), "path_rays_total": int(st.path_rays), "kernel_ms": st.trace_ms, "launches": int(st.trace_launches),
+         "alg_bytes_per_launch": queries_per_launch*ALG_BYTES_PER_QUERY,
+         "mqueries_per_s": st.path_rays_traversed/st.trace_ms/1e3 if st.trace_ms > 0 else 0.0,
+         "k_shadow": {"achieved": shadow_gbs, "frac": shadow_gbs/peak, "queries": int(st.shadow_rays_traversed), "shadow_rays_total": int(st.shadow_rays), "kernel_ms": st.shadow_ms,
+                      "mqueries_per_s": st.shadow_rays_traversed/st.shadow_ms/1e3 if st.shadow_ms > 0 else 0.0},
+         "note": "software BVH traversal is ALU-issue/latency bound with an L2-resident BVH (ncu: profiles/r02_*_k_trace*); 48 B/query is the algorithmic figure of SURVEY 8d"}
+    units = {"k_regen": float(st.samples), "k_shade": float(st.path_rays), "k_accum": float(st.path_rays)}
+    ms = {"k_regen": st.regen_ms, "k_shade": st.shade_ms, "k_accum": st.accum_ms}
+    stream = {}
+    for k, v in STREAM_BYTES.items():
+        gbs = units[k]*v["bytes_per_unit"]/1e9/(ms[k]/1e3) if ms[k] > 0 else 0.0
+        stream[k] = {"achieved": gbs, "frac": gbs/peak, "kernel_ms": ms[k], "bytes_per_unit": v["bytes_per_unit"], "unit_of_work": v["unit"], "units": units[k]}
+    stream["note"] = ("bytes per unit are upper bounds of what the kernel moves for one unit (conditional records counted in full); ncu shows these kernels "
+                      "issue bound, not DRAM bound (k_accum issues 0.74 inst/cycle/SMSP: 16-box BVH cut + analytic primitives per surviving ray)")
+    other = {"k_shadow_prep_ms": st.prep_ms, "sort_ms": st.sort_ms, "iterations": int(st.iterations)}
+    return r, stream, other
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -226,6 +376,7 @@ def main():
     ap.add_argument("--ref-spp", type=int, default=0, help="samples per pixel of one reference step (0 = calibrate to --ref-seconds)")
     ap.add_argument("--ref-seconds", type=float, default=6.0, help="target render time of one reference step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-other-configs", action="store_true", help="skip the short C2/C3/C4 measurements added to the C1 line")
     ap.add_argument("--config", default="c1", choices=sorted(CONFIGS))
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -241,7 +392,7 @@ def main():
 
     import numpy as np
     import torch
-    from tungsten_b200 import scene, lib, abi, integrator
+    from tungsten_b200 import scene, lib
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the CUDA library is the only implementation")
     torch.cuda.set_device(local_rank)
@@ -250,94 +401,55 @@ def main():
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
-    scene_path = make_scene(1024, args.config) if rank == 0 else None
-    if world > 1:
-        dist.barrier()
-        scene_path = make_scene(1024, args.config)
-    fs = scene.load_scene(scene_path)
-    ctx = lib.Context(fs, device=local_rank)
-    info = ctx.scene_info()
-    seed = 0xBA5EBA11
-    all_tiles = integrator.dice_tiles(W, H, seed)
-    my_tiles = integrator.shard_tiles(all_tiles, rank, world)
-    spp_step = args.spp_per_step*world
-    n_my_pix = sum(t.w*t.h for t in my_tiles)
-
-    # multi-GPU: one all-gather of the tile-major framebuffer (the only collective on the path)
-    if world > 1:
-        max_pix = max(sum(t.w*t.h for t in integrator.shard_tiles(all_tiles, r, world)) for r in range(world))
-        send = torch.zeros(max_pix*3, dtype=torch.float32, device="cuda")
-        recv = torch.zeros(world*max_pix*3, dtype=torch.float32, device="cuda")
-
-    def step(i, resident=True, mean=None, count=None):
-        if resident:
-            ctx.render_resident(spp_step, seed=seed, spp_begin=i*spp_step, tiles=my_tiles)
-        else:
-            ctx.render_tiles(spp_step, seed=seed, spp_begin=i*spp_step, tiles=my_tiles, mean=mean, count=count)
-        if world > 1:
-            ctx.pack_tiles(my_tiles, send.data_ptr())
-            dist.all_gather_into_tensor(recv, send)
-
-    def timed(n_steps, first, resident, mean=None, count=None):
+    def load(config):
+        scene_path = make_scene(1024, config) if rank == 0 else None
         if world > 1:
             dist.barrier()
-        torch.cuda.synchronize()
+            scene_path = make_scene(1024, config)
         t0 = time.perf_counter()
-        for i in range(n_steps):
-            step(first + i, resident, mean, count)
-        torch.cuda.synchronize()
-        t = time.perf_counter() - t0
-        if world > 1:
-            tt = torch.tensor([t], dtype=torch.float64, device="cuda")
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-            t = float(tt.item())
-        return t
+        fs = scene.load_scene(scene_path)
+        t1 = time.perf_counter()
+        ctx = lib.Context(fs, device=local_rank)
+        return scene_path, ctx, {"flatten_s": t1 - t0, "tgb200_create_s": time.perf_counter() - t1}
 
-    # ---- device-resident measurement -----------------------------------------------------------
-    ctx.clear()
-    for i in range(args.warmup):
-        step(i)
-    ctx.clear(); ctx.reset_stats(); ctx.set_profiling(True)
-    stop = threading.Event(); clk = []
-    th = threading.Thread(target=_clock_sampler, args=(stop, clk, local_rank), daemon=True); th.start()
-    wall = timed(args.steps, 0, True)
-    stop.set(); th.join()
-    st = ctx.stats()
-    dev_ms = st.total_ms
-    if world > 1:
-        tt = torch.tensor([float(st.samples), float(st.rays), float(st.hits), float(st.kernel_launches)], dtype=torch.float64, device="cuda")
-        dist.all_reduce(tt)
-        tot_samples, tot_rays, tot_hits, tot_launches = [float(x) for x in tt.tolist()]
-        de = torch.tensor([dev_ms], dtype=torch.float64, device="cuda"); dist.all_reduce(de, op=dist.ReduceOp.MAX)
-        dev_ms_max = float(de.item())
-    else:
-        tot_samples, tot_rays, tot_hits, tot_launches = float(st.samples), float(st.rays), float(st.hits), float(st.kernel_launches)
-        dev_ms_max = dev_ms
-    value = tot_samples/wall/1e6
+    seed = 0xBA5EBA11
+    scene_path, ctx, build_times = load(args.config)
+    info = ctx.scene_info()
+    m = _measure(ctx, args, torch, dist, rank, world, local_rank, W, H, seed, args.steps, args.warmup, args.spp_per_step)
+    st = m["st"]
+    tot_samples, tot_rays, tot_hits, tot_launches = m["tot"]
+    value = tot_samples/m["secs"]/1e6
     peak, peak_src = hbm_peak()
-    trace_gbs = (st.path_rays_traversed*ALG_BYTES_PER_QUERY/1e9)/(st.trace_ms/1e3) if st.trace_ms > 0 else 0.0
-    shadow_gbs = (st.shadow_rays_traversed*ALG_BYTES_PER_QUERY/1e9)/(st.shadow_ms/1e3) if st.shadow_ms > 0 else 0.0
     traffic = None
     tp = os.path.join(ROOT, "profiles", "k_trace_dram_bytes_per_launch.json")
     if os.path.exists(tp):
         try:
-            traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+            traffic = json.load(open(tp))
         except Exception:
             traffic = None
+    roof, stream, other = _roofline(st, peak, peak_src, traffic)
+    ctx.close()
 
-    # ---- end to end through the C ABI with host buffers ------------------------------------------
-    ctx.set_profiling(False)
-    mean = np.zeros((H, W, 3), dtype=np.float32); count = np.zeros((H, W), dtype=np.uint32)
-    e2e_steps = max(2, min(args.steps, 4))
-    timed(1, 0, False, mean, count)
-    mean[:] = 0; count[:] = 0
-    ctx.reset_stats()
-    e2e_wall = timed(e2e_steps, 0, False, mean, count)
-    e2e_samples = float(ctx.stats().samples)
-    if world > 1:
-        tt = torch.tensor([e2e_samples], dtype=torch.float64, device="cuda"); dist.all_reduce(tt); e2e_samples = float(tt.item())
-    e2e_value = e2e_samples/e2e_wall/1e6
-    fb_bytes = W*H*(12 + 4)
+    # ---- the other BASELINE.json workloads, short runs on this GPU (one line per config is `bench.py --config cN`) -----------
+    others = None
+    if world == 1 and args.config == "c1" and not args.no_other_configs:
+        others = {}
+        for cfg in ("c2", "c3", "c4"):
+            try:
+                W, H = CONFIGS[cfg]["res"]
+                _, c2, bt = load(cfg)
+                i2 = c2.scene_info()
+                mm = _measure(c2, args, torch, dist, rank, world, local_rank, W, H, seed, 3, 3, 8)
+                s2 = mm["st"]
+                others[cfg] = {"workload": CONFIGS[cfg]["label"], "value": mm["tot"][0]/mm["secs"]/1e6, "unit": "Msamples/s", "e2e": mm["e2e"]["value"],
+                               "steps": 3, "warmup": 3, "spp_per_step": 8, "triangles": i2["n_tris"], "bvh_nodes": i2["n_nodes"],
+                               "mrays_per_s": mm["tot"][1]/mm["secs"]/1e6,
+                               "k_trace_mqueries_per_s": s2.path_rays_traversed/s2.trace_ms/1e3 if s2.trace_ms > 0 else 0.0,
+                               "tgb200_create_s": bt["tgb200_create_s"]}
+                c2.close()
+            except Exception as e:                                   # a side measurement must not lose the headline line
+                others[cfg] = {"error": str(e)[:200]}
+        W, H = CONFIGS[args.config]["res"]
 
     if rank == 0:
         cpu = None
@@ -352,33 +464,37 @@ def main():
                            "sample": "%d spp x %dx%d of the same scene rendered in %.2f s by oracle/_ref/tungsten -t %d ('Render time': excludes "
                                      "scene load + BVH build, as the GPU arm excludes tgb200_create)" % (spp_c, W, H, r[1], host["usable"]),
                            "host": host}
+        pr = m["per_rank"]
         line = {
             "metric": "Msamples/sec (paths x spp)", "value": value, "unit": "Msamples/s", "n_gpus": world,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3*wall/args.steps,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3*m["secs"]/args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": CONFIGS[args.config]["label"] + ", %d spp per step (x%d steps = %d spp)" % (spp_step, args.steps, spp_step*args.steps),
-                       "tiles": "16x16, round-robin over %d rank(s)" % world, "paths_in_flight": info["capacity"],
+            "config": {"workload": CONFIGS[args.config]["label"],
+                       "step": "%d spp of the frame per step (x%d steps = %d spp)" % (m["spp_step"], args.steps, m["spp_step"]*args.steps),
+                       "tiles": "16x16, dealt to %d rank(s) in Morton order of the tile grid" % world, "paths_in_flight": info["capacity"],
                        "triangles": info["n_tris"], "bvh_nodes": info["n_nodes"], "geom_bytes": info["geom_bytes"],
-                       "l2": "per-batch path state (%.0f MB) and geometry exceed the 126 MB L2; no explicit flush" % (info["capacity"]*230/1e6)},
-            "mrays_per_s": tot_rays/wall/1e6, "mray_hits_per_s": tot_hits/wall/1e6,
-            "device_ms": dev_ms_max, "gpu_launches": int(tot_launches),
-            "e2e": {"value": e2e_value, "unit": "Msamples/s", "h2d_bytes_per_step": fb_bytes, "d2h_bytes_per_step": fb_bytes,
-                    "steps": e2e_steps},
-            "roofline": {"bound": "hbm", "kernel": "k_trace (closest-hit 4-ary BVH traversal of path rays)",
-                         "achieved": trace_gbs, "peak": peak, "unit": "GB/s", "frac": trace_gbs/peak, "traffic": traffic,
-                         "peak_source": peak_src, "alg_bytes_per_query": ALG_BYTES_PER_QUERY,
-                         "queries": int(st.path_rays_traversed), "path_rays_total": int(st.path_rays), "kernel_ms": st.trace_ms, "launches": int(st.trace_launches),
-                         "mqueries_per_s": st.path_rays_traversed/st.trace_ms/1e3 if st.trace_ms > 0 else 0.0,
-                         "k_shadow": {"achieved": shadow_gbs, "frac": shadow_gbs/peak, "queries": int(st.shadow_rays_traversed), "shadow_rays_total": int(st.shadow_rays), "kernel_ms": st.shadow_ms},
-                         "note": "traversal is latency/divergence bound with an L2-resident BVH; see DESIGN.md section 6"},
+                       "l2": "per-batch path state (%.0f MB) and geometry exceed the 126 MB L2; no explicit flush" % (info["capacity"]*344/1e6)},
+            "timing": "CUDA events on the stream the kernels (and the all-gather) are launched on, max over ranks; wall clock of the same region %.3f s" % m["wall"],
+            "mrays_per_s": tot_rays/m["secs"]/1e6, "mray_hits_per_s": tot_hits/m["secs"]/1e6,
+            "device_ms": max(p[1] for p in pr), "gpu_launches": int(tot_launches),
+            "ranks": {"step_ms_min": min(p[0] for p in pr)/args.steps, "step_ms_max": max(p[0] for p in pr)/args.steps,
+                      "device_ms_min": min(p[1] for p in pr), "device_ms_max": max(p[1] for p in pr),
+                      "k_trace_ms_min": min(p[2] for p in pr), "k_trace_ms_max": max(p[2] for p in pr),
+                      "collective_ms_per_step_max": max(p[4] for p in pr)/args.steps,
+                      "samples_min": min(p[5] for p in pr), "samples_max": max(p[5] for p in pr)},
+            "gather_check": m.get("gather_check"),
+            "e2e": m["e2e"],
+            "roofline": roof, "roofline_streaming": stream, "loop": other,
+            "setup": dict(build_times, note="scene flattening and tgb200_create (host SAH build of the BVH + upload) are outside the timed region, as the "
+                                            "reference's 'Render time' excludes its scene load and Embree build"),
+            "other_configs": others,
             "cpu_baseline": cpu,
-            "clocks": _summarise_clocks(clk),
+            "clocks": _summarise_clocks(m["clk"]),
         }
         print(json.dumps(line))
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
-    ctx.close()
 
 
 if __name__ == "__main__":

@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define TGB200_ABI_VERSION 2
+#define TGB200_ABI_VERSION 3
 
 /* ---- return codes -------------------------------------------------------------------------- */
 enum {
@@ -167,10 +167,13 @@ typedef struct tgb_stats {
     double   total_ms;          /* CUDA-event time of the whole device section                      */
     uint64_t path_rays;         /* queries issued by k_trace (primary + continuation)               */
     uint64_t shadow_rays;       /* queries issued by k_shadow (NEE + MIS)                           */
-    double   shadow_ms;         /* CUDA-event time inside k_shadow, profiling mode only             */
+    double   shadow_ms;         /* CUDA-event time inside k_shadow_bvh, profiling mode only         */
     uint64_t shadow_launches;
     uint64_t path_rays_traversed;    /* path rays that reached k_trace (the rest miss the BVH's top-level cut) */
     uint64_t shadow_rays_traversed;  /* queries that reached k_shadow_bvh (not resolved by k_shadow_prep)         */
+    /* profiling mode only: CUDA-event time inside the other kernels of the wavefront loop, and its iteration count */
+    double   regen_ms, shade_ms, prep_ms, accum_ms, sort_ms;
+    uint64_t iterations;
 } tgb_stats;
 
 typedef struct tgb_ctx tgb_ctx;
@@ -199,6 +202,26 @@ int tgb200_read_framebuffer(tgb_ctx *ctx, float *rgb_mean, uint32_t *count);
 /* Device address of the resident fp32 RGB framebuffer (w*h*3) for zero-copy hand-off to NCCL.       */
 int tgb200_framebuffer_device_ptr(tgb_ctx *ctx, void **rgb_mean_dev, uint64_t *n_bytes);
 
+int tgb200_write_framebuffer(tgb_ctx *ctx, const float *rgb_mean, const uint32_t *count);   /* resume: OutputBuffer -> device */
+
+/* ---- adaptive sampling (integrators/path_tracer/PathTraceIntegrator.cpp:44-156, SampleRecord.hpp:11-66) ----------------
+ * One record per 4x4 pixel block (PathTraceIntegrator::VarianceTileSize), row-major over ceil(w/4) x ceil(h/4): the
+ * reference's SampleRecord, field for field (it is also what saveState/loadState stream, SampleRecord.hpp:24-42).        */
+typedef struct tgb_sample_record {
+    uint32_t sample_count, next_sample_count, sample_index;
+    float    adaptive_weight, mean, running_variance;
+} tgb_sample_record;
+/* Host only, no GPU: PathTraceIntegrator::generateWork -- advance the blocks' sample indices and decide every block's sample
+ * count for the step [current_spp, next_spp): uniform, or (adaptive_sampling and current_spp >= 16) the 95th-percentile
+ * clamp + dilation + stochastic distribution of the reference, drawing from the integrator's UniformSampler whose 64-bit
+ * state is *sampler_state (= the stream that produced the tile seeds).  Returns 1 = render the step, 0 = nothing to do.    */
+int tgb200_generate_work(tgb_sample_record *records, uint32_t res_x, uint32_t res_y, uint32_t current_spp, uint32_t next_spp,
+                         int adaptive_sampling, uint64_t *sampler_state);
+/* Render one step with per-block sample counts / sample indices taken from `records` (host, in/out): the framebuffer stays
+ * resident (tgb200_read_framebuffer), the records come back with sample_count / mean / running_variance updated by every
+ * sample's luminance in the reference's order.  Replaces renderTile's per-block bookkeeping (PathTraceIntegrator.cpp:136-156). */
+int tgb200_render_adaptive(tgb_ctx *ctx, const tgb_tile *tiles, uint32_t n_tiles, uint32_t seed, tgb_sample_record *records);
+
 /* Multi-GPU hand-off: pack the resident pixels of `tiles` tile-major (3 floats per
  * pixel, tiles in list order, rows top-down inside a tile) into a DEVICE buffer -- the send buffer of the
  * single all-gather on this path -- and the inverse (de-tile a received buffer into the resident
@@ -211,8 +234,11 @@ int tgb200_unpack_tiles(tgb_ctx *ctx, const tgb_tile *tiles, uint32_t n_tiles, c
 int tgb200_trace_closest(tgb_ctx *ctx, const tgb_ray *rays, tgb_hit *hits, uint32_t n);
 
 int  tgb200_get_stats(tgb_ctx *ctx, tgb_stats *out);
-/* Time every traversal-kernel launch with CUDA events on the render stream (fills trace_ms).        */
+/* Time every kernel of the wavefront loop with CUDA events on the render stream (fills the *_ms fields of tgb_stats). */
 int  tgb200_set_profiling(tgb_ctx *ctx, int enable);
+/* Run the context's work on the caller's CUDA stream (a cudaStream_t; NULL = back to the context's own stream), so that a
+ * caller's events and collectives on that stream order with the renders.                                           */
+int  tgb200_set_stream(tgb_ctx *ctx, void *cuda_stream);
 /* Size of what was built: triangles, BVH nodes, BVH depth, bytes of nodes+triangle records, and the
  * wavefront capacity (paths in flight).  Any pointer may be NULL.                                   */
 int  tgb200_scene_info(tgb_ctx *ctx, uint32_t *n_tris, uint32_t *n_nodes, uint32_t *bvh_depth,

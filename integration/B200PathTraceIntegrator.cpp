@@ -298,7 +298,9 @@ struct Flattener
 B200PathTraceIntegrator::B200PathTraceIntegrator()
 : Integrator(),
   _ctx(nullptr),
-  _seed(0xBA5EBA11)
+  _seed(0xBA5EBA11),
+  _sampler(0xBA5EBA11),
+  _needsFramebufferPush(false)
 {
 }
 
@@ -320,8 +322,54 @@ rapidjson::Value B200PathTraceIntegrator::toJson(Allocator &allocator) const
     return v;
 }
 
-void B200PathTraceIntegrator::saveState(OutputStreamHandle &/*out*/) {}
-void B200PathTraceIntegrator::loadState(InputStreamHandle &/*in*/) {}
+// Resume files (Integrator::saveRenderResumeData / resumeRender, Integrator.cpp:108-162): the block records field by field
+// as SampleRecord::saveState streams them (SampleRecord.hpp:24-42), then the integrator's sampler state.  (The reference also
+// streams one sampler per tile: its supplemental PCG runs on across a tile's pixels; under the per-path reseed contract a
+// tile's sampler is its seed, which diceTiles re-derives from the render seed.)
+void B200PathTraceIntegrator::saveState(OutputStreamHandle &out)
+{
+    for (const tgb_sample_record &r : _samples) {
+        FileUtils::streamWrite(out, r.sample_count);
+        FileUtils::streamWrite(out, r.next_sample_count);
+        FileUtils::streamWrite(out, r.sample_index);
+        FileUtils::streamWrite(out, r.adaptive_weight);
+        FileUtils::streamWrite(out, r.mean);
+        FileUtils::streamWrite(out, r.running_variance);
+    }
+    _sampler.saveState(out);
+}
+
+void B200PathTraceIntegrator::loadState(InputStreamHandle &in)
+{
+    for (tgb_sample_record &r : _samples) {
+        FileUtils::streamRead(in, r.sample_count);
+        FileUtils::streamRead(in, r.next_sample_count);
+        FileUtils::streamRead(in, r.sample_index);
+        FileUtils::streamRead(in, r.adaptive_weight);
+        FileUtils::streamRead(in, r.mean);
+        FileUtils::streamRead(in, r.running_variance);
+    }
+    _sampler.loadState(in);
+    _needsFramebufferPush = true;      // resumeRender() has just deserialised the camera's output buffers (Integrator.cpp:152)
+}
+
+bool B200PathTraceIntegrator::supportsResumeRender() const
+{
+    return true;
+}
+
+// PathTraceIntegrator::generateWork (PathTraceIntegrator.cpp:110-134) through the library's host-side implementation
+bool B200PathTraceIntegrator::generateWork()
+{
+    Vec2u res = _scene->cam().resolution();
+    uint64_t state = _sampler.state();
+    int rc = tgb200_generate_work(_samples.data(), res.x(), res.y(), _currentSpp, _nextSpp,
+            _scene->rendererSettings().useAdaptiveSampling() ? 1 : 0, &state);
+    _sampler = UniformSampler(state);
+    if (rc < 0)
+        FAIL("b200_path_tracer: tgb200_generate_work failed");
+    return rc == 1;
+}
 
 void B200PathTraceIntegrator::prepareForRender(TraceableScene &scene, uint32 seed)
 {
@@ -331,8 +379,8 @@ void B200PathTraceIntegrator::prepareForRender(TraceableScene &scene, uint32 see
     advanceSpp();
     scene.cam().requestColorBuffer();
 
-    if (scene.rendererSettings().useAdaptiveSampling() || !scene.rendererSettings().useSobol())
-        FAIL("b200_path_tracer needs renderer.adaptive_sampling=false and renderer.stratified_sampler=true");
+    if (!scene.rendererSettings().useSobol())
+        FAIL("b200_path_tracer needs renderer.stratified_sampler=true");
     if (!scene.media().empty() || scene.cam().medium())
         FAIL("b200_path_tracer: participating media are outside the hot path");
     // The framebuffer hand-off (uploadFramebuffer) fills ONE plain colour buffer: running mean + sample counts.  Feature
@@ -384,6 +432,18 @@ void B200PathTraceIntegrator::prepareForRender(TraceableScene &scene, uint32 see
     if (tgb200_create(&desc, &_ctx) != TGB_OK)
         FAIL("b200_path_tracer: %s", tgb200_last_error(nullptr));
     tgb200_clear_framebuffer(_ctx);
+
+    // PathTraceIntegrator::prepareForRender (PathTraceIntegrator.cpp:184-201): _sampler is seeded with hash32(seed) and
+    // diceTiles draws one value per 16x16 tile (the library derives the same tile seeds from `seed`); what follows in the
+    // stream feeds distributeAdaptiveSamples.
+    Vec2u res = cam->resolution();
+    _sampler = UniformSampler(MathUtil::hash32(seed));
+    for (uint32 y = 0; y < res.y(); y += 16)
+        for (uint32 x = 0; x < res.x(); x += 16)
+            _sampler.nextI();
+    _samples.assign(size_t((res.x() + 3)/4)*((res.y() + 3)/4), tgb_sample_record());
+    std::memset(_samples.data(), 0, _samples.size()*sizeof(tgb_sample_record));
+    _needsFramebufferPush = false;
 }
 
 void B200PathTraceIntegrator::teardownAfterRender()
@@ -410,18 +470,41 @@ void B200PathTraceIntegrator::uploadFramebuffer()
     _scene->cam().colorBuffer()->deserialize(in);
 }
 
+// Camera::colorBuffer() -> GPU (after a resume): OutputBuffer::serialize is the mirror of deserialize
+void B200PathTraceIntegrator::pushFramebuffer()
+{
+    Vec2u res = _scene->cam().resolution();
+    size_t n = size_t(res.x())*res.y();
+    std::ostringstream *os = new std::ostringstream(std::ios_base::out | std::ios_base::binary);
+    OutputStreamHandle out(os);
+    _scene->cam().colorBuffer()->serialize(out);
+    std::string blob = os->str();
+    if (blob.size() != n*(sizeof(Vec3f) + sizeof(uint32)))
+        FAIL("b200_path_tracer: unexpected colour buffer layout in the resume data");
+    if (tgb200_write_framebuffer(_ctx, reinterpret_cast<const float *>(blob.data()),
+            reinterpret_cast<const uint32_t *>(blob.data() + n*sizeof(Vec3f))) != TGB_OK)
+        FAIL("b200_path_tracer: %s", tgb200_last_error(_ctx));
+}
+
 void B200PathTraceIntegrator::startRender(std::function<void()> completionCallback)
 {
-    if (done()) {
+    if (done() || !generateWork()) {
         _currentSpp = _nextSpp;
         advanceSpp();
         completionCallback();
         return;
     }
+    if (_needsFramebufferPush) {
+        pushFramebuffer();
+        _needsFramebufferPush = false;
+    }
     uint32 begin = _currentSpp, count = _nextSpp - _currentSpp;
+    const bool adaptive = _scene->rendererSettings().useAdaptiveSampling();
     tgb200_clear_abort(_ctx);          // an abortRender() from now on cancels THIS step, even before the worker reaches the library
-    _worker.reset(new std::thread([this, begin, count, completionCallback]() {
-        int rc = tgb200_render_resident(_ctx, nullptr, 0, _seed, begin, count);
+    _worker.reset(new std::thread([this, begin, count, adaptive, completionCallback]() {
+        // adaptive scenes: per-block sample counts from generateWork, SampleRecord statistics updated on the device
+        int rc = adaptive ? tgb200_render_adaptive(_ctx, nullptr, 0, _seed, _samples.data())
+                          : tgb200_render_resident(_ctx, nullptr, 0, _seed, begin, count);
         if (rc == TGB_OK) {
             uploadFramebuffer();
             _currentSpp = _nextSpp;

@@ -10,13 +10,15 @@
 
 #include "integrators/Integrator.hpp"
 #include "integrators/path_tracer/PathTracerSettings.hpp"
+#include "sampling/UniformSampler.hpp"
+
+#include "tgb200.h"
 
 #include <atomic>
 #include <memory>
 #include <string>
 #include <thread>
-
-struct tgb_ctx;
+#include <vector>
 
 namespace Tungsten {
 
@@ -27,8 +29,15 @@ class B200PathTraceIntegrator : public Integrator
     uint32 _seed;
     std::unique_ptr<std::thread> _worker;
     std::string _error;
+    // PathTraceIntegrator::_sampler / _samples (PathTraceIntegrator.hpp): the integrator's own PCG stream (tile seeds, adaptive
+    // sample distribution) and one SampleRecord per 4x4 pixel block
+    UniformSampler _sampler;
+    std::vector<tgb_sample_record> _samples;
+    bool _needsFramebufferPush;      // after loadState(): the camera's colour buffer has to go to the device first
 
     void uploadFramebuffer();
+    void pushFramebuffer();
+    bool generateWork();
 
 protected:
     virtual void saveState(OutputStreamHandle &out) override;
@@ -40,6 +49,8 @@ public:
 
     virtual void fromJson(JsonPtr value, const Scene &scene) override;
     virtual rapidjson::Value toJson(Allocator &allocator) const override;
+
+    virtual bool supportsResumeRender() const override;
 
     virtual void prepareForRender(TraceableScene &scene, uint32 seed) override;
     virtual void teardownAfterRender() override;

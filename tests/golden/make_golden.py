@@ -8,10 +8,12 @@ needs /root/reference and the binaries built by `make -C oracle/ref`).
                       draws each through its SobolPathSampler), from a host program linked against the reference's objects
   kat_lights.json     sampleDirect / intersect / directPdf / evalDirect of its Quad, TriangleMesh and InfiniteSphere (+ BitmapTexture
                       importance map) classes
+  kat_instances.json  Instance transforms: fromMatrix / quaternion composition / pos + rot*p through its Mat4f and QuaternionF classes
   kat_curves.json     HairBcsdf eval / pdf / sample and Curves::intersect (400 rays at 6 strands) of its classes
   <scene>/            scene JSON + .wo3 written by tungsten_b200.synth, plus
   <scene>/ref_pathseed.pfm   framebuffer of oracle/_ref/tungsten_pathseed (per-path reseed contract)
   <scene>/ref_stock.pfm      framebuffer of the UNMODIFIED reference binary
+  cornell_adaptive/          the same with renderer.adaptive_sampling = true, 48 spp in three 16-spp steps
 
 The fixtures are small (64x64) so that the CPU test-suite stays fast; they travel to the GPU box with the
 repository, /root/reference does not.
@@ -380,6 +382,61 @@ int main() {
 """
 
 
+KAT_INSTANCE_CPP = r'''
+// Instance transforms through the reference's own classes: Instance::fromJson (Instance.cpp:80-86) turns an instance matrix into
+// (extractTranslationVec, QuaternionF::fromMatrix(extractRotation)); prepareForRender (:392-400) composes it with the
+// primitive's transform (_transform*pos, rot*instanceRot); intersectionInfo (:325-334) maps master-space points / normals to
+// the world with pos + rot*p, rot*n.
+#include <cstdio>
+#include "math/Mat4f.hpp"
+#include "math/Quaternion.hpp"
+#include "sampling/UniformSampler.hpp"
+using namespace Tungsten;
+static unsigned bits(float v) { union { float f; unsigned u; } c; c.f = v; return c.u; }
+static void pv(const char *k, const float *v, int n, bool last = false) { printf("\"%s\": [", k); for (int i = 0; i < n; ++i) printf("%u%s", bits(v[i]), i + 1 < n ? ", " : ""); printf("]%s", last ? "" : ", "); }
+int main() {
+    UniformSampler rnd(0x5EED1234u);
+    printf("{\"cases\": [\n");
+    const int N = 32;
+    for (int c = 0; c < N; ++c) {
+        Vec3f ang(rnd.next1D()*360.0f - 180.0f, rnd.next1D()*360.0f - 180.0f, rnd.next1D()*360.0f - 180.0f);
+        Vec3f ang2(rnd.next1D()*360.0f - 180.0f, rnd.next1D()*360.0f - 180.0f, rnd.next1D()*360.0f - 180.0f);
+        if (c < 4) { ang = Vec3f(0.0f, 90.0f*c, 0.0f); ang2 = Vec3f(180.0f, 0.0f, 90.0f*c); }          // exercise every fromMatrix branch
+        Vec3f tr(rnd.next1D()*40.0f - 20.0f, rnd.next1D()*4.0f, rnd.next1D()*40.0f - 20.0f);
+        Vec3f tr2(rnd.next1D()*10.0f - 5.0f, rnd.next1D()*2.0f, rnd.next1D()*10.0f - 5.0f);
+        float sc = c % 3 == 0 ? 1.0f : 0.5f + rnd.next1D();
+        Mat4f inst = Mat4f::translate(tr)*Mat4f::rotYXZ(ang);                       // one entry of "instances"
+        Mat4f prim = Mat4f::translate(tr2)*Mat4f::rotYXZ(ang2)*Mat4f::scale(Vec3f(sc));   // the Instance primitive's own transform
+        Vec3f ipos = inst.extractTranslationVec();
+        QuaternionF irot = QuaternionF::fromMatrix(inst.extractRotation());
+        QuaternionF prot = QuaternionF::fromMatrix(prim.extractRotation());
+        Vec3f wpos = prim*ipos;
+        QuaternionF wrot = prot*irot;
+        float m1[16], m2[16];
+        for (int i = 0; i < 16; ++i) { m1[i] = inst[i]; m2[i] = prim[i]; }
+        printf("{"); pv("inst", m1, 16); pv("prim", m2, 16);
+        float q[4] = {irot[0], irot[1], irot[2], irot[3]}; pv("irot", q, 4);
+        float qw[4] = {wrot[0], wrot[1], wrot[2], wrot[3]}; pv("wrot", qw, 4);
+        float wp[3] = {wpos.x(), wpos.y(), wpos.z()}; pv("wpos", wp, 3);
+        float pts[4*3], outp[4*3], outn[4*3];
+        for (int k = 0; k < 4; ++k) {
+            Vec3f p(rnd.next1D()*2.0f - 1.0f, rnd.next1D()*3.0f, rnd.next1D()*2.0f - 1.0f);
+            Vec3f w = wpos + wrot*p, n = wrot*p;
+            for (int a = 0; a < 3; ++a) { pts[3*k + a] = p[a]; outp[3*k + a] = w[a]; outn[3*k + a] = n[a]; }
+        }
+        pv("p", pts, 12); pv("world_p", outp, 12); pv("world_n", outn, 12, true);
+        printf("}%s\n", c + 1 < N ? "," : "");
+    }
+    printf("]}\n");
+}
+'''
+
+
+def make_kat_instances():
+    """Instance transforms (quaternion + translation) through the reference's Mat4f / QuaternionF -> kat_instances.json."""
+    _build_and_run_kat(KAT_INSTANCE_CPP, "kat_instances", "kat_instances.json")
+
+
 def make_kat_lights():
     """Known answers of sampleDirect / intersect / directPdf / evalDirect of the reference's Quad, TriangleMesh and
     InfiniteSphere(+BitmapTexture importance map) classes -> kat_lights.json."""
@@ -430,6 +487,11 @@ def make_scenes():
     scenes["curves_plastic"] = synth.hair_scene(os.path.join(HERE, "curves_plastic"), "scene", n_curves=300, res=res, spp=spp, mode="cylinder",
                                                 bsdf={"type": "rough_plastic", "albedo": [0.6, 0.4, 0.2], "roughness": 0.2}, thickness=0.015,
                                                 taper=True, subsample=0.3)
+    # adaptive sampling (PathTraceIntegrator::generateWork): three 16-spp steps, the 2nd and 3rd distributed by the blocks' error
+    ad = synth.cornell_box(res=res, spp=48)
+    ad["renderer"].update(adaptive_sampling=True, spp_step=16)
+    d = os.path.join(HERE, "cornell_adaptive"); os.makedirs(d, exist_ok=True)
+    scenes["cornell_adaptive"] = synth.write_scene(d, "scene", ad)
     for name, path in scenes.items():
         d = os.path.dirname(path)
         for exe, tag in (("tungsten_pathseed", "ref_pathseed"), ("tungsten", "ref_stock")):
@@ -445,4 +507,5 @@ if __name__ == "__main__":
     make_kat_curves()
     make_kat_bsdfs()
     make_kat_lights()
+    make_kat_instances()
     make_scenes()

@@ -38,3 +38,48 @@ def test_reference_binary_with_b200_integrator(name, tmp_path):
     close = float((d <= 1e-5*(1.0 + np.abs(want).max(axis=2))).mean())
     print(name, "exact %.4f close %.4f" % (float((d == 0).mean()), close))
     assert close >= (0.97 if name in ("hair", "curves_plastic") else 0.985)     # curve scenes: see tests/test_gpu_parity.py::test_curves_and_hair
+
+
+def _run_dropin(tmp_path, js, name="b200.json", expect=None):
+    json.dump(js, open(tmp_path/name, "w"))
+    out = subprocess.run([EXE, "-t", "2", "-d", str(tmp_path/"out"), str(tmp_path/name)], stdout=subprocess.PIPE,
+                         stderr=subprocess.STDOUT, text=True)
+    assert out.returncode == 0, out.stdout
+    if expect:
+        assert expect in out.stdout, out.stdout
+    return scene.load_pfm(str(tmp_path/"out"/"out.pfm")), out.stdout
+
+
+@pytest.mark.skipif(not os.path.exists(EXE), reason="drop-in binary not built (needs /root/reference at build time)")
+def test_dropin_adaptive_sampling_as_shipped_scenes_use_it(tmp_path):
+    """renderer.adaptive_sampling = true (the as-shipped setting of data/materialtest and the example scenes) through the
+    literal drop-in: generateWork + per-block records in the adapter, tgb200_render_adaptive underneath, vs the reference
+    binary's own adaptive render of the same scene (tests/golden/cornell_adaptive)."""
+    src = os.path.join(G, "cornell_adaptive")
+    js = json.load(open(os.path.join(src, "scene.json")))
+    assert js["renderer"]["adaptive_sampling"] is True
+    js["integrator"]["type"] = "b200_path_tracer"
+    got, log = _run_dropin(tmp_path, js, expect="Completed 48/48 spp")
+    want = scene.load_pfm(os.path.join(src, "ref_pathseed.pfm"))
+    d = np.abs(got - want).max(axis=2)
+    close = float((d <= 1e-5*(1.0 + np.abs(want).max(axis=2))).mean())
+    print("adaptive drop-in: exact %.4f close %.4f" % (float((d == 0).mean()), close))
+    assert close >= 0.97
+
+
+@pytest.mark.skipif(not os.path.exists(EXE), reason="drop-in binary not built (needs /root/reference at build time)")
+def test_dropin_resume_render_continues_bit_exactly(tmp_path):
+    """Integrator::saveRenderResumeData / resumeRender (Integrator.cpp:108-162) with the adapter's saveState/loadState: a render
+    stopped after 16 spp and resumed to 48 spp (adaptive: block records + sampler state + framebuffer travel through the
+    resume file and back to the device) equals the uninterrupted 48-spp render bit for bit."""
+    src = os.path.join(G, "cornell_adaptive")
+    js = json.load(open(os.path.join(src, "scene.json")))
+    js["integrator"]["type"] = "b200_path_tracer"
+    js["renderer"]["enable_resume_render"] = True
+    whole, _ = _run_dropin(tmp_path, dict(js, renderer=dict(js["renderer"], enable_resume_render=False)), name="whole.json")
+    part = dict(js, renderer=dict(js["renderer"], spp=16))
+    _run_dropin(tmp_path, part, name="scene.json", expect="Completed 16/16 spp")
+    assert os.path.exists(tmp_path/"out"/"TungstenRenderState.dat")
+    resumed, log = _run_dropin(tmp_path, js, name="scene.json", expect="Resume successful")
+    assert "Completed 48/48 spp" in log
+    assert np.array_equal(resumed, whole)

@@ -270,3 +270,35 @@ def test_abort_returns_aborted_code():
     assert e.value.code == abi.TGB_ERR_ABORTED
     ctx.render_resident(1)                                    # ... exactly once
     ctx.close()
+
+
+def test_adaptive_sampling_against_reference_binary():
+    """renderer.adaptive_sampling = true through the Integrator twin: tgb200_generate_work + tgb200_render_adaptive (per-block
+    sample counts, Welford luminance statistics folded on the device in the reference's order) vs the framebuffer the
+    reference binary rendered for the same scene (tests/golden/cornell_adaptive: 48 spp in three steps, 18..107 samples per
+    pixel).  A last-ulp difference in one sample's luminance can move a block's sample count by one, so the bar is on the
+    fraction of pixels: >= 97 % with the reference's exact sample count, >= 97 % within 1e-5*(1+L)."""
+    import os
+    from tungsten_b200 import integrator
+    from test_host import _adaptive_reference_emulation
+    g = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "cornell_adaptive")
+    fs = scene.load_scene(os.path.join(g, "scene.json"))
+    want = scene.load_pfm(os.path.join(g, "ref_pathseed.pfm"))
+    it = integrator.B200PathTraceIntegrator()
+    it.prepareForRender(fs, 0xBA5EBA11)
+    steps = 0
+    while not it.done():
+        it.startRender(); it.waitForCompletion(); steps += 1
+    img, cnt = it.context.read_framebuffer()
+    rec = [(r.sample_count, r.sample_index, r.next_sample_count) for r in it.records]
+    it.teardownAfterRender()
+    ref_mean, ref_cnt, ref_rec = _adaptive_reference_emulation(fs)
+    assert np.array_equal(ref_mean, want)                                  # (the emulation IS the reference binary's image)
+    same_cnt = float((cnt == ref_cnt).mean())
+    d = np.abs(img - want).max(axis=2)
+    close = float((d <= 1e-5*(1.0 + np.abs(want).max(axis=2))).mean()); exact = float((d == 0).mean())
+    same_rec = np.mean([a[0] == b.sample_count for a, b in zip(rec, ref_rec)])
+    print("adaptive: %d steps, samples/pixel %d..%d, same count %.4f, close %.4f, exact %.4f, same record counts %.4f" % (
+        steps, cnt.min(), cnt.max(), same_cnt, close, exact, same_rec))
+    assert steps == 3 and cnt.min() >= 18 and cnt.max() > 48
+    assert same_cnt >= 0.97 and close >= 0.97

@@ -96,8 +96,10 @@ def test_mesh_transform_and_material_clamp(tmp_path):
 
 
 class _FakeCtx:
-    def __init__(self): self.calls = []; self.aborted = False
+    def __init__(self): self.calls = []; self.aborted = False; self.adaptive_calls = []; self.L = lib.load()
     def render_resident(self, count, seed, spp_begin, tiles): self.calls.append((spp_begin, count, len(tiles)))
+    def render_adaptive(self, records, seed, tiles): self.adaptive_calls.append([(r.sample_index, r.next_sample_count) for r in records])
+    def clear_abort(self): self.aborted = False
     def clear(self): pass
     def close(self): pass
     def abort(self): self.aborted = True
@@ -123,11 +125,24 @@ def test_integrator_spp_stepping(monkeypatch):
     it.teardownAfterRender()
 
 
-def test_integrator_rejects_adaptive(monkeypatch):
-    sc = synth.cornell_box(res=(16, 16), spp=4); sc["renderer"]["adaptive_sampling"] = True
+def test_integrator_adaptive_steps_carry_block_records(monkeypatch):
+    """adaptive scenes go through generateWork + the per-block records (PathTraceIntegrator.cpp:110-156): below 16 spp every
+    block gets the step's sample count, sample indices accumulate."""
+    sc = synth.cornell_box(res=(16, 16), spp=24); sc["renderer"]["adaptive_sampling"] = True; sc["renderer"]["spp_step"] = 8
     fs = scene.load_scene(sc)
-    with pytest.raises(lib.TgbError):
-        integrator.B200PathTraceIntegrator().prepareForRender(fs, 1)
+    fake = _FakeCtx()
+    monkeypatch.setattr(lib, "Context", lambda *a, **k: fake)
+    it = integrator.B200PathTraceIntegrator()
+    it.prepareForRender(fs, 1)
+    it.startRender(); it.waitForCompletion()
+    it.startRender(); it.waitForCompletion()
+    assert fake.calls == [] and len(fake.adaptive_calls) == 2
+    assert fake.adaptive_calls[0] == [(0, 8)]*16 and fake.adaptive_calls[1] == [(8, 8)]*16
+    # third step starts at 16 spp = AdaptiveThreshold: the (all-zero) error estimate says there is nothing to do
+    fired = []
+    it.startRender(lambda: fired.append(1))
+    assert fired == [1] and it.currentSpp() == 24 and len(fake.adaptive_calls) == 2
+    it.teardownAfterRender()
 
 
 def test_tile_sharding_partitions_the_image():
@@ -272,3 +287,66 @@ def test_quantised_bvh_walk_equals_brute_force():
             assert bad.value == 0, (case, treelet, bad.value)
             assert nt.value == min(treelet, nn.value)
             assert visits.value > m
+
+
+def _adaptive_reference_emulation(fs, seed=0xBA5EBA11):
+    """The reference's adaptive loop (PathTraceIntegrator::startRender/generateWork/renderTile) with the CPU oracle as the
+    per-sample renderer and the LIBRARY's host-side tgb200_generate_work as the sample distributor."""
+    import ctypes as C
+    from tungsten_b200 import lib, abi, integrator
+    from oracle import pyoracle
+    L = lib.load()
+    w, h = fs.resolution
+    var_w, var_h = (w + 3)//4, (h + 3)//4
+    sampler = integrator.UniformSampler(integrator.hash32(seed))
+    tiles = integrator.dice_tiles(w, h, seed, sampler)
+    records = (abi.SampleRecord*(var_w*var_h))()
+    st = C.c_uint64(sampler.state)
+    orc = pyoracle.Oracle(fs)
+    mean = np.zeros((h, w, 3), np.float32); count = np.zeros((h, w), np.uint32)
+    cur = 0
+    f32 = np.float32
+    while cur < fs.spp:
+        nxt = min(cur + fs.spp_step, fs.spp)
+        if L.tgb200_generate_work(records, w, h, cur, nxt, 1 if fs.adaptive else 0, C.byref(st)) == 1:
+            for t in tiles:
+                for by in range(t.y, t.y + t.h, 4):
+                    for bx in range(t.x, t.x + t.w, 4):
+                        r = records[bx//4 + (by//4)*var_w]
+                        blk = (abi.Tile*1)(abi.Tile(bx, by, min(4, w - bx), min(4, h - by), t.sampler_seed))
+                        n = r.next_sample_count
+                        if n == 0:
+                            continue
+                        # the block's samples one by one (for SampleRecord::addSample), then folded into the framebuffer
+                        smp = np.zeros((n, h, w, 3), np.float32)
+                        for i in range(n):
+                            orc.render(1, seed=seed, spp_begin=r.sample_index + i, tiles=blk, threads=1, mean=smp[i], count=np.zeros((h, w), np.uint32))
+                        orc.render(n, seed=seed, spp_begin=r.sample_index, tiles=blk, threads=1, mean=mean, count=count)
+                        for y in range(by, min(by + 4, h)):
+                            for x in range(bx, min(bx + 4, w)):
+                                for i in range(n):
+                                    c = smp[i, y, x]
+                                    lum = f32(f32(f32(c[0]*f32(0.2126)) + f32(c[1]*f32(0.7152))) + f32(c[2]*f32(0.0722)))
+                                    r.sample_count += 1
+                                    delta = f32(lum - f32(r.mean))
+                                    r.mean = f32(f32(r.mean) + f32(delta/f32(r.sample_count)))
+                                    r.running_variance = f32(f32(r.running_variance) + f32(delta*f32(lum - f32(r.mean))))
+        cur = nxt
+    orc.close()
+    return mean, count, records
+
+
+def test_adaptive_sampling_matches_reference_binary():
+    """renderer.adaptive_sampling = true (as shipped scenes have it): tgb200_generate_work (95th-percentile clamp, dilation,
+    stochastic distribution, PathTraceIntegrator.cpp:44-134) driven exactly like the reference's loop, samples from the CPU
+    oracle -> the framebuffer equals what the reference binary itself rendered (tests/golden/cornell_adaptive) bit for bit."""
+    from tungsten_b200 import scene
+    g = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "cornell_adaptive")
+    fs = scene.load_scene(os.path.join(g, "scene.json"))
+    assert fs.adaptive and fs.spp == 48 and fs.spp_step == 16
+    want = scene.load_pfm(os.path.join(g, "ref_pathseed.pfm"))
+    mean, count, records = _adaptive_reference_emulation(fs)
+    assert count.min() >= 16 + 2 and count.max() > 48                     # the two adaptive steps really redistributed samples (>= 1 per step)
+    exact = float((np.abs(mean - want).max(axis=2) == 0).mean())
+    print("adaptive: per-pixel samples %d..%d, exact %.4f" % (count.min(), count.max(), exact))
+    assert exact == 1.0

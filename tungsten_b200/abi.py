@@ -5,7 +5,7 @@ sizes against the values the library itself reports.
 """
 import ctypes as C
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 TGB_OK, TGB_ERR_INVALID, TGB_ERR_UNSUPPORTED, TGB_ERR_NO_DEVICE, TGB_ERR_CUDA, TGB_ERR_ABORTED, TGB_ERR_OOM = \
     0, -1, -2, -3, -4, -5, -6
@@ -93,12 +93,19 @@ class Stats(C.Structure):
     _fields_ = [("samples", u64), ("rays", u64), ("hits", u64), ("kernel_launches", u64),
                 ("trace_ms", C.c_double), ("trace_launches", u64), ("total_ms", C.c_double),
                 ("path_rays", u64), ("shadow_rays", u64), ("shadow_ms", C.c_double), ("shadow_launches", u64),
-                ("path_rays_traversed", u64), ("shadow_rays_traversed", u64)]
+                ("path_rays_traversed", u64), ("shadow_rays_traversed", u64),
+                ("regen_ms", C.c_double), ("shade_ms", C.c_double), ("prep_ms", C.c_double), ("accum_ms", C.c_double),
+                ("sort_ms", C.c_double), ("iterations", u64)]
+
+
+class SampleRecord(C.Structure):
+    _fields_ = [("sample_count", u32), ("next_sample_count", u32), ("sample_index", u32),
+                ("adaptive_weight", f32), ("mean", f32), ("running_variance", f32)]
 
 
 EXPORTS = [
     "tgb200_create", "tgb200_render_tiles", "tgb200_render_resident", "tgb200_clear_framebuffer",
-    "tgb200_read_framebuffer", "tgb200_framebuffer_device_ptr", "tgb200_trace_closest", "tgb200_pack_tiles", "tgb200_unpack_tiles",
-    "tgb200_get_stats", "tgb200_set_profiling", "tgb200_scene_info", "tgb200_reset_stats", "tgb200_bvh_selftest", "tgb200_hair_selftest", "tgb200_qbvh_selftest", "tgb200_abort", "tgb200_clear_abort", "tgb200_destroy", "tgb200_last_error",
+    "tgb200_read_framebuffer", "tgb200_write_framebuffer", "tgb200_generate_work", "tgb200_render_adaptive", "tgb200_framebuffer_device_ptr", "tgb200_trace_closest", "tgb200_pack_tiles", "tgb200_unpack_tiles",
+    "tgb200_get_stats", "tgb200_set_profiling", "tgb200_set_stream", "tgb200_scene_info", "tgb200_reset_stats", "tgb200_bvh_selftest", "tgb200_hair_selftest", "tgb200_qbvh_selftest", "tgb200_abort", "tgb200_clear_abort", "tgb200_destroy", "tgb200_last_error",
     "tgb200_abi_version",
 ]

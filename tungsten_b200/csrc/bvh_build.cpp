@@ -206,7 +206,7 @@ inline float node_half_area(const Node4 &nd, int k) {
 }
 }  // namespace
 
-void quantize_bvh4(const Bvh4 &in, uint32_t max_treelet, QBvh4 &out) {
+void quantize_bvh4(const Bvh4 &in, uint32_t max_treelet, QBvh4 &out, int32_t empty_link) {
     out.nodes.clear(); out.old_index.clear(); out.treelet_image.clear(); out.n_treelet = 0;
     const size_t n = in.nodes.size();
     if (n == 0) return;
@@ -281,7 +281,7 @@ void quantize_bvh4(const Bvh4 &in, uint32_t max_treelet, QBvh4 &out) {
         }
         q.ox = org[0]; q.oy = org[1]; q.oz = org[2]; q.sx = S[0]; q.sy = S[1]; q.sz = S[2];
         q.lox = lo[0]; q.hix = hi[0]; q.loy = lo[1]; q.hiy = hi[1]; q.loz = lo[2]; q.hiz = hi[2];
-        for (int k = 0; k < 4; ++k) q.link[k] = nd.link[k] >= 0 ? new_index[size_t(nd.link[k])] : nd.link[k];
+        for (int k = 0; k < 4; ++k) q.link[k] = nd.link[k] >= 0 ? new_index[size_t(nd.link[k])] : (nd.link[k] == kEmptyLink ? empty_link : nd.link[k]);
         out.nodes[i] = q;
     }
     out.treelet_image.resize(out.n_treelet);

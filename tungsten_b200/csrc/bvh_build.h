@@ -60,7 +60,10 @@ struct QBvh4 {
                                          // chunk c of node i sits at chunk c ^ ((i >> 1) & 3)  (conflict-free-ish LDS.128)
 };
 // Quantise `in` (float 4-ary BVH) into `out`; at most max_treelet nodes go to the treelet (0 = none).
-void quantize_bvh4(const Bvh4 &in, uint32_t max_treelet, QBvh4 &out);
+// Empty child slots get the inverted box (lo 255, hi 0), which no ray can enter, and `empty_link` instead of kEmptyLink: the
+// kernels do not test for empty slots, so the link must be harmless to follow (the caller passes a one-primitive leaf that
+// holds an all-zero record, which every primitive test rejects).
+void quantize_bvh4(const Bvh4 &in, uint32_t max_treelet, QBvh4 &out, int32_t empty_link = kEmptyLink);
 // Host evaluation of one node visit with the kernels' arithmetic (tests + tgb200_qbvh_selftest): entry distance of the
 // four children for the ray (o, 1/d), INFINITY where the slab test fails.
 void qnode_slab_host(const QNode4 &nd, const float o[3], const float inv_d[3], float tnear, float tfar, float t_out[4]);

@@ -2,6 +2,7 @@
 // Host logic mirrors the reference's TraceableScene constructor + PathTraceIntegrator (prepare, tile
 // dicing, sample stepping); all rendering arithmetic runs in the CUDA kernels of tgb_wavefront.cuh.
 // There is NO CPU fallback: without a CUDA device every entry point fails with TGB_ERR_NO_DEVICE.
+#include <algorithm>
 #include <atomic>
 #include <cmath>
 #include <cstdarg>
@@ -41,7 +42,7 @@ struct tgb_ctx {
     uint32_t capacity = 0;
     PathBuf pb[2]{};                // persistent path state, double buffered (k_accum compacts from one into the other)
     Scratch sr{};                   // per-bounce scratch records + per-step results
-    uint32_t *order = nullptr, *squeue = nullptr;       // ray-coherence visiting order of k_trace; shadow-query queue
+    uint32_t *order = nullptr, *squeue = nullptr, *squeue2 = nullptr;   // ray-coherence visiting order of k_trace; shadow-query queues (emitted / left after the analytic pass)
     uint32_t persist_blocks = 0;    // grid of the persistent traversal kernels
     size_t trace_smem = 0;          // their dynamic shared memory: treelet image + stacks + mbarrier
     size_t l2_window_bytes = 0;     // bytes of BVH data pinned in L2 through the stream's access-policy window (0 = none)
@@ -51,12 +52,18 @@ struct tgb_ctx {
     size_t res_capacity = 0;
     Ctl *ctl = nullptr;             // device-resident loop control block
     Ctl *h_ctl = nullptr;           // pinned: [0..3] snapshot ring (read one iteration late), [4] initial value
-    cudaEvent_t ev_ring[4]{}, ev_t0[4]{}, ev_t1[4]{}, ev_s0[4]{}, ev_s1[4]{};
+    cudaEvent_t ev_ring[4]{};
+    cudaEvent_t ev_k[4][8]{};       // profiling: boundaries between the kernels of an iteration (regen|trace|shade|prep|shadow|accum|sort)
+    cudaStream_t own_stream = nullptr;
     Counters *ctr = nullptr; Counters *h_ctr = nullptr;
     float *fb = nullptr; uint32_t *fb_count = nullptr;
     float *h_fb = nullptr; uint32_t *h_fb_count = nullptr;   // pinned staging
     // cached pixel list
     std::vector<tgb_tile> tiles_cached; uint32_t *pix_id = nullptr, *pix_seed = nullptr; uint32_t n_pix = 0, pix_capacity = 0;
+    std::vector<uint32_t> h_pix_id;                  // host copy of the pixel list (adaptive steps build per-pixel sample ranges from it)
+    // adaptive sampling: per-pixel result-slot offsets / first sample index, pixel -> list index map, the 4x4 blocks' SampleRecords
+    uint32_t *pix_first = nullptr, *pix_base = nullptr, *pix_slot = nullptr; uint32_t adaptive_capacity = 0; bool pix_slot_valid = false;
+    SampleRecordD *rec_dev = nullptr;
     tgb_stats stats{};
     bool profiling = false;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -326,7 +333,9 @@ int upload_scene(tgb_ctx *c, const tgb_scene_desc *d) {
                 float4 s1 = make_float4(b.normal[1], b.normal[2], cc.normal[0], cc.normal[1]);
                 float4 s2 = make_float4(cc.normal[2], a.uv[0], a.uv[1], b.uv[0]);
                 float4 s3 = make_float4(b.uv[1], cc.uv[0], cc.uv[1], 0.0f);
-                std::memcpy(&s3.w, &mat, 4);
+                if (mat > 1023 || i >= (1u << 22)) return fail(c, TGB_ERR_UNSUPPORTED, "mesh %u: more than 1024 materials in one mesh or more than 4 Mi primitives", i);
+                uint32_t packed = uint32_t(mat) | (i << 10);            // material | primitive << 10 (make_surface)
+                std::memcpy(&s3.w, &packed, 4);
                 tri_shade.push_back(s0); tri_shade.push_back(s1); tri_shade.push_back(s2); tri_shade.push_back(s3);
                 V3 p0 = f3(a.pos), p1 = f3(b.pos), p2 = f3(cc.pos);
                 areas[k] = length(cross(p1 - p0, p2 - p0))*0.5f;                           // MathUtil::triangleArea
@@ -537,7 +546,7 @@ int upload_scene(tgb_ctx *c, const tgb_scene_desc *d) {
     }
     if (3*bvh.max_depth + 2 > uint32_t(kStackSize)) return fail(c, TGB_ERR_UNSUPPORTED, "BVH depth %u exceeds the traversal stack", bvh.max_depth);
     c->bvh_depth = bvh.max_depth; c->n_tris = uint32_t(btris.size()); c->bvh_sah = bvh.sah_cost;
-    std::vector<float4> tri_isect(3*(btris.size() + cboxes.size()));
+    std::vector<float4> tri_isect(3*(btris.size() + cboxes.size() + 1), make_float4(0.0f, 0.0f, 0.0f, 0.0f));   // + one all-zero record: the target of empty child slots
     for (size_t k = btris.size(); k < bvh.order.size(); ++k) {      // curve records: the segment's three nodes + which quarter, leaf order
         size_t seg = bvh.order[k] - btris.size();
         for (int j = 0; j < 3; ++j) tri_isect[3*k + j] = crecs[3*seg + j];
@@ -557,12 +566,17 @@ int upload_scene(tgb_ctx *c, const tgb_scene_desc *d) {
     {
         // shared-memory budget of one traversal CTA: 227 KB / resident CTAs - stacks - 1 KB system reserve
         const long budget = long(227*1024)/TGB_MINB - long(kStackSmemBytes) - 1024 - 16;
-        long want = std::max(0L, budget/64);
-        if (const char *e = getenv("TGB_TREELET")) want = std::min(want, std::max(0L, atol(e)));
+        // Measured on C1 (profiles/r02_d_summary.md): staging the top 320 nodes costs more than it saves (k_trace 286 -> 312 ms per
+        // 4 steps: the carve-out shrinks L1, whose hit rate falls from 55 % to 43 %, and the treelet branch adds instructions to
+        // a kernel that is ALU-issue bound), so the treelet is opt-in: TGB_TREELET=<nodes> (capped by the budget above).
+        long want = 0;
+        if (const char *e = getenv("TGB_TREELET")) want = std::min(std::max(0L, budget/64), std::max(0L, atol(e)));
 #if !TGB_QNODES
         want = 0;
 #endif
-        quantize_bvh4(bvh, uint32_t(want), qb);
+        // empty child slots link to a one-triangle leaf holding the all-zero record behind the last primitive (den == 0: rejected)
+        const int32_t empty_link = ~int32_t(uint32_t(btris.size() + cboxes.size()) << 3);
+        quantize_bvh4(bvh, uint32_t(want), qb, empty_link);
     }
 #if TGB_QNODES
     std::vector<float4> nodes;                                  // float nodes stay on the host (cut construction above)
@@ -583,7 +597,11 @@ int upload_scene(tgb_ctx *c, const tgb_scene_desc *d) {
     if ((rc = dev_upload(c, &sc.analytic, analytic))) return rc;
     if ((rc = dev_upload(c, &sc.tri_global, bvh.order))) return rc;
     if ((rc = dev_upload(c, &sc.tri_prim, tri_prim))) return rc;
-    if ((rc = dev_upload(c, &sc.tri_shade, tri_shade))) return rc;
+    {   // shading records follow the intersection records into BVH leaf order (one hop from a hit id)
+        std::vector<float4> shade_leaf(tri_shade.size());
+        for (size_t k = 0; k < btris.size(); ++k) std::memcpy(&shade_leaf[4*k], &tri_shade[4*size_t(bvh.order[k])], 4*sizeof(float4));
+        if ((rc = dev_upload(c, &sc.tri_shade, shade_leaf))) return rc;
+    }
     {   // BVH nodes + intersection records in ONE allocation, so that a single L2 access-policy window can pin them.
         // The traversal kernels re-read this working set (C1: 78 MB) for every wavefront while ~2 GB of path state streams
         // through the same L2 in between, which is why ncu shows 5x the algorithmic DRAM bytes for k_trace.  Measured
@@ -599,7 +617,7 @@ int upload_scene(tgb_ctx *c, const tgb_scene_desc *d) {
         if (tb) CU(cudaMemcpy(slab + nb_al, tri_isect.data(), tb, cudaMemcpyHostToDevice));
         sc.nodes = reinterpret_cast<const float4 *>(slab); sc.qnodes = reinterpret_cast<const uint4 *>(slab + fb_al);
         sc.tri_isect = reinterpret_cast<const float4 *>(slab + nb_al);
-        sc.n_treelet = qb.n_treelet; sc.treelet_img = nullptr;
+        sc.n_treelet = qb.n_treelet; sc.treelet_img = nullptr; sc.qy = 0x3F80u;
         if (qb.n_treelet) {
             QNode4 *img = nullptr;
             if ((rc = dev_alloc(c, &img, qb.treelet_image.size()))) return rc;
@@ -648,7 +666,7 @@ int alloc_wavefront(tgb_ctx *c, uint32_t capacity) {
     c->capacity = capacity;
     int rc;
     for (int k = 0; k < 2; ++k) {
-        if ((rc = dev_alloc(c, &c->pb[k].T, size_t(capacity)*4))) return rc;
+        for (float4 **p : {&c->pb[k].T0, &c->pb[k].T1, &c->pb[k].T2, &c->pb[k].T3}) if ((rc = dev_alloc(c, p, capacity))) return rc;
         if ((rc = dev_alloc(c, &c->pb[k].E, capacity))) return rc;
         if ((rc = dev_alloc(c, &c->pb[k].pcg, capacity))) return rc;
     }
@@ -657,6 +675,7 @@ int alloc_wavefront(tgb_ctx *c, uint32_t capacity) {
     if ((rc = dev_alloc(c, &c->sr.vis, size_t(capacity)*2))) return rc;
     if ((rc = dev_alloc(c, &c->sr.SH, size_t(capacity)*2))) return rc;
     if ((rc = dev_alloc(c, &c->squeue, size_t(capacity)*2))) return rc;
+    if ((rc = dev_alloc(c, &c->squeue2, size_t(capacity)*2))) return rc;
     if ((rc = dev_alloc(c, &c->order, capacity))) return rc;
     if ((rc = dev_alloc(c, &c->bin_keys, capacity))) return rc;
     if ((rc = dev_alloc(c, &c->bin_hist, size_t(kBins) + 4))) return rc;
@@ -710,6 +729,7 @@ int set_tiles(tgb_ctx *c, const tgb_tile *tiles, uint32_t n_tiles, uint32_t seed
         c->pix_capacity = uint32_t(pid.size());
     }
     c->n_pix = uint32_t(pid.size());
+    c->h_pix_id = pid; c->pix_slot_valid = false;
     if (c->n_pix) {
         CU(cudaMemcpyAsync(c->pix_id, pid.data(), pid.size()*4, cudaMemcpyHostToDevice, c->stream));
         CU(cudaMemcpyAsync(c->pix_seed, pseed.data(), pseed.size()*4, cudaMemcpyHostToDevice, c->stream));
@@ -741,15 +761,17 @@ void enqueue_iteration(tgb_ctx *c, const BatchInfo &bi, int cur, uint32_t bound,
     const bool has_bvh = sc.n_nodes != 0, curves = c->has_curves;
     PathBuf &pb = c->pb[cur], &nxt = c->pb[cur ^ 1];
     cudaStream_t st = c->stream;
+    const bool prof = c->profiling;
+    if (prof) cudaEventRecord(c->ev_k[slot][0], st);
     k_regen<<<blocks(bound, 256), 256, 0, st>>>(sc, pb, bi, c->ctl, c->order, c->bin_hist); launches++;
-    if (c->profiling) cudaEventRecord(c->ev_t0[slot], st);
+    if (prof) cudaEventRecord(c->ev_k[slot][1], st);
     if (has_bvh) {
         uint32_t grid = std::min(blocks(bound, kTraceBlock), c->persist_blocks);
         if (curves) k_trace<true><<<grid, kTraceBlock, c->trace_smem, st>>>(sc, pb, c->order, c->ctl);
         else k_trace<false><<<grid, kTraceBlock, c->trace_smem, st>>>(sc, pb, c->order, c->ctl);
         launches++;
     }
-    if (c->profiling) cudaEventRecord(c->ev_t1[slot], st);
+    if (prof) cudaEventRecord(c->ev_k[slot][2], st);
     if (c->sort_materials) {
         if (curves) k_shade<true, true><<<blocks(bound, kShadeSortBlock), kShadeSortBlock, 0, st>>>(sc, pb, c->sr, bi, c->ctl, c->squeue, c->ctr);
         else k_shade<false, true><<<blocks(bound, kShadeSortBlock), kShadeSortBlock, 0, st>>>(sc, pb, c->sr, bi, c->ctl, c->squeue, c->ctr);
@@ -758,36 +780,51 @@ void enqueue_iteration(tgb_ctx *c, const BatchInfo &bi, int cur, uint32_t bound,
         else k_shade<false, false><<<blocks(bound, 128), 128, 0, st>>>(sc, pb, c->sr, bi, c->ctl, c->squeue, c->ctr);
     }
     launches++;
-    if (c->profiling) cudaEventRecord(c->ev_s0[slot], st);
+    if (prof) cudaEventRecord(c->ev_k[slot][3], st);
+    if (curves) k_shadow_prep<true><<<blocks(2*bound, 256), 256, 0, st>>>(sc, c->sr, c->squeue, c->ctl, c->squeue2, c->ctr);
+    else k_shadow_prep<false><<<blocks(2*bound, 256), 256, 0, st>>>(sc, c->sr, c->squeue, c->ctl, c->squeue2, c->ctr);
+    launches++;
+    if (prof) cudaEventRecord(c->ev_k[slot][4], st);
     if (has_bvh) {
         uint32_t grid = std::min(blocks(2*bound, kTraceBlock), c->persist_blocks);
-        if (curves) k_shadow_bvh<true><<<grid, kTraceBlock, c->trace_smem, st>>>(sc, c->sr, c->squeue, c->ctl, c->ctr);
-        else k_shadow_bvh<false><<<grid, kTraceBlock, c->trace_smem, st>>>(sc, c->sr, c->squeue, c->ctl, c->ctr);
+        if (curves) k_shadow_bvh<true><<<grid, kTraceBlock, c->trace_smem, st>>>(sc, c->sr, c->squeue2, c->ctl, c->ctr);
+        else k_shadow_bvh<false><<<grid, kTraceBlock, c->trace_smem, st>>>(sc, c->sr, c->squeue2, c->ctl, c->ctr);
         launches++;
     }
-    if (c->profiling) cudaEventRecord(c->ev_s1[slot], st);
-    k_accum<<<blocks(bound, 256), 256, 0, st>>>(sc, pb, nxt, c->sr, c->ctl, c->bin_keys, c->bin_hist); launches++;
+    if (prof) cudaEventRecord(c->ev_k[slot][5], st);
+    k_accum<<<blocks(bound, 256), 256, 0, st>>>(sc, pb, nxt, c->sr, bi, c->ctl, c->bin_keys, c->bin_hist); launches++;
+    if (prof) cudaEventRecord(c->ev_k[slot][6], st);
     k_iter_end<<<1, 1024, 0, st>>>(c->bin_hist, c->ctl, has_bvh ? 1 : 0); launches++;
     if (has_bvh) { k_bin_scatter<<<blocks(bound, 256), 256, 0, st>>>(c->bin_keys, c->bin_hist, c->ctl, c->order); launches++; }
+    if (prof) cudaEventRecord(c->ev_k[slot][7], st);
 }
 
-int render_device(tgb_ctx *c, uint32_t spp_begin, uint32_t spp_count) {
-    if (c->n_pix == 0 || spp_count == 0) return TGB_OK;
+// `adaptive`: per-pixel sample ranges come from c->pix_first / c->pix_base (tgb200_render_adaptive), else every pixel
+// renders samples [spp_begin, spp_begin + spp_count).
+int render_device(tgb_ctx *c, uint32_t spp_begin, uint32_t spp_count, bool adaptive = false, uint32_t adaptive_total = 0) {
+    if (c->n_pix == 0 || (!adaptive && spp_count == 0) || (adaptive && adaptive_total == 0)) return TGB_OK;
     CU(cudaEventRecord(c->ev0, c->stream));
     uint64_t launches = 0;
     float trace_ms = 0.0f, shadow_ms = 0.0f; uint64_t trace_launches = 0, traversed = 0, shadow_traversed = 0;
+    double kms[7] = {0, 0, 0, 0, 0, 0, 0}; uint64_t iterations = 0;
     // a step's finished radiances are kept per path (16 B each) until k_resolve folds them in sample order;
-    // split the sample range so that this buffer stays below 8 GB and path ids fit 32 bits
+    // split the sample range so that this buffer stays below 8 GB and (sample within the call, pixel) fits 32 bits
+    uint32_t pix_bits = 0; while (pix_bits < 32 && (uint64_t(1) << pix_bits) < uint64_t(c->n_pix)) ++pix_bits;
+    const uint64_t max_k = uint64_t(1) << (32 - pix_bits);
     const uint64_t max_paths = 512ull << 20;
-    uint32_t spp_sub = uint32_t(std::max<uint64_t>(1, std::min<uint64_t>(spp_count, max_paths/c->n_pix)));
+    uint32_t spp_sub = adaptive ? 1u : uint32_t(std::max<uint64_t>(1, std::min<uint64_t>(std::min<uint64_t>(spp_count, max_k), max_paths/c->n_pix)));
     if (uint64_t(c->n_pix)*spp_sub > 0xFFFFFFFFull) return fail(c, TGB_ERR_UNSUPPORTED, "tile list too large");
+    if (adaptive) spp_count = 1;                               // one pass over the per-pixel ranges
     const bool trace_bounces = getenv("TGB_TRACE_BOUNCES") != nullptr;
+    uint64_t samples_done = 0;
     for (uint32_t s0 = 0; s0 < spp_count; s0 += spp_sub) {
         uint32_t ns = std::min(spp_sub, spp_count - s0);
-        uint32_t total = c->n_pix*ns;
+        uint32_t total = adaptive ? adaptive_total : c->n_pix*ns;
+        samples_done += total;
         int rc = ensure_results(c, total);
         if (rc) return rc;
         BatchInfo bi; bi.pix_id = c->pix_id; bi.pix_seed = c->pix_seed; bi.n_pix = c->n_pix; bi.spp_begin = spp_begin + s0;
+        bi.pix_first = adaptive ? c->pix_first : nullptr; bi.pix_base = adaptive ? c->pix_base : nullptr; bi.pix_bits = pix_bits;
         // control block of the first iteration; from then on k_iter_end keeps it
         Ctl &init = c->h_ctl[4];
         std::memset(&init, 0, sizeof(Ctl));
@@ -810,12 +847,11 @@ int render_device(tgb_ctx *c, uint32_t spp_begin, uint32_t spp_count) {
             CU(cudaEventSynchronize(c->ev_ring[p]));
             const Ctl S = c->h_ctl[p];                        // state after iteration iter-1 = the sizes of iteration iter
             if (c->profiling) {
-                float ms = 0.0f;
-                cudaEventElapsedTime(&ms, c->ev_t0[p], c->ev_t1[p]); trace_ms += ms; trace_launches++;
-                cudaEventElapsedTime(&ms, c->ev_s0[p], c->ev_s1[p]); shadow_ms += ms;
+                for (int k = 0; k < 7; ++k) { float ms = 0.0f; cudaEventElapsedTime(&ms, c->ev_k[p][k], c->ev_k[p][k + 1]); kms[k] += ms; }
+                trace_launches++;
             }
             if (trace_bounces) fprintf(stderr, "after iter %u: next n %u (survivors %u, new %u, to traverse %u) issued %u/%u\n", iter - 1, S.n, S.n_surv, S.n_new, S.n_sorted, S.issued, S.total);
-            if (S.n == 0) { traversed += S.traversed; shadow_traversed += S.shadow_traversed; break; }   // iteration `iter`, already queued, is empty
+            if (S.n == 0) { traversed += S.traversed; shadow_traversed += S.shadow_traversed; iterations += S.iterations; break; }   // iteration `iter`, already queued, is empty
             // n(iter+1) <= n(iter) + the camera paths not yet issued after iteration iter's refill
             bound = uint32_t(std::min<uint64_t>(c->capacity, uint64_t(S.n) + (S.total - S.issued)));
             if (iter > (1u << 24)) return fail(c, TGB_ERR_INVALID, "wavefront loop did not terminate");
@@ -827,9 +863,12 @@ int render_device(tgb_ctx *c, uint32_t spp_begin, uint32_t spp_count) {
     CU(cudaStreamSynchronize(c->stream));
     CU(cudaGetLastError());
     float ms = 0.0f; cudaEventElapsedTime(&ms, c->ev0, c->ev1);
-    c->stats.samples += uint64_t(c->n_pix)*spp_count;
+    c->stats.samples += samples_done;
     c->stats.path_rays = c->h_ctr->rays; c->stats.shadow_rays = c->h_ctr->shadow_rays;
     c->stats.rays = c->h_ctr->rays + c->h_ctr->shadow_rays; c->stats.hits = c->h_ctr->hits + c->h_ctr->shadow_hits;
+    trace_ms = float(kms[1]); shadow_ms = float(kms[4]);
+    c->stats.regen_ms += kms[0]; c->stats.shade_ms += kms[2]; c->stats.prep_ms += kms[3]; c->stats.accum_ms += kms[5]; c->stats.sort_ms += kms[6];
+    c->stats.iterations += iterations;
     c->stats.shadow_ms += shadow_ms; c->stats.shadow_launches += trace_launches;
     c->stats.kernel_launches += launches;
     c->stats.path_rays_traversed += traversed; c->stats.shadow_rays_traversed += shadow_traversed;
@@ -857,8 +896,8 @@ void tgb200_destroy(tgb_ctx *c) {
     if (c->h_fb) cudaFreeHost(c->h_fb);
     if (c->h_fb_count) cudaFreeHost(c->h_fb_count);
     for (cudaEvent_t e : {c->ev0, c->ev1}) if (e) cudaEventDestroy(e);
-    for (int k = 0; k < 4; ++k) for (cudaEvent_t e : {c->ev_ring[k], c->ev_t0[k], c->ev_t1[k], c->ev_s0[k], c->ev_s1[k]}) if (e) cudaEventDestroy(e);
-    if (c->stream) cudaStreamDestroy(c->stream);
+    for (int k = 0; k < 4; ++k) { if (c->ev_ring[k]) cudaEventDestroy(c->ev_ring[k]); for (cudaEvent_t e : c->ev_k[k]) if (e) cudaEventDestroy(e); }
+    if (c->own_stream) cudaStreamDestroy(c->own_stream);
     delete c;
 }
 
@@ -884,11 +923,12 @@ int tgb200_create(const tgb_scene_desc *d, tgb_ctx **out) {
     int rc = TGB_OK;
     do {
         if (cudaSetDevice(dev) != cudaSuccess) { rc = fail(c, TGB_ERR_CUDA, "cudaSetDevice(%d) failed", dev); break; }
-        if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { rc = fail(c, TGB_ERR_CUDA, "cudaStreamCreate failed"); break; }
+        if (cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) != cudaSuccess) { rc = fail(c, TGB_ERR_CUDA, "cudaStreamCreate failed"); break; }
+        c->stream = c->own_stream;
         for (cudaEvent_t *e : {&c->ev0, &c->ev1}) cudaEventCreate(e);
         for (int k = 0; k < 4; ++k) {
             cudaEventCreateWithFlags(&c->ev_ring[k], cudaEventDisableTiming);
-            for (cudaEvent_t *e : {&c->ev_t0[k], &c->ev_t1[k], &c->ev_s0[k], &c->ev_s1[k]}) cudaEventCreate(e);
+            for (cudaEvent_t &e : c->ev_k[k]) cudaEventCreate(&e);
         }
         if ((rc = upload_scene(c, d))) break;
         uint32_t cap = d->settings.max_paths_in_flight ? d->settings.max_paths_in_flight : (1u << 22);
@@ -1032,6 +1072,14 @@ int tgb200_reset_stats(tgb_ctx *c) {
     return TGB_OK;
 }
 
+int tgb200_set_stream(tgb_ctx *c, void *cuda_stream) {
+    if (!c) return TGB_ERR_INVALID;
+    CU(cudaSetDevice(c->device));
+    CU(cudaStreamSynchronize(c->stream));
+    c->stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : c->own_stream;
+    return TGB_OK;
+}
+
 int tgb200_set_profiling(tgb_ctx *c, int enable) {
     if (!c) return TGB_ERR_INVALID;
     c->profiling = enable != 0;
@@ -1158,6 +1206,132 @@ int tgb200_bvh_selftest(const float *tri_verts, uint32_t n, uint32_t *n_nodes, u
     return TGB_OK;
 }
 
+int tgb200_write_framebuffer(tgb_ctx *c, const float *rgb_mean, const uint32_t *count) {
+    if (!c || !rgb_mean || !count) return TGB_ERR_INVALID;
+    CU(cudaSetDevice(c->device));
+    size_t npx = size_t(c->res_x)*c->res_y;
+    std::memcpy(c->h_fb, rgb_mean, npx*3*sizeof(float)); std::memcpy(c->h_fb_count, count, npx*sizeof(uint32_t));
+    CU(cudaMemcpyAsync(c->fb, c->h_fb, npx*3*sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(c->fb_count, c->h_fb_count, npx*sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return TGB_OK;
+}
+
+// One adaptive step (PathTraceIntegrator::renderTile with per-block sample counts, PathTraceIntegrator.cpp:136-156): every pixel
+// of 4x4 block b renders records[b].next_sample_count samples starting at sample index records[b].sample_index; the resident
+// framebuffer takes them in sample order and the records' Welford statistics are updated in the reference's order.
+int tgb200_render_adaptive(tgb_ctx *c, const tgb_tile *tiles, uint32_t n_tiles, uint32_t seed, tgb_sample_record *records) {
+    if (!c || !records) return c ? fail(c, TGB_ERR_INVALID, "null records") : TGB_ERR_INVALID;
+    if (n_tiles && !tiles) return fail(c, TGB_ERR_INVALID, "null tile list");
+    static_assert(sizeof(tgb_sample_record) == sizeof(SampleRecordD), "record layout");
+    CU(cudaSetDevice(c->device));
+    int rc = set_tiles(c, tiles, n_tiles, seed);
+    if (rc) return rc;
+    const uint32_t var_w = (c->res_x + 3)/4, var_h = (c->res_y + 3)/4, n_blocks = var_w*var_h;
+    if (c->n_pix == 0) return TGB_OK;
+    if (c->adaptive_capacity < c->n_pix + 1 || !c->rec_dev) {
+        if ((rc = dev_alloc(c, &c->pix_first, size_t(c->n_pix) + 1))) return rc;
+        if ((rc = dev_alloc(c, &c->pix_base, size_t(c->n_pix) + 1))) return rc;
+        if (!c->pix_slot && (rc = dev_alloc(c, &c->pix_slot, size_t(c->res_x)*c->res_y))) return rc;
+        if (!c->rec_dev && (rc = dev_alloc(c, &c->rec_dev, n_blocks))) return rc;
+        c->adaptive_capacity = c->n_pix + 1;
+    }
+    std::vector<uint32_t> first(size_t(c->n_pix) + 1), base(size_t(c->n_pix) + 1, 0);
+    uint64_t total = 0; uint32_t max_cnt = 0;
+    for (uint32_t i = 0; i < c->n_pix; ++i) {
+        const uint32_t px = c->h_pix_id[i] % c->res_x, py = c->h_pix_id[i]/c->res_x;
+        const tgb_sample_record &r = records[px/4 + (py/4)*var_w];
+        first[i] = uint32_t(total); base[i] = r.sample_index;
+        total += r.next_sample_count; max_cnt = std::max(max_cnt, r.next_sample_count);
+        if (total > 0xFFFFFFFFull) return fail(c, TGB_ERR_UNSUPPORTED, "adaptive step too large");
+    }
+    first[c->n_pix] = uint32_t(total);
+    uint32_t pix_bits = 0; while (pix_bits < 32 && (uint64_t(1) << pix_bits) < uint64_t(c->n_pix)) ++pix_bits;
+    if (uint64_t(max_cnt) > (uint64_t(1) << (32 - pix_bits))) return fail(c, TGB_ERR_UNSUPPORTED, "adaptive step: %u samples for one pixel do not fit the path id", max_cnt);
+    if (!c->pix_slot_valid) {
+        std::vector<uint32_t> slot(size_t(c->res_x)*c->res_y, 0xFFFFFFFFu);
+        for (uint32_t i = 0; i < c->n_pix; ++i) slot[c->h_pix_id[i]] = i;
+        CU(cudaMemcpyAsync(c->pix_slot, slot.data(), slot.size()*4, cudaMemcpyHostToDevice, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+        c->pix_slot_valid = true;
+    }
+    CU(cudaMemcpyAsync(c->pix_first, first.data(), first.size()*4, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(c->pix_base, base.data(), base.size()*4, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(c->rec_dev, records, size_t(n_blocks)*sizeof(SampleRecordD), cudaMemcpyHostToDevice, c->stream));
+    CU(cudaStreamSynchronize(c->stream));                       // (the host vectors go out of scope)
+    if (total == 0) return TGB_OK;
+    if ((rc = render_device(c, 0, 0, true, uint32_t(total)))) return rc;
+    BatchInfo bi; bi.pix_id = c->pix_id; bi.pix_seed = c->pix_seed; bi.n_pix = c->n_pix; bi.spp_begin = 0;
+    bi.pix_first = c->pix_first; bi.pix_base = c->pix_base; bi.pix_bits = pix_bits;
+    k_block_stats<<<blocks(n_blocks, 128), 128, 0, c->stream>>>(c->sr.R, bi, c->pix_slot, c->res_x, c->res_y, var_w, n_blocks, c->rec_dev);
+    c->stats.kernel_launches++;
+    CU(cudaMemcpyAsync(records, c->rec_dev, size_t(n_blocks)*sizeof(SampleRecordD), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    CU(cudaGetLastError());
+    return TGB_OK;
+}
+
+namespace {
+// UniformSampler (sampling/UniformSampler.hpp:40-52): the integrator's own PCG32 stream (tile seeds, adaptive distribution)
+inline float pcg_next1d(uint64_t &state) { return normalized_uint(pcg_next(state)); }
+}
+
+// PathTraceIntegrator::generateWork (PathTraceIntegrator.cpp:44-134), host only: advances every block's sample index, then
+// either gives every block spp_count samples or -- adaptive sampling on and current_spp >= 16 -- distributes the step's
+// budget by the blocks' clamped, dilated error estimates.  sampler_state = the integrator's UniformSampler state (it already
+// produced the tile seeds); returns 1 when there is work, 0 when the error estimate is zero everywhere (the reference
+// then skips the step), negative on bad arguments.
+int tgb200_generate_work(tgb_sample_record *records, uint32_t res_x, uint32_t res_y, uint32_t current_spp, uint32_t next_spp,
+                         int adaptive_sampling, uint64_t *sampler_state) {
+    if (!records || !sampler_state || !res_x || !res_y || next_spp < current_spp) return TGB_ERR_INVALID;
+    const uint32_t var_w = (res_x + 3)/4, var_h = (res_y + 3)/4; const size_t n = size_t(var_w)*var_h;
+    for (size_t i = 0; i < n; ++i) records[i].sample_index += records[i].next_sample_count;
+    const int spp_count = int(next_spp - current_spp);
+    if (adaptive_sampling && current_spp >= 16) {                                        // AdaptiveThreshold (PathTraceIntegrator.hpp)
+        // errorPercentile95 (:44-59)
+        std::vector<float> errors; errors.reserve(n);
+        for (size_t i = 0; i < n; ++i) {
+            tgb_sample_record &r = records[i];
+            float variance = r.running_variance/float(r.sample_count - 1u);              // SampleRecord::variance (uint32 arithmetic, then float)
+            r.adaptive_weight = variance/(float(r.sample_count)*std::max(r.mean*r.mean, 1e-3f));
+            if (r.adaptive_weight > 0.0f) errors.push_back(r.adaptive_weight);
+        }
+        if (errors.empty()) return 0;
+        std::sort(errors.begin(), errors.end());
+        const float max_error = errors[(errors.size()*95)/100];
+        if (max_error == 0.0f) return 0;
+        for (size_t i = 0; i < n; ++i) records[i].adaptive_weight = std::min(records[i].adaptive_weight, max_error);
+        // dilateAdaptiveWeights (:61-88)
+        for (uint32_t y = 0; y < var_h; ++y) for (uint32_t x = 0; x < var_w; ++x) {
+            size_t idx = x + size_t(y)*var_w;
+            if (y < var_h - 1) records[idx].adaptive_weight = std::max(records[idx].adaptive_weight, records[idx + var_w].adaptive_weight);
+            if (x < var_w - 1) records[idx].adaptive_weight = std::max(records[idx].adaptive_weight, records[idx + 1].adaptive_weight);
+        }
+        for (int y = int(var_h) - 1; y >= 0; --y) for (int x = int(var_w) - 1; x >= 0; --x) {
+            size_t idx = size_t(x) + size_t(y)*var_w;
+            if (y > 0) records[idx].adaptive_weight = std::max(records[idx].adaptive_weight, records[idx - var_w].adaptive_weight);
+            if (x > 0) records[idx].adaptive_weight = std::max(records[idx].adaptive_weight, records[idx - 1].adaptive_weight);
+        }
+        // distributeAdaptiveSamples (:90-112)
+        double total_weight = 0.0;
+        for (size_t i = 0; i < n; ++i) total_weight += records[i].adaptive_weight;
+        const int adaptive_budget = (spp_count - 1)*int(res_x)*int(res_y);
+        const int budget_per_tile = adaptive_budget/16;
+        const float weight_to_sample = float(double(budget_per_tile)/total_weight);
+        float pixel_pdf = 0.0f;
+        for (size_t i = 0; i < n; ++i) {
+            float fractional = records[i].adaptive_weight*weight_to_sample;
+            int adaptive = int(fractional);
+            pixel_pdf += fractional - float(adaptive);
+            if (pcg_next1d(*sampler_state) < pixel_pdf) { adaptive++; pixel_pdf -= 1.0f; }
+            records[i].next_sample_count = uint32_t(adaptive + 1);
+        }
+    } else {
+        for (size_t i = 0; i < n; ++i) records[i].next_sample_count = uint32_t(spp_count);
+    }
+    return 1;
+}
+
 // Host-only check of the quantised device BVH (no GPU needed): builds the 4-ary SAH tree over n triangles exactly as
 // tgb200_create does (same padding), quantises it (QNode4 + treelet), and walks it on the HOST with the kernels' node
 // arithmetic (qnode_slab_host mirrors Traversal::visit) and their triangle test for every ray (8 floats: o, d, tmin, tmax).
@@ -1171,7 +1345,8 @@ int tgb200_qbvh_selftest(const float *tri_verts, uint32_t n, const float *rays, 
     for (uint32_t i = 0; i < n; ++i) { std::memcpy(&tris[i], tri_verts + 9*size_t(i), sizeof(BuildTri)); for (int k = 0; k < 9; ++k) extent = std::max(extent, std::fabs(tri_verts[9*size_t(i) + k])); }
     for (uint32_t r = 0; r < n_rays; ++r) for (int k = 0; k < 3; ++k) extent = std::max(extent, std::fabs(rays[8*size_t(r) + k]));
     Bvh4 bvh; build_bvh4(tris.data(), n, bvh, 0, 1e-6f*extent, 4, 0.5f);
-    QBvh4 qb; quantize_bvh4(bvh, max_treelet, qb);
+    const int32_t empty_link = ~int32_t(n << 3);                       // a leaf past the last triangle (the walk below skips it)
+    QBvh4 qb; quantize_bvh4(bvh, max_treelet, qb, empty_link);
     if (n_nodes) *n_nodes = uint32_t(qb.nodes.size());
     if (n_treelet) *n_treelet = qb.n_treelet;
     if (qb.nodes.size() != bvh.nodes.size() || qb.n_treelet > qb.nodes.size() || qb.treelet_image.size() != qb.n_treelet) return TGB_ERR_INVALID;
@@ -1183,7 +1358,7 @@ int tgb200_qbvh_selftest(const float *tri_verts, uint32_t n, const float *rays, 
         const Node4 &src = bvh.nodes[size_t(qb.old_index[i])];
         for (int k = 0; k < 4; ++k) {
             int32_t l = qb.nodes[i].link[k];
-            if (src.link[k] < 0) { if (l != src.link[k]) return TGB_ERR_INVALID; }
+            if (src.link[k] < 0) { if (l != (src.link[k] == kEmptyLink ? empty_link : src.link[k])) return TGB_ERR_INVALID; }
             else if (l < 0 || size_t(l) >= qb.nodes.size() || qb.old_index[size_t(l)] != src.link[k]) return TGB_ERR_INVALID;
         }
     }
@@ -1222,7 +1397,7 @@ int tgb200_qbvh_selftest(const float *tri_verts, uint32_t n, const float *rays, 
                     for (int k = 0; k < 4; ++k) if (t4[k] != INFINITY) stack.push_back(qb.nodes[size_t(cur)].link[k]);
                 } else {
                     int code = ~cur; uint32_t first = uint32_t(code >> 3), count = uint32_t(code & 3) + 1;
-                    for (uint32_t i = 0; i < count; ++i) tri_test(bvh.order[first + i], o, d, tnear, best);
+                    for (uint32_t i = 0; i < count; ++i) if (first + i < n) tri_test(bvh.order[first + i], o, d, tnear, best);
                 }
             }
         }

@@ -5,8 +5,8 @@
 //                    memory with one bulk-async copy (TMA engine, mbarrier), pull rays from the coherence-sorted queue and walk
 //                    the 4-ary BVH over all mesh triangles (+ curve segments); analytic primitives were tested by the kernel
 //                    that created the ray
-//   k_shade        : makeLocalScatterEvent + handleSurface (NEE/MIS query generation, emission, BSDF sample, Russian roulette),
-//                    then the analytic part of this bounce's NEE/MIS queries + top-level BVH cut + compaction of what is left
+//   k_shade        : makeLocalScatterEvent + handleSurface (NEE/MIS query generation, emission, BSDF sample, Russian roulette)
+//   k_shadow_prep  : analytic part of the NEE/MIS queries, top-level BVH cut, compaction of what is left
 //   k_shadow_bvh   : attenuatedEmission / generalizedShadowRay for those (same traversal + epilogue)
 //   k_accum        : folds the bounce's direct-light estimate into the path, NaN guards, compacts survivors into the other
 //                    state buffer, analytic test + BVH cut + coherence key of their next ray
@@ -23,12 +23,14 @@
 namespace tgb {
 
 // ---- path state ----------------------------------------------------------------------------------
-// Persistent per slot (double buffered).  T = 4 consecutive float4 per slot (one 64-byte line: the traversal kernel reaches a
-// path through the sort index and touches exactly this line):
-//   T[4s+0] = (ray origin, tmin)                  T[4s+1] = (ray direction, info)   info = dimension[0:16) | bounce[16:24) | flags
-//   T[4s+2] = closest hit (t, u, v, id)           T[4s+3] = (throughput, path id)   path id = sample_rel*n_pix + pixel_list_index
+// Persistent per slot (double buffered), one float4 array per record so that the streaming kernels move 512 contiguous bytes
+// per warp instruction:
+//   T0[s] = (ray origin, tmin)                    T1[s] = (ray direction, info)     info = dimension[0:16) | bounce[16:24) | flags
+//   T2[s] = closest hit (t, u, v, id)             T3[s] = (throughput, path id)     path id = (sample within the call << pix_bits) | pixel_list_index
+// (One 64-byte record per slot -- a single line per gathered ray in k_trace -- was measured: k_shade +14 %, k_accum +20 %, the
+// 64-byte lane stride quarters the bytes each of their load/store instructions moves per cache line; profiles/r02_d.)
 struct PathBuf {
-    float4 *T;
+    float4 *T0, *T1, *T2, *T3;
     float4 *E;          // (emission accumulated so far = the sample's radiance, unused)
     uint64_t *pcg;      // supplemental PCG state
 };
@@ -61,10 +63,11 @@ struct Ctl {
     uint32_t total;         // camera paths of the (sub)step
     uint32_t capacity;
     uint32_t next_count;    // survivors appended by k_accum
-    uint32_t shadow_count;  // NEE/MIS queries queued for k_shadow_bvh
+    uint32_t shadow_count;  // NEE/MIS queries emitted by k_shade
+    uint32_t shadow_count2; // ... of which k_shadow_prep could not resolve analytically: the queue of k_shadow_bvh
     uint32_t cursor_trace, cursor_shadow;       // ray cursors of the persistent traversal kernels
     unsigned long long traversed, shadow_traversed;   // statistics: queries that reached k_trace / k_shadow_bvh
-    uint32_t iterations, pad;
+    uint32_t iterations;
 };
 
 // ---- closest-hit traversal -------------------------------------------------------------------
@@ -254,23 +257,25 @@ constexpr size_t kStackSmemBytes = size_t(kSmemStack)*kTraceBlock*sizeof(int);
 // dynamic shared memory of a traversal kernel: [treelet image: n_treelet x 64 B][stack][mbarrier]
 TGB_HD size_t trace_smem_bytes(uint32_t n_treelet) { return size_t(n_treelet)*64 + kStackSmemBytes + 16; }
 
+TGB_D uint32_t smem_addr(const void *p) { return uint32_t(__cvta_generic_to_shared(p)); }
+// The stack pointer lives in a plain register variable next to this struct (a member would be spilled with the array).
 struct TravStack {
-    int *smem;                       // this thread's column of the shared stack
+    uint32_t base;                   // shared-space byte address of this thread's column of the shared stack (entry 0)
     int local[kLocalStack];
-    int sp;
-    TGB_D void push(int v) {
-        if (sp < kSmemStack) smem[sp*kTraceBlock] = v;
+    static TGB_D void sts(uint32_t addr, int v) { asm volatile("st.shared.b32 [%0], %1;" :: "r"(addr), "r"(v) : "memory"); }
+    static TGB_D int lds(uint32_t addr) { int v; asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory"); return v; }
+    TGB_D void push(int &sp, int v) {
+        if (sp < kSmemStack) sts(base + uint32_t(sp)*(kTraceBlock*4u), v);
         else if (sp < kStackSize) local[sp - kSmemStack] = v;
         sp++;
     }
-    TGB_D int pop() {
+    TGB_D int pop(int &sp) {
         --sp;
-        return sp < kSmemStack ? smem[sp*kTraceBlock] : local[sp - kSmemStack];
+        return sp < kSmemStack ? lds(base + uint32_t(sp)*(kTraceBlock*4u)) : local[sp - kSmemStack];
     }
 };
 
 // ---- bulk-async staging of the top treelet (cp.async.bulk + mbarrier: the TMA engine copies, no thread touches the data) ----
-TGB_D uint32_t smem_addr(const void *p) { return uint32_t(__cvta_generic_to_shared(p)); }
 TGB_D void mbar_init(uint64_t *bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_addr(bar)), "r"(count) : "memory");
 }
@@ -315,8 +320,18 @@ TGB_D const uint4 *stage_treelet(const DScene &sc, unsigned char *smem_raw) {
 // traversal, if-if state machines with and without several rays per lane, 32-byte quantised BINARY nodes, higher occupancy.
 #define TGB_CSWAP(ta, la, tb, lb) { bool sw_ = tb < ta; float tt_ = sw_ ? tb : ta; tb = sw_ ? ta : tb; ta = tt_; \
                                     int ll_ = sw_ ? lb : la; lb = sw_ ? la : lb; la = ll_; }
-// 1 + q*2^-15 for byte K of word W: bytes (0x3F, 0x80, q, 0x00)
-#define TGB_QF(W, K) __uint_as_float(__byte_perm(W, 0x3F80u, 0x5406u | ((K) << 4)))
+// 1 + q*2^-15 for byte K of word W: result bytes (0x3F, 0x80, q, 0x00).  The selector is an immediate and the constant word
+// 0x3F80 sits in ONE register for all 24 planes of a visit (left to itself the compiler keeps the selector in a register
+// and re-materialises it per plane: +28 instructions per visit, profiles/r02_c_k_trace.md).
+template <int K> TGB_D float qplane(uint32_t w, uint32_t y) {
+    uint32_t r;
+    if (K == 0) asm("prmt.b32 %0, %1, %2, 0x5406;" : "=r"(r) : "r"(w), "r"(y));
+    else if (K == 1) asm("prmt.b32 %0, %1, %2, 0x5416;" : "=r"(r) : "r"(w), "r"(y));
+    else if (K == 2) asm("prmt.b32 %0, %1, %2, 0x5426;" : "=r"(r) : "r"(w), "r"(y));
+    else asm("prmt.b32 %0, %1, %2, 0x5436;" : "=r"(r) : "r"(w), "r"(y));
+    return __uint_as_float(r);
+}
+#define TGB_QF(W, K) qplane<K>(W, qy)
 // CURVES: leaves whose code has bit 2 set hold curve segments (three float4 nodes per record, stored after the triangles);
 // a curve hit keeps (t, position along the segment, interpolated width) in (t, u, v) and id >= n_tris.
 // The traversal is a resumable object: run() walks until the ray is finished (true) or until `yield()` asks for a pause
@@ -346,7 +361,6 @@ struct Traversal {
 
     // one node visit: entry distances of the four children (INFINITY = culled) and their links
     TGB_D void visit(const DScene &sc, const uint4 *treelet, float &t0, float &t1, float &t2, float &t3, int4 &lk) {
-        const int EMPTY = int(0x80000000u);
 #if TGB_QNODES
         uint4 c0, c1, c2;
         if (uint32_t(cur) < sc.n_treelet && treelet) {
@@ -361,6 +375,7 @@ struct Traversal {
         const float bx_ = __fmaf_rn(__uint_as_float(c0.x), idx, -oodx) - ax_;
         const float by_ = __fmaf_rn(__uint_as_float(c0.y), idy, -oody) - ay_;
         const float bz_ = __fmaf_rn(__uint_as_float(c0.z), idz, -oodz) - az_;
+        const uint32_t qy = sc.qy;          // 0x3F80 from the kernel parameters: a value ptxas cannot fold into the PRMT as an immediate
         const uint32_t nxw = nx ? c1.w : c1.z, fxw = nx ? c1.z : c1.w;
         const uint32_t nyw = (ny & 1) ? c2.y : c2.x, fyw = (ny & 1) ? c2.x : c2.y;
         const uint32_t nzw = (nz & 1) ? c2.w : c2.z, fzw = (nz & 1) ? c2.z : c2.w;
@@ -369,10 +384,13 @@ struct Traversal {
             float ay = __fmaf_rn(TGB_QF(nyw, K), ay_, by_), by = __fmaf_rn(TGB_QF(fyw, K), ay_, by_); \
             float az = __fmaf_rn(TGB_QF(nzw, K), az_, bz_), bz = __fmaf_rn(TGB_QF(fzw, K), az_, bz_); \
             float tmn = fmaxf(fmaxf(fmaxf(ax, ay), az), tnear); float tmx = fminf(fminf(fminf(bx, by), bz), h.t); \
-            OUT = (tmn <= tmx && LK != EMPTY) ? tmn : INFINITY; }
+            OUT = tmn <= tmx ? tmn : INFINITY; }
+        // (an empty child slot holds the inverted box lo = 255, hi = 0: its entry distance exceeds its exit distance by 255
+        // grid steps for every ray, so it needs no test of its own)
         TGB_SLAB(0, lk.x, t0) TGB_SLAB(1, lk.y, t1) TGB_SLAB(2, lk.z, t2) TGB_SLAB(3, lk.w, t3)
 #undef TGB_SLAB
 #else
+        const int EMPTY = int(0x80000000u);
         const float4 *nd = sc.nodes + 8*size_t(cur);
         const float4 nrx = __ldg(nd + nx), frx = __ldg(nd + fx), nry = __ldg(nd + ny), fry = __ldg(nd + fy), nrz = __ldg(nd + nz), frz = __ldg(nd + fz);
         lk = __ldg(reinterpret_cast<const int4 *>(nd + 6));
@@ -389,7 +407,7 @@ struct Traversal {
     }
 
     template <class Y>
-    TGB_D bool run(const DScene &sc, const uint4 *treelet, TravStack &stk, Y yield) {
+    TGB_D bool run(const DScene &sc, const uint4 *treelet, TravStack &stk, int &sp, Y yield) {
         while (true) {
         while (cur >= 0) {
             float t0, t1, t2, t3; int4 lk;
@@ -397,22 +415,23 @@ struct Traversal {
             int l0 = lk.x, l1 = lk.y, l2 = lk.z, l3 = lk.w;
             TGB_CSWAP(t0, l0, t1, l1) TGB_CSWAP(t2, l2, t3, l3) TGB_CSWAP(t0, l0, t2, l2) TGB_CSWAP(t1, l1, t3, l3) TGB_CSWAP(t1, l1, t2, l2)
             if (t0 == INFINITY) {
-                if (stk.sp == 0) return true;
-                cur = stk.pop();
+                if (sp == 0) return true;
+                cur = stk.pop(sp);
             } else {
                 // sorted, so the children to push are a prefix of (l1, l2, l3); the nearest of them must end up on top
                 const bool p1 = t1 != INFINITY, p2 = t2 != INFINITY, p3 = t3 != INFINITY;
-                const int c = int(p1) + int(p2) + int(p3);
-                if (stk.sp + 3 <= kSmemStack) {
-                    int *p = stk.smem + stk.sp*kTraceBlock;
-                    if (p3) p[0] = l3;                               // p3 implies c == 3
-                    if (p2) p[(c - 2)*kTraceBlock] = l2;
-                    if (p1) p[(c - 1)*kTraceBlock] = l1;
-                    stk.sp += c;
+                if (sp + 3 <= kSmemStack) {
+                    // slot of l3 = sp, of l2 = sp + [p3], of l1 = sp + [p3] + [p2]
+                    const uint32_t a3 = stk.base + uint32_t(sp)*(kTraceBlock*4u);
+                    const uint32_t a2 = a3 + (p3 ? kTraceBlock*4u : 0u), a1 = a2 + (p2 ? kTraceBlock*4u : 0u);
+                    if (p3) TravStack::sts(a3, l3);
+                    if (p2) TravStack::sts(a2, l2);
+                    if (p1) TravStack::sts(a1, l1);
+                    sp += int(p1) + int(p2) + int(p3);
                 } else {
-                    if (p3) stk.push(l3);
-                    if (p2) stk.push(l2);
-                    if (p1) stk.push(l1);
+                    if (p3) stk.push(sp, l3);
+                    if (p2) stk.push(sp, l2);
+                    if (p1) stk.push(sp, l1);
                 }
                 cur = l0;
             }
@@ -450,8 +469,8 @@ struct Traversal {
             h.t = T/absDen; h.u = U/absDen; h.v = V/absDen; h.id = first + i;
             if (any) return true;
         }
-        if (stk.sp == 0) return true;
-            cur = stk.pop();
+        if (sp == 0) return true;
+            cur = stk.pop(sp);
             if (yield()) return false;
         }
     }
@@ -459,9 +478,9 @@ struct Traversal {
 
 template <bool CURVES>
 TGB_D void bvh_traverse(const DScene &sc, const uint4 *treelet, int *smem_stack, V3 o, V3 d, float tnear, bool any, Hit &h) {
-    Traversal<CURVES> tr; TravStack stk; stk.smem = smem_stack + threadIdx.x; stk.sp = 0;
+    Traversal<CURVES> tr; TravStack stk; stk.base = smem_addr(smem_stack + threadIdx.x); int sp = 0;
     tr.begin(o, d, tnear, any, h);
-    tr.run(sc, treelet, stk, [] { return false; });
+    tr.run(sc, treelet, stk, sp, [] { return false; });
     h = tr.h;
 }
 
@@ -475,7 +494,7 @@ TGB_D void bvh_traverse(const DScene &sc, const uint4 *treelet, int *smem_stack,
 template <bool CURVES, class P>
 TGB_D void bvh_traverse_persistent(const DScene &sc, const uint4 *treelet, int *smem_stack, P &pol, uint32_t n, uint32_t *counter) {
     const unsigned FULL = 0xffffffffu, lane = threadIdx.x & 31u;
-    Traversal<CURVES> tr; TravStack stk; stk.smem = smem_stack + threadIdx.x; stk.sp = 0;
+    Traversal<CURVES> tr; TravStack stk; stk.base = smem_addr(smem_stack + threadIdx.x); int sp = 0;
     bool active = false, exhausted = false;
     for (;;) {
         unsigned need = __ballot_sync(FULL, !active);
@@ -488,13 +507,13 @@ TGB_D void bvh_traverse_persistent(const DScene &sc, const uint4 *treelet, int *
             if (!active) {
                 uint32_t i = base + unsigned(__popc(need & ((1u << lane) - 1u)));
                 V3 o, d; float tnear; Hit h; bool any;
-                if (i < n && pol.fetch(i, o, d, tnear, h, any)) { tr.begin(o, d, tnear, any, h); stk.sp = 0; active = true; }
+                if (i < n && pol.fetch(i, o, d, tnear, h, any)) { tr.begin(o, d, tnear, any, h); sp = 0; active = true; }
             }
         }
         if (!__any_sync(FULL, active)) break;
         if (active) {
             const bool may_refill = !exhausted;
-            bool done = tr.run(sc, treelet, stk, [=] { return may_refill && __popc(__activemask()) < TGB_REFILL_BELOW; });
+            bool done = tr.run(sc, treelet, stk, sp, [=] { return may_refill && __popc(__activemask()) < TGB_REFILL_BELOW; });
             if (done) { pol.finish(tr.h); active = false; }
         }
     }
@@ -565,17 +584,19 @@ TGB_D void make_surface(const DScene &sc, const Hit &h, V3 o, V3 d, Surface &s) 
         s.bsdf = int(__ldg(sc.slots + c.bsdf_first));
         s.eps = maxf(s.eps, (c.curve_mode == TGB_CURVE_CYLINDER ? 0.1f : 0.01f)*h.v);
     } else if (h.id >= 0) {
-        uint32_t g = __ldg(sc.tri_global + h.id);
-        int pi = int(__ldg(sc.tri_prim + g));
+        // shading record of the triangle, stored in BVH leaf order like the intersection records: one hop from the hit id
+        // (no leaf order -> triangle id -> primitive chain of dependent gathers); its last word packs material | primitive << 10
+        const float4 *sh = sc.tri_shade + 4*size_t(h.id);
+        const float4 s0 = __ldg(sh), s1 = __ldg(sh + 1), s2 = __ldg(sh + 2), s3 = __ldg(sh + 3);
+        const float4 c = __ldg(sc.tri_isect + 3*size_t(h.id) + 2);
+        const uint32_t packed = __float_as_uint(s3.w);
+        int pi = int(packed >> 10);
         const DPrim &m = sc.prims[pi];
         s.prim = pi;
-        const float4 c = __ldg(sc.tri_isect + 3*size_t(h.id) + 2);
         // (p1-p0)x(p2-p0) == -(e1 x e2) exactly (e1 = p0-p1, e2 = p2-p0; negation is exact in IEEE)
         V3 isectNg = v3(-c.y, -c.z, -c.w);
         s.backside = dot(isectNg, d) > 0.0f;
         s.Ng = normalize(isectNg);
-        const float4 *sh = sc.tri_shade + 4*size_t(g);
-        const float4 s0 = __ldg(sh), s1 = __ldg(sh + 1), s2 = __ldg(sh + 2), s3 = __ldg(sh + 3);
         float u = h.u, v = h.v;
         if (m.flags & PF_SMOOTH) {
             V3 n0 = v3(s0.x, s0.y, s0.z), n1 = v3(s0.w, s1.x, s1.y), n2 = v3(s1.z, s1.w, s2.x);
@@ -584,7 +605,7 @@ TGB_D void make_surface(const DScene &sc, const Hit &h, V3 o, V3 d, Surface &s) 
         float w0 = 1.0f - u - v;
         s.u = w0*s2.y + u*s2.w + v*s3.y;
         s.v = w0*s2.z + u*s3.x + v*s3.z;
-        int mat = __float_as_int(s3.w);
+        int mat = int(packed & 1023u);
         s.bsdf = int(__ldg(sc.slots + m.bsdf_first + mat));
     } else {
         int pi = -h.id - 2;
@@ -646,7 +667,18 @@ TGB_D uint32_t ray_bin(const DScene &sc, V3 o, V3 d) {
     return (oct << 12) | (uint32_t(cx) << 8) | (uint32_t(cy) << 4) | uint32_t(cz);       // (Morton order of the cell: no gain)
 }
 // ---- kernels ---------------------------------------------------------------------------------
-struct BatchInfo { const uint32_t *pix_id, *pix_seed; uint32_t n_pix, spp_begin; };
+// One render call = a list of pixels (tile-major) x a sample range per pixel.  Uniform steps give every pixel the samples
+// [spp_begin, spp_begin + ns); adaptive steps (PathTraceIntegrator::generateWork, PathTraceIntegrator.cpp:110-134) give the
+// pixels of each 4x4 block their own count and first sample index.  A path carries (k << pix_bits) | pixel_list_index, k = its
+// sample's position within the call; its result slot is k*n_pix + pix (uniform) or pix_first[pix] + k (adaptive).
+struct BatchInfo {
+    const uint32_t *pix_id, *pix_seed; uint32_t n_pix, spp_begin;
+    const uint32_t *pix_first, *pix_base;       // adaptive only (else nullptr): n_pix + 1 result-slot offsets, first sample index per pixel
+    uint32_t pix_bits;
+};
+TGB_D void path_decode(const BatchInfo &bi, uint32_t packed, uint32_t &pix, uint32_t &k) { pix = packed & ((1u << bi.pix_bits) - 1u); k = packed >> bi.pix_bits; }
+TGB_D uint32_t path_sample_index(const BatchInfo &bi, uint32_t pix, uint32_t k) { return (bi.pix_base ? __ldg(bi.pix_base + pix) : bi.spp_begin) + k; }
+TGB_D size_t path_result_slot(const BatchInfo &bi, uint32_t pix, uint32_t k) { return bi.pix_first ? size_t(__ldg(bi.pix_first + pix)) + k : size_t(k)*bi.n_pix + pix; }
 
 // Path (re)generation: the ctl.n_new camera paths [first_path, first_path + n_new) of the step start in slots
 // [n_surv, n_surv + n_new), right behind the survivors that k_accum compacted to the front of the same buffer.  Consecutive
@@ -659,7 +691,14 @@ __global__ void __launch_bounds__(256) k_regen(DScene sc, PathBuf pb, BatchInfo 
     if (j >= ctl->n_new) return;
     const uint32_t i = ctl->n_surv + j;
     const uint32_t path = ctl->first_path + j;
-    uint32_t pix = path % bi.n_pix, smp_i = bi.spp_begin + path/bi.n_pix;
+    uint32_t pix, k;
+    if (!bi.pix_first) { pix = path % bi.n_pix; k = path/bi.n_pix; }
+    else {                                              // adaptive: the pixel whose result slots contain `path`
+        uint32_t lo = 0, hi = bi.n_pix;                 // pix_first[lo] <= path < pix_first[hi]
+        while (hi - lo > 1) { uint32_t mid = (lo + hi) >> 1; if (__ldg(bi.pix_first + mid) <= path) lo = mid; else hi = mid; }
+        pix = lo; k = path - __ldg(bi.pix_first + lo);
+    }
+    const uint32_t smp_i = path_sample_index(bi, pix, k);
     uint32_t pixel_id = __ldg(bi.pix_id + pix);
     Sampler smp; sampler_start(smp, sc.sobol, __ldg(bi.pix_seed + pix), pixel_id, smp_i);
     uint32_t px = pixel_id % sc.cam.res_x, py = pixel_id/sc.cam.res_x;
@@ -674,11 +713,10 @@ __global__ void __launch_bounds__(256) k_regen(DScene sc, PathBuf pb, BatchInfo 
                              sc.cam.plane_dist));
     V3 d = m3mul(sc.cam.m, localD);
     Hit h = analytic_closest(sc, sc.cam.pos, d, 1e-4f, INFINITY);
-    float4 *T = pb.T + 4*size_t(i);
-    T[0] = make_float4(sc.cam.pos.x, sc.cam.pos.y, sc.cam.pos.z, 1e-4f);                      // nearT: math/Ray.hpp:24
-    T[1] = make_float4(d.x, d.y, d.z, __uint_as_float(smp.dimension | F_WAS_SPECULAR | F_ALIVE));
-    T[2] = pack_hit(h);
-    T[3] = make_float4(1.0f, 1.0f, 1.0f, __uint_as_float(path));
+    pb.T0[i] = make_float4(sc.cam.pos.x, sc.cam.pos.y, sc.cam.pos.z, 1e-4f);                  // nearT: math/Ray.hpp:24
+    pb.T1[i] = make_float4(d.x, d.y, d.z, __uint_as_float(smp.dimension | F_WAS_SPECULAR | F_ALIVE));
+    pb.T2[i] = pack_hit(h);
+    pb.T3[i] = make_float4(1.0f, 1.0f, 1.0f, __uint_as_float((k << bi.pix_bits) | pix));
     pb.E[i] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
     pb.pcg[i] = smp.pcg;
     order[i] = i;                    // new camera paths are already coherent: visited in slot order, after the sorted survivors
@@ -693,28 +731,27 @@ TGB_D void count_block(unsigned long long *rays, unsigned long long *hits, bool 
 }
 
 // TraceableScene::intersect for the path rays: the analytic part of the query was done by the kernel that made the
-// ray (k_regen / k_accum); this kernel walks the BVH.  A ray is reached through the sort index and costs one 64-byte line:
-// 48 bytes read (origin, direction, analytic hit) + 16 bytes written (closest hit) = the algorithmic 48 B per query.
+// ray (k_regen / k_accum); this kernel walks the BVH.  A ray is reached through the sort index: 48 bytes read (origin,
+// direction, analytic hit: three 16-byte records) + 16 bytes written (closest hit).
 struct PathRayPolicy {
-    float4 *T; const uint32_t *order; uint32_t n_sorted, n_surv, n_all; uint32_t s;
+    const float4 *T0, *T1; float4 *T2; const uint32_t *order; uint32_t n_sorted, n_surv, n_all; uint32_t s;
     TGB_D bool fetch(uint32_t i, V3 &o, V3 &d, float &tnear, Hit &h, bool &any) {
         // order[] = [survivors to trace, key order | unused (survivors that miss the BVH cut) | new camera paths]
         if (i >= n_sorted) { i += n_surv - n_sorted; if (i >= n_all) return false; }
         s = order[i];
-        const float4 *r = T + 4*size_t(s);
-        float4 a = r[0], b = r[1];
+        float4 a = T0[s], b = T1[s];
         o = v3(a.x, a.y, a.z); tnear = a.w; d = v3(b.x, b.y, b.z);
-        h = unpack_hit(r[2]); any = false;
+        h = unpack_hit(T2[s]); any = false;
         return true;
     }
-    TGB_D void finish(const Hit &h) { T[4*size_t(s) + 2] = pack_hit(h); }
+    TGB_D void finish(const Hit &h) { T2[s] = pack_hit(h); }
 };
 template <bool CURVES>
 __global__ void __launch_bounds__(kTraceBlock, TGB_MINB) k_trace(DScene sc, PathBuf pb, const uint32_t *order, Ctl *ctl) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const uint4 *treelet = stage_treelet(sc, smem_raw);
     int *smem_stack = reinterpret_cast<int *>(smem_raw + size_t(sc.n_treelet)*64);
-    PathRayPolicy pol; pol.T = pb.T; pol.order = order; pol.n_sorted = ctl->n_sorted; pol.n_surv = ctl->n_surv; pol.n_all = ctl->n; pol.s = 0;
+    PathRayPolicy pol; pol.T0 = pb.T0; pol.T1 = pb.T1; pol.T2 = pb.T2; pol.order = order; pol.n_sorted = ctl->n_sorted; pol.n_surv = ctl->n_surv; pol.n_all = ctl->n; pol.s = 0;
     // rays to pull: the sorted survivors + the new camera paths
     const uint32_t n = ctl->n_sorted + ctl->n_new;
     bvh_traverse_persistent<CURVES>(sc, treelet, smem_stack, pol, n, &ctl->cursor_trace);
@@ -798,10 +835,13 @@ TGB_D uint32_t shade_sort_key(const DScene &sc, const Hit &h) {
     if (h.id == HID_MISS) return 0u;
     int bsdf;
     if (h.id >= 0) {
-        uint32_t g = __ldg(sc.tri_global + h.id);
-        const DPrim &m = sc.prims[__ldg(sc.tri_prim + g)];
-        int mat = (uint32_t(h.id) >= sc.n_tris) ? 0 : __float_as_int(__ldg(sc.tri_shade + 4*size_t(g) + 3).w);
-        bsdf = int(__ldg(sc.slots + m.bsdf_first + mat));
+        if (uint32_t(h.id) >= sc.n_tris) {                       // curve segment: one material per primitive
+            const DPrim &m = sc.prims[__ldg(sc.tri_prim + __ldg(sc.tri_global + h.id))];
+            bsdf = int(__ldg(sc.slots + m.bsdf_first));
+        } else {
+            const uint32_t packed = __float_as_uint(__ldg(sc.tri_shade + 4*size_t(h.id) + 3).w);
+            bsdf = int(__ldg(sc.slots + sc.prims[packed >> 10].bsdf_first + (packed & 1023u)));
+        }
     } else bsdf = int(__ldg(sc.slots + sc.prims[-h.id - 2].bsdf_first));
     return 1u + min(sc.bsdfs[bsdf].type, 13u);
 }
@@ -849,16 +889,15 @@ k_shade(DScene sc, PathBuf pb, Scratch sr, BatchInfo bi, Ctl *ctl, uint32_t *squ
     bool valid = i < n;
     // this bounce's NEE / MIS queries: direction, far end (t of the light for occlusion queries), kind
     bool qn = false, qm = false, qn_any = false, qm_any = false;
-    V3 qp = v3s(0.0f), qnd = v3s(0.0f), qmd = v3s(0.0f); float qeps = 5e-4f, qnt = INFINITY, qmt = INFINITY; int qli = 0;
     uint32_t s = 0;
     // one path query (TraceableScene::intersect) was completed for every slot in the queue
-    count_block(&ctr->rays, &ctr->hits, valid, valid && __float_as_int(pb.T[4*size_t(valid ? i : 0) + 2].w) != HID_MISS);
+    count_block(&ctr->rays, &ctr->hits, valid, valid && __float_as_int(pb.T2[valid ? i : 0].w) != HID_MISS);
     if (MATSORT) {
         __shared__ uint32_t bucket[16];
         __shared__ uint16_t perm[kShadeSortBlock];
         if (threadIdx.x < 16) bucket[threadIdx.x] = 0u;
         __syncthreads();
-        uint32_t key = valid ? shade_sort_key(sc, unpack_hit(pb.T[4*size_t(i) + 2])) : 15u;      // slots past the end sort last
+        uint32_t key = valid ? shade_sort_key(sc, unpack_hit(pb.T2[i])) : 15u;      // slots past the end sort last
         uint32_t rank = atomicAdd(&bucket[key], 1u);
         __syncthreads();
         uint32_t before = 0;
@@ -870,8 +909,7 @@ k_shade(DScene sc, PathBuf pb, Scratch sr, BatchInfo bi, Ctl *ctl, uint32_t *squ
     }
     if (valid) {
         s = i;
-        float4 *T = pb.T + 4*size_t(s);
-        const float4 t0 = T[0], t1 = T[1], t2 = T[2], t3 = T[3];
+        const float4 t0 = pb.T0[s], t1 = pb.T1[s], t2 = pb.T2[s], t3 = pb.T3[s];
         uint32_t info = __float_as_uint(t1.w);
         int bounce = int((info >> 16) & 0xFFu);
         bool wasSpecular = (info & F_WAS_SPECULAR) != 0;
@@ -894,18 +932,18 @@ k_shade(DScene sc, PathBuf pb, Scratch sr, BatchInfo bi, Ctl *ctl, uint32_t *squ
                     pb.E[s] = e4;
                 }
             }
-            T[1] = make_float4(d.x, d.y, d.z, __uint_as_float((info & 0x00FFFFFFu) | F_FINAL_CHECK));
+            pb.T1[s] = make_float4(d.x, d.y, d.z, __uint_as_float((info & 0x00FFFFFFu) | F_FINAL_CHECK));
         } else {
             Sampler smp; smp.sobol = sc.sobol; smp.pcg = pb.pcg[s]; smp.dimension = info & 0xFFFFu;
-            const uint32_t path = __float_as_uint(t3.w);
             {
-                uint32_t pix = path % bi.n_pix;
-                smp.index = bi.spp_begin + path/bi.n_pix;
+                uint32_t pix, k; path_decode(bi, __float_as_uint(t3.w), pix, k);
+                smp.index = path_sample_index(bi, pix, k);
                 smp.scramble = __ldg(bi.pix_seed + pix) ^ hash32(__ldg(bi.pix_id + pix));
             }
             Surface sf; make_surface<CURVES>(sc, h, o, d, sf);
             const DBsdf &b = sc.bsdfs[sf.bsdf];
             const float epsilon = sf.eps;                                                    // IntersectionInfo::epsilon
+            int qli = 0;
 
             // makeLocalScatterEvent (TraceBase.cpp:24-51)
             Event e;
@@ -939,6 +977,7 @@ k_shade(DScene sc, PathBuf pb, Scratch sr, BatchInfo bi, Ctl *ctl, uint32_t *squ
                     // (attenuatedEmission, :160-165) and lightF (:279-284) are resolved here and the query that is
                     // traced is a pure blocker test; mesh lights keep the closest-hit query + epilogue.
                     float4 n1 = make_float4(0.0f, 0.0f, 0.0f, 0.0f), m1 = make_float4(0.0f, 0.0f, 0.0f, 0.0f); float mpb = 0.0f;
+                    V3 qnd = v3s(0.0f), qmd = v3s(0.0f); float qnt = INFINITY, qmt = INFINITY;
                     LightSample ls;
                     if (light_sample_direct(sc, l, sf.p, smp, ls)) {
                         e.wo = to_local(e.frame, ls.d);
@@ -1013,8 +1052,7 @@ k_shade(DScene sc, PathBuf pb, Scratch sr, BatchInfo bi, Ctl *ctl, uint32_t *squ
                     // generalizedShadowRay returns 0 unless bounce+1 >= minBounces (TraceBase.cpp:117)
                     if (bounce + 1 < set.min_bounces) { qn = false; qm = false; }
                     if (qn || qm) {
-                        flags |= F_HAS_NEE;
-                        qp = sf.p; qeps = epsilon; qli = li;
+                        flags |= F_HAS_NEE; qli = li;
                         sr.P[s] = make_float4(sf.p.x, sf.p.y, sf.p.z, epsilon);
                         if (qn) { sr.N0[s] = make_float4(qnd.x, qnd.y, qnd.z, qnt); }
                         sr.N1[s] = n1;
@@ -1065,56 +1103,64 @@ k_shade(DScene sc, PathBuf pb, Scratch sr, BatchInfo bi, Ctl *ctl, uint32_t *squ
                         status = bounce < set.max_bounces ? F_ALIVE : (F_ALIVE | F_FINAL_CHECK);
                     }
                 }
-                T[0] = make_float4(no.x, no.y, no.z, ntmin);
-                T[3] = make_float4(thr.x, thr.y, thr.z, t3.w);
+                pb.T0[s] = make_float4(no.x, no.y, no.z, ntmin);
+                pb.T3[s] = make_float4(thr.x, thr.y, thr.z, t3.w);
             }
             pb.pcg[s] = smp.pcg;
-            T[1] = make_float4(nd.x, nd.y, nd.z, __uint_as_float((smp.dimension & 0xFFFFu) | (uint32_t(bounce) << 16) | (wasSpecular ? F_WAS_SPECULAR : 0u) | status | flags));
+            pb.T1[s] = make_float4(nd.x, nd.y, nd.z, __uint_as_float((smp.dimension & 0xFFFFu) | (uint32_t(bounce) << 16) | (wasSpecular ? F_WAS_SPECULAR : 0u) | status | flags));
         }
     }
-    // ---- this bounce's shadow queries: analytic part + top-level cut here (the data is in registers), the rest is queued
-    // for k_shadow_bvh with warp-vote compaction, one atomic per warp
-    bool keep_n = false, keep_m = false; Hit hn, hm; uint32_t vis_n = 0u, vis_m = 0u; bool blk_n = false, blk_m = false;
-    hn.t = INFINITY; hn.u = hn.v = 0.0f; hn.id = HID_MISS; hm = hn;
-    if (qn) {
-        if (qn_any) {
-            blk_n = analytic_any(sc, qp, qnd, qeps, qnt, qli);
-            if (!blk_n) { if (!mesh_cut_hit(sc, qp, qnd, qeps, qnt)) vis_n = 1u; else keep_n = true; }
-        } else {
-            hn = analytic_closest(sc, qp, qnd, qeps, INFINITY);
-            if (!mesh_cut_hit(sc, qp, qnd, qeps, hn.t)) blk_n = hn.id != HID_MISS;     // an analytic primitive is never the (mesh) light
-            else keep_n = true;
-        }
-    }
-    if (qm) {
-        if (qm_any) {
-            blk_m = analytic_any(sc, qp, qmd, qeps, qmt, qli);
-            if (!blk_m) { if (!mesh_cut_hit(sc, qp, qmd, qeps, qmt)) vis_m = 1u; else keep_m = true; }
-        } else {
-            hm = analytic_closest(sc, qp, qmd, qeps, INFINITY);
-            if (!mesh_cut_hit(sc, qp, qmd, qeps, hm.t)) blk_m = hm.id != HID_MISS;
-            else keep_m = true;
-        }
-    }
-    if (qn || qm) *reinterpret_cast<uint2 *>(sr.vis + 2*size_t(s)) = make_uint2(vis_n, vis_m);
+    // enqueue this bounce's shadow queries: warp-vote compaction, one atomic per warp
+    if (qn || qm) *reinterpret_cast<uint2 *>(sr.vis + 2*size_t(s)) = make_uint2(0u, 0u);
     {
         const unsigned FULL = 0xffffffffu;
-        unsigned an = __ballot_sync(FULL, qn), am = __ballot_sync(FULL, qm);
-        unsigned bn = __ballot_sync(FULL, blk_n), bm = __ballot_sync(FULL, blk_m);
-        unsigned mn = __ballot_sync(FULL, keep_n), mm = __ballot_sync(FULL, keep_m);
-        unsigned lane = threadIdx.x & 31;
-        if (lane == 0 && (an | am)) {
-            atomicAdd(&ctr->shadow_rays, (unsigned long long)(__popc(an) + __popc(am)));
-            if (bn | bm) atomicAdd(&ctr->shadow_hits, (unsigned long long)(__popc(bn) + __popc(bm)));
-        }
+        unsigned mn = __ballot_sync(FULL, qn), mm = __ballot_sync(FULL, qm);
         unsigned total = __popc(mn) + __popc(mm);
         if (total) {
-            unsigned base = 0;
+            unsigned lane = threadIdx.x & 31, base = 0;
             if (lane == 0) base = atomicAdd(&ctl->shadow_count, total);
             base = __shfl_sync(FULL, base, 0);
             unsigned lt = (1u << lane) - 1u;
-            if (keep_n) { unsigned at = base + __popc(mn & lt); squeue[at] = (s << 2) | (qn_any ? 2u : 0u); if (!qn_any) sr.SH[at] = pack_hit(hn); }
-            if (keep_m) { unsigned at = base + __popc(mn) + __popc(mm & lt); squeue[at] = (s << 2) | 1u | (qm_any ? 2u : 0u); if (!qm_any) sr.SH[at] = pack_hit(hm); }
+            if (qn) squeue[base + __popc(mn & lt)] = (s << 2) | (qn_any ? 2u : 0u);
+            if (qm) squeue[base + __popc(mn) + __popc(mm & lt)] = (s << 2) | 1u | (qm_any ? 2u : 0u);
+        }
+    }
+}
+
+// Analytic part of the NEE/MIS queries (quads and cubes are tested coherently, every lane runs the same loop), top-level
+// BVH cut, and compaction of what is left for k_shadow_bvh.  (Fusing this into k_shade's tail was measured: the 13 values it
+// needs stay live across the BSDF code, k_shade spills and gets 20 % slower than both kernels together, profiles/r02_b.)
+template <bool CURVES>
+__global__ void __launch_bounds__(256) k_shadow_prep(DScene sc, Scratch sr, const uint32_t *squeue, Ctl *ctl, uint32_t *squeue2, Counters *ctr) {
+    uint32_t i = blockIdx.x*blockDim.x + threadIdx.x;
+    bool valid = i < ctl->shadow_count;
+    bool keep = false, blocked = false; uint32_t q = 0; Hit h; h.t = INFINITY; h.u = h.v = 0.0f; h.id = HID_MISS;
+    if (valid) {
+        q = squeue[i];
+        uint32_t s = q >> 2; bool mis = q & 1u, any = q & 2u;
+        const float4 P = sr.P[s], D = mis ? sr.M0[s] : sr.N0[s];
+        V3 p = v3(P.x, P.y, P.z), d = v3(D.x, D.y, D.z);
+        const float eps = P.w;                                        // info.epsilon of the shading point (TraceBase.cpp:254,295)
+        if (any) {
+            const int li = __float_as_int(sr.D1[s].w);
+            blocked = analytic_any(sc, p, d, eps, D.w, li);
+            if (!blocked) { if (!mesh_cut_hit(sc, p, d, eps, D.w)) sr.vis[2*size_t(s) + (mis ? 1 : 0)] = 1u; else keep = true; }
+        } else {
+            h = analytic_closest(sc, p, d, eps, INFINITY);
+            if (!mesh_cut_hit(sc, p, d, eps, h.t)) blocked = h.id != HID_MISS;       // an analytic primitive is never the (mesh) light: not visible
+            else keep = true;
+        }
+    }
+    count_block(&ctr->shadow_rays, &ctr->shadow_hits, valid, blocked);
+    unsigned m = __ballot_sync(0xffffffffu, keep);
+    if (m) {
+        unsigned lane = threadIdx.x & 31, base = 0;
+        if (lane == 0) base = atomicAdd(&ctl->shadow_count2, unsigned(__popc(m)));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (keep) {
+            uint32_t at = base + __popc(m & ((1u << lane) - 1u));
+            squeue2[at] = q;
+            if (!(q & 2u)) sr.SH[at] = pack_hit(h);
         }
     }
 }
@@ -1145,21 +1191,20 @@ __global__ void __launch_bounds__(kTraceBlock, TGB_MINB) k_shadow_bvh(DScene sc,
     const uint4 *treelet = stage_treelet(sc, smem_raw);
     int *smem_stack = reinterpret_cast<int *>(smem_raw + size_t(sc.n_treelet)*64);
     ShadowPolicy<CURVES> pol; pol.sc = sc; pol.sr = sr; pol.squeue = squeue; pol.hits = &ctr->shadow_hits;
-    bvh_traverse_persistent<CURVES>(sc, treelet, smem_stack, pol, ctl->shadow_count, &ctl->cursor_shadow);
+    bvh_traverse_persistent<CURVES>(sc, treelet, smem_stack, pol, ctl->shadow_count2, &ctl->cursor_shadow);
 }
 
 // Fold this bounce's direct light + surface emission into the path (order as in handleSurface:537-543), apply the
 // NaN guards of traceSample (PathTracer.cpp:119-122,130), store finished samples, and MOVE the survivors' persistent
 // state to the front of the other state buffer (physical compaction: all later accesses are coalesced, no slot
 // indirection).  The survivors' next ray gets the analytic part of its TraceableScene::intersect here.
-__global__ void __launch_bounds__(256) k_accum(DScene sc, PathBuf pb, PathBuf dst, Scratch sr, Ctl *ctl, uint32_t *keys, uint32_t *hist) {
+__global__ void __launch_bounds__(256) k_accum(DScene sc, PathBuf pb, PathBuf dst, Scratch sr, BatchInfo bi, Ctl *ctl, uint32_t *keys, uint32_t *hist) {
     uint32_t s = blockIdx.x*blockDim.x + threadIdx.x;
     bool valid = s < ctl->n;
     bool alive = false; uint32_t info = 0; V3 em = v3s(0.0f);
     float4 t0 = make_float4(0.0f, 0.0f, 0.0f, 0.0f), t1 = t0, t3 = t0;
     if (valid) {
-        const float4 *T = pb.T + 4*size_t(s);
-        t1 = T[1]; t3 = T[3];
+        t1 = pb.T1[s]; t3 = pb.T3[s];
         info = __float_as_uint(t1.w);
         const float4 e4 = pb.E[s];
         em = v3(e4.x, e4.y, e4.z);
@@ -1179,14 +1224,17 @@ __global__ void __launch_bounds__(256) k_accum(DScene sc, PathBuf pb, PathBuf ds
             V3 thr = v3(t3.x, t3.y, t3.z);
             bool bad = false;
             if (alive) {
-                t0 = T[0];
+                t0 = pb.T0[s];
                 bad = isnan(sum(v3(t1.x, t1.y, t1.z)) + sum(v3(t0.x, t0.y, t0.z)));
             }
             bad = bad || isnan(sum(thr) + sum(em));
             if (bad) { em = v3s(0.0f); alive = false; }
         }
         if (alive && finalCheck) alive = false;                  // bounce reached maxBounces: loop exits
-        if (!alive) sr.R[__float_as_uint(t3.w)] = make_float4(em.x, em.y, em.z, 0.0f);       // the sample's radiance
+        if (!alive) {                                                                           // the sample's radiance
+            uint32_t pix, k; path_decode(bi, __float_as_uint(t3.w), pix, k);
+            sr.R[path_result_slot(bi, pix, k)] = make_float4(em.x, em.y, em.z, 0.0f);
+        }
     }
     unsigned m = __ballot_sync(0xffffffffu, alive);
     if (m) {
@@ -1197,11 +1245,10 @@ __global__ void __launch_bounds__(256) k_accum(DScene sc, PathBuf pb, PathBuf ds
             uint32_t t = base + __popc(m & ((1u << lane) - 1u));
             V3 o = v3(t0.x, t0.y, t0.z), d = v3(t1.x, t1.y, t1.z); float tmin = t0.w;
             Hit h = analytic_closest(sc, o, d, tmin, INFINITY);
-            float4 *D = dst.T + 4*size_t(t);
-            D[0] = t0;
-            D[1] = make_float4(t1.x, t1.y, t1.z, __uint_as_float((info & ~(F_HAS_NEE | F_HAS_SURF | F_ALIVE | F_FINAL_CHECK)) | F_ALIVE));
-            D[2] = pack_hit(h);
-            D[3] = t3;
+            dst.T0[t] = t0;
+            dst.T1[t] = make_float4(t1.x, t1.y, t1.z, __uint_as_float((info & ~(F_HAS_NEE | F_HAS_SURF | F_ALIVE | F_FINAL_CHECK)) | F_ALIVE));
+            dst.T2[t] = pack_hit(h);
+            dst.T3[t] = t3;
             dst.E[t] = make_float4(em.x, em.y, em.z, 0.0f);
             dst.pcg[t] = pb.pcg[s];
             uint32_t key = mesh_cut_hit(sc, o, d, tmin, h.t) ? ray_bin(sc, o, d) : kBins;       // kBins: nothing to traverse
@@ -1251,13 +1298,13 @@ __global__ void __launch_bounds__(1024) k_iter_end(uint32_t *hist, Ctl *ctl, int
     }
     __syncthreads();
     if (t == 0) {
-        if (has_bvh) { ctl->traversed += (unsigned long long)ctl->n_sorted + ctl->n_new; ctl->shadow_traversed += ctl->shadow_count; }
+        if (has_bvh) { ctl->traversed += (unsigned long long)ctl->n_sorted + ctl->n_new; ctl->shadow_traversed += ctl->shadow_count2; }
         ctl->iterations++;
         const uint32_t n_surv = ctl->next_count;
         const uint32_t n_new = min(ctl->capacity - n_surv, ctl->total - ctl->issued);
         ctl->first_path = ctl->issued; ctl->issued += n_new;
         ctl->n_surv = n_surv; ctl->n_new = n_new; ctl->n = n_surv + n_new; ctl->n_sorted = total_sorted;
-        ctl->next_count = 0u; ctl->shadow_count = 0u; ctl->cursor_trace = 0u; ctl->cursor_shadow = 0u;
+        ctl->next_count = 0u; ctl->shadow_count = 0u; ctl->shadow_count2 = 0u; ctl->cursor_trace = 0u; ctl->cursor_shadow = 0u;
     }
 }
 // ... and scatter of the slot indices (4 bytes each) to their sorted positions.
@@ -1275,8 +1322,9 @@ __global__ void __launch_bounds__(256) k_resolve(const float4 *R, BatchInfo bi, 
     uint32_t pid = bi.pix_id[pix];
     float mx = fb[3*size_t(pid)], my = fb[3*size_t(pid) + 1], mz = fb[3*size_t(pid) + 2];
     uint32_t cnt = fb_count[pid];
+    if (bi.pix_first) spp_count = bi.pix_first[pix + 1] - bi.pix_first[pix];
     for (uint32_t k = 0; k < spp_count; ++k) {
-        const float4 c = R[size_t(k)*bi.n_pix + pix];
+        const float4 c = R[path_result_slot(bi, pix, k)];
         float cx = c.x, cy = c.y, cz = c.z;
         if (isnan(cx) || isnan(cy) || isnan(cz) || isinf(cx) || isinf(cy) || isinf(cz)) continue;
         float n = float(cnt + 1u); cnt++;
@@ -1284,6 +1332,33 @@ __global__ void __launch_bounds__(256) k_resolve(const float4 *R, BatchInfo bi, 
     }
     fb[3*size_t(pid)] = mx; fb[3*size_t(pid) + 1] = my; fb[3*size_t(pid) + 2] = mz;
     fb_count[pid] = cnt;
+}
+
+// SampleRecord::addSample for every sample of an adaptive step (integrators/path_tracer/SampleRecord.hpp:44-55): one thread per
+// 4x4 variance block folds the luminance of its pixels' samples in the order renderTile produces them
+// (PathTraceIntegrator.cpp:136-156: rows, then columns, then sample index; a block never straddles a 16x16 tile).
+struct SampleRecordD { uint32_t sample_count, next_sample_count, sample_index; float adaptive_weight, mean, running_variance; };
+__global__ void __launch_bounds__(128) k_block_stats(const float4 *R, BatchInfo bi, const uint32_t *pix_slot, uint32_t res_x, uint32_t res_y,
+                                                     uint32_t var_w, uint32_t n_blocks, SampleRecordD *rec) {
+    uint32_t b = blockIdx.x*blockDim.x + threadIdx.x;
+    if (b >= n_blocks) return;
+    SampleRecordD r = rec[b];
+    const uint32_t bx = (b % var_w)*4u, by = (b/var_w)*4u;
+    for (uint32_t y = by; y < min(by + 4u, res_y); ++y)
+        for (uint32_t x = bx; x < min(bx + 4u, res_x); ++x) {
+            const uint32_t pix = pix_slot[x + y*res_x];
+            if (pix == 0xFFFFFFFFu) continue;                       // pixel not in this call's tile list
+            const uint32_t first = bi.pix_first[pix], cnt = bi.pix_first[pix + 1] - first;
+            for (uint32_t k = 0; k < cnt; ++k) {
+                const float4 c = R[size_t(first) + k];
+                const float lum = c.x*0.2126f + c.y*0.7152f + c.z*0.0722f;              // Vec3f::luminance (math/Vec.hpp:195-199)
+                r.sample_count++;
+                const float delta = lum - r.mean;
+                r.mean += delta/float(r.sample_count);
+                r.running_variance += delta*(lum - r.mean);
+            }
+        }
+    rec[b] = r;
 }
 
 // Tile-major pack / unpack of the resident framebuffer: the send/receive side of the one collective on

@@ -45,10 +45,11 @@ class UniformSampler:
         return ((xs >> rot) | (xs << ((-rot) & 31))) & MASK32
 
 
-def dice_tiles(w, h, seed):
+def dice_tiles(w, h, seed, sampler=None):
     """PathTraceIntegrator::diceTiles with the sampler seeded as in prepareForRender
-    (PathTraceIntegrator.cpp:27-42,187): row-major 16x16 tiles, tile sampler seed = hash32(_sampler.nextI())."""
-    s = UniformSampler(hash32(seed))
+    (PathTraceIntegrator.cpp:27-42,187): row-major 16x16 tiles, tile sampler seed = hash32(_sampler.nextI()).
+    `sampler`: the integrator's own UniformSampler (its stream continues into distributeAdaptiveSamples)."""
+    s = sampler if sampler is not None else UniformSampler(hash32(seed))
     n = ((w + TILE_SIZE - 1)//TILE_SIZE)*((h + TILE_SIZE - 1)//TILE_SIZE)
     tiles = (abi.Tile*n)()
     i = 0
@@ -107,6 +108,8 @@ class B200PathTraceIntegrator:
         self.tiles = None
         self.all_tiles = None
         self.seed = 0
+        self.records = None         # one SampleRecord per 4x4 block (PathTraceIntegrator::_samples)
+        self._sampler = None        # PathTraceIntegrator::_sampler
 
     # -- Integrator.cpp:51
     def _advance_spp(self):
@@ -114,17 +117,29 @@ class B200PathTraceIntegrator:
 
     def prepareForRender(self, flat_scene, seed):
         """PathTraceIntegrator::prepareForRender (PathTraceIntegrator.cpp:184-201)."""
-        if flat_scene.adaptive:
-            raise lib.TgbError(abi.TGB_ERR_UNSUPPORTED, "adaptive sampling is outside the hot path (set renderer.adaptive_sampling=false)")
         self._scene = flat_scene
         self.seed = seed & MASK32
         self._current_spp = 0
         self._advance_spp()
         self._ctx = lib.Context(flat_scene, device=self.device, max_paths_in_flight=self.max_paths_in_flight)
         w, h = flat_scene.resolution
-        self.all_tiles = dice_tiles(w, h, self.seed)
+        self._sampler = UniformSampler(hash32(self.seed))
+        self.all_tiles = dice_tiles(w, h, self.seed, self._sampler)
         self.tiles = shard_tiles(self.all_tiles, self.rank, self.world)
+        self.records = (abi.SampleRecord*(((w + 3)//4)*((h + 3)//4)))()
         self._ctx.clear()
+
+    def _generate_work(self):
+        """PathTraceIntegrator::generateWork (PathTraceIntegrator.cpp:110-134) through the library's host-side helper."""
+        import ctypes as C
+        w, h = self._scene.resolution
+        st = C.c_uint64(self._sampler.state)
+        rc = self._ctx.L.tgb200_generate_work(self.records, w, h, self._current_spp, self._next_spp,
+                                              1 if self._scene.adaptive else 0, C.byref(st))
+        self._sampler.state = st.value
+        if rc < 0:
+            raise lib.TgbError(rc, "tgb200_generate_work failed")
+        return rc == 1
 
     def teardownAfterRender(self):
         self.waitForCompletion_noraise()
@@ -145,16 +160,20 @@ class B200PathTraceIntegrator:
     def startRender(self, completionCallback=lambda: None):
         """Asynchronous like the reference (PathTraceIntegrator.cpp:220-239): returns after enqueueing; the
         callback fires when the step's samples are in the framebuffer (or immediately if there is no work)."""
-        if self.done():
+        if self.done() or not self._generate_work():
             self._current_spp = self._next_spp
             self._advance_spp()
             completionCallback()
             return
         begin, count = self._current_spp, self._next_spp - self._current_spp
+        self._ctx.clear_abort()
 
         def work():
             try:
-                self._ctx.render_resident(count, seed=self.seed, spp_begin=begin, tiles=self.tiles)
+                if self._scene.adaptive:        # per-block sample counts + Welford statistics (SampleRecord) on the device
+                    self._ctx.render_adaptive(self.records, seed=self.seed, tiles=self.tiles)
+                else:
+                    self._ctx.render_resident(count, seed=self.seed, spp_begin=begin, tiles=self.tiles)
                 self._current_spp = self._next_spp
                 self._advance_spp()
             except Exception as e:      # captured and rethrown from waitForCompletion (thread/TaskGroup.hpp:57-74)

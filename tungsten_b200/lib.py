@@ -31,12 +31,16 @@ def load():
     L.tgb200_render_resident.argtypes = [vp, vp, u32, u32, u32, u32]
     L.tgb200_clear_framebuffer.argtypes = [vp]
     L.tgb200_read_framebuffer.argtypes = [vp, vp, vp]
+    L.tgb200_write_framebuffer.argtypes = [vp, vp, vp]
+    L.tgb200_generate_work.argtypes = [vp, u32, u32, u32, u32, C.c_int, C.POINTER(C.c_uint64)]
+    L.tgb200_render_adaptive.argtypes = [vp, vp, u32, u32, vp]
     L.tgb200_framebuffer_device_ptr.argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_uint64)]
     L.tgb200_trace_closest.argtypes = [vp, vp, vp, u32]
     L.tgb200_pack_tiles.argtypes = [vp, vp, u32, vp]
     L.tgb200_unpack_tiles.argtypes = [vp, vp, u32, vp, u32]
     L.tgb200_get_stats.argtypes = [vp, C.POINTER(abi.Stats)]
     L.tgb200_set_profiling.argtypes = [vp, C.c_int]
+    L.tgb200_set_stream.argtypes = [vp, vp]
     L.tgb200_scene_info.argtypes = [vp, C.POINTER(u32), C.POINTER(u32), C.POINTER(u32), C.POINTER(C.c_uint64), C.POINTER(u32)]
     L.tgb200_reset_stats.argtypes = [vp]
     L.tgb200_abort.argtypes = [vp]
@@ -103,6 +107,15 @@ class Context:
         self._check(self.L.tgb200_read_framebuffer(self.h, mean.ctypes.data, count.ctypes.data))
         return mean, count
 
+    def write_framebuffer(self, mean, count):
+        mean = np.ascontiguousarray(mean, dtype=np.float32); count = np.ascontiguousarray(count, dtype=np.uint32)
+        self._check(self.L.tgb200_write_framebuffer(self.h, mean.ctypes.data, count.ctypes.data))
+
+    def render_adaptive(self, records, seed=0xBA5EBA11, tiles=None):
+        """records: ctypes array of abi.SampleRecord, one per 4x4 block (in/out)."""
+        n = 0 if tiles is None else len(tiles)
+        self._check(self.L.tgb200_render_adaptive(self.h, tiles, n, seed, records))
+
     def framebuffer_device_ptr(self):
         p = C.c_void_p(); n = C.c_uint64()
         self._check(self.L.tgb200_framebuffer_device_ptr(self.h, C.byref(p), C.byref(n)))
@@ -127,6 +140,10 @@ class Context:
 
     def reset_stats(self):
         self._check(self.L.tgb200_reset_stats(self.h))
+
+    def set_stream(self, cuda_stream):
+        """Run on the caller's CUDA stream (e.g. torch.cuda.current_stream().cuda_stream); None = the context's own."""
+        self._check(self.L.tgb200_set_stream(self.h, cuda_stream))
 
     def set_profiling(self, on):
         self._check(self.L.tgb200_set_profiling(self.h, 1 if on else 0))
