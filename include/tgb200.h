@@ -50,7 +50,8 @@ typedef struct tgb_texture {
     const float *texels;    /* BITMAP: res_u*res_v RGB fp32, row-major, top row first (host ptr)   */
 } tgb_texture;
 
-/* ---- BSDFs (reference: src/core/bsdfs/; the lobes north_star names + Null) ------------- */
+/* ---- BSDFs (reference: src/core/bsdfs/; the lobes north_star names + Null, the coat of config C0, the Dirac lobes the
+ *      shipped scenes use: MirrorBsdf, ConductorBsdf, DielectricBsdf) ------------------------------------------------ */
 enum {
     TGB_BSDF_NULL = 0, TGB_BSDF_LAMBERT = 1, TGB_BSDF_ROUGH_CONDUCTOR = 2,
     TGB_BSDF_ROUGH_DIELECTRIC = 3, TGB_BSDF_PLASTIC = 4, TGB_BSDF_ROUGH_PLASTIC = 5,
@@ -80,7 +81,11 @@ typedef struct tgb_bsdf {
 typedef struct tgb_vertex   { float pos[3]; float normal[3]; float uv[2]; } tgb_vertex;
 typedef struct tgb_triangle { uint32_t v0, v1, v2; int32_t material; } tgb_triangle;
 
-enum { TGB_PRIM_MESH = 0, TGB_PRIM_QUAD = 1, TGB_PRIM_CUBE = 2, TGB_PRIM_INFINITE_SPHERE = 3, TGB_PRIM_CURVES = 4 };
+enum { TGB_PRIM_MESH = 0, TGB_PRIM_QUAD = 1, TGB_PRIM_CUBE = 2, TGB_PRIM_INFINITE_SPHERE = 3, TGB_PRIM_CURVES = 4,
+       TGB_PRIM_INFINITE_SPHERE_CAP = 5,   /* primitives/InfiniteSphereCap.cpp: a disc of directions on the sky ("sun")          */
+       TGB_PRIM_SKYDOME = 6 };             /* primitives/Skydome.cpp: an InfiniteSphere whose emission bitmap is the prepared
+                                              512x256 sky image (Skydome::prepareForRender; the caller passes its texels), lookup
+                                              without rotation, approximateRadiance 4 pi avg (Skydome.cpp:281)                 */
 /* Curves::CurveMode (primitives/Curves.cpp:20-25); "ribbon" is outside the hot path                 */
 enum { TGB_CURVE_CYLINDER = 0, TGB_CURVE_HALF_CYLINDER = 1, TGB_CURVE_BCSDF_CYLINDER = 2 };
 
@@ -105,6 +110,9 @@ typedef struct tgb_primitive {
     const float    *curve_nodes;    uint32_t n_curve_nodes;
     const uint32_t *curve_segments; uint32_t n_curve_segments;
     uint32_t curve_mode;        /* TGB_CURVE_*                                                      */
+    /* INFINITE_SPHERE_CAP: InfiniteSphereCap::_capDir and _cosCapAngle as prepared (InfiniteSphereCap.cpp:231-247); do_sample;
+     * emission_tex is evaluated at uv (0, 0) (:191-199)                                                                   */
+    float cap_dir[3]; float cap_cos;
 } tgb_primitive;
 
 /* ---- camera (reference: cameras/PinholeCamera.cpp:28-35,70-86; Camera.cpp:44-68) ------------ */

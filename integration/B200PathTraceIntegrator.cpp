@@ -6,6 +6,9 @@
 #include "cameras/PinholeCamera.hpp"
 #include "cameras/OutputBufferSettings.hpp"
 #include "primitives/InfiniteSphere.hpp"
+#include "primitives/InfiniteSphereCap.hpp"
+#include "primitives/Skydome.hpp"
+#include "math/Angle.hpp"
 #include "primitives/TriangleMesh.hpp"
 #include "primitives/Curves.hpp"
 #include "bsdfs/HairBcsdf.hpp"
@@ -14,6 +17,9 @@
 #include "primitives/Quad.hpp"
 #include "primitives/Cube.hpp"
 #include "bsdfs/RoughDielectricBsdf.hpp"
+#include "bsdfs/DielectricBsdf.hpp"
+#include "bsdfs/ConductorBsdf.hpp"
+#include "bsdfs/MirrorBsdf.hpp"
 #include "bsdfs/RoughConductorBsdf.hpp"
 #include "bsdfs/RoughPlasticBsdf.hpp"
 #include "bsdfs/SmoothCoatBsdf.hpp"
@@ -50,6 +56,7 @@ struct Flattener
     rapidjson::Document jsonDoc;    // allocator for the toJson() calls that read back private parameters
     std::map<const Bsdf *, int> bsdfIds;
     std::map<const Texture *, int> texIds;
+    const std::vector<std::shared_ptr<Primitive>> *scenePrims = nullptr;
 
     static void put(float *dst, const Vec3f &v) { dst[0] = v.x(); dst[1] = v.y(); dst[2] = v.z(); }
 
@@ -67,7 +74,12 @@ struct Flattener
             o.res_u = c->resU();
             o.res_v = c->resV();
         } else if (const BitmapTexture *b = dynamic_cast<const BitmapTexture *>(t)) {
-            // texel centres through the public operator[]: (x+0.5)/w, 1-(y+0.5)/h reproduce the stored texels exactly
+            // texel centres through the public operator[] of a NEAREST-filtered clone: (x+0.5)/w and 1-(y+0.5)/h land inside texel
+            // (x, y) for every size, so the stored texels come back exactly (a bilinear read-back would mix in a neighbour with
+            // a weight of ~1e-7..1e-4 whenever w or h is not a power of two)
+            std::unique_ptr<Texture> nearestOwner(b->clone());
+            BitmapTexture *nearest = static_cast<BitmapTexture *>(nearestOwner.get());
+            nearest->setLinear(false);
             o.type = TGB_TEX_BITMAP;
             o.res_u = b->w();
             o.res_v = b->h();
@@ -76,7 +88,7 @@ struct Flattener
             std::vector<float> &tx = texelStore.back();
             for (int y = 0; y < b->h(); ++y) {
                 for (int x = 0; x < b->w(); ++x) {
-                    Vec3f c = (*b)[Vec2f((x + 0.5f)/b->w(), 1.0f - (y + 0.5f)/b->h())];
+                    Vec3f c = (*nearest)[Vec2f((x + 0.5f)/b->w(), 1.0f - (y + 0.5f)/b->h())];
                     put(&tx[3*(size_t(y)*b->w() + x)], c);
                 }
             }
@@ -124,6 +136,16 @@ struct Flattener
             o.roughness_tex = texture(c->roughness().get());
             put(o.eta, c->eta());
             put(o.k, c->k());
+        } else if (dynamic_cast<const MirrorBsdf *>(b)) {
+            o.type = TGB_BSDF_MIRROR;
+        } else if (const ConductorBsdf *cd = dynamic_cast<const ConductorBsdf *>(b)) {
+            o.type = TGB_BSDF_CONDUCTOR;
+            put(o.eta, cd->eta());
+            put(o.k, cd->k());
+        } else if (const DielectricBsdf *di = dynamic_cast<const DielectricBsdf *>(b)) {
+            o.type = TGB_BSDF_DIELECTRIC;
+            o.ior = di->ior();
+            o.enable_refraction = di->enableTransmission() ? 1 : 0;
         } else if (const RoughDielectricBsdf *d = dynamic_cast<const RoughDielectricBsdf *>(b)) {
             o.type = TGB_BSDF_ROUGH_DIELECTRIC;
             o.distribution = distribution(d->distributionName());
@@ -278,6 +300,30 @@ struct Flattener
             for (int r = 0; r < 3; ++r)
                 for (int c = 0; c < 3; ++c)
                     o.rot[r*3 + c] = rot[r*4 + c];
+        } else if (InfiniteSphereCap *cap = dynamic_cast<InfiniteSphereCap *>(&p)) {
+            // InfiniteSphereCap::prepareForRender (InfiniteSphereCap.cpp:231-247); the pivot object's name is private: read it back
+            o.type = TGB_PRIM_INFINITE_SPHERE_CAP;
+            Mat4f capTform = tform;
+            rapidjson::Value js = cap->toJson(jsonDoc.GetAllocator());
+            if (js.HasMember("skydome") && js["skydome"].IsString() && scenePrims) {
+                for (const std::shared_ptr<Primitive> &q : *scenePrims)
+                    if (q->name() == js["skydome"].GetString())
+                        capTform = q->transform();
+            }
+            put(o.cap_dir, capTform.transformVector(Vec3f(0.0f, 1.0f, 0.0f)).normalized());
+            o.cap_cos = std::cos(Angle::degToRad(cap->capAngleDeg()));
+            o.do_sample = p.isSamplable() ? 1 : 0;
+            o.bsdf_count = 0;
+        } else if (dynamic_cast<Skydome *>(&p)) {
+            // Skydome::prepareForRender has already built the 512x256 sky image: it IS the primitive's emission texture
+            // (Skydome.cpp:317-320); the library treats it as an environment sphere without rotation
+            o.type = TGB_PRIM_SKYDOME;
+            if (o.emission_tex < 0 || textures[size_t(o.emission_tex)].type != TGB_TEX_BITMAP)
+                FAIL("b200_path_tracer: skydome without a prepared sky image");
+            const float id[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+            std::memcpy(o.rot, id, sizeof(id));
+            o.do_sample = p.isSamplable() ? 1 : 0;
+            o.bsdf_count = 0;
         } else if (dynamic_cast<InfiniteSphere *>(&p)) {
             o.type = TGB_PRIM_INFINITE_SPHERE;
             Mat4f rot = tform.extractRotation();
@@ -397,6 +443,7 @@ void B200PathTraceIntegrator::prepareForRender(TraceableScene &scene, uint32 see
         FAIL("b200_path_tracer: only the pinhole camera is on the hot path");
 
     Flattener f;
+    f.scenePrims = &scene.primitives();
     for (const std::shared_ptr<Primitive> &p : scene.primitives())
         f.primitive(*p);
 

@@ -13,6 +13,8 @@ needs /root/reference and the binaries built by `make -C oracle/ref`).
   <scene>/            scene JSON + .wo3 written by tungsten_b200.synth, plus
   <scene>/ref_pathseed.pfm   framebuffer of oracle/_ref/tungsten_pathseed (per-path reseed contract)
   <scene>/ref_stock.pfm      framebuffer of the UNMODIFIED reference binary
+  hair_sky/                  curves + hair BCSDF lit by the shipped hair scene's own emitters (infinite_sphere_cap + skydome);
+                             scene_sky.pfm = the image Skydome::prepareForRender computed, dumped through the reference's classes
   cornell_adaptive/          the same with renderer.adaptive_sampling = true, 48 spp in three 16-spp steps
 
 The fixtures are small (64x64) so that the CPU test-suite stays fast; they travel to the GPU box with the
@@ -197,6 +199,9 @@ KAT_BSDF_CPP = r"""
 #include "bsdfs/PlasticBsdf.hpp"
 #include "bsdfs/RoughPlasticBsdf.hpp"
 #include "bsdfs/SmoothCoatBsdf.hpp"
+#include "bsdfs/MirrorBsdf.hpp"
+#include "bsdfs/ConductorBsdf.hpp"
+#include "bsdfs/DielectricBsdf.hpp"
 #include "textures/ConstantTexture.hpp"
 #include "primitives/IntersectionInfo.hpp"
 #include "samplerecords/SurfaceScatterEvent.hpp"
@@ -226,6 +231,13 @@ int main() {
       b->setSigmaA(Vec3f(0.1f, 0.2f, 0.3f)); b->setAlbedo(std::make_shared<ConstantTexture>(Vec3f(0.8f, 0.3f, 0.2f))); list.push_back(b); }
     { auto sub = std::make_shared<RoughConductorBsdf>(); sub->setDistributionName("beckmann");
       auto b = std::make_shared<SmoothCoatBsdf>(); b->setIor(1.7f); b->setThickness(5.0f); b->setSigmaA(Vec3f(0.1f, 0.2f, 0.5f)); b->setSubstrate(sub); list.push_back(b); }
+    // the Dirac lobes (appended: the serial PCG stream of the draws above is unchanged)
+    { auto b = std::make_shared<MirrorBsdf>(); b->setAlbedo(std::make_shared<ConstantTexture>(Vec3f(0.9f, 0.8f, 0.7f))); list.push_back(b); }
+    { auto b = std::make_shared<ConductorBsdf>(); list.push_back(b); }
+    { auto b = std::make_shared<ConductorBsdf>(); b->setEta(Vec3f(0.143f, 0.375f, 1.442f)); b->setK(Vec3f(3.98f, 2.39f, 1.6f));
+      b->setAlbedo(std::make_shared<ConstantTexture>(Vec3f(0.95f, 0.9f, 0.85f))); list.push_back(b); }
+    { auto b = std::make_shared<DielectricBsdf>(); list.push_back(b); }
+    { auto b = std::make_shared<DielectricBsdf>(1.33f); b->setEnableTransmission(false); b->setAlbedo(std::make_shared<ConstantTexture>(Vec3f(0.8f, 0.9f, 1.0f))); list.push_back(b); }
     IntersectionInfo info; info.uv = Vec2f(0.3f, 0.4f);
     printf("{\n\"bsdfs\": [");
     for (size_t n = 0; n < list.size(); ++n) {
@@ -261,9 +273,13 @@ int main() {
             sampler.startPath(uint32(k), 7);
             SurfaceScatterEvent ev(&info, &sampler, TangentFrame(Vec3f(0.0f, 0.0f, 1.0f)), wi, BsdfLobes::AllLobes, false);
             bool ok = list[n]->sample(ev);
-            printf("%s[%u, %u, %u, %d, %u, %u, %u, %u, %u, %u, %u, %u]", k ? ", " : "", bits(wi.x()), bits(wi.y()), bits(wi.z()), ok ? 1 : 0,
+            // eval()/pdf() at the sampled direction (all lobes requested): exact mirror / refraction directions for the Dirac lobes
+            Vec3f fs(0.0f); float ps = 0.0f;
+            if (ok) { SurfaceScatterEvent e2(&info, nullptr, TangentFrame(Vec3f(0.0f, 0.0f, 1.0f)), wi, BsdfLobes::AllLobes, false); e2.wo = ev.wo; fs = list[n]->eval(e2); ps = list[n]->pdf(e2); }
+            printf("%s[%u, %u, %u, %d, %u, %u, %u, %u, %u, %u, %u, %u, %u, %u, %u, %u]", k ? ", " : "", bits(wi.x()), bits(wi.y()), bits(wi.z()), ok ? 1 : 0,
                    ok ? bits(ev.wo.x()) : 0u, ok ? bits(ev.wo.y()) : 0u, ok ? bits(ev.wo.z()) : 0u, ok ? bits(ev.weight.x()) : 0u,
-                   ok ? bits(ev.weight.y()) : 0u, ok ? bits(ev.weight.z()) : 0u, ok ? bits(ev.pdf) : 0u, ok ? lobe_mask(ev.sampledLobe) : 0u);
+                   ok ? bits(ev.weight.y()) : 0u, ok ? bits(ev.weight.z()) : 0u, ok ? bits(ev.pdf) : 0u, ok ? lobe_mask(ev.sampledLobe) : 0u,
+                   bits(fs.x()), bits(fs.y()), bits(fs.z()), bits(ps));
         }
         printf("]");
     }
@@ -437,6 +453,67 @@ def make_kat_instances():
     _build_and_run_kat(KAT_INSTANCE_CPP, "kat_instances", "kat_instances.json")
 
 
+SKY_DUMP_CPP = r'''
+// Dumps the image Skydome::prepareForRender computes (Hosek-Wilkie model, thirdparty/skylight) for the first skydome of a scene
+// file: 512 x 256 RGB float32, top row first, raw.
+#include <cstdio>
+#include <memory>
+#include "io/Scene.hpp"
+#include "primitives/Skydome.hpp"
+#include "textures/BitmapTexture.hpp"
+#include "thread/ThreadUtils.hpp"
+using namespace Tungsten;
+int main(int argc, char **argv) {
+    ThreadUtils::startThreads(1);
+    std::unique_ptr<Scene> scene(Scene::load(Path(argv[1])));
+    for (const std::shared_ptr<Primitive> &p : scene->primitives()) {
+        Skydome *sky = dynamic_cast<Skydome *>(p.get());
+        if (!sky) continue;
+        sky->prepareForRender();
+        BitmapTexture *b = dynamic_cast<BitmapTexture *>(sky->emission().get());
+        std::unique_ptr<Texture> owner(b->clone());
+        BitmapTexture *nearest = static_cast<BitmapTexture *>(owner.get());
+        nearest->setLinear(false);
+        FILE *f = fopen(argv[2], "wb");
+        for (int y = 0; y < b->h(); ++y) for (int x = 0; x < b->w(); ++x) {
+            Vec3f c = (*nearest)[Vec2f((x + 0.5f)/b->w(), 1.0f - (y + 0.5f)/b->h())];
+            float v[3] = {c.x(), c.y(), c.z()};
+            fwrite(v, 4, 3, f);
+        }
+        fclose(f);
+        printf("%d %d\n", b->w(), b->h());
+        return 0;
+    }
+    return 1;
+}
+'''
+
+
+def dump_sky_image(scene_json, out_pfm):
+    """Skydome::prepareForRender of the scene's skydome, through the reference's own classes -> PFM (the flattener's "sky_image")."""
+    import glob
+    import numpy as np
+    from tungsten_b200 import scene as S
+    d = tempfile.mkdtemp()
+    src = os.path.join(d, "skydump.cpp"); open(src, "w").write(SKY_DUMP_CPP)
+    exe = os.path.join(d, "skydump")
+    obj = os.path.join(ROOT, "oracle", "_ref", "obj")
+    objs = [o for o in glob.glob(os.path.join(obj, "**", "*.o"), recursive=True)
+            if not o.endswith("tungsten_main.o") and os.sep + "pathseed" + os.sep not in o]
+    cmd = ["/opt/gcc/bin/g++", "-std=c++11", "-O2", "-march=core2", "-mssse3", "-mno-fma", "-DCONSTEXPR=constexpr", "-DRAPIDJSON_HAS_STDSTRING=1",
+           "-I" + REF + "/src/core", "-I" + REF + "/src/thirdparty", "-I" + REF + "/src/thirdparty/embree/include", "-I" + REF + "/src", "-w", src] + objs + \
+          ["-o", exe, "-lpthread", "-ldl"]
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if r.returncode != 0:
+        print(r.stdout[-3000:]); raise SystemExit("sky dump program failed to build")
+    raw = os.path.join(d, "sky.bin")
+    w, h = [int(x) for x in subprocess.check_output([exe, os.path.abspath(scene_json), raw], text=True).split()]
+    img = np.fromfile(raw, dtype=np.float32).reshape(h, w, 3)
+    S.save_pfm(out_pfm, img)
+    shutil.rmtree(d)
+    return img
+
+
 def make_kat_lights():
     """Known answers of sampleDirect / intersect / directPdf / evalDirect of the reference's Quad, TriangleMesh and
     InfiniteSphere(+BitmapTexture importance map) classes -> kat_lights.json."""
@@ -487,6 +564,9 @@ def make_scenes():
     scenes["curves_plastic"] = synth.hair_scene(os.path.join(HERE, "curves_plastic"), "scene", n_curves=300, res=res, spp=spp, mode="cylinder",
                                                 bsdf={"type": "rough_plastic", "albedo": [0.6, 0.4, 0.2], "roughness": 0.2}, thickness=0.015,
                                                 taper=True, subsample=0.3)
+    # the two emitters of the shipped hair scene: infinite_sphere_cap (sampled sun) + skydome (unsampled sky); min_bounces 1 as shipped
+    scenes["hair_sky"] = synth.hair_scene(os.path.join(HERE, "hair_sky"), "scene", n_curves=300, res=res, spp=spp, shipped_lights=True, min_bounces=1)
+    dump_sky_image(scenes["hair_sky"], os.path.join(HERE, "hair_sky", "scene_sky.pfm"))
     # adaptive sampling (PathTraceIntegrator::generateWork): three 16-spp steps, the 2nd and 3rd distributed by the blocks' error
     ad = synth.cornell_box(res=res, spp=48)
     ad["renderer"].update(adaptive_sampling=True, spp_step=16)

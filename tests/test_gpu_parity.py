@@ -77,7 +77,7 @@ def test_golden_scenes_against_reference_fixtures():
     # curve scenes: see test_curves_and_hair for why their "close" bar is lower
     for name, exact_min, close_min in [("cornell", 0.5, 0.985), ("cornell_short", 0.5, 0.985), ("cornell_mesh", 0.5, 0.985),
                                        ("materials", 0.5, 0.985), ("materials_env", 0.5, 0.985), ("coat_env", 0.3, 0.985),
-                                       ("hair", 0.3, 0.97), ("hair_dark", 0.3, 0.97), ("curves_lambert", 0.5, 0.97),
+                                       ("hair", 0.3, 0.97), ("hair_dark", 0.3, 0.97), ("hair_sky", 0.3, 0.97), ("curves_lambert", 0.5, 0.97),
                                        ("curves_plastic", 0.5, 0.97)]:
         fs = scene.load_scene(os.path.join(g, name, "scene.json"))
         want = scene.load_pfm(os.path.join(g, name, "ref_pathseed.pfm"))
@@ -302,3 +302,33 @@ def test_adaptive_sampling_against_reference_binary():
         steps, cnt.min(), cnt.max(), same_cnt, close, exact, same_rec))
     assert steps == 3 and cnt.min() >= 18 and cnt.max() > 48
     assert same_cnt >= 0.97 and close >= 0.97
+
+
+@pytest.mark.parametrize("adaptive", [False, True])
+def test_resume_state_round_trip(adaptive):
+    """Integrator::saveRenderResumeData / resumeRender (Integrator.cpp:108-162) through the twin's save_state / load_state (=
+    the adapter's saveState / loadState + tgb200_write_framebuffer): a render stopped after 16 spp, torn down, and continued in
+    a fresh context to 48 spp equals the uninterrupted render bit for bit (block records, sampler state and the device
+    framebuffer all travel)."""
+    import os
+    from tungsten_b200 import integrator
+    g = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "cornell_adaptive")
+    fs = scene.load_scene(os.path.join(g, "scene.json"))
+    fs.adaptive = adaptive
+
+    def run(it, until):
+        while not it.done() and it.currentSpp() < until:
+            it.startRender(); it.waitForCompletion()
+
+    a = integrator.B200PathTraceIntegrator(); a.prepareForRender(fs, 0xBA5EBA11); run(a, 48)
+    whole, whole_cnt = a.context.read_framebuffer(); a.teardownAfterRender()
+    b = integrator.B200PathTraceIntegrator(); b.prepareForRender(fs, 0xBA5EBA11); run(b, 16)
+    assert b.currentSpp() == 16
+    state = b.save_state(); b.teardownAfterRender()
+    c = integrator.B200PathTraceIntegrator(); c.prepareForRender(fs, 0xBA5EBA11); c.load_state(state)
+    assert c.currentSpp() == 16 and c.nextSpp() == 32
+    run(c, 48)
+    resumed, resumed_cnt = c.context.read_framebuffer(); c.teardownAfterRender()
+    assert np.array_equal(resumed_cnt, whole_cnt) and np.array_equal(resumed, whole)
+    if adaptive:
+        assert whole_cnt.max() > 48

@@ -14,7 +14,7 @@ TEX_CONSTANT, TEX_CHECKER, TEX_BITMAP = 0, 1, 2
 (BSDF_NULL, BSDF_LAMBERT, BSDF_ROUGH_CONDUCTOR, BSDF_ROUGH_DIELECTRIC, BSDF_PLASTIC, BSDF_ROUGH_PLASTIC,
  BSDF_SMOOTH_COAT, BSDF_CONDUCTOR, BSDF_DIELECTRIC, BSDF_MIRROR, BSDF_HAIR) = range(11)
 DIST_BECKMANN, DIST_PHONG, DIST_GGX = 0, 1, 2
-PRIM_MESH, PRIM_QUAD, PRIM_CUBE, PRIM_INFINITE_SPHERE, PRIM_CURVES = 0, 1, 2, 3, 4
+PRIM_MESH, PRIM_QUAD, PRIM_CUBE, PRIM_INFINITE_SPHERE, PRIM_CURVES, PRIM_INFINITE_SPHERE_CAP, PRIM_SKYDOME = 0, 1, 2, 3, 4, 5, 6
 CURVE_CYLINDER, CURVE_HALF_CYLINDER, CURVE_BCSDF_CYLINDER = 0, 1, 2
 (FILTER_DIRAC, FILTER_BOX, FILTER_TENT, FILTER_GAUSSIAN, FILTER_MITCHELL, FILTER_CATMULL_ROM,
  FILTER_LANCZOS) = range(7)
@@ -53,7 +53,8 @@ class Primitive(C.Structure):
                 ("do_sample", u32),
                 ("curve_nodes", C.POINTER(f32)), ("n_curve_nodes", u32),
                 ("curve_segments", C.POINTER(u32)), ("n_curve_segments", u32),
-                ("curve_mode", u32)]
+                ("curve_mode", u32),
+                ("cap_dir", F3), ("cap_cos", f32)]
 
 
 class Camera(C.Structure):

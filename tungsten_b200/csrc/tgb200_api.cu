@@ -169,6 +169,8 @@ uint32_t bsdf_lobes(const tgb_bsdf &b) {
     case TGB_BSDF_ROUGH_DIELECTRIC: return b.enable_refraction ? (LOBE_GLOSSY_R | LOBE_GLOSSY_T) : LOBE_GLOSSY_R;
     case TGB_BSDF_PLASTIC: return LOBE_SPEC_R | LOBE_DIFFUSE_R;
     case TGB_BSDF_ROUGH_PLASTIC: return LOBE_GLOSSY_R | LOBE_DIFFUSE_R;
+    case TGB_BSDF_MIRROR: case TGB_BSDF_CONDUCTOR: return LOBE_SPEC_R;                   // MirrorBsdf.cpp:13, ConductorBsdf.cpp:19
+    case TGB_BSDF_DIELECTRIC: return b.enable_refraction ? (LOBE_SPEC_R | LOBE_SPEC_T) : LOBE_SPEC_R;   // DielectricBsdf.cpp:174-180
     case TGB_BSDF_SMOOTH_COAT: return LOBE_SPEC_R;          // | substrate lobes, added by upload_scene
     case TGB_BSDF_HAIR: return LOBE_GLOSSY_R | LOBE_GLOSSY_T | LOBE_ANISO;                  // bsdfs/HairBcsdf.cpp:20
     default: return 0xFFFFFFFFu;
@@ -311,7 +313,7 @@ int upload_scene(tgb_ctx *c, const tgb_scene_desc *d) {
         if (p.emission_tex >= int(d->n_textures)) return fail(c, TGB_ERR_INVALID, "primitive %u: bad emission texture", i);
         bool emissive = p.emission_tex >= 0 && max_comp(tex[p.emission_tex].maxv) > 0.0f;  // primitives/Primitive.hpp:111-115
         bool samplable = true, infinite = false;
-        if (p.type != TGB_PRIM_INFINITE_SPHERE) {
+        if (p.type != TGB_PRIM_INFINITE_SPHERE && p.type != TGB_PRIM_INFINITE_SPHERE_CAP && p.type != TGB_PRIM_SKYDOME) {
             if (p.bsdf_count == 0 || p.bsdf_first + p.bsdf_count > d->n_bsdf_slots) return fail(c, TGB_ERR_INVALID, "primitive %u: bad bsdf range", i);
             for (uint32_t k = 0; k < p.bsdf_count; ++k) if (d->bsdf_slots[p.bsdf_first + k] >= d->n_bsdfs) return fail(c, TGB_ERR_INVALID, "primitive %u: bad bsdf index", i);
         }
@@ -372,8 +374,18 @@ int upload_scene(tgb_ctx *c, const tgb_scene_desc *d) {
             if (emissive) return fail(c, TGB_ERR_UNSUPPORTED, "emissive cubes are outside the hot path");
             analytic.push_back(int(i));
             break; }
+        case TGB_PRIM_INFINITE_SPHERE_CAP: {                                              // primitives/InfiniteSphereCap.cpp:231-247
+            o.normal = f3(p.cap_dir); o.area = p.cap_cos;
+            if (!(p.cap_cos < 1.0f)) return fail(c, TGB_ERR_INVALID, "infinite_sphere_cap %u: cap angle must be positive", i);
+            samplable = p.do_sample != 0; infinite = true;
+            break; }
+        case TGB_PRIM_SKYDOME:                                                            // primitives/Skydome.cpp: an environment sphere with its own prepared image
+            if (p.emission_tex < 0 || tex[p.emission_tex].d.type != TGB_TEX_BITMAP) return fail(c, TGB_ERR_INVALID, "skydome %u: pass the prepared sky image (Skydome::prepareForRender) as a bitmap emission texture", i);
+            o.type = TGB_PRIM_INFINITE_SPHERE; o.flags |= PF_SKYDOME;
+            /* fall through: lookup without rotation (Skydome::directionToUV, Skydome.cpp:29-38) = identity matrices from the caller */
         case TGB_PRIM_INFINITE_SPHERE: {                                                  // primitives/InfiniteSphere.cpp prepareForRender
             std::memcpy(o.rot, p.rot, sizeof(o.rot)); transpose3(o.rot, o.inv_rot);
+            if (p.type == TGB_PRIM_SKYDOME) { const float id[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}; std::memcpy(o.rot, id, sizeof(id)); std::memcpy(o.inv_rot, id, sizeof(id)); }
             samplable = p.do_sample != 0; infinite = true;
             if (emissive && tex[p.emission_tex].d.type == TGB_TEX_CHECKER) return fail(c, TGB_ERR_UNSUPPORTED, "checker environment maps are outside the hot path");
             break; }
@@ -434,6 +446,8 @@ int upload_scene(tgb_ctx *c, const tgb_scene_desc *d) {
     if (analytic.size() > 4096) return fail(c, TGB_ERR_UNSUPPORTED, "more than 4096 analytic primitives");
     for (int li : lights) {
         DPrim &l = prims[li];
+        if (l.type == TGB_PRIM_INFINITE_SPHERE_CAP && tex[l.emission_tex].d.type == TGB_TEX_BITMAP)
+            return fail(c, TGB_ERR_UNSUPPORTED, "bitmap emission on an infinite_sphere_cap is outside the hot path");
         if (l.type == TGB_PRIM_INFINITE_SPHERE && tex[l.emission_tex].d.type == TGB_TEX_BITMAP && !tex[l.emission_tex].has_dist)
             build_spherical_distribution(d->textures[l.emission_tex], tex[l.emission_tex]);
     }
@@ -530,6 +544,8 @@ int upload_scene(tgb_ctx *c, const tgb_scene_desc *d) {
         auto child = [&](const Node4 &nd, int k) { CutBox b; for (int a = 0; a < 3; ++a) { b.lo[a] = nd.f[8*a + k]; b.hi[a] = nd.f[8*a + 4 + k]; } b.link = nd.link[k]; return b; };
         auto area = [](const CutBox &b) { float e[3] = {b.hi[0] - b.lo[0], b.hi[1] - b.lo[1], b.hi[2] - b.lo[2]}; return e[0]*e[1] + e[1]*e[2] + e[2]*e[0]; };
         std::vector<CutBox> cut;
+        size_t max_cut = 16;                     // TGB_CUT_BOXES: fewer boxes = cheaper pre-test in k_accum / k_shadow_prep, looser cut
+        if (const char *e = getenv("TGB_CUT_BOXES")) max_cut = size_t(std::min(16, std::max(4, atoi(e))));
         for (int k = 0; k < 4; ++k) if (bvh.nodes[0].link[k] != kEmptyLink) cut.push_back(child(bvh.nodes[0], k));
         while (true) {
             int best = -1;
@@ -537,7 +553,7 @@ int upload_scene(tgb_ctx *c, const tgb_scene_desc *d) {
             if (best < 0) break;
             const Node4 &nd = bvh.nodes[size_t(cut[size_t(best)].link)];
             int kids = 0; for (int k = 0; k < 4; ++k) kids += nd.link[k] != kEmptyLink;
-            if (cut.size() - 1 + size_t(kids) > 16) break;
+            if (cut.size() - 1 + size_t(kids) > max_cut) break;
             cut.erase(cut.begin() + best);
             for (int k = 0; k < 4; ++k) if (nd.link[k] != kEmptyLink) cut.push_back(child(nd, k));
         }
@@ -650,7 +666,7 @@ int upload_scene(tgb_ctx *c, const tgb_scene_desc *d) {
         uint32_t types = 0;
         for (uint32_t i = 0; i < d->n_primitives; ++i) {
             const tgb_primitive &p = d->primitives[i];
-            if (p.type == TGB_PRIM_INFINITE_SPHERE) continue;
+            if (p.type == TGB_PRIM_INFINITE_SPHERE || p.type == TGB_PRIM_INFINITE_SPHERE_CAP || p.type == TGB_PRIM_SKYDOME) continue;
             for (uint32_t k = 0; k < p.bsdf_count; ++k) {
                 uint32_t t = d->bsdfs[d->bsdf_slots[p.bsdf_first + k]].type;
                 if (t != TGB_BSDF_NULL) types |= 1u << std::min(t, 31u);

@@ -104,11 +104,11 @@ struct DBsdf {
     // the 64 normalised row pdfs / cdfs (65 entries per row) and the row sums
     float hair_v[3], hair_scale_rad; const float *hair_table[3], *hair_pdfs[3], *hair_cdfs[3], *hair_sums[3];
 };
-enum : uint32_t { PF_EMISSIVE = 1, PF_SAMPLABLE = 2, PF_INFINITE = 4, PF_SMOOTH = 8 };
+enum : uint32_t { PF_EMISSIVE = 1, PF_SAMPLABLE = 2, PF_INFINITE = 4, PF_SMOOTH = 8, PF_SKYDOME = 16 };
 struct DPrim {
     uint32_t type, flags; int emission_tex;
     uint32_t tri_first, n_tris, bsdf_first, bsdf_count;
-    V3 base, edge0, edge1, normal; float inv_uv_sq0, inv_uv_sq1, area;      // quad
+    V3 base, edge0, edge1, normal; float inv_uv_sq0, inv_uv_sq1, area;      // quad; infinite sphere cap: normal = cap direction, area = cos(cap angle)
     V3 pos, scale; float rot[9], inv_rot[9];                                // cube / infinite sphere rotation
     float total_area; const float *tri_pdf, *tri_cdf; const float *light_verts;   // emissive meshes: p0 p1 p2 per tri
     uint32_t curve_mode;                                                    // curves: TGB_CURVE_*; tri_first/n_tris = its segments' global ids
@@ -301,6 +301,10 @@ TGB_D float bsdf_roughness(const DScene &sc, const DBsdf &b, const Surface &s) {
 TGB_D bool check_reflection_constraint(V3 wi, V3 wo) {                                 // bsdfs/Bsdf.hpp:43-46
     return fabsf(wi.z*wo.z - wi.x*wo.x - wi.y*wo.y - 1.0f) < 1e-3f;
 }
+TGB_D bool check_refraction_constraint(V3 wi, V3 wo, float eta, float cosThetaT) {      // bsdfs/Bsdf.hpp:49-53
+    float dotP = -wi.x*wo.x*eta - wi.y*wo.y*eta - copysignf(cosThetaT, wi.z)*wo.z;
+    return fabsf(dotP - 1.0f) < 1e-3f;
+}
 TGB_D V3 vexp(V3 a) { return v3(expf(a.x), expf(a.y), expf(a.z)); }
 
 // RoughDielectricBsdf::sampleBase / evalBase / pdfBase (bsdfs/RoughDielectricBsdf.cpp:55-131,133-164,198-234)
@@ -378,7 +382,7 @@ TGB_D V3 plastic_substrate(const DBsdf &b, V3 albedo, float Fi, float Fo, float 
     return (albedo/denom)*((1.0f - Fi)*(1.0f - Fo)*eta*eta);
 }
 TGB_D float bsdf_eta(const DBsdf &b, const Event &e) {                                 // bsdfs/Bsdf.hpp:99-103; RoughDielectricBsdf.cpp:274-280
-    if (b.type == TGB_BSDF_ROUGH_DIELECTRIC) {
+    if (b.type == TGB_BSDF_ROUGH_DIELECTRIC || b.type == TGB_BSDF_DIELECTRIC) {         // DielectricBsdf.cpp:166-172
         if (e.wi.z*e.wo.z >= 0.0f) return 1.0f;
         return e.wi.z < 0.0f ? b.ior : b.inv_ior;
     }
@@ -425,6 +429,45 @@ TGB_D bool bsdf_sample_base(const DScene &sc, const DBsdf &b, const Surface &s, 
         ok = rd_sample_base(smp, e, sampleR, sampleT, roughness, b.ior, b.dist);
         e.weight = e.weight*bsdf_albedo(sc, b, s);
         break; }
+    case TGB_BSDF_MIRROR: {                                                            // bsdfs/MirrorBsdf.cpp:28-37
+        if (!(e.requested & LOBE_SPEC_R)) break;
+        e.wo = v3(-e.wi.x, -e.wi.y, e.wi.z);
+        e.pdf = 1.0f;
+        e.sampled = LOBE_SPEC_R;
+        e.weight = bsdf_albedo(sc, b, s);
+        ok = true; break; }
+    case TGB_BSDF_CONDUCTOR: {                                                         // bsdfs/ConductorBsdf.cpp:58-68
+        if (!(e.requested & LOBE_SPEC_R)) break;
+        e.wo = v3(-e.wi.x, -e.wi.y, e.wi.z);
+        e.pdf = 1.0f;
+        e.weight = bsdf_albedo(sc, b, s)*conductor_reflectance(b.eta, b.k, e.wi.z);
+        e.sampled = LOBE_SPEC_R;
+        ok = true; break; }
+    case TGB_BSDF_DIELECTRIC: {                                                        // bsdfs/DielectricBsdf.cpp:49-87
+        bool sampleR = (e.requested & LOBE_SPEC_R) != 0;
+        bool sampleT = (e.requested & LOBE_SPEC_T) != 0 && b.enable_t;
+        float eta = e.wi.z < 0.0f ? b.ior : b.inv_ior;
+        float cosThetaT = 0.0f;
+        float F = dielectric_reflectance(eta, fabsf(e.wi.z), cosThetaT);
+        float reflectionProbability;
+        if (sampleR && sampleT) reflectionProbability = F;
+        else if (sampleR) reflectionProbability = 1.0f;
+        else if (sampleT) reflectionProbability = 0.0f;
+        else break;
+        if (sampler_boolean(smp, reflectionProbability)) {
+            e.wo = v3(-e.wi.x, -e.wi.y, e.wi.z);
+            e.pdf = reflectionProbability;
+            e.sampled = LOBE_SPEC_R;
+            e.weight = sampleT ? v3s(1.0f) : v3s(F);
+        } else {
+            if (F == 1.0f) break;
+            e.wo = v3(-e.wi.x*eta, -e.wi.y*eta, -copysignf(cosThetaT, e.wi.z));
+            e.pdf = 1.0f - reflectionProbability;
+            e.sampled = LOBE_SPEC_T;
+            e.weight = sampleR ? v3s(1.0f) : v3s(1.0f - F);
+        }
+        e.weight = e.weight*bsdf_albedo(sc, b, s);
+        ok = true; break; }
     case TGB_BSDF_PLASTIC: {                                                           // bsdfs/PlasticBsdf.cpp:45-88
         if (e.wi.z <= 0.0f) break;
         bool sampleR = (e.requested & LOBE_SPEC_R) != 0, sampleT = (e.requested & LOBE_DIFFUSE_R) != 0;
@@ -534,6 +577,22 @@ TGB_D V3 bsdf_eval_base(const DScene &sc, const DBsdf &b, const Surface &s, cons
         bool sampleT = (e.requested & LOBE_GLOSSY_T) != 0 && b.enable_t;
         f = rd_eval_base(e, sampleR, sampleT, bsdf_roughness(sc, b, s), b.ior, b.dist)*bsdf_albedo(sc, b, s);
         break; }
+    case TGB_BSDF_MIRROR:                                                              // MirrorBsdf.cpp:39-46
+        if ((e.requested & LOBE_SPEC_R) && check_reflection_constraint(e.wi, e.wo)) f = bsdf_albedo(sc, b, s);
+        break;
+    case TGB_BSDF_CONDUCTOR:                                                           // ConductorBsdf.cpp:70-77
+        if ((e.requested & LOBE_SPEC_R) && check_reflection_constraint(e.wi, e.wo))
+            f = bsdf_albedo(sc, b, s)*conductor_reflectance(b.eta, b.k, e.wi.z);
+        break;
+    case TGB_BSDF_DIELECTRIC: {                                                        // DielectricBsdf.cpp:89-109
+        bool evalR = (e.requested & LOBE_SPEC_R) != 0;
+        bool evalT = (e.requested & LOBE_SPEC_T) != 0 && b.enable_t;
+        float eta = e.wi.z < 0.0f ? b.ior : b.inv_ior;
+        float cosThetaT = 0.0f;
+        float F = dielectric_reflectance(eta, fabsf(e.wi.z), cosThetaT);
+        if (e.wi.z*e.wo.z >= 0.0f) { if (evalR && check_reflection_constraint(e.wi, e.wo)) f = bsdf_albedo(sc, b, s)*F; }
+        else if (evalT && check_refraction_constraint(e.wi, e.wo, eta, cosThetaT)) f = bsdf_albedo(sc, b, s)*(1.0f - F);
+        break; }
     case TGB_BSDF_PLASTIC: {                                                           // PlasticBsdf.cpp:125-151
         if (e.wi.z <= 0.0f || e.wo.z <= 0.0f) break;
         bool evalR = (e.requested & LOBE_SPEC_R) != 0, evalT = (e.requested & LOBE_DIFFUSE_R) != 0;
@@ -590,6 +649,17 @@ TGB_D float bsdf_pdf_base(const DScene &sc, const DBsdf &b, const Surface &s, co
         bool sampleR = (e.requested & LOBE_GLOSSY_R) != 0;
         bool sampleT = (e.requested & LOBE_GLOSSY_T) != 0 && b.enable_t;
         return rd_pdf_base(e, sampleR, sampleT, bsdf_roughness(sc, b, s), b.ior, b.dist); }
+    case TGB_BSDF_MIRROR:                                                              // MirrorBsdf.cpp:57-64
+    case TGB_BSDF_CONDUCTOR:                                                           // ConductorBsdf.cpp:84-91
+        return ((e.requested & LOBE_SPEC_R) && check_reflection_constraint(e.wi, e.wo)) ? 1.0f : 0.0f;
+    case TGB_BSDF_DIELECTRIC: {                                                        // DielectricBsdf.cpp:144-164
+        bool sampleR = (e.requested & LOBE_SPEC_R) != 0;
+        bool sampleT = (e.requested & LOBE_SPEC_T) != 0 && b.enable_t;
+        float eta = e.wi.z < 0.0f ? b.ior : b.inv_ior;
+        float cosThetaT = 0.0f;
+        float F = dielectric_reflectance(eta, fabsf(e.wi.z), cosThetaT);
+        if (e.wi.z*e.wo.z >= 0.0f) return (sampleR && check_reflection_constraint(e.wi, e.wo)) ? (sampleT ? F : 1.0f) : 0.0f;
+        return (sampleT && check_refraction_constraint(e.wi, e.wo, eta, cosThetaT)) ? (sampleR ? 1.0f - F : 1.0f) : 0.0f; }
     case TGB_BSDF_PLASTIC: {                                                           // PlasticBsdf.cpp:153-177
         if (e.wi.z <= 0.0f || e.wo.z <= 0.0f) return 0.0f;
         bool sampleR = (e.requested & LOBE_SPEC_R) != 0, sampleT = (e.requested & LOBE_DIFFUSE_R) != 0;
@@ -933,7 +1003,29 @@ TGB_D bool light_sample_direct(const DScene &sc, const DPrim &l, V3 p, Sampler &
         out.dist = INFINITY;
         return out.pdf != 0.0f;
     }
+    if (l.type == TGB_PRIM_INFINITE_SPHERE_CAP) {                                      // primitives/InfiniteSphereCap.cpp:131-139
+        float xa = sampler_next1d(smp), xb = sampler_next1d(smp);
+        float phi = xa*TWO_PI_F;                                                       // SampleWarp::uniformSphericalCap (SampleWarp.hpp:119-129)
+        float z = xb*(1.0f - l.area) + l.area;
+        float r = sqrtf(maxf(1.0f - z*z, 0.0f));
+        out.d = to_global(frame_from_normal(l.normal), v3(cosf(phi)*r, sinf(phi)*r, z));
+        out.dist = INFINITY;
+        out.pdf = INV_TWO_PI_F/(1.0f - l.area);                                        // uniformSphericalCapPdf (:131-134)
+        return true;
+    }
     return false;
+}
+// InfiniteSphereCap::intersect (InfiniteSphereCap.cpp:69-80): the cap is "hit" by directions inside its cone
+TGB_D bool cap_hit(const DPrim &l, V3 d) { return !(dot(d, l.normal) < l.area); }
+// TraceableScene::intersectInfinites (renderer/TraceableScene.hpp:194-209): every infinite light is asked in list order and the
+// LAST one that is hit owns the ray -> walk the list backwards to the first hit.  Returns the primitive index or -1.
+TGB_D int infinite_light_hit(const DScene &sc, V3 d) {
+    for (int i = sc.n_inf_lights - 1; i >= 0; --i) {
+        int li = sc.inf_lights[i];
+        const DPrim &l = sc.prims[li];
+        if (l.type != TGB_PRIM_INFINITE_SPHERE_CAP || cap_hit(l, d)) return li;
+    }
+    return -1;
 }
 
 TGB_D float light_approx_radiance(const DScene &sc, const DPrim &l, V3 p) {
@@ -949,8 +1041,13 @@ TGB_D float light_approx_radiance(const DScene &sc, const DPrim &l, V3 p) {
     }
     if (l.type == TGB_PRIM_MESH) return -1.0f;                                         // primitives/TriangleMesh.cpp:514-517
     if (l.type == TGB_PRIM_INFINITE_SPHERE) {                                          // primitives/InfiniteSphere.cpp:261-266
+        if (l.flags & PF_SKYDOME) return (TWO_PI_F*2.0f)*max_comp(sc.tex[l.emission_tex].avg);   // Skydome.cpp:279-282: FOUR_PI*average().max(), no flag test
         if (!(l.flags & PF_EMISSIVE) || !(l.flags & PF_SAMPLABLE)) return 0.0f;
         return TWO_PI_F*max_comp(sc.tex[l.emission_tex].avg);
+    }
+    if (l.type == TGB_PRIM_INFINITE_SPHERE_CAP) {                                      // InfiniteSphereCap.cpp:207-212
+        if (!(l.flags & PF_EMISSIVE) || !(l.flags & PF_SAMPLABLE)) return 0.0f;
+        return TWO_PI_F*(1.0f - l.area)*max_comp(sc.tex[l.emission_tex].avg);
     }
     return 0.0f;
 }

@@ -529,14 +529,22 @@ TGB_D bool mesh_cut_hit(const DScene &sc, V3 o, V3 d, float tnear, float tfar) {
     const float idz = 1.0f/(fabsf(d.z) > ooeps ? d.z : copysignf(ooeps, d.z));
     const float oodx = o.x*idx, oody = o.y*idy, oodz = o.z*idz;
     bool hit = false;
-#pragma unroll                              // static indices: the boxes are read straight from the kernel parameters
-    for (int k = 0; k < 16; ++k) {
-        float ax = __fmaf_rn(sc.cut[0][k], idx, -oodx), bx = __fmaf_rn(sc.cut[1][k], idx, -oodx);
-        float ay = __fmaf_rn(sc.cut[2][k], idy, -oody), by = __fmaf_rn(sc.cut[3][k], idy, -oody);
-        float az = __fmaf_rn(sc.cut[4][k], idz, -oodz), bz = __fmaf_rn(sc.cut[5][k], idz, -oodz);
-        float tmn = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fmaxf(fminf(az, bz), tnear));
-        float tmx = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fminf(fmaxf(az, bz), tfar));
-        hit = hit || (k < sc.n_cut && tmn <= tmx);
+    // groups of four boxes with static indices inside a group (the boxes are read straight from the kernel parameters); the
+    // number of groups is uniform across the grid
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+        if (4*g < sc.n_cut) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int k = 4*g + j;
+                float ax = __fmaf_rn(sc.cut[0][k], idx, -oodx), bx = __fmaf_rn(sc.cut[1][k], idx, -oodx);
+                float ay = __fmaf_rn(sc.cut[2][k], idy, -oody), by = __fmaf_rn(sc.cut[3][k], idy, -oody);
+                float az = __fmaf_rn(sc.cut[4][k], idz, -oodz), bz = __fmaf_rn(sc.cut[5][k], idz, -oodz);
+                float tmn = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fmaxf(fminf(az, bz), tnear));
+                float tmx = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fminf(fmaxf(az, bz), tfar));
+                hit = hit || (k < sc.n_cut && tmn <= tmx);
+            }
+        }
     }
     return hit;
 }
@@ -922,14 +930,17 @@ k_shade(DScene sc, PathBuf pb, Scratch sr, BatchInfo bi, Ctl *ctl, uint32_t *squ
         if (h.id == HID_MISS) {
             // loop exit with didHit == false: handleInfiniteLights (TraceBase.cpp:570-578, TraceableScene.hpp:194-209)
             if (bounce >= set.min_bounces && bounce < set.max_bounces && sc.n_inf_lights > 0) {
-                int li = sc.inf_lights[sc.n_inf_lights - 1];
-                const DPrim &l = sc.prims[li];
-                if (!set.enable_light_sampling || wasSpecular || !(l.flags & PF_SAMPLABLE)) {
-                    float u, v; direction_to_uv(l, d, u, v, nullptr);
-                    V3 em = tex_eval(sc.tex[l.emission_tex], u, v);
-                    float4 e4 = pb.E[s];
-                    e4.x += thr.x*em.x; e4.y += thr.y*em.y; e4.z += thr.z*em.z;
-                    pb.E[s] = e4;
+                int li = infinite_light_hit(sc, d);
+                if (li >= 0) {
+                    const DPrim &l = sc.prims[li];
+                    if (!set.enable_light_sampling || wasSpecular || !(l.flags & PF_SAMPLABLE)) {
+                        float u = 0.0f, v = 0.0f;                                        // InfiniteSphereCap::evalDirect looks up uv (0, 0)
+                        if (l.type != TGB_PRIM_INFINITE_SPHERE_CAP) direction_to_uv(l, d, u, v, nullptr);
+                        V3 em = tex_eval(sc.tex[l.emission_tex], u, v);
+                        float4 e4 = pb.E[s];
+                        e4.x += thr.x*em.x; e4.y += thr.y*em.y; e4.z += thr.z*em.z;
+                        pb.E[s] = e4;
+                    }
                 }
             }
             pb.T1[s] = make_float4(d.x, d.y, d.z, __uint_as_float((info & 0x00FFFFFFu) | F_FINAL_CHECK));
@@ -999,6 +1010,9 @@ k_shade(DScene sc, PathBuf pb, Scratch sr, BatchInfo bi, Ctl *ctl, uint32_t *squ
                                         hitL = quad_light_hit(l, sf.p, ls.d, epsilon, t, l0, l1, back) && !(t*(1.0f + 1e-3f) < ls.dist);
                                         if (hitL && !back) em = tex_eval(sc.tex[l.emission_tex], l0, l1);
                                         tfar = t;
+                                    } else if (l.type == TGB_PRIM_INFINITE_SPHERE_CAP) {
+                                        hitL = cap_hit(l, ls.d);                               // light.intersect (TraceBase.cpp:160)
+                                        if (hitL) em = tex_eval(sc.tex[l.emission_tex], 0.0f, 0.0f);
                                     } else {
                                         float u, v; direction_to_uv(l, ls.d, u, v, nullptr);
                                         em = tex_eval(sc.tex[l.emission_tex], u, v);
@@ -1033,6 +1047,10 @@ k_shade(DScene sc, PathBuf pb, Scratch sr, BatchInfo bi, Ctl *ctl, uint32_t *squ
                                     if (hitL && !back) em = tex_eval(sc.tex[l.emission_tex], l0, l1);
                                     tfar = t;
                                     directPdf = t*t/(fabsf(dot(l.normal, wo))*l.area);                 // Quad::directPdf (Quad.cpp:216-222)
+                                } else if (l.type == TGB_PRIM_INFINITE_SPHERE_CAP) {
+                                    hitL = cap_hit(l, wo);
+                                    if (hitL) em = tex_eval(sc.tex[l.emission_tex], 0.0f, 0.0f);
+                                    directPdf = INV_TWO_PI_F/(1.0f - l.area);                          // InfiniteSphereCap::directPdf (:173-177)
                                 } else {
                                     float u, v, sinTheta; direction_to_uv(l, wo, u, v, &sinTheta);
                                     const DTex &et = sc.tex[l.emission_tex];

@@ -196,6 +196,23 @@ class B200PathTraceIntegrator:
                 return
             raise e
 
+    # -- Integrator::saveRenderResumeData / resumeRender (Integrator.cpp:108-162) + PathTraceIntegrator::saveState/loadState
+    #    (PathTraceIntegrator.cpp:158-172): current spp, the colour buffer (running mean + counts), the block records and the
+    #    integrator's sampler state.  (Per-tile samplers carry no running state under the per-path reseed contract.)
+    def save_state(self):
+        mean, count = self._ctx.read_framebuffer()
+        return {"current_spp": self._current_spp, "mean": mean, "count": count,
+                "records": bytes(self.records), "sampler_state": self._sampler.state}
+
+    def load_state(self, state):
+        """After prepareForRender, before the next startRender: continue a render from a saved state."""
+        import ctypes as C
+        C.memmove(self.records, state["records"], len(state["records"]))
+        self._sampler.state = state["sampler_state"]
+        self._ctx.write_framebuffer(state["mean"], state["count"])
+        self._current_spp = state["current_spp"]
+        self._advance_spp()
+
     def abortRender(self):
         """PathTraceIntegrator::abortRender (PathTraceIntegrator.cpp:249-254): abort + wait."""
         if self._ctx is not None and self._thread is not None:

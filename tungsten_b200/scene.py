@@ -452,6 +452,23 @@ class FlatScene:
             o.eta[:] = [float(f32(x)) for x in eta]; o.k[:] = [float(f32(x)) for x in k]
             o.distribution = _DIST[b.get("distribution", "ggx")]
             o.roughness_tex = self.add_texture(b.get("roughness", 0.1), base_dir)
+        elif ty == "mirror":
+            o.type = abi.BSDF_MIRROR
+        elif ty == "conductor":
+            # ConductorBsdf ctor (ConductorBsdf.cpp:20-26): rounded copper constants; the table is consulted only for "material"
+            o.type = abi.BSDF_CONDUCTOR
+            eta, k = (0.200438, 0.924033, 1.10221), (3.91295, 2.45285, 2.14219)
+            if "eta" in b and "k" in b:
+                eta, k = _vec3_field(b, "eta"), _vec3_field(b, "k")
+            if "material" in b:
+                if b["material"] not in COMPLEX_IOR:
+                    raise SceneError("conductor material '%s' not in the table" % b["material"])
+                eta, k = COMPLEX_IOR[b["material"]]
+            o.eta[:] = [float(f32(x)) for x in eta]; o.k[:] = [float(f32(x)) for x in k]
+        elif ty == "dielectric":
+            o.type = abi.BSDF_DIELECTRIC
+            o.ior = float(f32(b.get("ior", 1.5)))
+            o.enable_refraction = 1 if b.get("enable_refraction", True) else 0
         elif ty == "rough_dielectric":
             o.type = abi.BSDF_ROUGH_DIELECTRIC
             o.ior = float(f32(b.get("ior", 1.5)))
@@ -648,6 +665,25 @@ class FlatScene:
         p.rot[:] = [float(x) for x in rot.reshape(-1)]
         self.primitives.append(p)
 
+    def add_infinite_sphere_cap(self, transform, emission_tex, sample=True, cap_angle_deg=10.0):
+        """InfiniteSphereCap::prepareForRender (primitives/InfiniteSphereCap.cpp:231-247): cap direction = the transform's
+        image of +y, normalised; cos of the cap angle through degToRad (math/Angle.hpp:19-22) and libm's cosf."""
+        cap_dir = normalized(mat4_vector(transform, v3(0.0, 1.0, 0.0)))
+        rad = f32(f32(cap_angle_deg)*f32(f32(PI)/f32(180.0)))
+        p = abi.Primitive(type=abi.PRIM_INFINITE_SPHERE_CAP, emission_tex=emission_tex, do_sample=1 if sample else 0)
+        p.cap_dir[:] = [float(x) for x in cap_dir]; p.cap_cos = float(_cosf(rad))
+        self.primitives.append(p)
+
+    def add_skydome(self, sky_texels, sample=True):
+        """Skydome (primitives/Skydome.cpp): an environment sphere looked up WITHOUT rotation whose emission is the 512x256
+        image Skydome::prepareForRender computes from the Hosek-Wilkie model (thirdparty/skylight).  That model is not
+        restated here: the caller passes the prepared image (the C++ adapter reads it from the live Skydome object, tests
+        use an image dumped from the reference)."""
+        tex = self.add_bitmap_texture(np.ascontiguousarray(sky_texels, dtype=np.float32), True, False)
+        p = abi.Primitive(type=abi.PRIM_SKYDOME, emission_tex=tex, do_sample=1 if sample else 0)
+        p.rot[:] = [1.0, 0.0, 0.0, 0.0, 1.0, 0.0, 0.0, 0.0, 1.0]
+        self.primitives.append(p)
+
     def set_camera(self, cam, base_dir="."):
         """Camera::fromJson + PinholeCamera::fromJson (cameras/Camera.cpp:44-68, PinholeCamera.cpp:37-43)."""
         if cam.get("type", "pinhole") != "pinhole":
@@ -719,6 +755,18 @@ def load_scene(path_or_dict, base_dir=None):
         tf = parse_transform(p.get("transform"))
         if ty == "infinite_sphere":
             fs.add_infinite_sphere(tf, fs._emission(p, base_dir), p.get("sample", True))
+            continue
+        if ty == "infinite_sphere_cap":
+            if p.get("skydome"):                                  # pivot object: the cap follows that primitive's transform
+                piv = [q for q in js.get("primitives", []) if q.get("name") == p["skydome"]]
+                if piv:
+                    tf = parse_transform(piv[0].get("transform"))
+            fs.add_infinite_sphere_cap(tf, fs._emission(p, base_dir), p.get("sample", True), p.get("cap_angle", 10.0))
+            continue
+        if ty == "skydome":
+            if "sky_image" not in p:
+                raise SceneError("skydome: the Hosek-Wilkie sky model is outside the hot path; pass the prepared image as 'sky_image' (PFM)")
+            fs.add_skydome(load_pfm(os.path.join(base_dir, p["sky_image"])), p.get("sample", True))
             continue
         if ty == "instances":
             masters = []

@@ -330,10 +330,13 @@ def curly_fibers(n_curves=200, nodes_per_curve=14, radius=0.45, length=1.1, widt
 
 
 def hair_scene(out_dir, name="hair", n_curves=200, nodes_per_curve=14, mode="bcsdf_cylinder", bsdf=None, res=(128, 128),
-               spp=16, max_bounces=16, thickness=None, taper=False, subsample=0.0, env=(0.35, 0.4, 0.5), width=0.01, head=False):
+               spp=16, max_bounces=16, thickness=None, taper=False, subsample=0.0, env=(0.35, 0.4, 0.5), width=0.01, head=False,
+               shipped_lights=False, min_bounces=0):
     """C4 stand-in: curly strands (`curves` primitive + `.fiber` file) with the hair BCSDF over a Lambert floor, lit by a
-    quad light and a constant environment.  (The shipped hair scene's emitters, infinite_sphere_cap + skydome, are
-    outside the hot path)"""
+    quad light and a constant environment, or -- shipped_lights -- by exactly the two emitters of the reference's
+    data/example-scenes/hair/scene.json: an `infinite_sphere_cap` sun (sampled) and a `skydome` (not sampled), same parameters;
+    the skydome then names "sky_image": <name>_sky.pfm, the 512x256 image Skydome::prepareForRender computes, which the caller has
+    to provide (tests/golden/make_golden.py dumps it from the reference; the reference itself ignores the key)."""
     from .scene import save_fiber
     os.makedirs(out_dir, exist_ok=True)
     ends, nodes = curly_fibers(n_curves, nodes_per_curve, width=width)
@@ -350,7 +353,13 @@ def hair_scene(out_dir, name="hair", n_curves=200, nodes_per_curve=14, mode="bcs
              curves,
              {"name": "light", "type": "quad", "bsdf": "light", "emission": [30, 28, 24],
               "transform": {"position": [0.9, 2.6, 1.2], "scale": [0.7, 1, 0.7], "rotation": [0, 0, 150]}}]
-    if env is not None:
+    if shipped_lights:
+        prims = prims[:2]
+        rot = [34.1619, -2.60535, 23.5692]
+        prims.append({"name": "sun", "transform": {"rotation": rot}, "emission": 200, "type": "infinite_sphere_cap", "sample": True, "cap_angle": 10})
+        prims.append({"name": "sky", "transform": {"rotation": rot}, "type": "skydome", "temperature": 5777, "gamma_scale": 1, "turbidity": 3,
+                      "intensity": 5, "sample": False, "sky_image": name + "_sky.pfm"})
+    elif env is not None:
         prims.append({"name": "env", "type": "infinite_sphere", "emission": list(env), "sample": True})
     meshes = {}
     if head:        # a triangle mesh under the strands: triangles and curve segments then share one BVH (joint root)
@@ -363,7 +372,7 @@ def hair_scene(out_dir, name="hair", n_curves=200, nodes_per_curve=14, mode="bcs
           "camera": {"tonemap": "filmic", "resolution": list(res), "reconstruction_filter": "tent",
                      "transform": {"position": [0.3, 1.2, 3.4], "look_at": [0, 0.95, 0], "up": [0, 1, 0]},
                      "type": "pinhole", "fov": 35},
-          "integrator": {"type": "path_tracer", "min_bounces": 0, "max_bounces": max_bounces,
+          "integrator": {"type": "path_tracer", "min_bounces": min_bounces, "max_bounces": max_bounces,
                          "enable_consistency_checks": False, "enable_two_sided_shading": True,
                          "enable_light_sampling": True},
           "renderer": _renderer(spp)}
