@@ -138,6 +138,14 @@ typedef struct tgb_settings {
     uint32_t supplemental_mode; /* 0 = per-path reseed (parity contract)        */
     int32_t  device;            /* CUDA ordinal, -1 = current                                        */
     uint32_t max_paths_in_flight; /* 0 = library default                                             */
+    /* Device list: n_devices >= 2 replicates the scene on devices[0 .. n_devices) of this process.  Every render
+     * call then deals its 16x16 tiles to the GPUs in Morton order of the tile grid (tgb200_shard_tiles), the GPUs render their
+     * shares concurrently (one host thread each), and the shares are gathered on devices[0] with peer-to-peer copies over
+     * NVLink (the single collective of the path; a multi-PROCESS caller uses tgb200_pack_tiles + its own NCCL all-gather
+     * instead, as bench.py does).  Framebuffer reads, tgb200_trace_closest and the device pointers refer to devices[0].
+     * n_devices 0 or 1: one GPU, `device`.                                                                           */
+    uint32_t n_devices;
+    int32_t  devices[8];
 } tgb_settings;
 
 typedef struct tgb_scene_desc {
@@ -237,6 +245,12 @@ int tgb200_render_adaptive(tgb_ctx *ctx, const tgb_tile *tiles, uint32_t n_tiles
 int tgb200_pack_tiles(tgb_ctx *ctx, const tgb_tile *tiles, uint32_t n_tiles, void *rgb_out_dev);
 int tgb200_unpack_tiles(tgb_ctx *ctx, const tgb_tile *tiles, uint32_t n_tiles, const void *rgb_in_dev,
                         uint32_t sample_count);
+
+/* The tile deal of the multi-GPU path: writes into `order` (n_tiles entries) the tile indices in Morton (Z) order of the tile grid;
+ * share k of N = order[k], order[k + N], ...  Any N consecutive entries form a compact block of the image, so every share samples
+ * the whole frame evenly (row-major `id mod N` degenerates into column stripes whenever a tile row holds a multiple of N tiles).
+ * Host only.                                                                                                          */
+int tgb200_shard_tiles(const tgb_tile *tiles, uint32_t n_tiles, uint32_t *order);
 
 /* Batch of closest-hit queries through the same traversal kernel the renderer uses.                 */
 int tgb200_trace_closest(tgb_ctx *ctx, const tgb_ray *rays, tgb_hit *hits, uint32_t n);

@@ -166,3 +166,38 @@ def test_shard_pack_gather_unpack_equals_unsharded(scenes, world):
         assert np.array_equal(got, full), deal
         assert np.array_equal(got_cnt, full_cnt), deal
     ctx.close()
+
+
+def test_multi_device_context_equals_single_device(scenes):
+    """tgb_settings::devices: the scene replicated on two GPUs of this process, tiles dealt in Morton order, shares gathered
+    on devices[0] with peer copies -> the same framebuffer as one GPU, bit for bit; also through the host-buffer call and
+    for an adaptive step (block records merged from the GPU that owns each tile)."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs (gpurun --gpus 2)")
+    fs = scenes("c1")
+    one = lib.Context(fs, device=0)
+    a, ca = one.render_tiles(4)
+    n_blocks = ((fs.resolution[0] + 3)//4)*((fs.resolution[1] + 3)//4)
+    rec1 = (abi.SampleRecord*n_blocks)()
+    for i, r in enumerate(rec1):
+        r.next_sample_count = 1 + (i % 3); r.sample_index = 4
+    one.render_adaptive(rec1)
+    a2, ca2 = one.read_framebuffer()
+    one.close()
+    two = lib.Context(fs, devices=[0, 1])
+    b, cb = two.render_tiles(4)
+    assert np.array_equal(a, b) and np.array_equal(ca, cb)
+    rec2 = (abi.SampleRecord*n_blocks)()
+    for i, r in enumerate(rec2):
+        r.next_sample_count = 1 + (i % 3); r.sample_index = 4
+    two.render_adaptive(rec2)
+    b2, cb2 = two.read_framebuffer()
+    assert np.array_equal(a2, b2) and np.array_equal(ca2, cb2)
+    assert bytes(rec1) == bytes(rec2)
+    st = two.stats()
+    assert st.samples >= fs.resolution[0]*fs.resolution[1]*4
+    two.clear(); two.render_resident(2); c, _ = two.read_framebuffer()
+    two.close()
+    one = lib.Context(fs, device=0); one.render_resident(2); d, _ = one.read_framebuffer(); one.close()
+    assert np.array_equal(c, d)

@@ -63,6 +63,13 @@ def test_material_room_env(scratch):
     _compare(fs, 8, same_ray_count=False)
 
 
+def test_dirac_lobes(scratch):
+    """f4: MirrorBsdf, ConductorBsdf, DielectricBsdf (refraction on and off) on cubes and smooth meshes: pure-specular surfaces
+    skip NEE, their bounces carry wasSpecular, refraction scales radiance by eta^2."""
+    fs = scene.load_scene(synth.dirac_room(scratch, res=(96, 96), spp=8, subdiv=3))
+    _compare(fs, 8, same_ray_count=False)
+
+
 def test_coat_checker_envmap(scratch):
     """C0 stand-in: smooth_coat over rough_conductor, checker floor, importance-sampled HDR environment."""
     fs = scene.load_scene(synth.materialtest_standin(scratch, res=(96, 96), spp=8, subdiv=3))
@@ -76,7 +83,7 @@ def test_golden_scenes_against_reference_fixtures():
     # the bit-exact fraction is informational (CUDA's sinf/cosf/expf differ from glibc's in the last ulp); the bar is "close"
     # curve scenes: see test_curves_and_hair for why their "close" bar is lower
     for name, exact_min, close_min in [("cornell", 0.5, 0.985), ("cornell_short", 0.5, 0.985), ("cornell_mesh", 0.5, 0.985),
-                                       ("materials", 0.5, 0.985), ("materials_env", 0.5, 0.985), ("coat_env", 0.3, 0.985),
+                                       ("materials", 0.5, 0.985), ("materials_env", 0.5, 0.985), ("coat_env", 0.3, 0.985), ("dirac", 0.5, 0.985),
                                        ("hair", 0.3, 0.97), ("hair_dark", 0.3, 0.97), ("hair_sky", 0.3, 0.97), ("curves_lambert", 0.5, 0.97),
                                        ("curves_plastic", 0.5, 0.97)]:
         fs = scene.load_scene(os.path.join(g, name, "scene.json"))

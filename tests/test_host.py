@@ -350,3 +350,25 @@ def test_adaptive_sampling_matches_reference_binary():
     exact = float((np.abs(mean - want).max(axis=2) == 0).mean())
     print("adaptive: per-pixel samples %d..%d, exact %.4f" % (count.min(), count.max(), exact))
     assert exact == 1.0
+
+
+def test_library_tile_deal_matches_the_python_twin():
+    """tgb200_shard_tiles (the in-library multi-GPU deal) == integrator.shard_order (what bench.py's ranks use): same Morton
+    order, every share covers the frame evenly."""
+    import ctypes as C
+    L = lib.load()
+    for (w, h) in [(1920, 1080), (250, 90), (16, 16), (3840, 2160)]:
+        tiles = integrator.dice_tiles(w, h, 0xBA5EBA11)
+        order = (C.c_uint32*len(tiles))()
+        assert L.tgb200_shard_tiles(tiles, len(tiles), order) == 0
+        assert list(order) == integrator.shard_order(tiles, "morton")
+        if w == 1920:
+            for world in (2, 4, 8):                 # a share is a regular sub-lattice of the tile grid spanning the whole frame, not a stripe
+                sizes = []
+                for r in range(world):
+                    mine = integrator.shard_tiles(tiles, r, world)
+                    sizes.append(len(mine))
+                    xs = {t.x for t in mine}; ys = {t.y for t in mine}
+                    assert len(xs) >= 120//4 and len(ys) >= 68//4
+                    assert max(xs) - min(xs) >= 0.9*1920 and max(ys) - min(ys) >= 0.9*1080
+                assert max(sizes) - min(sizes) <= 1

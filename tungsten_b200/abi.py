@@ -66,7 +66,7 @@ class Settings(C.Structure):
     _fields_ = [("min_bounces", i32), ("max_bounces", i32), ("enable_light_sampling", u32),
                 ("enable_two_sided_shading", u32), ("enable_consistency_checks", u32),
                 ("use_sobol", u32), ("supplemental_mode", u32), ("device", i32),
-                ("max_paths_in_flight", u32)]
+                ("max_paths_in_flight", u32), ("n_devices", u32), ("devices", i32*8)]
 
 
 class SceneDesc(C.Structure):
@@ -106,7 +106,7 @@ class SampleRecord(C.Structure):
 
 EXPORTS = [
     "tgb200_create", "tgb200_render_tiles", "tgb200_render_resident", "tgb200_clear_framebuffer",
-    "tgb200_read_framebuffer", "tgb200_write_framebuffer", "tgb200_generate_work", "tgb200_render_adaptive", "tgb200_framebuffer_device_ptr", "tgb200_trace_closest", "tgb200_pack_tiles", "tgb200_unpack_tiles",
+    "tgb200_read_framebuffer", "tgb200_write_framebuffer", "tgb200_generate_work", "tgb200_render_adaptive", "tgb200_framebuffer_device_ptr", "tgb200_trace_closest", "tgb200_shard_tiles", "tgb200_pack_tiles", "tgb200_unpack_tiles",
     "tgb200_get_stats", "tgb200_set_profiling", "tgb200_set_stream", "tgb200_scene_info", "tgb200_reset_stats", "tgb200_bvh_selftest", "tgb200_hair_selftest", "tgb200_qbvh_selftest", "tgb200_abort", "tgb200_clear_abort", "tgb200_destroy", "tgb200_last_error",
     "tgb200_abi_version",
 ]

@@ -20,6 +20,22 @@ extern "C" const unsigned char tgb_sobol_blob[];      // sobol_blob.cpp (.incbin
 
 using namespace tgb;
 
+#include <thread>
+#include <map>
+
+struct tgb_ctx;
+struct Group {
+    std::vector<tgb_ctx *> members;                     // members[0] = root
+    std::vector<tgb_tile> deal_key; uint32_t deal_seed = 0;      // tile list the cached deal belongs to
+    std::vector<std::vector<tgb_tile>> shares;           // per member
+    std::vector<uint32_t *> root_pix;                    // per member k >= 1: its share's pixel ids on the ROOT device
+    std::vector<uint32_t> share_pixels;
+    std::vector<float4 *> send;                          // per member k >= 1: pack buffer on ITS device
+    float4 *recv = nullptr; size_t recv_capacity = 0;    // on the root device
+    std::vector<size_t> send_capacity;
+    double gather_ms = 0.0;
+};
+
 namespace {
 
 thread_local std::string g_create_error;
@@ -55,6 +71,7 @@ struct tgb_ctx {
     cudaEvent_t ev_ring[4]{};
     cudaEvent_t ev_k[4][8]{};       // profiling: boundaries between the kernels of an iteration (regen|trace|shade|prep|shadow|accum|sort)
     cudaStream_t own_stream = nullptr;
+    struct Group *group = nullptr;  // multi-GPU: set on the root context (devices[0]); members[0] == the root itself
     Counters *ctr = nullptr; Counters *h_ctr = nullptr;
     float *fb = nullptr; uint32_t *fb_count = nullptr;
     float *h_fb = nullptr; uint32_t *h_fb_count = nullptr;   // pinned staging
@@ -892,6 +909,132 @@ int render_device(tgb_ctx *c, uint32_t spp_begin, uint32_t spp_count, bool adapt
     return TGB_OK;
 }
 
+// apply f to every member of a multi-GPU context (the root last, so that the current device ends up being the root's)
+template <class F> int for_members(tgb_ctx *c, F f) {
+    if (!c->group) return TGB_OK;
+    Group *g = c->group;
+    for (size_t k = g->members.size(); k-- > 1;) { int rc = f(g->members[k]); if (rc) { c->error = g->members[k]->error; return rc; } }
+    return TGB_OK;
+}
+
+// ---- multi-GPU group (tgb_settings::devices) ----------------------------------------------------------------------
+uint32_t morton2(uint32_t x, uint32_t y) {
+    auto part = [](uint32_t v) { v &= 0xFFFFu; v = (v | (v << 8)) & 0x00FF00FFu; v = (v | (v << 4)) & 0x0F0F0F0Fu; v = (v | (v << 2)) & 0x33333333u; v = (v | (v << 1)) & 0x55555555u; return v; };
+    return part(x) | (part(y) << 1);
+}
+void shard_order(const tgb_tile *tiles, uint32_t n, std::vector<uint32_t> &order) {
+    order.resize(n);
+    for (uint32_t i = 0; i < n; ++i) order[i] = i;
+    std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return morton2(tiles[a].x/16u, tiles[a].y/16u) < morton2(tiles[b].x/16u, tiles[b].y/16u); });
+}
+
+int single_render_resident(tgb_ctx *c, const tgb_tile *tiles, uint32_t n_tiles, uint32_t seed, uint32_t spp_begin, uint32_t spp_count);
+int single_render_adaptive(tgb_ctx *c, const tgb_tile *tiles, uint32_t n_tiles, uint32_t seed, tgb_sample_record *records);
+
+// Deal the call's tiles to the members (Morton order, round-robin) and make sure the root knows every share's pixel list.
+int group_deal(tgb_ctx *root, const tgb_tile *tiles, uint32_t n_tiles, uint32_t seed) {
+    tgb_ctx *c = root; Group &g = *root->group;
+    std::vector<tgb_tile> own;
+    if (n_tiles == 0) { dice_tiles(root->res_x, root->res_y, seed, own); tiles = own.data(); n_tiles = uint32_t(own.size()); }
+    if (g.deal_key.size() == n_tiles && n_tiles && std::memcmp(g.deal_key.data(), tiles, n_tiles*sizeof(tgb_tile)) == 0) return TGB_OK;
+    const size_t N = g.members.size();
+    std::vector<uint32_t> order; shard_order(tiles, n_tiles, order);
+    g.shares.assign(N, {});
+    for (uint32_t i = 0; i < n_tiles; ++i) g.shares[i % N].push_back(tiles[order[i]]);
+    CU(cudaSetDevice(root->device));
+    for (uint32_t *p : g.root_pix) if (p) cudaFree(p);
+    g.root_pix.assign(N, nullptr); g.share_pixels.assign(N, 0);
+    size_t max_share = 0;
+    for (size_t k = 0; k < N; ++k) {
+        std::vector<uint32_t> pid;
+        for (const tgb_tile &tl : g.shares[k]) {
+            if (tl.x >= root->res_x || tl.w > root->res_x - tl.x || tl.y >= root->res_y || tl.h > root->res_y - tl.y) return fail(c, TGB_ERR_INVALID, "tile lies outside the image");
+            for (uint32_t y = 0; y < tl.h; ++y) for (uint32_t x = 0; x < tl.w; ++x) pid.push_back((tl.x + x) + (tl.y + y)*root->res_x);
+        }
+        g.share_pixels[k] = uint32_t(pid.size());
+        max_share = std::max(max_share, pid.size());
+        if (k >= 1 && !pid.empty()) {
+            CU(cudaMalloc(reinterpret_cast<void **>(&g.root_pix[k]), pid.size()*4));
+            CU(cudaMemcpy(g.root_pix[k], pid.data(), pid.size()*4, cudaMemcpyHostToDevice));
+        }
+    }
+    if (max_share > g.recv_capacity) {
+        if (g.recv) cudaFree(g.recv);
+        g.recv = nullptr; g.recv_capacity = 0;
+        CU(cudaMalloc(reinterpret_cast<void **>(&g.recv), max_share*sizeof(float4)));
+        g.recv_capacity = max_share;
+    }
+    g.send.resize(N, nullptr); g.send_capacity.resize(N, 0);
+    for (size_t k = 1; k < N; ++k) {
+        if (g.share_pixels[k] > g.send_capacity[k]) {
+            tgb_ctx *m = g.members[k];
+            if (cudaSetDevice(m->device) != cudaSuccess) return fail(c, TGB_ERR_CUDA, "cudaSetDevice(%d) failed", m->device);
+            if (g.send[k]) cudaFree(g.send[k]);
+            g.send[k] = nullptr; g.send_capacity[k] = 0;
+            if (cudaMalloc(reinterpret_cast<void **>(&g.send[k]), size_t(g.share_pixels[k])*sizeof(float4)) != cudaSuccess) return fail(c, TGB_ERR_OOM, "gather buffer allocation failed on device %d", m->device);
+            g.send_capacity[k] = g.share_pixels[k];
+        }
+    }
+    g.deal_key.assign(tiles, tiles + n_tiles); g.deal_seed = seed;
+    return TGB_OK;
+}
+
+// Every member renders its share concurrently (one host thread per GPU), then the shares travel to the root over NVLink.
+int group_render(tgb_ctx *root, const tgb_tile *tiles, uint32_t n_tiles, uint32_t seed, uint32_t spp_begin, uint32_t spp_count, tgb_sample_record *records) {
+    tgb_ctx *c = root; Group &g = *root->group;
+    int rc = group_deal(root, tiles, n_tiles, seed);
+    if (rc) return rc;
+    const size_t N = g.members.size();
+    const uint32_t var_w = (root->res_x + 3)/4, var_h = (root->res_y + 3)/4; const size_t n_blocks = size_t(var_w)*var_h;
+    std::vector<int> rcs(N, TGB_OK);
+    std::vector<std::vector<tgb_sample_record>> recs(records ? N : 0);
+    std::vector<std::thread> th;
+    for (size_t k = 0; k < N; ++k) {
+        if (records) recs[k].assign(records, records + n_blocks);
+        th.emplace_back([&, k] {
+            tgb_ctx *m = g.members[k];
+            if (g.shares[k].empty()) return;
+            rcs[k] = records ? single_render_adaptive(m, g.shares[k].data(), uint32_t(g.shares[k].size()), seed, recs[k].data())
+                             : single_render_resident(m, g.shares[k].data(), uint32_t(g.shares[k].size()), seed, spp_begin, spp_count);
+        });
+    }
+    for (std::thread &t : th) t.join();
+    for (size_t k = 0; k < N; ++k) if (rcs[k]) { root->error = "device " + std::to_string(g.members[k]->device) + ": " + g.members[k]->error; return rcs[k]; }
+    if (records) {          // a 4x4 block lies inside one 16x16 tile: its record comes back from the member that owns the tile
+        for (size_t k = 0; k < N; ++k)
+            for (const tgb_tile &tl : g.shares[k])
+                for (uint32_t by = tl.y/4; by < (tl.y + tl.h + 3)/4; ++by)
+                    for (uint32_t bx = tl.x/4; bx < (tl.x + tl.w + 3)/4; ++bx)
+                        records[bx + size_t(by)*var_w] = recs[k][bx + size_t(by)*var_w];
+    }
+    // gather: pack on the member, one peer copy, de-tile on the root
+    CU(cudaSetDevice(root->device));
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
+    CU(cudaEventRecord(e0, root->stream));
+    for (size_t k = 1; k < N; ++k) {
+        tgb_ctx *m = g.members[k];
+        const uint32_t np = g.share_pixels[k];
+        if (!np) continue;
+        if (cudaSetDevice(m->device) != cudaSuccess) return fail(c, TGB_ERR_CUDA, "cudaSetDevice(%d) failed", m->device);
+        k_pack_share<<<blocks(np, 256), 256, 0, m->stream>>>(m->pix_id, np, m->fb, m->fb_count, g.send[k]);
+        m->stats.kernel_launches++;
+        cudaError_t e = cudaStreamSynchronize(m->stream);
+        if (e != cudaSuccess) return fail(c, TGB_ERR_CUDA, "pack on device %d failed: %s", m->device, cudaGetErrorString(e));
+        CU(cudaSetDevice(root->device));
+        CU(cudaMemcpyPeerAsync(g.recv, root->device, g.send[k], m->device, size_t(np)*sizeof(float4), root->stream));
+        k_unpack_share<<<blocks(np, 256), 256, 0, root->stream>>>(g.root_pix[k], np, g.recv, root->fb, root->fb_count);
+        root->stats.kernel_launches++;
+    }
+    CU(cudaSetDevice(root->device));
+    CU(cudaEventRecord(e1, root->stream));
+    CU(cudaStreamSynchronize(root->stream));
+    float ms = 0.0f; cudaEventElapsedTime(&ms, e0, e1); g.gather_ms += ms;
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    CU(cudaGetLastError());
+    return TGB_OK;
+}
+
 }  // namespace
 
 extern "C" {
@@ -902,6 +1045,18 @@ const char *tgb200_last_error(const tgb_ctx *ctx) { return ctx ? ctx->error.c_st
 
 void tgb200_destroy(tgb_ctx *c) {
     if (!c) return;
+    if (c->group) {
+        Group *g = c->group; c->group = nullptr;
+        cudaSetDevice(c->device);
+        for (uint32_t *p : g->root_pix) if (p) cudaFree(p);
+        if (g->recv) cudaFree(g->recv);
+        for (size_t k = 1; k < g->members.size(); ++k) {
+            cudaSetDevice(g->members[k]->device);
+            if (k < g->send.size() && g->send[k]) cudaFree(g->send[k]);
+            tgb200_destroy(g->members[k]);
+        }
+        delete g;
+    }
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     if (c->l2_window_bytes) cudaCtxResetPersistingL2Cache();
@@ -917,9 +1072,50 @@ void tgb200_destroy(tgb_ctx *c) {
     delete c;
 }
 
+static int create_single(const tgb_scene_desc *d, tgb_ctx **out);
+
 int tgb200_create(const tgb_scene_desc *d, tgb_ctx **out) {
-    tgb_ctx *c = nullptr;
     if (!d || !out) return fail(nullptr, TGB_ERR_INVALID, "null argument");
+    *out = nullptr;
+    const uint32_t N = d->settings.n_devices;
+    if (N <= 1) {
+        tgb_scene_desc one = *d;
+        if (N == 1) one.settings.device = d->settings.devices[0];
+        one.settings.n_devices = 0;
+        return create_single(&one, out);
+    }
+    if (N > 8) return fail(nullptr, TGB_ERR_INVALID, "at most 8 devices");
+    for (uint32_t i = 0; i < N; ++i) for (uint32_t j = 0; j < i; ++j)
+        if (d->settings.devices[i] == d->settings.devices[j]) return fail(nullptr, TGB_ERR_INVALID, "device %d listed twice", d->settings.devices[i]);
+    // one context per GPU, created concurrently (each uploads its own replica of the scene; the host BVH build runs per member)
+    std::vector<tgb_ctx *> members(N, nullptr); std::vector<int> rcs(N, TGB_OK); std::vector<std::string> errs(N);
+    std::vector<std::thread> th;
+    for (uint32_t k = 0; k < N; ++k) th.emplace_back([&, k] {
+        tgb_scene_desc one = *d; one.settings.device = d->settings.devices[k]; one.settings.n_devices = 0;
+        rcs[k] = create_single(&one, &members[k]);
+        if (rcs[k]) errs[k] = g_create_error;
+    });
+    for (std::thread &t : th) t.join();
+    for (uint32_t k = 0; k < N; ++k) if (rcs[k]) {
+        for (tgb_ctx *m : members) if (m) tgb200_destroy(m);
+        return fail(nullptr, rcs[k], "device %d: %s", d->settings.devices[k], errs[k].c_str());
+    }
+    tgb_ctx *root = members[0];
+    for (uint32_t k = 1; k < N; ++k) {             // NVLink peer access root <-> member (without it the copies stage through the host)
+        int can = 0;
+        cudaDeviceCanAccessPeer(&can, root->device, members[k]->device);
+        if (can) { cudaSetDevice(root->device); cudaDeviceEnablePeerAccess(members[k]->device, 0); cudaSetDevice(members[k]->device); cudaDeviceEnablePeerAccess(root->device, 0); }
+        cudaGetLastError();
+    }
+    cudaSetDevice(root->device);
+    root->group = new Group();
+    root->group->members = members;
+    *out = root;
+    return TGB_OK;
+}
+
+static int create_single(const tgb_scene_desc *d, tgb_ctx **out) {
+    tgb_ctx *c = nullptr;
     *out = nullptr;
     if (d->abi_version != TGB200_ABI_VERSION) return fail(nullptr, TGB_ERR_INVALID, "ABI version mismatch (got %u, library is %u)", d->abi_version, TGB200_ABI_VERSION);
     if (!d->settings.use_sobol) return fail(nullptr, TGB_ERR_UNSUPPORTED, "only the Sobol sampler (renderer.stratified_sampler = true) is on the hot path");
@@ -974,6 +1170,7 @@ int tgb200_create(const tgb_scene_desc *d, tgb_ctx **out) {
 
 int tgb200_clear_framebuffer(tgb_ctx *c) {
     if (!c) return TGB_ERR_INVALID;
+    { int rc = for_members(c, [](tgb_ctx *m) { return tgb200_clear_framebuffer(m); }); if (rc) return rc; }
     CU(cudaSetDevice(c->device));
     size_t npx = size_t(c->res_x)*c->res_y;
     CU(cudaMemsetAsync(c->fb, 0, npx*3*sizeof(float), c->stream));
@@ -985,11 +1182,19 @@ int tgb200_clear_framebuffer(tgb_ctx *c) {
 int tgb200_render_resident(tgb_ctx *c, const tgb_tile *tiles, uint32_t n_tiles, uint32_t seed, uint32_t spp_begin, uint32_t spp_count) {
     if (!c) return TGB_ERR_INVALID;
     if (n_tiles && !tiles) return fail(c, TGB_ERR_INVALID, "null tile list");
+    if (c->group) return group_render(c, tiles, n_tiles, seed, spp_begin, spp_count, nullptr);
+    return single_render_resident(c, tiles, n_tiles, seed, spp_begin, spp_count);
+}
+}  // extern "C"
+namespace {
+int single_render_resident(tgb_ctx *c, const tgb_tile *tiles, uint32_t n_tiles, uint32_t seed, uint32_t spp_begin, uint32_t spp_count) {
     CU(cudaSetDevice(c->device));
     int rc = set_tiles(c, tiles, n_tiles, seed);
     if (rc) return rc;
     return render_device(c, spp_begin, spp_count);
 }
+}  // namespace
+extern "C" {
 
 int tgb200_read_framebuffer(tgb_ctx *c, float *rgb_mean, uint32_t *count) {
     if (!c || !rgb_mean) return TGB_ERR_INVALID;
@@ -1007,6 +1212,14 @@ int tgb200_render_tiles(tgb_ctx *c, const tgb_tile *tiles, uint32_t n_tiles, uin
                         float *rgb_mean, uint32_t *count) {
     if (!c || !rgb_mean) return c ? fail(c, TGB_ERR_INVALID, "null framebuffer") : TGB_ERR_INVALID;
     if (n_tiles && !tiles) return fail(c, TGB_ERR_INVALID, "null tile list");
+    if (c->group) {         // every member needs the caller's running means for its own pixels
+        std::vector<uint32_t> base;
+        if (!count) base.assign(size_t(c->res_x)*c->res_y, spp_begin);
+        int rc = tgb200_write_framebuffer(c, rgb_mean, count ? count : base.data());
+        if (rc) return rc;
+        if ((rc = group_render(c, tiles, n_tiles, seed, spp_begin, spp_count, nullptr))) return rc;
+        return tgb200_read_framebuffer(c, rgb_mean, count);
+    }
     CU(cudaSetDevice(c->device));
     size_t npx = size_t(c->res_x)*c->res_y;
     // host -> device: the caller's running mean and counts are the input state
@@ -1076,11 +1289,26 @@ int tgb200_trace_closest(tgb_ctx *c, const tgb_ray *rays, tgb_hit *hits, uint32_
 int tgb200_get_stats(tgb_ctx *c, tgb_stats *out) {
     if (!c || !out) return TGB_ERR_INVALID;
     *out = c->stats;
+    if (c->group) {         // counts add up over the GPUs, times are those of the slowest GPU
+        for (size_t k = 1; k < c->group->members.size(); ++k) {
+            const tgb_stats &m = c->group->members[k]->stats;
+            out->samples += m.samples; out->rays += m.rays; out->hits += m.hits; out->kernel_launches += m.kernel_launches;
+            out->path_rays += m.path_rays; out->shadow_rays += m.shadow_rays; out->trace_launches += m.trace_launches;
+            out->shadow_launches += m.shadow_launches; out->path_rays_traversed += m.path_rays_traversed;
+            out->shadow_rays_traversed += m.shadow_rays_traversed; out->iterations += m.iterations;
+            out->trace_ms = std::max(out->trace_ms, m.trace_ms); out->total_ms = std::max(out->total_ms, m.total_ms);
+            out->shadow_ms = std::max(out->shadow_ms, m.shadow_ms); out->regen_ms = std::max(out->regen_ms, m.regen_ms);
+            out->shade_ms = std::max(out->shade_ms, m.shade_ms); out->prep_ms = std::max(out->prep_ms, m.prep_ms);
+            out->accum_ms = std::max(out->accum_ms, m.accum_ms); out->sort_ms = std::max(out->sort_ms, m.sort_ms);
+        }
+        out->sort_ms += c->group->gather_ms;            // (the gather is accounted with the loop's bookkeeping time)
+    }
     return TGB_OK;
 }
 
 int tgb200_reset_stats(tgb_ctx *c) {
     if (!c) return TGB_ERR_INVALID;
+    { int rc = for_members(c, [](tgb_ctx *m) { return tgb200_reset_stats(m); }); if (rc) return rc; if (c->group) c->group->gather_ms = 0.0; }
     CU(cudaSetDevice(c->device));
     c->stats = tgb_stats{};
     CU(cudaMemsetAsync(c->ctr, 0, sizeof(Counters), c->stream));
@@ -1090,6 +1318,7 @@ int tgb200_reset_stats(tgb_ctx *c) {
 
 int tgb200_set_stream(tgb_ctx *c, void *cuda_stream) {
     if (!c) return TGB_ERR_INVALID;
+    if (c->group && cuda_stream) return fail(c, TGB_ERR_UNSUPPORTED, "a multi-GPU context runs every GPU on its own stream");
     CU(cudaSetDevice(c->device));
     CU(cudaStreamSynchronize(c->stream));
     c->stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : c->own_stream;
@@ -1098,6 +1327,7 @@ int tgb200_set_stream(tgb_ctx *c, void *cuda_stream) {
 
 int tgb200_set_profiling(tgb_ctx *c, int enable) {
     if (!c) return TGB_ERR_INVALID;
+    for_members(c, [enable](tgb_ctx *m) { return tgb200_set_profiling(m, enable); });
     c->profiling = enable != 0;
     return TGB_OK;
 }
@@ -1224,6 +1454,7 @@ int tgb200_bvh_selftest(const float *tri_verts, uint32_t n, uint32_t *n_nodes, u
 
 int tgb200_write_framebuffer(tgb_ctx *c, const float *rgb_mean, const uint32_t *count) {
     if (!c || !rgb_mean || !count) return TGB_ERR_INVALID;
+    { int rc = for_members(c, [=](tgb_ctx *m) { return tgb200_write_framebuffer(m, rgb_mean, count); }); if (rc) return rc; }
     CU(cudaSetDevice(c->device));
     size_t npx = size_t(c->res_x)*c->res_y;
     std::memcpy(c->h_fb, rgb_mean, npx*3*sizeof(float)); std::memcpy(c->h_fb_count, count, npx*sizeof(uint32_t));
@@ -1239,6 +1470,12 @@ int tgb200_write_framebuffer(tgb_ctx *c, const float *rgb_mean, const uint32_t *
 int tgb200_render_adaptive(tgb_ctx *c, const tgb_tile *tiles, uint32_t n_tiles, uint32_t seed, tgb_sample_record *records) {
     if (!c || !records) return c ? fail(c, TGB_ERR_INVALID, "null records") : TGB_ERR_INVALID;
     if (n_tiles && !tiles) return fail(c, TGB_ERR_INVALID, "null tile list");
+    if (c->group) return group_render(c, tiles, n_tiles, seed, 0, 0, records);
+    return single_render_adaptive(c, tiles, n_tiles, seed, records);
+}
+}  // extern "C"
+namespace {
+int single_render_adaptive(tgb_ctx *c, const tgb_tile *tiles, uint32_t n_tiles, uint32_t seed, tgb_sample_record *records) {
     static_assert(sizeof(tgb_sample_record) == sizeof(SampleRecordD), "record layout");
     CU(cudaSetDevice(c->device));
     int rc = set_tiles(c, tiles, n_tiles, seed);
@@ -1284,6 +1521,15 @@ int tgb200_render_adaptive(tgb_ctx *c, const tgb_tile *tiles, uint32_t n_tiles, 
     CU(cudaMemcpyAsync(records, c->rec_dev, size_t(n_blocks)*sizeof(SampleRecordD), cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
     CU(cudaGetLastError());
+    return TGB_OK;
+}
+}  // namespace
+extern "C" {
+
+int tgb200_shard_tiles(const tgb_tile *tiles, uint32_t n_tiles, uint32_t *order) {
+    if ((n_tiles && !tiles) || !order) return TGB_ERR_INVALID;
+    std::vector<uint32_t> o; shard_order(tiles, n_tiles, o);
+    std::memcpy(order, o.data(), size_t(n_tiles)*4);
     return TGB_OK;
 }
 
@@ -1426,12 +1672,14 @@ int tgb200_qbvh_selftest(const float *tri_verts, uint32_t n, const float *rays, 
 
 int tgb200_clear_abort(tgb_ctx *c) {
     if (!c) return TGB_ERR_INVALID;
+    for_members(c, [](tgb_ctx *m) { return tgb200_clear_abort(m); });
     c->abort_flag.store(0);
     return TGB_OK;
 }
 
 int tgb200_abort(tgb_ctx *c) {
     if (!c) return TGB_ERR_INVALID;
+    for_members(c, [](tgb_ctx *m) { return tgb200_abort(m); });
     c->abort_flag.store(1);
     return TGB_OK;
 }

@@ -1395,4 +1395,23 @@ __global__ void __launch_bounds__(256) k_unpack_tiles(const uint32_t *pix_id, ui
     fb_count[pix_id[i]] = count;
 }
 
+// In-library multi-GPU hand-off (tgb_settings::devices): a member packs the pixels of its tile share as (mean.rgb, sample count)
+// records, the records travel to the root GPU with one peer-to-peer copy over NVLink, the root de-tiles them into its framebuffer.
+__global__ void __launch_bounds__(256) k_pack_share(const uint32_t *pix_id, uint32_t n_pix, const float *fb, const uint32_t *fb_count, float4 *out) {
+    uint32_t i = blockIdx.x*blockDim.x + threadIdx.x;
+    if (i >= n_pix) return;
+    const uint32_t pid = pix_id[i];
+    size_t p = size_t(pid)*3;
+    out[i] = make_float4(fb[p], fb[p + 1], fb[p + 2], __uint_as_float(fb_count[pid]));
+}
+__global__ void __launch_bounds__(256) k_unpack_share(const uint32_t *pix_id, uint32_t n_pix, const float4 *in, float *fb, uint32_t *fb_count) {
+    uint32_t i = blockIdx.x*blockDim.x + threadIdx.x;
+    if (i >= n_pix) return;
+    const uint32_t pid = pix_id[i];
+    const float4 v = in[i];
+    size_t p = size_t(pid)*3;
+    fb[p] = v.x; fb[p + 1] = v.y; fb[p + 2] = v.z;
+    fb_count[pid] = __float_as_uint(v.w);
+}
+
 }  // namespace tgb

@@ -36,6 +36,7 @@ def load():
     L.tgb200_render_adaptive.argtypes = [vp, vp, u32, u32, vp]
     L.tgb200_framebuffer_device_ptr.argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_uint64)]
     L.tgb200_trace_closest.argtypes = [vp, vp, vp, u32]
+    L.tgb200_shard_tiles.argtypes = [vp, u32, vp]
     L.tgb200_pack_tiles.argtypes = [vp, vp, u32, vp]
     L.tgb200_unpack_tiles.argtypes = [vp, vp, u32, vp, u32]
     L.tgb200_get_stats.argtypes = [vp, C.POINTER(abi.Stats)]
@@ -56,11 +57,16 @@ def load():
 class Context:
     """RAII wrapper of a `tgb_ctx` (one scene on one GPU)."""
 
-    def __init__(self, flat_scene, device=-1, max_paths_in_flight=0):
+    def __init__(self, flat_scene, device=-1, max_paths_in_flight=0, devices=None):
+        """devices: list of CUDA ordinals -> one replica per GPU inside this process (tgb_settings::devices); tiles are dealt to
+        them per render call and gathered on devices[0] over NVLink."""
         self.L = load()
         self.fs = flat_scene
         flat_scene.settings.device = device
         flat_scene.settings.max_paths_in_flight = max_paths_in_flight
+        flat_scene.settings.n_devices = 0 if not devices else len(devices)
+        for i, dv in enumerate(devices or []):
+            flat_scene.settings.devices[i] = int(dv)
         self._desc = flat_scene.desc()
         h = C.c_void_p()
         rc = self.L.tgb200_create(C.byref(self._desc), C.byref(h))

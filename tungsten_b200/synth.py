@@ -158,6 +158,25 @@ def cornell_mesh(out_dir, name="cornell_mesh", subdiv=3, res=(128, 128), spp=16,
     return write_scene(out_dir, name, sc, {name + "_blob.wo3": (v, t)})
 
 
+def dirac_room(out_dir, name="dirac", res=(128, 128), spp=16, max_bounces=16, subdiv=3):
+    """Cornell box whose boxes are a mirror (MirrorBsdf) and a smooth conductor (ConductorBsdf, gold), plus a smooth dielectric
+    ball (DielectricBsdf, ior 1.5, refraction on) and a reflect-only dielectric blob: the Dirac lobes of f4."""
+    v, t = icosphere(subdiv, 1.0)
+    bs = [{"name": "glass", "type": "dielectric", "ior": 1.5, "albedo": 1.0},
+          {"name": "lacquer", "type": "dielectric", "ior": 1.8, "enable_refraction": False, "albedo": [0.9, 0.95, 1.0]}]
+    prims = [{"name": "ball", "type": "mesh", "file": name + "_ball.wo3", "smooth": True, "bsdf": "glass",
+              "transform": {"position": [0.35, 0.95, 0.45], "scale": [0.3, 0.3, 0.3]}},
+             {"name": "blob", "type": "mesh", "file": name + "_ball.wo3", "smooth": True, "bsdf": "lacquer",
+              "transform": {"position": [-0.55, 0.3, 0.55], "scale": [0.28, 0.28, 0.28]}}]
+    sc = cornell_box(res, spp, max_bounces, extra_bsdfs=bs, extra_prims=prims)
+    for b in sc["bsdfs"]:
+        if b["name"] == "shortBox":
+            b.clear(); b.update({"name": "shortBox", "type": "mirror", "albedo": [0.95, 0.95, 0.95]})
+        if b["name"] == "tallBox":
+            b.clear(); b.update({"name": "tallBox", "type": "conductor", "material": "Au", "albedo": 1.0})
+    return write_scene(out_dir, name, sc, {name + "_ball.wo3": (v, t)})
+
+
 def cornell_dragon_standin(out_dir, name="cornell_dragon", res=(1920, 1080), spp=1024, max_bounces=64):
     """BASELINE.json config C1: Cornell box + ~870k-triangle Lambert mesh.  The Stanford dragon is not in
     the reference repository; the stand-in is a lobed, displaced icosphere at subdivision 7 (327,680
