@@ -543,7 +543,7 @@ def make_kat_curves():
     shutil.rmtree(d)
 
 
-def make_scenes():
+def make_scenes(only=None):
     from tungsten_b200 import synth
     scenes = {}
     res, spp = (64, 64), 8
@@ -564,6 +564,8 @@ def make_scenes():
     scenes["curves_plastic"] = synth.hair_scene(os.path.join(HERE, "curves_plastic"), "scene", n_curves=300, res=res, spp=spp, mode="cylinder",
                                                 bsdf={"type": "rough_plastic", "albedo": [0.6, 0.4, 0.2], "roughness": 0.2}, thickness=0.015,
                                                 taper=True, subsample=0.3)
+    # 39 samplable lights (36 quads + the ceiling light + 2 mesh lights): chooseLight beyond 16 lights
+    scenes["many_lights"] = synth.many_lights(os.path.join(HERE, "many_lights"), "scene", res=res, spp=spp, subdiv=2)
     scenes["dirac"] = synth.dirac_room(os.path.join(HERE, "dirac"), "scene", res=res, spp=spp, subdiv=2)
     # the two emitters of the shipped hair scene: infinite_sphere_cap (sampled sun) + skydome (unsampled sky); min_bounces 1 as shipped
     scenes["hair_sky"] = synth.hair_scene(os.path.join(HERE, "hair_sky"), "scene", n_curves=300, res=res, spp=spp, shipped_lights=True, min_bounces=1)
@@ -574,6 +576,8 @@ def make_scenes():
     d = os.path.join(HERE, "cornell_adaptive"); os.makedirs(d, exist_ok=True)
     scenes["cornell_adaptive"] = synth.write_scene(d, "scene", ad)
     for name, path in scenes.items():
+        if only and name not in only:
+            continue
         d = os.path.dirname(path)
         for exe, tag in (("tungsten_pathseed", "ref_pathseed"), ("tungsten", "ref_stock")):
             out = tempfile.mkdtemp()

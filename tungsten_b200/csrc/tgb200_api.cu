@@ -459,7 +459,6 @@ int upload_scene(tgb_ctx *c, const tgb_scene_desc *d) {
         lights.push_back(int(prims.size())); inf_lights.push_back(int(prims.size()));
         prims.push_back(o);
     }
-    if (lights.size() > 16) return fail(c, TGB_ERR_UNSUPPORTED, "more than 16 samplable lights");
     if (analytic.size() > 4096) return fail(c, TGB_ERR_UNSUPPORTED, "more than 4096 analytic primitives");
     for (int li : lights) {
         DPrim &l = prims[li];

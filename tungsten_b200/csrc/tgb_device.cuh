@@ -1053,29 +1053,58 @@ TGB_D float light_approx_radiance(const DScene &sc, const DPrim &l, V3 p) {
 }
 
 // TraceBase::chooseLight (integrators/TraceBase.cpp:416-459).  Returns the primitive index or -1.
+// The reference keeps one pdf per light in a vector.  Up to 16 lights they live in registers/local memory here; beyond that
+// (any number of lights) the approximate radiances are re-evaluated in three passes -- totals, the running-total replacement of
+// the "unknown" (negative) entries, selection -- which performs the same float operations in the same order.
 TGB_D int choose_light(const DScene &sc, V3 p, Sampler &smp, float &weight) {
-    int n = sc.n_lights;
+    const int n = sc.n_lights;
     if (n == 0) return -1;
     if (n == 1) { weight = 1.0f; return sc.lights[0]; }
-    float pdfs[16];
-    if (n > 16) n = 16;
-    float total = 0.0f; unsigned numNonNegative = 0;
-    for (int i = 0; i < n; ++i) {
-        pdfs[i] = light_approx_radiance(sc, sc.prims[sc.lights[i]], p);
-        if (pdfs[i] >= 0.0f) { total += pdfs[i]; numNonNegative++; }
-    }
-    if (numNonNegative == 0) { for (int i = 0; i < n; ++i) pdfs[i] = 1.0f; total = float(n); }
-    else if (numNonNegative < unsigned(n)) {
+    if (n <= 16) {
+        float pdfs[16];
+        float total = 0.0f; unsigned numNonNegative = 0;
         for (int i = 0; i < n; ++i) {
-            float uniformWeight = (total == 0.0f ? 1.0f : total)/numNonNegative;
-            if (pdfs[i] < 0.0f) { pdfs[i] = uniformWeight; total += uniformWeight; }
+            pdfs[i] = light_approx_radiance(sc, sc.prims[sc.lights[i]], p);
+            if (pdfs[i] >= 0.0f) { total += pdfs[i]; numNonNegative++; }
         }
+        if (numNonNegative == 0) { for (int i = 0; i < n; ++i) pdfs[i] = 1.0f; total = float(n); }
+        else if (numNonNegative < unsigned(n)) {
+            for (int i = 0; i < n; ++i) {
+                float uniformWeight = (total == 0.0f ? 1.0f : total)/numNonNegative;
+                if (pdfs[i] < 0.0f) { pdfs[i] = uniformWeight; total += uniformWeight; }
+            }
+        }
+        if (total == 0.0f) return -1;
+        float t = sampler_next1d(smp)*total;
+        for (int i = 0; i < n; ++i) {
+            if (t < pdfs[i] || i == n - 1) { weight = total/pdfs[i]; return sc.lights[i]; }
+            t -= pdfs[i];
+        }
+        return -1;
+    }
+    float known = 0.0f; unsigned numNonNegative = 0;
+    for (int i = 0; i < n; ++i) {
+        const float r = light_approx_radiance(sc, sc.prims[sc.lights[i]], p);
+        if (r >= 0.0f) { known += r; numNonNegative++; }
+    }
+    const bool none_known = numNonNegative == 0, some_unknown = numNonNegative < unsigned(n);
+    float total = known;
+    if (none_known) total = float(n);
+    else if (some_unknown) {
+        for (int i = 0; i < n; ++i)
+            if (light_approx_radiance(sc, sc.prims[sc.lights[i]], p) < 0.0f) total += (total == 0.0f ? 1.0f : total)/numNonNegative;
     }
     if (total == 0.0f) return -1;
     float t = sampler_next1d(smp)*total;
+    float running = known;
     for (int i = 0; i < n; ++i) {
-        if (t < pdfs[i] || i == n - 1) { weight = total/pdfs[i]; return sc.lights[i]; }
-        t -= pdfs[i];
+        float pdf = 1.0f;
+        if (!none_known) {
+            pdf = light_approx_radiance(sc, sc.prims[sc.lights[i]], p);
+            if (pdf < 0.0f) { pdf = (running == 0.0f ? 1.0f : running)/numNonNegative; running += pdf; }
+        }
+        if (t < pdf || i == n - 1) { weight = total/pdf; return sc.lights[i]; }
+        t -= pdf;
     }
     return -1;
 }

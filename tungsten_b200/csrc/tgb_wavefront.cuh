@@ -190,10 +190,16 @@ TGB_D void curve_half_cylinder(const CurvePiece &node, float tMin, float &tMax, 
     float newT = segmentT*(node.tMax - node.tMin) + node.tMin;
     if (newT >= 0.0f && newT <= 1.0f) { hu = newT; ht = t0; hw = width; tMax = t0; }
 }
-// pointOnSpline<false>: p0..p2 are the projected nodes; true when a hit closer than tMax was found (t, u, w are set)
+// pointOnSpline<false>: p0..p2 are the projected nodes; true when a hit closer than tMax was found (t, u, w are set).
+// The reference keeps an explicit stack of pieces (tMin, tMax, both end points).  Every end point is the same function of its
+// dyadic parameter (q0*t*t + q1*t + q2, t = k/2^depth, exact in float), and the stack is strictly LIFO with one pending sibling
+// per depth, so the stack is a 5-bit mask here and a popped piece's end points are re-evaluated: same values, same visiting
+// order, no local-memory traffic (the 5 x 44-byte stack was the kernel's only local array).
+TGB_D float4 curve_eval(float4 q0, float4 q1, float4 q2, float t) {
+    return f4add(f4add(f4scale(q0, t*t), f4scale(q1, t)), q2);
+}
 TGB_D bool curve_point_on_spline(float4 p0, float4 p1, float4 p2, float tMin, float tMax, float &ht, float &hu, float &hw) {
     constexpr int MaxDepth = 5;
-    CurvePiece stack[MaxDepth]; int sp = 0;
     float4 q0 = f4add(f4sub(f4scale(p0, 0.5f), p1), f4scale(p2, 0.5f));
     float4 q1 = f4sub(p1, p0);
     float4 q2 = f4scale(f4add(p0, p1), 0.5f);
@@ -201,6 +207,7 @@ TGB_D bool curve_point_on_spline(float4 p0, float4 p1, float4 p2, float tMin, fl
     float xFlat = q0.x*tFlatX*tFlatX + q1.x*tFlatX + q2.x;
     float yFlat = q0.y*tFlatY*tFlatY + q1.y*tFlatY + q2.y;
     CurvePiece cur; cur.p0 = q2; cur.p1 = f4add(f4add(q0, q1), q2); cur.tMin = 0.0f; cur.tMax = 1.0f; cur.depth = 0;
+    uint32_t idx = 0, pending = 0;                 // the piece is [idx, idx + 1]/2^depth; bit L of pending = the sibling at depth L waits
     float closestDepth = tMax;
     for (;;) {
         float pMinX = cur.p1.x < cur.p0.x ? cur.p1.x : cur.p0.x, pMinY = cur.p1.y < cur.p0.y ? cur.p1.y : cur.p0.y;
@@ -213,21 +220,22 @@ TGB_D bool curve_point_on_spline(float4 p0, float4 p1, float4 p2, float tMin, fl
                 curve_half_cylinder(cur, tMin, closestDepth, ht, hu, hw);
             } else {
                 float splitT = (cur.tMin + cur.tMax)*0.5f;
-                float4 qSplit = f4add(f4add(f4scale(q0, splitT*splitT), f4scale(q1, splitT)), q2);
-                CurvePiece &top = stack[sp++];
-                if (cur.p0.z < qSplit.z) {
-                    top.tMin = splitT; top.tMax = cur.tMax; top.p0 = qSplit; top.p1 = cur.p1; top.depth = cur.depth + 1;
-                    cur.tMax = splitT; cur.p1 = qSplit; cur.depth = cur.depth + 1;
-                } else {
-                    top.tMin = cur.tMin; top.tMax = splitT; top.p0 = cur.p0; top.p1 = qSplit; top.depth = cur.depth + 1;
-                    cur.tMin = splitT; cur.p0 = qSplit; cur.depth = cur.depth + 1;
-                }
+                float4 qSplit = curve_eval(q0, q1, q2, splitT);
+                cur.depth = cur.depth + 1; pending |= 1u << cur.depth;
+                if (cur.p0.z < qSplit.z) { idx = 2*idx;     cur.tMax = splitT; cur.p1 = qSplit; }     // near half first, the other half waits
+                else                     { idx = 2*idx + 1; cur.tMin = splitT; cur.p0 = qSplit; }
                 continue;
             }
         }
         do {
-            if (sp == 0) return closestDepth < tMax;
-            cur = stack[--sp];
+            if (pending == 0) return closestDepth < tMax;
+            int L = 31 - __clz(pending); pending ^= 1u << L;
+            idx = (idx >> (cur.depth - L)) ^ 1u; cur.depth = L;
+            float scale = __uint_as_float(uint32_t(127 - L) << 23);                   // 2^-L
+            cur.tMin = float(idx)*scale; cur.tMax = float(idx + 1)*scale;
+            float4 e0 = curve_eval(q0, q1, q2, cur.tMin);
+            cur.p0 = idx == 0 ? q2 : e0;                                              // (the root's first end point is q2 itself)
+            cur.p1 = curve_eval(q0, q1, q2, cur.tMax);
         } while (minf(cur.p0.z - cur.p0.w, cur.p1.z - cur.p1.w) > closestDepth);
     }
 }
@@ -406,6 +414,25 @@ struct Traversal {
 #endif
     }
 
+    // Moeller-Trumbore on leaf-order record k; true (and h updated) when it is hit closer than h.t
+    TGB_D bool triangle(const DScene &sc, int k) {
+        const float4 *tr = sc.tri_isect + 3*size_t(k);
+        const float4 a = __ldg(tr), b = __ldg(tr + 1), c = __ldg(tr + 2);
+        V3 v0 = v3(a.x, a.y, a.z), e1 = v3(a.w, b.x, b.y), e2 = v3(b.z, b.w, c.x), ng = v3(c.y, c.z, c.w);
+        V3 C = v0 - o;
+        V3 R = cross(d, C);
+        float den = edot(ng, d);
+        float absDen = fabsf(den);
+        uint32_t sgn = __float_as_uint(den) & 0x80000000u;
+        float U = xor_sign(edot(R, e2), sgn);
+        float V = xor_sign(edot(R, e1), sgn);
+        if (!(den != 0.0f && U >= 0.0f && V >= 0.0f && U + V <= absDen)) return false;
+        float T = xor_sign(edot(ng, C), sgn);
+        if (!(T > absDen*tnear && T < absDen*h.t)) return false;
+        h.t = T/absDen; h.u = U/absDen; h.v = V/absDen; h.id = k;
+        return true;
+    }
+
     template <class Y>
     TGB_D bool run(const DScene &sc, const uint4 *treelet, TravStack &stk, int &sp, Y yield) {
         while (true) {
@@ -453,21 +480,7 @@ struct Traversal {
             }
         } else
         for (int i = 0; i < count; ++i) {
-            const float4 *tr = sc.tri_isect + 3*size_t(first + i);
-            const float4 a = __ldg(tr), b = __ldg(tr + 1), c = __ldg(tr + 2);
-            V3 v0 = v3(a.x, a.y, a.z), e1 = v3(a.w, b.x, b.y), e2 = v3(b.z, b.w, c.x), ng = v3(c.y, c.z, c.w);
-            V3 C = v0 - o;
-            V3 R = cross(d, C);
-            float den = edot(ng, d);
-            float absDen = fabsf(den);
-            uint32_t sgn = __float_as_uint(den) & 0x80000000u;
-            float U = xor_sign(edot(R, e2), sgn);
-            float V = xor_sign(edot(R, e1), sgn);
-            if (!(den != 0.0f && U >= 0.0f && V >= 0.0f && U + V <= absDen)) continue;
-            float T = xor_sign(edot(ng, C), sgn);
-            if (!(T > absDen*tnear && T < absDen*h.t)) continue;
-            h.t = T/absDen; h.u = U/absDen; h.v = V/absDen; h.id = first + i;
-            if (any) return true;
+            if (triangle(sc, first + i) && any) return true;
         }
         if (sp == 0) return true;
             cur = stk.pop(sp);
@@ -491,8 +504,20 @@ TGB_D void bvh_traverse(const DScene &sc, const uint4 *treelet, int *smem_stack,
 #ifndef TGB_REFILL_BELOW
 #define TGB_REFILL_BELOW 20
 #endif
+// resident blocks the CURVE instantiations of the traversal kernels are compiled for (4 x 128 threads: up to 128 registers; the
+// state machine keeps a ray's traversal AND bisection state live, and it is issue bound, not latency bound)
+#ifndef TGB_MINB_CURVES
+#define TGB_MINB_CURVES 5
+#endif
+template <bool CURVES, class P>
+TGB_D void machine_traverse_persistent(const DScene &sc, const uint4 *treelet, int *smem_stack, P &pol, uint32_t n, uint32_t *counter);
+// 1 = triangle-only scenes go through the state machine too (measured: see profiles/r02_k)
+#ifndef TGB_MACHINE_TRIS
+#define TGB_MACHINE_TRIS 1
+#endif
 template <bool CURVES, class P>
 TGB_D void bvh_traverse_persistent(const DScene &sc, const uint4 *treelet, int *smem_stack, P &pol, uint32_t n, uint32_t *counter) {
+    if constexpr (CURVES || TGB_MACHINE_TRIS) { machine_traverse_persistent<CURVES>(sc, treelet, smem_stack, pol, n, counter); return; }
     const unsigned FULL = 0xffffffffu, lane = threadIdx.x & 31u;
     Traversal<CURVES> tr; TravStack stk; stk.base = smem_addr(smem_stack + threadIdx.x); int sp = 0;
     bool active = false, exhausted = false;
@@ -515,6 +540,191 @@ TGB_D void bvh_traverse_persistent(const DScene &sc, const uint4 *treelet, int *
             const bool may_refill = !exhausted;
             bool done = tr.run(sc, treelet, stk, sp, [=] { return may_refill && __popc(__activemask()) < TGB_REFILL_BELOW; });
             if (done) { pol.finish(tr.h); active = false; }
+        }
+    }
+}
+
+// Curve scenes: the same persistent loop as a warp-level STATE MACHINE.  A segment test is a data-dependent bisection of 1..63
+// steps and the while-while form above ran it inside the leaf loop of each lane: ncu (profiles/r02_i_c4_k_trace.md) showed the
+// kernel issue bound (0.84 instructions / cycle / scheduler) with 3.97 of 32 threads active per instruction -- every lane
+// waiting for the warp's longest bisection.  Here each lane is in one of four states and every trip of the loop runs ONE block
+// of code for all the lanes that are in the state most lanes are in:
+//      NODE    one 4-ary node visit                          LEAF   next primitive of the leaf: triangle tests, or the set-up
+//      BISECT  one step of pointOnSpline (box test, split     CYL    intersectHalfCylinder of a depth-5 piece, then pop
+//              or pop)
+// so a lane in a long bisection no longer stalls the others: they go on visiting nodes and starting their own segment tests in
+// the same trips.  A ray's arithmetic and the order of ITS node visits / segment tests are unchanged (parity unaffected);
+// idle lanes are refilled from the ray cursor as above.
+#ifndef TGB_CURVE_REFILL_IDLE
+#define TGB_CURVE_REFILL_IDLE 8
+#endif
+#ifndef TGB_CM_WN            // scheduling weights of the four blocks (the block with the largest weight x lanes runs)
+#define TGB_CM_WN 4
+#endif
+#ifndef TGB_CM_WL
+#define TGB_CM_WL 4
+#endif
+#ifndef TGB_CM_WB
+#define TGB_CM_WB 4
+#endif
+#ifndef TGB_CM_WC
+#define TGB_CM_WC 4
+#endif
+enum : int { CM_IDLE = 0, CM_NODE = 1, CM_LEAF = 2, CM_BISECT = 3, CM_CYL = 4 };
+template <bool CURVES, class P>
+TGB_D void machine_traverse_persistent(const DScene &sc, const uint4 *treelet, int *smem_stack, P &pol, uint32_t n, uint32_t *counter) {
+    const unsigned FULL = 0xffffffffu, lane = threadIdx.x & 31u;
+    constexpr int kW[4] = {TGB_CM_WN, TGB_CM_WL, TGB_CM_WB, TGB_CM_WC};
+    Traversal<CURVES> tr; TravStack stk; stk.base = smem_addr(smem_stack + threadIdx.x); int sp = 0;
+    int mode = CM_IDLE; bool exhausted = false;
+    int li = 0, prim = 0; bool seg_hit = false;                                        // leaf cursor, BVH primitive under test
+    float4 q0 = {}, q1 = {}, q2 = {}, c0 = {}, c1 = {};                                 // the segment's quadratic, the current piece's end points
+    float tFlatX = 0.0f, tFlatY = 0.0f, xFlat = 0.0f, yFlat = 0.0f, pMin = 0.0f, pMax = 1.0f;
+    uint32_t bidx = 0, pending = 0; int depth = 0;                                      // piece = [bidx, bidx + 1]/2^depth; pending siblings by depth
+    auto finish_ray = [&]() { pol.finish(tr.h); mode = CM_IDLE; };
+    auto pop_node = [&]() {                                                             // leave a leaf: next stack entry or done
+        if (sp == 0) { finish_ray(); return; }
+        tr.cur = stk.pop(sp); li = 0; mode = tr.cur >= 0 ? CM_NODE : CM_LEAF;
+    };
+    // box test of pointOnSpline's loop head for the piece (a, b) = the curve on [ta, tb]
+    auto piece_box = [&](const float4 &a, const float4 &b, float ta, float tb) {
+        float mnx = b.x < a.x ? b.x : a.x, mny = b.y < a.y ? b.y : a.y;
+        float mxx = b.x > a.x ? b.x : a.x, mxy = b.y > a.y ? b.y : a.y;
+        if (tFlatX > ta && tFlatX < tb) { mnx = minf(mnx, xFlat); mxx = maxf(mxx, xFlat); }
+        if (tFlatY > ta && tFlatY < tb) { mny = minf(mny, yFlat); mxy = maxf(mxy, yFlat); }
+        const float mw = maxf(a.w, b.w);
+        return mnx <= mw && mny <= mw && mxx >= -mw && mxy >= -mw;
+    };
+    // The do-while at the end of pointOnSpline's loop.  Only pieces whose box test passed are ever marked pending (the test does
+    // not depend on the closest hit, so it is made when the parent is split), hence a popped piece goes straight on.
+    auto pop_piece = [&]() {
+        do {
+            if (pending == 0) {                                                          // segment finished
+                if (seg_hit && tr.any) finish_ray(); else mode = CM_LEAF;
+                return;
+            }
+            const int L = 31 - __clz(pending); pending ^= 1u << L;
+            bidx = (bidx >> (depth - L)) ^ 1u; depth = L;
+            const float scale = __uint_as_float(uint32_t(127 - L) << 23);                // 2^-L
+            pMin = float(bidx)*scale; pMax = float(bidx + 1)*scale;
+            const float4 e0 = curve_eval(q0, q1, q2, pMin);
+            c0 = bidx == 0 ? q2 : e0;
+            c1 = curve_eval(q0, q1, q2, pMax);
+        } while (minf(c0.z - c0.w, c1.z - c1.w) > tr.h.t);
+        mode = depth >= 5 ? CM_CYL : CM_BISECT;
+    };
+    for (;;) {
+        const unsigned idle = __ballot_sync(FULL, mode == CM_IDLE);
+        if (!exhausted && __popc(idle) >= TGB_CURVE_REFILL_IDLE) {
+            const unsigned cnt = unsigned(__popc(idle)), leader = unsigned(__ffs(int(idle))) - 1u;
+            uint32_t base = 0;
+            if (lane == leader) base = atomicAdd(counter, cnt);
+            base = __shfl_sync(FULL, base, int(leader));
+            exhausted = base + cnt >= n;
+            if (mode == CM_IDLE) {
+                const uint32_t i = base + unsigned(__popc(idle & ((1u << lane) - 1u)));
+                V3 o, d; float tnear; Hit h; bool any;
+                if (i < n && pol.fetch(i, o, d, tnear, h, any)) { tr.begin(o, d, tnear, any, h); sp = 0; mode = CM_NODE; }
+            }
+            continue;
+        }
+        if (idle == FULL) break;                                                        // (only reached once the cursor is exhausted)
+        const int sN = kW[0]*__popc(__ballot_sync(FULL, mode == CM_NODE)), sL = kW[1]*__popc(__ballot_sync(FULL, mode == CM_LEAF));
+        const int sB = CURVES ? kW[2]*__popc(__ballot_sync(FULL, mode == CM_BISECT)) : -1, sC = CURVES ? kW[3]*__popc(__ballot_sync(FULL, mode == CM_CYL)) : -1;
+        const int best = max(max(sN, sL), max(sB, sC));
+        if (CURVES && sB == best) {
+            // BISECT: split a piece that passed its box test (depth < 5) and test BOTH halves: the near half is entered if it
+            // passes, the far half is marked pending if it passes (the reference pushes it untested and tests it when popped;
+            // a failing piece has no side effect, so dropping it here changes nothing).  With only the far half left it is
+            // entered the way the reference reaches it -- through a pop, i.e. after the pruning comparison.
+            if (mode == CM_BISECT) {
+                const float splitT = (pMin + pMax)*0.5f;
+                const float4 qS = curve_eval(q0, q1, q2, splitT);
+                const bool first_near = c0.z < qS.z;
+                const bool passA = piece_box(c0, qS, pMin, splitT), passB = piece_box(qS, c1, splitT, pMax);
+                const bool passN = first_near ? passA : passB, passF = first_near ? passB : passA;
+                depth++;
+                bool second = !first_near;                                              // which half becomes the current piece
+                bool enter = passN;
+                if (passN) { if (passF) pending |= 1u << depth; }
+                else if (passF) {
+                    second = first_near;
+                    const float4 f0 = second ? qS : c0, f1 = second ? c1 : qS;
+                    enter = !(minf(f0.z - f0.w, f1.z - f1.w) > tr.h.t);
+                }
+                bidx = 2*bidx + (second ? 1u : 0u);
+                if (enter) {
+                    if (second) { pMin = splitT; c0 = qS; } else { pMax = splitT; c1 = qS; }
+                    if (depth >= 5) mode = CM_CYL;
+                } else pop_piece();
+            }
+        } else if (CURVES && sC == best) {
+            if (mode == CM_CYL) {
+                CurvePiece pc; pc.p0 = c0; pc.p1 = c1; pc.tMin = pMin; pc.tMax = pMax; pc.depth = depth;
+                const float before = tr.h.t;
+                float ht = 0.0f, hu = 0.0f, hw = 0.0f, closest = before;
+                curve_half_cylinder(pc, tr.tnear, closest, ht, hu, hw);
+                if (closest != before) { tr.h.t = ht; tr.h.u = hu; tr.h.v = hw; tr.h.id = prim; seg_hit = true; }
+                pop_piece();
+            }
+        } else if (sN == best) {
+            if (mode == CM_NODE) {
+                float t0, t1, t2, t3; int4 lk;
+                tr.visit(sc, treelet, t0, t1, t2, t3, lk);
+                int l0 = lk.x, l1 = lk.y, l2 = lk.z, l3 = lk.w;
+                TGB_CSWAP(t0, l0, t1, l1) TGB_CSWAP(t2, l2, t3, l3) TGB_CSWAP(t0, l0, t2, l2) TGB_CSWAP(t1, l1, t3, l3) TGB_CSWAP(t1, l1, t2, l2)
+                if (t0 == INFINITY) pop_node();
+                else {
+                    // sorted, so the children to push are a prefix of (l1, l2, l3); the nearest of them must end up on top
+                    const bool p1 = t1 != INFINITY, p2 = t2 != INFINITY, p3 = t3 != INFINITY;
+                    if (sp + 3 <= kSmemStack) {
+                        const uint32_t a3 = stk.base + uint32_t(sp)*(kTraceBlock*4u);
+                        const uint32_t a2 = a3 + (p3 ? kTraceBlock*4u : 0u), a1 = a2 + (p2 ? kTraceBlock*4u : 0u);
+                        if (p3) TravStack::sts(a3, l3);
+                        if (p2) TravStack::sts(a2, l2);
+                        if (p1) TravStack::sts(a1, l1);
+                        sp += int(p1) + int(p2) + int(p3);
+                    } else {
+                        if (p3) stk.push(sp, l3);
+                        if (p2) stk.push(sp, l2);
+                        if (p1) stk.push(sp, l1);
+                    }
+                    tr.cur = l0;
+                    if (l0 < 0) { mode = CM_LEAF; li = 0; }
+                }
+            }
+        } else {
+            if (mode == CM_LEAF) {
+                const int code = ~tr.cur, first = code >> 3, count = (code & 3) + 1;
+                if (CURVES && (code & 4)) {
+                    bool started = false;
+                    while (li < count) {
+                        const int i = li++;
+                        const int seg = int(__ldg(sc.tri_global + first + i) - sc.n_tris)/kCurvePieces;
+                        if (seg == tr.last_seg) continue;
+                        tr.last_seg = seg;
+                        const float4 *cr = sc.tri_isect + 3*size_t(first + i);
+                        const float4 p0 = curve_project(tr.o, tr.cf, tr.d, __ldg(cr)), p1 = curve_project(tr.o, tr.cf, tr.d, __ldg(cr + 1)), p2 = curve_project(tr.o, tr.cf, tr.d, __ldg(cr + 2));
+                        q0 = f4add(f4sub(f4scale(p0, 0.5f), p1), f4scale(p2, 0.5f));
+                        q1 = f4sub(p1, p0);
+                        q2 = f4scale(f4add(p0, p1), 0.5f);
+                        tFlatX = -q1.x*0.5f/q0.x; tFlatY = -q1.y*0.5f/q0.y;
+                        xFlat = q0.x*tFlatX*tFlatX + q1.x*tFlatX + q2.x;
+                        yFlat = q0.y*tFlatY*tFlatY + q1.y*tFlatY + q2.y;
+                        c0 = q2; c1 = f4add(f4add(q0, q1), q2); pMin = 0.0f; pMax = 1.0f; depth = 0; bidx = 0; pending = 0;
+                        if (!piece_box(c0, c1, 0.0f, 1.0f)) continue;                    // the whole segment misses: nothing else happens in pointOnSpline
+                        prim = first + i; seg_hit = false; mode = CM_BISECT; started = true;
+                        break;
+                    }
+                    if (!started) pop_node();
+                } else {
+                    bool hit_any = false;
+                    for (int i = 0; i < count; ++i) {
+                        if (tr.triangle(sc, first + i) && tr.any) { hit_any = true; break; }
+                    }
+                    if (hit_any) finish_ray(); else pop_node();
+                }
+            }
         }
     }
 }
@@ -755,7 +965,7 @@ struct PathRayPolicy {
     TGB_D void finish(const Hit &h) { T2[s] = pack_hit(h); }
 };
 template <bool CURVES>
-__global__ void __launch_bounds__(kTraceBlock, TGB_MINB) k_trace(DScene sc, PathBuf pb, const uint32_t *order, Ctl *ctl) {
+__global__ void __launch_bounds__(kTraceBlock, CURVES ? TGB_MINB_CURVES : TGB_MINB) k_trace(DScene sc, PathBuf pb, const uint32_t *order, Ctl *ctl) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const uint4 *treelet = stage_treelet(sc, smem_raw);
     int *smem_stack = reinterpret_cast<int *>(smem_raw + size_t(sc.n_treelet)*64);
@@ -801,7 +1011,7 @@ struct HookPersistPolicy {
     TGB_D void finish(const Hit &h) { out[i] = h; }
 };
 template <bool CURVES>
-__global__ void __launch_bounds__(kTraceBlock, TGB_MINB) k_hook_persist(DScene sc, const tgb_ray *rays, Hit *out, uint32_t n, uint32_t *counter) {
+__global__ void __launch_bounds__(kTraceBlock, CURVES ? TGB_MINB_CURVES : TGB_MINB) k_hook_persist(DScene sc, const tgb_ray *rays, Hit *out, uint32_t n, uint32_t *counter) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const uint4 *treelet = stage_treelet(sc, smem_raw);
     int *smem_stack = reinterpret_cast<int *>(smem_raw + size_t(sc.n_treelet)*64);
@@ -1204,7 +1414,7 @@ struct ShadowPolicy {
     }
 };
 template <bool CURVES>
-__global__ void __launch_bounds__(kTraceBlock, TGB_MINB) k_shadow_bvh(DScene sc, Scratch sr, const uint32_t *squeue, Ctl *ctl, Counters *ctr) {
+__global__ void __launch_bounds__(kTraceBlock, CURVES ? TGB_MINB_CURVES : TGB_MINB) k_shadow_bvh(DScene sc, Scratch sr, const uint32_t *squeue, Ctl *ctl, Counters *ctr) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const uint4 *treelet = stage_treelet(sc, smem_raw);
     int *smem_stack = reinterpret_cast<int *>(smem_raw + size_t(sc.n_treelet)*64);

@@ -226,6 +226,31 @@ def material_room(out_dir, name="materials", res=(128, 128), spp=16, max_bounces
     return write_scene(out_dir, name, sc, meshes)
 
 
+def many_lights(out_dir, name="many_lights", n_quads=36, res=(128, 128), spp=16, max_bounces=16, subdiv=3):
+    """Cornell room + blob lit by the ceiling light, a 6 x 6 grid of small coloured quad lights under the ceiling and two mesh
+    lights (whose approximate radiance is "unknown" in TraceBase::chooseLight): 39 samplable lights.  The reference keeps
+    one pdf per light in a vector of any length; this scene pins the device's > 16 lights path."""
+    v, t = icosphere(subdiv, 1.0, displace=0.12)
+    lv, lt = grid_mesh(2, 2, 1.0)
+    meshes = {name + "_blob.wo3": (v, t), name + "_lamp.wo3": (lv, lt)}
+    bsdfs = [_lambert("blob", [0.6, 0.55, 0.7]), {"name": "lamp", "type": "null", "albedo": 1.0}]
+    prims = [{"name": "blob", "type": "mesh", "file": name + "_blob.wo3", "smooth": True, "bsdf": "blob",
+              "transform": {"position": [0.0, 0.6, 0.0], "scale": [0.5, 0.5, 0.5], "rotation": [0, 30, 0]}}]
+    side = int(round(n_quads**0.5))
+    for k in range(n_quads):
+        i, j = k % side, k//side
+        x, z = -0.8 + 1.6*i/max(side - 1, 1), -0.8 + 1.6*j/max(side - 1, 1)
+        em = [1.5 + 4.0*((k*7) % 5)/4.0, 1.5 + 4.0*((k*3) % 4)/3.0, 1.5 + 4.0*((k*5) % 3)/2.0]
+        prims.append({"name": "q%d" % k, "type": "quad", "bsdf": "lamp", "emission": em,
+                      "transform": {"position": [x, 1.9 - 0.01*(k % 3), z], "scale": [0.09, 1, 0.07], "rotation": [0, 17.0*k, 180]}})
+    for k, (pos, rot) in enumerate([((0.93, 1.0, -0.3), (0, 0, 90)), ((-0.93, 0.7, 0.2), (0, 0, -90))]):
+        prims.append({"name": "m%d" % k, "type": "mesh", "file": name + "_lamp.wo3", "smooth": False, "bsdf": "lamp",
+                      "emission": [3.0 + 2*k, 4.0, 6.0 - 2*k],
+                      "transform": {"position": list(pos), "scale": [0.3, 0.3, 0.3], "rotation": list(rot)}})
+    sc = cornell_box(res, spp, max_bounces, extra_bsdfs=bsdfs, extra_prims=prims, boxes=False, light_emission=(8, 6, 2))
+    return write_scene(out_dir, name, sc, meshes)
+
+
 # ---- HDR environment maps ----------------------------------------------------------------------
 def save_rgbe(path, img):
     """Flat (non-RLE) Radiance .hdr writer; rows top-down ("-Y h +X w")."""
