@@ -359,12 +359,32 @@ B200PathTraceIntegrator::~B200PathTraceIntegrator()
 void B200PathTraceIntegrator::fromJson(JsonPtr value, const Scene &/*scene*/)
 {
     _settings.fromJson(value);
+    // "devices": [0, 1, ...] (or a single number N = devices 0..N-1): tgb_settings::devices, the in-library multi-GPU path
+    _devices.clear();
+    if (auto d = value["devices"]) {
+        if (d.isArray()) {
+            for (unsigned i = 0; i < d.size(); ++i)
+                _devices.push_back(d[i].cast<int>());
+        } else {
+            int n = d.cast<int>();
+            for (int i = 0; i < n; ++i)
+                _devices.push_back(i);
+        }
+        if (_devices.size() > 8)
+            value.parseError("b200_path_tracer: at most 8 devices");
+    }
 }
 
 rapidjson::Value B200PathTraceIntegrator::toJson(Allocator &allocator) const
 {
     rapidjson::Value v = _settings.toJson(allocator);
     v["type"].SetString("b200_path_tracer");
+    if (!_devices.empty()) {
+        rapidjson::Value a(rapidjson::kArrayType);
+        for (int d : _devices)
+            a.PushBack(d, allocator);
+        v.AddMember("devices", a, allocator);
+    }
     return v;
 }
 
@@ -471,6 +491,11 @@ void B200PathTraceIntegrator::prepareForRender(TraceableScene &scene, uint32 see
     desc.settings.use_sobol = 1;
     desc.settings.supplemental_mode = 0;
     desc.settings.device = -1;
+    if (_devices.size() == 1)
+        desc.settings.device = _devices[0];
+    desc.settings.n_devices = uint32_t(_devices.size());
+    for (size_t i = 0; i < _devices.size(); ++i)
+        desc.settings.devices[i] = _devices[i];
     desc.primitives = f.prims.data(); desc.n_primitives = uint32_t(f.prims.size());
     desc.bsdfs = f.bsdfs.data(); desc.n_bsdfs = uint32_t(f.bsdfs.size());
     desc.bsdf_slots = f.slots.data(); desc.n_bsdf_slots = uint32_t(f.slots.size());

@@ -34,6 +34,7 @@ class B200PathTraceIntegrator : public Integrator
     UniformSampler _sampler;
     std::vector<tgb_sample_record> _samples;
     bool _needsFramebufferPush;      // after loadState(): the camera's colour buffer has to go to the device first
+    std::vector<int> _devices;       // "devices": [0, 1, ...] in the integrator's JSON block: GPUs to spread the tiles over (empty = the current one)
 
     void uploadFramebuffer();
     void pushFramebuffer();

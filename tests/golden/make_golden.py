@@ -566,6 +566,8 @@ def make_scenes(only=None):
                                                 taper=True, subsample=0.3)
     # 39 samplable lights (36 quads + the ceiling light + 2 mesh lights): chooseLight beyond 16 lights
     scenes["many_lights"] = synth.many_lights(os.path.join(HERE, "many_lights"), "scene", res=res, spp=spp, subdiv=2)
+    # 151 analytic primitives, no mesh: from 24 on the library keeps them in BVH leaves instead of its per-ray loop
+    scenes["cube_city"] = synth.cube_city(os.path.join(HERE, "cube_city"), "scene", n=12, res=res, spp=spp)
     scenes["dirac"] = synth.dirac_room(os.path.join(HERE, "dirac"), "scene", res=res, spp=spp, subdiv=2)
     # the two emitters of the shipped hair scene: infinite_sphere_cap (sampled sun) + skydome (unsampled sky); min_bounces 1 as shipped
     scenes["hair_sky"] = synth.hair_scene(os.path.join(HERE, "hair_sky"), "scene", n_curves=300, res=res, spp=spp, shipped_lights=True, min_bounces=1)

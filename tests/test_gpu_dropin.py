@@ -104,3 +104,22 @@ def test_dropin_writes_resume_state(tmp_path):
     assert np.array_equal(mean, st["mean"])
     assert bytes(recs) == st["records"]
     assert sampler_state == st["sampler_state"]
+
+
+@pytest.mark.skipif(not os.path.exists(EXE), reason="drop-in binary not built (needs /root/reference at build time)")
+def test_dropin_on_two_gpus_equals_one_gpu(tmp_path):
+    """"devices": [0, 1] in the integrator block -> tgb_settings::devices: the library replicates the scene, deals the tiles
+    in Morton order, gathers the shares on devices[0] over NVLink.  Under the per-path reseed contract the image does not
+    depend on who rendered which tile: bit for bit the one-GPU image."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    js = json.load(open(os.path.join(G, "materials", "scene.json")))
+    for f in os.listdir(os.path.join(G, "materials")):
+        if not f.endswith(".pfm") and f != "scene.json":
+            os.symlink(os.path.join(G, "materials", f), tmp_path/f)
+    js["integrator"]["type"] = "b200_path_tracer"
+    one, _ = _run_dropin(tmp_path, js, name="one.json")
+    js["integrator"]["devices"] = [0, 1]
+    two, _ = _run_dropin(tmp_path, js, name="two.json")
+    assert np.array_equal(one, two)

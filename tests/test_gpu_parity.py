@@ -85,6 +85,7 @@ def test_golden_scenes_against_reference_fixtures():
     for name, exact_min, close_min in [("cornell", 0.5, 0.985), ("cornell_short", 0.5, 0.985), ("cornell_mesh", 0.5, 0.985),
                                        ("materials", 0.5, 0.985), ("materials_env", 0.5, 0.985), ("coat_env", 0.3, 0.985), ("dirac", 0.5, 0.985),
                                        ("many_lights", 0.5, 0.985),      # 39 samplable lights: chooseLight's > 16 lights path
+                                       ("cube_city", 0.5, 0.985),        # 151 analytic primitives: kept in BVH leaves
                                        ("hair", 0.3, 0.97), ("hair_dark", 0.3, 0.97), ("hair_sky", 0.3, 0.97), ("curves_lambert", 0.5, 0.97),
                                        ("curves_plastic", 0.5, 0.97)]:
         fs = scene.load_scene(os.path.join(g, name, "scene.json"))
@@ -177,6 +178,41 @@ def test_trace_closest_hit_ids(scratch):
     assert bad.sum() == 0
     assert np.array_equal(ref["t"][same], got["t"][same])
     assert np.array_equal(ref["backside"][same], got["backside"][same])
+
+
+def test_many_analytic_primitives_live_in_the_bvh(scratch, monkeypatch):
+    """Quads and cubes are tested by a per-ray loop while they are few and become BVH leaves from 24 on (the reference keeps
+    them in Embree's top-level user-geometry BVH, TraceableScene.hpp:112-134).  (a) a 151-primitive scene against the oracle:
+    image and hit ids; (b) the BVH path forced on scenes that normally use the loop gives the loop's image (occlusion queries
+    skip the light they are aimed at in both)."""
+    fs = scene.load_scene(synth.cube_city(res=(96, 96), spp=8, n=12))
+    _compare(fs, 8, same_ray_count=False)
+    rng = np.random.RandomState(3)
+    n = 100000
+    o = np.tile(np.float32([7.5, 5.0, 9.0]), (n, 1)) + rng.randn(n, 3).astype(np.float32)*0.5
+    tgt = (rng.rand(n, 3).astype(np.float32) - 0.5)*np.float32([9, 2, 9])
+    d = tgt - o; d /= np.linalg.norm(d, axis=1, keepdims=True)
+    rays = np.concatenate([o, d.astype(np.float32), np.full((n, 1), 1e-4, np.float32), np.full((n, 1), np.inf, np.float32)], axis=1)
+    orc = pyoracle.Oracle(fs); ref = orc.trace(rays); orc.close()
+    ctx = lib.Context(fs); got = ctx.trace_closest(rays); info = ctx.scene_info(); ctx.close()
+    assert info["n_nodes"] > 0 and info["n_tris"] == 0                     # a BVH without a single triangle
+    same = (ref["primitive"] == got["primitive"])
+    with np.errstate(invalid="ignore"):
+        tie = np.abs(ref["t"] - got["t"]) <= 4*np.spacing(np.abs(ref["t"]).astype(np.float32))
+    print("analytic hits equal %.6f of %d (%d hit), ties %d" % (same.mean(), n, int((ref["primitive"] >= 0).sum()), int((~same & tie).sum())))
+    assert (~same & ~tie).sum() == 0
+    assert np.array_equal(ref["t"][same], got["t"][same]) and np.array_equal(ref["backside"][same], got["backside"][same])
+    for make in (lambda: synth.cornell_box(res=(64, 64), spp=8), lambda: synth.cornell_mesh(scratch, res=(64, 64), spp=8, subdiv=3),
+                 lambda: synth.material_room(scratch, name="mat_abvh", res=(64, 64), spp=8, subdiv=2)):
+        fs2 = scene.load_scene(make())
+        monkeypatch.delenv("TGB_ANALYTIC_BVH_MIN", raising=False)
+        ctx = lib.Context(fs2); loop_img, _ = ctx.render_tiles(8); ctx.close()
+        monkeypatch.setenv("TGB_ANALYTIC_BVH_MIN", "1")
+        ctx = lib.Context(fs2); bvh_img, _ = ctx.render_tiles(8); ctx.close()
+        monkeypatch.delenv("TGB_ANALYTIC_BVH_MIN", raising=False)
+        eq = float((np.abs(loop_img - bvh_img).max(axis=2) == 0).mean())
+        print("loop vs BVH leaves: %.5f of pixels identical" % eq)
+        assert eq >= 0.999
 
 
 # ---- edge cases the reference's path handles (SURVEY 8a/8c): settings, ragged images, degenerate inputs ----------

@@ -30,7 +30,7 @@ def _render(name, mode):
     return img
 
 
-@pytest.mark.parametrize("name", ["cornell", "cornell_short"])
+@pytest.mark.parametrize("name", ["cornell", "cornell_short", "cube_city"])
 @pytest.mark.parametrize("mode,ref", [(0, "ref_pathseed.pfm"), (1, "ref_stock.pfm")])
 def test_analytic_scenes_bit_exact(name, mode, ref):
     img = _render(name, mode)

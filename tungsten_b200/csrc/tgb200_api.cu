@@ -459,7 +459,6 @@ int upload_scene(tgb_ctx *c, const tgb_scene_desc *d) {
         lights.push_back(int(prims.size())); inf_lights.push_back(int(prims.size()));
         prims.push_back(o);
     }
-    if (analytic.size() > 4096) return fail(c, TGB_ERR_UNSUPPORTED, "more than 4096 analytic primitives");
     for (int li : lights) {
         DPrim &l = prims[li];
         if (l.type == TGB_PRIM_INFINITE_SPHERE_CAP && tex[l.emission_tex].d.type == TGB_TEX_BITMAP)
@@ -493,52 +492,94 @@ int upload_scene(tgb_ctx *c, const tgb_scene_desc *d) {
         build_bvh4(btris.data(), uint32_t(btris.size()), bvh, 0, 1e-6f*extent, tri_leaf, tri_cost);
     }
     const uint32_t n_tris_total = uint32_t(btris.size()), n_segs_total = uint32_t(cboxes.size());
+    // Leaf positions: [0, n_tris) triangles, [n_tris, n_tris + n_segs) curve segments, one all-zero record (the target of empty
+    // child slots), then -- only when they are many -- the analytic primitives.  Leaves of the last two kinds carry bit 2.
+    // Analytic quads/cubes are few in most scenes and are then tested coherently by the kernel that creates a ray; from
+    // TGB_ANALYTIC_BVH_MIN (24) primitives on they get a third SAH tree instead (the reference keeps them in Embree's top-level
+    // user-geometry BVH, renderer/TraceableScene.hpp:112-134), so a ray's cost no longer grows with their number.
+    size_t analytic_bvh_min = 24;
+    if (const char *e = getenv("TGB_ANALYTIC_BVH_MIN")) analytic_bvh_min = size_t(std::max(1, atoi(e)));
+    const bool analytic_in_bvh = analytic.size() >= analytic_bvh_min;
+    const uint32_t analytic_base = n_tris_total + n_segs_total + 1;
+    Bvh4 cb, ab;
     if (n_segs_total) {
-        // Curve segments get their own SAH tree (leaf bit 2 = "curve leaf", records stored behind the triangles); with
-        // triangles present the two trees hang under a new root, so one traversal answers TraceableScene::intersect.
-        Bvh4 cb;
         // a segment test (3 projections + up to 32 half-cylinder pieces) costs far more than a triangle test: small leaves
         // (the reference's BinaryBvh also keeps <= 2 segments per leaf, Curves.cpp:613)
         uint32_t curve_leaf = 2; float curve_cost = 4.0f;
         if (const char *e = getenv("TGB_CURVE_LEAF")) curve_leaf = uint32_t(atoi(e));
         if (const char *e = getenv("TGB_CURVE_COST")) curve_cost = float(atof(e));
         build_bvh4_boxes(cboxes.data(), n_segs_total, cb, 0, 1e-6f*extent, curve_leaf, curve_cost);
-        const bool both = !bvh.nodes.empty();
-        const int32_t tri_base = both ? 1 : 0, curve_base = tri_base + int32_t(bvh.nodes.size());
-        std::vector<Node4> merged(size_t(curve_base) + cb.nodes.size());
-        for (size_t k = 0; k < bvh.nodes.size(); ++k) {
-            Node4 nd = bvh.nodes[k];
-            for (int j = 0; j < 4; ++j) if (nd.link[j] >= 0) nd.link[j] += tri_base;
-            merged[size_t(tri_base) + k] = nd;
-        }
-        for (size_t k = 0; k < cb.nodes.size(); ++k) {
-            Node4 nd = cb.nodes[k];
-            for (int j = 0; j < 4; ++j) {
-                if (nd.link[j] >= 0) nd.link[j] += curve_base;
-                else if (nd.link[j] != kEmptyLink) { int32_t code = ~nd.link[j]; nd.link[j] = ~int32_t((((code >> 3) + int32_t(n_tris_total)) << 3) | 4 | (code & 3)); }
+    }
+    if (analytic_in_bvh) {
+        std::vector<BuildBox> aboxes(analytic.size());
+        for (size_t k = 0; k < analytic.size(); ++k) {
+            const DPrim &p = prims[size_t(analytic[k])];
+            float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+            auto grow = [&](V3 q) { float v[3] = {q.x, q.y, q.z}; for (int a = 0; a < 3; ++a) { lo[a] = std::min(lo[a], v[a]); hi[a] = std::max(hi[a], v[a]); } };
+            if (p.type == TGB_PRIM_QUAD) { grow(p.base); grow(p.base + p.edge0); grow(p.base + p.edge1); grow(p.base + p.edge0 + p.edge1); }
+            else for (int j = 0; j < 8; ++j) grow(p.pos + m3mul(p.rot, v3((j & 1 ? p.scale.x : -p.scale.x), (j & 2 ? p.scale.y : -p.scale.y), (j & 4 ? p.scale.z : -p.scale.z))));
+            // the primitives' own tests work on a point o + d*t computed in fp32: pad by the rounding of that point as well
+            for (int a = 0; a < 3; ++a) {
+                const float pad = 4e-6f*std::max(std::fabs(lo[a]), std::fabs(hi[a]));
+                aboxes[k].lo[a] = lo[a] - pad; aboxes[k].hi[a] = hi[a] + pad; aboxes[k].centroid[a] = 0.5f*(lo[a] + hi[a]);
+                extent = std::max(extent, std::max(std::fabs(lo[a]), std::fabs(hi[a])));
             }
-            merged[size_t(curve_base) + k] = nd;
         }
-        if (both) {
+        build_bvh4_boxes(aboxes.data(), uint32_t(aboxes.size()), ab, 0, 2e-6f*extent, 2, 2.0f);
+    }
+    {
+        // the trees that exist hang under one new root (a single tree keeps its own root), so ONE traversal answers
+        // TraceableScene::intersect
+        struct Sub { Bvh4 *b; uint32_t pos_base; bool flag; };
+        std::vector<Sub> subs;
+        if (!bvh.nodes.empty()) subs.push_back({&bvh, 0u, false});
+        if (!cb.nodes.empty()) subs.push_back({&cb, n_tris_total, true});
+        if (!ab.nodes.empty()) subs.push_back({&ab, analytic_base, true});
+        const bool rooted = subs.size() > 1;
+        if (rooted || (subs.size() == 1 && subs[0].b != &bvh)) {
+            size_t total = rooted ? 1 : 0;
+            for (const Sub &sb : subs) total += sb.b->nodes.size();
+            std::vector<Node4> merged(total);
             Node4 root; std::memset(&root, 0, sizeof(root));
             for (int j = 0; j < 4; ++j) root.link[j] = kEmptyLink;
-            for (int a = 0; a < 3; ++a) {
-                root.f[8*a] = bvh.lo[a]; root.f[8*a + 4] = bvh.hi[a];
-                root.f[8*a + 1] = cb.lo[a]; root.f[8*a + 5] = cb.hi[a];
+            float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+            uint32_t depth = 0; double sah = 0.0;
+            int32_t base = rooted ? 1 : 0;
+            for (size_t t = 0; t < subs.size(); ++t) {
+                const Sub &sb = subs[t];
+                for (size_t k = 0; k < sb.b->nodes.size(); ++k) {
+                    Node4 nd = sb.b->nodes[k];
+                    for (int j = 0; j < 4; ++j) {
+                        if (nd.link[j] >= 0) nd.link[j] += base;
+                        else if (nd.link[j] != kEmptyLink) { const int32_t code = ~nd.link[j]; nd.link[j] = ~int32_t((((code >> 3) + int32_t(sb.pos_base)) << 3) | (sb.flag ? 4 : 0) | (code & 3)); }
+                    }
+                    merged[size_t(base) + k] = nd;
+                }
+                for (int a = 0; a < 3; ++a) {
+                    root.f[8*a + t] = sb.b->lo[a]; root.f[8*a + 4 + t] = sb.b->hi[a];
+                    lo[a] = std::min(lo[a], sb.b->lo[a]); hi[a] = std::max(hi[a], sb.b->hi[a]);
+                }
+                root.link[t] = base;
+                depth = std::max(depth, sb.b->max_depth); sah += sb.b->sah_cost;
+                base += int32_t(sb.b->nodes.size());
             }
-            root.link[0] = tri_base; root.link[1] = curve_base;
-            merged[0] = root;
-            bvh.max_depth = std::max(bvh.max_depth, cb.max_depth) + 1;
-            for (int a = 0; a < 3; ++a) { bvh.lo[a] = std::min(bvh.lo[a], cb.lo[a]); bvh.hi[a] = std::max(bvh.hi[a], cb.hi[a]); }
-        } else {
-            bvh.max_depth = cb.max_depth;
-            for (int a = 0; a < 3; ++a) { bvh.lo[a] = cb.lo[a]; bvh.hi[a] = cb.hi[a]; }
+            if (rooted) { merged[0] = root; depth += 1; }
+            std::vector<uint32_t> order = bvh.order;
+            for (uint32_t k : cb.order) order.push_back(n_tris_total + k);
+            bvh.nodes.swap(merged); bvh.order.swap(order);
+            bvh.max_depth = depth; bvh.sah_cost = sah;
+            for (int a = 0; a < 3; ++a) { bvh.lo[a] = lo[a]; bvh.hi[a] = hi[a]; }
         }
-        bvh.nodes.swap(merged);
-        for (uint32_t k : cb.order) bvh.order.push_back(n_tris_total + k);
-        bvh.sah_cost += cb.sah_cost;
-        for (uint32_t pi : cseg_prim) tri_prim.push_back(pi);
-        for (DPrim &p : prims) if (p.type == TGB_PRIM_CURVES) p.tri_first += n_tris_total;
+        if (n_segs_total) {
+            for (uint32_t pi : cseg_prim) tri_prim.push_back(pi);
+            for (DPrim &p : prims) if (p.type == TGB_PRIM_CURVES) p.tri_first += n_tris_total;
+        }
+    }
+    std::vector<int> analytic_loop = analytic;           // what the ray-creating kernels loop over
+    if (analytic_in_bvh) {                                // ... nothing: the list goes into BVH leaf order instead
+        std::vector<int> in_leaf_order(analytic.size());
+        for (size_t k = 0; k < ab.order.size(); ++k) in_leaf_order[k] = analytic[ab.order[k]];
+        analytic_loop.swap(in_leaf_order);
     }
     {   // ray-binning grid: bounds of every finite primitive (TraceableScene::_sceneBounds, TraceableScene.hpp:104-110)
         float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
@@ -626,7 +667,7 @@ int upload_scene(tgb_ctx *c, const tgb_scene_desc *d) {
     if ((rc = dev_upload(c, &sc.tex, dtex))) return rc;
     if ((rc = dev_upload(c, &sc.lights, lights))) return rc;
     if ((rc = dev_upload(c, &sc.inf_lights, inf_lights))) return rc;
-    if ((rc = dev_upload(c, &sc.analytic, analytic))) return rc;
+    if ((rc = dev_upload(c, &sc.analytic, analytic_loop))) return rc;
     if ((rc = dev_upload(c, &sc.tri_global, bvh.order))) return rc;
     if ((rc = dev_upload(c, &sc.tri_prim, tri_prim))) return rc;
     {   // shading records follow the intersection records into BVH leaf order (one hop from a hit id)
@@ -676,7 +717,8 @@ int upload_scene(tgb_ctx *c, const tgb_scene_desc *d) {
     std::memcpy(sobol.data(), tgb_sobol_blob, sobol.size()*4);
     if ((rc = dev_upload(c, &sc.sobol, sobol))) return rc;
     sc.n_prims = uint32_t(prims.size()); sc.n_lights = int(lights.size()); sc.n_inf_lights = int(inf_lights.size());
-    sc.n_analytic = int(analytic.size()); sc.n_nodes = uint32_t(bvh.nodes.size()); sc.n_tris = uint32_t(btris.size());
+    sc.n_analytic = analytic_in_bvh ? 0 : int(analytic.size()); sc.analytic_base = analytic_in_bvh ? int(analytic_base) : 0x7fffffff;
+    sc.n_nodes = uint32_t(bvh.nodes.size()); sc.n_tris = uint32_t(btris.size());
     sc.n_curve_segs = uint32_t(cboxes.size()); c->has_curves = !cboxes.empty();
     {
         uint32_t types = 0;

@@ -120,7 +120,8 @@ struct DScene {
     const DPrim *prims; uint32_t n_prims;
     const DBsdf *bsdfs; const uint32_t *slots; const DTex *tex;
     const int *lights; int n_lights; const int *inf_lights; int n_inf_lights;
-    const int *analytic; int n_analytic;
+    const int *analytic; int n_analytic;    // quads/cubes: the list the ray-creating kernels loop over (n_analytic = 0 when they are BVH leaves)
+    int analytic_base;                      // first leaf position of the analytic primitives when they are in the BVH, else INT_MAX
     // triangles: intersection records in BVH leaf order (3 x float4 each), leaf order -> global id,
     // global id -> primitive, shading records ALSO in leaf order (4 x float4 each: 3 normals, 3 uvs, material | primitive << 10)
     const float4 *tri_isect; const uint32_t *tri_global; const uint32_t *tri_prim; const float4 *tri_shade;

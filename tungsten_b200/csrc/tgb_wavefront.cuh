@@ -349,6 +349,7 @@ struct Traversal {
     V3 o, d; float tnear; bool any; Hit h;
     float idx, idy, idz, oodx, oody, oodz; int nx, ny, nz, fx, fy, fz;
     CurveFrame cf; int last_seg; int cur;
+    int ignore;         // analytic primitive an occlusion query must not count (the light it is aimed at), -1 = none
     // (the stack is a separate object: its dynamically indexed spill array would drag this whole struct into local memory)
 
     TGB_D void begin(V3 o_, V3 d_, float tnear_, bool any_, const Hit &h_) {
@@ -362,7 +363,7 @@ struct Traversal {
         // monotone, so this IS min(a, b) / max(a, b) of the two plane distances): pick which to read per axis once per ray.
         nx = idx < 0.0f ? 1 : 0; ny = idy < 0.0f ? 3 : 2; nz = idz < 0.0f ? 5 : 4;
         fx = nx ^ 1; fy = ny ^ 1; fz = nz ^ 1;
-        last_seg = -1;
+        last_seg = -1; ignore = -1;
         if (CURVES) cf = curve_frame(d);
         cur = 0;
     }
@@ -433,6 +434,21 @@ struct Traversal {
         return true;
     }
 
+    // leaf of analytic primitives (scenes with many quads / cubes keep them in the BVH): Quad::intersect / Cube::intersect on the
+    // primitives at leaf positions first .. first + count; true when an occlusion query is done
+    TGB_D bool analytic_leaf(const DScene &sc, int first, int count) {
+        for (int i = 0; i < count; ++i) {
+            const int pi = __ldg(sc.analytic + (first - sc.analytic_base) + i);
+            if (pi == ignore) continue;
+            const DPrim &p = sc.prims[pi];
+            const int before = h.id;
+            if (p.type == TGB_PRIM_QUAD) quad_intersect(p, pi, o, d, tnear, h);
+            else cube_intersect(p, pi, o, d, tnear, h);
+            if (any && h.id != before) return true;
+        }
+        return false;
+    }
+
     template <class Y>
     TGB_D bool run(const DScene &sc, const uint4 *treelet, TravStack &stk, int &sp, Y yield) {
         while (true) {
@@ -465,6 +481,9 @@ struct Traversal {
         }
         int code = ~cur;
         int first = code >> 3, count = (code & 3) + 1;
+        if ((code & 4) && (!CURVES || first >= sc.analytic_base)) {
+            if (analytic_leaf(sc, first, count)) return true;
+        } else
         if (CURVES && (code & 4)) {
             for (int i = 0; i < count; ++i) {
                 int seg = int(__ldg(sc.tri_global + first + i) - sc.n_tris)/kCurvePieces;     // global id of a curve record: n_tris + 4*segment + quarter
@@ -532,7 +551,7 @@ TGB_D void bvh_traverse_persistent(const DScene &sc, const uint4 *treelet, int *
             if (!active) {
                 uint32_t i = base + unsigned(__popc(need & ((1u << lane) - 1u)));
                 V3 o, d; float tnear; Hit h; bool any;
-                if (i < n && pol.fetch(i, o, d, tnear, h, any)) { tr.begin(o, d, tnear, any, h); sp = 0; active = true; }
+                if (i < n && pol.fetch(i, o, d, tnear, h, any)) { tr.begin(o, d, tnear, any, h); tr.ignore = pol.ignore(); sp = 0; active = true; }
             }
         }
         if (!__any_sync(FULL, active)) break;
@@ -555,8 +574,16 @@ TGB_D void bvh_traverse_persistent(const DScene &sc, const uint4 *treelet, int *
 // so a lane in a long bisection no longer stalls the others: they go on visiting nodes and starting their own segment tests in
 // the same trips.  A ray's arithmetic and the order of ITS node visits / segment tests are unchanged (parity unaffected);
 // idle lanes are refilled from the ray cursor as above.
+// idle lanes a warp tolerates before it pulls new rays (C4: 4 / 8 / 16 -> 35.8 / 35.7 / 33.9; C1: 4 / 8 / 12 / 16 -> 624 / 642 / 643 / 645 Msamples/s)
 #ifndef TGB_CURVE_REFILL_IDLE
 #define TGB_CURVE_REFILL_IDLE 8
+#endif
+// rays a warp takes from the queue cursor per atomicAdd
+#ifndef TGB_RAY_CHUNK
+#define TGB_RAY_CHUNK 64
+#endif
+#ifndef TGB_TRI_REFILL_IDLE
+#define TGB_TRI_REFILL_IDLE 16
 #endif
 #ifndef TGB_CM_WN            // scheduling weights of the four blocks (the block with the largest weight x lanes runs)
 #define TGB_CM_WN 4
@@ -577,6 +604,7 @@ TGB_D void machine_traverse_persistent(const DScene &sc, const uint4 *treelet, i
     constexpr int kW[4] = {TGB_CM_WN, TGB_CM_WL, TGB_CM_WB, TGB_CM_WC};
     Traversal<CURVES> tr; TravStack stk; stk.base = smem_addr(smem_stack + threadIdx.x); int sp = 0;
     int mode = CM_IDLE; bool exhausted = false;
+    uint32_t chunk_next = 0, chunk_end = 0;
     int li = 0, prim = 0; bool seg_hit = false;                                        // leaf cursor, BVH primitive under test
     float4 q0 = {}, q1 = {}, q2 = {}, c0 = {}, c1 = {};                                 // the segment's quadratic, the current piece's end points
     float tFlatX = 0.0f, tFlatY = 0.0f, xFlat = 0.0f, yFlat = 0.0f, pMin = 0.0f, pMax = 1.0f;
@@ -615,17 +643,22 @@ TGB_D void machine_traverse_persistent(const DScene &sc, const uint4 *treelet, i
     };
     for (;;) {
         const unsigned idle = __ballot_sync(FULL, mode == CM_IDLE);
-        if (!exhausted && __popc(idle) >= TGB_CURVE_REFILL_IDLE) {
-            const unsigned cnt = unsigned(__popc(idle)), leader = unsigned(__ffs(int(idle))) - 1u;
-            uint32_t base = 0;
-            if (lane == leader) base = atomicAdd(counter, cnt);
-            base = __shfl_sync(FULL, base, int(leader));
-            exhausted = base + cnt >= n;
-            if (mode == CM_IDLE) {
-                const uint32_t i = base + unsigned(__popc(idle & ((1u << lane) - 1u)));
-                V3 o, d; float tnear; Hit h; bool any;
-                if (i < n && pol.fetch(i, o, d, tnear, h, any)) { tr.begin(o, d, tnear, any, h); sp = 0; mode = CM_NODE; }
+        if (!exhausted && __popc(idle) >= (CURVES ? TGB_CURVE_REFILL_IDLE : TGB_TRI_REFILL_IDLE)) {
+            // the warp owns rays [chunk_next, chunk_end) of the queue: one atomicAdd per TGB_RAY_CHUNK rays instead of one per refill
+            if (chunk_next == chunk_end) {
+                uint32_t b = 0;
+                if (lane == 0) b = atomicAdd(counter, uint32_t(TGB_RAY_CHUNK));
+                b = __shfl_sync(FULL, b, 0);
+                if (b >= n) { exhausted = true; continue; }
+                chunk_next = b; chunk_end = min(b + uint32_t(TGB_RAY_CHUNK), n);
             }
+            const uint32_t rank = unsigned(__popc(idle & ((1u << lane) - 1u)));
+            const uint32_t cnt = min(uint32_t(__popc(idle)), chunk_end - chunk_next);
+            if (mode == CM_IDLE && rank < cnt) {
+                V3 o, d; float tnear; Hit h; bool any;
+                if (pol.fetch(chunk_next + rank, o, d, tnear, h, any)) { tr.begin(o, d, tnear, any, h); tr.ignore = pol.ignore(); sp = 0; mode = CM_NODE; }
+            }
+            chunk_next += cnt;
             continue;
         }
         if (idle == FULL) break;                                                        // (only reached once the cursor is exhausted)
@@ -696,7 +729,9 @@ TGB_D void machine_traverse_persistent(const DScene &sc, const uint4 *treelet, i
         } else {
             if (mode == CM_LEAF) {
                 const int code = ~tr.cur, first = code >> 3, count = (code & 3) + 1;
-                if (CURVES && (code & 4)) {
+                if ((code & 4) && (!CURVES || first >= sc.analytic_base)) {
+                    if (tr.analytic_leaf(sc, first, count)) finish_ray(); else pop_node();
+                } else if (CURVES && (code & 4)) {
                     bool started = false;
                     while (li < count) {
                         const int i = li++;
@@ -963,6 +998,7 @@ struct PathRayPolicy {
         return true;
     }
     TGB_D void finish(const Hit &h) { T2[s] = pack_hit(h); }
+    TGB_D int ignore() const { return -1; }
 };
 template <bool CURVES>
 __global__ void __launch_bounds__(kTraceBlock, CURVES ? TGB_MINB_CURVES : TGB_MINB) k_trace(DScene sc, PathBuf pb, const uint32_t *order, Ctl *ctl) {
@@ -986,6 +1022,7 @@ struct HookPolicy {
         return true;
     }
     TGB_D void finish(const Hit &h) { out[i] = h; }
+    TGB_D int ignore() const { return -1; }
 };
 __global__ void __launch_bounds__(256) k_hook_analytic(DScene sc, const tgb_ray *rays, Hit *out, uint32_t n) {
     uint32_t i = blockIdx.x*blockDim.x + threadIdx.x;
@@ -1009,6 +1046,7 @@ struct HookPersistPolicy {
         return true;
     }
     TGB_D void finish(const Hit &h) { out[i] = h; }
+    TGB_D int ignore() const { return -1; }
 };
 template <bool CURVES>
 __global__ void __launch_bounds__(kTraceBlock, CURVES ? TGB_MINB_CURVES : TGB_MINB) k_hook_persist(DScene sc, const tgb_ray *rays, Hit *out, uint32_t n, uint32_t *counter) {
@@ -1396,17 +1434,22 @@ __global__ void __launch_bounds__(256) k_shadow_prep(DScene sc, Scratch sr, cons
 template <bool CURVES>
 struct ShadowPolicy {
     DScene sc; Scratch sr; const uint32_t *squeue; unsigned long long *hits;
-    uint32_t s; bool mis, any; int li; V3 p, d;
+    uint32_t s; bool mis, any; int li, ign; V3 p, d;
     TGB_D bool fetch(uint32_t i, V3 &o, V3 &dd, float &tnear, Hit &h, bool &anyq) {
         uint32_t q = squeue[i];
         s = q >> 2; mis = q & 1u; any = q & 2u;
         const float4 P = sr.P[s], D = mis ? sr.M0[s] : sr.N0[s];
         p = v3(P.x, P.y, P.z); d = v3(D.x, D.y, D.z);
         o = p; dd = d; tnear = P.w; anyq = any; li = 0;
-        if (any) { h.t = D.w; h.u = 0.0f; h.v = 0.0f; h.id = HID_MISS; }
-        else { h = unpack_hit(sr.SH[i]); li = __float_as_int(sr.D1[s].w); }
+        if (any) {
+            h.t = D.w; h.u = 0.0f; h.v = 0.0f; h.id = HID_MISS;
+            // analytic primitives in the BVH: the query must not count the light it is aimed at (generalizedShadowRay's
+            // `hit == endCap`, TraceBase.cpp:79-83); with the usual per-ray loop k_shadow_prep has dealt with them already
+            ign = sc.n_analytic == 0 && sc.analytic_base != 0x7fffffff ? __float_as_int(sr.D1[s].w) : -1;
+        } else { h = unpack_hit(sr.SH[i]); li = __float_as_int(sr.D1[s].w); ign = -1; }
         return true;
     }
+    TGB_D int ignore() const { return ign; }
     TGB_D void finish(const Hit &h) {
         if (h.id != HID_MISS) atomicAdd(hits, 1ull);
         if (any) { if (h.id == HID_MISS) sr.vis[2*size_t(s) + (mis ? 1 : 0)] = 1u; }

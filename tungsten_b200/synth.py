@@ -251,6 +251,37 @@ def many_lights(out_dir, name="many_lights", n_quads=36, res=(128, 128), spp=16,
     return write_scene(out_dir, name, sc, meshes)
 
 
+def cube_city(out_dir=None, name="cube_city", n=12, res=(128, 128), spp=16, max_bounces=8, seed=7, n_lights=6):
+    """A floor, n x n rotated cubes of random height and colour and a few quad lights: hundreds of ANALYTIC primitives and no
+    mesh at all.  The reference keeps such primitives in Embree's top-level user-geometry BVH (TraceableScene.hpp:112-134);
+    the library moves them from its per-ray loop into BVH leaves from 24 primitives on."""
+    rng = np.random.RandomState(seed)
+    bsdfs = [_lambert("floor", [0.5, 0.5, 0.5]), {"name": "lamp", "type": "null", "albedo": 1.0}]
+    prims = [{"name": "floor", "type": "quad", "bsdf": "floor", "transform": {"position": [0, 0, 0], "scale": [12, 1, 12]}}]
+    for k in range(n*n):
+        i, j = k % n, k//n
+        col = [float(c) for c in 0.2 + 0.7*rng.rand(3)]
+        bsdfs.append(_lambert("c%d" % k, col))
+        h = float(0.2 + 1.3*rng.rand())
+        x, z = -4.5 + 9.0*(i + 0.5)/n, -4.5 + 9.0*(j + 0.5)/n
+        prims.append({"name": "c%d" % k, "type": "cube", "bsdf": "c%d" % k,
+                      "transform": {"position": [x, 0.5*h, z], "scale": [0.55*9.0/n, h, 0.55*9.0/n], "rotation": [0, float(90*rng.rand()), 0]}})
+    for k in range(n_lights):
+        ang = 2*np.pi*k/n_lights
+        prims.append({"name": "l%d" % k, "type": "quad", "bsdf": "lamp", "emission": [20.0 + 5*k, 18.0, 25.0 - 3*k],
+                      "transform": {"position": [float(3.5*np.cos(ang)), 3.2 + 0.1*k, float(3.5*np.sin(ang))], "scale": [0.8, 1, 0.6],
+                                    "rotation": [0, float(30*k), 180]}})
+    sc = {"media": [], "bsdfs": bsdfs, "primitives": prims,
+          "camera": {"tonemap": "filmic", "resolution": list(res), "reconstruction_filter": "tent",
+                     "transform": {"position": [7.5, 5.0, 9.0], "look_at": [0, 0.6, 0], "up": [0, 1, 0]}, "type": "pinhole", "fov": 40},
+          "integrator": {"type": "path_tracer", "min_bounces": 0, "max_bounces": max_bounces, "enable_consistency_checks": False,
+                         "enable_two_sided_shading": True, "enable_light_sampling": True},
+          "renderer": _renderer(spp)}
+    if out_dir is None:
+        return sc
+    return write_scene(out_dir, name, sc)
+
+
 # ---- HDR environment maps ----------------------------------------------------------------------
 def save_rgbe(path, img):
     """Flat (non-RLE) Radiance .hdr writer; rows top-down ("-Y h +X w")."""
