@@ -375,3 +375,18 @@ def test_resume_state_round_trip(adaptive):
     assert np.array_equal(resumed_cnt, whole_cnt) and np.array_equal(resumed, whole)
     if adaptive:
         assert whole_cnt.max() > 48
+
+
+def test_settings_the_library_refuses_rather_than_renders_differently():
+    """max_bounces 0 (the reference's loop never runs: black samples) and the hair BCSDF on a primitive that is not `curves`
+    (it needs the curve's tangent space) are refused loudly."""
+    from tungsten_b200 import abi
+    sc = synth.cornell_box(res=(16, 16), spp=1, max_bounces=0)
+    with pytest.raises(lib.TgbError) as e:
+        lib.Context(scene.load_scene(sc))
+    assert e.value.code == abi.TGB_ERR_UNSUPPORTED
+    sc = synth.cornell_box(res=(16, 16), spp=1)
+    sc["bsdfs"].append({"name": "fur", "type": "hair", "roughness": 0.3})
+    sc["primitives"][0]["bsdf"] = "fur"
+    with pytest.raises((lib.TgbError, scene.SceneError)) as e:
+        lib.Context(scene.load_scene(sc))

@@ -333,6 +333,16 @@ int upload_scene(tgb_ctx *c, const tgb_scene_desc *d) {
         if (p.type != TGB_PRIM_INFINITE_SPHERE && p.type != TGB_PRIM_INFINITE_SPHERE_CAP && p.type != TGB_PRIM_SKYDOME) {
             if (p.bsdf_count == 0 || p.bsdf_first + p.bsdf_count > d->n_bsdf_slots) return fail(c, TGB_ERR_INVALID, "primitive %u: bad bsdf range", i);
             for (uint32_t k = 0; k < p.bsdf_count; ++k) if (d->bsdf_slots[p.bsdf_first + k] >= d->n_bsdfs) return fail(c, TGB_ERR_INVALID, "primitive %u: bad bsdf index", i);
+            // the hair BCSDF is evaluated in the curve's tangent space (Curves::tangentSpace): on any other primitive the kernels
+            // compiled for curve-free scenes would not know the lobe at all
+            if (p.type != TGB_PRIM_CURVES)
+                for (uint32_t k = 0; k < p.bsdf_count; ++k) {
+                    const tgb_bsdf *b = &d->bsdfs[d->bsdf_slots[p.bsdf_first + k]];
+                    for (int hop = 0; hop < 4 && b; ++hop) {
+                        if (b->type == TGB_BSDF_HAIR) return fail(c, TGB_ERR_UNSUPPORTED, "primitive %u: the hair BCSDF on a primitive that is not `curves` is outside the hot path", i);
+                        b = (b->type == TGB_BSDF_SMOOTH_COAT && b->substrate >= 0 && uint32_t(b->substrate) < d->n_bsdfs) ? &d->bsdfs[b->substrate] : nullptr;
+                    }
+                }
         }
         switch (p.type) {
         case TGB_PRIM_MESH: {
@@ -879,7 +889,7 @@ int render_device(tgb_ctx *c, uint32_t spp_begin, uint32_t spp_count, bool adapt
     if (c->n_pix == 0 || (!adaptive && spp_count == 0) || (adaptive && adaptive_total == 0)) return TGB_OK;
     CU(cudaEventRecord(c->ev0, c->stream));
     uint64_t launches = 0;
-    float trace_ms = 0.0f, shadow_ms = 0.0f; uint64_t trace_launches = 0, traversed = 0, shadow_traversed = 0;
+    float trace_ms = 0.0f, shadow_ms = 0.0f; uint64_t trace_launches = 0, shadow_launches = 0, traversed = 0, shadow_traversed = 0;
     double kms[7] = {0, 0, 0, 0, 0, 0, 0}; uint64_t iterations = 0;
     // a step's finished radiances are kept per path (16 B each) until k_resolve folds them in sample order;
     // split the sample range so that this buffer stays below 8 GB and (sample within the call, pixel) fits 32 bits
@@ -922,7 +932,7 @@ int render_device(tgb_ctx *c, uint32_t spp_begin, uint32_t spp_count, bool adapt
             const Ctl S = c->h_ctl[p];                        // state after iteration iter-1 = the sizes of iteration iter
             if (c->profiling) {
                 for (int k = 0; k < 7; ++k) { float ms = 0.0f; cudaEventElapsedTime(&ms, c->ev_k[p][k], c->ev_k[p][k + 1]); kms[k] += ms; }
-                trace_launches++;
+                trace_launches++; shadow_launches++;           // one k_trace and one k_shadow_bvh per timed iteration
             }
             if (trace_bounces) fprintf(stderr, "after iter %u: next n %u (survivors %u, new %u, to traverse %u) issued %u/%u\n", iter - 1, S.n, S.n_surv, S.n_new, S.n_sorted, S.issued, S.total);
             if (S.n == 0) { traversed += S.traversed; shadow_traversed += S.shadow_traversed; iterations += S.iterations; break; }   // iteration `iter`, already queued, is empty
@@ -943,7 +953,7 @@ int render_device(tgb_ctx *c, uint32_t spp_begin, uint32_t spp_count, bool adapt
     trace_ms = float(kms[1]); shadow_ms = float(kms[4]);
     c->stats.regen_ms += kms[0]; c->stats.shade_ms += kms[2]; c->stats.prep_ms += kms[3]; c->stats.accum_ms += kms[5]; c->stats.sort_ms += kms[6];
     c->stats.iterations += iterations;
-    c->stats.shadow_ms += shadow_ms; c->stats.shadow_launches += trace_launches;
+    c->stats.shadow_ms += shadow_ms; c->stats.shadow_launches += shadow_launches;
     c->stats.kernel_launches += launches;
     c->stats.path_rays_traversed += traversed; c->stats.shadow_rays_traversed += shadow_traversed;
     c->stats.total_ms += ms; c->stats.trace_ms += trace_ms; c->stats.trace_launches += trace_launches;
@@ -1162,7 +1172,9 @@ static int create_single(const tgb_scene_desc *d, tgb_ctx **out) {
     if (!d->settings.use_sobol) return fail(nullptr, TGB_ERR_UNSUPPORTED, "only the Sobol sampler (renderer.stratified_sampler = true) is on the hot path");
     if (d->settings.supplemental_mode != 0) return fail(nullptr, TGB_ERR_UNSUPPORTED, "supplemental_mode %u: the per-tile serial PCG stream cannot be reproduced by a wavefront renderer (DESIGN.md section 3)", d->settings.supplemental_mode);
     if (d->camera.res_x == 0 || d->camera.res_y == 0) return fail(nullptr, TGB_ERR_INVALID, "empty image");
-    if (d->settings.max_bounces > 255 || d->settings.max_bounces < 0) return fail(nullptr, TGB_ERR_UNSUPPORTED, "max_bounces must be in [0, 255]");
+    // max_bounces 0: PathTracer::traceSample's loop never runs and every sample is black; the wavefront's first shade would add
+    // bounce-0 emission, so the setting is refused rather than rendered differently
+    if (d->settings.max_bounces > 255 || d->settings.max_bounces < 1) return fail(nullptr, TGB_ERR_UNSUPPORTED, "max_bounces must be in [1, 255]");
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { cudaGetLastError(); return fail(nullptr, TGB_ERR_NO_DEVICE, "no CUDA device available (this library has no CPU fallback)"); }
     int dev = d->settings.device;

@@ -418,7 +418,9 @@ struct Traversal {
     // Moeller-Trumbore on leaf-order record k; true (and h updated) when it is hit closer than h.t
     TGB_D bool triangle(const DScene &sc, int k) {
         const float4 *tr = sc.tri_isect + 3*size_t(k);
-        const float4 a = __ldg(tr), b = __ldg(tr + 1), c = __ldg(tr + 2);
+        return triangle_rec(__ldg(tr), __ldg(tr + 1), __ldg(tr + 2), k);
+    }
+    TGB_D bool triangle_rec(const float4 a, const float4 b, const float4 c, int k) {
         V3 v0 = v3(a.x, a.y, a.z), e1 = v3(a.w, b.x, b.y), e2 = v3(b.z, b.w, c.x), ng = v3(c.y, c.z, c.w);
         V3 C = v0 - o;
         V3 R = cross(d, C);
@@ -578,9 +580,15 @@ TGB_D void bvh_traverse_persistent(const DScene &sc, const uint4 *treelet, int *
 #ifndef TGB_CURVE_REFILL_IDLE
 #define TGB_CURVE_REFILL_IDLE 8
 #endif
-// rays a warp takes from the queue cursor per atomicAdd
+// rays a warp reserves from the queue cursor per atomicAdd; 0 = exactly the idle lanes of each refill.  Reserving ahead saves
+// atomics but leaves the reserved rays waiting for ONE warp at the end of a launch (C1, refill at 16: 0 / 32 / 64 / 128 ->
+// 645 / 639 / 631 / 600 Msamples/s)
 #ifndef TGB_RAY_CHUNK
-#define TGB_RAY_CHUNK 64
+#define TGB_RAY_CHUNK 0
+#endif
+// 1 = the machine tests ONE triangle per LEAF trip and loads the next triangle's record a trip ahead (12 more registers)
+#ifndef TGB_TRI_PREFETCH
+#define TGB_TRI_PREFETCH 0
 #endif
 #ifndef TGB_TRI_REFILL_IDLE
 #define TGB_TRI_REFILL_IDLE 16
@@ -604,15 +612,25 @@ TGB_D void machine_traverse_persistent(const DScene &sc, const uint4 *treelet, i
     constexpr int kW[4] = {TGB_CM_WN, TGB_CM_WL, TGB_CM_WB, TGB_CM_WC};
     Traversal<CURVES> tr; TravStack stk; stk.base = smem_addr(smem_stack + threadIdx.x); int sp = 0;
     int mode = CM_IDLE; bool exhausted = false;
-    uint32_t chunk_next = 0, chunk_end = 0;
+    uint32_t chunk_next = 0, chunk_end = 0; (void)chunk_next; (void)chunk_end;
     int li = 0, prim = 0; bool seg_hit = false;                                        // leaf cursor, BVH primitive under test
     float4 q0 = {}, q1 = {}, q2 = {}, c0 = {}, c1 = {};                                 // the segment's quadratic, the current piece's end points
     float tFlatX = 0.0f, tFlatY = 0.0f, xFlat = 0.0f, yFlat = 0.0f, pMin = 0.0f, pMax = 1.0f;
     uint32_t bidx = 0, pending = 0; int depth = 0;                                      // piece = [bidx, bidx + 1]/2^depth; pending siblings by depth
     auto finish_ray = [&]() { pol.finish(tr.h); mode = CM_IDLE; };
+#if TGB_TRI_PREFETCH
+    float4 ra = {}, rb = {}, rc = {};                                                   // the triangle record the next LEAF trip tests
+    auto prefetch_tri = [&](int link, int i) {
+        const int code = ~link;
+        if (!(code & 4)) { const float4 *t = sc.tri_isect + 3*size_t((code >> 3) + i); ra = __ldg(t); rb = __ldg(t + 1); rc = __ldg(t + 2); }
+    };
+#else
+    auto prefetch_tri = [&](int, int) {};
+#endif
     auto pop_node = [&]() {                                                             // leave a leaf: next stack entry or done
         if (sp == 0) { finish_ray(); return; }
         tr.cur = stk.pop(sp); li = 0; mode = tr.cur >= 0 ? CM_NODE : CM_LEAF;
+        if (tr.cur < 0) prefetch_tri(tr.cur, 0);
     };
     // box test of pointOnSpline's loop head for the piece (a, b) = the curve on [ta, tb]
     auto piece_box = [&](const float4 &a, const float4 &b, float ta, float tb) {
@@ -644,6 +662,7 @@ TGB_D void machine_traverse_persistent(const DScene &sc, const uint4 *treelet, i
     for (;;) {
         const unsigned idle = __ballot_sync(FULL, mode == CM_IDLE);
         if (!exhausted && __popc(idle) >= (CURVES ? TGB_CURVE_REFILL_IDLE : TGB_TRI_REFILL_IDLE)) {
+#if TGB_RAY_CHUNK
             // the warp owns rays [chunk_next, chunk_end) of the queue: one atomicAdd per TGB_RAY_CHUNK rays instead of one per refill
             if (chunk_next == chunk_end) {
                 uint32_t b = 0;
@@ -654,11 +673,20 @@ TGB_D void machine_traverse_persistent(const DScene &sc, const uint4 *treelet, i
             }
             const uint32_t rank = unsigned(__popc(idle & ((1u << lane) - 1u)));
             const uint32_t cnt = min(uint32_t(__popc(idle)), chunk_end - chunk_next);
-            if (mode == CM_IDLE && rank < cnt) {
-                V3 o, d; float tnear; Hit h; bool any;
-                if (pol.fetch(chunk_next + rank, o, d, tnear, h, any)) { tr.begin(o, d, tnear, any, h); tr.ignore = pol.ignore(); sp = 0; mode = CM_NODE; }
-            }
+            const uint32_t first_ray = chunk_next;
             chunk_next += cnt;
+#else
+            const uint32_t cnt = unsigned(__popc(idle)), leader = unsigned(__ffs(int(idle))) - 1u;
+            const uint32_t rank = unsigned(__popc(idle & ((1u << lane) - 1u)));
+            uint32_t first_ray = 0;
+            if (lane == leader) first_ray = atomicAdd(counter, cnt);
+            first_ray = __shfl_sync(FULL, first_ray, int(leader));
+            exhausted = first_ray + cnt >= n;
+#endif
+            if (mode == CM_IDLE && rank < cnt && first_ray + rank < n) {
+                V3 o, d; float tnear; Hit h; bool any;
+                if (pol.fetch(first_ray + rank, o, d, tnear, h, any)) { tr.begin(o, d, tnear, any, h); tr.ignore = pol.ignore(); sp = 0; mode = CM_NODE; }
+            }
             continue;
         }
         if (idle == FULL) break;                                                        // (only reached once the cursor is exhausted)
@@ -723,7 +751,7 @@ TGB_D void machine_traverse_persistent(const DScene &sc, const uint4 *treelet, i
                         if (p1) stk.push(sp, l1);
                     }
                     tr.cur = l0;
-                    if (l0 < 0) { mode = CM_LEAF; li = 0; }
+                    if (l0 < 0) { mode = CM_LEAF; li = 0; prefetch_tri(l0, 0); }
                 }
             }
         } else {
@@ -753,11 +781,19 @@ TGB_D void machine_traverse_persistent(const DScene &sc, const uint4 *treelet, i
                     }
                     if (!started) pop_node();
                 } else {
+#if TGB_TRI_PREFETCH
+                    const bool hit_any = tr.triangle_rec(ra, rb, rc, first + li) && tr.any;
+                    ++li;
+                    if (hit_any) finish_ray();
+                    else if (li < count) prefetch_tri(tr.cur, li);
+                    else pop_node();
+#else
                     bool hit_any = false;
                     for (int i = 0; i < count; ++i) {
                         if (tr.triangle(sc, first + i) && tr.any) { hit_any = true; break; }
                     }
                     if (hit_any) finish_ray(); else pop_node();
+#endif
                 }
             }
         }
