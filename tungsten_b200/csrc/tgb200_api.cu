@@ -62,6 +62,7 @@ struct tgb_ctx {
     uint32_t persist_blocks = 0;    // grid of the persistent traversal kernels
     size_t trace_smem = 0;          // their dynamic shared memory: treelet image + stacks + mbarrier
     size_t l2_window_bytes = 0;     // bytes of BVH data pinned in L2 through the stream's access-policy window (0 = none)
+    bool diffuse_only = false;      // all surfaces Lambert / null: k_shade<.., .., 1>
     bool sort_materials = false;    // >= 2 lobe models in use: k_shade deals the paths of a block to its threads by BSDF type
     bool has_curves = false;        // selects the kernel instantiations with the curve-segment test and per-hit epsilon
     uint32_t *bin_keys = nullptr, *bin_hist = nullptr;
@@ -742,6 +743,10 @@ int upload_scene(tgb_ctx *c, const tgb_scene_desc *d) {
         }
         const char *env = getenv("TGB_SORT_MATERIALS");
         c->sort_materials = env ? env[0] == '1' : __builtin_popcount(types) >= 2;
+        // every surface Lambert (lights: null BSDF): k_shade's lobe-set-1 instantiation (same arithmetic, a fraction of the code)
+        const char *ls = getenv("TGB_LOBE_SET");
+        c->diffuse_only = (types & ~(1u << TGB_BSDF_LAMBERT)) == 0 && !c->has_curves && !(ls && ls[0] == '0');
+        if (c->diffuse_only) c->sort_materials = false;
     }
     return TGB_OK;
 }
@@ -861,6 +866,7 @@ void enqueue_iteration(tgb_ctx *c, const BatchInfo &bi, int cur, uint32_t bound,
         else k_shade<false, true><<<blocks(bound, kShadeSortBlock), kShadeSortBlock, 0, st>>>(sc, pb, c->sr, bi, c->ctl, c->squeue, c->ctr);
     } else {
         if (curves) k_shade<true, false><<<blocks(bound, 128), 128, 0, st>>>(sc, pb, c->sr, bi, c->ctl, c->squeue, c->ctr);
+        else if (c->diffuse_only) k_shade<false, false, 1><<<blocks(bound, 128), 128, 0, st>>>(sc, pb, c->sr, bi, c->ctl, c->squeue, c->ctr);
         else k_shade<false, false><<<blocks(bound, 128), 128, 0, st>>>(sc, pb, c->sr, bi, c->ctl, c->squeue, c->ctr);
     }
     launches++;

@@ -840,8 +840,22 @@ TGB_D bool hair_sample(const DBsdf &b, Sampler &smp, Event &e) {                
     return true;
 }
 
-template <bool HAIR = false>
+// LS = lobe set the kernel is compiled for: 0 = every lobe model on the path; 1 = scenes whose surfaces are all Lambert (or the
+// null BSDF of lights): the same Lambert arithmetic without the other models' code (k_shade<.., .., 1>: no spills at 64 registers)
+template <bool HAIR = false, int LS = 0>
 TGB_D bool bsdf_sample(const DScene &sc, const DBsdf &b, const Surface &s, Sampler &smp, Event &e) {
+    if (LS == 1) {
+        if (b.type != TGB_BSDF_LAMBERT) return false;                          // NullBsdf::sample() == false
+        if (!(e.requested & LOBE_DIFFUSE_R)) return false;
+        if (e.wi.z <= 0.0f) return false;
+        float xa = sampler_next1d(smp), xb = sampler_next1d(smp);
+        e.wo = cosine_hemisphere(xa, xb);
+        e.pdf = cosine_hemisphere_pdf(e.wo);
+        e.weight = bsdf_albedo(sc, b, s);
+        e.sampled = LOBE_DIFFUSE_R;
+        e.weight = e.weight*sqr(1.0f);                                          // (Bsdf::sample scales by eta^2 = 1)
+        return true;
+    }
     if (HAIR && b.type == TGB_BSDF_HAIR) return hair_sample(b, smp, e);      // Bsdf::eta() is 1 for the BCSDF
     if (b.type != TGB_BSDF_SMOOTH_COAT) {
         if (!bsdf_sample_base(sc, b, s, smp, e)) return false;
@@ -886,8 +900,12 @@ TGB_D bool bsdf_sample(const DScene &sc, const DBsdf &b, const Surface &s, Sampl
     }
     return true;
 }
-template <bool HAIR = false>
+template <bool HAIR = false, int LS = 0>
 TGB_D V3 bsdf_eval(const DScene &sc, const DBsdf &b, const Surface &s, const Event &e) {
+    if (LS == 1) {
+        if (b.type != TGB_BSDF_LAMBERT || !(e.requested & LOBE_DIFFUSE_R) || e.wi.z <= 0.0f || e.wo.z <= 0.0f) return v3s(0.0f)*sqr(1.0f);
+        return ((bsdf_albedo(sc, b, s)*INV_PI_F)*e.wo.z)*sqr(1.0f);
+    }
     if (HAIR && b.type == TGB_BSDF_HAIR) return hair_eval(b, e);
     if (b.type != TGB_BSDF_SMOOTH_COAT) return bsdf_eval_base(sc, b, s, e)*sqr(bsdf_eta(b, e));
     const DBsdf &sub = sc.bsdfs[b.substrate];
@@ -905,8 +923,12 @@ TGB_D V3 bsdf_eval(const DScene &sc, const DBsdf &b, const Surface &s, const Eve
     }
     return v3s(0.0f);
 }
-template <bool HAIR = false>
+template <bool HAIR = false, int LS = 0>
 TGB_D float bsdf_pdf(const DScene &sc, const DBsdf &b, const Surface &s, const Event &e) {
+    if (LS == 1) {
+        if (b.type != TGB_BSDF_LAMBERT || !(e.requested & LOBE_DIFFUSE_R) || e.wi.z <= 0.0f || e.wo.z <= 0.0f) return 0.0f;
+        return cosine_hemisphere_pdf(e.wo);
+    }
     if (HAIR && b.type == TGB_BSDF_HAIR) return hair_pdf(b, e);
     if (b.type != TGB_BSDF_SMOOTH_COAT) return bsdf_pdf_base(sc, b, s, e);
     const DBsdf &sub = sc.bsdfs[b.substrate];

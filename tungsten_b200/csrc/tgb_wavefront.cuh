@@ -1173,7 +1173,7 @@ TGB_D void shadow_resolve_closest(const DScene &sc, const Scratch &sr, uint32_t 
     sr.vis[2*size_t(s) + (mis ? 1 : 0)] = 1u;
 }
 
-template <bool CURVES, bool MATSORT>
+template <bool CURVES, bool MATSORT, int LS = 0>
 __global__ void __launch_bounds__(MATSORT ? kShadeSortBlock : 128, MATSORT ? 2 : TGB_SHADE_MINB)
 k_shade(DScene sc, PathBuf pb, Scratch sr, BatchInfo bi, Ctl *ctl, uint32_t *squeue, Counters *ctr) {
     const uint32_t n = ctl->n;
@@ -1281,9 +1281,9 @@ k_shade(DScene sc, PathBuf pb, Scratch sr, BatchInfo bi, Ctl *ctl, uint32_t *squ
                             ok = (dot(ls.d, sf.Ng) < 0.0f) == ((e.wo.z < 0.0f) != e.flipped);
                         if (ok) {
                             e.requested = LOBE_ALL_BUT_SPECULAR;
-                            V3 f = bsdf_eval<CURVES>(sc, b, sf, e);
+                            V3 f = bsdf_eval<CURVES, LS>(sc, b, sf, e);
                             if (!is_zero(f)) {
-                                float pdfB = bsdf_pdf<CURVES>(sc, b, sf, e);
+                                float pdfB = bsdf_pdf<CURVES, LS>(sc, b, sf, e);
                                 if (l.type == TGB_PRIM_MESH) {
                                     qn = true; qn_any = false;
                                     qnt = ls.dist; n1 = make_float4(f.x, f.y, f.z, ls.pdf); m1.w = pdfB;
@@ -1314,7 +1314,7 @@ k_shade(DScene sc, PathBuf pb, Scratch sr, BatchInfo bi, Ctl *ctl, uint32_t *squ
                     }
                     // bsdfSample (TraceBase.cpp:287-321)
                     e.requested = LOBE_ALL_BUT_SPECULAR;
-                    if (bsdf_sample<CURVES>(sc, b, sf, smp, e) && !is_zero(e.weight)) {
+                    if (bsdf_sample<CURVES, LS>(sc, b, sf, smp, e) && !is_zero(e.weight)) {
                         V3 wo = to_global(e.frame, e.wo);
                         bool ok = true;
                         if (set.enable_consistency_checks)
@@ -1380,7 +1380,7 @@ k_shade(DScene sc, PathBuf pb, Scratch sr, BatchInfo bi, Ctl *ctl, uint32_t *squ
             // continuation sample (TraceBase.cpp:545-565)
             uint32_t status = 0;
             e.requested = LOBE_ALL;
-            bool cont = bsdf_sample<CURVES>(sc, b, sf, smp, e);
+            bool cont = bsdf_sample<CURVES, LS>(sc, b, sf, smp, e);
             V3 wo = v3s(0.0f);
             if (cont) {
                 wo = to_global(e.frame, e.wo);
