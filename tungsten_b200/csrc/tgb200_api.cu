@@ -862,8 +862,8 @@ void enqueue_iteration(tgb_ctx *c, const BatchInfo &bi, int cur, uint32_t bound,
     }
     if (prof) cudaEventRecord(c->ev_k[slot][2], st);
     if (c->sort_materials) {
-        if (curves) k_shade<true, true><<<blocks(bound, kShadeSortBlock), kShadeSortBlock, 0, st>>>(sc, pb, c->sr, bi, c->ctl, c->squeue, c->ctr);
-        else k_shade<false, true><<<blocks(bound, kShadeSortBlock), kShadeSortBlock, 0, st>>>(sc, pb, c->sr, bi, c->ctl, c->squeue, c->ctr);
+        if (curves) k_shade<true, true><<<blocks(bound, kShadeSortBlock*kShadeSortItems), kShadeSortBlock, 0, st>>>(sc, pb, c->sr, bi, c->ctl, c->squeue, c->ctr);
+        else k_shade<false, true><<<blocks(bound, kShadeSortBlock*kShadeSortItems), kShadeSortBlock, 0, st>>>(sc, pb, c->sr, bi, c->ctl, c->squeue, c->ctr);
     } else {
         if (curves) k_shade<true, false><<<blocks(bound, 128), 128, 0, st>>>(sc, pb, c->sr, bi, c->ctl, c->squeue, c->ctr);
         else if (c->diffuse_only) k_shade<false, false, 1><<<blocks(bound, 128), 128, 0, st>>>(sc, pb, c->sr, bi, c->ctl, c->squeue, c->ctr);

@@ -1122,7 +1122,13 @@ __global__ void __launch_bounds__(256) k_hook_finish(DScene sc, const tgb_ray *r
 // slots, so every state array is still read in full sectors by the block as a whole); which thread shades which slot
 // cannot change a result.  The key costs the hit -> primitive -> material gathers once more, so scenes with a single
 // lobe model keep the unsorted kernel.
-constexpr int kShadeSortBlock = 512;
+#ifndef TGB_SHADE_SORT_BLOCK
+#define TGB_SHADE_SORT_BLOCK 1024
+#endif
+#ifndef TGB_SHADE_SORT_ITEMS
+#define TGB_SHADE_SORT_ITEMS 2
+#endif
+constexpr int kShadeSortBlock = TGB_SHADE_SORT_BLOCK, kShadeSortItems = TGB_SHADE_SORT_ITEMS;
 TGB_D uint32_t shade_sort_key(const DScene &sc, const Hit &h) {
     if (h.id == HID_MISS) return 0u;
     int bsdf;
@@ -1174,31 +1180,48 @@ TGB_D void shadow_resolve_closest(const DScene &sc, const Scratch &sr, uint32_t 
 }
 
 template <bool CURVES, bool MATSORT, int LS = 0>
-__global__ void __launch_bounds__(MATSORT ? kShadeSortBlock : 128, MATSORT ? 2 : TGB_SHADE_MINB)
+__global__ void __launch_bounds__(MATSORT ? kShadeSortBlock : 128, MATSORT ? 1024/kShadeSortBlock : (LS == 1 ? 6 : TGB_SHADE_MINB))
 k_shade(DScene sc, PathBuf pb, Scratch sr, BatchInfo bi, Ctl *ctl, uint32_t *squeue, Counters *ctr) {
     const uint32_t n = ctl->n;
-    uint32_t i = blockIdx.x*blockDim.x + threadIdx.x;
-    bool valid = i < n;
+    // MATSORT: the block owns a window of kShadeSortItems x blockDim consecutive slots, counting-sorts them by BSDF type in shared
+    // memory and shades them in sorted order, kShadeSortItems per thread (a wider window = purer warps: C2 with 512 / 1024 /
+    // 2048 slots per window, see profiles/r02_summary.md)
+    constexpr int ITEMS = MATSORT ? kShadeSortItems : 1;
+    __shared__ uint16_t perm[MATSORT ? kShadeSortBlock*kShadeSortItems : 1];
+    const uint32_t window = blockIdx.x*blockDim.x*ITEMS;
+    if (MATSORT) {
+        __shared__ uint32_t bucket[16];
+        if (threadIdx.x < 16) bucket[threadIdx.x] = 0u;
+        __syncthreads();
+        uint32_t key[ITEMS], rank[ITEMS];
+#pragma unroll
+        for (int it = 0; it < ITEMS; ++it) {
+            const uint32_t j = window + it*blockDim.x + threadIdx.x;
+            const bool v = j < n;
+            // one path query (TraceableScene::intersect) was completed for every slot in the queue
+            const Hit hk = v ? unpack_hit(pb.T2[j]) : Hit{0.0f, 0.0f, 0.0f, HID_MISS};
+            count_block(&ctr->rays, &ctr->hits, v, v && hk.id != HID_MISS);
+            key[it] = v ? shade_sort_key(sc, hk) : 15u;                               // slots past the end sort last
+            rank[it] = atomicAdd(&bucket[key[it]], 1u);
+        }
+        __syncthreads();
+#pragma unroll
+        for (int it = 0; it < ITEMS; ++it) {
+            uint32_t before = 0;
+            for (uint32_t k = 0; k < key[it]; ++k) before += bucket[k];
+            perm[before + rank[it]] = uint16_t(it*blockDim.x + threadIdx.x);
+        }
+        __syncthreads();
+    } else {
+        const uint32_t j = window + threadIdx.x;
+        count_block(&ctr->rays, &ctr->hits, j < n, j < n && __float_as_int(pb.T2[j < n ? j : 0].w) != HID_MISS);
+    }
+    for (int item = 0; item < ITEMS; ++item) {
+    const uint32_t i = window + (MATSORT ? uint32_t(perm[item*blockDim.x + threadIdx.x]) : threadIdx.x);
+    const bool valid = i < n;
     // this bounce's NEE / MIS queries: direction, far end (t of the light for occlusion queries), kind
     bool qn = false, qm = false, qn_any = false, qm_any = false;
     uint32_t s = 0;
-    // one path query (TraceableScene::intersect) was completed for every slot in the queue
-    count_block(&ctr->rays, &ctr->hits, valid, valid && __float_as_int(pb.T2[valid ? i : 0].w) != HID_MISS);
-    if (MATSORT) {
-        __shared__ uint32_t bucket[16];
-        __shared__ uint16_t perm[kShadeSortBlock];
-        if (threadIdx.x < 16) bucket[threadIdx.x] = 0u;
-        __syncthreads();
-        uint32_t key = valid ? shade_sort_key(sc, unpack_hit(pb.T2[i])) : 15u;      // slots past the end sort last
-        uint32_t rank = atomicAdd(&bucket[key], 1u);
-        __syncthreads();
-        uint32_t before = 0;
-        for (uint32_t k = 0; k < key; ++k) before += bucket[k];
-        perm[before + rank] = uint16_t(threadIdx.x);
-        __syncthreads();
-        i = blockIdx.x*blockDim.x + perm[threadIdx.x];
-        valid = i < n;
-    }
     if (valid) {
         s = i;
         const float4 t0 = pb.T0[s], t1 = pb.T1[s], t2 = pb.T2[s], t3 = pb.T3[s];
@@ -1427,6 +1450,7 @@ k_shade(DScene sc, PathBuf pb, Scratch sr, BatchInfo bi, Ctl *ctl, uint32_t *squ
             if (qm) squeue[base + __popc(mn) + __popc(mm & lt)] = (s << 2) | 1u | (qm_any ? 2u : 0u);
         }
     }
+    }   // item
 }
 
 // Analytic part of the NEE/MIS queries (quads and cubes are tested coherently, every lane runs the same loop), top-level
