@@ -1,0 +1,13 @@
+# r02-u (1 GPU): 4-ary CDF search (C2), leaf pair loads (C1): parity + A/B
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_gpu_bench_scenes.py -m gpu -q --tb=short 2>&1 | grep -v "^$" | tail -4
+run() { python bench.py --config $2 --steps $3 --warmup 3 --spp-per-step $4 --no-cpu-baseline --no-other-configs 2>/dev/null | python -c "
+import json,sys; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); r=d['roofline']; s=d['roofline_streaming']
+print('$1 $2: value %.1f e2e %.1f trace %.0f ms (%.0f Mq/s) shadow %.0f ms shade %.0f ms accum %.0f ms dev %.0f ms' % (d['value'], d['e2e']['value'], r['kernel_ms'], r['mqueries_per_s'], r['k_shadow']['kernel_ms'], s['k_shade']['kernel_ms'], s['k_accum']['kernel_ms'], d['device_ms']))"; }
+for v in base pairs base; do
+  if [ "$v" = base ]; then unset TGB200_LIB; else export TGB200_LIB=$PWD/tungsten_b200/libtgb200_$v.so; fi
+  run $v c1 4 64
+done
+unset TGB200_LIB
+run base c2 3 8; run base c3 3 8
+TGB200_LIB=$PWD/tungsten_b200/libtgb200_pairs.so run pairs c3 3 8

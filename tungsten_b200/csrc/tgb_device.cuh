@@ -951,7 +951,15 @@ TGB_D float bsdf_pdf(const DScene &sc, const DBsdf &b, const Surface &s, const E
 struct LightSample { V3 d; float dist, pdf; };
 
 TGB_D int dist1d_warp(const float *cdf, const float *pdf, int n, float &u) {           // sampling/Distribution1D.hpp:37-41
+    // std::upper_bound = the first index whose cdf exceeds u.  The cdf is non-decreasing, so any bracketing order finds the same
+    // index; three independent probes per step (4-ary search) halve the chain of dependent loads of the binary search (a
+    // 1024 x 512 environment map: 10 + 9 dependent loads per sample -> 5 + 5).
     int lo = 0, hi = n + 1;
+    while (hi - lo >= 4) {
+        const int q = (hi - lo) >> 2, m1 = lo + q, m2 = m1 + q, m3 = m2 + q;
+        const bool p1 = u < __ldg(cdf + m1), p2 = u < __ldg(cdf + m2), p3 = u < __ldg(cdf + m3);
+        if (p1) hi = m1; else if (p2) { lo = m1 + 1; hi = m2; } else if (p3) { lo = m2 + 1; hi = m3; } else lo = m3 + 1;
+    }
     while (lo < hi) { int mid = (lo + hi) >> 1; if (u < __ldg(cdf + mid)) hi = mid; else lo = mid + 1; }
     int idx = lo - 1;
     float r = (u - __ldg(cdf + idx))/__ldg(pdf + idx);
