@@ -288,7 +288,7 @@ int main() {
 """
 
 
-def _build_and_run_kat(source, name, out_json):
+def _build_and_run_kat(source, name, out_json, args=()):
     import glob
     d = tempfile.mkdtemp()
     src = os.path.join(d, name + ".cpp")
@@ -304,7 +304,7 @@ def _build_and_run_kat(source, name, out_json):
     if r.returncode != 0:
         print(r.stdout[-3000:])
         raise SystemExit(name + ": KAT program failed to build")
-    out = subprocess.check_output([exe], text=True)
+    out = subprocess.check_output([exe] + list(args), text=True)
     json.loads(out)
     open(os.path.join(HERE, out_json), "w").write(out)
     shutil.rmtree(d)
@@ -514,6 +514,73 @@ def dump_sky_image(scene_json, out_pfm):
     return img
 
 
+# Closest hits of the reference's own TraceableScene::intersect (Embree BVH4 + Moeller-Trumbore for meshes, the top-level
+# user-geometry BVH for quads / cubes) on a scene loaded by the reference's own Scene::load: SURVEY 7 step 1-iii's "--dump-hits".
+KAT_SCENE_HITS_CPP = r"""
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+#include <memory>
+#include "io/Scene.hpp"
+#include "io/Path.hpp"
+#include "renderer/TraceableScene.hpp"
+#include "primitives/EmbreeUtil.hpp"
+#include "primitives/TriangleMesh.hpp"
+#include "primitives/IntersectionInfo.hpp"
+#include "primitives/IntersectionTemporary.hpp"
+#include "thread/ThreadUtils.hpp"
+#include "math/Ray.hpp"
+using namespace Tungsten;
+static unsigned bits(float v) { union { float f; unsigned u; } c; c.f = v; return c.u; }
+struct MeshIntersectionView { Vec3f Ng; float u; float v; int primId; bool backSide; };     // TriangleMesh.cpp:22-29 (private to that file)
+int main(int argc, char **argv) {
+    EmbreeUtil::initDevice();
+    ThreadUtils::startThreads(2);
+    std::unique_ptr<Scene> scene(Scene::load(Path(argv[1])));
+    scene->loadResources();
+    std::unique_ptr<TraceableScene> flat(scene->makeTraceable(0xBA5EBA11u));
+    FILE *f = fopen(argv[2], "rb");
+    std::vector<float> rays; float buf[8];
+    while (fread(buf, 4, 8, f) == 8) rays.insert(rays.end(), buf, buf + 8);
+    fclose(f);
+    printf("{\"hits\": [");
+    size_t n = rays.size()/8;
+    for (size_t i = 0; i < n; ++i) {
+        const float *r = &rays[8*i];
+        Ray ray(Vec3f(r[0], r[1], r[2]), Vec3f(r[3], r[4], r[5]), r[6]);
+        IntersectionTemporary data; IntersectionInfo info;
+        bool hit = flat->intersect(ray, data, info);
+        int prim = -1, tri = -1; unsigned back = 0;
+        if (hit) {
+            for (size_t k = 0; k < scene->primitives().size(); ++k) if (scene->primitives()[k].get() == info.primitive) prim = int(k);
+            if (dynamic_cast<const TriangleMesh *>(info.primitive)) tri = data.as<MeshIntersectionView>()->primId;
+            back = info.primitive->hitBackside(data) ? 1u : 0u;
+        }
+        printf("%s[%d, %d, %u, %u]", i ? ", " : "", prim, tri, hit ? bits(ray.farT()) : 0u, back);
+    }
+    printf("]}\n");
+    return 0;
+}
+"""
+
+
+def scene_hit_rays(n=6000, seed=11):
+    """The rays of kat_scene_hits.json (tests regenerate them from the seed): origins in the room, uniform directions."""
+    import numpy as np
+    rng = np.random.RandomState(seed)
+    o = rng.uniform(-0.9, 0.9, (n, 3)).astype(np.float32); o[:, 1] = rng.uniform(0.05, 1.9, n).astype(np.float32)
+    d = rng.normal(size=(n, 3)); d /= np.linalg.norm(d, axis=1, keepdims=True)
+    return np.concatenate([o, d.astype(np.float32), np.full((n, 1), 5e-4, np.float32), np.full((n, 1), np.inf, np.float32)], axis=1).astype(np.float32)
+
+
+def make_kat_scene_hits():
+    rays = scene_hit_rays()
+    d = tempfile.mkdtemp()
+    rp = os.path.join(d, "rays.bin"); rays.tofile(rp)
+    _build_and_run_kat(KAT_SCENE_HITS_CPP, "kat_scene_hits", "kat_scene_hits.json", args=[os.path.join(HERE, "materials", "scene.json"), rp])
+    shutil.rmtree(d)
+
+
 def make_kat_lights():
     """Known answers of sampleDirect / intersect / directPdf / evalDirect of the reference's Quad, TriangleMesh and
     InfiniteSphere(+BitmapTexture importance map) classes -> kat_lights.json."""
@@ -595,4 +662,5 @@ if __name__ == "__main__":
     make_kat_bsdfs()
     make_kat_lights()
     make_kat_instances()
+    make_kat_scene_hits()
     make_scenes()
