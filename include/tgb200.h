@@ -56,7 +56,8 @@ enum {
     TGB_BSDF_NULL = 0, TGB_BSDF_LAMBERT = 1, TGB_BSDF_ROUGH_CONDUCTOR = 2,
     TGB_BSDF_ROUGH_DIELECTRIC = 3, TGB_BSDF_PLASTIC = 4, TGB_BSDF_ROUGH_PLASTIC = 5,
     TGB_BSDF_SMOOTH_COAT = 6, TGB_BSDF_CONDUCTOR = 7, TGB_BSDF_DIELECTRIC = 8, TGB_BSDF_MIRROR = 9,
-    TGB_BSDF_HAIR = 10          /* bsdfs/HairBcsdf.cpp; only on CURVES primitives                  */
+    TGB_BSDF_HAIR = 10,         /* bsdfs/HairBcsdf.cpp; only on CURVES primitives                  */
+    TGB_BSDF_ROUGH_COAT = 11    /* bsdfs/RoughCoatBsdf.cpp: rough dielectric coat over `substrate`  */
 };
 enum { TGB_DIST_BECKMANN = 0, TGB_DIST_PHONG = 1, TGB_DIST_GGX = 2 };
 
@@ -69,7 +70,7 @@ typedef struct tgb_bsdf {
     float    eta[3], k[3];      /* conductor complex IOR (RGB)                                     */
     float    thickness;         /* plastic / coat                                                  */
     float    sigma_a[3];        /* plastic / coat absorption                                       */
-    int32_t  substrate;         /* SMOOTH_COAT: index of the substrate bsdf, else -1               */
+    int32_t  substrate;         /* SMOOTH_COAT / ROUGH_COAT: index of the substrate bsdf, else -1   */
     uint32_t enable_refraction; /* (rough) dielectric "enable_refraction"                          */
     /* HAIR: sigma_a[] = HairBcsdf::_sigmaA as prepared (HairBcsdf.cpp:435-443), plus:              */
     float    hair_scale_angle_deg, hair_roughness;

@@ -23,6 +23,7 @@
 #include "bsdfs/RoughConductorBsdf.hpp"
 #include "bsdfs/RoughPlasticBsdf.hpp"
 #include "bsdfs/SmoothCoatBsdf.hpp"
+#include "bsdfs/RoughCoatBsdf.hpp"
 #include "bsdfs/PlasticBsdf.hpp"
 #include "bsdfs/LambertBsdf.hpp"
 #include "bsdfs/NullBsdf.hpp"
@@ -170,6 +171,14 @@ struct Flattener
             o.thickness = sc->thickness();
             put(o.sigma_a, sc->sigmaA());
             o.substrate = bsdf(sc->substrate().get());
+        } else if (const RoughCoatBsdf *rc = dynamic_cast<const RoughCoatBsdf *>(b)) {
+            o.type = TGB_BSDF_ROUGH_COAT;
+            o.distribution = distribution(rc->distributionName());
+            o.roughness_tex = texture(rc->roughness().get());
+            o.ior = rc->ior();
+            o.thickness = rc->thickness();
+            put(o.sigma_a, rc->sigmaA());
+            o.substrate = bsdf(rc->substrate().get());
         } else if (const HairBcsdf *hb = dynamic_cast<const HairBcsdf *>(b)) {
             // HairBcsdf keeps its parameters private; its own toJson() returns them (HairBcsdf.cpp:173-181),
             // the melanin mix is HairBcsdf::prepareForRender's (:435-443)

@@ -199,6 +199,7 @@ KAT_BSDF_CPP = r"""
 #include "bsdfs/PlasticBsdf.hpp"
 #include "bsdfs/RoughPlasticBsdf.hpp"
 #include "bsdfs/SmoothCoatBsdf.hpp"
+#include "bsdfs/RoughCoatBsdf.hpp"
 #include "bsdfs/MirrorBsdf.hpp"
 #include "bsdfs/ConductorBsdf.hpp"
 #include "bsdfs/DielectricBsdf.hpp"
@@ -238,6 +239,15 @@ int main() {
       b->setAlbedo(std::make_shared<ConstantTexture>(Vec3f(0.95f, 0.9f, 0.85f))); list.push_back(b); }
     { auto b = std::make_shared<DielectricBsdf>(); list.push_back(b); }
     { auto b = std::make_shared<DielectricBsdf>(1.33f); b->setEnableTransmission(false); b->setAlbedo(std::make_shared<ConstantTexture>(Vec3f(0.8f, 0.9f, 1.0f))); list.push_back(b); }
+    // RoughCoatBsdf (appended, see above): constructor defaults; Beckmann coat with absorption over Lambert; GGX coat over plastic
+    { auto b = std::make_shared<RoughCoatBsdf>(); list.push_back(b); }
+    { auto sub = std::make_shared<LambertBsdf>(); sub->setAlbedo(std::make_shared<ConstantTexture>(Vec3f(0.6f, 0.3f, 0.2f)));
+      auto b = std::make_shared<RoughCoatBsdf>(); b->setDistributionName("beckmann"); b->setRoughness(std::make_shared<ConstantTexture>(0.3f)); b->setIor(1.5f);
+      b->setThickness(2.0f); b->setSigmaA(Vec3f(0.2f, 0.1f, 0.4f)); b->setSubstrate(sub); list.push_back(b); }
+    // (a substrate taken from the scene's bsdf list by name is prepared by TraceableScene, TraceableScene.hpp:76-77; an INLINE
+    //  substrate object never is -- Scene::fetchObject only instantiates it -- which leaves PlasticBsdf's derived members unset)
+    { auto sub = std::make_shared<PlasticBsdf>(); sub->setAlbedo(std::make_shared<ConstantTexture>(Vec3f(0.2f, 0.5f, 0.7f))); sub->prepareForRender();
+      auto b = std::make_shared<RoughCoatBsdf>(); b->setRoughness(std::make_shared<ConstantTexture>(0.15f)); b->setIor(1.6f); b->setSubstrate(sub); list.push_back(b); }
     IntersectionInfo info; info.uv = Vec2f(0.3f, 0.4f);
     printf("{\n\"bsdfs\": [");
     for (size_t n = 0; n < list.size(); ++n) {
@@ -635,6 +645,8 @@ def make_scenes(only=None):
     scenes["many_lights"] = synth.many_lights(os.path.join(HERE, "many_lights"), "scene", res=res, spp=spp, subdiv=2)
     # 151 analytic primitives, no mesh: from 24 on the library keeps them in BVH leaves instead of its per-ray loop
     scenes["cube_city"] = synth.cube_city(os.path.join(HERE, "cube_city"), "scene", n=12, res=res, spp=spp)
+    # RoughCoatBsdf over Lambert / rough conductor / plastic substrates (+ a smooth coat)
+    scenes["coats"] = synth.coat_room(os.path.join(HERE, "coats"), "scene", res=res, spp=spp, subdiv=2)
     scenes["dirac"] = synth.dirac_room(os.path.join(HERE, "dirac"), "scene", res=res, spp=spp, subdiv=2)
     # the two emitters of the shipped hair scene: infinite_sphere_cap (sampled sun) + skydome (unsampled sky); min_bounces 1 as shipped
     scenes["hair_sky"] = synth.hair_scene(os.path.join(HERE, "hair_sky"), "scene", n_curves=300, res=res, spp=spp, shipped_lights=True, min_bounces=1)

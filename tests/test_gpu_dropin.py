@@ -18,7 +18,7 @@ G = os.path.join(ROOT, "tests", "golden")
 
 
 @pytest.mark.skipif(not os.path.exists(EXE), reason="drop-in binary not built (needs /root/reference at build time)")
-@pytest.mark.parametrize("name", ["cornell", "materials", "coat_env", "hair", "curves_plastic", "hair_sky", "dirac", "many_lights", "cube_city"])
+@pytest.mark.parametrize("name", ["cornell", "materials", "coat_env", "hair", "curves_plastic", "hair_sky", "dirac", "many_lights", "cube_city", "coats"])
 def test_reference_binary_with_b200_integrator(name, tmp_path):
     src = os.path.join(G, name)
     for f in os.listdir(src):

@@ -70,6 +70,13 @@ def test_dirac_lobes(scratch):
     _compare(fs, 8, same_ray_count=False)
 
 
+def test_rough_coat(scratch):
+    """f4: RoughCoatBsdf (rough dielectric interface over Lambert / rough conductor / plastic substrates) next to a SmoothCoatBsdf:
+    lobe choice through the supplemental PCG, one-sample MIS weights between coat and substrate."""
+    fs = scene.load_scene(synth.coat_room(scratch, res=(96, 96), spp=8, subdiv=3))
+    _compare(fs, 8, same_ray_count=False)
+
+
 def test_coat_checker_envmap(scratch):
     """C0 stand-in: smooth_coat over rough_conductor, checker floor, importance-sampled HDR environment."""
     fs = scene.load_scene(synth.materialtest_standin(scratch, res=(96, 96), spp=8, subdiv=3))
@@ -85,6 +92,7 @@ def test_golden_scenes_against_reference_fixtures():
     for name, exact_min, close_min in [("cornell", 0.5, 0.985), ("cornell_short", 0.5, 0.985), ("cornell_mesh", 0.5, 0.985),
                                        ("materials", 0.5, 0.985), ("materials_env", 0.5, 0.985), ("coat_env", 0.3, 0.985), ("dirac", 0.5, 0.985),
                                        ("many_lights", 0.5, 0.985),      # 39 samplable lights: chooseLight's > 16 lights path
+                                       ("coats", 0.5, 0.985),            # RoughCoatBsdf over three kinds of substrate + a smooth coat
                                        ("cube_city", 0.3, 0.985),        # 151 analytic primitives: kept in BVH leaves (8 diffuse bounces: libm ulps add up)
                                        ("hair", 0.3, 0.97), ("hair_dark", 0.3, 0.97), ("hair_sky", 0.3, 0.97), ("curves_lambert", 0.5, 0.97),
                                        ("curves_plastic", 0.5, 0.97)]:

@@ -38,7 +38,7 @@ def test_analytic_scenes_bit_exact(name, mode, ref):
     assert np.array_equal(img, want)
 
 
-@pytest.mark.parametrize("name", ["cornell_mesh", "materials", "materials_env", "coat_env", "dirac", "many_lights"])
+@pytest.mark.parametrize("name", ["cornell_mesh", "materials", "materials_env", "coat_env", "dirac", "many_lights", "coats"])
 @pytest.mark.parametrize("mode,ref", [(0, "ref_pathseed.pfm"), (1, "ref_stock.pfm")])
 def test_mesh_scenes_close(name, mode, ref):
     img = _render(name, mode)

@@ -12,7 +12,7 @@ TGB_OK, TGB_ERR_INVALID, TGB_ERR_UNSUPPORTED, TGB_ERR_NO_DEVICE, TGB_ERR_CUDA, T
 
 TEX_CONSTANT, TEX_CHECKER, TEX_BITMAP = 0, 1, 2
 (BSDF_NULL, BSDF_LAMBERT, BSDF_ROUGH_CONDUCTOR, BSDF_ROUGH_DIELECTRIC, BSDF_PLASTIC, BSDF_ROUGH_PLASTIC,
- BSDF_SMOOTH_COAT, BSDF_CONDUCTOR, BSDF_DIELECTRIC, BSDF_MIRROR, BSDF_HAIR) = range(11)
+ BSDF_SMOOTH_COAT, BSDF_CONDUCTOR, BSDF_DIELECTRIC, BSDF_MIRROR, BSDF_HAIR, BSDF_ROUGH_COAT) = range(12)
 DIST_BECKMANN, DIST_PHONG, DIST_GGX = 0, 1, 2
 PRIM_MESH, PRIM_QUAD, PRIM_CUBE, PRIM_INFINITE_SPHERE, PRIM_CURVES, PRIM_INFINITE_SPHERE_CAP, PRIM_SKYDOME = 0, 1, 2, 3, 4, 5, 6
 CURVE_CYLINDER, CURVE_HALF_CYLINDER, CURVE_BCSDF_CYLINDER = 0, 1, 2

@@ -190,6 +190,7 @@ uint32_t bsdf_lobes(const tgb_bsdf &b) {
     case TGB_BSDF_MIRROR: case TGB_BSDF_CONDUCTOR: return LOBE_SPEC_R;                   // MirrorBsdf.cpp:13, ConductorBsdf.cpp:19
     case TGB_BSDF_DIELECTRIC: return b.enable_refraction ? (LOBE_SPEC_R | LOBE_SPEC_T) : LOBE_SPEC_R;   // DielectricBsdf.cpp:174-180
     case TGB_BSDF_SMOOTH_COAT: return LOBE_SPEC_R;          // | substrate lobes, added by upload_scene
+    case TGB_BSDF_ROUGH_COAT: return LOBE_GLOSSY_R;         // | substrate lobes (RoughCoatBsdf.cpp:301-306)
     case TGB_BSDF_HAIR: return LOBE_GLOSSY_R | LOBE_GLOSSY_T | LOBE_ANISO;                  // bsdfs/HairBcsdf.cpp:20
     default: return 0xFFFFFFFFu;
     }
@@ -287,16 +288,17 @@ int upload_scene(tgb_ctx *c, const tgb_scene_desc *d) {
         o.type = b.type; o.lobes = bsdf_lobes(b);
         if (o.lobes == 0xFFFFFFFFu) return fail(c, TGB_ERR_UNSUPPORTED, "bsdf type %u is outside the hot path", b.type);
         if (b.albedo_tex < 0 || uint32_t(b.albedo_tex) >= d->n_textures) return fail(c, TGB_ERR_INVALID, "bsdf %u: bad albedo texture", i);
-        bool rough = b.type == TGB_BSDF_ROUGH_CONDUCTOR || b.type == TGB_BSDF_ROUGH_DIELECTRIC || b.type == TGB_BSDF_ROUGH_PLASTIC;
+        bool rough = b.type == TGB_BSDF_ROUGH_CONDUCTOR || b.type == TGB_BSDF_ROUGH_DIELECTRIC || b.type == TGB_BSDF_ROUGH_PLASTIC || b.type == TGB_BSDF_ROUGH_COAT;
         if (rough && (b.roughness_tex < 0 || uint32_t(b.roughness_tex) >= d->n_textures)) return fail(c, TGB_ERR_INVALID, "bsdf %u: bad roughness texture", i);
         o.dist = b.distribution; o.albedo_tex = b.albedo_tex; o.rough_tex = b.roughness_tex;
         o.ior = b.ior; o.inv_ior = 1.0f/b.ior; o.eta = f3(b.eta); o.k = f3(b.k); o.enable_t = b.enable_refraction; o.substrate = b.substrate;
-        if (b.type == TGB_BSDF_SMOOTH_COAT) {                                             // bsdfs/SmoothCoatBsdf.cpp:218-223
-            if (b.substrate < 0 || uint32_t(b.substrate) >= d->n_bsdfs || d->bsdfs[b.substrate].type == TGB_BSDF_SMOOTH_COAT)
-                return fail(c, TGB_ERR_UNSUPPORTED, "bsdf %u: smooth_coat needs a non-coat substrate", i);
+        if (b.type == TGB_BSDF_SMOOTH_COAT || b.type == TGB_BSDF_ROUGH_COAT) {             // SmoothCoatBsdf.cpp:218-223, RoughCoatBsdf.cpp:301-306
+            if (b.substrate < 0 || uint32_t(b.substrate) >= d->n_bsdfs || d->bsdfs[b.substrate].type == TGB_BSDF_SMOOTH_COAT ||
+                d->bsdfs[b.substrate].type == TGB_BSDF_ROUGH_COAT || d->bsdfs[b.substrate].type == TGB_BSDF_HAIR)
+                return fail(c, TGB_ERR_UNSUPPORTED, "bsdf %u: a coat needs a substrate that is neither a coat nor the hair BCSDF", i);
             o.scaled_sigma_a = f3(b.sigma_a)*b.thickness;
             o.avg_transmittance = std::exp(-2.0f*avg(o.scaled_sigma_a));
-            o.lobes = LOBE_SPEC_R | bsdf_lobes(d->bsdfs[b.substrate]);
+            o.lobes = (b.type == TGB_BSDF_SMOOTH_COAT ? LOBE_SPEC_R : LOBE_GLOSSY_R) | bsdf_lobes(d->bsdfs[b.substrate]);
         }
         if (b.type == TGB_BSDF_HAIR) {                                                    // bsdfs/HairBcsdf.cpp:422-446
             HairTables ht;
@@ -341,7 +343,7 @@ int upload_scene(tgb_ctx *c, const tgb_scene_desc *d) {
                     const tgb_bsdf *b = &d->bsdfs[d->bsdf_slots[p.bsdf_first + k]];
                     for (int hop = 0; hop < 4 && b; ++hop) {
                         if (b->type == TGB_BSDF_HAIR) return fail(c, TGB_ERR_UNSUPPORTED, "primitive %u: the hair BCSDF on a primitive that is not `curves` is outside the hot path", i);
-                        b = (b->type == TGB_BSDF_SMOOTH_COAT && b->substrate >= 0 && uint32_t(b->substrate) < d->n_bsdfs) ? &d->bsdfs[b->substrate] : nullptr;
+                        b = ((b->type == TGB_BSDF_SMOOTH_COAT || b->type == TGB_BSDF_ROUGH_COAT) && b->substrate >= 0 && uint32_t(b->substrate) < d->n_bsdfs) ? &d->bsdfs[b->substrate] : nullptr;
                     }
                 }
         }

@@ -840,6 +840,127 @@ TGB_D bool hair_sample(const DBsdf &b, Sampler &smp, Event &e) {                
     return true;
 }
 
+// RoughCoatBsdf (bsdfs/RoughCoatBsdf.cpp): a rough dielectric interface (RoughDielectricBsdf::*Base, reflection only) over any
+// non-coat substrate.  substrateEvalAndPdf :50-80, sample :82-151, eval :153-195, pdf :257-299.
+TGB_D void rcoat_substrate_eval_pdf(const DScene &sc, const DBsdf &b, const DBsdf &sub, const Surface &s, const Event &e, float eta,
+                                    float Fi, float cosThetaTi, float &pdf, V3 &brdf) {
+    float cosThetaTo;
+    float Fo = dielectric_reflectance(eta, e.wo.z, cosThetaTo);
+    if (Fi == 1.0f || Fo == 1.0f) { pdf = 0.0f; brdf = v3s(0.0f); return; }
+    Event q = e;
+    q.wi = v3(e.wi.x*eta, e.wi.y*eta, copysignf(cosThetaTi, e.wi.z));
+    q.wo = v3(e.wo.x*eta, e.wo.y*eta, copysignf(cosThetaTo, e.wo.z));
+    pdf = bsdf_pdf_base(sc, sub, s, q);
+    pdf *= eta*eta*fabsf(e.wo.z/cosThetaTo);
+    float compressionProjection = eta*eta*e.wo.z/cosThetaTo;
+    V3 substrateF = bsdf_eval_base(sc, sub, s, q);
+    if (max_comp(b.scaled_sigma_a) > 0.0f)
+        substrateF = substrateF*vexp(b.scaled_sigma_a*(-1.0f/cosThetaTo - 1.0f/cosThetaTi));
+    brdf = substrateF*(compressionProjection*(1.0f - Fi)*(1.0f - Fo));
+}
+TGB_D bool rcoat_sample(const DScene &sc, const DBsdf &b, const Surface &s, Sampler &smp, Event &e) {
+    const DBsdf &sub = sc.bsdfs[b.substrate];
+    if (e.wi.z <= 0.0f) return false;
+    bool sampleR = (e.requested & LOBE_GLOSSY_R) != 0, sampleT = (e.requested & sub.lobes) != 0;
+    if (!sampleR && !sampleT) return false;
+    V3 wi = e.wi;
+    float eta = 1.0f/b.ior;
+    float cosThetaTi;
+    float Fi = dielectric_reflectance(eta, wi.z, cosThetaTi);
+    float substrateWeight = b.avg_transmittance*(1.0f - Fi);
+    float specularWeight = Fi;
+    float specularProbability = specularWeight/(specularWeight + substrateWeight);
+    if (sampleR && (sampler_boolean(smp, specularProbability) || !sampleT)) {
+        float roughness = bsdf_roughness(sc, b, s);
+        if (!rd_sample_base(smp, e, true, false, roughness, b.ior, b.dist)) return false;
+        if (sampleT) {
+            V3 brdfSubstrate, brdfSpecular = e.weight*e.pdf;
+            float pdfSubstrate, pdfSpecular = e.pdf*specularProbability;
+            rcoat_substrate_eval_pdf(sc, b, sub, s, e, eta, Fi, cosThetaTi, pdfSubstrate, brdfSubstrate);
+            pdfSubstrate *= 1.0f - specularProbability;
+            e.weight = (brdfSpecular + brdfSubstrate)/(pdfSpecular + pdfSubstrate);
+            e.pdf = pdfSpecular + pdfSubstrate;
+        }
+        return true;
+    }
+    V3 wiSubstrate = v3(wi.x*eta, wi.y*eta, cosThetaTi);
+    e.wi = wiSubstrate;
+    bool success = bsdf_sample_base(sc, sub, s, smp, e);
+    e.wi = wi;
+    if (!success) return false;
+    float cosThetaTo;
+    float Fo = dielectric_reflectance(b.ior, e.wo.z, cosThetaTo);
+    if (Fo == 1.0f) return false;
+    float cosThetaSubstrate = e.wo.z;
+    e.wo = v3(e.wo.x*b.ior, e.wo.y*b.ior, cosThetaTo);
+    e.weight = e.weight*((1.0f - Fi)*(1.0f - Fo));
+    if (max_comp(b.scaled_sigma_a) > 0.0f)
+        e.weight = e.weight*vexp(b.scaled_sigma_a*(-1.0f/cosThetaSubstrate - 1.0f/cosThetaTi));
+    e.weight = e.weight*(wi.z/wiSubstrate.z);
+    e.pdf *= eta*eta*cosThetaTo/cosThetaSubstrate;
+    if (sampleR) {
+        float roughness = bsdf_roughness(sc, b, s);
+        V3 brdfSubstrate = e.weight*e.pdf;
+        float pdfSubstrate = e.pdf*(1.0f - specularProbability);
+        V3 brdfSpecular = rd_eval_base(e, true, false, roughness, b.ior, b.dist);
+        float pdfSpecular = rd_pdf_base(e, true, false, roughness, b.ior, b.dist);
+        pdfSpecular *= specularProbability;
+        e.weight = (brdfSpecular + brdfSubstrate)/(pdfSpecular + pdfSubstrate);
+        e.pdf = pdfSpecular + pdfSubstrate;
+    }
+    return true;
+}
+TGB_D V3 rcoat_eval(const DScene &sc, const DBsdf &b, const Surface &s, const Event &e) {
+    const DBsdf &sub = sc.bsdfs[b.substrate];
+    bool sampleR = (e.requested & LOBE_GLOSSY_R) != 0, sampleT = (e.requested & sub.lobes) != 0;
+    if (!sampleT && !sampleR) return v3s(0.0f);
+    if (e.wi.z <= 0.0f || e.wo.z <= 0.0f) return v3s(0.0f);
+    V3 glossyR = v3s(0.0f);
+    if (sampleR) glossyR = rd_eval_base(e, true, false, bsdf_roughness(sc, b, s), b.ior, b.dist);
+    V3 substrateR = v3s(0.0f);
+    if (sampleT) {
+        float eta = 1.0f/b.ior, cosThetaTi, cosThetaTo;
+        float Fi = dielectric_reflectance(eta, e.wi.z, cosThetaTi);
+        float Fo = dielectric_reflectance(eta, e.wo.z, cosThetaTo);
+        if (Fi == 1.0f || Fo == 1.0f) return glossyR;
+        Event q = e;
+        q.wi = v3(e.wi.x*eta, e.wi.y*eta, copysignf(cosThetaTi, e.wi.z));
+        q.wo = v3(e.wo.x*eta, e.wo.y*eta, copysignf(cosThetaTo, e.wo.z));
+        float compressionProjection = eta*eta*e.wo.z/cosThetaTo;
+        V3 substrateF = bsdf_eval_base(sc, sub, s, q);
+        if (max_comp(b.scaled_sigma_a) > 0.0f)
+            substrateF = substrateF*vexp(b.scaled_sigma_a*(-1.0f/cosThetaTo - 1.0f/cosThetaTi));
+        substrateR = substrateF*(compressionProjection*(1.0f - Fi)*(1.0f - Fo));
+    }
+    return glossyR + substrateR;
+}
+TGB_D float rcoat_pdf(const DScene &sc, const DBsdf &b, const Surface &s, const Event &e) {
+    const DBsdf &sub = sc.bsdfs[b.substrate];
+    bool sampleR = (e.requested & LOBE_GLOSSY_R) != 0, sampleT = (e.requested & sub.lobes) != 0;
+    if (!sampleT && !sampleR) return 0.0f;
+    if (e.wi.z <= 0.0f || e.wo.z <= 0.0f) return 0.0f;
+    float eta = 1.0f/b.ior, cosThetaTi, cosThetaTo;
+    float Fi = dielectric_reflectance(eta, e.wi.z, cosThetaTi);
+    float Fo = dielectric_reflectance(eta, e.wo.z, cosThetaTo);
+    float specularProbability;
+    if (sampleR && sampleT) {
+        float substrateWeight = b.avg_transmittance*(1.0f - Fi);
+        float specularWeight = Fi;
+        specularProbability = specularWeight/(specularWeight + substrateWeight);
+    } else specularProbability = sampleR ? 1.0f : 0.0f;
+    float glossyPdf = 0.0f;
+    if (sampleR) glossyPdf = rd_pdf_base(e, true, false, bsdf_roughness(sc, b, s), b.ior, b.dist);
+    float substratePdf = 0.0f;
+    if (sampleT && Fi < 1.0f && Fo < 1.0f) {
+        Event q = e;
+        q.wi = v3(e.wi.x*eta, e.wi.y*eta, copysignf(cosThetaTi, e.wi.z));
+        q.wo = v3(e.wo.x*eta, e.wo.y*eta, copysignf(cosThetaTo, e.wo.z));
+        substratePdf = bsdf_pdf_base(sc, sub, s, q);
+        substratePdf *= eta*eta*fabsf(e.wo.z/cosThetaTo);
+    }
+    return glossyPdf*specularProbability + substratePdf*(1.0f - specularProbability);
+}
+
 // LS = lobe set the kernel is compiled for: 0 = every lobe model on the path; 1 = scenes whose surfaces are all Lambert (or the
 // null BSDF of lights): the same Lambert arithmetic without the other models' code (k_shade<.., .., 1>: no spills at 64 registers)
 template <bool HAIR = false, int LS = 0>
@@ -857,6 +978,7 @@ TGB_D bool bsdf_sample(const DScene &sc, const DBsdf &b, const Surface &s, Sampl
         return true;
     }
     if (HAIR && b.type == TGB_BSDF_HAIR) return hair_sample(b, smp, e);      // Bsdf::eta() is 1 for the BCSDF
+    if (b.type == TGB_BSDF_ROUGH_COAT) return rcoat_sample(sc, b, s, smp, e);
     if (b.type != TGB_BSDF_SMOOTH_COAT) {
         if (!bsdf_sample_base(sc, b, s, smp, e)) return false;
         e.weight = e.weight*sqr(bsdf_eta(b, e));
@@ -907,6 +1029,7 @@ TGB_D V3 bsdf_eval(const DScene &sc, const DBsdf &b, const Surface &s, const Eve
         return ((bsdf_albedo(sc, b, s)*INV_PI_F)*e.wo.z)*sqr(1.0f);
     }
     if (HAIR && b.type == TGB_BSDF_HAIR) return hair_eval(b, e);
+    if (b.type == TGB_BSDF_ROUGH_COAT) return rcoat_eval(sc, b, s, e);
     if (b.type != TGB_BSDF_SMOOTH_COAT) return bsdf_eval_base(sc, b, s, e)*sqr(bsdf_eta(b, e));
     const DBsdf &sub = sc.bsdfs[b.substrate];
     if (e.wi.z <= 0.0f || e.wo.z <= 0.0f) return v3s(0.0f);
@@ -930,6 +1053,7 @@ TGB_D float bsdf_pdf(const DScene &sc, const DBsdf &b, const Surface &s, const E
         return cosine_hemisphere_pdf(e.wo);
     }
     if (HAIR && b.type == TGB_BSDF_HAIR) return hair_pdf(b, e);
+    if (b.type == TGB_BSDF_ROUGH_COAT) return rcoat_pdf(sc, b, s, e);
     if (b.type != TGB_BSDF_SMOOTH_COAT) return bsdf_pdf_base(sc, b, s, e);
     const DBsdf &sub = sc.bsdfs[b.substrate];
     if (e.wi.z <= 0.0f || e.wo.z <= 0.0f) return 0.0f;

@@ -483,8 +483,11 @@ class FlatScene:
             if ty == "rough_plastic":
                 o.distribution = _DIST[b.get("distribution", "ggx")]
                 o.roughness_tex = self.add_texture(b.get("roughness", 0.02), base_dir)
-        elif ty == "smooth_coat":
-            o.type = abi.BSDF_SMOOTH_COAT
+        elif ty in ("smooth_coat", "rough_coat"):
+            o.type = abi.BSDF_SMOOTH_COAT if ty == "smooth_coat" else abi.BSDF_ROUGH_COAT
+            if ty == "rough_coat":                     # RoughCoatBsdf ctor (RoughCoatBsdf.cpp:15-23): ggx, roughness 0.02
+                o.distribution = _DIST[b.get("distribution", "ggx")]
+                o.roughness_tex = self.add_texture(b.get("roughness", 0.02), base_dir)
             o.ior = float(f32(b.get("ior", 1.3)))
             o.thickness = float(f32(b.get("thickness", 1.0)))
             o.sigma_a[:] = [float(x) for x in (_vec3_field(b, "sigma_a") if "sigma_a" in b else v3(0.0))]
@@ -495,7 +498,7 @@ class FlatScene:
                 o.substrate = named[sub]
             else:
                 o.substrate = self.add_bsdf(sub, base_dir, named)
-            if self.bsdfs[o.substrate].type == abi.BSDF_SMOOTH_COAT:
+            if self.bsdfs[o.substrate].type in (abi.BSDF_SMOOTH_COAT, abi.BSDF_ROUGH_COAT):
                 raise SceneError("nested coats are outside the hot path")
         elif ty == "hair":
             # HairBcsdf ctor defaults + fromJson + the sigma_a part of prepareForRender (bsdfs/HairBcsdf.cpp:13-21,163-171,435-443)

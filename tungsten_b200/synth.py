@@ -226,6 +226,32 @@ def material_room(out_dir, name="materials", res=(128, 128), spp=16, max_bounces
     return write_scene(out_dir, name, sc, meshes)
 
 
+def coat_room(out_dir, name="coats", res=(128, 128), spp=16, max_bounces=16, subdiv=3):
+    """RoughCoatBsdf three ways -- Beckmann coat with absorption over Lambert, GGX coat over a rough conductor, GGX coat over
+    plastic -- on two blobs and a cube, plus a SmoothCoatBsdf blob for comparison.  The substrates are NAMED bsdfs of the scene:
+    the reference prepares (prepareForRender) only the bsdfs in its scene list, an inline substrate object never is."""
+    v, t = icosphere(subdiv, 1.0, displace=0.08)
+    meshes = {name + "_blob.wo3": (v, t)}
+    bsdfs = [
+        {"name": "subLambert", "type": "lambert", "albedo": [0.6, 0.3, 0.2]},
+        {"name": "subMetal", "type": "rough_conductor", "material": "Au", "distribution": "beckmann", "roughness": 0.3},
+        {"name": "subPlastic", "type": "plastic", "albedo": [0.2, 0.5, 0.7], "ior": 1.5},
+        {"name": "coatA", "type": "rough_coat", "distribution": "beckmann", "roughness": 0.25, "ior": 1.5, "thickness": 2.0,
+         "sigma_a": [0.2, 0.1, 0.4], "substrate": "subLambert"},
+        {"name": "coatB", "type": "rough_coat", "distribution": "ggx", "roughness": 0.1, "ior": 1.4, "substrate": "subMetal"},
+        {"name": "coatC", "type": "rough_coat", "roughness": 0.15, "ior": 1.6, "substrate": "subPlastic"},
+        {"name": "coatS", "type": "smooth_coat", "ior": 1.5, "thickness": 1.0, "sigma_a": [0.3, 0.3, 0.1], "substrate": "subMetal"},
+    ]
+    def blob(nm, bsdf, pos, s=0.3):
+        return {"name": nm, "type": "mesh", "file": name + "_blob.wo3", "smooth": True, "bsdf": bsdf,
+                "transform": {"position": list(pos), "scale": [s, s, s]}}
+    prims = [blob("b0", "coatA", (-0.5, 0.32, 0.25)), blob("b1", "coatB", (0.5, 0.32, 0.25)), blob("b2", "coatS", (0.0, 1.05, -0.2), 0.28),
+             {"name": "c0", "type": "cube", "bsdf": "coatC",
+              "transform": {"position": [0.0, 0.25, -0.45], "scale": [0.5, 0.5, 0.5], "rotation": [0, 25, 0]}}]
+    sc = cornell_box(res, spp, max_bounces, extra_bsdfs=bsdfs, extra_prims=prims, boxes=False)
+    return write_scene(out_dir, name, sc, meshes)
+
+
 def many_lights(out_dir, name="many_lights", n_quads=36, res=(128, 128), spp=16, max_bounces=16, subdiv=3):
     """Cornell room + blob lit by the ceiling light, a 6 x 6 grid of small coloured quad lights under the ceiling and two mesh
     lights (whose approximate radiance is "unknown" in TraceBase::chooseLight): 39 samplable lights.  The reference keeps
