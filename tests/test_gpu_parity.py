@@ -45,42 +45,42 @@ def _compare(fs, spp, frac_ok=0.99, rel_rmse=1e-2, same_ray_count=True):
 
 def test_cornell_box(scratch):
     fs = scene.load_scene(synth.cornell_box(res=(96, 96), spp=8))
-    _compare(fs, 8)
+    _compare(fs, 8, frac_ok=0.9999, rel_rmse=1e-5)                 # measured: 1.00000, 1.2e-7
 
 
 def test_cornell_mesh(scratch):
     fs = scene.load_scene(synth.cornell_mesh(scratch, res=(96, 96), spp=8, subdiv=3))
-    _compare(fs, 8)
+    _compare(fs, 8, frac_ok=0.9999, rel_rmse=1e-5)                 # measured: 1.00000, 3.4e-7
 
 
 def test_material_room(scratch):
     fs = scene.load_scene(synth.material_room(scratch, res=(96, 96), spp=8, subdiv=3))
-    _compare(fs, 8, same_ray_count=False)
+    _compare(fs, 8, frac_ok=0.997, rel_rmse=1e-2, same_ray_count=False)      # measured: 0.99913, 2.2e-3 (one diverged rough-dielectric path)
 
 
 def test_material_room_env(scratch):
     fs = scene.load_scene(synth.material_room(scratch, name="matenv", res=(64, 64), spp=8, subdiv=2, env=[0.4, 0.5, 0.7]))
-    _compare(fs, 8, same_ray_count=False)
+    _compare(fs, 8, frac_ok=0.998, rel_rmse=1e-4, same_ray_count=False)      # measured: 0.99976, 7.4e-7
 
 
 def test_dirac_lobes(scratch):
     """f4: MirrorBsdf, ConductorBsdf, DielectricBsdf (refraction on and off) on cubes and smooth meshes: pure-specular surfaces
     skip NEE, their bounces carry wasSpecular, refraction scales radiance by eta^2."""
     fs = scene.load_scene(synth.dirac_room(scratch, res=(96, 96), spp=8, subdiv=3))
-    _compare(fs, 8, same_ray_count=False)
+    _compare(fs, 8, frac_ok=0.9999, rel_rmse=1e-5, same_ray_count=False)     # measured: 1.00000, 7.1e-7
 
 
 def test_rough_coat(scratch):
     """f4: RoughCoatBsdf (rough dielectric interface over Lambert / rough conductor / plastic substrates) next to a SmoothCoatBsdf:
     lobe choice through the supplemental PCG, one-sample MIS weights between coat and substrate."""
     fs = scene.load_scene(synth.coat_room(scratch, res=(96, 96), spp=8, subdiv=3))
-    _compare(fs, 8, same_ray_count=False)
+    _compare(fs, 8, frac_ok=0.9999, rel_rmse=1e-5, same_ray_count=False)     # measured: 1.00000, 2.4e-7
 
 
 def test_coat_checker_envmap(scratch):
     """C0 stand-in: smooth_coat over rough_conductor, checker floor, importance-sampled HDR environment."""
     fs = scene.load_scene(synth.materialtest_standin(scratch, res=(96, 96), spp=8, subdiv=3))
-    _compare(fs, 8, same_ray_count=False)
+    _compare(fs, 8, frac_ok=0.9999, rel_rmse=1e-5, same_ray_count=False)     # measured: 1.00000, 1.2e-7
 
 
 def test_golden_scenes_against_reference_fixtures():
@@ -109,7 +109,7 @@ def test_instanced_forest(scratch):
     """C3 stand-in: rigid instances (quaternion + translation, Instance.cpp:290-334) flattened into world space."""
     fs = scene.load_scene(synth.instanced_forest(scratch, res=(96, 96), spp=8, n_instances=30))
     assert fs.n_triangles == 30*(320 + 80)
-    _compare(fs, 8, frac_ok=0.985, same_ray_count=False)
+    _compare(fs, 8, frac_ok=0.9999, rel_rmse=1e-5, same_ray_count=False)     # measured: 1.00000, 1.5e-7
 
 
 @pytest.mark.parametrize("kw", [
@@ -124,9 +124,10 @@ def test_instanced_forest(scratch):
 def test_curves_and_hair(scratch, kw):
     """C4 stand-ins: quadratic B-spline curve segments (Curves.cpp) in the three cylinder modes, hair BCSDF (HairBcsdf.cpp).
     A few grazing rays resolve differently than in the oracle (different segment BVH + the bisection's pruning bound, see
-    tests/test_oracle_golden.py); each moves a pixel by ~L/spp: >= 97% of pixels within tolerance, RMSE <= 3% of the mean."""
+    tests/test_oracle_golden.py); each moves a pixel by ~L/spp: >= 99% of pixels within tolerance, RMSE <= 3% of the mean
+    (measured: 0.9924-0.9987 and 2e-3..1.6e-2 over the five cases)."""
     fs = scene.load_scene(synth.hair_scene(scratch, res=(96, 96), spp=8, **kw))
-    _compare(fs, 8, frac_ok=0.97, rel_rmse=3e-2, same_ray_count=False)
+    _compare(fs, 8, frac_ok=0.99, rel_rmse=3e-2, same_ray_count=False)
 
 
 def test_curve_hits_match_oracle(scratch):
@@ -194,7 +195,16 @@ def test_many_analytic_primitives_live_in_the_bvh(scratch, monkeypatch):
     image and hit ids; (b) the BVH path forced on scenes that normally use the loop gives the loop's image (occlusion queries
     skip the light they are aimed at in both)."""
     fs = scene.load_scene(synth.cube_city(res=(96, 96), spp=8, n=12))
-    _compare(fs, 8, same_ray_count=False)
+    # measured: 0.99891 within tolerance, rmse/mean 1.3e-5 (144 cubes = thousands of silhouette edges: a direction that differs in
+    # the last ulp of CUDA's sinf/cosf flips hit/miss along them); the loop-vs-BVH comparison below is bit-identical
+    _compare(fs, 8, frac_ok=0.997, rel_rmse=1e-3, same_ray_count=False)
+    monkeypatch.setenv("TGB_ANALYTIC_BVH_MIN", "100000")
+    ctx = lib.Context(fs); loop_img, _ = ctx.render_tiles(8); assert ctx.scene_info()["n_nodes"] == 0; ctx.close()
+    monkeypatch.delenv("TGB_ANALYTIC_BVH_MIN", raising=False)
+    ctx = lib.Context(fs); bvh_img, _ = ctx.render_tiles(8); ctx.close()
+    eq = float((np.abs(loop_img - bvh_img).max(axis=2) == 0).mean())
+    print("cube_city, per-ray loop vs BVH leaves: %.5f of pixels identical" % eq)      # measured: 1.00000
+    assert eq >= 0.9995
     rng = np.random.RandomState(3)
     n = 100000
     o = np.tile(np.float32([7.5, 5.0, 9.0]), (n, 1)) + rng.randn(n, 3).astype(np.float32)*0.5
@@ -297,7 +307,7 @@ def test_many_lights(scratch):
     path for more than 16 lights."""
     fs = scene.load_scene(synth.many_lights(scratch, res=(96, 96), spp=8, subdiv=3))
     assert sum(1 for p in fs.primitives if p.emission_tex >= 0) == 39
-    _compare(fs, 8, same_ray_count=False)
+    _compare(fs, 8, frac_ok=0.99, rel_rmse=1e-2, same_ray_count=False)       # measured: 0.99338, 1.9e-3 (39 lights incl. two mesh lights: many discrete choices per path)
 
 
 def test_abort_returns_aborted_code():
