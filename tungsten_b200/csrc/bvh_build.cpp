@@ -293,7 +293,7 @@ void quantize_bvh4(const Bvh4 &in, uint32_t max_treelet, QBvh4 &out, int32_t emp
 }
 
 void qnode_slab_host(const QNode4 &nd, const float o[3], const float inv_d[3], float tnear, float tfar, float t_out[4]) {
-    // mirrors Traversal::visit in tgb_kernels.cuh operation for operation (fmaf = one rounding, as FFMA)
+    // mirrors Traversal::visit_loaded in tgb_wavefront.cuh operation for operation (fmaf = one rounding, as FFMA)
     const float org[3] = {nd.ox, nd.oy, nd.oz}, S[3] = {nd.sx, nd.sy, nd.sz};
     const uint32_t lo[3] = {nd.lox, nd.loy, nd.loz}, hi[3] = {nd.hix, nd.hiy, nd.hiz};
     float a[3], b[3]; uint32_t nearw[3], farw[3];

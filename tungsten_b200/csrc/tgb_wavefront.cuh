@@ -1,11 +1,13 @@
 // Wavefront kernels of the B200 path tracer (sm_100a).  One iteration of the loop =
 //   k_regen        : SobolPathSampler::startPath + ReconstructionFilter::sample + PinholeCamera::sampleDirection for the camera
 //                    paths that replace finished ones (appended behind the compacted survivors)
-//   k_trace        : TraceableScene::intersect (closest hit): persistent CTAs stage the top of the quantised BVH in shared
-//                    memory with one bulk-async copy (TMA engine, mbarrier), pull rays from the coherence-sorted queue and walk
-//                    the 4-ary BVH over all mesh triangles (+ curve segments); analytic primitives were tested by the kernel
-//                    that created the ray
-//   k_shade        : makeLocalScatterEvent + handleSurface (NEE/MIS query generation, emission, BSDF sample, Russian roulette)
+//   k_trace        : TraceableScene::intersect (closest hit): persistent CTAs pull rays from the coherence-sorted queue and walk
+//                    the 4-ary BVH of 64-byte quantised nodes over all mesh triangles (+ curve segments, + the analytic
+//                    primitives when they are many) as a warp state machine (machine_traverse_persistent); optionally the
+//                    top of the tree is staged in shared memory by one bulk-async copy (TMA engine, mbarrier; off by default).
+//                    Few analytic primitives are tested by the kernel that creates the ray instead
+//   k_shade        : makeLocalScatterEvent + handleSurface (NEE/MIS query generation, emission, BSDF sample, Russian roulette);
+//                    instantiations: material-sorted window, all-Lambert lobe set, curves
 //   k_shadow_prep  : analytic part of the NEE/MIS queries, top-level BVH cut, compaction of what is left
 //   k_shadow_bvh   : attenuatedEmission / generalizedShadowRay for those (same traversal + epilogue)
 //   k_accum        : folds the bounce's direct-light estimate into the path, NaN guards, compacts survivors into the other
@@ -14,9 +16,9 @@
 //                    a device-resident control block, the host only reads them one iteration late (no sync in the loop)
 //   k_bin_scatter  : counting sort of the survivors' slot indices by ray-coherence key
 //   k_resolve      : OutputBuffer::addSample running mean, samples folded in sample-index order
-// Path state is stored as 16-byte records (one LDG/STG.128 per record): a 64-byte traversal record per slot + 24 bytes of
-// emission / RNG state, double buffered (k_accum compacts from one buffer into the other); per-bounce scratch records for the
-// direct-light estimate.
+// Path state is stored as 16-byte records, one array per record kind (one LDG/STG.128 per record, 512 contiguous bytes per warp
+// instruction): four traversal/shading records + emission + RNG state per slot, double buffered (k_accum compacts from one
+// buffer into the other); per-bounce scratch records for the direct-light estimate.
 #pragma once
 #include "tgb_device.cuh"
 
