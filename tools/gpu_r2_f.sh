@@ -1,3 +1,4 @@
+# r02-f: f3 adaptive sampling + resume through the drop-in, full parity suites, C1 bench with the streaming-kernel rooflines
 mkdir -p gpurun_out
 timeout 600 python -m pytest tests/test_gpu_dropin.py -m gpu -q -k "resume or adaptive" 2>&1 | tail -60
 timeout 1200 python -m pytest tests -m gpu -q --deselect tests/test_gpu_dropin.py::test_dropin_resume_render_continues_bit_exactly 2>&1 | tail -8

@@ -1,3 +1,4 @@
+# r02-i (1 GPU): C4 curve parity + bench, ncu evidence: C4 k_trace (full set + source), C1 k_trace with the launch query count -> traffic JSON, C1 streaming kernels
 mkdir -p gpurun_out
 timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_gpu_bench_scenes.py -m gpu -q -k "hair or curve or c4" 2>&1 | tail -4
 python bench.py --config c4 --steps 3 --warmup 2 --spp-per-step 8 --no-cpu-baseline --no-other-configs 2>/dev/null | python -c "
